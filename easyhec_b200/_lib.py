@@ -1,0 +1,253 @@
+"""ctypes binding of libehb.so (the C ABI in include/easyhec_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every compute call goes through
+the C ABI with raw pointers.  There is no CPU or eager fallback -- if the library is missing or there is
+no CUDA device the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+__all__ = ["EhbError", "lib", "Context", "library_path"]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libehb.so")
+_lib = None
+
+EHB_FLAG_PAIR_OVERFLOW = 1
+EHB_FLAG_NEEDS_CLIP = 2
+
+
+class EhbError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return _SO
+
+
+_PROTOS = {
+    "ehb_version": (C.c_int, []),
+    "ehb_last_error": (C.c_char_p, []),
+    "ehb_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "ehb_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "ehb_ctx_reserve": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ehb_ctx_set_fill_rule": (C.c_int, [C.c_void_p, C.c_int]),
+    "ehb_ctx_grow_pairs": (C.c_int, [C.c_void_p]),
+    "ehb_ctx_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint), C.POINTER(C.c_longlong)]),
+    "ehb_mesh_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "ehb_mesh_update_verts": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "ehb_mesh_release": (C.c_int, [C.c_void_p, C.c_int]),
+    "ehb_mesh_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ehb_render_mask_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_void_p]),
+    "ehb_render_mask_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
+    "ehb_render_views_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ehb_render_views_fused_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                            C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ehb_render_binary_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_void_p]),
+    "ehb_variance_score": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "ehb_explore_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p]),
+    "ehb_solver_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                       C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ehb_launch_count": (C.c_longlong, [C.c_void_p]),
+}
+
+
+def lib():
+    """Load libehb.so (built by `make -C easyhec_b200/csrc` / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise EhbError("libehb.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "or `make -C easyhec_b200/csrc`); there is no fallback path")
+        l = C.CDLL(_SO)
+        for name, (res, args) in _PROTOS.items():
+            f = getattr(l, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = l
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        msg = lib().ehb_last_error()
+        raise EhbError("libehb error %d: %s" % (rc, msg.decode("utf-8", "replace") if msg else "?"))
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _dev_check(t, dtype, device, name):
+    if t is None:
+        return
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.device != device:
+        raise EhbError("%s must be a CUDA tensor on %s" % (name, device))
+    if t.dtype != dtype:
+        raise EhbError("%s must have dtype %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise EhbError("%s must be contiguous" % name)
+
+
+class Context:
+    """One rasterizer context per device (replaces dr.RasterizeCudaContext, nvdiffrast_renderer.py:23)."""
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise EhbError("no CUDA device: easyhec_b200 has no CPU path")
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = device
+        torch.cuda.init()
+        with torch.cuda.device(device):
+            torch.zeros(1, device=device)  # make sure the primary context exists
+        h = C.c_void_p()
+        _check(lib().ehb_ctx_create(device.index, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ehb_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- meshes ------------------------------------------------------------------------------------------
+    def register_mesh(self, verts, faces) -> int:
+        v = np.ascontiguousarray(verts.detach().cpu().numpy() if isinstance(verts, torch.Tensor) else verts,
+                                 dtype=np.float32).reshape(-1, 3)
+        f = np.ascontiguousarray(faces.detach().cpu().numpy() if isinstance(faces, torch.Tensor) else faces,
+                                 dtype=np.int32).reshape(-1, 3)
+        mid = C.c_int(-1)
+        _check(lib().ehb_mesh_register(self._h, v.ctypes.data_as(C.c_void_p), len(v), f.ctypes.data_as(C.c_void_p),
+                                       len(f), C.byref(mid)))
+        return mid.value
+
+    def update_verts(self, mesh_id: int, verts: torch.Tensor):
+        _dev_check(verts, torch.float32, self.device, "verts")
+        _check(lib().ehb_mesh_update_verts(self._h, mesh_id, _ptr(verts), verts.shape[0], _stream(self.device)))
+
+    def release_mesh(self, mesh_id: int):
+        _check(lib().ehb_mesh_release(self._h, mesh_id))
+
+    def mesh_info(self, mesh_id: int):
+        V, F = C.c_int(), C.c_int()
+        _check(lib().ehb_mesh_info(self._h, mesh_id, C.byref(V), C.byref(F)))
+        return V.value, F.value
+
+    # -- control -----------------------------------------------------------------------------------------
+    def reserve(self, n_items, n_links, max_faces, H, W):
+        _check(lib().ehb_ctx_reserve(self._h, n_items, n_links, max_faces, H, W))
+
+    def set_fill_rule(self, rule: int):
+        _check(lib().ehb_ctx_set_fill_rule(self._h, rule))
+
+    def grow_pairs(self):
+        _check(lib().ehb_ctx_grow_pairs(self._h))
+
+    def status(self):
+        """Synchronises; returns (flags, n_need_clip) and clears them."""
+        fl, nc = C.c_uint(), C.c_longlong()
+        _check(lib().ehb_ctx_status(self._h, C.byref(fl), C.byref(nc)))
+        return fl.value, nc.value
+
+    def launch_count(self) -> int:
+        return int(lib().ehb_launch_count(self._h))
+
+    # -- compute -----------------------------------------------------------------------------------------
+    def render_mask_fwd(self, mesh_id, mvp, H, W, anti_aliasing=True):
+        _dev_check(mvp, torch.float32, self.device, "mvp")
+        out = torch.empty((H, W), dtype=torch.float32 if anti_aliasing else torch.uint8, device=self.device)
+        _check(lib().ehb_render_mask_fwd(self._h, mesh_id, _ptr(mvp), H, W, int(bool(anti_aliasing)), _ptr(out),
+                                         _stream(self.device)))
+        return out
+
+    def render_mask_bwd(self, mesh_id, mvp, H, W, dy, want_gpos=False):
+        _dev_check(mvp, torch.float32, self.device, "mvp")
+        _dev_check(dy, torch.float32, self.device, "dy")
+        g_mvp = torch.empty((4, 4), dtype=torch.float64, device=self.device)
+        g_pos = None
+        if want_gpos:
+            V, _ = self.mesh_info(mesh_id)
+            g_pos = torch.empty((V, 4), dtype=torch.float32, device=self.device)
+        _check(lib().ehb_render_mask_bwd(self._h, mesh_id, _ptr(mvp), H, W, _ptr(dy), _ptr(g_mvp), _ptr(g_pos),
+                                         _stream(self.device)))
+        return g_mvp, g_pos
+
+    def render_views_fused(self, mesh_ids, mvp, ref, H, W, backward=True, want_masks=True, out=None):
+        """mvp (B,L,4,4) f32, ref (B,H,W) f32 or u8 (or None) -> masks (B,H,W) f32 | None, loss (B,) f64,
+        g_mvp (B,L,4,4) f64 | None.  `out` = (masks, loss, g_mvp) pre-allocated tensors to reuse."""
+        _dev_check(mvp, torch.float32, self.device, "mvp")
+        B, L = mvp.shape[0], mvp.shape[1]
+        ids = (C.c_int * L)(*mesh_ids)
+        if out is not None:
+            masks, loss, g_mvp = out
+        else:
+            masks = torch.empty((B, H, W), dtype=torch.float32, device=self.device) if want_masks else None
+            loss = torch.empty((B,), dtype=torch.float64, device=self.device) if ref is not None else None
+            g_mvp = torch.empty((B, L, 4, 4), dtype=torch.float64, device=self.device) if backward else None
+        if ref is not None and ref.dtype == torch.uint8:
+            _dev_check(ref, torch.uint8, self.device, "ref")
+            _check(lib().ehb_render_views_fused_u8(self._h, ids, L, B, _ptr(mvp), _ptr(ref), H, W, int(bool(backward)),
+                                                   _ptr(masks), _ptr(loss), _ptr(g_mvp), _stream(self.device)))
+        else:
+            _dev_check(ref, torch.float32, self.device, "ref")
+            _check(lib().ehb_render_views_fused(self._h, ids, L, B, _ptr(mvp), _ptr(ref), H, W, int(bool(backward)),
+                                                _ptr(masks), _ptr(loss), _ptr(g_mvp), _stream(self.device)))
+        return masks, loss, g_mvp
+
+    def render_binary_batch(self, mesh_ids, mvp, H, W, out=None):
+        """mvp (N,L,4,4) -> u8 (N,H,W): packed robot, one depth buffer per render, no antialiasing."""
+        _dev_check(mvp, torch.float32, self.device, "mvp")
+        N, L = mvp.shape[0], mvp.shape[1]
+        ids = (C.c_int * L)(*mesh_ids)
+        if out is None:
+            out = torch.empty((N, H, W), dtype=torch.uint8, device=self.device)
+        _check(lib().ehb_render_binary_batch(self._h, ids, L, N, _ptr(mvp), H, W, _ptr(out), _stream(self.device)))
+        return out
+
+    def variance_score(self, masks):
+        """masks (Q,C,H,W) u8/bool -> (Q,) f64 = sum_px var_c (unbiased)."""
+        if masks.dtype == torch.bool:
+            masks = masks.view(torch.uint8)
+        _dev_check(masks, torch.uint8, self.device, "masks")
+        Q, Cn = masks.shape[0], masks.shape[1]
+        n = masks[0, 0].numel() if Q else 0
+        score = torch.empty((Q,), dtype=torch.float64, device=self.device)
+        _check(lib().ehb_variance_score(self._h, _ptr(masks), Q, Cn, n, _ptr(score), _stream(self.device)))
+        return score
+
+    def explore_scores(self, mesh_ids, mvp, H, W):
+        """mvp (Q,C,L,4,4) -> (Q,) f64 variance scores (space_explorer.py:152-165), masks never leave the GPU."""
+        _dev_check(mvp, torch.float32, self.device, "mvp")
+        Q, Cn, L = mvp.shape[0], mvp.shape[1], mvp.shape[2]
+        ids = (C.c_int * L)(*mesh_ids)
+        score = torch.empty((Q,), dtype=torch.float64, device=self.device)
+        _check(lib().ehb_explore_scores(self._h, ids, L, Q, Cn, _ptr(mvp), H, W, _ptr(score), _stream(self.device)))
+        return score
+
+    def solver_step_host(self, mesh_ids, mvp_host, ref_dev, H, W, loss_host, g_mvp_host):
+        """Host-buffer form: mvp_host (B,L,4,4) f32 pinned CPU tensor; loss_host (B,), g_mvp_host (B,L,4,4) f64
+        pinned CPU tensors (written, stream synchronised on return)."""
+        B, L = mvp_host.shape[0], mvp_host.shape[1]
+        ids = (C.c_int * L)(*mesh_ids)
+        _dev_check(ref_dev, torch.float32, self.device, "ref")
+        _check(lib().ehb_solver_step_host(self._h, ids, L, B, _ptr(mvp_host), _ptr(ref_dev), H, W, _ptr(loss_host),
+                                          _ptr(g_mvp_host), _stream(self.device)))

@@ -1,0 +1,561 @@
+// ehb_api.cu -- C ABI of libehb.so (see include/easyhec_b200.h for the contract of every entry point).
+//
+// Host side of the B200 silhouette rasterizer: context, mesh registry (padded float4/int4 buffers and the
+// cached edge adjacency that replaces dr.antialias' per-call topology hash, nvdiffrast_renderer.py:43),
+// scratch management and the launch sequence count -> alloc -> fill -> raster.  No torch types, no CPU
+// fallback: every compute entry point enqueues CUDA kernels on the caller's stream or fails.
+#include "../../include/easyhec_b200.h"
+#include "ehb_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess) return fail(EHB_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct Mesh {
+    float4* verts = nullptr;
+    int4* faces = nullptr;
+    int4* opp = nullptr;
+    int V = 0, F = 0;
+    bool live = false;
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    int ensure(size_t want, bool capturing)
+    {
+        if (want <= n) return EHB_OK;
+        if (capturing) return fail(EHB_E_CAPACITY, "scratch too small during stream capture; call ehb_ctx_reserve first");
+        if (p) CU(cudaFree(p));
+        p = nullptr; n = 0;
+        size_t cap = want + want / 4 + 256;
+        CU(cudaMalloc((void**)&p, cap * sizeof(T)));
+        n = cap;
+        return EHB_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct Ctx {
+    int device = 0;
+    int nSM = 148;
+    int rule = 0;
+    std::vector<Mesh> meshes;
+    DevBuf<uint32_t> range, cnt, start, cur, tileList, pairs;
+    EhbCounters* ctr = nullptr;
+    EhbCounters* ctrHost = nullptr;   // pinned
+    // staging for the host-buffer entry points
+    DevBuf<float> mvpDev;
+    DevBuf<double> outDev;            // loss[B] + gmvp[B*L*16]
+    DevBuf<uint8_t> refDev, maskDev;
+    DevBuf<unsigned long long> numDev;
+    float* mvpPinned = nullptr; size_t mvpPinnedN = 0;
+    double* outPinned = nullptr; size_t outPinnedN = 0;
+    long long launches = 0;
+    size_t pairFactor = 3;            // pair capacity = items * Ftot * pairFactor (+ slack); grown on overflow
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+bool is_capturing(cudaStream_t s)
+{
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &st) != cudaSuccess) { cudaGetLastError(); return false; }
+    return st != cudaStreamCaptureStatusNone;
+}
+
+// Edge adjacency: for triangle t and corner k, the vertex opposite to edge k (joining corners k+1, k+2) in the
+// other triangle on that edge, or -1.  An edge keeps the first two opposite vertices in triangle order.
+void build_adjacency(const int* tri, int F, int V, std::vector<int4>& opp)
+{
+    struct Rec { unsigned long long key; int order; int other; };
+    std::vector<Rec> rec;
+    rec.reserve((size_t)F * 3);
+    for (int t = 0; t < F; t++) {
+        const int v[3] = {tri[3 * t], tri[3 * t + 1], tri[3 * t + 2]};
+        bool bad = false;
+        for (int k = 0; k < 3; k++) bad |= (v[k] < 0 || v[k] >= V);
+        if (bad || v[0] == v[1] || v[1] == v[2] || v[2] == v[0]) continue;
+        for (int k = 0; k < 3; k++) {
+            const int a = v[(k + 1) % 3], b = v[(k + 2) % 3];
+            const unsigned long long lo = (unsigned)std::min(a, b), hi = (unsigned)std::max(a, b);
+            rec.push_back({(lo << 32) | hi, 3 * t + k, v[k]});
+        }
+    }
+    std::sort(rec.begin(), rec.end(), [](const Rec& x, const Rec& y) {
+        return x.key != y.key ? x.key < y.key : x.order < y.order;
+    });
+    std::vector<int> flat((size_t)F * 3, -1);
+    for (size_t i = 0; i < rec.size();) {
+        size_t j = i;
+        while (j < rec.size() && rec[j].key == rec[i].key) j++;
+        const int n0 = rec[i].other, n1 = (j - i >= 2) ? rec[i + 1].other : -1;
+        for (size_t k = i; k < j; k++) flat[rec[k].order] = (n0 == rec[k].other) ? n1 : n0;
+        i = j;
+    }
+    opp.resize(F);
+    for (int t = 0; t < F; t++) opp[t] = make_int4(flat[3 * t], flat[3 * t + 1], flat[3 * t + 2], 0);
+}
+
+__global__ void ehb_k_pad_verts(const float* __restrict__ src, float4* __restrict__ dst, int V)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < V) dst[i] = make_float4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 1.f);
+}
+
+// num[q] += sum over this block's pixels of k (C - k), k = number of cameras whose mask covers the pixel.
+// sum_px unbiased_var_c(mask) = num / (C (C - 1)) exactly, so the reduction is integer and order-free.
+__global__ void __launch_bounds__(256) ehb_k_variance(const uint8_t* __restrict__ masks, int C, long long n,
+                                                      unsigned long long* __restrict__ num)
+{
+    const int q = blockIdx.y;
+    const uint8_t* base = masks + (size_t)q * C * n;
+    unsigned long long acc = 0;
+    const bool vec = (n & 15) == 0 && (((uintptr_t)masks) & 15) == 0;
+    if (vec) {
+        const long long n16 = n >> 4;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+            unsigned k[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) k[j] = 0;
+            for (int c = 0; c < C; c++) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)c * n) + i);
+                const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 16; j++) k[j] += ((w[j >> 2] >> (8 * (j & 3))) & 255u) != 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j++) acc += (unsigned long long)(k[j] * ((unsigned)C - k[j]));
+        }
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+            unsigned k = 0;
+            for (int c = 0; c < C; c++) k += __ldg(base + (size_t)c * n + i) != 0;
+            acc += (unsigned long long)(k * ((unsigned)C - k));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(num + q, acc);
+}
+
+__global__ void ehb_k_variance_finish(const unsigned long long* __restrict__ num, int Q, int C, double* __restrict__ score)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < Q) score[q] = C > 1 ? (double)num[q] / ((double)C * (double)(C - 1)) : 0.0;
+}
+
+constexpr int PMAX_FUSED = 6;
+
+size_t raster_smem(int pmax) { return (size_t)pmax * EHB_NP * 8 + ((EHB_NP + 3) & ~3) * 4 + sizeof(EhbRasterSmem); }
+
+struct Io {
+    const float* ref = nullptr; const uint8_t* ref_u8 = nullptr;
+    float* masks = nullptr; double* loss = nullptr; double* gmvp = nullptr; float* gpos = nullptr;
+    const float* dy = nullptr; uint8_t* out_u8 = nullptr; float* score = nullptr; int C = 0;
+    int do_bwd = 0, clamp = 0; float invB = 1.f;
+};
+
+int build_robot(Ctx* c, const int* mesh_ids, int L, EhbRobot& rb)
+{
+    if (L < 1 || L > EHB_MAX_LINKS) return fail(EHB_E_ARG, "number of links %d outside [1, %d]", L, EHB_MAX_LINKS);
+    memset(&rb, 0, sizeof rb);
+    rb.L = L;
+    for (int l = 0; l < L; l++) {
+        const int id = mesh_ids[l];
+        if (id < 0 || id >= (int)c->meshes.size() || !c->meshes[id].live) return fail(EHB_E_ARG, "unknown mesh id %d", id);
+        const Mesh& m = c->meshes[id];
+        if (m.F > (int)EHB_FACE_MASK) return fail(EHB_E_ARG, "mesh %d has too many faces", id);
+        rb.link[l].verts = m.verts; rb.link[l].faces = m.faces; rb.link[l].opp = m.opp;
+        rb.link[l].V = m.V; rb.link[l].F = m.F;
+        rb.foff[l + 1] = rb.foff[l] + m.F;
+    }
+    return EHB_OK;
+}
+
+int ensure_scratch(Ctx* c, int items, int Ftot, int ntiles, int Lk, bool capturing)
+{
+    int r;
+    if ((r = c->range.ensure((size_t)items * std::max(Ftot, 1), capturing))) return r;
+    const size_t bins = (size_t)items * ntiles * Lk;
+    if ((r = c->cnt.ensure(bins, capturing))) return r;
+    if ((r = c->start.ensure(bins, capturing))) return r;
+    if ((r = c->cur.ensure(bins, capturing))) return r;
+    if ((r = c->tileList.ensure((size_t)items * ntiles, capturing))) return r;
+    if ((r = c->pairs.ensure((size_t)items * Ftot * c->pairFactor + 4096, capturing))) return r;
+    return EHB_OK;
+}
+
+int run_pass(Ctx* c, const int* mesh_ids, int L, int items, const float* mvp_dev, int H, int W, int mode, const Io& io,
+             cudaStream_t st)
+{
+    if (!c) return fail(EHB_E_ARG, "null context");
+    if (H < 1 || W < 1 || H > 8160 || W > 8160) return fail(EHB_E_ARG, "resolution %dx%d outside [1, 8160]", H, W);
+    if (items < 0) return fail(EHB_E_ARG, "negative item count");
+    if (items == 0) return EHB_OK;
+    if (items > 65535) return fail(EHB_E_ARG, "more than 65535 items per launch");
+    if (!mvp_dev) return fail(EHB_E_ARG, "null mvp pointer");
+    DeviceGuard guard(c->device);
+    EhbRobot rb;
+    int r = build_robot(c, mesh_ids, L, rb);
+    if (r) return r;
+    const bool unionMode = mode == EHB_MODE_UNION || mode == EHB_MODE_UNION_VAR;
+    EhbParams p;
+    memset(&p, 0, sizeof p);
+    p.H = H; p.W = W;
+    p.ntx = (W + EHB_T - 1) / EHB_T; p.nty = (H + EHB_T - 1) / EHB_T; p.ntiles = p.ntx * p.nty;
+    p.items = items; p.L = L; p.Lk = unionMode ? 1 : L; p.Ftot = rb.foff[L];
+    switch (mode) {
+    case EHB_MODE_FUSED: p.hlo = 1; p.hhi = io.do_bwd ? 2 : 1; break;
+    case EHB_MODE_AA_FWD: p.hlo = 1; p.hhi = 1; break;
+    case EHB_MODE_AA_BWD: p.hlo = 0; p.hhi = 1; break;
+    default: p.hlo = 0; p.hhi = 0; break;
+    }
+    p.mode = mode; p.rule = c->rule; p.do_bwd = io.do_bwd; p.clamp = io.clamp; p.invB = io.invB;
+    const bool capturing = is_capturing(st);
+    if ((r = ensure_scratch(c, items, p.Ftot, p.ntiles, p.Lk, capturing))) return r;
+    p.mvp = mvp_dev;
+    p.range = c->range.p; p.cnt = c->cnt.p; p.start = c->start.p; p.cur = c->cur.p; p.tileList = c->tileList.p;
+    p.pairs = c->pairs.p; p.pairCap = c->pairs.n; p.ctr = c->ctr;
+    p.ref = io.ref; p.ref_u8 = io.ref_u8; p.masks = io.masks; p.loss = io.loss; p.gmvp = io.gmvp; p.gpos = io.gpos;
+    p.dy = io.dy; p.out_u8 = io.out_u8; p.score = io.score; p.C = io.C;
+
+    const size_t bins = (size_t)items * p.ntiles * p.Lk;
+    CU(cudaMemsetAsync(p.cnt, 0, bins * sizeof(uint32_t), st));
+    const dim3 gt((unsigned)std::max(1, (p.Ftot + 255) / 256), (unsigned)items);
+    ehb_k_count<<<gt, 256, 0, st>>>(rb, p);
+    const long long warps = (long long)items * p.ntiles;
+    ehb_k_alloc<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(p);
+    ehb_k_fill<<<gt, 256, 0, st>>>(rb, p);
+    if (unionMode || L == 1) {
+        const size_t sm = raster_smem(1);
+        ehb_k_raster<1><<<c->nSM * 6, EHB_THREADS, sm, st>>>(rb, p);
+    } else {
+        const size_t sm = raster_smem(PMAX_FUSED);
+        ehb_k_raster<PMAX_FUSED><<<c->nSM * 3, EHB_THREADS, sm, st>>>(rb, p);
+    }
+    c->launches += 4;
+    CU(cudaGetLastError());
+    return EHB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ehb_version(void) { return 100; }
+const char* ehb_last_error(void) { return g_err.c_str(); }
+
+int ehb_ctx_create(int device, ehb_ctx_t* out)
+{
+    if (!out) return fail(EHB_E_ARG, "null output pointer");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(EHB_E_CUDA, "no CUDA device available (this library has no CPU path)");
+    }
+    if (device < 0 || device >= n) return fail(EHB_E_ARG, "device %d out of range (%d devices)", device, n);
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(EHB_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    Ctx* c = new Ctx();
+    c->device = device;
+    c->nSM = prop.multiProcessorCount;
+    CU(cudaMalloc((void**)&c->ctr, sizeof(EhbCounters)));
+    CU(cudaMemset(c->ctr, 0, sizeof(EhbCounters)));
+    CU(cudaMallocHost((void**)&c->ctrHost, sizeof(EhbCounters)));
+    CU(cudaFuncSetAttribute(ehb_k_raster<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem(1)));
+    CU(cudaFuncSetAttribute(ehb_k_raster<PMAX_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem(PMAX_FUSED)));
+    *out = c;
+    return EHB_OK;
+}
+
+int ehb_ctx_destroy(ehb_ctx_t h)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c) return EHB_OK;
+    DeviceGuard guard(c->device);
+    cudaDeviceSynchronize();
+    for (auto& m : c->meshes) if (m.live) { cudaFree(m.verts); cudaFree(m.faces); cudaFree(m.opp); }
+    c->range.release(); c->cnt.release(); c->start.release(); c->cur.release(); c->tileList.release(); c->pairs.release();
+    c->mvpDev.release(); c->outDev.release(); c->refDev.release(); c->maskDev.release(); c->numDev.release();
+    if (c->mvpPinned) cudaFreeHost(c->mvpPinned);
+    if (c->outPinned) cudaFreeHost(c->outPinned);
+    cudaFree(c->ctr);
+    cudaFreeHost(c->ctrHost);
+    delete c;
+    return EHB_OK;
+}
+
+int ehb_ctx_set_fill_rule(ehb_ctx_t h, int rule)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || (rule != 0 && rule != 1)) return fail(EHB_E_ARG, "bad context or rule");
+    c->rule = rule;
+    return EHB_OK;
+}
+
+int ehb_ctx_reserve(ehb_ctx_t h, int n_items, int n_links, int max_faces, int H, int W)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || n_items < 1 || n_links < 1 || max_faces < 0 || H < 1 || W < 1) return fail(EHB_E_ARG, "bad reserve arguments");
+    DeviceGuard guard(c->device);
+    const int ntiles = ((W + EHB_T - 1) / EHB_T) * ((H + EHB_T - 1) / EHB_T);
+    int r = ensure_scratch(c, n_items, max_faces, ntiles, n_links, false);
+    if (r) return r;
+    if ((r = c->mvpDev.ensure((size_t)n_items * n_links * 16, false))) return r;
+    if ((r = c->outDev.ensure((size_t)n_items * (1 + n_links * 16), false))) return r;
+    return EHB_OK;
+}
+
+int ehb_ctx_grow_pairs(ehb_ctx_t h)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c) return fail(EHB_E_ARG, "null context");
+    c->pairFactor *= 2;
+    return EHB_OK;
+}
+
+int ehb_ctx_status(ehb_ctx_t h, unsigned* flags, long long* n_need_clip)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c) return fail(EHB_E_ARG, "null context");
+    DeviceGuard guard(c->device);
+    CU(cudaDeviceSynchronize());
+    EhbCounters hc;
+    CU(cudaMemcpy(&hc, c->ctr, sizeof hc, cudaMemcpyDeviceToHost));
+    if (flags) *flags = hc.flags;
+    if (n_need_clip) *n_need_clip = (long long)hc.nNeedClip;
+    hc.flags = 0; hc.nNeedClip = 0;
+    CU(cudaMemcpy(c->ctr, &hc, sizeof hc, cudaMemcpyHostToDevice));
+    return EHB_OK;
+}
+
+int ehb_mesh_register(ehb_ctx_t h, const float* verts, int V, const int* faces, int F, int* mesh_id)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || !mesh_id || V < 0 || F < 0 || (V > 0 && !verts) || (F > 0 && !faces)) return fail(EHB_E_ARG, "bad mesh arguments");
+    DeviceGuard guard(c->device);
+    std::vector<float4> v4((size_t)std::max(V, 1));
+    for (int i = 0; i < V; i++) v4[i] = make_float4(verts[3 * i], verts[3 * i + 1], verts[3 * i + 2], 1.f);
+    std::vector<int4> f4((size_t)std::max(F, 1));
+    for (int i = 0; i < F; i++) f4[i] = make_int4(faces[3 * i], faces[3 * i + 1], faces[3 * i + 2], 0);
+    std::vector<int4> opp;
+    build_adjacency(faces, F, V, opp);
+    opp.resize((size_t)std::max(F, 1));
+    Mesh m;
+    m.V = V; m.F = F;
+    CU(cudaMalloc((void**)&m.verts, v4.size() * sizeof(float4)));
+    CU(cudaMalloc((void**)&m.faces, f4.size() * sizeof(int4)));
+    CU(cudaMalloc((void**)&m.opp, opp.size() * sizeof(int4)));
+    CU(cudaMemcpy(m.verts, v4.data(), v4.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(m.faces, f4.data(), f4.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(m.opp, opp.data(), opp.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    m.live = true;
+    int id = -1;
+    for (size_t i = 0; i < c->meshes.size(); i++) if (!c->meshes[i].live) { id = (int)i; break; }
+    if (id < 0) { id = (int)c->meshes.size(); c->meshes.push_back(m); } else c->meshes[id] = m;
+    *mesh_id = id;
+    return EHB_OK;
+}
+
+int ehb_mesh_update_verts(ehb_ctx_t h, int mesh_id, const float* verts_dev, int V, void* stream)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || mesh_id < 0 || mesh_id >= (int)c->meshes.size() || !c->meshes[mesh_id].live) return fail(EHB_E_ARG, "unknown mesh id %d", mesh_id);
+    Mesh& m = c->meshes[mesh_id];
+    if (V != m.V || (V > 0 && !verts_dev)) return fail(EHB_E_ARG, "vertex count %d does not match the registered mesh (%d)", V, m.V);
+    if (V == 0) return EHB_OK;
+    DeviceGuard guard(c->device);
+    ehb_k_pad_verts<<<(V + 255) / 256, 256, 0, (cudaStream_t)stream>>>(verts_dev, m.verts, V);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    return EHB_OK;
+}
+
+int ehb_mesh_release(ehb_ctx_t h, int mesh_id)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || mesh_id < 0 || mesh_id >= (int)c->meshes.size() || !c->meshes[mesh_id].live) return fail(EHB_E_ARG, "unknown mesh id %d", mesh_id);
+    DeviceGuard guard(c->device);
+    CU(cudaDeviceSynchronize());
+    Mesh& m = c->meshes[mesh_id];
+    cudaFree(m.verts); cudaFree(m.faces); cudaFree(m.opp);
+    m = Mesh();
+    return EHB_OK;
+}
+
+int ehb_mesh_info(ehb_ctx_t h, int mesh_id, int* V, int* F)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || mesh_id < 0 || mesh_id >= (int)c->meshes.size() || !c->meshes[mesh_id].live) return fail(EHB_E_ARG, "unknown mesh id %d", mesh_id);
+    if (V) *V = c->meshes[mesh_id].V;
+    if (F) *F = c->meshes[mesh_id].F;
+    return EHB_OK;
+}
+
+int ehb_render_mask_fwd(ehb_ctx_t h, int mesh_id, const float* mvp_dev, int H, int W, int anti_aliasing, void* out_dev,
+                        void* stream)
+{
+    if (!out_dev) return fail(EHB_E_ARG, "null output pointer");
+    Io io;
+    if (anti_aliasing) { io.masks = (float*)out_dev; return run_pass((Ctx*)h, &mesh_id, 1, 1, mvp_dev, H, W, EHB_MODE_AA_FWD, io, (cudaStream_t)stream); }
+    io.out_u8 = (uint8_t*)out_dev;
+    return run_pass((Ctx*)h, &mesh_id, 1, 1, mvp_dev, H, W, EHB_MODE_UNION, io, (cudaStream_t)stream);
+}
+
+int ehb_render_mask_bwd(ehb_ctx_t h, int mesh_id, const float* mvp_dev, int H, int W, const float* dy_dev,
+                        double* g_mvp_dev, float* g_pos_dev, void* stream)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || !dy_dev || !g_mvp_dev) return fail(EHB_E_ARG, "null pointer argument");
+    if (g_pos_dev) {
+        int V = 0;
+        int r = ehb_mesh_info(h, mesh_id, &V, nullptr);
+        if (r) return r;
+        DeviceGuard guard(c->device);
+        if (V > 0) CU(cudaMemsetAsync(g_pos_dev, 0, (size_t)V * 4 * sizeof(float), (cudaStream_t)stream));
+    }
+    Io io;
+    io.dy = dy_dev; io.gmvp = g_mvp_dev; io.gpos = g_pos_dev; io.do_bwd = 1;
+    return run_pass(c, &mesh_id, 1, 1, mvp_dev, H, W, EHB_MODE_AA_BWD, io, (cudaStream_t)stream);
+}
+
+int ehb_render_views_fused(ehb_ctx_t h, const int* mesh_ids, int L, int B, const float* mvp_dev, const float* ref_dev,
+                           int H, int W, int do_bwd, float* masks_dev, double* loss_dev, double* g_mvp_dev, void* stream)
+{
+    if (!mesh_ids) return fail(EHB_E_ARG, "null mesh id list");
+    if (do_bwd && (!ref_dev || !g_mvp_dev)) return fail(EHB_E_ARG, "backward needs ref_dev and g_mvp_dev");
+    if (ref_dev && !loss_dev) return fail(EHB_E_ARG, "ref_dev given without loss_dev");
+    Io io;
+    io.ref = ref_dev; io.masks = masks_dev; io.loss = ref_dev ? loss_dev : nullptr; io.gmvp = do_bwd ? g_mvp_dev : nullptr;
+    io.do_bwd = do_bwd ? 1 : 0; io.clamp = 1; io.invB = B > 0 ? 1.0f / (float)B : 1.f;
+    return run_pass((Ctx*)h, mesh_ids, L, B, mvp_dev, H, W, EHB_MODE_FUSED, io, (cudaStream_t)stream);
+}
+
+int ehb_render_views_fused_u8(ehb_ctx_t h, const int* mesh_ids, int L, int B, const float* mvp_dev,
+                              const uint8_t* ref_u8_dev, int H, int W, int do_bwd, float* masks_dev, double* loss_dev,
+                              double* g_mvp_dev, void* stream)
+{
+    if (!mesh_ids) return fail(EHB_E_ARG, "null mesh id list");
+    if (!ref_u8_dev || !loss_dev || (do_bwd && !g_mvp_dev)) return fail(EHB_E_ARG, "null pointer argument");
+    Io io;
+    io.ref_u8 = ref_u8_dev; io.masks = masks_dev; io.loss = loss_dev; io.gmvp = do_bwd ? g_mvp_dev : nullptr;
+    io.do_bwd = do_bwd ? 1 : 0; io.clamp = 1; io.invB = B > 0 ? 1.0f / (float)B : 1.f;
+    return run_pass((Ctx*)h, mesh_ids, L, B, mvp_dev, H, W, EHB_MODE_FUSED, io, (cudaStream_t)stream);
+}
+
+int ehb_render_binary_batch(ehb_ctx_t h, const int* mesh_ids, int L, int N, const float* mvp_dev, int H, int W,
+                            uint8_t* out_dev, void* stream)
+{
+    if (!mesh_ids || !out_dev) return fail(EHB_E_ARG, "null pointer argument");
+    Io io;
+    io.out_u8 = out_dev;
+    return run_pass((Ctx*)h, mesh_ids, L, N, mvp_dev, H, W, EHB_MODE_UNION, io, (cudaStream_t)stream);
+}
+
+int ehb_variance_score(ehb_ctx_t h, const uint8_t* masks_dev, int Q, int C, long long n, double* score_dev, void* stream)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || Q < 0 || C < 1 || n < 0 || (Q > 0 && (!masks_dev || !score_dev))) return fail(EHB_E_ARG, "bad variance arguments");
+    if (Q == 0) return EHB_OK;
+    if (Q > 65535) return fail(EHB_E_ARG, "more than 65535 candidates per call");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int r = c->numDev.ensure((size_t)Q, is_capturing(st));
+    if (r) return r;
+    CU(cudaMemsetAsync(c->numDev.p, 0, (size_t)Q * sizeof(unsigned long long), st));
+    const long long work = (n + 15) / 16;
+    const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>((work + 255) / 256, 4 * c->nSM));
+    ehb_k_variance<<<dim3(gx, (unsigned)Q), 256, 0, st>>>(masks_dev, C, n, c->numDev.p);
+    ehb_k_variance_finish<<<(Q + 255) / 256, 256, 0, st>>>(c->numDev.p, Q, C, score_dev);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    return EHB_OK;
+}
+
+int ehb_explore_scores(ehb_ctx_t h, const int* mesh_ids, int L, int Q, int C, const float* mvp_dev, int H, int W,
+                       double* score_dev, void* stream)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || !mesh_ids || Q < 0 || C < 1 || (Q > 0 && (!mvp_dev || !score_dev))) return fail(EHB_E_ARG, "bad explore arguments");
+    if (Q == 0) return EHB_OK;
+    DeviceGuard guard(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = (long long)H * W;
+    // candidates are processed in chunks so that the transient masks stay L2-sized and scratch stays bounded
+    const int chunk = std::max(1, std::min(Q, std::max(1, 64 / C)));
+    int r = c->maskDev.ensure((size_t)chunk * C * n, is_capturing(st));
+    if (r) return r;
+    for (int q0 = 0; q0 < Q; q0 += chunk) {
+        const int nq = std::min(chunk, Q - q0);
+        r = ehb_render_binary_batch(h, mesh_ids, L, nq * C, mvp_dev + (size_t)q0 * C * L * 16, H, W, c->maskDev.p, stream);
+        if (r) return r;
+        r = ehb_variance_score(h, c->maskDev.p, nq, C, n, score_dev + q0, stream);
+        if (r) return r;
+    }
+    return EHB_OK;
+}
+
+int ehb_solver_step_host(ehb_ctx_t h, const int* mesh_ids, int L, int B, const float* mvp_host, const float* ref_dev,
+                         int H, int W, double* loss_host, double* g_mvp_host, void* stream)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || !mvp_host || !ref_dev || !loss_host || !g_mvp_host) return fail(EHB_E_ARG, "null pointer argument");
+    if (B < 1 || L < 1) return fail(EHB_E_ARG, "empty batch");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int r;
+    const size_t nm = (size_t)B * L * 16, no = (size_t)B + nm;
+    if ((r = c->mvpDev.ensure(nm, false))) return r;
+    if ((r = c->outDev.ensure(no, false))) return r;
+    CU(cudaMemcpyAsync(c->mvpDev.p, mvp_host, nm * sizeof(float), cudaMemcpyHostToDevice, st));
+    for (int attempt = 0;; attempt++) {
+        r = ehb_render_views_fused(h, mesh_ids, L, B, c->mvpDev.p, ref_dev, H, W, 1, nullptr, c->outDev.p, c->outDev.p + B, st);
+        if (r) return r;
+        CU(cudaMemcpyAsync(loss_host, c->outDev.p, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(g_mvp_host, c->outDev.p + B, nm * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(c->ctrHost, c->ctr, sizeof(EhbCounters), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (!(c->ctrHost->flags & EHB_FLAG_PAIR_OVERFLOW)) break;
+        if (attempt >= 6) return fail(EHB_E_OVERFLOW, "triangle/tile pair buffer overflow persists after growing");
+        c->pairFactor *= 2;   // grow the pair buffer and run the step again
+        unsigned int zero = 0;
+        CU(cudaMemcpyAsync(&c->ctr->flags, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
+    }
+    return EHB_OK;
+}
+
+long long ehb_launch_count(ehb_ctx_t h) { return h ? ((Ctx*)h)->launches : 0; }
+
+}  // extern "C"

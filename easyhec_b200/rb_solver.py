@@ -1,0 +1,124 @@
+"""RBSolver with the mask loop on the B200 rasterizer.
+
+Mirror of easyhec/modeling/models/rb_solve/rb_solver.py:15-96: same parameter (``dof``, 6-DoF se(3) of
+``Tc_c2b``), same ``forward(dps) -> (output, loss_dict)`` contract, same loss
+
+    S_b = clamp(sum_l render_mask(link_l, K, Tc_c2b @ link_poses[b, l]), max=1)
+    loss = mean_b sum_px (S_b - mask_ref_b)^2
+
+``fused=True`` (default) replaces the per-view / per-link Python loop (rb_solver.py:60-72) by ONE call of
+``ehb_render_views_fused``; ``fused=False`` keeps the reference's loop over ``renderer.render_mask`` (the
+drop-in operator), which is what the parity tests compare the fused path with.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .meshio import load_mesh
+from .projection import K_to_projection, opencv2gl
+from .renderer import B200Renderer
+from .se3 import se3_exp_map, se3_log_map
+
+__all__ = ["RBSolver", "compose_link_mvp"]
+
+
+def compose_link_mvp(K, H, W, Tc_c2b, link_poses):
+    """mvp[b,l] = K_to_projection(K) @ diag(1,-1,-1,1) @ Tc_c2b @ link_poses[b,l]   (B,L,4,4), differentiable.
+
+    nvdiffrast_renderer.py:33-37 with ``object_pose = Tc_c2b @ link_poses[bid, link_idx]`` (rb_solver.py:63)."""
+    proj = K_to_projection(K, H, W).to(link_poses.device)
+    P = proj @ opencv2gl(link_poses.device)
+    return P @ (Tc_c2b @ link_poses)
+
+
+class _FusedViews(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mvp, ref, solver, want_masks):
+        r = solver.renderer
+        need_grad = mvp.requires_grad
+        masks, loss_b, g_mvp = r.ctx.render_views_fused(solver.mesh_ids, mvp.detach().contiguous().float(), ref,
+                                                        r.H, r.W, backward=need_grad, want_masks=want_masks)
+        ctx.g_mvp = g_mvp
+        loss = (loss_b.sum() / mvp.shape[0]).to(torch.float32)
+        if masks is None:
+            masks = torch.empty(0, device=mvp.device)
+        ctx.mark_non_differentiable(masks)
+        return loss, masks
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_masks):
+        return (ctx.g_mvp * g_loss.to(torch.float64)).to(torch.float32), None, None, None
+
+
+class RBSolver(nn.Module):
+    def __init__(self, cfg=None, *, meshes=None, init_Tc_c2b=None, H=None, W=None, fused=True, device=None,
+                 want_outputs=True):
+        super().__init__()
+        if cfg is not None:  # reference-style config: cfg.model.rbsolver.{mesh_paths, init_Tc_c2b, H, W}
+            c = cfg.model.rbsolver
+            meshes = [load_mesh(p) for p in c.mesh_paths]
+            init_Tc_c2b, H, W = c.init_Tc_c2b, c.H, c.W
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        for link_idx, m in enumerate(meshes):
+            v, f = (m.vertices, m.faces) if hasattr(m, "vertices") else m
+            self.register_buffer(f"vertices_{link_idx}", torch.as_tensor(np.asarray(v), dtype=torch.float32))
+            self.register_buffer(f"faces_{link_idx}", torch.as_tensor(np.asarray(f), dtype=torch.int32))
+        self.nlinks = len(meshes)
+        init_dof = se3_log_map(torch.as_tensor(np.asarray(init_Tc_c2b), dtype=torch.float32)[None].permute(0, 2, 1),
+                               eps=1e-5)[0]
+        self.dof = nn.Parameter(init_dof, requires_grad=True)
+        self.H, self.W = int(H), int(W)
+        self.fused = fused
+        self.want_outputs = want_outputs
+        self.to(device)
+        self.renderer = B200Renderer([self.H, self.W], device=device)
+        self.mesh_ids = [self.renderer.ctx.register_mesh(getattr(self, f"vertices_{i}"), getattr(self, f"faces_{i}"))
+                         for i in range(self.nlinks)]
+        self.register_buffer("history_ops", torch.zeros(10000, 6, device=device))
+        self._put_id = 0
+
+    def forward(self, dps):
+        assert dps["global_step"] == 0
+        if self._put_id < self.history_ops.shape[0]:   # host-side cursor: no device sync (cf. rb_solver.py:50)
+            self.history_ops[self._put_id] = self.dof.detach()
+            self._put_id += 1
+        Tc_c2b = se3_exp_map(self.dof[None]).permute(0, 2, 1)[0]
+        masks_ref = dps["mask"]
+        link_poses = dps["link_poses"]
+        K = dps["K"][0]
+        batch_size = masks_ref.shape[0]
+        if self.fused:
+            mvp = compose_link_mvp(K, self.H, self.W, Tc_c2b, link_poses.float())
+            ref = masks_ref if masks_ref.dtype == torch.uint8 else masks_ref.float()
+            if ref.dtype == torch.bool:
+                ref = ref.view(torch.uint8)
+            loss, rendered = _FusedViews.apply(mvp, ref.contiguous(), self, self.want_outputs)
+        else:
+            losses, frames = [], []
+            for bid in range(batch_size):
+                all_link_si = []
+                for link_idx in range(self.nlinks):
+                    Tc_c2l = Tc_c2b @ link_poses[bid, link_idx]
+                    verts, faces = getattr(self, f"vertices_{link_idx}"), getattr(self, f"faces_{link_idx}")
+                    all_link_si.append(self.renderer.render_mask(verts, faces, K=K, object_pose=Tc_c2l))
+                all_link_si = torch.stack(all_link_si).sum(0).clamp(max=1)
+                frames.append(all_link_si)
+                losses.append(torch.sum((all_link_si - masks_ref[bid].float()) ** 2))
+            loss = torch.stack(losses).mean()
+            rendered = torch.stack(frames)
+        output = {}
+        if self.want_outputs:
+            output = {"rendered_masks": rendered, "ref_masks": masks_ref,
+                      "error_maps": (rendered - masks_ref.float()).abs()}
+        gt = dps.get("Tc_c2b")
+        if gt is not None:
+            gt_Tc_c2b = gt[0]
+            if not torch.allclose(gt_Tc_c2b, torch.eye(4).to(gt_Tc_c2b.device)):
+                gt_dof6 = se3_log_map(gt_Tc_c2b[None].permute(0, 2, 1))[0]
+                trans_err = ((gt_dof6[:3] - self.dof[:3]) * 100).abs()
+                rot_err = (gt_dof6[3:] - self.dof[3:]).abs().max() / np.pi * 180
+                output["metrics"] = {"err_x": trans_err[0], "err_y": trans_err[1], "err_z": trans_err[2],
+                                     "err_trans": trans_err.norm(), "err_rot": rot_err}
+        if self.want_outputs:
+            output["tsfm"] = se3_exp_map(self.dof[None].detach().cpu()).permute(0, 2, 1)[0]
+        return output, {"mask_loss": loss}

@@ -1,0 +1,125 @@
+/*
+ * easyhec_b200.h -- C ABI of the B200-native silhouette rasterizer (libehb.so).
+ *
+ * Drop-in boundary for EasyHeC's render_mask hot path.  Every entry point takes plain pointers,
+ * sizes and a CUDA stream handle (void* = cudaStream_t); no torch types.  All functions return 0
+ * on success or a negative EHB_E_* code; ehb_last_error() gives the message of the last failure
+ * on the calling thread.  Nothing here falls back to the CPU: without a usable CUDA device every
+ * compute entry point fails with EHB_E_CUDA.
+ *
+ * Reference interfaces replaced (paths relative to the EasyHeC tree):
+ *   dr.RasterizeCudaContext()                 easyhec/structures/nvdiffrast_renderer.py:23   -> ehb_ctx_create
+ *   dr.rasterize / interpolate / antialias    easyhec/structures/nvdiffrast_renderer.py:39-47 -> ehb_render_mask_fwd / _bwd
+ *   batch_render_mask (packed links, no AA)   easyhec/structures/nvdiffrast_renderer.py:50-73,
+ *                                             easyhec/utils/render_api.py:70-96              -> ehb_render_binary_batch
+ *   RBSolver per-view / per-link loop + loss  easyhec/modeling/models/rb_solve/rb_solver.py:60-72 -> ehb_render_views_fused
+ *   SpaceExplorer variance score              easyhec/modeling/models/rb_solve/space_explorer.py:152-165 -> ehb_variance_score,
+ *                                                                                                ehb_explore_scores
+ *
+ * Conventions:
+ *   mvp        row-major 4x4 fp32, clip = mvp * [x y z 1]^T, mvp = K_to_projection(K,H,W) @ diag(1,-1,-1,1) @ pose
+ *              (easyhec/utils/nvdiffrast_utils.py:5-18, nvdiffrast_renderer.py:33-37)
+ *   masks      image rows, row 0 = top (the reference flips nvdiffrast's output, nvdiffrast_renderer.py:47)
+ *   *_dev      device pointer on the context's device;   *_host   host pointer
+ *   stream     work is only enqueued; nothing synchronises except where stated.  One context per
+ *              device, not thread-safe, one stream at a time (same contract as the reference ctx).
+ */
+#ifndef EASYHEC_B200_H
+#define EASYHEC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define EHB_API __attribute__((visibility("default")))
+#else
+#define EHB_API
+#endif
+
+#define EHB_OK 0
+#define EHB_E_ARG (-1)      /* bad argument (null pointer, size, unknown mesh id, resolution > 8160) */
+#define EHB_E_CUDA (-2)     /* CUDA runtime error or no device */
+#define EHB_E_CAPACITY (-3) /* scratch too small and cannot grow here (stream capture in progress) */
+#define EHB_E_OVERFLOW (-4) /* a previous launch overflowed the triangle/tile pair buffer (see ehb_ctx_status) */
+
+/* bits of *flags from ehb_ctx_status */
+#define EHB_FLAG_PAIR_OVERFLOW 1u /* pair buffer too small: results of that launch are incomplete */
+#define EHB_FLAG_NEEDS_CLIP 2u    /* triangles crossing the near/far plane were skipped (not supported yet) */
+
+typedef void* ehb_ctx_t;
+
+EHB_API int ehb_version(void);
+EHB_API const char* ehb_last_error(void);
+
+/* Context = per-device scratch (tile bins, pair lists) + registered meshes.  Replaces dr.RasterizeCudaContext. */
+EHB_API int ehb_ctx_create(int device, ehb_ctx_t* out);
+EHB_API int ehb_ctx_destroy(ehb_ctx_t ctx);
+/* Pre-size scratch so later launches never allocate (required before CUDA-graph capture).
+ * n_items = views (or renders) per launch, max_faces = sum of faces over the links of one item. */
+EHB_API int ehb_ctx_reserve(ehb_ctx_t ctx, int n_items, int n_links, int max_faces, int H, int W);
+/* Tie rule for a pixel centre lying exactly on a snapped edge: 0 (default) or 1 (mirror); see DESIGN.md. */
+EHB_API int ehb_ctx_set_fill_rule(ehb_ctx_t ctx, int rule);
+/* Doubles the triangle/tile pair capacity used for later launches (call after EHB_FLAG_PAIR_OVERFLOW). */
+EHB_API int ehb_ctx_grow_pairs(ehb_ctx_t ctx);
+/* Synchronises the device, returns and clears the sticky flags, reports triangles skipped for clipping. */
+EHB_API int ehb_ctx_status(ehb_ctx_t ctx, unsigned* flags, long long* n_need_clip);
+
+/* Register a mesh once: verts_host f32[V*3], faces_host i32[F*3].  Builds the padded float4 / int4 device
+ * buffers and the cached edge adjacency (replaces the per-call topology hash of dr.antialias). */
+EHB_API int ehb_mesh_register(ehb_ctx_t ctx, const float* verts_host, int V, const int* faces_host, int F, int* mesh_id);
+/* Replace the vertex positions of a registered mesh from a device buffer f32[V*3] (topology unchanged). */
+EHB_API int ehb_mesh_update_verts(ehb_ctx_t ctx, int mesh_id, const float* verts_dev, int V, void* stream);
+EHB_API int ehb_mesh_release(ehb_ctx_t ctx, int mesh_id);
+EHB_API int ehb_mesh_info(ehb_ctx_t ctx, int mesh_id, int* V, int* F);
+
+/* render_mask forward, one mesh, one pose.  anti_aliasing != 0: out_dev is f32[H*W] in [0,1];
+ * anti_aliasing == 0: out_dev is u8[H*W] (0/1) = (z/w of nearest triangle > 0). */
+EHB_API int ehb_render_mask_fwd(ehb_ctx_t ctx, int mesh_id, const float* mvp_dev, int H, int W, int anti_aliasing,
+                        void* out_dev, void* stream);
+/* render_mask backward (anti-aliased mask only): dy_dev f32[H*W] -> g_mvp_dev f64[16] (overwritten) and,
+ * when g_pos_dev != NULL, the clip-space position gradient f32[V*4] (overwritten; x, y, w non-zero). */
+EHB_API int ehb_render_mask_bwd(ehb_ctx_t ctx, int mesh_id, const float* mvp_dev, int H, int W, const float* dy_dev,
+                        double* g_mvp_dev, float* g_pos_dev, void* stream);
+
+/* RBSolver mask loop, fused: for b < B views and l < L links
+ *     S_b = min(sum_l aa_mask(mesh_l, mvp[b,l]), 1)           -> masks_dev f32[B*H*W] (may be NULL)
+ *     loss_b = sum_px (S_b - ref_b)^2                          -> loss_dev f64[B]      (needs ref_dev)
+ *     g_mvp[b,l] = d( (1/B) sum_b loss_b ) / d mvp[b,l]        -> g_mvp_dev f64[B*L*16] (when do_bwd)
+ * ref_dev f32[B*H*W] (NULL: masks only). */
+EHB_API int ehb_render_views_fused(ehb_ctx_t ctx, const int* mesh_ids, int L, int B, const float* mvp_dev,
+                           const float* ref_dev, int H, int W, int do_bwd, float* masks_dev, double* loss_dev,
+                           double* g_mvp_dev, void* stream);
+
+/* Same with the reference masks as bytes (non-zero = 1), the form EasyHeC's dataset holds them in before
+ * `.float()` (easyhec/data/datasets/xarm_real.py:36,40): a quarter of the HBM and PCIe bytes. */
+EHB_API int ehb_render_views_fused_u8(ehb_ctx_t ctx, const int* mesh_ids, int L, int B, const float* mvp_dev,
+                              const uint8_t* ref_u8_dev, int H, int W, int do_bwd, float* masks_dev,
+                              double* loss_dev, double* g_mvp_dev, void* stream);
+
+/* N renders of the packed robot (all L links into one depth buffer, no anti-aliasing) -> out_dev u8[N*H*W]. */
+EHB_API int ehb_render_binary_batch(ehb_ctx_t ctx, const int* mesh_ids, int L, int N, const float* mvp_dev, int H, int W,
+                            uint8_t* out_dev, void* stream);
+/* score[q] = sum_px unbiased_var_c(masks[q,c,px]), masks_dev u8[Q*C*n] -> score_dev f64[Q]. */
+EHB_API int ehb_variance_score(ehb_ctx_t ctx, const uint8_t* masks_dev, int Q, int C, long long n, double* score_dev,
+                       void* stream);
+/* Fused space-exploration score: renders Q*C packed binary masks (mvp_dev f32[Q*C*L*16]) tile by tile and
+ * reduces the per-pixel variance over the C cameras without writing the masks. */
+EHB_API int ehb_explore_scores(ehb_ctx_t ctx, const int* mesh_ids, int L, int Q, int C, const float* mvp_dev, int H, int W,
+                       double* score_dev, void* stream);
+
+/* Host-buffer form of ehb_render_views_fused for callers without device pointers of their own: copies
+ * mvp_host (pinned or pageable) to the device, runs the fused step on ref_dev, copies loss f64[B] and
+ * g_mvp f64[B*L*16] back and synchronises the stream. */
+EHB_API int ehb_solver_step_host(ehb_ctx_t ctx, const int* mesh_ids, int L, int B, const float* mvp_host,
+                         const float* ref_dev, int H, int W, double* loss_host, double* g_mvp_host, void* stream);
+
+/* Number of kernels this library has launched on the context since creation (for launch accounting). */
+EHB_API long long ehb_launch_count(ehb_ctx_t ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -137,6 +137,13 @@ EHO_API int eho_rasterize(const float* clip, int V, const int* tri, int F, int H
         int64_t x0 = rni_sat(v0[0] * r0 * vsx), y0 = rni_sat(v0[1] * r0 * vsy);
         int64_t x1 = rni_sat(v1[0] * r1 * vsx), y1 = rni_sat(v1[1] * r1 * vsy);
         int64_t x2 = rni_sat(v2[0] * r2 * vsx), y2 = rni_sat(v2[1] * r2 * vsy);
+        /* guard band: beyond +-2^28 sub-pixel units the 64-bit edge products could overflow; such a
+         * triangle would go through the clipper in cudaraster => counted with the needs-clip ones */
+        {
+            const int64_t G = (int64_t)1 << 28;
+            if (x0 > G || x0 < -G || y0 > G || y0 < -G || x1 > G || x1 < -G || y1 > G || y1 < -G ||
+                x2 > G || x2 < -G || y2 > G || y2 < -G) { nclip++; continue; }
+        }
         int64_t area = (x1 - x0) * (y2 - y0) - (y1 - y0) * (x2 - x0);
         if (area == 0) continue;
         if (area < 0) { int64_t tx = x1, ty = y1; x1 = x2; y1 = y2; x2 = tx; y2 = ty; }

@@ -1,0 +1,193 @@
+"""CUDA kernels (through the C ABI) against the CPU oracle on identical inputs.
+
+Bar (BASELINE.json north_star): binary masks bit-exact; antialiased masks are compared bit-exact too
+(same fp32 operation order on both sides); gradients within 1e-4 relative (asserted much tighter).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+from easyhec_b200.meshio import Mesh, concat_meshes, synthetic_links
+from easyhec_b200.scenes import SAMPLE_POSE, make_scene, scaled_K
+from util import mvp_of, quad, rel_err, scene_mvps, to_dev, zero_pose_robot
+
+pytestmark = pytest.mark.gpu
+
+GRAD_RTOL = 1e-4   # the contract; the asserts below use a much tighter bound where fp order allows
+
+
+def _status_ok(ctx):
+    flags, nclip = ctx.status()
+    assert flags & 1 == 0, "pair buffer overflow"
+    return flags, nclip
+
+
+@pytest.mark.parametrize("H,W", [(128, 128), (480, 640), (720, 1280)])
+def test_binary_mask_bit_exact_xarm7_zero_pose(gpu_ctx, xarm, H, W):
+    m = zero_pose_robot(xarm)
+    mvp = mvp_of(scaled_K(H, W), H, W, SAMPLE_POSE)
+    want = oracle.render_mask(m.vertices, m.faces, mvp, H, W, anti_aliasing=False)
+    mid = gpu_ctx.register_mesh(m.vertices, m.faces)
+    got = gpu_ctx.render_mask_fwd(mid, to_dev(mvp), H, W, anti_aliasing=False).cpu().numpy().astype(bool)
+    _status_ok(gpu_ctx)
+    gpu_ctx.release_mesh(mid)
+    assert want.sum() > 0.02 * H * W
+    assert np.array_equal(got, want), "%d pixels differ" % int((got != want).sum())
+
+
+@pytest.mark.parametrize("H,W", [(128, 128), (480, 640), (720, 1280), (101, 67)])
+def test_aa_mask_and_backward_single_link(gpu_ctx, xarm, H, W):
+    m = xarm["meshes"][6].transformed(xarm["fk_zero"][6])
+    mvp = mvp_of(scaled_K(H, W), H, W, SAMPLE_POSE)
+    want, state = oracle.render_mask(m.vertices, m.faces, mvp, H, W, anti_aliasing=True, save=True)
+    mid = gpu_ctx.register_mesh(m.vertices, m.faces)
+    got = gpu_ctx.render_mask_fwd(mid, to_dev(mvp), H, W, anti_aliasing=True).cpu().numpy()
+    assert want.max() > 0.5
+    assert np.array_equal(got, want), "max |diff| = %g at %d px" % (np.abs(got - want).max(), (got != want).sum())
+    rng = np.random.RandomState(1)
+    dy = rng.randn(H, W).astype(np.float32)
+    gpos_w, gmvp_w = oracle.render_mask_bwd(m.vertices, m.faces, mvp, H, W, state, dy)
+    g_mvp, g_pos = gpu_ctx.render_mask_bwd(mid, to_dev(mvp), H, W, to_dev(dy), want_gpos=True)
+    _status_ok(gpu_ctx)
+    gpu_ctx.release_mesh(mid)
+    assert np.abs(gmvp_w).max() > 0
+    assert rel_err(g_mvp.cpu().numpy(), gmvp_w) < 1e-9
+    assert rel_err(g_pos.cpu().numpy(), gpos_w) < 1e-5
+    assert np.all(g_mvp.cpu().numpy()[2] == 0)
+
+
+@pytest.mark.parametrize("B,H,W,links", [(3, 120, 160, "xarm7"), (2, 480, 640, "xarm7"), (2, 360, 640, "xarm7_all")])
+def test_fused_views_match_oracle(gpu_ctx, B, H, W, links):
+    sc = make_scene(B, H, W, links=links, seed=3)
+    mvp = scene_mvps(sc, H, W)
+    packed = oracle.pack_links(sc["meshes"])
+    ref = oracle.union_binary(packed, mvp, H, W).astype(np.float32)
+    # perturbed camera -> non-zero loss and gradient
+    from easyhec_b200.scenes import perturb_pose
+    mvp2 = scene_mvps(sc, H, W, perturb_pose(sc["Tc_c2b"], np.random.RandomState(5), 0.02, 2.0))
+    want = oracle.render_views(packed, mvp2, ref, H, W)
+    ids = [gpu_ctx.register_mesh(m.vertices, m.faces) for m in sc["meshes"]]
+    masks, loss, g_mvp = gpu_ctx.render_views_fused(ids, to_dev(mvp2), to_dev(ref), H, W, backward=True)
+    masks_u8, loss_u8, g_u8 = gpu_ctx.render_views_fused(ids, to_dev(mvp2), to_dev(ref.astype(np.uint8)), H, W)
+    _status_ok(gpu_ctx)
+    for i in ids:
+        gpu_ctx.release_mesh(i)
+    assert np.array_equal(masks.cpu().numpy(), want["masks"])
+    assert np.allclose(loss.cpu().numpy(), want["loss_per_view"], rtol=1e-12, atol=0)
+    assert want["loss"] > 0 and np.abs(want["g_mvp"]).max() > 0
+    assert rel_err(g_mvp.cpu().numpy(), want["g_mvp"]) < 1e-9
+    assert np.array_equal(masks_u8.cpu().numpy(), want["masks"])
+    assert np.allclose(loss_u8.cpu().numpy(), want["loss_per_view"], rtol=1e-12, atol=0)
+    assert rel_err(g_u8.cpu().numpy(), want["g_mvp"]) < 1e-9
+
+
+def test_fused_more_links_than_resident_planes(gpu_ctx):
+    """9 overlapping links > the 6 planes a CTA keeps resident: the multi-round path must give the same answer."""
+    H, W, B = 96, 128, 2
+    links = synthetic_links([300] * 9, radius=0.05, length=0.2, seed=2)
+    rng = np.random.RandomState(0)
+    lp = np.tile(np.eye(4, dtype=np.float32), (B, 9, 1, 1))
+    lp[:, :, :3, 3] = rng.uniform(-0.03, 0.03, (B, 9, 3))
+    sc = dict(meshes=links, link_poses=lp, K=scaled_K(H, W), Tc_c2b=SAMPLE_POSE)
+    mvp = scene_mvps(sc, H, W)
+    packed = oracle.pack_links(links)
+    ref = (np.random.RandomState(1).rand(B, H, W) > 0.5).astype(np.float32)
+    want = oracle.render_views(packed, mvp, ref, H, W)
+    ids = [gpu_ctx.register_mesh(m.vertices, m.faces) for m in links]
+    masks, loss, g_mvp = gpu_ctx.render_views_fused(ids, to_dev(mvp), to_dev(ref), H, W, backward=True)
+    _status_ok(gpu_ctx)
+    for i in ids:
+        gpu_ctx.release_mesh(i)
+    assert want["masks"].max() == 1.0 and (want["masks"] > 0).mean() > 0.05
+    assert np.array_equal(masks.cpu().numpy(), want["masks"])
+    assert np.allclose(loss.cpu().numpy(), want["loss_per_view"], rtol=1e-12, atol=0)
+    assert rel_err(g_mvp.cpu().numpy(), want["g_mvp"]) < 1e-9
+
+
+def test_union_batch_and_variance(gpu_ctx, xarm):
+    H, W, Q, C = 270, 480, 3, 4
+    sc = make_scene(Q * C, H, W, links="xarm7_all", seed=7)
+    from easyhec_b200.scenes import perturb_pose
+    rng = np.random.RandomState(2)
+    mvps = []
+    for q in range(Q):
+        for c in range(C):
+            cam = perturb_pose(sc["Tc_c2b"], rng, 0.02, 2.0)
+            one = dict(sc, link_poses=sc["link_poses"][q * C:q * C + 1])   # same qpos for the C cameras of a candidate
+            mvps.append(scene_mvps(one, H, W, cam)[0])
+    mvp = np.stack(mvps).astype(np.float32)
+    packed = oracle.pack_links(sc["meshes"])
+    want = oracle.union_binary(packed, mvp, H, W)
+    ids = [gpu_ctx.register_mesh(m.vertices, m.faces) for m in sc["meshes"]]
+    got = gpu_ctx.render_binary_batch(ids, to_dev(mvp), H, W)
+    assert np.array_equal(got.cpu().numpy().astype(bool), want)
+    sw = oracle.variance_scores(want.reshape(Q, C, H, W))
+    sg = gpu_ctx.variance_score(got.view(Q, C, H, W))
+    assert np.allclose(sg.cpu().numpy(), sw, rtol=1e-12)
+    se = gpu_ctx.explore_scores(ids, to_dev(mvp.reshape(Q, C, len(ids), 4, 4)), H, W)
+    _status_ok(gpu_ctx)
+    for i in ids:
+        gpu_ctx.release_mesh(i)
+    assert np.allclose(se.cpu().numpy(), sw, rtol=1e-12)
+    assert sw.min() > 0
+
+
+def test_edge_cases(gpu_ctx):
+    H, W = 75, 130
+    K = scaled_K(H, W)
+    eye = np.eye(4)
+    # (a) full-screen quad: every pixel covered, warp path, no silhouette inside the image
+    q = quad()
+    mvp = mvp_of(K, H, W, eye)
+    mid = gpu_ctx.register_mesh(q.vertices, q.faces)
+    for aa in (False, True):
+        want = oracle.render_mask(q.vertices, q.faces, mvp, H, W, anti_aliasing=aa)
+        got = gpu_ctx.render_mask_fwd(mid, to_dev(mvp), H, W, anti_aliasing=aa).cpu().numpy()
+        assert np.array_equal(got.astype(want.dtype), want) and want.all()
+    # (b) mesh entirely off-screen / behind the camera: empty mask, zero gradient
+    behind = np.eye(4); behind[2, 3] = -5.0
+    mvp_b = mvp_of(K, H, W, behind)
+    got = gpu_ctx.render_mask_fwd(mid, to_dev(mvp_b), H, W, anti_aliasing=True).cpu().numpy()
+    assert not got.any()
+    g_mvp, _ = gpu_ctx.render_mask_bwd(mid, to_dev(mvp_b), H, W, to_dev(np.ones((H, W), np.float32)))
+    assert not g_mvp.cpu().numpy().any()
+    # (c) triangle crossing the near plane: skipped and counted on both sides
+    near = np.eye(4); near[2, 3] = -1.0 + 1e-4
+    mvp_n = mvp_of(K, H, W, near)
+    want, st = oracle.render_mask(q.vertices, q.faces, mvp_n, H, W, anti_aliasing=False, save=True)
+    gpu_ctx.status()
+    got = gpu_ctx.render_mask_fwd(mid, to_dev(mvp_n), H, W, anti_aliasing=False).cpu().numpy().astype(bool)
+    flags, nclip = gpu_ctx.status()
+    assert np.array_equal(got, want) and nclip == st[3]
+    gpu_ctx.release_mesh(mid)
+    # (d) empty mesh
+    mid = gpu_ctx.register_mesh(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int32))
+    got = gpu_ctx.render_mask_fwd(mid, to_dev(mvp), H, W, anti_aliasing=True).cpu().numpy()
+    assert got.shape == (H, W) and not got.any()
+    gpu_ctx.release_mesh(mid)
+    # (e) degenerate and out-of-range faces are ignored
+    v = np.array([[-.2, -.2, 1], [.2, -.2, 1], [.2, .2, 1], [0, 0, 1]], np.float32)
+    f = np.array([[0, 1, 2], [0, 0, 1], [0, 1, 7], [3, 3, 3]], np.int32)
+    want = oracle.render_mask(v, f, mvp, H, W, anti_aliasing=True)
+    mid = gpu_ctx.register_mesh(v, f)
+    got = gpu_ctx.render_mask_fwd(mid, to_dev(mvp), H, W, anti_aliasing=True).cpu().numpy()
+    gpu_ctx.release_mesh(mid)
+    assert np.array_equal(got, want) and want.any()
+
+
+def test_subpixel_square_known_answers(gpu_ctx):
+    """Axis-aligned squares at integer / half-integer offsets: coverage counts follow the tie rule."""
+    H = W = 64
+    K = np.array([[64.0, 0, 32.0], [0, 64.0, 32.0], [0, 0, 1]], np.float32)   # 1 unit at z=1 -> 64 px
+    mvp = mvp_of(K, H, W, np.eye(4))
+    for off, size in [(0.0, 8), (0.5, 8), (0.25, 4), (0.5, 1)]:
+        a, b = (10 + off - 32) / 64.0, (10 + off + size - 32) / 64.0
+        v = np.array([[a, a, 1], [b, a, 1], [b, b, 1], [a, b, 1]], np.float32)
+        f = np.array([[0, 1, 2], [0, 2, 3]], np.int32)
+        want = oracle.render_mask(v, f, mvp, H, W, anti_aliasing=False)
+        mid = gpu_ctx.register_mesh(v, f)
+        got = gpu_ctx.render_mask_fwd(mid, to_dev(mvp), H, W, anti_aliasing=False).cpu().numpy().astype(bool)
+        gpu_ctx.release_mesh(mid)
+        assert np.array_equal(got, want)
+        assert want.sum() == size * size, (off, size, want.sum())
