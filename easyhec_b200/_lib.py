@@ -36,6 +36,8 @@ _PROTOS = {
     "ehb_ctx_reserve": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ehb_ctx_set_fill_rule": (C.c_int, [C.c_void_p, C.c_int]),
     "ehb_ctx_grow_pairs": (C.c_int, [C.c_void_p]),
+    "ehb_ctx_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "ehb_ctx_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "ehb_ctx_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint), C.POINTER(C.c_longlong)]),
     "ehb_mesh_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "ehb_mesh_update_verts": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
@@ -56,6 +58,8 @@ _PROTOS = {
                                      C.c_void_p, C.c_void_p]),
     "ehb_solver_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ehb_solver_step_host_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                          C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ehb_launch_count": (C.c_longlong, [C.c_void_p]),
 }
 
@@ -168,6 +172,16 @@ class Context:
         _check(lib().ehb_ctx_status(self._h, C.byref(fl), C.byref(nc)))
         return fl.value, nc.value
 
+    def profile(self, enable: bool):
+        _check(lib().ehb_ctx_profile(self._h, int(bool(enable))))
+
+    def kernel_times(self):
+        """-> ({count, alloc, fill, raster: summed ms}, passes) since the last query; synchronises."""
+        ms = (C.c_double * 4)()
+        n = C.c_longlong()
+        _check(lib().ehb_ctx_kernel_times(self._h, ms, C.byref(n)))
+        return dict(zip(("count", "alloc", "fill", "raster"), list(ms))), n.value
+
     def launch_count(self) -> int:
         return int(lib().ehb_launch_count(self._h))
 
@@ -251,3 +265,13 @@ class Context:
         _dev_check(ref_dev, torch.float32, self.device, "ref")
         _check(lib().ehb_solver_step_host(self._h, ids, L, B, _ptr(mvp_host), _ptr(ref_dev), H, W, _ptr(loss_host),
                                           _ptr(g_mvp_host), _stream(self.device)))
+
+    def solver_step_host_u8(self, mesh_ids, mvp_host, ref_u8_host, H, W, loss_host, g_mvp_host):
+        """Everything from host memory: mvp_host (B,L,4,4) f32 and ref_u8_host (B,H,W) u8 pinned CPU tensors are
+        copied in, loss_host (B,) / g_mvp_host (B,L,4,4) f64 pinned CPU tensors are written; synchronises."""
+        B, L = mvp_host.shape[0], mvp_host.shape[1]
+        ids = (C.c_int * L)(*mesh_ids)
+        if ref_u8_host.dtype != torch.uint8 or not ref_u8_host.is_contiguous():
+            raise EhbError("ref_u8_host must be a contiguous uint8 CPU tensor")
+        _check(lib().ehb_solver_step_host_u8(self._h, ids, L, B, _ptr(mvp_host), _ptr(ref_u8_host), H, W,
+                                             _ptr(loss_host), _ptr(g_mvp_host), _stream(self.device)))

@@ -64,6 +64,7 @@ struct DevBuf {
 struct Ctx {
     int device = 0;
     int nSM = 148;
+    int occ1 = 2, occF = 2;           // resident raster CTAs per SM (single-plane / fused instantiation)
     int rule = 0;
     std::vector<Mesh> meshes;
     DevBuf<uint32_t> range, cnt, start, cur, tileList, pairs;
@@ -77,6 +78,9 @@ struct Ctx {
     float* mvpPinned = nullptr; size_t mvpPinnedN = 0;
     double* outPinned = nullptr; size_t outPinnedN = 0;
     long long launches = 0;
+    bool profiling = false;           // per-kernel CUDA events (ehb_ctx_profile)
+    std::vector<cudaEvent_t> evPool;  // 5 events per profiled pass
+    size_t evUsed = 0;
     size_t pairFactor = 3;            // pair capacity = items * Ftot * pairFactor (+ slack); grown on overflow
 };
 
@@ -176,7 +180,7 @@ __global__ void ehb_k_variance_finish(const unsigned long long* __restrict__ num
 
 constexpr int PMAX_FUSED = 6;
 
-size_t raster_smem(int pmax) { return (size_t)pmax * EHB_NP * 8 + ((EHB_NP + 3) & ~3) * 4 + sizeof(EhbRasterSmem); }
+size_t raster_smem(int pmax) { return EHB_PLANES_BYTES(pmax) + EHB_SUM_BYTES + ((sizeof(EhbOverlay) + 15) & ~15) + sizeof(EhbRasterSmem); }
 
 struct Io {
     const float* ref = nullptr; const uint8_t* ref_u8 = nullptr;
@@ -251,18 +255,33 @@ int run_pass(Ctx* c, const int* mesh_ids, int L, int items, const float* mvp_dev
 
     const size_t bins = (size_t)items * p.ntiles * p.Lk;
     CU(cudaMemsetAsync(p.cnt, 0, bins * sizeof(uint32_t), st));
+    cudaEvent_t* ev = nullptr;
+    if (c->profiling && !capturing) {
+        if (c->evUsed + 5 > c->evPool.size()) {
+            const size_t old = c->evPool.size();
+            c->evPool.resize(old + 5 * 256);
+            for (size_t i = old; i < c->evPool.size(); i++) CU(cudaEventCreate(&c->evPool[i]));
+        }
+        ev = &c->evPool[c->evUsed];
+        c->evUsed += 5;
+    }
     const dim3 gt((unsigned)std::max(1, (p.Ftot + 255) / 256), (unsigned)items);
+    if (ev) cudaEventRecord(ev[0], st);
     ehb_k_count<<<gt, 256, 0, st>>>(rb, p);
+    if (ev) cudaEventRecord(ev[1], st);
     const long long warps = (long long)items * p.ntiles;
     ehb_k_alloc<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(p);
+    if (ev) cudaEventRecord(ev[2], st);
     ehb_k_fill<<<gt, 256, 0, st>>>(rb, p);
+    if (ev) cudaEventRecord(ev[3], st);
     if (unionMode || L == 1) {
         const size_t sm = raster_smem(1);
-        ehb_k_raster<1><<<c->nSM * 6, EHB_THREADS, sm, st>>>(rb, p);
+        ehb_k_raster<1><<<c->nSM * c->occ1, EHB_THREADS, sm, st>>>(rb, p);
     } else {
         const size_t sm = raster_smem(PMAX_FUSED);
-        ehb_k_raster<PMAX_FUSED><<<c->nSM * 3, EHB_THREADS, sm, st>>>(rb, p);
+        ehb_k_raster<PMAX_FUSED><<<c->nSM * c->occF, EHB_THREADS, sm, st>>>(rb, p);
     }
+    if (ev) cudaEventRecord(ev[4], st);
     c->launches += 4;
     CU(cudaGetLastError());
     return EHB_OK;
@@ -296,6 +315,9 @@ int ehb_ctx_create(int device, ehb_ctx_t* out)
     CU(cudaMallocHost((void**)&c->ctrHost, sizeof(EhbCounters)));
     CU(cudaFuncSetAttribute(ehb_k_raster<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem(1)));
     CU(cudaFuncSetAttribute(ehb_k_raster<PMAX_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem(PMAX_FUSED)));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ1, ehb_k_raster<1>, EHB_THREADS, raster_smem(1)));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occF, ehb_k_raster<PMAX_FUSED>, EHB_THREADS, raster_smem(PMAX_FUSED)));
+    c->occ1 = std::max(1, c->occ1); c->occF = std::max(1, c->occF);
     *out = c;
     return EHB_OK;
 }
@@ -311,6 +333,7 @@ int ehb_ctx_destroy(ehb_ctx_t h)
     c->mvpDev.release(); c->outDev.release(); c->refDev.release(); c->maskDev.release(); c->numDev.release();
     if (c->mvpPinned) cudaFreeHost(c->mvpPinned);
     if (c->outPinned) cudaFreeHost(c->outPinned);
+    for (auto e : c->evPool) cudaEventDestroy(e);
     cudaFree(c->ctr);
     cudaFreeHost(c->ctrHost);
     delete c;
@@ -343,6 +366,32 @@ int ehb_ctx_grow_pairs(ehb_ctx_t h)
     Ctx* c = (Ctx*)h;
     if (!c) return fail(EHB_E_ARG, "null context");
     c->pairFactor *= 2;
+    return EHB_OK;
+}
+
+int ehb_ctx_profile(ehb_ctx_t h, int enable)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c) return fail(EHB_E_ARG, "null context");
+    c->profiling = enable != 0;
+    return EHB_OK;
+}
+
+int ehb_ctx_kernel_times(ehb_ctx_t h, double* ms4, long long* n_passes)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || !ms4 || !n_passes) return fail(EHB_E_ARG, "null pointer argument");
+    DeviceGuard guard(c->device);
+    CU(cudaDeviceSynchronize());
+    for (int k = 0; k < 4; k++) ms4[k] = 0.0;
+    for (size_t i = 0; i + 5 <= c->evUsed; i += 5)
+        for (int k = 0; k < 4; k++) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, c->evPool[i + k], c->evPool[i + k + 1]));
+            ms4[k] += ms;
+        }
+    *n_passes = (long long)(c->evUsed / 5);
+    c->evUsed = 0;
     return EHB_OK;
 }
 
@@ -550,6 +599,37 @@ int ehb_solver_step_host(ehb_ctx_t h, const int* mesh_ids, int L, int B, const f
         if (!(c->ctrHost->flags & EHB_FLAG_PAIR_OVERFLOW)) break;
         if (attempt >= 6) return fail(EHB_E_OVERFLOW, "triangle/tile pair buffer overflow persists after growing");
         c->pairFactor *= 2;   // grow the pair buffer and run the step again
+        unsigned int zero = 0;
+        CU(cudaMemcpyAsync(&c->ctr->flags, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
+    }
+    return EHB_OK;
+}
+
+int ehb_solver_step_host_u8(ehb_ctx_t h, const int* mesh_ids, int L, int B, const float* mvp_host,
+                             const uint8_t* ref_u8_host, int H, int W, double* loss_host, double* g_mvp_host, void* stream)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || !mvp_host || !ref_u8_host || !loss_host || !g_mvp_host) return fail(EHB_E_ARG, "null pointer argument");
+    if (B < 1 || L < 1) return fail(EHB_E_ARG, "empty batch");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int r;
+    const size_t nm = (size_t)B * L * 16, no = (size_t)B + nm, npx = (size_t)B * H * W;
+    if ((r = c->mvpDev.ensure(nm, false))) return r;
+    if ((r = c->outDev.ensure(no, false))) return r;
+    if ((r = c->refDev.ensure(npx, false))) return r;
+    CU(cudaMemcpyAsync(c->mvpDev.p, mvp_host, nm * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->refDev.p, ref_u8_host, npx, cudaMemcpyHostToDevice, st));
+    for (int attempt = 0;; attempt++) {
+        r = ehb_render_views_fused_u8(h, mesh_ids, L, B, c->mvpDev.p, c->refDev.p, H, W, 1, nullptr, c->outDev.p, c->outDev.p + B, st);
+        if (r) return r;
+        CU(cudaMemcpyAsync(loss_host, c->outDev.p, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(g_mvp_host, c->outDev.p + B, nm * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(c->ctrHost, c->ctr, sizeof(EhbCounters), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (!(c->ctrHost->flags & EHB_FLAG_PAIR_OVERFLOW)) break;
+        if (attempt >= 6) return fail(EHB_E_OVERFLOW, "triangle/tile pair buffer overflow persists after growing");
+        c->pairFactor *= 2;
         unsigned int zero = 0;
         CU(cudaMemcpyAsync(&c->ctr->flags, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
     }

@@ -20,8 +20,6 @@
 #define EHB_RS 35           // plane row stride = T + max halo (1 low, 2 high)
 #define EHB_NP (EHB_RS * EHB_RS)
 #define EHB_THREADS 256
-#define EHB_BIGQ 512
-#define EHB_BIG_SAMPLES 64  // a triangle with more candidate samples in the tile goes to the warp path
 
 enum { EHB_MODE_FUSED = 0, EHB_MODE_AA_FWD = 1, EHB_MODE_AA_BWD = 2, EHB_MODE_UNION = 3, EHB_MODE_UNION_VAR = 4 };
 
@@ -249,71 +247,36 @@ __global__ void __launch_bounds__(256) ehb_k_fill(const __grid_constant__ EhbRob
 }
 
 // ------------------------------------------------------------------------------------------------ k_raster
-struct EhbTileCtx {
-    int item, tx, ty;
-    int rx0, ry0, rx1, ry1;  // pixel extent of the region held in the planes (clipped to the image later)
+//
+// One CTA per non-empty tile (persistent CTAs pull tiles from a queue).  Per tile:
+//   raster : triangles are taken 256 at a time, one per thread: setup -> a 64-byte record in shared memory
+//            (edge functions at the first candidate sample, per-pixel steps, clipped bbox).  A block scan of
+//            the candidate-sample counts turns the batch into ONE flat sample space that is cut into 256 equal
+//            chunks, so every thread tests the same number of samples whatever the triangle sizes are.
+//            Covered samples are not shaded in place: they go to a per-warp queue (warp-ballot aggregated)
+//            that is drained with all 32 lanes busy: z/w from the unsnapped clip positions, 64-bit
+//            (depth key | triangle id) atomicMin into the link's plane.
+//   AA fwd : per resident link: silhouette pixel pairs (covered next to empty) are compacted into a queue, their
+//            blend weights are computed with all lanes busy and scattered into two alpha planes, then every
+//            pixel adds colour + its four pair contributions in the reference's order.
+//   loss   : S = min(sum_links, 1), (S - ref)^2, g = dL/dsum kept in shared memory.
+//   AA bwd : pairs owned by interior pixels are compacted again, weights recomputed, analytic gradient of
+//            the active edge's two vertices contracted with [x y z 1] on the fly, warp-shuffle reduced and
+//            added to d loss / d mvp[item, link] with fp64 atomics.
+struct __align__(16) EhbRec {
+    long long E[3];          // edge functions at the first candidate sample of the clipped bbox
+    int ex[3], ey[3];        // edge vectors (1/16 px): one pixel right adds -16*ey, one pixel up adds +16*ex
+    unsigned short w, h;     // clipped bbox, in pixels
+    unsigned char lx, ly;    // its origin inside the plane
+    unsigned char slot, thr; // plane slot; bit k set: edge k excludes samples exactly on it
+    uint32_t id;             // triangle id stored in the depth key
 };
 
-template <typename I>
-__device__ __forceinline__ void ehb_cover_rows(const EhbTri& s, int xlo, int xhi, int ylo, int yhi,
-                                               unsigned long long* pl, int rx0, int ry0, uint32_t id, int H, int W,
-                                               int rule)
-{
-    const int bx = 8 * W - 8, by = 8 * H - 8;
-    const int ex0 = s.x1 - s.x0, ey0 = s.y1 - s.y0, ex1 = s.x2 - s.x1, ey1 = s.y2 - s.y1, ex2 = s.x0 - s.x2,
-              ey2 = s.y0 - s.y2;
-    const I t0 = ehb_edge_inclusive(ex0, ey0, rule) ? 0 : 1, t1 = ehb_edge_inclusive(ex1, ey1, rule) ? 0 : 1,
-            t2 = ehb_edge_inclusive(ex2, ey2, rule) ? 0 : 1;
-    const float xs = 2.f / (float)W, xo = 1.f / (float)W - 1.f;
-    const float ys = 2.f / (float)H, yo = 1.f / (float)H - 1.f;
-    const int sx0 = 16 * xlo - bx;
-    for (int py = ylo; py <= yhi; py++) {
-        const int sy = 16 * py - by;
-        I e0 = (I)ex0 * (I)(sy - s.y0) - (I)ey0 * (I)(sx0 - s.x0);
-        I e1 = (I)ex1 * (I)(sy - s.y1) - (I)ey1 * (I)(sx0 - s.x1);
-        I e2 = (I)ex2 * (I)(sy - s.y2) - (I)ey2 * (I)(sx0 - s.x2);
-        for (int px = xlo; px <= xhi; px++) {
-            if (e0 >= t0 && e1 >= t1 && e2 >= t2) {
-                const float fx = xs * (float)px + xo, fy = ys * (float)py + yo;
-                const float zw = ehb_shade_zw(s.c0, s.c1, s.c2, fx, fy);
-                const unsigned long long key = ((unsigned long long)ehb_order_key(zw) << 32) | id;
-                unsigned long long* dst = pl + (py - ry0) * EHB_RS + (px - rx0);
-                if (key < *dst) atomicMin(dst, key);
-            }
-            e0 -= (I)16 * (I)ey0; e1 -= (I)16 * (I)ey1; e2 -= (I)16 * (I)ey2;
-        }
-    }
-}
-
-// Warp path: lanes stride over the candidate samples of one triangle.
-__device__ __forceinline__ void ehb_cover_warp(const EhbTri& s, int xlo, int xhi, int ylo, int yhi,
-                                               unsigned long long* pl, int rx0, int ry0, uint32_t id, int H, int W,
-                                               int rule, int lane)
-{
-    const int bx = 8 * W - 8, by = 8 * H - 8;
-    const int ex0 = s.x1 - s.x0, ey0 = s.y1 - s.y0, ex1 = s.x2 - s.x1, ey1 = s.y2 - s.y1, ex2 = s.x0 - s.x2,
-              ey2 = s.y0 - s.y2;
-    const long long t0 = ehb_edge_inclusive(ex0, ey0, rule) ? 0 : 1, t1 = ehb_edge_inclusive(ex1, ey1, rule) ? 0 : 1,
-                    t2 = ehb_edge_inclusive(ex2, ey2, rule) ? 0 : 1;
-    const float xs = 2.f / (float)W, xo = 1.f / (float)W - 1.f;
-    const float ys = 2.f / (float)H, yo = 1.f / (float)H - 1.f;
-    const int w = xhi - xlo + 1, n = w * (yhi - ylo + 1);
-    for (int i = lane; i < n; i += 32) {
-        const int ry = i / w;
-        const int px = xlo + (i - ry * w), py = ylo + ry;
-        const int sx = 16 * px - bx, sy = 16 * py - by;
-        const long long e0 = (long long)ex0 * (sy - s.y0) - (long long)ey0 * (sx - s.x0);
-        const long long e1 = (long long)ex1 * (sy - s.y1) - (long long)ey1 * (sx - s.x1);
-        const long long e2 = (long long)ex2 * (sy - s.y2) - (long long)ey2 * (sx - s.x2);
-        if (e0 >= t0 && e1 >= t1 && e2 >= t2) {
-            const float fx = xs * (float)px + xo, fy = ys * (float)py + yo;
-            const float zw = ehb_shade_zw(s.c0, s.c1, s.c2, fx, fy);
-            const unsigned long long key = ((unsigned long long)ehb_order_key(zw) << 32) | id;
-            unsigned long long* dst = pl + (py - ry0) * EHB_RS + (px - rx0);
-            if (key < *dst) atomicMin(dst, key);
-        }
-    }
-}
+#define EHB_PLANES_BYTES(pmax) ((((size_t)(pmax) * EHB_NP * 8) + 15) & ~(size_t)15)
+#define EHB_SUM_BYTES ((((size_t)EHB_NP * 4) + 15) & ~(size_t)15)
+#define EHB_BATCH 256
+#define EHB_WQ 128           // per-warp queue of covered samples
+#define EHB_PAIRQ (2 * EHB_NP)
 
 struct EhbRasterSmem {
     float mvp[EHB_MAX_LINKS * 16];
@@ -321,56 +284,96 @@ struct EhbRasterSmem {
     uint32_t lstart[EHB_MAX_LINKS];
     uint32_t lcnt[EHB_MAX_LINKS];
     int slotOf[EHB_MAX_LINKS];    // link -> plane slot in the current round
-    uint32_t big[EHB_BIGQ];
-    int nbig;
+    int warpTot[EHB_THREADS / 32];
     int nP;
     int work;
     unsigned int nTiles;
+    int qn;                       // pair queue length
 };
 
-// antialiased value of one link at pixel (px,py); lx,ly = position inside the plane
-__device__ __forceinline__ float ehb_aa_out(const unsigned long long* pl, const EhbLink& lk, const float* m, int px,
-                                            int py, int lx, int ly, int H, int W)
+union EhbOverlay {
+    struct {
+        EhbRec rec[EHB_BATCH];
+        float clip[EHB_BATCH][12];
+        int off[EHB_BATCH + 1];
+        uint32_t wq[EHB_THREADS / 32][EHB_WQ];
+    } r;
+    struct {
+        float alpha[2][EHB_NP];
+        uint32_t pairq[EHB_PAIRQ];
+    } a;
+};
+
+__device__ __forceinline__ void ehb_shade_entry(uint32_t ent, const EhbOverlay& ov, unsigned long long* planes,
+                                                int rx0, int ry0, float xs, float xo, float ys, float yo)
 {
-    const int idx = ly * EHB_RS + lx;
-    const unsigned long long k = pl[idx];
-    const bool c = k != EHB_EMPTY;
-    const float cf = c ? 1.f : 0.f;
-    float o = cf;
-    int di;
-    if (px < W - 1) {
-        const unsigned long long k1 = pl[idx + 1];
-        const bool c1 = k1 != EHB_EMPTY;
-        if (c1 != c) {
-            const float a = ehb_aa_pair(lk, m, (int)(uint32_t)(c ? k : k1), c ? 0 : 1, px, py, 0, H, W, &di);
-            if (a > 0.f) o += a * ((c1 ? 1.f : 0.f) - cf);
+    const int t = ent >> 12, lx = (ent >> 6) & 63, ly = ent & 63;
+    const float* c = ov.r.clip[t];
+    const float4 a = *reinterpret_cast<const float4*>(c), b = *reinterpret_cast<const float4*>(c + 4),
+                 d = *reinterpret_cast<const float4*>(c + 8);
+    const float p0[4] = {a.x, a.y, a.z, a.w}, p1[4] = {b.x, b.y, b.z, b.w}, p2[4] = {d.x, d.y, d.z, d.w};
+    const float fx = xs * (float)(rx0 + lx) + xo, fy = ys * (float)(ry0 + ly) + yo;
+    const float zw = ehb_shade_zw(p0, p1, p2, fx, fy);
+    const EhbRec& r = ov.r.rec[t];
+    const unsigned long long key = ((unsigned long long)ehb_order_key(zw) << 32) | r.id;
+    unsigned long long* dst = planes + r.slot * EHB_NP + ly * EHB_RS + lx;
+    if (key < *dst) atomicMin(dst, key);
+}
+
+// Sweep this thread's chunk [s, s_end) of the batch's flat sample space; `iters` is the block-uniform trip count.
+template <typename I>
+__device__ __forceinline__ void ehb_sweep(const EhbOverlay& ov, uint32_t* wq, int& wqn, int s, int s_end, int iters,
+                                          int lane, unsigned long long* planes, int rx0, int ry0, float xs, float xo,
+                                          float ys, float yo)
+{
+    int t = 0, dx = 0, dy = 0, w = 1, rem = 0, lx0 = 0, ly0 = 0;
+    I C0 = 0, C1 = 0, C2 = 0, R0 = 0, R1 = 0, R2 = 0, ax0 = 0, ax1 = 0, ax2 = 0, ay0 = 0, ay1 = 0, ay2 = 0;
+    I t0 = 0, t1 = 0, t2 = 0;
+    auto load = [&](int loc) {
+        const EhbRec& r = ov.r.rec[t];
+        w = r.w;
+        lx0 = r.lx; ly0 = r.ly;
+        dy = loc / w; dx = loc - dy * w;
+        rem = (int)r.w * (int)r.h - loc;
+        ax0 = (I)-16 * (I)r.ey[0]; ax1 = (I)-16 * (I)r.ey[1]; ax2 = (I)-16 * (I)r.ey[2];
+        ay0 = (I)16 * (I)r.ex[0]; ay1 = (I)16 * (I)r.ex[1]; ay2 = (I)16 * (I)r.ex[2];
+        R0 = (I)r.E[0] + ay0 * (I)dy; R1 = (I)r.E[1] + ay1 * (I)dy; R2 = (I)r.E[2] + ay2 * (I)dy;
+        C0 = R0 + ax0 * (I)dx; C1 = R1 + ax1 * (I)dx; C2 = R2 + ax2 * (I)dx;
+        t0 = r.thr & 1; t1 = (r.thr >> 1) & 1; t2 = (r.thr >> 2) & 1;
+    };
+    if (s < s_end) {
+        int lo = 0, hi = EHB_BATCH;   // last t with off[t] <= s
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (ov.r.off[mid] <= s) lo = mid; else hi = mid;
+        }
+        t = lo;
+        load(s - ov.r.off[t]);
+    }
+    for (int it = 0; it < iters; it++) {
+        const bool act = s < s_end;
+        const bool cov = act && C0 >= t0 && C1 >= t1 && C2 >= t2;
+        const unsigned bal = __ballot_sync(0xffffffffu, cov);
+        if (bal) {
+            if (wqn + 32 > EHB_WQ) {   // drain the warp's queue with all lanes busy
+                __syncwarp();
+                for (int j = lane; j < wqn; j += 32) ehb_shade_entry(wq[j], ov, planes, rx0, ry0, xs, xo, ys, yo);
+                __syncwarp();
+                wqn = 0;
+            }
+            if (cov) wq[wqn + __popc(bal & ((1u << lane) - 1u))] = ((uint32_t)t << 12) | ((uint32_t)(lx0 + dx) << 6) | (uint32_t)(ly0 + dy);
+            wqn += __popc(bal);
+        }
+        if (act) {
+            s++; rem--; dx++;
+            C0 += ax0; C1 += ax1; C2 += ax2;
+            if (dx == w) { dx = 0; dy++; R0 += ay0; R1 += ay1; R2 += ay2; C0 = R0; C1 = R1; C2 = R2; }
+            if (rem == 0 && s < s_end) {
+                do { t++; } while (ov.r.off[t + 1] == ov.r.off[t]);
+                load(0);
+            }
         }
     }
-    if (py < H - 1) {
-        const unsigned long long k1 = pl[idx + EHB_RS];
-        const bool c1 = k1 != EHB_EMPTY;
-        if (c1 != c) {
-            const float a = ehb_aa_pair(lk, m, (int)(uint32_t)(c ? k : k1), c ? 0 : 1, px, py, 1, H, W, &di);
-            if (a > 0.f) o += a * ((c1 ? 1.f : 0.f) - cf);
-        }
-    }
-    if (px > 0) {
-        const unsigned long long k0 = pl[idx - 1];
-        const bool c0 = k0 != EHB_EMPTY;
-        if (c0 != c) {
-            const float a = ehb_aa_pair(lk, m, (int)(uint32_t)(c0 ? k0 : k), c0 ? 0 : 1, px - 1, py, 0, H, W, &di);
-            if (!(a > 0.f) && a != 0.f) o += a * (cf - (c0 ? 1.f : 0.f));
-        }
-    }
-    if (py > 0) {
-        const unsigned long long k0 = pl[idx - EHB_RS];
-        const bool c0 = k0 != EHB_EMPTY;
-        if (c0 != c) {
-            const float a = ehb_aa_pair(lk, m, (int)(uint32_t)(c0 ? k0 : k), c0 ? 0 : 1, px, py - 1, 1, H, W, &di);
-            if (!(a > 0.f) && a != 0.f) o += a * (cf - (c0 ? 1.f : 0.f));
-        }
-    }
-    return o;
 }
 
 template <int PMAX>
@@ -379,11 +382,14 @@ __global__ void __launch_bounds__(EHB_THREADS) ehb_k_raster(const __grid_constan
 {
     extern __shared__ __align__(16) unsigned char ehb_smem_raw[];
     unsigned long long* planes = reinterpret_cast<unsigned long long*>(ehb_smem_raw);
-    float* sumpl = reinterpret_cast<float*>(planes + PMAX * EHB_NP);
-    EhbRasterSmem& sm = *reinterpret_cast<EhbRasterSmem*>(sumpl + ((EHB_NP + 3) & ~3));
+    float* sumpl = reinterpret_cast<float*>(ehb_smem_raw + EHB_PLANES_BYTES(PMAX));
+    EhbOverlay& ov = *reinterpret_cast<EhbOverlay*>(ehb_smem_raw + EHB_PLANES_BYTES(PMAX) + EHB_SUM_BYTES);
+    EhbRasterSmem& sm = *reinterpret_cast<EhbRasterSmem*>(reinterpret_cast<unsigned char*>(&ov) + ((sizeof(EhbOverlay) + 15) & ~15));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = p.H, W = p.W;
     const bool perLink = p.Lk != 1;
+    const float xs = 2.f / (float)W, xo = 1.f / (float)W - 1.f;
+    const float ys = 2.f / (float)H, yo = 1.f / (float)H - 1.f;
 
     for (;;) {
         if (tid == 0) {
@@ -410,7 +416,7 @@ __global__ void __launch_bounds__(EHB_THREADS) ehb_k_raster(const __grid_constan
                 sm.lstart[k] = p.start[bin0 + lane];
                 sm.lcnt[k] = c;
             }
-            if (lane == 0) { sm.nP = __popc(b); sm.nbig = 0; }
+            if (lane == 0) sm.nP = __popc(b);
         }
         for (int i = tid; i < p.L * 16; i += EHB_THREADS) sm.mvp[i] = __ldg(p.mvp + (size_t)item * p.L * 16 + i);
         __syncthreads();
@@ -428,45 +434,158 @@ __global__ void __launch_bounds__(EHB_THREADS) ehb_k_raster(const __grid_constan
             if (tid < EHB_MAX_LINKS) sm.slotOf[tid] = 0;
             __syncthreads();
             if (perLink && tid < k1 - k0) sm.slotOf[sm.links[k0 + tid]] = tid;
-            if (tid == 0) sm.nbig = 0;
-            __syncthreads();
             const uint32_t lo = sm.lstart[k0];
             const uint32_t n = sm.lstart[k1 - 1] + sm.lcnt[k1 - 1] - lo;
-            for (uint32_t i = tid; i < n; i += EHB_THREADS) {
-                const uint32_t e = __ldg(p.pairs + lo + i);
-                const int l = e >> EHB_LINK_SHIFT;
-                const int f = e & EHB_FACE_MASK;
-                EhbTri s;
-                if (ehb_tri_setup(rb.link[l], sm.mvp + 16 * l, f, H, W, s)) continue;
-                const int xlo = max(s.pxlo, rx0), xhi = min(s.pxhi, rx1);
-                const int ylo = max(s.pylo, ry0), yhi = min(s.pyhi, ry1);
-                if (xlo > xhi || ylo > yhi) continue;
-                if ((xhi - xlo + 1) * (yhi - ylo + 1) > EHB_BIG_SAMPLES) {
-                    const int k = atomicAdd(&sm.nbig, 1);
-                    if (k < EHB_BIGQ) { sm.big[k] = e; continue; }
+            int wqn = 0;
+            uint32_t* wq = ov.r.wq[warp];
+            for (uint32_t b0 = 0; b0 < n; b0 += EHB_BATCH) {
+                __syncthreads();   // slotOf visible / previous batch's records no longer in use
+                // -- setup: one triangle per thread -> record
+                int ns = 0, wide = 0;
+                if (b0 + tid < n) {
+                    const uint32_t e = __ldg(p.pairs + lo + b0 + tid);
+                    const int l = e >> EHB_LINK_SHIFT;
+                    const int f = e & EHB_FACE_MASK;
+                    EhbTri s;
+                    if (ehb_tri_setup(rb.link[l], sm.mvp + 16 * l, f, H, W, s) == 0) {
+                        const int xlo = max(s.pxlo, rx0), xhi = min(s.pxhi, rx1);
+                        const int ylo = max(s.pylo, ry0), yhi = min(s.pyhi, ry1);
+                        if (xlo <= xhi && ylo <= yhi) {
+                            EhbRec& rc = ov.r.rec[tid];
+                            const int bx = 8 * W - 8, by = 8 * H - 8;
+                            const int sx = 16 * xlo - bx, sy = 16 * ylo - by;
+                            const int ex0 = s.x1 - s.x0, ey0 = s.y1 - s.y0, ex1 = s.x2 - s.x1, ey1 = s.y2 - s.y1,
+                                      ex2 = s.x0 - s.x2, ey2 = s.y0 - s.y2;
+                            rc.E[0] = (long long)ex0 * (sy - s.y0) - (long long)ey0 * (sx - s.x0);
+                            rc.E[1] = (long long)ex1 * (sy - s.y1) - (long long)ey1 * (sx - s.x1);
+                            rc.E[2] = (long long)ex2 * (sy - s.y2) - (long long)ey2 * (sx - s.x2);
+                            rc.ex[0] = ex0; rc.ex[1] = ex1; rc.ex[2] = ex2;
+                            rc.ey[0] = ey0; rc.ey[1] = ey1; rc.ey[2] = ey2;
+                            rc.w = (unsigned short)(xhi - xlo + 1); rc.h = (unsigned short)(yhi - ylo + 1);
+                            rc.lx = (unsigned char)(xlo - rx0); rc.ly = (unsigned char)(ylo - ry0);
+                            rc.slot = (unsigned char)sm.slotOf[l];
+                            rc.thr = (unsigned char)((ehb_edge_inclusive(ex0, ey0, p.rule) ? 0 : 1) |
+                                                     (ehb_edge_inclusive(ex1, ey1, p.rule) ? 0 : 2) |
+                                                     (ehb_edge_inclusive(ex2, ey2, p.rule) ? 0 : 4));
+                            rc.id = perLink ? (uint32_t)f : (uint32_t)(rb.foff[l] + f);
+                            float* cc = ov.r.clip[tid];
+#pragma unroll
+                            for (int i = 0; i < 4; i++) { cc[i] = s.c0[i]; cc[4 + i] = s.c1[i]; cc[8 + i] = s.c2[i]; }
+                            ns = (xhi - xlo + 1) * (yhi - ylo + 1);
+                            // 32-bit edge arithmetic is exact while every edge vector stays below 2^15 sub-pixel units
+                            const int ext = max(max(abs(ex0), abs(ex1)), max(max(abs(ex2), abs(ey0)), max(abs(ey1), abs(ey2))));
+                            wide = ext >= 32768;
+                        }
+                    }
                 }
-                unsigned long long* pl = planes + sm.slotOf[l] * EHB_NP;
-                const uint32_t id = perLink ? (uint32_t)f : (uint32_t)(rb.foff[l] + f);
-                const int ext = max(max(s.x0, max(s.x1, s.x2)) - min(s.x0, min(s.x1, s.x2)),
-                                    max(s.y0, max(s.y1, s.y2)) - min(s.y0, min(s.y1, s.y2)));
-                if (ext < 32768) ehb_cover_rows<int>(s, xlo, xhi, ylo, yhi, pl, rx0, ry0, id, H, W, p.rule);
-                else ehb_cover_rows<long long>(s, xlo, xhi, ylo, yhi, pl, rx0, ry0, id, H, W, p.rule);
+                // -- block scan of the candidate-sample counts
+                int inc = ns;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                if (lane == 31) sm.warpTot[warp] = inc;
+                const int anyWide = __syncthreads_or(wide);
+                int wbase = 0, total = 0;
+#pragma unroll
+                for (int i = 0; i < EHB_THREADS / 32; i++) {
+                    const int v = sm.warpTot[i];
+                    if (i < warp) wbase += v;
+                    total += v;
+                }
+                ov.r.off[tid] = wbase + inc - ns;
+                if (tid == 0) ov.r.off[EHB_BATCH] = total;
+                __syncthreads();
+                // -- balanced sweep of the flat sample space
+                const int chunk = (total + EHB_THREADS - 1) / EHB_THREADS;
+                const int s0 = min(tid * chunk, total), s1 = min(s0 + chunk, total);
+                if (anyWide) ehb_sweep<long long>(ov, wq, wqn, s0, s1, chunk, lane, planes, rx0, ry0, xs, xo, ys, yo);
+                else ehb_sweep<int>(ov, wq, wqn, s0, s1, chunk, lane, planes, rx0, ry0, xs, xo, ys, yo);
+                __syncwarp();
+                for (int j = lane; j < wqn; j += 32) ehb_shade_entry(wq[j], ov, planes, rx0, ry0, xs, xo, ys, yo);
+                __syncwarp();
+                wqn = 0;
             }
             __syncthreads();
-            const int nb = min(sm.nbig, EHB_BIGQ);
-            for (int k = warp; k < nb; k += EHB_THREADS / 32) {
-                const uint32_t e = sm.big[k];
-                const int l = e >> EHB_LINK_SHIFT;
-                const int f = e & EHB_FACE_MASK;
-                EhbTri s;
-                if (ehb_tri_setup(rb.link[l], sm.mvp + 16 * l, f, H, W, s)) continue;
-                const int xlo = max(s.pxlo, rx0), xhi = min(s.pxhi, rx1);
-                const int ylo = max(s.pylo, ry0), yhi = min(s.pyhi, ry1);
-                unsigned long long* pl = planes + sm.slotOf[l] * EHB_NP;
-                const uint32_t id = perLink ? (uint32_t)f : (uint32_t)(rb.foff[l] + f);
-                ehb_cover_warp(s, xlo, xhi, ylo, yhi, pl, rx0, ry0, id, H, W, p.rule, lane);
+        };
+
+        // ---- silhouette pairs of one plane -> queue.  Pair (q, d): q and its right (d=0) / upper (d=1) neighbour,
+        //      one covered and one empty.  fwd: every pair of the region (and alpha planes zeroed); bwd: pairs
+        //      whose first pixel is an interior pixel.
+        auto detect_pairs = [&](const unsigned long long* pl, bool fwd) {
+            if (tid == 0) sm.qn = 0;
+            __syncthreads();
+            const int rw = fwd ? (rx1 - rx0) : EHB_T, rh = fwd ? (ry1 - ry0) : EHB_T;   // first pixels visited
+            const int bx = fwd ? rx0 : x0, by = fwd ? ry0 : y0;
+            const int total = rw * rh;
+            for (int i0 = 0; i0 < total; i0 += EHB_THREADS) {
+                const int i = i0 + tid;
+                unsigned m = 0;
+                int idx = 0;
+                if (i < total) {
+                    const int qy = i / rw, qx = i - qy * rw;
+                    const int px = bx + qx, py = by + qy;
+                    idx = (py - ry0) * EHB_RS + (px - rx0);
+                    if (fwd) { ov.a.alpha[0][idx] = 0.f; ov.a.alpha[1][idx] = 0.f; }
+                    if (px >= 0 && py >= 0 && px < W && py < H) {
+                        const bool c0 = pl[idx] != EHB_EMPTY;
+                        if (px < W - 1 && (pl[idx + 1] != EHB_EMPTY) != c0) m |= 1u;
+                        if (py < H - 1 && (pl[idx + EHB_RS] != EHB_EMPTY) != c0) m |= 2u;
+                    }
+                }
+                const unsigned b0 = __ballot_sync(0xffffffffu, m & 1u), b1 = __ballot_sync(0xffffffffu, m & 2u);
+                const int n0 = __popc(b0), n1 = __popc(b1);
+                int base = 0;
+                if (lane == 0 && n0 + n1) base = atomicAdd(&sm.qn, n0 + n1);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (m & 1u) ov.a.pairq[base + __popc(b0 & ((1u << lane) - 1u))] = (uint32_t)idx << 1;
+                if (m & 2u) ov.a.pairq[base + n0 + __popc(b1 & ((1u << lane) - 1u))] = ((uint32_t)idx << 1) | 1u;
             }
             __syncthreads();
+        };
+
+        // ---- antialias forward of the links resident in the planes: sumpl += per-link antialiased value ------
+        auto aa_forward_round = [&](int r) {
+            const int k0 = r * PMAX, k1 = min(nP, k0 + PMAX);
+            for (int k = k0; k < k1; k++) {
+                const int l = sm.links[k];
+                const EhbLink& lk = rb.link[l];
+                const float* m = sm.mvp + 16 * l;
+                const unsigned long long* pl = planes + (k - k0) * EHB_NP;
+                detect_pairs(pl, true);
+                const int qn = sm.qn;
+                for (int j = tid; j < qn; j += EHB_THREADS) {
+                    const uint32_t e = ov.a.pairq[j];
+                    const int d = e & 1, idx = e >> 1;
+                    const int ly = idx / EHB_RS, lx = idx - ly * EHB_RS;
+                    const unsigned long long ka = pl[idx], kb = pl[idx + (d ? EHB_RS : 1)];
+                    const bool c0 = ka != EHB_EMPTY;
+                    int di;
+                    ov.a.alpha[d][idx] = ehb_aa_pair(lk, m, (int)(uint32_t)(c0 ? ka : kb), c0 ? 0 : 1, rx0 + lx, ry0 + ly,
+                                                     d, H, W, &di);
+                }
+                __syncthreads();
+                for (int i = tid; i < ow * ow; i += EHB_THREADS) {
+                    const int qy = i / ow, qx = i - qy * ow;
+                    const int px = x0 + qx, py = y0 + qy;
+                    if (px >= W || py >= H) continue;
+                    const int idx = (py - ry0) * EHB_RS + (px - rx0);
+                    const float cf = pl[idx] != EHB_EMPTY ? 1.f : 0.f;
+                    float o = cf, a;
+                    // colour, pair(p,p+x), pair(p,p+y), pair(p-x,p), pair(p-y,p): the receiving pixel is p0 when alpha > 0
+                    a = ov.a.alpha[0][idx];
+                    if (a > 0.f) o += a * ((pl[idx + 1] != EHB_EMPTY ? 1.f : 0.f) - cf);
+                    a = ov.a.alpha[1][idx];
+                    if (a > 0.f) o += a * ((pl[idx + EHB_RS] != EHB_EMPTY ? 1.f : 0.f) - cf);
+                    a = ov.a.alpha[0][idx - 1];
+                    if (!(a > 0.f) && a != 0.f) o += a * (cf - (pl[idx - 1] != EHB_EMPTY ? 1.f : 0.f));
+                    a = ov.a.alpha[1][idx - EHB_RS];
+                    if (!(a > 0.f) && a != 0.f) o += a * (cf - (pl[idx - EHB_RS] != EHB_EMPTY ? 1.f : 0.f));
+                    sumpl[idx] = sumpl[idx] + o;   // links are added in link order (rb_solver.py:68); absent links add 0
+                }
+                __syncthreads();
+            }
         };
 
         // ---- antialias backward of the links resident in the planes ----------------------------------------
@@ -477,51 +596,45 @@ __global__ void __launch_bounds__(EHB_THREADS) ehb_k_raster(const __grid_constan
                 const EhbLink& lk = rb.link[l];
                 const float* m = sm.mvp + 16 * l;
                 const unsigned long long* pl = planes + (k - k0) * EHB_NP;
+                detect_pairs(pl, false);
+                const int qn = sm.qn;
                 double acc[12];
 #pragma unroll
                 for (int i = 0; i < 12; i++) acc[i] = 0.0;
                 bool had = false;
-                for (int i = tid; i < EHB_T * EHB_T; i += EHB_THREADS) {
-                    const int px = x0 + (i & 31), py = y0 + (i >> 5);
-                    if (px >= W || py >= H) continue;
-                    const int idx = (py - ry0) * EHB_RS + (px - rx0);
-                    const unsigned long long ka = pl[idx];
+                for (int j = tid; j < qn; j += EHB_THREADS) {
+                    const uint32_t e = ov.a.pairq[j];
+                    const int d = e & 1, idx = e >> 1, idx1 = idx + (d ? EHB_RS : 1);
+                    const int ly = idx / EHB_RS, lx = idx - ly * EHB_RS;
+                    const int px = rx0 + lx, py = ry0 + ly;
+                    const unsigned long long ka = pl[idx], kb = pl[idx1];
                     const bool c0 = ka != EHB_EMPTY;
-#pragma unroll 1
-                    for (int d = 0; d < 2; d++) {
-                        if (d == 0 ? (px >= W - 1) : (py >= H - 1)) continue;
-                        const int idx1 = idx + (d ? EHB_RS : 1);
-                        const unsigned long long kb = pl[idx1];
-                        const bool c1 = kb != EHB_EMPTY;
-                        if (c0 == c1) continue;
-                        const int side = c0 ? 0 : 1;
-                        const int t = (int)(uint32_t)(c0 ? ka : kb);
-                        int di;
-                        const float al = ehb_aa_pair(lk, m, t, side, px, py, d, H, W, &di);
-                        if (al == 0.f) continue;
-                        const float g = sumpl[al > 0.f ? idx : idx1];
-                        const float dd = g * ((c1 ? 1.f : 0.f) - (c0 ? 1.f : 0.f));
-                        if (dd == 0.f) continue;
-                        int vi1, vi2;
-                        float g1[3], g2[3];
-                        ehb_aa_pair_grad(lk, m, t, side, di, al, dd, px, py, d, H, W, &vi1, &vi2, g1, g2);
-                        const float4 va = __ldg(lk.verts + vi1), vb = __ldg(lk.verts + vi2);
-                        const double ha[4] = {(double)va.x, (double)va.y, (double)va.z, 1.0};
-                        const double hb[4] = {(double)vb.x, (double)vb.y, (double)vb.z, 1.0};
+                    const int side = c0 ? 0 : 1;
+                    const int t = (int)(uint32_t)(c0 ? ka : kb);
+                    int di;
+                    const float al = ehb_aa_pair(lk, m, t, side, px, py, d, H, W, &di);
+                    if (al == 0.f) continue;
+                    const float g = sumpl[al > 0.f ? idx : idx1];
+                    const float dd = g * (c0 ? -1.f : 1.f);   // g * (c1 - c0)
+                    if (dd == 0.f) continue;
+                    int vi1, vi2;
+                    float g1[3], g2[3];
+                    ehb_aa_pair_grad(lk, m, t, side, di, al, dd, px, py, d, H, W, &vi1, &vi2, g1, g2);
+                    const float4 va = __ldg(lk.verts + vi1), vb = __ldg(lk.verts + vi2);
+                    const double ha[4] = {(double)va.x, (double)va.y, (double)va.z, 1.0};
+                    const double hb[4] = {(double)vb.x, (double)vb.y, (double)vb.z, 1.0};
 #pragma unroll
-                        for (int rr = 0; rr < 3; rr++)
+                    for (int rr = 0; rr < 3; rr++)
 #pragma unroll
-                            for (int c = 0; c < 4; c++)
-                                acc[4 * rr + c] += (double)g1[rr] * ha[c] + (double)g2[rr] * hb[c];
-                        had = true;
-                        if (p.gpos) {
-                            atomicAdd(p.gpos + 4 * (size_t)vi1 + 0, g1[0]);
-                            atomicAdd(p.gpos + 4 * (size_t)vi1 + 1, g1[1]);
-                            atomicAdd(p.gpos + 4 * (size_t)vi1 + 3, g1[2]);
-                            atomicAdd(p.gpos + 4 * (size_t)vi2 + 0, g2[0]);
-                            atomicAdd(p.gpos + 4 * (size_t)vi2 + 1, g2[1]);
-                            atomicAdd(p.gpos + 4 * (size_t)vi2 + 3, g2[2]);
-                        }
+                        for (int c = 0; c < 4; c++) acc[4 * rr + c] += (double)g1[rr] * ha[c] + (double)g2[rr] * hb[c];
+                    had = true;
+                    if (p.gpos) {
+                        atomicAdd(p.gpos + 4 * (size_t)vi1 + 0, g1[0]);
+                        atomicAdd(p.gpos + 4 * (size_t)vi1 + 1, g1[1]);
+                        atomicAdd(p.gpos + 4 * (size_t)vi1 + 3, g1[2]);
+                        atomicAdd(p.gpos + 4 * (size_t)vi2 + 0, g2[0]);
+                        atomicAdd(p.gpos + 4 * (size_t)vi2 + 1, g2[1]);
+                        atomicAdd(p.gpos + 4 * (size_t)vi2 + 3, g2[2]);
                     }
                 }
                 if (__any_sync(0xffffffffu, had)) {
@@ -533,6 +646,7 @@ __global__ void __launch_bounds__(EHB_THREADS) ehb_k_raster(const __grid_constan
                         if (lane == 0 && v != 0.0) atomicAdd(dst + (i < 8 ? i : i + 4), v);
                     }
                 }
+                __syncthreads();
             }
         };
 
@@ -541,24 +655,7 @@ __global__ void __launch_bounds__(EHB_THREADS) ehb_k_raster(const __grid_constan
             for (int i = tid; i < EHB_NP; i += EHB_THREADS) sumpl[i] = 0.f;
         for (int r = 0; r < nR; r++) {
             raster_round(r);
-            if (needAA) {
-                const int k0 = r * PMAX, k1 = min(nP, k0 + PMAX);
-                for (int i = tid; i < ow * ow; i += EHB_THREADS) {
-                    const int qx = i % ow, qy = i / ow;
-                    const int px = x0 + qx, py = y0 + qy;
-                    if (px >= W || py >= H) continue;
-                    const int lx = px - rx0, ly = py - ry0;
-                    float a = sumpl[ly * EHB_RS + lx];
-                    for (int k = k0; k < k1; k++) {
-                        const int l = sm.links[k];
-                        const float o = ehb_aa_out(planes + (k - k0) * EHB_NP, rb.link[l], sm.mvp + 16 * l, px, py, lx,
-                                                   ly, H, W);
-                        a = a + o;  // links are added in link order (rb_solver.py:68); absent links add exactly 0
-                    }
-                    sumpl[ly * EHB_RS + lx] = a;
-                }
-                __syncthreads();
-            }
+            if (needAA) aa_forward_round(r);
         }
 
         if (p.mode == EHB_MODE_UNION) {
@@ -574,7 +671,7 @@ __global__ void __launch_bounds__(EHB_THREADS) ehb_k_raster(const __grid_constan
             double lacc = 0.0;
             const bool haveRef = p.ref != nullptr || p.ref_u8 != nullptr;
             for (int i = tid; i < ow * ow; i += EHB_THREADS) {
-                const int qx = i % ow, qy = i / ow;
+                const int qy = i / ow, qx = i - qy * ow;
                 const int px = x0 + qx, py = y0 + qy;
                 if (px >= W || py >= H) continue;
                 const int idx = (py - ry0) * EHB_RS + (px - rx0);
@@ -610,7 +707,6 @@ __global__ void __launch_bounds__(EHB_THREADS) ehb_k_raster(const __grid_constan
             for (int r = 0; r < nR; r++) {
                 if (nR > 1) raster_round(r);
                 backward_round(r);
-                if (nR > 1) __syncthreads();
             }
         }
         __syncthreads();

@@ -64,6 +64,11 @@ EHB_API int ehb_ctx_reserve(ehb_ctx_t ctx, int n_items, int n_links, int max_fac
 EHB_API int ehb_ctx_set_fill_rule(ehb_ctx_t ctx, int rule);
 /* Doubles the triangle/tile pair capacity used for later launches (call after EHB_FLAG_PAIR_OVERFLOW). */
 EHB_API int ehb_ctx_grow_pairs(ehb_ctx_t ctx);
+/* Per-kernel timing for benchmarks: while enabled every pass records CUDA events around its four kernels on the
+ * caller's stream.  ehb_ctx_kernel_times synchronises, returns the summed milliseconds of
+ * {count, alloc, fill, raster} over the passes recorded since the last query, and their number. */
+EHB_API int ehb_ctx_profile(ehb_ctx_t ctx, int enable);
+EHB_API int ehb_ctx_kernel_times(ehb_ctx_t ctx, double* ms4, long long* n_passes);
 /* Synchronises the device, returns and clears the sticky flags, reports triangles skipped for clipping. */
 EHB_API int ehb_ctx_status(ehb_ctx_t ctx, unsigned* flags, long long* n_need_clip);
 
@@ -115,6 +120,13 @@ EHB_API int ehb_explore_scores(ehb_ctx_t ctx, const int* mesh_ids, int L, int Q,
  * g_mvp f64[B*L*16] back and synchronises the stream. */
 EHB_API int ehb_solver_step_host(ehb_ctx_t ctx, const int* mesh_ids, int L, int B, const float* mvp_host,
                          const float* ref_dev, int H, int W, double* loss_host, double* g_mvp_host, void* stream);
+
+/* Fully host-facing step: reference masks come from HOST memory as bytes (non-zero = 1; what the dataset holds
+ * before `.float()`, easyhec/data/datasets/xarm_real.py:36) and are copied to the device inside the call, like
+ * the reference trainer's per-step `to_cuda(batch)` (easyhec/trainer/rbsolver.py:31). */
+EHB_API int ehb_solver_step_host_u8(ehb_ctx_t ctx, const int* mesh_ids, int L, int B, const float* mvp_host,
+                            const uint8_t* ref_u8_host, int H, int W, double* loss_host, double* g_mvp_host,
+                            void* stream);
 
 /* Number of kernels this library has launched on the context since creation (for launch accounting). */
 EHB_API long long ehb_launch_count(ehb_ctx_t ctx);
