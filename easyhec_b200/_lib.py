@@ -13,7 +13,7 @@ import torch
 __all__ = ["EhbError", "lib", "Context", "library_path"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libehb.so")
+_SO = os.environ.get("EHB_LIB") or os.path.join(_HERE, "libehb.so")
 _lib = None
 
 EHB_FLAG_PAIR_OVERFLOW = 1

@@ -64,10 +64,11 @@ struct DevBuf {
 struct Ctx {
     int device = 0;
     int nSM = 148;
-    int occ1 = 2, occF = 2;           // resident raster CTAs per SM (single-plane / fused instantiation)
+    int occ = 4;                      // resident raster CTAs per SM
     int rule = 0;
     std::vector<Mesh> meshes;
     DevBuf<uint32_t> range, cnt, start, cur, tileList, pairs;
+    DevBuf<EhbPairEnt> spill;         // per raster CTA: overflow of the shared-memory silhouette-pair list
     EhbCounters* ctr = nullptr;
     EhbCounters* ctrHost = nullptr;   // pinned
     // staging for the host-buffer entry points
@@ -178,9 +179,8 @@ __global__ void ehb_k_variance_finish(const unsigned long long* __restrict__ num
     if (q < Q) score[q] = C > 1 ? (double)num[q] / ((double)C * (double)(C - 1)) : 0.0;
 }
 
-constexpr int PMAX_FUSED = 6;
-
-size_t raster_smem(int pmax) { return EHB_PLANES_BYTES(pmax) + EHB_SUM_BYTES + ((sizeof(EhbOverlay) + 15) & ~15) + sizeof(EhbRasterSmem); }
+size_t raster_smem() { return sizeof(EhbSmem); }
+constexpr int SPILL_PER_LINK = 2 * (EHB_RS - 1) * (EHB_RS - 1);   // most silhouette pairs one link can have in a tile
 
 struct Io {
     const float* ref = nullptr; const uint8_t* ref_u8 = nullptr;
@@ -209,6 +209,7 @@ int build_robot(Ctx* c, const int* mesh_ids, int L, EhbRobot& rb)
 int ensure_scratch(Ctx* c, int items, int Ftot, int ntiles, int Lk, bool capturing)
 {
     int r;
+    if ((r = c->spill.ensure((size_t)c->nSM * c->occ * SPILL_PER_LINK * Lk, capturing))) return r;
     if ((r = c->range.ensure((size_t)items * std::max(Ftot, 1), capturing))) return r;
     const size_t bins = (size_t)items * ntiles * Lk;
     if ((r = c->cnt.ensure(bins, capturing))) return r;
@@ -274,13 +275,8 @@ int run_pass(Ctx* c, const int* mesh_ids, int L, int items, const float* mvp_dev
     if (ev) cudaEventRecord(ev[2], st);
     ehb_k_fill<<<gt, 256, 0, st>>>(rb, p);
     if (ev) cudaEventRecord(ev[3], st);
-    if (unionMode || L == 1) {
-        const size_t sm = raster_smem(1);
-        ehb_k_raster<1><<<c->nSM * c->occ1, EHB_THREADS, sm, st>>>(rb, p);
-    } else {
-        const size_t sm = raster_smem(PMAX_FUSED);
-        ehb_k_raster<PMAX_FUSED><<<c->nSM * c->occF, EHB_THREADS, sm, st>>>(rb, p);
-    }
+    p.pairSpill = c->spill.p; p.spillCap = SPILL_PER_LINK * p.Lk;
+    ehb_k_raster<<<c->nSM * c->occ, EHB_RTHREADS, raster_smem(), st>>>(rb, p);
     if (ev) cudaEventRecord(ev[4], st);
     c->launches += 4;
     CU(cudaGetLastError());
@@ -313,11 +309,9 @@ int ehb_ctx_create(int device, ehb_ctx_t* out)
     CU(cudaMalloc((void**)&c->ctr, sizeof(EhbCounters)));
     CU(cudaMemset(c->ctr, 0, sizeof(EhbCounters)));
     CU(cudaMallocHost((void**)&c->ctrHost, sizeof(EhbCounters)));
-    CU(cudaFuncSetAttribute(ehb_k_raster<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem(1)));
-    CU(cudaFuncSetAttribute(ehb_k_raster<PMAX_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem(PMAX_FUSED)));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ1, ehb_k_raster<1>, EHB_THREADS, raster_smem(1)));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occF, ehb_k_raster<PMAX_FUSED>, EHB_THREADS, raster_smem(PMAX_FUSED)));
-    c->occ1 = std::max(1, c->occ1); c->occF = std::max(1, c->occF);
+    CU(cudaFuncSetAttribute(ehb_k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem()));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ, ehb_k_raster, EHB_RTHREADS, raster_smem()));
+    c->occ = std::max(1, c->occ);
     *out = c;
     return EHB_OK;
 }
@@ -329,7 +323,7 @@ int ehb_ctx_destroy(ehb_ctx_t h)
     DeviceGuard guard(c->device);
     cudaDeviceSynchronize();
     for (auto& m : c->meshes) if (m.live) { cudaFree(m.verts); cudaFree(m.faces); cudaFree(m.opp); }
-    c->range.release(); c->cnt.release(); c->start.release(); c->cur.release(); c->tileList.release(); c->pairs.release();
+    c->spill.release(); c->range.release(); c->cnt.release(); c->start.release(); c->cur.release(); c->tileList.release(); c->pairs.release();
     c->mvpDev.release(); c->outDev.release(); c->refDev.release(); c->maskDev.release(); c->numDev.release();
     if (c->mvpPinned) cudaFreeHost(c->mvpPinned);
     if (c->outPinned) cudaFreeHost(c->outPinned);

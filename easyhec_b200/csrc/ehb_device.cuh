@@ -60,28 +60,33 @@ __device__ __forceinline__ uint32_t ehb_order_key(float f)
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-// 0: drawable, 1: culled, 2: needs the near/far clipper or lies outside the guard band (skipped, counted)
+// 0: drawable, 1: culled, 2: needs the near/far clipper or lies outside the guard band (skipped, counted).
+// TRUSTED: the triangle already passed this function for the same mvp (it was binned by k_count), so the
+// index / frustum / depth-range / guard-band tests are skipped; the arithmetic that is kept is identical.
+template <bool TRUSTED = false>
 __device__ __forceinline__ int ehb_tri_setup(const EhbLink& lk, const float* __restrict__ m, int f, int H, int W,
                                              EhbTri& s)
 {
     const int4 id = __ldg(lk.faces + f);
-    if ((unsigned)id.x >= (unsigned)lk.V || (unsigned)id.y >= (unsigned)lk.V || (unsigned)id.z >= (unsigned)lk.V)
+    if (!TRUSTED && ((unsigned)id.x >= (unsigned)lk.V || (unsigned)id.y >= (unsigned)lk.V || (unsigned)id.z >= (unsigned)lk.V))
         return 1;
     ehb_xform(__ldg(lk.verts + id.x), m, s.c0);
     ehb_xform(__ldg(lk.verts + id.y), m, s.c1);
     ehb_xform(__ldg(lk.verts + id.z), m, s.c2);
     const float *v0 = s.c0, *v1 = s.c1, *v2 = s.c2;
+    if (!TRUSTED)
     if ((v0[3] < v0[0] && v1[3] < v1[0] && v2[3] < v2[0]) || (v0[3] < -v0[0] && v1[3] < -v1[0] && v2[3] < -v2[0]) ||
         (v0[3] < v0[1] && v1[3] < v1[1] && v2[3] < v2[1]) || (v0[3] < -v0[1] && v1[3] < -v1[1] && v2[3] < -v2[1]) ||
         (v0[3] < v0[2] && v1[3] < v1[2] && v2[3] < v2[2]) || (v0[3] < -v0[2] && v1[3] < -v1[2] && v2[3] < -v2[2]))
         return 1;
-    if (!(v0[3] >= fabsf(v0[2]) && v1[3] >= fabsf(v1[2]) && v2[3] >= fabsf(v2[2]))) return 2;
+    if (!TRUSTED && !(v0[3] >= fabsf(v0[2]) && v1[3] >= fabsf(v1[2]) && v2[3] >= fabsf(v2[2]))) return 2;
     const float vsx = (float)(W * 8), vsy = (float)(H * 8);
     const float r0 = 1.0f / v0[3], r1 = 1.0f / v1[3], r2 = 1.0f / v2[3];
     int x0 = ehb_rni_sat(v0[0] * r0 * vsx), y0 = ehb_rni_sat(v0[1] * r0 * vsy);
     int x1 = ehb_rni_sat(v1[0] * r1 * vsx), y1 = ehb_rni_sat(v1[1] * r1 * vsy);
     int x2 = ehb_rni_sat(v2[0] * r2 * vsx), y2 = ehb_rni_sat(v2[1] * r2 * vsy);
     const int G = 1 << 28;
+    if (!TRUSTED)
     if (x0 > G || x0 < -G || y0 > G || y0 < -G || x1 > G || x1 < -G || y1 > G || y1 < -G || x2 > G || x2 < -G ||
         y2 > G || y2 < -G)
         return 2;
