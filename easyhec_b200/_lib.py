@@ -60,6 +60,12 @@ _PROTOS = {
                                        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ehb_solver_step_host_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                           C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ehb_pose_compose": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_void_p, C.c_void_p]),
+    "ehb_pose_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                    C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
+    "ehb_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
+                                C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
     "ehb_launch_count": (C.c_longlong, [C.c_void_p]),
 }
 
@@ -275,3 +281,36 @@ class Context:
             raise EhbError("ref_u8_host must be a contiguous uint8 CPU tensor")
         _check(lib().ehb_solver_step_host_u8(self._h, ids, L, B, _ptr(mvp_host), _ptr(ref_u8_host), H, W,
                                              _ptr(loss_host), _ptr(g_mvp_host), _stream(self.device)))
+
+    # -- pose chain ----------------------------------------------------------------------------------------
+    def pose_compose(self, dof, K, link_poses, H, W, out=None):
+        """dof (6,), K (3,3), link_poses (B,L,4,4) f32 -> mvp (B,L,4,4) f32"""
+        for t, n in ((dof, "dof"), (K, "K"), (link_poses, "link_poses")):
+            _dev_check(t, torch.float32, self.device, n)
+        B, L = link_poses.shape[0], link_poses.shape[1]
+        if out is None:
+            out = torch.empty((B, L, 4, 4), dtype=torch.float32, device=self.device)
+        _check(lib().ehb_pose_compose(self._h, _ptr(dof), _ptr(K), _ptr(link_poses), B, L, H, W, _ptr(out),
+                                      _stream(self.device)))
+        return out
+
+    def pose_backward(self, dof, K, link_poses, g_mvp, loss, H, W, grad_scale=1.0, loss_scale=None, out=None):
+        """-> out7 f32 (7,) = [grad_scale * dL/ddof, loss_scale * sum(loss)]"""
+        _dev_check(g_mvp, torch.float64, self.device, "g_mvp")
+        _dev_check(loss, torch.float64, self.device, "loss")
+        B, L = link_poses.shape[0], link_poses.shape[1]
+        if loss_scale is None:
+            loss_scale = 1.0 / B
+        if out is None:
+            out = torch.empty((7,), dtype=torch.float32, device=self.device)
+        _check(lib().ehb_pose_backward(self._h, _ptr(dof), _ptr(K), _ptr(link_poses), _ptr(g_mvp), _ptr(loss), B, L, H,
+                                       W, float(grad_scale), float(loss_scale), _ptr(out), _stream(self.device)))
+        return out
+
+    def adam_step(self, dof, g7, state, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, hist=None):
+        _dev_check(dof, torch.float32, self.device, "dof")
+        _dev_check(g7, torch.float32, self.device, "g7")
+        _dev_check(state, torch.float32, self.device, "state")
+        cap = 0 if hist is None else hist.shape[0]
+        _check(lib().ehb_adam_step(self._h, _ptr(dof), _ptr(g7), _ptr(state), lr, betas[0], betas[1], eps, weight_decay,
+                                   _ptr(hist), cap, _stream(self.device)))

@@ -6,6 +6,7 @@
 // fallback: every compute entry point enqueues CUDA kernels on the caller's stream or fails.
 #include "../../include/easyhec_b200.h"
 #include "ehb_kernels.cuh"
+#include "ehb_pose.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -627,6 +628,46 @@ int ehb_solver_step_host_u8(ehb_ctx_t h, const int* mesh_ids, int L, int B, cons
         unsigned int zero = 0;
         CU(cudaMemcpyAsync(&c->ctr->flags, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
     }
+    return EHB_OK;
+}
+
+int ehb_pose_compose(ehb_ctx_t h, const float* dof_dev, const float* K_dev, const float* link_poses_dev, int B, int L,
+                     int H, int W, float* mvp_dev, void* stream)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || !dof_dev || !K_dev || !link_poses_dev || !mvp_dev || B < 1 || L < 1) return fail(EHB_E_ARG, "bad pose_compose arguments");
+    DeviceGuard guard(c->device);
+    const int n = B * L;
+    ehb_k_pose_compose<<<std::min((n + 127) / 128, 64), 128, 0, (cudaStream_t)stream>>>(dof_dev, K_dev, link_poses_dev, n, H, W, mvp_dev);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    return EHB_OK;
+}
+
+int ehb_pose_backward(ehb_ctx_t h, const float* dof_dev, const float* K_dev, const float* link_poses_dev,
+                      const double* g_mvp_dev, const double* loss_dev, int B, int L, int H, int W, double grad_scale,
+                      double loss_scale, float* out7_dev, void* stream)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || !dof_dev || !K_dev || !link_poses_dev || !g_mvp_dev || !loss_dev || !out7_dev || B < 1 || L < 1)
+        return fail(EHB_E_ARG, "bad pose_backward arguments");
+    DeviceGuard guard(c->device);
+    ehb_k_pose_backward<<<1, 256, 0, (cudaStream_t)stream>>>(dof_dev, K_dev, link_poses_dev, g_mvp_dev, loss_dev, B, L, H, W,
+                                                             grad_scale, loss_scale, out7_dev);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    return EHB_OK;
+}
+
+int ehb_adam_step(ehb_ctx_t h, float* dof_dev, const float* g7_dev, float* state_dev, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, float* hist_dev, int hist_cap, void* stream)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || !dof_dev || !g7_dev || !state_dev) return fail(EHB_E_ARG, "bad adam arguments");
+    DeviceGuard guard(c->device);
+    ehb_k_adam<<<1, 32, 0, (cudaStream_t)stream>>>(dof_dev, g7_dev, state_dev, lr, beta1, beta2, eps, weight_decay, hist_dev, hist_cap);
+    c->launches += 1;
+    CU(cudaGetLastError());
     return EHB_OK;
 }
 

@@ -1,0 +1,138 @@
+"""Pose optimisation loop on the device: RBSolver's Adam iteration as one CUDA graph.
+
+The reference runs one Adam step per "epoch": zero_grad -> RBSolver.forward (B x L render_mask calls) ->
+backward -> Adam (easyhec/trainer/rbsolver.py:29-43, easyhec/solver/build.py:12-29: lr 3e-3, weight decay 5e-4
+as L2 on ``dof``).  Here one iteration is a fixed sequence of kernels
+
+    pose_compose -> [memset, count, alloc, fill, raster] -> pose_backward -> (all-reduce 7 floats) -> adam
+
+captured once into a CUDA graph and replayed; nothing returns to the host inside the loop.  When views are sharded
+over ranks (``torch.distributed``), each rank renders its own views and the only exchange is the 7-float
+all-reduce of (d loss/d dof, loss) -- the collective DDP performs for the reference (trainer/base.py:349).
+"""
+import numpy as np
+import torch
+
+from ._lib import Context
+from .se3 import dof_to_matrix, matrix_to_dof
+
+__all__ = ["PoseSolver", "shard_views"]
+
+
+def shard_views(n_views: int, rank: int, world: int):
+    """Round-robin view indices of one rank (views are independent given dof, rb_solver.py:60-72)."""
+    return list(range(rank, n_views, world))
+
+
+class PoseSolver:
+    def __init__(self, meshes, link_poses, K, masks_ref, init_Tc_c2b, H, W, lr=3e-3, weight_decay=5e-4,
+                 betas=(0.9, 0.999), eps=1e-8, device=None, group=None, n_views_global=None, use_graph=True,
+                 ctx=None, history=10000):
+        """meshes: list of (verts, faces) / Mesh;  link_poses (B,L,4,4);  K (3,3);  masks_ref (B,H,W) bool/u8/f32
+        -- this rank's views only;  n_views_global: total views over all ranks (defaults to B)."""
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.ctx = ctx or Context(self.device)
+        self.H, self.W = int(H), int(W)
+        self.mesh_ids = [self.ctx.register_mesh(*((m.vertices, m.faces) if hasattr(m, "vertices") else m))
+                         for m in meshes]
+        dev = self.device
+        self.link_poses = torch.as_tensor(np.asarray(link_poses), dtype=torch.float32).to(dev).contiguous()
+        self.K = torch.as_tensor(np.asarray(K), dtype=torch.float32).to(dev).contiguous()
+        ref = torch.as_tensor(np.asarray(masks_ref)) if not isinstance(masks_ref, torch.Tensor) else masks_ref
+        if ref.dtype == torch.bool:
+            ref = ref.to(torch.uint8)
+        if ref.dtype not in (torch.uint8, torch.float32):
+            ref = ref.float()
+        self.ref = ref.to(dev).contiguous()
+        self.B, self.L = self.link_poses.shape[0], self.link_poses.shape[1]
+        self.B_global = int(n_views_global or self.B)
+        self.group = group
+        self.world = torch.distributed.get_world_size(group) if (group is not None or (
+            torch.distributed.is_available() and torch.distributed.is_initialized())) else 1
+        self.lr, self.wd, self.betas, self.eps = float(lr), float(weight_decay), betas, float(eps)
+        self.dof = matrix_to_dof(torch.as_tensor(np.asarray(init_Tc_c2b), dtype=torch.float32)).to(dev).contiguous()
+        self.state = torch.zeros(13, dtype=torch.float32, device=dev)
+        self.hist = torch.zeros((history, 6), dtype=torch.float32, device=dev) if history else None
+        self.mvp = torch.empty((self.B, self.L, 4, 4), dtype=torch.float32, device=dev)
+        self.loss_b = torch.empty((self.B,), dtype=torch.float64, device=dev)
+        self.g_mvp = torch.empty((self.B, self.L, 4, 4), dtype=torch.float64, device=dev)
+        self.g7 = torch.zeros(7, dtype=torch.float32, device=dev)
+        self.masks = None
+        F = sum(self.ctx.mesh_info(i)[1] for i in self.mesh_ids)
+        self.ctx.reserve(self.B, self.L, F, self.H, self.W)
+        self.use_graph = use_graph
+        self._graph = None
+        self.iterations = 0
+
+    # one iteration, enqueued on the current stream
+    def _iteration(self):
+        c = self.ctx
+        c.pose_compose(self.dof, self.K, self.link_poses, self.H, self.W, out=self.mvp)
+        c.render_views_fused(self.mesh_ids, self.mvp, self.ref, self.H, self.W, backward=True,
+                             out=(self.masks, self.loss_b, self.g_mvp))
+        # fused kernel scaled by 1/B_local; rescale so that the sum over ranks is the global mean's gradient
+        c.pose_backward(self.dof, self.K, self.link_poses, self.g_mvp, self.loss_b, self.H, self.W,
+                        grad_scale=self.B / self.B_global, loss_scale=1.0 / self.B_global, out=self.g7)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.g7, group=self.group)
+        c.adam_step(self.dof, self.g7, self.state, self.lr, self.betas, self.eps, self.wd, hist=self.hist)
+
+    def _check_flags(self):
+        flags, _ = self.ctx.status()
+        if flags & 1:
+            self.ctx.grow_pairs()
+            return False
+        return True
+
+    def step(self, n: int = 1):
+        """Run n Adam iterations (no host synchronisation inside)."""
+        if self.iterations == 0:   # first iteration eagerly: sizes scratch, validates capacity
+            while True:
+                snap = (self.dof.clone(), self.state.clone())
+                self._iteration()
+                if self._check_flags():
+                    break
+                self.dof.copy_(snap[0]); self.state.copy_(snap[1])
+            self.iterations += 1
+            n -= 1
+        if n <= 0:
+            return
+        if self.use_graph and self._graph is None:
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            s = torch.cuda.Stream(self.device)
+            s.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(s):
+                snap = (self.dof.clone(), self.state.clone(), None if self.hist is None else self.hist.clone())
+                with torch.cuda.graph(g, stream=s):
+                    self._iteration()
+                # capture does not execute; nothing to restore, but keep the snapshot semantics explicit
+                del snap
+            torch.cuda.current_stream(self.device).wait_stream(s)
+            self._graph = g
+        for _ in range(n):
+            if self._graph is not None:
+                self._graph.replay()
+            else:
+                self._iteration()
+        self.iterations += n
+
+    @property
+    def loss(self) -> torch.Tensor:
+        """Mean mask loss of the last iteration (device scalar, before that iteration's update)."""
+        return self.g7[6]
+
+    def Tc_c2b(self) -> torch.Tensor:
+        return dof_to_matrix(self.dof.detach().cpu())
+
+    def history_ops(self) -> torch.Tensor:
+        n = int(self.state[12].item())
+        return self.hist[:n].clone() if self.hist is not None else torch.zeros(0, 6)
+
+    def pose_error(self, gt_Tc_c2b):
+        """(translation error in metres, rotation error in degrees) against a ground-truth pose."""
+        T = self.Tc_c2b().double().numpy()
+        G = np.asarray(gt_Tc_c2b, dtype=np.float64)
+        dR = T[:3, :3].T @ G[:3, :3]
+        ang = np.degrees(np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1)))
+        return float(np.linalg.norm(T[:3, 3] - G[:3, 3])), float(ang)

@@ -128,6 +128,22 @@ EHB_API int ehb_solver_step_host_u8(ehb_ctx_t ctx, const int* mesh_ids, int L, i
                             const uint8_t* ref_u8_host, int H, int W, double* loss_host, double* g_mvp_host,
                             void* stream);
 
+/* The pose chain of RBSolver around the rasterizer, on the device (no host round trip, CUDA-graph capturable):
+ *   ehb_pose_compose : dof f32[6] -> Tc_c2b = se3_exp_map(dof)^T (easyhec/utils/pytorch3d_se3.py:46-130, rb_solver.py:52)
+ *                      -> mvp[b,l] = K_to_projection(K,H,W) @ diag(1,-1,-1,1) @ Tc_c2b @ link_poses[b,l]   f32[B*L*16]
+ *   ehb_pose_backward: g_mvp f64[B*L*16], loss f64[B] -> out7 f32[7] = { grad_scale * d loss/d dof [6],
+ *                      loss_scale * sum_b loss_b }   (one rank's share; all-reduce out7 across ranks when sharding views)
+ *   ehb_adam_step    : torch.optim.Adam(lr, betas, eps, weight_decay as L2) on dof (easyhec/solver/build.py:12-29);
+ *                      state f32[13] = { m[6], v[6], step }; hist_dev (optional) f32[hist_cap*6] records dof before
+ *                      each update (RBSolver.history_ops, rb_solver.py:50-51). */
+EHB_API int ehb_pose_compose(ehb_ctx_t ctx, const float* dof_dev, const float* K_dev, const float* link_poses_dev, int B,
+                     int L, int H, int W, float* mvp_dev, void* stream);
+EHB_API int ehb_pose_backward(ehb_ctx_t ctx, const float* dof_dev, const float* K_dev, const float* link_poses_dev,
+                      const double* g_mvp_dev, const double* loss_dev, int B, int L, int H, int W, double grad_scale,
+                      double loss_scale, float* out7_dev, void* stream);
+EHB_API int ehb_adam_step(ehb_ctx_t ctx, float* dof_dev, const float* g7_dev, float* state_dev, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, float* hist_dev, int hist_cap, void* stream);
+
 /* Number of kernels this library has launched on the context since creation (for launch accounting). */
 EHB_API long long ehb_launch_count(ehb_ctx_t ctx);
 
