@@ -35,7 +35,7 @@ _PROTOS = {
     "ehb_ctx_destroy": (C.c_int, [C.c_void_p]),
     "ehb_ctx_reserve": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ehb_ctx_set_fill_rule": (C.c_int, [C.c_void_p, C.c_int]),
-    "ehb_ctx_grow_pairs": (C.c_int, [C.c_void_p]),
+    "ehb_ctx_grow_scratch": (C.c_int, [C.c_void_p]),
     "ehb_ctx_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "ehb_ctx_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "ehb_ctx_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint), C.POINTER(C.c_longlong)]),
@@ -169,8 +169,8 @@ class Context:
     def set_fill_rule(self, rule: int):
         _check(lib().ehb_ctx_set_fill_rule(self._h, rule))
 
-    def grow_pairs(self):
-        _check(lib().ehb_ctx_grow_pairs(self._h))
+    def grow_scratch(self):
+        _check(lib().ehb_ctx_grow_scratch(self._h))
 
     def status(self):
         """Synchronises; returns (flags, n_need_clip) and clears them."""
@@ -182,11 +182,11 @@ class Context:
         _check(lib().ehb_ctx_profile(self._h, int(bool(enable))))
 
     def kernel_times(self):
-        """-> ({count, alloc, fill, raster: summed ms}, passes) since the last query; synchronises."""
-        ms = (C.c_double * 4)()
+        """-> ({bbox, plan, clear, raster, tiles: summed ms}, passes) since the last query; synchronises."""
+        ms = (C.c_double * 5)()
         n = C.c_longlong()
         _check(lib().ehb_ctx_kernel_times(self._h, ms, C.byref(n)))
-        return dict(zip(("count", "alloc", "fill", "raster"), list(ms))), n.value
+        return dict(zip(("bbox", "plan", "clear", "raster", "tiles"), list(ms))), n.value
 
     def launch_count(self) -> int:
         return int(lib().ehb_launch_count(self._h))

@@ -65,11 +65,16 @@ struct DevBuf {
 struct Ctx {
     int device = 0;
     int nSM = 148;
-    int occ = 4;                      // resident raster CTAs per SM
+    int occ = 4;                      // resident k_tiles CTAs per SM
     int rule = 0;
     std::vector<Mesh> meshes;
-    DevBuf<uint32_t> range, cnt, start, cur, tileList, pairs;
-    DevBuf<EhbPairEnt> spill;         // per raster CTA: overflow of the shared-memory silhouette-pair list
+    DevBuf<int> bbraw;                // raw snapped bounding boxes, kept at the "empty" sentinel between passes
+    DevBuf<EhbPlane> plane;
+    DevBuf<unsigned long long> pool;  // depth planes of one pass, bump-allocated
+    DevBuf<uint32_t> tileList;
+    DevBuf<EhbRec> bigRec;
+    DevBuf<EhbUnit> units;
+    DevBuf<EhbPairEnt> spill;         // per k_tiles CTA: overflow of the shared-memory silhouette-pair list
     EhbCounters* ctr = nullptr;
     EhbCounters* ctrHost = nullptr;   // pinned
     // staging for the host-buffer entry points
@@ -83,7 +88,7 @@ struct Ctx {
     bool profiling = false;           // per-kernel CUDA events (ehb_ctx_profile)
     std::vector<cudaEvent_t> evPool;  // 5 events per profiled pass
     size_t evUsed = 0;
-    size_t pairFactor = 3;            // pair capacity = items * Ftot * pairFactor (+ slack); grown on overflow
+    double poolFactor = 2.0;          // plane pool = items * H * W * poolFactor entries (per-link mode); grown on overflow
 };
 
 struct DeviceGuard {
@@ -180,8 +185,16 @@ __global__ void ehb_k_variance_finish(const unsigned long long* __restrict__ num
     if (q < Q) score[q] = C > 1 ? (double)num[q] / ((double)C * (double)(C - 1)) : 0.0;
 }
 
-size_t raster_smem() { return sizeof(EhbSmem); }
+size_t tiles_smem() { return sizeof(EhbSmem); }
 constexpr int SPILL_PER_LINK = 2 * (EHB_RS - 1) * (EHB_RS - 1);   // most silhouette pairs one link can have in a tile
+constexpr int BIG_CAP = 1 << 17;     // deferred triangles per pass (16 MB of records)
+constexpr int UNIT_CAP = 1 << 19;
+
+__global__ void ehb_k_init_raw(int* raw, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        raw[i] = (i & 2) ? EHB_RAW_MAX : EHB_RAW_MIN;
+}
 
 struct Io {
     const float* ref = nullptr; const uint8_t* ref_u8 = nullptr;
@@ -203,21 +216,28 @@ int build_robot(Ctx* c, const int* mesh_ids, int L, EhbRobot& rb)
         rb.link[l].verts = m.verts; rb.link[l].faces = m.faces; rb.link[l].opp = m.opp;
         rb.link[l].V = m.V; rb.link[l].F = m.F;
         rb.foff[l + 1] = rb.foff[l] + m.F;
+        rb.voff[l + 1] = rb.voff[l] + m.V;
     }
     return EHB_OK;
 }
 
-int ensure_scratch(Ctx* c, int items, int Ftot, int ntiles, int Lk, bool capturing)
+int ensure_scratch(Ctx* c, int items, int L, int Lp, int H, int W, bool capturing)
 {
     int r;
-    if ((r = c->spill.ensure((size_t)c->nSM * c->occ * SPILL_PER_LINK * Lk, capturing))) return r;
-    if ((r = c->range.ensure((size_t)items * std::max(Ftot, 1), capturing))) return r;
-    const size_t bins = (size_t)items * ntiles * Lk;
-    if ((r = c->cnt.ensure(bins, capturing))) return r;
-    if ((r = c->start.ensure(bins, capturing))) return r;
-    if ((r = c->cur.ensure(bins, capturing))) return r;
+    const int ntiles = ((W + EHB_T - 1) / EHB_T) * ((H + EHB_T - 1) / EHB_T);
+    if ((r = c->spill.ensure((size_t)c->nSM * c->occ * SPILL_PER_LINK * L, capturing))) return r;
+    const size_t nraw = (size_t)items * Lp * 4;
+    if (nraw > c->bbraw.n) {
+        if ((r = c->bbraw.ensure(nraw, capturing))) return r;
+        ehb_k_init_raw<<<64, 256>>>(c->bbraw.p, c->bbraw.n);
+        CU(cudaDeviceSynchronize());
+    }
+    if ((r = c->plane.ensure((size_t)items * Lp, capturing))) return r;
     if ((r = c->tileList.ensure((size_t)items * ntiles, capturing))) return r;
-    if ((r = c->pairs.ensure((size_t)items * Ftot * c->pairFactor + 4096, capturing))) return r;
+    if ((r = c->bigRec.ensure((size_t)BIG_CAP, capturing))) return r;
+    if ((r = c->units.ensure((size_t)UNIT_CAP, capturing))) return r;
+    const double f = Lp == 1 ? 1.0 : std::min(c->poolFactor, (double)Lp);
+    if ((r = c->pool.ensure((size_t)((double)items * H * W * f) + 1024, capturing))) return r;
     return EHB_OK;
 }
 
@@ -234,12 +254,12 @@ int run_pass(Ctx* c, const int* mesh_ids, int L, int items, const float* mvp_dev
     EhbRobot rb;
     int r = build_robot(c, mesh_ids, L, rb);
     if (r) return r;
-    const bool unionMode = mode == EHB_MODE_UNION || mode == EHB_MODE_UNION_VAR;
+    const bool unionMode = mode == EHB_MODE_UNION;
     EhbParams p;
     memset(&p, 0, sizeof p);
     p.H = H; p.W = W;
     p.ntx = (W + EHB_T - 1) / EHB_T; p.nty = (H + EHB_T - 1) / EHB_T; p.ntiles = p.ntx * p.nty;
-    p.items = items; p.L = L; p.Lk = unionMode ? 1 : L; p.Ftot = rb.foff[L];
+    p.items = items; p.L = L; p.Lp = unionMode ? 1 : L; p.Ftot = rb.foff[L]; p.Vtot = rb.voff[L];
     switch (mode) {
     case EHB_MODE_FUSED: p.hlo = 1; p.hhi = io.do_bwd ? 2 : 1; break;
     case EHB_MODE_AA_FWD: p.hlo = 1; p.hhi = 1; break;
@@ -248,38 +268,45 @@ int run_pass(Ctx* c, const int* mesh_ids, int L, int items, const float* mvp_dev
     }
     p.mode = mode; p.rule = c->rule; p.do_bwd = io.do_bwd; p.clamp = io.clamp; p.invB = io.invB;
     const bool capturing = is_capturing(st);
-    if ((r = ensure_scratch(c, items, p.Ftot, p.ntiles, p.Lk, capturing))) return r;
+    if ((r = ensure_scratch(c, items, L, p.Lp, H, W, capturing))) return r;
     p.mvp = mvp_dev;
-    p.range = c->range.p; p.cnt = c->cnt.p; p.start = c->start.p; p.cur = c->cur.p; p.tileList = c->tileList.p;
-    p.pairs = c->pairs.p; p.pairCap = c->pairs.n; p.ctr = c->ctr;
+    p.bbraw = c->bbraw.p; p.plane = c->plane.p; p.pool = c->pool.p; p.poolCap = c->pool.n;
+    p.tileList = c->tileList.p; p.bigRec = c->bigRec.p; p.units = c->units.p; p.bigCap = BIG_CAP; p.unitCap = UNIT_CAP; p.ctr = c->ctr;
     p.ref = io.ref; p.ref_u8 = io.ref_u8; p.masks = io.masks; p.loss = io.loss; p.gmvp = io.gmvp; p.gpos = io.gpos;
-    p.dy = io.dy; p.out_u8 = io.out_u8; p.score = io.score; p.C = io.C;
+    p.dy = io.dy; p.out_u8 = io.out_u8;
+    p.pairSpill = c->spill.p; p.spillCap = SPILL_PER_LINK * L;
 
-    const size_t bins = (size_t)items * p.ntiles * p.Lk;
-    CU(cudaMemsetAsync(p.cnt, 0, bins * sizeof(uint32_t), st));
     cudaEvent_t* ev = nullptr;
     if (c->profiling && !capturing) {
-        if (c->evUsed + 5 > c->evPool.size()) {
+        if (c->evUsed + 6 > c->evPool.size()) {
             const size_t old = c->evPool.size();
-            c->evPool.resize(old + 5 * 256);
+            c->evPool.resize(old + 6 * 256);
             for (size_t i = old; i < c->evPool.size(); i++) CU(cudaEventCreate(&c->evPool[i]));
         }
         ev = &c->evPool[c->evUsed];
-        c->evUsed += 5;
+        c->evUsed += 6;
     }
-    const dim3 gt((unsigned)std::max(1, (p.Ftot + 255) / 256), (unsigned)items);
     if (ev) cudaEventRecord(ev[0], st);
-    ehb_k_count<<<gt, 256, 0, st>>>(rb, p);
+    ehb_k_bbox<<<dim3((unsigned)std::max(1, (p.Vtot + 255) / 256), (unsigned)items), 256, 0, st>>>(rb, p);
     if (ev) cudaEventRecord(ev[1], st);
-    const long long warps = (long long)items * p.ntiles;
-    ehb_k_alloc<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(p);
+    const int planBlocks = (items * p.Lp + 255) / 256;
+    const long long tileWarps = unionMode ? 0 : (long long)items * p.ntiles;
+    ehb_k_plan<<<(unsigned)(planBlocks + (tileWarps * 32 + 255) / 256), 256, 0, st>>>(p, planBlocks);
     if (ev) cudaEventRecord(ev[2], st);
-    ehb_k_fill<<<gt, 256, 0, st>>>(rb, p);
+    ehb_k_clear<<<c->nSM * 4, 256, 0, st>>>(p);
     if (ev) cudaEventRecord(ev[3], st);
-    p.pairSpill = c->spill.p; p.spillCap = SPILL_PER_LINK * p.Lk;
-    ehb_k_raster<<<c->nSM * c->occ, EHB_RTHREADS, raster_smem(), st>>>(rb, p);
+    ehb_k_raster<<<dim3((unsigned)std::max(1, (p.Ftot + EHB_RWARPS * 32 - 1) / (EHB_RWARPS * 32)), (unsigned)items),
+                   EHB_RWARPS * 32, 0, st>>>(rb, p);
+    ehb_k_raster_big<<<c->nSM * 4, 256, 0, st>>>(p);
     if (ev) cudaEventRecord(ev[4], st);
-    c->launches += 4;
+    if (unionMode) {
+        const int nq = ((W + 3) / 4) * H;
+        ehb_k_union_out<<<dim3((unsigned)std::min((nq + 255) / 256, 4 * c->nSM), (unsigned)items), 256, 0, st>>>(p);
+    } else {
+        ehb_k_tiles<<<c->nSM * c->occ, EHB_TTHREADS, tiles_smem(), st>>>(rb, p);
+    }
+    if (ev) cudaEventRecord(ev[5], st);
+    c->launches += 6;
     CU(cudaGetLastError());
     return EHB_OK;
 }
@@ -310,8 +337,8 @@ int ehb_ctx_create(int device, ehb_ctx_t* out)
     CU(cudaMalloc((void**)&c->ctr, sizeof(EhbCounters)));
     CU(cudaMemset(c->ctr, 0, sizeof(EhbCounters)));
     CU(cudaMallocHost((void**)&c->ctrHost, sizeof(EhbCounters)));
-    CU(cudaFuncSetAttribute(ehb_k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem()));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ, ehb_k_raster, EHB_RTHREADS, raster_smem()));
+    CU(cudaFuncSetAttribute(ehb_k_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiles_smem()));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ, ehb_k_tiles, EHB_TTHREADS, tiles_smem()));
     c->occ = std::max(1, c->occ);
     *out = c;
     return EHB_OK;
@@ -324,7 +351,7 @@ int ehb_ctx_destroy(ehb_ctx_t h)
     DeviceGuard guard(c->device);
     cudaDeviceSynchronize();
     for (auto& m : c->meshes) if (m.live) { cudaFree(m.verts); cudaFree(m.faces); cudaFree(m.opp); }
-    c->spill.release(); c->range.release(); c->cnt.release(); c->start.release(); c->cur.release(); c->tileList.release(); c->pairs.release();
+    c->spill.release(); c->bbraw.release(); c->plane.release(); c->pool.release(); c->tileList.release(); c->bigRec.release(); c->units.release();
     c->mvpDev.release(); c->outDev.release(); c->refDev.release(); c->maskDev.release(); c->numDev.release();
     if (c->mvpPinned) cudaFreeHost(c->mvpPinned);
     if (c->outPinned) cudaFreeHost(c->outPinned);
@@ -348,19 +375,18 @@ int ehb_ctx_reserve(ehb_ctx_t h, int n_items, int n_links, int max_faces, int H,
     Ctx* c = (Ctx*)h;
     if (!c || n_items < 1 || n_links < 1 || max_faces < 0 || H < 1 || W < 1) return fail(EHB_E_ARG, "bad reserve arguments");
     DeviceGuard guard(c->device);
-    const int ntiles = ((W + EHB_T - 1) / EHB_T) * ((H + EHB_T - 1) / EHB_T);
-    int r = ensure_scratch(c, n_items, max_faces, ntiles, n_links, false);
+    int r = ensure_scratch(c, n_items, n_links, n_links, H, W, false);
     if (r) return r;
     if ((r = c->mvpDev.ensure((size_t)n_items * n_links * 16, false))) return r;
     if ((r = c->outDev.ensure((size_t)n_items * (1 + n_links * 16), false))) return r;
     return EHB_OK;
 }
 
-int ehb_ctx_grow_pairs(ehb_ctx_t h)
+int ehb_ctx_grow_scratch(ehb_ctx_t h)
 {
     Ctx* c = (Ctx*)h;
     if (!c) return fail(EHB_E_ARG, "null context");
-    c->pairFactor *= 2;
+    c->poolFactor *= 2.0;
     return EHB_OK;
 }
 
@@ -378,14 +404,14 @@ int ehb_ctx_kernel_times(ehb_ctx_t h, double* ms4, long long* n_passes)
     if (!c || !ms4 || !n_passes) return fail(EHB_E_ARG, "null pointer argument");
     DeviceGuard guard(c->device);
     CU(cudaDeviceSynchronize());
-    for (int k = 0; k < 4; k++) ms4[k] = 0.0;
-    for (size_t i = 0; i + 5 <= c->evUsed; i += 5)
-        for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < 5; k++) ms4[k] = 0.0;
+    for (size_t i = 0; i + 6 <= c->evUsed; i += 6)
+        for (int k = 0; k < 5; k++) {
             float ms = 0.f;
             CU(cudaEventElapsedTime(&ms, c->evPool[i + k], c->evPool[i + k + 1]));
             ms4[k] += ms;
         }
-    *n_passes = (long long)(c->evUsed / 5);
+    *n_passes = (long long)(c->evUsed / 6);
     c->evUsed = 0;
     return EHB_OK;
 }
@@ -592,8 +618,8 @@ int ehb_solver_step_host(ehb_ctx_t h, const int* mesh_ids, int L, int B, const f
         CU(cudaMemcpyAsync(c->ctrHost, c->ctr, sizeof(EhbCounters), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if (!(c->ctrHost->flags & EHB_FLAG_PAIR_OVERFLOW)) break;
-        if (attempt >= 6) return fail(EHB_E_OVERFLOW, "triangle/tile pair buffer overflow persists after growing");
-        c->pairFactor *= 2;   // grow the pair buffer and run the step again
+        if (attempt >= 6) return fail(EHB_E_OVERFLOW, "plane pool overflow persists after growing");
+        c->poolFactor *= 2.0;   // grow the plane pool and run the step again
         unsigned int zero = 0;
         CU(cudaMemcpyAsync(&c->ctr->flags, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
     }
@@ -623,8 +649,8 @@ int ehb_solver_step_host_u8(ehb_ctx_t h, const int* mesh_ids, int L, int B, cons
         CU(cudaMemcpyAsync(c->ctrHost, c->ctr, sizeof(EhbCounters), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if (!(c->ctrHost->flags & EHB_FLAG_PAIR_OVERFLOW)) break;
-        if (attempt >= 6) return fail(EHB_E_OVERFLOW, "triangle/tile pair buffer overflow persists after growing");
-        c->pairFactor *= 2;
+        if (attempt >= 6) return fail(EHB_E_OVERFLOW, "plane pool overflow persists after growing");
+        c->poolFactor *= 2.0;
         unsigned int zero = 0;
         CU(cudaMemcpyAsync(&c->ctr->flags, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
     }

@@ -26,6 +26,7 @@ struct EhbLink {
 struct EhbRobot {
     EhbLink link[EHB_MAX_LINKS];
     int foff[EHB_MAX_LINKS + 1];  // prefix sum of F over links
+    int voff[EHB_MAX_LINKS + 1];  // prefix sum of V over links
     int L;
 };
 

@@ -1,73 +1,99 @@
-// ehb_kernels.cuh -- the four kernels of one rasterizer pass (count -> alloc -> fill -> raster).
+// ehb_kernels.cuh -- the kernels of one rasterizer pass.
 //
-// Work decomposition (B200: 148 SMs, 227 KB smem/SM, 126 MB L2):
-//   * the screen of every item (a camera view, or one render of a batch) is cut into 32x32-pixel tiles;
-//     a tile's CTA keeps one 64-bit (depth key | triangle id) plane PER LINK in shared memory, because the
-//     reference antialiases every link separately before summing (rb_solver.py:62-68);
-//   * k_count  : one thread per (item, triangle): transform, snap, cull, bbox -> per-(tile, link) counts;
-//   * k_alloc  : one warp per tile: contiguous, 16-byte aligned segment of the pair buffer per tile, list of
-//                non-empty tiles; EMPTY tiles are finished right here as a pure float4 stream
-//                (mask = 0, loss += ref^2), which is the HBM-bound part of the frame;
-//   * k_fill   : one thread per (item, triangle): scatter triangle ids into the tile segments;
-//   * k_raster : persistent CTAs pull non-empty tiles from a queue: coverage + nearest depth with shared
-//                memory atomicMin, antialias forward of every link, sum / clamp / loss / dL/dmask, antialias
-//                backward reduced by warp shuffles straight to d loss / d mvp[item, link] (fp64 atomics).
-// No intermediate image (rast, colour, work queue, clip-space vertex buffer) ever goes to HBM.
+// Work decomposition (B200: 148 SMs, 126 MB L2, 227 KB smem/SM).  The reference antialiases every link separately
+// before summing (rb_solver.py:62-68), so visibility is resolved per (item, link) -- an "item" is a camera view or
+// one render of a batch.  Each (item, link) gets a 64-bit (depth key | triangle id) plane covering only the
+// link's screen bounding box; for robot views all planes of a step are a few tens of MB and stay L2-resident.
+//   k_bbox   : one thread per (item, vertex): transform, snap -> per-(item, link) bounding box (warp reduce + atomics)
+//   k_plan   : (a) one thread per plane: pixel bbox, bump allocation of the plane in the plane pool;
+//              (b) one warp per 32x32 tile: tiles no link's bbox touches are finished right here as a float4 stream
+//                  (mask = 0, loss += ref^2) -- the HBM-bound part of the frame; the others go to the tile queue
+//   k_clear  : planes := EMPTY (only the allocated part of the pool)
+//   k_raster : NO binning, NO block barriers: each warp takes 32 triangles (one per lane): setup -> record in the
+//              warp's shared memory; the rows of the 32 clipped bboxes form one flat space; 32 rows at a time (one per
+//              lane) get their exactly covered span (float estimate + integer fix-up == testing every sample), and
+//              the warp then shades the covered samples of those rows cooperatively, 32 at a time: z/w from the
+//              unsnapped clip positions, atomicMin (RED.MIN.U64, served by L2) into the plane.  Triangles with very
+//              many rows are deferred to k_raster_big, where free warps pull 32-row slabs from a queue.
+//   k_tiles  : persistent CTAs over the non-empty tiles: per link whose bbox touches the tile: load the 35x35 window
+//              of its plane, 35 row bitmasks -> silhouette pairs by XOR -> blend weights with all lanes busy -> pair
+//              list (triangle, edge, alpha) -> gather into the per-view sum in the reference's order; then
+//              S = min(sum, 1), mask write, (S - ref)^2, g = dL/dsum; the backward walks the pair list, contracts
+//              the analytic vertex gradients with [x y z 1] on the fly, warp-shuffle reduce, fp64 atomicAdd into
+//              d loss / d mvp[item, link].
+// No intermediate image (rast, colour, antialias work queue, clip-space vertex buffer) is ever written.
 #pragma once
 #include "ehb_device.cuh"
 
 #define EHB_T 32            // tile interior
-#define EHB_RS 35           // plane row stride = T + max halo (1 low, 2 high)
+#define EHB_RS 35           // window row stride = T + max halo (1 low, 2 high)
 #define EHB_NP (EHB_RS * EHB_RS)
 
-enum { EHB_MODE_FUSED = 0, EHB_MODE_AA_FWD = 1, EHB_MODE_AA_BWD = 2, EHB_MODE_UNION = 3, EHB_MODE_UNION_VAR = 4 };
+enum { EHB_MODE_FUSED = 0, EHB_MODE_AA_FWD = 1, EHB_MODE_AA_BWD = 2, EHB_MODE_UNION = 3 };
 
-struct EhbPairEnt;
-struct EhbCounters {
-    unsigned long long pairCursor;
-    unsigned long long nNeedClip;
-    unsigned int nHeavy;     // non-empty tiles with many triangles: listed from the front of tileList
-    unsigned int nLight;     // the others: listed from the back; the raster queue serves the heavy ones first
-    unsigned int workCursor;
-    unsigned int flags;
+struct EhbPairEnt {
+    uint32_t packed;         // idx (11) | d << 11 | own << 12 | side << 13 | di << 14
+    uint32_t tri;
+    float alpha;
 };
-#define EHB_HEAVY_PAIRS 192
+
+struct EhbPlane {            // depth plane of one (item, link): pixels [x0, x0+w) x [y0, y0+h), GL rows
+    int x0, y0, w, h;
+    long long off;           // first element in the plane pool
+    long long pad;
+};
+
+struct EhbUnit { uint32_t rec; unsigned short dx0, dy0; };   // a 64 x 32 pixel window of a deferred triangle's bbox
+
+struct EhbCounters {
+    unsigned long long planeCursor;
+    unsigned long long nNeedClip;
+    unsigned int nTiles;
+    unsigned int workCursor;
+    unsigned int nBigRec;    // deferred (not small) triangles: records parked in global memory ...
+    unsigned int nUnits;     // ... and cut into bounded units that k_raster_big spreads over the whole chip
+    unsigned int flags;      // 1: plane pool too small (results invalid, grow and rerun), 2: triangles need clipping
+    unsigned int pad;
+};
 
 struct EhbParams {
     int H, W, ntx, nty, ntiles;
-    int items, L, Lk, Ftot;
+    int items, L, Lp, Ftot, Vtot;   // Lp = planes per item: L (per-link visibility) or 1 (packed robot)
     int hlo, hhi;
     int mode, rule, do_bwd, clamp;
     float invB;
-    const float* mvp;     // [items, L, 16]
-    uint32_t* range;      // [items, Ftot] packed tile range of every triangle
-    uint32_t* cnt;        // [items * ntiles * Lk]
-    uint32_t* start;
-    uint32_t* cur;
-    uint32_t* tileList;   // [items * ntiles]
-    uint32_t* pairs;
-    unsigned long long pairCap;
+    const float* mvp;        // [items, L, 16]
+    int* bbraw;              // [items, Lp, 4]  min X, min Y, max X, max Y of the snapped vertices
+    EhbPlane* plane;         // [items, Lp]
+    unsigned long long* pool;
+    unsigned long long poolCap;
+    uint32_t* tileList;      // [items * ntiles]
+    struct EhbRec* bigRec;   // [bigCap]
+    EhbUnit* units;          // [unitCap]
+    int bigCap, unitCap;
     EhbCounters* ctr;
-    const float* ref;     // [items, H, W]  FUSED
-    const uint8_t* ref_u8;// same, as bytes (either ref or ref_u8)
-    float* masks;         // [items, H, W]  FUSED / AA_FWD
-    double* loss;         // [items]
-    double* gmvp;         // [items, L, 16]
-    float* gpos;          // [V, 4] (AA_BWD, single link) or NULL
-    const float* dy;      // [items, H, W]  AA_BWD
-    uint8_t* out_u8;      // [items, H, W]  UNION
-    float* score;         // [items / C]    UNION_VAR
-    int C;
-    struct EhbPairEnt* pairSpill;   // [gridDim.x of k_raster][spillCap] overflow of the shared-memory pair lists
+    const float* ref;        // [items, H, W]  FUSED
+    const uint8_t* ref_u8;   // same, as bytes (either ref or ref_u8)
+    float* masks;            // [items, H, W]  FUSED / AA_FWD
+    double* loss;            // [items]
+    double* gmvp;            // [items, L, 16]
+    float* gpos;             // [V, 4] (AA_BWD, single link) or NULL
+    const float* dy;         // [items, H, W]  AA_BWD
+    uint8_t* out_u8;         // [items, H, W]  UNION
+    EhbPairEnt* pairSpill;   // [gridDim.x of k_tiles][spillCap] overflow of the shared-memory pair lists
     int spillCap;
 };
 
-#define EHB_RANGE_NONE 1u  // lo_x = 1 > hi_x = 0
+#define EHB_RAW_MIN 0x7F7F7F7F          // memset(0x7F) / memset(0x80) patterns: "no vertex yet"
+#define EHB_RAW_MAX ((int)0x80808080)
+#define EHB_SMALL_AREA 96               // triangles whose clipped bbox has more candidate samples are deferred
+#define EHB_UNIT_W 64
+#define EHB_UNIT_H 32
 
-__device__ __forceinline__ int ehb_find_link(const EhbRobot& rb, int g)
+__device__ __forceinline__ int ehb_find_link(const int* off, int L, int g)
 {
     int l = 0;
-    while (l + 1 < rb.L && g >= rb.foff[l + 1]) l++;
+    while (l + 1 < L && g >= off[l + 1]) l++;
     return l;
 }
 
@@ -81,47 +107,6 @@ __device__ __forceinline__ void ehb_load_mvp(const float* __restrict__ src, floa
     }
 }
 
-// ------------------------------------------------------------------------------------------------ k_count
-__global__ void __launch_bounds__(256) ehb_k_count(const __grid_constant__ EhbRobot rb,
-                                                   const __grid_constant__ EhbParams p)
-{
-    const int item = blockIdx.y;
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (blockIdx.x == 0) {
-        if (item == 0 && threadIdx.x == 0) {
-            p.ctr->pairCursor = 0ull;
-            p.ctr->nHeavy = 0u;
-            p.ctr->nLight = 0u;
-            p.ctr->workCursor = 0u;
-        }
-        if (p.loss && threadIdx.x == 0) p.loss[item] = 0.0;
-        if (p.gmvp)
-            for (int i = threadIdx.x; i < p.L * 16; i += blockDim.x) p.gmvp[(size_t)item * p.L * 16 + i] = 0.0;
-        if (p.score && p.C > 0 && item % p.C == 0 && threadIdx.x == 0) p.score[item / p.C] = 0.f;
-    }
-    if (g >= p.Ftot) return;
-    const int l = ehb_find_link(rb, g);
-    float m[16];
-    ehb_load_mvp(p.mvp + ((size_t)item * p.L + l) * 16, m);
-    EhbTri s;
-    const int st = ehb_tri_setup(rb.link[l], m, g - rb.foff[l], p.H, p.W, s);
-    uint32_t packed = EHB_RANGE_NONE;
-    if (st == 2) {
-        atomicAdd(&p.ctr->nNeedClip, 1ull);
-        atomicOr(&p.ctr->flags, 2u);
-    } else if (st == 0) {
-        const int txlo = max(0, (s.pxlo - p.hhi) >> 5), txhi = min(p.ntx - 1, (s.pxhi + p.hlo) >> 5);
-        const int tylo = max(0, (s.pylo - p.hhi) >> 5), tyhi = min(p.nty - 1, (s.pyhi + p.hlo) >> 5);
-        packed = (uint32_t)txlo | ((uint32_t)txhi << 8) | ((uint32_t)tylo << 16) | ((uint32_t)tyhi << 24);
-        const int lb = p.Lk == 1 ? 0 : l;
-        for (int ty = tylo; ty <= tyhi; ty++)
-            for (int tx = txlo; tx <= txhi; tx++)
-                atomicAdd(&p.cnt[((size_t)item * p.ntiles + ty * p.ntx + tx) * p.Lk + lb], 1u);
-    }
-    p.range[(size_t)item * p.Ftot + g] = packed;
-}
-
-// ------------------------------------------------------------------------------------------------ k_alloc
 __device__ __forceinline__ double ehb_warp_sum(double v)
 {
 #pragma unroll
@@ -129,7 +114,74 @@ __device__ __forceinline__ double ehb_warp_sum(double v)
     return v;
 }
 
-// A tile no triangle touches: mask = 0 and loss += sum ref^2, streamed by one warp.
+// pixel bbox of a plane from the raw snapped extremes (same formulas as ehb_tri_setup's per-triangle range)
+__device__ __forceinline__ bool ehb_raw_to_pixels(const int* raw, int H, int W, int& x0, int& y0, int& x1, int& y1)
+{
+    const int mnx = raw[0], mny = raw[1], mxx = raw[2], mxy = raw[3];
+    if (mnx > mxx || mny > mxy) return false;
+    const int bx = 8 * W - 8, by = 8 * H - 8;
+    x0 = max((mnx + bx + 15) >> 4, 0); x1 = min((mxx + bx) >> 4, W - 1);
+    y0 = max((mny + by + 15) >> 4, 0); y1 = min((mxy + by) >> 4, H - 1);
+    return x0 <= x1 && y0 <= y1;
+}
+
+// ------------------------------------------------------------------------------------------------ k_bbox
+__global__ void __launch_bounds__(256) ehb_k_bbox(const __grid_constant__ EhbRobot rb,
+                                                  const __grid_constant__ EhbParams p)
+{
+    const int item = blockIdx.y;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    if (blockIdx.x == 0) {
+        if (item == 0 && threadIdx.x == 0) {
+            p.ctr->planeCursor = 0ull;
+            p.ctr->nTiles = 0u;
+            p.ctr->workCursor = 0u;
+            p.ctr->nBigRec = 0u;
+            p.ctr->nUnits = 0u;
+        }
+        if (p.loss && threadIdx.x == 0) p.loss[item] = 0.0;
+        if (p.gmvp)
+            for (int i = threadIdx.x; i < p.L * 16; i += blockDim.x) p.gmvp[(size_t)item * p.L * 16 + i] = 0.0;
+    }
+    int l = -1, X = 0, Y = 0;
+    if (g < p.Vtot) {
+        const int lk = ehb_find_link(rb.voff, rb.L, g);
+        float m[16], c[4];
+        ehb_load_mvp(p.mvp + ((size_t)item * p.L + lk) * 16, m);
+        ehb_xform(__ldg(rb.link[lk].verts + (g - rb.voff[lk])), m, c);
+        if (c[3] >= fabsf(c[2])) {   // only such vertices can belong to a drawable triangle
+            const float r = 1.0f / c[3];
+            X = ehb_rni_sat(c[0] * r * (float)(p.W * 8));
+            Y = ehb_rni_sat(c[1] * r * (float)(p.H * 8));
+            const int G = 1 << 28;
+            if (X <= G && X >= -G && Y <= G && Y >= -G) l = p.Lp == 1 ? 0 : lk;
+        }
+    }
+    // warp-aggregate when the whole warp works on the same plane, else per-lane atomics
+    const int l0 = __shfl_sync(0xffffffffu, l, 0);
+    const bool same = __all_sync(0xffffffffu, l == l0 || l < 0);
+    if (same) {
+        int mnx = l >= 0 ? X : INT_MAX, mny = l >= 0 ? Y : INT_MAX, mxx = l >= 0 ? X : INT_MIN, mxy = l >= 0 ? Y : INT_MIN;
+        int lv = l;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+            mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o)); mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+            lv = max(lv, __shfl_xor_sync(0xffffffffu, lv, o));
+        }
+        if (lane == 0 && lv >= 0) {
+            int* raw = p.bbraw + ((size_t)item * p.Lp + lv) * 4;
+            atomicMin(raw + 0, mnx); atomicMin(raw + 1, mny); atomicMax(raw + 2, mxx); atomicMax(raw + 3, mxy);
+        }
+    } else if (l >= 0) {
+        int* raw = p.bbraw + ((size_t)item * p.Lp + l) * 4;
+        atomicMin(raw + 0, X); atomicMin(raw + 1, Y); atomicMax(raw + 2, X); atomicMax(raw + 3, Y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ k_plan
+// A tile no link touches: mask = 0 and loss += sum ref^2, streamed by one warp.
 __device__ __forceinline__ void ehb_stream_empty_tile(const EhbParams& p, int item, int tx, int ty, int lane)
 {
     const int x0 = tx * EHB_T, y0 = ty * EHB_T;
@@ -137,7 +189,8 @@ __device__ __forceinline__ void ehb_stream_empty_tile(const EhbParams& p, int it
     const size_t ibase = (size_t)item * H * W;
     if (p.mode == EHB_MODE_FUSED || p.mode == EHB_MODE_AA_FWD) {
         double acc = 0.0;
-        const bool vec = (W & 3) == 0 && ((((uintptr_t)p.masks) | ((uintptr_t)p.ref)) & 15) == 0;
+        const bool vec = (W & 3) == 0 && ((((uintptr_t)p.masks) | ((uintptr_t)p.ref)) & 15) == 0 &&
+                         (((uintptr_t)p.ref_u8) & 3) == 0;
         if (vec) {
             const int cx = x0 + 4 * (lane & 7);
 #pragma unroll
@@ -170,178 +223,75 @@ __device__ __forceinline__ void ehb_stream_empty_tile(const EhbParams& p, int it
             acc = ehb_warp_sum(acc);
             if (lane == 0 && acc != 0.0) atomicAdd(&p.loss[item], acc);
         }
-    } else if (p.mode == EHB_MODE_UNION) {
-        if ((W & 3) == 0 && (((uintptr_t)p.out_u8) & 3) == 0) {
-            const int cx = x0 + 4 * (lane & 7);
-#pragma unroll
-            for (int it = 0; it < 8; it++) {
-                const int py = y0 + it * 4 + (lane >> 3);
-                if (py < H && cx < W)
-                    *reinterpret_cast<uint32_t*>(p.out_u8 + ibase + (size_t)(H - 1 - py) * W + cx) = 0u;
-            }
-        } else {
-            for (int i = lane; i < EHB_T * EHB_T; i += 32) {
-                const int px = x0 + (i & 31), py = y0 + (i >> 5);
-                if (px < W && py < H) p.out_u8[ibase + (size_t)(H - 1 - py) * W + px] = 0;
-            }
-        }
     }
 }
 
-__global__ void __launch_bounds__(256) ehb_k_alloc(const __grid_constant__ EhbParams p)
+__global__ void __launch_bounds__(256) ehb_k_plan(const __grid_constant__ EhbParams p, int planBlocks)
 {
-    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if ((int)blockIdx.x < planBlocks) {   // (a) plane allocation
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= p.items * p.Lp) return;
+        EhbPlane pl;
+        pl.x0 = pl.y0 = pl.w = pl.h = 0; pl.off = 0; pl.pad = 0;
+        int x0, y0, x1, y1;
+        if (ehb_raw_to_pixels(p.bbraw + (size_t)i * 4, p.H, p.W, x0, y0, x1, y1)) {
+            const unsigned long long area = (unsigned long long)(x1 - x0 + 1) * (unsigned long long)(y1 - y0 + 1);
+            const unsigned long long off = atomicAdd(&p.ctr->planeCursor, area);
+            if (off + area <= p.poolCap) { pl.x0 = x0; pl.y0 = y0; pl.w = x1 - x0 + 1; pl.h = y1 - y0 + 1; pl.off = (long long)off; }
+            else atomicOr(&p.ctr->flags, 1u);
+        }
+        p.plane[i] = pl;
+        return;
+    }
+    // (b) tile classification: one warp per tile
+    const int wid = (((int)blockIdx.x - planBlocks) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wid >= p.items * p.ntiles) return;
     const int item = wid / p.ntiles, tile = wid - item * p.ntiles;
-    const size_t bin0 = (size_t)wid * p.Lk;
-    const uint32_t c = lane < p.Lk ? p.cnt[bin0 + lane] : 0u;
-    uint32_t inc = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-    bool empty = total == 0;
-    unsigned long long base = 0;
-    if (!empty) {
-        const uint32_t padded = (total + 3u) & ~3u;
-        if (lane == 0) base = atomicAdd(&p.ctr->pairCursor, (unsigned long long)padded);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base + padded > p.pairCap) {  // pair buffer too small: flag it, the host grows the buffer and reruns
-            if (lane == 0) atomicOr(&p.ctr->flags, 1u);
-            if (lane < p.Lk) p.cnt[bin0 + lane] = 0u;
-            empty = true;
+    const int tx = tile % p.ntx, ty = tile / p.ntx;
+    bool hit = false;
+    if (lane < p.Lp) {
+        int x0, y0, x1, y1;
+        if (ehb_raw_to_pixels(p.bbraw + ((size_t)item * p.Lp + lane) * 4, p.H, p.W, x0, y0, x1, y1)) {
+            const int rx0 = tx * EHB_T - p.hlo, ry0 = ty * EHB_T - p.hlo;
+            const int rx1 = tx * EHB_T + EHB_T - 1 + p.hhi, ry1 = ty * EHB_T + EHB_T - 1 + p.hhi;
+            hit = x0 <= rx1 && x1 >= rx0 && y0 <= ry1 && y1 >= ry0;
         }
     }
-    if (empty) {
-        if (lane < p.Lk) { p.start[bin0 + lane] = 0xFFFFFFFFu; p.cur[bin0 + lane] = 0xFFFFFFFFu; }
-        ehb_stream_empty_tile(p, item, tile % p.ntx, tile / p.ntx, lane);
-        return;
-    }
-    if (lane < p.Lk) {
-        const uint32_t s = (uint32_t)base + (inc - c);
-        p.start[bin0 + lane] = s;
-        p.cur[bin0 + lane] = s;
-    }
-    if (lane == 0) {
-        if (total >= EHB_HEAVY_PAIRS) p.tileList[atomicAdd(&p.ctr->nHeavy, 1u)] = (uint32_t)wid;
-        else p.tileList[(unsigned)(p.items * p.ntiles) - 1u - atomicAdd(&p.ctr->nLight, 1u)] = (uint32_t)wid;
+    if (__any_sync(0xffffffffu, hit)) {
+        if (lane == 0) p.tileList[atomicAdd(&p.ctr->nTiles, 1u)] = (uint32_t)wid;
+    } else if (p.mode != EHB_MODE_UNION && p.mode != EHB_MODE_AA_BWD) {
+        ehb_stream_empty_tile(p, item, tx, ty, lane);
     }
 }
 
-// ------------------------------------------------------------------------------------------------ k_fill
-__global__ void __launch_bounds__(256) ehb_k_fill(const __grid_constant__ EhbRobot rb,
-                                                  const __grid_constant__ EhbParams p)
+// ------------------------------------------------------------------------------------------------ k_clear
+__global__ void __launch_bounds__(256) ehb_k_clear(const __grid_constant__ EhbParams p)
 {
-    const int item = blockIdx.y;
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= p.Ftot) return;
-    const uint32_t r = p.range[(size_t)item * p.Ftot + g];
-    const int txlo = r & 255, txhi = (r >> 8) & 255, tylo = (r >> 16) & 255, tyhi = r >> 24;
-    if (txlo > txhi) return;
-    const int l = ehb_find_link(rb, g);
-    const uint32_t entry = ((uint32_t)l << EHB_LINK_SHIFT) | (uint32_t)(g - rb.foff[l]);
-    const int lb = p.Lk == 1 ? 0 : l;
-    for (int ty = tylo; ty <= tyhi; ty++)
-        for (int tx = txlo; tx <= txhi; tx++) {
-            const size_t bin = ((size_t)item * p.ntiles + ty * p.ntx + tx) * p.Lk + lb;
-            if (p.start[bin] == 0xFFFFFFFFu) continue;  // tile dropped by an overflowing alloc
-            const uint32_t slot = atomicAdd(&p.cur[bin], 1u);
-            p.pairs[slot] = entry;
-        }
+    const unsigned long long total = min(p.ctr->planeCursor, p.poolCap);
+    const unsigned long long n2 = total >> 1;
+    ulonglong2* p2 = reinterpret_cast<ulonglong2*>(p.pool);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        p2[i] = make_ulonglong2(EHB_EMPTY, EHB_EMPTY);
+    if ((total & 1ull) && blockIdx.x == 0 && threadIdx.x == 0) p.pool[total - 1] = EHB_EMPTY;
+    // the raw bounding boxes have been consumed by k_plan: reset them for the next pass
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.items * p.Lp * 4; i += gridDim.x * blockDim.x)
+        p.bbraw[i] = (i & 2) ? EHB_RAW_MAX : EHB_RAW_MIN;
 }
 
 // ------------------------------------------------------------------------------------------------ k_raster
-//
-// One CTA (128 threads) per non-empty tile; persistent CTAs pull tiles from a queue.  The links present in a
-// tile are processed ONE AT A TIME through a single 64-bit (depth key | triangle id) plane in shared memory:
-//   raster : the link's triangles are taken 128 at a time, one per thread: setup -> a 64-byte record (edge
-//            functions at the first candidate sample, per-pixel steps, clipped bbox).  A block scan of the
-//            candidate-sample counts turns the batch into ONE flat sample space cut into 128 equal chunks, so
-//            every thread tests the same number of samples whatever the triangle sizes are.  Covered samples
-//            go to a per-warp queue (warp-ballot aggregated) that is drained with all 32 lanes busy: z/w from
-//            the unsnapped clip positions, atomicMin into the plane.
-//   pairs  : the plane is reduced to 35 row bitmasks; silhouette pixel pairs (covered next to empty) fall out
-//            of XORs of those masks and are appended to the tile's pair list; their blend weights are computed
-//            with all lanes busy and kept in the list (triangle, edge, alpha) -- this list is all the backward
-//            needs, so the plane can be reused by the next link and nothing is ever re-rasterised.
-//   gather : alpha is scattered to two small planes and every pixel adds colour + its (up to four) pair
-//            contributions in the reference's order into the per-view sum.
-// After the last link: S = min(sum, 1), mask write, (S - ref)^2, g = dL/dsum; then the backward walks the pair
-// list link by link: analytic gradient of the active edge's two vertices, contracted with [x y z 1] on the
-// fly, warp-shuffle reduced, added to d loss / d mvp[item, link] with fp64 atomics.
-#ifndef EHB_RTHREADS
-#define EHB_RTHREADS 256
-#endif
-#define EHB_RWARPS (EHB_RTHREADS / 32)
-#define EHB_BATCH EHB_RTHREADS
-#ifndef EHB_PAIRCAP
-#define EHB_PAIRCAP 768      // pair-list entries kept in shared memory; the rest spills to a per-CTA global area
-#endif
+#define EHB_RWARPS 8         // warps per raster CTA; every warp works alone on batches of 32 triangles
 
 struct __align__(16) EhbRec {
     long long E[3];          // edge function minus its threshold at the first candidate sample (covered: >= 0)
     int ex[3], ey[3];        // edge vectors (1/16 px): one pixel right adds -16*ey, one pixel up adds +16*ex
-    uint32_t geom;           // w | h << 8 | lx << 16 | ly << 24 : clipped bbox and its origin inside the plane
+    int x0, y0, w, h;        // clipped bbox (pixels, GL rows)
+    long long base;          // pool index of pixel (0,0) of this triangle's plane: idx = base + py * pw + px
+    int pw;                  // plane width
     uint32_t id;             // triangle id stored in the depth key
+    float clip[12];          // unsnapped clip positions of the three vertices
 };
-
-struct EhbPairEnt {
-    uint32_t packed;         // idx (11) | d << 11 | own << 12 | side << 13 | di << 14
-    uint32_t tri;
-    float alpha;
-};
-
-struct __align__(16) EhbSmem {
-    unsigned long long plane[EHB_NP];
-    union {
-        struct {
-            EhbRec rec[EHB_BATCH];
-            float clip[EHB_BATCH][12];
-            int off[EHB_BATCH + 1];
-        } r;
-        struct {
-            float alpha[2][EHB_NP];
-        } a;
-    } ov;
-    float sum[EHB_NP + 3];
-    EhbPairEnt pairs[EHB_PAIRCAP];
-    unsigned long long cov[EHB_RS + 1], hx[EHB_RS + 1], vy[EHB_RS + 1];
-    float mvp[EHB_MAX_LINKS * 16];
-    int links[EHB_MAX_LINKS];
-    uint32_t lstart[EHB_MAX_LINKS];
-    uint32_t lcnt[EHB_MAX_LINKS];
-    int segStart[EHB_MAX_LINKS + 1];
-    int rowCnt[EHB_RS + 1];
-    int warpTot[EHB_RWARPS];
-    int nP;
-    int work;
-};
-
-__device__ __forceinline__ unsigned long long ehb_bits(int lo, int hi)   // bits lo..hi (inclusive), empty if lo > hi
-{
-    lo = max(lo, 0); hi = min(hi, 63);
-    if (lo > hi) return 0ull;
-    const unsigned long long up = hi >= 63 ? ~0ull : ((1ull << (hi + 1)) - 1ull);
-    return up & ~((1ull << lo) - 1ull);
-}
-
-__device__ __forceinline__ void ehb_shade_entry(uint32_t ent, EhbSmem& sm, int rx0, int ry0, float xs, float xo,
-                                                float ys, float yo)
-{
-    const int t = ent >> 12, ly = (ent >> 6) & 63, lx = ent & 63;
-    const float* c = sm.ov.r.clip[t];
-    const float4 a = *reinterpret_cast<const float4*>(c), b = *reinterpret_cast<const float4*>(c + 4),
-                 d = *reinterpret_cast<const float4*>(c + 8);
-    const float p0[4] = {a.x, a.y, a.z, a.w}, p1[4] = {b.x, b.y, b.z, b.w}, p2[4] = {d.x, d.y, d.z, d.w};
-    const float fx = xs * (float)(rx0 + lx) + xo, fy = ys * (float)(ry0 + ly) + yo;
-    const float zw = ehb_shade_zw(p0, p1, p2, fx, fy);
-    const unsigned long long key = ((unsigned long long)ehb_order_key(zw) << 32) | sm.ov.r.rec[t].id;
-    unsigned long long* dst = sm.plane + ly * EHB_RS + lx;
-    if (key < *dst) atomicMin(dst, key);
-}
 
 __device__ __forceinline__ float ehb_fast_div(float a, float b) { return __fdividef(a, b); }
 __device__ __forceinline__ double ehb_fast_div(double a, double b) { return a / b; }
@@ -378,74 +328,255 @@ __device__ __forceinline__ void ehb_row_span(const I R0, const I R1, const I R2,
     }
 }
 
-// Rows of the batch's triangles -> covered spans -> shaded samples.  The batch's rows form one flat space
-// (off[] = prefix of the clipped bbox heights); each warp takes 32 rows at a time (one per lane), computes their
-// spans, and the warp then shades the covered samples of those 32 rows cooperatively, 32 at a time.
-template <typename I, typename F>
-__device__ __forceinline__ void ehb_rows_fill(EhbSmem& sm, int nRows, int warp, int lane, int rx0, int ry0, float xs,
-                                              float xo, float ys, float yo)
+// setup of one triangle -> record.  Returns the number of rows of its clipped bbox (0: nothing to draw).
+__device__ __forceinline__ int ehb_make_record(const EhbRobot& rb, const EhbParams& p, int item, int g, EhbRec& rc,
+                                               bool count_clip)
 {
-    for (int g = warp * 32; g < nRows; g += EHB_RWARPS * 32) {
-        const int r = g + lane;
-        int len = 0;
-        uint32_t pos = 0;   // t << 12 | ly << 6 | lx of the first covered sample of this lane's row
-        if (r < nRows) {
-            int lo = 0, hi = EHB_BATCH;   // last t with off[t] <= r
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (sm.ov.r.off[mid] <= r) lo = mid; else hi = mid;
-            }
-            const int t = lo, dy = r - sm.ov.r.off[t];
-            const EhbRec& rc = sm.ov.r.rec[t];
-            const uint32_t gm = rc.geom;
-            const int w = gm & 255, lx0 = (gm >> 16) & 255, ly0 = gm >> 24;
-            const I R0 = (I)rc.E[0] + (I)16 * (I)rc.ex[0] * (I)dy, R1 = (I)rc.E[1] + (I)16 * (I)rc.ex[1] * (I)dy,
-                    R2 = (I)rc.E[2] + (I)16 * (I)rc.ex[2] * (I)dy;
-            int a, b;
-            ehb_row_span<I, F>(R0, R1, R2, (I)-16 * (I)rc.ey[0], (I)-16 * (I)rc.ey[1], (I)-16 * (I)rc.ey[2], w, a, b);
-            len = max(0, b - a + 1);
-            pos = ((uint32_t)t << 12) | ((uint32_t)(ly0 + dy) << 6) | (uint32_t)(lx0 + a);
-        }
-        int inc = len;
+    const int l = ehb_find_link(rb.foff, rb.L, g);
+    const int f = g - rb.foff[l];
+    float m[16];
+    ehb_load_mvp(p.mvp + ((size_t)item * p.L + l) * 16, m);
+    EhbTri s;
+    const int st = ehb_tri_setup<false>(rb.link[l], m, f, p.H, p.W, s);
+    if (st == 2 && count_clip) {
+        atomicAdd(&p.ctr->nNeedClip, 1ull);
+        atomicOr(&p.ctr->flags, 2u);
+    }
+    if (st != 0) return 0;
+    const EhbPlane pl = p.plane[(size_t)item * p.Lp + (p.Lp == 1 ? 0 : l)];
+    if (pl.w == 0) return 0;   // pool overflow: flagged, the pass is rerun
+    const int bx = 8 * p.W - 8, by = 8 * p.H - 8;
+    const int sx = 16 * s.pxlo - bx, sy = 16 * s.pylo - by;
+    const int ex0 = s.x1 - s.x0, ey0 = s.y1 - s.y0, ex1 = s.x2 - s.x1, ey1 = s.y2 - s.y1, ex2 = s.x0 - s.x2,
+              ey2 = s.y0 - s.y2;
+    rc.E[0] = (long long)ex0 * (sy - s.y0) - (long long)ey0 * (sx - s.x0) - (ehb_edge_inclusive(ex0, ey0, p.rule) ? 0 : 1);
+    rc.E[1] = (long long)ex1 * (sy - s.y1) - (long long)ey1 * (sx - s.x1) - (ehb_edge_inclusive(ex1, ey1, p.rule) ? 0 : 1);
+    rc.E[2] = (long long)ex2 * (sy - s.y2) - (long long)ey2 * (sx - s.x2) - (ehb_edge_inclusive(ex2, ey2, p.rule) ? 0 : 1);
+    rc.ex[0] = ex0; rc.ex[1] = ex1; rc.ex[2] = ex2;
+    rc.ey[0] = ey0; rc.ey[1] = ey1; rc.ey[2] = ey2;
+    rc.x0 = s.pxlo; rc.y0 = s.pylo; rc.w = s.pxhi - s.pxlo + 1; rc.h = s.pyhi - s.pylo + 1;
+    rc.base = pl.off - (long long)pl.y0 * pl.w - pl.x0;
+    rc.pw = pl.w;
+    rc.id = p.Lp == 1 ? (uint32_t)g : (uint32_t)f;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
-        }
-        const int total = __shfl_sync(0xffffffffu, inc, 31);
-        const int exc = inc - len;
-        for (int j0 = 0; j0 < total; j0 += 32) {
-            const int j = j0 + lane;
-            int o = 0;   // owner lane = number of lanes whose inclusive prefix is <= j
+    for (int i = 0; i < 4; i++) { rc.clip[i] = s.c0[i]; rc.clip[4 + i] = s.c1[i]; rc.clip[8 + i] = s.c2[i]; }
+    return rc.h;
+}
+
+__device__ __forceinline__ void ehb_shade_global(const EhbRec& rc, int px, int py, unsigned long long* pool, float xs,
+                                                 float xo, float ys, float yo)
+{
+    const float4 a = *reinterpret_cast<const float4*>(rc.clip), b = *reinterpret_cast<const float4*>(rc.clip + 4),
+                 d = *reinterpret_cast<const float4*>(rc.clip + 8);
+    const float p0[4] = {a.x, a.y, a.z, a.w}, p1[4] = {b.x, b.y, b.z, b.w}, p2[4] = {d.x, d.y, d.z, d.w};
+    const float fx = xs * (float)px + xo, fy = ys * (float)py + yo;
+    const float zw = ehb_shade_zw(p0, p1, p2, fx, fy);
+    const unsigned long long key = ((unsigned long long)ehb_order_key(zw) << 32) | rc.id;
+    atomicMin(pool + (rc.base + (long long)py * rc.pw + px), key);
+}
+
+// One group of up to 32 rows (one per lane): spans, then the warp shades the covered samples 32 at a time.
+// `t` = this lane's record index in recs (-1: no row), `dy` = its row inside that record's bbox.
+template <typename I, typename F>
+__device__ __forceinline__ void ehb_rows_group(const EhbRec* recs, int t, int dy, int lane, unsigned long long* pool,
+                                               float xs, float xo, float ys, float yo, int cx0 = 0, int cx1 = 1 << 20)
+{
+    int len = 0;
+    uint32_t pos = 0;   // t << 26 | py << 13 | px of the first covered sample of this lane's row
+    if (t >= 0) {
+        const EhbRec& rc = recs[t];
+        const I R0 = (I)rc.E[0] + (I)16 * (I)rc.ex[0] * (I)dy, R1 = (I)rc.E[1] + (I)16 * (I)rc.ex[1] * (I)dy,
+                R2 = (I)rc.E[2] + (I)16 * (I)rc.ex[2] * (I)dy;
+        int a, b;
+        ehb_row_span<I, F>(R0, R1, R2, (I)-16 * (I)rc.ey[0], (I)-16 * (I)rc.ey[1], (I)-16 * (I)rc.ey[2], rc.w, a, b);
+        a = max(a, cx0); b = min(b, cx1);   // window of a deferred triangle's unit
+        len = max(0, b - a + 1);
+        pos = ((uint32_t)t << 26) | ((uint32_t)(rc.y0 + dy) << 13) | (uint32_t)(rc.x0 + a);
+    }
+    int inc = len;
 #pragma unroll
-            for (int st = 16; st >= 1; st >>= 1) {
-                const int v = __shfl_sync(0xffffffffu, inc, o + st - 1);
-                if (v <= j) o += st;
-            }
-            o = min(o, 31);
-            const uint32_t opos = __shfl_sync(0xffffffffu, pos, o);
-            const int oexc = __shfl_sync(0xffffffffu, exc, o);
-            if (j < total) ehb_shade_entry(opos + (uint32_t)(j - oexc), sm, rx0, ry0, xs, xo, ys, yo);
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    const int exc = inc - len;
+    for (int j0 = 0; j0 < total; j0 += 32) {
+        const int j = j0 + lane;
+        int o = 0;   // owner lane = number of lanes whose inclusive prefix is <= j
+#pragma unroll
+        for (int st = 16; st >= 1; st >>= 1) {
+            const int v = __shfl_sync(0xffffffffu, inc, o + st - 1);
+            if (v <= j) o += st;
+        }
+        o = min(o, 31);
+        const uint32_t opos = __shfl_sync(0xffffffffu, pos, o);
+        const int oexc = __shfl_sync(0xffffffffu, exc, o);
+        if (j < total) {
+            const uint32_t q = opos + (uint32_t)(j - oexc);
+            ehb_shade_global(recs[q >> 26], (int)(q & 8191u), (int)((q >> 13) & 8191u), pool, xs, xo, ys, yo);
         }
     }
 }
 
-#ifndef EHB_MIN_BLOCKS
-#define EHB_MIN_BLOCKS 2
+__global__ void __launch_bounds__(EHB_RWARPS * 32) ehb_k_raster(const __grid_constant__ EhbRobot rb,
+                                                                const __grid_constant__ EhbParams p)
+{
+    __shared__ EhbRec s_rec[EHB_RWARPS][32];
+    __shared__ int s_off[EHB_RWARPS][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int item = blockIdx.y;
+    const int g = (blockIdx.x * EHB_RWARPS + warp) * 32 + lane;
+    const float xs = 2.f / (float)p.W, xo = 1.f / (float)p.W - 1.f;
+    const float ys = 2.f / (float)p.H, yo = 1.f / (float)p.H - 1.f;
+    EhbRec* recs = s_rec[warp];
+    int* off = s_off[warp];
+    int rows = 0, wide = 0;
+    if (g < p.Ftot) {
+        rows = ehb_make_record(rb, p, item, g, recs[lane], true);
+        if (rows > 0) {
+            const EhbRec& rc = recs[lane];
+            const int ext = max(max(abs(rc.ex[0]), abs(rc.ex[1])), max(max(abs(rc.ex[2]), abs(rc.ey[0])), max(abs(rc.ey[1]), abs(rc.ey[2]))));
+            wide = ext >= 32768;   // 32-bit edge arithmetic is exact below 2^15 sub-pixel units per edge
+            if (rc.w * rc.h > EHB_SMALL_AREA) {   // not small: park the record, cut the bbox into bounded units
+                const int nux = (rc.w + EHB_UNIT_W - 1) / EHB_UNIT_W, nuy = (rc.h + EHB_UNIT_H - 1) / EHB_UNIT_H;
+                const unsigned k = atomicAdd(&p.ctr->nBigRec, 1u);
+                const unsigned u0 = atomicAdd(&p.ctr->nUnits, (unsigned)(nux * nuy));
+                if ((int)k < p.bigCap && (int)(u0 + nux * nuy) <= p.unitCap) {
+                    p.bigRec[k] = rc;
+                    for (int uy = 0; uy < nuy; uy++)
+                        for (int ux = 0; ux < nux; ux++)
+                            p.units[u0 + uy * nux + ux] = EhbUnit{k, (unsigned short)(ux * EHB_UNIT_W), (unsigned short)(uy * EHB_UNIT_H)};
+                    rows = 0;
+                } else {
+                    atomicOr(&p.ctr->flags, 4u);   // queues full: this one is drawn inline (slow but complete); its units are void
+                    for (int i = 0; i < nux * nuy && (int)(u0 + i) < p.unitCap; i++) p.units[u0 + i] = EhbUnit{0xFFFFFFFFu, 0, 0};
+                }
+            }
+        }
+    }
+    int inc = rows;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    off[lane] = inc - rows;
+    if (lane == 31) off[32] = inc;
+    const bool anyWide = __any_sync(0xffffffffu, wide && rows > 0);
+    __syncwarp();
+    const int nRows = off[32];
+    for (int r0 = 0; r0 < nRows; r0 += 32) {
+        const int r = r0 + lane;
+        int t = -1, dy = 0;
+        if (r < nRows) {
+            int lo = 0, hi = 32;   // last t with off[t] <= r
+#pragma unroll
+            for (int st = 0; st < 5; st++) {
+                const int mid = (lo + hi) >> 1;
+                if (off[mid] <= r) lo = mid; else hi = mid;
+            }
+            t = lo; dy = r - off[t];
+        }
+        if (anyWide) ehb_rows_group<long long, double>(recs, t, dy, lane, p.pool, xs, xo, ys, yo);
+        else ehb_rows_group<int, float>(recs, t, dy, lane, p.pool, xs, xo, ys, yo);
+    }
+}
+
+// Deferred triangles: warps stride over the unit list; one unit = a 64 x 32 pixel window of one triangle's bbox.
+__global__ void __launch_bounds__(256) ehb_k_raster_big(const __grid_constant__ EhbParams p)
+{
+    __shared__ EhbRec s_rec[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = min((int)p.ctr->nUnits, p.unitCap);
+    const float xs = 2.f / (float)p.W, xo = 1.f / (float)p.W - 1.f;
+    const float ys = 2.f / (float)p.H, yo = 1.f / (float)p.H - 1.f;
+    EhbRec* rc = &s_rec[warp];
+    for (int u = blockIdx.x * 8 + warp; u < n; u += gridDim.x * 8) {
+        const EhbUnit un = p.units[u];
+        if (un.rec == 0xFFFFFFFFu) continue;
+        __syncwarp();
+        reinterpret_cast<uint32_t*>(rc)[lane] = reinterpret_cast<const uint32_t*>(p.bigRec + un.rec)[lane];   // 128 B
+        __syncwarp();
+        const int ext = max(max(abs(rc->ex[0]), abs(rc->ex[1])), max(max(abs(rc->ex[2]), abs(rc->ey[0])), max(abs(rc->ey[1]), abs(rc->ey[2]))));
+        const int dy = un.dy0 + lane;
+        const int t = dy < rc->h ? 0 : -1;
+        if (ext >= 32768) ehb_rows_group<long long, double>(rc, t, dy, lane, p.pool, xs, xo, ys, yo, un.dx0, un.dx0 + EHB_UNIT_W - 1);
+        else ehb_rows_group<int, float>(rc, t, dy, lane, p.pool, xs, xo, ys, yo, un.dx0, un.dx0 + EHB_UNIT_W - 1);
+    }
+}
+
+// UNION (packed robot, no antialiasing): mask = (z/w of the nearest triangle > 0), straight from the item's plane.
+__global__ void __launch_bounds__(256) ehb_k_union_out(const __grid_constant__ EhbParams p)
+{
+    const int item = blockIdx.y;
+    const EhbPlane pl = p.plane[item];
+    const int H = p.H, W = p.W;
+    const size_t ibase = (size_t)item * H * W;
+    const int nq = (W + 3) >> 2;   // groups of 4 pixels per row
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nq * H; i += gridDim.x * blockDim.x) {
+        const int row = i / nq, q = i - row * nq;   // image row (row 0 = top)
+        const int py = H - 1 - row;
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int px = 4 * q + k;
+            if (px < W && px >= pl.x0 && px < pl.x0 + pl.w && py >= pl.y0 && py < pl.y0 + pl.h) {
+                const unsigned long long key = p.pool[pl.off + (long long)(py - pl.y0) * pl.w + (px - pl.x0)];
+                if (key != EHB_EMPTY && (uint32_t)(key >> 32) > 0x80000000u) v |= 1u << (8 * k);
+            }
+        }
+        uint8_t* dst = p.out_u8 + ibase + (size_t)row * W + 4 * q;
+        if (4 * q + 3 < W && (((uintptr_t)dst) & 3) == 0) *reinterpret_cast<uint32_t*>(dst) = v;
+        else
+            for (int k = 0; k < 4 && 4 * q + k < W; k++) dst[k] = (uint8_t)((v >> (8 * k)) & 1u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ k_tiles
+#ifndef EHB_TTHREADS
+#define EHB_TTHREADS 128
 #endif
-__global__ void __launch_bounds__(EHB_RTHREADS, EHB_MIN_BLOCKS) ehb_k_raster(const __grid_constant__ EhbRobot rb,
+#define EHB_TWARPS (EHB_TTHREADS / 32)
+#ifndef EHB_PAIRCAP
+#define EHB_PAIRCAP 768      // pair-list entries kept in shared memory; the rest spills to a per-CTA global area
+#endif
+
+struct __align__(16) EhbSmem {
+    unsigned long long plane[EHB_NP];
+    float alpha[2][EHB_NP];
+    float sum[EHB_NP + 3];
+    EhbPairEnt pairs[EHB_PAIRCAP];
+    unsigned long long cov[EHB_RS + 1], hx[EHB_RS + 1], vy[EHB_RS + 1];
+    float mvp[EHB_MAX_LINKS * 16];
+    EhbPlane pl[EHB_MAX_LINKS];
+    int links[EHB_MAX_LINKS];
+    int segStart[EHB_MAX_LINKS + 1];
+    int rowCnt[EHB_RS + 1];
+    int nP;
+    int work;
+};
+
+__device__ __forceinline__ unsigned long long ehb_bits(int lo, int hi)   // bits lo..hi (inclusive), empty if lo > hi
+{
+    lo = max(lo, 0); hi = min(hi, 63);
+    if (lo > hi) return 0ull;
+    const unsigned long long up = hi >= 63 ? ~0ull : ((1ull << (hi + 1)) - 1ull);
+    return up & ~((1ull << lo) - 1ull);
+}
+
+#ifndef EHB_TMIN_BLOCKS
+#define EHB_TMIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(const __grid_constant__ EhbRobot rb,
                                                                              const __grid_constant__ EhbParams p)
 {
     extern __shared__ __align__(16) unsigned char ehb_smem_raw[];
     EhbSmem& sm = *reinterpret_cast<EhbSmem*>(ehb_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = p.H, W = p.W;
-    const bool perLink = p.Lk != 1;
-    const float xs = 2.f / (float)W, xo = 1.f / (float)W - 1.f;
-    const float ys = 2.f / (float)H, yo = 1.f / (float)H - 1.f;
     const int hlo = p.hlo;
     const bool needAA = p.mode == EHB_MODE_FUSED || p.mode == EHB_MODE_AA_FWD;
-    const bool needPairs = needAA || p.mode == EHB_MODE_AA_BWD;
     const bool doBwd = (p.mode == EHB_MODE_FUSED && p.do_bwd) || p.mode == EHB_MODE_AA_BWD;
     // out region: interior, plus one column/row on the high side when the backward follows in this pass
     const int oext = (p.mode == EHB_MODE_FUSED && p.do_bwd) ? 1 : 0;
@@ -453,15 +584,12 @@ __global__ void __launch_bounds__(EHB_RTHREADS, EHB_MIN_BLOCKS) ehb_k_raster(con
     EhbPairEnt* spill = p.pairSpill + (size_t)blockIdx.x * p.spillCap;
     auto pair_at = [&](int i) -> EhbPairEnt& { return i < EHB_PAIRCAP ? sm.pairs[i] : spill[i - EHB_PAIRCAP]; };
 
-    // the alpha planes stay all-zero between uses (every scatter is undone after its gather)
-    if (needAA)
-        ;  // zeroed per link below: they share storage with the raster records
+    for (int i = tid; i < 2 * EHB_NP; i += EHB_TTHREADS) (&sm.alpha[0][0])[i] = 0.f;   // kept all-zero between uses
 
     for (;;) {
         if (tid == 0) {
             const unsigned w = atomicAdd(&p.ctr->workCursor, 1u);
-            const unsigned nh = p.ctr->nHeavy, nl = p.ctr->nLight;
-            sm.work = w < nh ? (int)w : (w < nh + nl ? (int)((unsigned)(p.items * p.ntiles) - 1u - (w - nh)) : -1);
+            sm.work = w < p.ctr->nTiles ? (int)w : -1;
         }
         __syncthreads();
         if (sm.work < 0) break;
@@ -471,25 +599,28 @@ __global__ void __launch_bounds__(EHB_RTHREADS, EHB_MIN_BLOCKS) ehb_k_raster(con
         const int x0 = tx * EHB_T, y0 = ty * EHB_T;
         const int rx0 = x0 - hlo, ry0 = y0 - hlo;
         const int rx1 = x0 + EHB_T - 1 + p.hhi, ry1 = y0 + EHB_T - 1 + p.hhi;
-        const size_t bin0 = (size_t)wid * p.Lk;
         const size_t ibase = (size_t)item * H * W;
 
-        if (warp == 0) {
-            const uint32_t c = lane < p.Lk ? p.cnt[bin0 + lane] : 0u;
-            const unsigned b = __ballot_sync(0xffffffffu, c > 0);
-            if (c > 0) {
+        if (warp == 0) {   // links whose plane touches this tile's window
+            bool hit = false;
+            EhbPlane pl;
+            if (lane < p.L) {
+                pl = p.plane[(size_t)item * p.L + lane];
+                hit = pl.w > 0 && pl.x0 <= rx1 && pl.x0 + pl.w - 1 >= rx0 && pl.y0 <= ry1 && pl.y0 + pl.h - 1 >= ry0;
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, hit);
+            if (hit) {
                 const int k = __popc(b & ((1u << lane) - 1u));
                 sm.links[k] = lane;
-                sm.lstart[k] = p.start[bin0 + lane];
-                sm.lcnt[k] = c;
+                sm.pl[k] = pl;
             }
             if (lane == 0) { sm.nP = __popc(b); sm.segStart[0] = 0; }
         }
-        for (int i = tid; i < p.L * 16; i += EHB_RTHREADS) sm.mvp[i] = __ldg(p.mvp + (size_t)item * p.L * 16 + i);
+        for (int i = tid; i < p.L * 16; i += EHB_TTHREADS) sm.mvp[i] = __ldg(p.mvp + (size_t)item * p.L * 16 + i);
         if (needAA)
-            for (int i = tid; i < EHB_NP; i += EHB_RTHREADS) sm.sum[i] = 0.f;
+            for (int i = tid; i < EHB_NP; i += EHB_TTHREADS) sm.sum[i] = 0.f;
         if (p.mode == EHB_MODE_AA_BWD)   // g = dL/dmask comes from the caller
-            for (int i = tid; i < (EHB_T + 1) * (EHB_T + 1); i += EHB_RTHREADS) {
+            for (int i = tid; i < (EHB_T + 1) * (EHB_T + 1); i += EHB_TTHREADS) {
                 const int qy = i / (EHB_T + 1), qx = i - qy * (EHB_T + 1);
                 const int px = x0 + qx, py = y0 + qy;
                 if (px < W && py < H)
@@ -499,84 +630,37 @@ __global__ void __launch_bounds__(EHB_RTHREADS, EHB_MIN_BLOCKS) ehb_k_raster(con
         const int nP = sm.nP;
 
         for (int k = 0; k < nP; k++) {
-            const int l = sm.links[k];   // UNION: the single bin holds triangles of every link
-            // ================================ raster of link k =================================================
-            for (int i = tid; i < EHB_NP; i += EHB_RTHREADS) sm.plane[i] = EHB_EMPTY;
-            const uint32_t lo = sm.lstart[k], n = sm.lcnt[k];
-            for (uint32_t b0 = 0; b0 < n; b0 += EHB_BATCH) {
-                __syncthreads();   // plane cleared / previous batch's records (or alpha planes) no longer in use
-                int ns = 0, wide = 0;
-                if (b0 + tid < n) {
-                    const uint32_t e = __ldg(p.pairs + lo + b0 + tid);
-                    const int el = e >> EHB_LINK_SHIFT;
-                    const int f = e & EHB_FACE_MASK;
-                    EhbTri s;
-                    if (ehb_tri_setup<true>(rb.link[el], sm.mvp + 16 * el, f, H, W, s) == 0) {
-                        const int xlo = max(s.pxlo, rx0), xhi = min(s.pxhi, rx1);
-                        const int ylo = max(s.pylo, ry0), yhi = min(s.pyhi, ry1);
-                        if (xlo <= xhi && ylo <= yhi) {
-                            EhbRec& rc = sm.ov.r.rec[tid];
-                            const int bx = 8 * W - 8, by = 8 * H - 8;
-                            const int sx = 16 * xlo - bx, sy = 16 * ylo - by;
-                            const int ex0 = s.x1 - s.x0, ey0 = s.y1 - s.y0, ex1 = s.x2 - s.x1, ey1 = s.y2 - s.y1,
-                                      ex2 = s.x0 - s.x2, ey2 = s.y0 - s.y2;
-                            rc.E[0] = (long long)ex0 * (sy - s.y0) - (long long)ey0 * (sx - s.x0) - (ehb_edge_inclusive(ex0, ey0, p.rule) ? 0 : 1);
-                            rc.E[1] = (long long)ex1 * (sy - s.y1) - (long long)ey1 * (sx - s.x1) - (ehb_edge_inclusive(ex1, ey1, p.rule) ? 0 : 1);
-                            rc.E[2] = (long long)ex2 * (sy - s.y2) - (long long)ey2 * (sx - s.x2) - (ehb_edge_inclusive(ex2, ey2, p.rule) ? 0 : 1);
-                            rc.ex[0] = ex0; rc.ex[1] = ex1; rc.ex[2] = ex2;
-                            rc.ey[0] = ey0; rc.ey[1] = ey1; rc.ey[2] = ey2;
-                            rc.geom = (uint32_t)(xhi - xlo + 1) | ((uint32_t)(yhi - ylo + 1) << 8) |
-                                      ((uint32_t)(xlo - rx0) << 16) | ((uint32_t)(ylo - ry0) << 24);
-                            rc.id = perLink ? (uint32_t)f : (uint32_t)(rb.foff[el] + f);
-                            float* cc = sm.ov.r.clip[tid];
-                            *reinterpret_cast<float4*>(cc) = make_float4(s.c0[0], s.c0[1], s.c0[2], s.c0[3]);
-                            *reinterpret_cast<float4*>(cc + 4) = make_float4(s.c1[0], s.c1[1], s.c1[2], s.c1[3]);
-                            *reinterpret_cast<float4*>(cc + 8) = make_float4(s.c2[0], s.c2[1], s.c2[2], s.c2[3]);
-                            ns = yhi - ylo + 1;   // rows of the clipped bbox
-                            // 32-bit edge arithmetic is exact while every edge vector stays below 2^15 sub-pixel units
-                            const int ext = max(max(abs(ex0), abs(ex1)), max(max(abs(ex2), abs(ey0)), max(abs(ey1), abs(ey2))));
-                            wide = ext >= 32768;
-                        }
-                    }
-                }
-                int inc = ns;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += v;
-                }
-                if (lane == 31) sm.warpTot[warp] = inc;
-                const int anyWide = __syncthreads_or(wide);
-                int wbase = 0, total = 0;
-#pragma unroll
-                for (int i = 0; i < EHB_RWARPS; i++) {
-                    const int v = sm.warpTot[i];
-                    if (i < warp) wbase += v;
-                    total += v;
-                }
-                sm.ov.r.off[tid] = wbase + inc - ns;
-                if (tid == 0) sm.ov.r.off[EHB_BATCH] = total;
-                __syncthreads();
-                if (anyWide) ehb_rows_fill<long long, double>(sm, total, warp, lane, rx0, ry0, xs, xo, ys, yo);
-                else ehb_rows_fill<int, float>(sm, total, warp, lane, rx0, ry0, xs, xo, ys, yo);
-            }
-            __syncthreads();
-
-            if (!needPairs) break;   // UNION: one pass, the plane is the result
+            const int l = sm.links[k];
             const EhbLink& lk = rb.link[l];
             const float* m = sm.mvp + 16 * l;
+            // ================================ window of link k's plane -> shared memory =========================
+            {
+                const EhbPlane pl = sm.pl[k];
+                int any = 0;
+                for (int i = tid; i < EHB_NP; i += EHB_TTHREADS) {
+                    const int ly = i / EHB_RS, lx = i - ly * EHB_RS;
+                    const int px = rx0 + lx - pl.x0, py = ry0 + ly - pl.y0;
+                    unsigned long long v = EHB_EMPTY;
+                    if (px >= 0 && py >= 0 && px < pl.w && py < pl.h && rx0 + lx <= rx1 && ry0 + ly <= ry1)
+                        v = p.pool[pl.off + (long long)py * pl.w + px];
+                    sm.plane[i] = v;
+                    any |= v != EHB_EMPTY;
+                }
+                if (!__syncthreads_or(any)) {   // the bbox touches the window but no sample does
+                    if (tid == 0) sm.segStart[k + 1] = sm.segStart[k];
+                    __syncthreads();
+                    continue;
+                }
+            }
             // ================================ row bitmasks and silhouette pairs =================================
-            for (int r = warp; r < EHB_RS; r += EHB_RWARPS) {
+            for (int r = warp; r < EHB_RS; r += EHB_TWARPS) {
                 const unsigned b0 = __ballot_sync(0xffffffffu, sm.plane[r * EHB_RS + lane] != EHB_EMPTY);
                 const unsigned b1 = __ballot_sync(0xffffffffu, lane < EHB_RS - 32 && sm.plane[r * EHB_RS + 32 + lane] != EHB_EMPTY);
                 if (lane == 0) sm.cov[r] = (unsigned long long)b0 | ((unsigned long long)b1 << 32);
             }
             if (tid == 0) sm.cov[EHB_RS] = 0ull;
-            if (needAA)   // the alpha planes reuse the raster records' storage
-                for (int i = tid; i < 2 * EHB_NP; i += EHB_RTHREADS) (&sm.ov.a.alpha[0][0])[i] = 0.f;
             __syncthreads();
             unsigned long long hxm = 0ull, vym = 0ull, ownm = 0ull;
-            int ownRow = 0;
             if (tid < EHB_RS) {
                 const int r = tid, py = ry0 + r;
                 const unsigned long long cm = sm.cov[r], cu = sm.cov[r + 1];
@@ -593,8 +677,7 @@ __global__ void __launch_bounds__(EHB_RTHREADS, EHB_MIN_BLOCKS) ehb_k_raster(con
                 const bool rowIn = py >= 0 && py < H;
                 if (rowIn) hxm = (cm ^ (cm >> 1)) & inX1 & wantH & ehb_bits(0, EHB_RS - 2);
                 if (rowIn && py < H - 1 && r < EHB_RS - 1) vym = (cm ^ cu) & inX & wantV;
-                ownRow = r >= hlo && r <= hlo + EHB_T - 1;
-                ownm = ownRow ? ehb_bits(hlo, hlo + EHB_T - 1) : 0ull;
+                ownm = (r >= hlo && r <= hlo + EHB_T - 1) ? ehb_bits(hlo, hlo + EHB_T - 1) : 0ull;
                 sm.hx[r] = hxm; sm.vy[r] = vym;
                 sm.rowCnt[r] = __popcll(hxm) + __popcll(vym);
             }
@@ -619,7 +702,7 @@ __global__ void __launch_bounds__(EHB_RTHREADS, EHB_MIN_BLOCKS) ehb_k_raster(con
             __syncthreads();
             const int seg1 = sm.segStart[k + 1];
             // ================================ blend weights, all lanes busy =====================================
-            for (int j = seg0 + tid; j < seg1; j += EHB_RTHREADS) {
+            for (int j = seg0 + tid; j < seg1; j += EHB_TTHREADS) {
                 EhbPairEnt& pe = pair_at(j);
                 const uint32_t pk = pe.packed;
                 const int idx = pk & 2047, d = (pk >> 11) & 1;
@@ -632,13 +715,13 @@ __global__ void __launch_bounds__(EHB_RTHREADS, EHB_MIN_BLOCKS) ehb_k_raster(con
                 pe.packed = pk | ((uint32_t)side << 13) | ((uint32_t)di << 14);
                 pe.tri = t;
                 pe.alpha = al;
-                if (needAA) sm.ov.a.alpha[d][idx] = al;
+                if (needAA) sm.alpha[d][idx] = al;
             }
             if (needAA) {
                 __syncthreads();
                 // ============================ gather: sum += colour + pair contributions ========================
                 // pixel (qx, qy) of the out region; column 32 (the extra one) is handled by the last pass
-                for (int q = tid; q < ow * EHB_T + (oext ? ow : 0); q += EHB_RTHREADS) {
+                for (int q = tid; q < ow * EHB_T + (oext ? ow : 0); q += EHB_TTHREADS) {
                     int qx, qy;
                     if (q < ow * EHB_T) { qy = q >> 5; qx = q & 31; } else { qy = q - ow * EHB_T; qx = EHB_T; }
                     const int lx = hlo + qx, ly = hlo + qy;
@@ -651,29 +734,26 @@ __global__ void __launch_bounds__(EHB_RTHREADS, EHB_MIN_BLOCKS) ehb_k_raster(con
                     const float cf = c ? 1.f : 0.f;
                     float o = cf, a;
                     // colour, pair(p,p+x), pair(p,p+y), pair(p-x,p), pair(p-y,p); the receiver is p0 when alpha > 0
-                    if (h0) { a = sm.ov.a.alpha[0][idx]; if (a > 0.f) o += a * ((c ? 0.f : 1.f) - cf); }
-                    if (v0) { a = sm.ov.a.alpha[1][idx]; if (a > 0.f) o += a * ((c ? 0.f : 1.f) - cf); }
-                    if (h1) { a = sm.ov.a.alpha[0][idx - 1]; if (!(a > 0.f) && a != 0.f) o += a * (cf - (c ? 0.f : 1.f)); }
-                    if (v1) { a = sm.ov.a.alpha[1][idx - EHB_RS]; if (!(a > 0.f) && a != 0.f) o += a * (cf - (c ? 0.f : 1.f)); }
+                    if (h0) { a = sm.alpha[0][idx]; if (a > 0.f) o += a * ((c ? 0.f : 1.f) - cf); }
+                    if (v0) { a = sm.alpha[1][idx]; if (a > 0.f) o += a * ((c ? 0.f : 1.f) - cf); }
+                    if (h1) { a = sm.alpha[0][idx - 1]; if (!(a > 0.f) && a != 0.f) o += a * (cf - (c ? 0.f : 1.f)); }
+                    if (v1) { a = sm.alpha[1][idx - EHB_RS]; if (!(a > 0.f) && a != 0.f) o += a * (cf - (c ? 0.f : 1.f)); }
                     sm.sum[idx] = sm.sum[idx] + o;   // links are added in link order (rb_solver.py:68); absent links add 0
+                }
+                __syncthreads();
+                for (int j = seg0 + tid; j < seg1; j += EHB_TTHREADS) {   // undo the scatter: alpha planes back to zero
+                    const uint32_t pk = pair_at(j).packed;
+                    sm.alpha[(pk >> 11) & 1][pk & 2047] = 0.f;
                 }
             }
             __syncthreads();
         }
 
-        if (p.mode == EHB_MODE_UNION) {
-            for (int i = tid; i < EHB_T * EHB_T; i += EHB_RTHREADS) {
-                const int px = x0 + (i & 31), py = y0 + (i >> 5);
-                if (px >= W || py >= H) continue;
-                const unsigned long long kk = sm.plane[(py - ry0) * EHB_RS + (px - rx0)];
-                p.out_u8[ibase + (size_t)(H - 1 - py) * W + px] =
-                    (kk != EHB_EMPTY) && ((uint32_t)(kk >> 32) > 0x80000000u);
-            }
-        } else if (needAA) {
+        if (needAA) {
             // S = min(sum, 1); loss; g = dL/dsum kept in sm.sum for the backward
             double lacc = 0.0;
             const bool haveRef = p.ref != nullptr || p.ref_u8 != nullptr;
-            for (int q = tid; q < ow * EHB_T + (oext ? ow : 0); q += EHB_RTHREADS) {
+            for (int q = tid; q < ow * EHB_T + (oext ? ow : 0); q += EHB_TTHREADS) {
                 int qx, qy;
                 if (q < ow * EHB_T) { qy = q >> 5; qx = q & 31; } else { qy = q - ow * EHB_T; qx = EHB_T; }
                 const int px = x0 + qx, py = y0 + qy;
@@ -710,7 +790,7 @@ __global__ void __launch_bounds__(EHB_RTHREADS, EHB_MIN_BLOCKS) ehb_k_raster(con
 #pragma unroll
                 for (int i = 0; i < 12; i++) acc[i] = 0.0;
                 bool had = false;
-                for (int j = seg0 + tid; j < seg1; j += EHB_RTHREADS) {
+                for (int j = seg0 + tid; j < seg1; j += EHB_TTHREADS) {
                     const EhbPairEnt pe = pair_at(j);
                     const float al = pe.alpha;
                     if (!(pe.packed & (1u << 12)) || al == 0.f) continue;

@@ -80,7 +80,7 @@ class PoseSolver:
     def _check_flags(self):
         flags, _ = self.ctx.status()
         if flags & 1:
-            self.ctx.grow_pairs()
+            self.ctx.grow_scratch()
             return False
         return True
 

@@ -43,10 +43,11 @@ extern "C" {
 #define EHB_E_ARG (-1)      /* bad argument (null pointer, size, unknown mesh id, resolution > 8160) */
 #define EHB_E_CUDA (-2)     /* CUDA runtime error or no device */
 #define EHB_E_CAPACITY (-3) /* scratch too small and cannot grow here (stream capture in progress) */
-#define EHB_E_OVERFLOW (-4) /* a previous launch overflowed the triangle/tile pair buffer (see ehb_ctx_status) */
+#define EHB_E_OVERFLOW (-4) /* the depth-plane pool stayed too small after growing (see ehb_ctx_status) */
 
 /* bits of *flags from ehb_ctx_status */
-#define EHB_FLAG_PAIR_OVERFLOW 1u /* pair buffer too small: results of that launch are incomplete */
+#define EHB_FLAG_POOL_OVERFLOW 1u /* depth-plane pool too small: results of that launch are incomplete */
+#define EHB_FLAG_PAIR_OVERFLOW EHB_FLAG_POOL_OVERFLOW
 #define EHB_FLAG_NEEDS_CLIP 2u    /* triangles crossing the near/far plane were skipped (not supported yet) */
 
 typedef void* ehb_ctx_t;
@@ -54,7 +55,7 @@ typedef void* ehb_ctx_t;
 EHB_API int ehb_version(void);
 EHB_API const char* ehb_last_error(void);
 
-/* Context = per-device scratch (tile bins, pair lists) + registered meshes.  Replaces dr.RasterizeCudaContext. */
+/* Context = per-device scratch (depth-plane pool, tile queue) + registered meshes.  Replaces dr.RasterizeCudaContext. */
 EHB_API int ehb_ctx_create(int device, ehb_ctx_t* out);
 EHB_API int ehb_ctx_destroy(ehb_ctx_t ctx);
 /* Pre-size scratch so later launches never allocate (required before CUDA-graph capture).
@@ -62,13 +63,13 @@ EHB_API int ehb_ctx_destroy(ehb_ctx_t ctx);
 EHB_API int ehb_ctx_reserve(ehb_ctx_t ctx, int n_items, int n_links, int max_faces, int H, int W);
 /* Tie rule for a pixel centre lying exactly on a snapped edge: 0 (default) or 1 (mirror); see DESIGN.md. */
 EHB_API int ehb_ctx_set_fill_rule(ehb_ctx_t ctx, int rule);
-/* Doubles the triangle/tile pair capacity used for later launches (call after EHB_FLAG_PAIR_OVERFLOW). */
-EHB_API int ehb_ctx_grow_pairs(ehb_ctx_t ctx);
+/* Doubles the depth-plane pool used for later launches (call after EHB_FLAG_POOL_OVERFLOW). */
+EHB_API int ehb_ctx_grow_scratch(ehb_ctx_t ctx);
 /* Per-kernel timing for benchmarks: while enabled every pass records CUDA events around its four kernels on the
- * caller's stream.  ehb_ctx_kernel_times synchronises, returns the summed milliseconds of
- * {count, alloc, fill, raster} over the passes recorded since the last query, and their number. */
+ * caller's stream.  ehb_ctx_kernel_times synchronises, returns the summed milliseconds of the five stages
+ * {bbox, plan, clear, raster (+ big), tiles} (ms5[5]) over the passes recorded since the last query, and their number. */
 EHB_API int ehb_ctx_profile(ehb_ctx_t ctx, int enable);
-EHB_API int ehb_ctx_kernel_times(ehb_ctx_t ctx, double* ms4, long long* n_passes);
+EHB_API int ehb_ctx_kernel_times(ehb_ctx_t ctx, double* ms5, long long* n_passes);
 /* Synchronises the device, returns and clears the sticky flags, reports triangles skipped for clipping. */
 EHB_API int ehb_ctx_status(ehb_ctx_t ctx, unsigned* flags, long long* n_need_clip);
 
