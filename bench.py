@@ -173,6 +173,8 @@ def run_b200(args):
     wl = WORKLOAD
     B, H, W, R = wl["B"], wl["H"], wl["W"], wl["ring"]
     ctx = Context(dev)
+    if os.environ.get("EHB_PIPES"):
+        ctx.set_pipelines(int(os.environ["EHB_PIPES"]))
     sets = build_sets(wl, rank, R)
     meshes = sets[0]["scene"]["meshes"]
     ids = [ctx.register_mesh(m.vertices, m.faces) for m in meshes]

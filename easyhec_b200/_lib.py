@@ -35,9 +35,11 @@ _PROTOS = {
     "ehb_ctx_destroy": (C.c_int, [C.c_void_p]),
     "ehb_ctx_reserve": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ehb_ctx_set_fill_rule": (C.c_int, [C.c_void_p, C.c_int]),
+    "ehb_ctx_set_pipelines": (C.c_int, [C.c_void_p, C.c_int]),
     "ehb_ctx_grow_scratch": (C.c_int, [C.c_void_p]),
     "ehb_ctx_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "ehb_ctx_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "ehb_ctx_debug_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]),
     "ehb_ctx_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint), C.POINTER(C.c_longlong)]),
     "ehb_mesh_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "ehb_mesh_update_verts": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
@@ -169,6 +171,9 @@ class Context:
     def set_fill_rule(self, rule: int):
         _check(lib().ehb_ctx_set_fill_rule(self._h, rule))
 
+    def set_pipelines(self, n: int):
+        _check(lib().ehb_ctx_set_pipelines(self._h, int(n)))
+
     def grow_scratch(self):
         _check(lib().ehb_ctx_grow_scratch(self._h))
 
@@ -187,6 +192,11 @@ class Context:
         n = C.c_longlong()
         _check(lib().ehb_ctx_kernel_times(self._h, ms, C.byref(n)))
         return dict(zip(("bbox", "plan", "clear", "raster", "tiles"), list(ms))), n.value
+
+    def debug_counters(self, reset=True):
+        out = (C.c_ulonglong * 16)()
+        _check(lib().ehb_ctx_debug_counters(self._h, out, int(reset)))
+        return list(out)
 
     def launch_count(self) -> int:
         return int(lib().ehb_launch_count(self._h))

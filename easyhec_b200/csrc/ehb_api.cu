@@ -62,31 +62,48 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+constexpr int MAX_PIPES = 4;
+
+// Scratch of one pipeline.  A call's items are split over up to MAX_PIPES independent pipelines that run on internal
+// streams: every kernel of the pass is latency / tail bound, so the pipelines fill each other's idle SMs.
+struct Scratch {
+    DevBuf<float4> vclip;             // pre-transformed vertices of one pass
+    DevBuf<int2> vsnap;
+    DevBuf<int> bbraw;                // raw snapped bounding boxes, kept at the "empty" sentinel between passes
+    DevBuf<EhbPlane> plane;
+    DevBuf<unsigned long long> pool;  // depth planes of one pass, bump-allocated
+    DevBuf<uint32_t> tileList, touch;
+    DevBuf<EhbRec> bigRec;
+    DevBuf<EhbUnit> units;
+    DevBuf<EhbPairEnt> spill;         // per k_tiles CTA: overflow of the shared-memory silhouette-pair list
+    EhbCounters* ctr = nullptr;
+    void release()
+    {
+        vclip.release(); vsnap.release(); bbraw.release(); plane.release(); pool.release(); tileList.release();
+        touch.release(); bigRec.release(); units.release(); spill.release();
+    }
+};
+
 struct Ctx {
     int device = 0;
     int nSM = 148;
     int occ = 4;                      // resident k_tiles CTAs per SM
     int rule = 0;
+    int nPipes = 2;
     std::vector<Mesh> meshes;
-    DevBuf<int> bbraw;                // raw snapped bounding boxes, kept at the "empty" sentinel between passes
-    DevBuf<EhbPlane> plane;
-    DevBuf<unsigned long long> pool;  // depth planes of one pass, bump-allocated
-    DevBuf<uint32_t> tileList;
-    DevBuf<EhbRec> bigRec;
-    DevBuf<EhbUnit> units;
-    DevBuf<EhbPairEnt> spill;         // per k_tiles CTA: overflow of the shared-memory silhouette-pair list
-    EhbCounters* ctr = nullptr;
-    EhbCounters* ctrHost = nullptr;   // pinned
+    Scratch sc[MAX_PIPES];
+    cudaStream_t pipeStream[MAX_PIPES] = {};
+    cudaEvent_t evFork = nullptr, evJoin[MAX_PIPES] = {};
+    EhbCounters* ctr = nullptr;       // device array [MAX_PIPES]
+    EhbCounters* ctrHost = nullptr;   // pinned mirror [MAX_PIPES]
     // staging for the host-buffer entry points
     DevBuf<float> mvpDev;
     DevBuf<double> outDev;            // loss[B] + gmvp[B*L*16]
     DevBuf<uint8_t> refDev, maskDev;
     DevBuf<unsigned long long> numDev;
-    float* mvpPinned = nullptr; size_t mvpPinnedN = 0;
-    double* outPinned = nullptr; size_t outPinnedN = 0;
     long long launches = 0;
-    bool profiling = false;           // per-kernel CUDA events (ehb_ctx_profile)
-    std::vector<cudaEvent_t> evPool;  // 5 events per profiled pass
+    bool profiling = false;           // per-kernel CUDA events (ehb_ctx_profile): forces a single pipeline
+    std::vector<cudaEvent_t> evPool;  // 6 events per profiled pass
     size_t evUsed = 0;
     double poolFactor = 2.0;          // plane pool = items * H * W * poolFactor entries (per-link mode); grown on overflow
 };
@@ -221,28 +238,31 @@ int build_robot(Ctx* c, const int* mesh_ids, int L, EhbRobot& rb)
     return EHB_OK;
 }
 
-int ensure_scratch(Ctx* c, int items, int L, int Lp, int H, int W, bool capturing)
+int ensure_scratch(Ctx* c, Scratch& sc, int items, int L, int Lp, int H, int W, int Vtot, bool capturing)
 {
     int r;
+    if ((r = sc.vclip.ensure((size_t)items * std::max(Vtot, 1), capturing))) return r;
+    if ((r = sc.vsnap.ensure((size_t)items * std::max(Vtot, 1), capturing))) return r;
     const int ntiles = ((W + EHB_T - 1) / EHB_T) * ((H + EHB_T - 1) / EHB_T);
-    if ((r = c->spill.ensure((size_t)c->nSM * c->occ * SPILL_PER_LINK * L, capturing))) return r;
+    if ((r = sc.spill.ensure((size_t)c->nSM * c->occ * SPILL_PER_LINK * L, capturing))) return r;
     const size_t nraw = (size_t)items * Lp * 4;
-    if (nraw > c->bbraw.n) {
-        if ((r = c->bbraw.ensure(nraw, capturing))) return r;
-        ehb_k_init_raw<<<64, 256>>>(c->bbraw.p, c->bbraw.n);
+    if (nraw > sc.bbraw.n) {
+        if ((r = sc.bbraw.ensure(nraw, capturing))) return r;
+        ehb_k_init_raw<<<64, 256>>>(sc.bbraw.p, sc.bbraw.n);
         CU(cudaDeviceSynchronize());
     }
-    if ((r = c->plane.ensure((size_t)items * Lp, capturing))) return r;
-    if ((r = c->tileList.ensure((size_t)items * ntiles, capturing))) return r;
-    if ((r = c->bigRec.ensure((size_t)BIG_CAP, capturing))) return r;
-    if ((r = c->units.ensure((size_t)UNIT_CAP, capturing))) return r;
+    if ((r = sc.plane.ensure((size_t)items * Lp, capturing))) return r;
+    if ((r = sc.tileList.ensure((size_t)items * ntiles, capturing))) return r;
+    if ((r = sc.touch.ensure((size_t)items * ntiles, capturing))) return r;
+    if ((r = sc.bigRec.ensure((size_t)BIG_CAP, capturing))) return r;
+    if ((r = sc.units.ensure((size_t)UNIT_CAP, capturing))) return r;
     const double f = Lp == 1 ? 1.0 : std::min(c->poolFactor, (double)Lp);
-    if ((r = c->pool.ensure((size_t)((double)items * H * W * f) + 1024, capturing))) return r;
+    if ((r = sc.pool.ensure((size_t)((double)items * H * W * f) + 1024, capturing))) return r;
     return EHB_OK;
 }
 
-int run_pass(Ctx* c, const int* mesh_ids, int L, int items, const float* mvp_dev, int H, int W, int mode, const Io& io,
-             cudaStream_t st)
+int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const float* mvp_dev, int H, int W, int mode,
+             const Io& io, cudaStream_t st)
 {
     if (!c) return fail(EHB_E_ARG, "null context");
     if (H < 1 || W < 1 || H > 8160 || W > 8160) return fail(EHB_E_ARG, "resolution %dx%d outside [1, 8160]", H, W);
@@ -268,13 +288,14 @@ int run_pass(Ctx* c, const int* mesh_ids, int L, int items, const float* mvp_dev
     }
     p.mode = mode; p.rule = c->rule; p.do_bwd = io.do_bwd; p.clamp = io.clamp; p.invB = io.invB;
     const bool capturing = is_capturing(st);
-    if ((r = ensure_scratch(c, items, L, p.Lp, H, W, capturing))) return r;
+    if ((r = ensure_scratch(c, sc, items, L, p.Lp, H, W, p.Vtot, capturing))) return r;
     p.mvp = mvp_dev;
-    p.bbraw = c->bbraw.p; p.plane = c->plane.p; p.pool = c->pool.p; p.poolCap = c->pool.n;
-    p.tileList = c->tileList.p; p.bigRec = c->bigRec.p; p.units = c->units.p; p.bigCap = BIG_CAP; p.unitCap = UNIT_CAP; p.ctr = c->ctr;
+    p.vclip = sc.vclip.p; p.vsnap = sc.vsnap.p;
+    p.bbraw = sc.bbraw.p; p.plane = sc.plane.p; p.pool = sc.pool.p; p.poolCap = sc.pool.n;
+    p.tileList = sc.tileList.p; p.touch = unionMode ? nullptr : sc.touch.p; p.bigRec = sc.bigRec.p; p.units = sc.units.p; p.bigCap = BIG_CAP; p.unitCap = UNIT_CAP; p.ctr = sc.ctr;
     p.ref = io.ref; p.ref_u8 = io.ref_u8; p.masks = io.masks; p.loss = io.loss; p.gmvp = io.gmvp; p.gpos = io.gpos;
     p.dy = io.dy; p.out_u8 = io.out_u8;
-    p.pairSpill = c->spill.p; p.spillCap = SPILL_PER_LINK * L;
+    p.pairSpill = sc.spill.p; p.spillCap = SPILL_PER_LINK * L;
 
     cudaEvent_t* ev = nullptr;
     if (c->profiling && !capturing) {
@@ -287,7 +308,7 @@ int run_pass(Ctx* c, const int* mesh_ids, int L, int items, const float* mvp_dev
         c->evUsed += 6;
     }
     if (ev) cudaEventRecord(ev[0], st);
-    ehb_k_bbox<<<dim3((unsigned)std::max(1, (p.Vtot + 255) / 256), (unsigned)items), 256, 0, st>>>(rb, p);
+    ehb_k_vertex<<<dim3((unsigned)std::max(1, (p.Vtot + 255) / 256), (unsigned)items), 256, 0, st>>>(rb, p);
     if (ev) cudaEventRecord(ev[1], st);
     const int planBlocks = (items * p.Lp + 255) / 256;
     const long long tileWarps = unionMode ? 0 : (long long)items * p.ntiles;
@@ -308,6 +329,40 @@ int run_pass(Ctx* c, const int* mesh_ids, int L, int items, const float* mvp_dev
     if (ev) cudaEventRecord(ev[5], st);
     c->launches += 6;
     CU(cudaGetLastError());
+    return EHB_OK;
+}
+
+// Split the items of one call over the context's pipelines (fork on internal streams, join back into `st`).
+int run_split(Ctx* c, const int* mesh_ids, int L, int items, const float* mvp_dev, int H, int W, int mode, const Io& io,
+              cudaStream_t st)
+{
+    if (!c) return fail(EHB_E_ARG, "null context");
+    const int n = (c->profiling || items < 2) ? 1 : std::min(c->nPipes, items);
+    if (n <= 1) return run_pass(c, c->sc[0], mesh_ids, L, items, mvp_dev, H, W, mode, io, st);
+    DeviceGuard guard(c->device);
+    const size_t px = (size_t)H * W;
+    CU(cudaEventRecord(c->evFork, st));
+    int first = 0;
+    for (int k = 0; k < n; k++) {
+        const int cnt = items / n + (k < items % n ? 1 : 0);
+        Io s = io;
+        if (s.ref) s.ref += first * px;
+        if (s.ref_u8) s.ref_u8 += first * px;
+        if (s.masks) s.masks += first * px;
+        if (s.dy) s.dy += first * px;
+        if (s.out_u8) s.out_u8 += first * px;
+        if (s.loss) s.loss += first;
+        if (s.gmvp) s.gmvp += (size_t)first * L * 16;
+        cudaStream_t sk = k == 0 ? st : c->pipeStream[k];
+        if (k > 0) CU(cudaStreamWaitEvent(sk, c->evFork, 0));
+        const int r = run_pass(c, c->sc[k], mesh_ids, L, cnt, mvp_dev + (size_t)first * L * 16, H, W, mode, s, sk);
+        if (r) return r;
+        if (k > 0) {
+            CU(cudaEventRecord(c->evJoin[k], sk));
+            CU(cudaStreamWaitEvent(st, c->evJoin[k], 0));
+        }
+        first += cnt;
+    }
     return EHB_OK;
 }
 
@@ -334,9 +389,15 @@ int ehb_ctx_create(int device, ehb_ctx_t* out)
     Ctx* c = new Ctx();
     c->device = device;
     c->nSM = prop.multiProcessorCount;
-    CU(cudaMalloc((void**)&c->ctr, sizeof(EhbCounters)));
-    CU(cudaMemset(c->ctr, 0, sizeof(EhbCounters)));
-    CU(cudaMallocHost((void**)&c->ctrHost, sizeof(EhbCounters)));
+    CU(cudaMalloc((void**)&c->ctr, MAX_PIPES * sizeof(EhbCounters)));
+    CU(cudaMemset(c->ctr, 0, MAX_PIPES * sizeof(EhbCounters)));
+    CU(cudaMallocHost((void**)&c->ctrHost, MAX_PIPES * sizeof(EhbCounters)));
+    CU(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+    for (int k = 0; k < MAX_PIPES; k++) {
+        c->sc[k].ctr = c->ctr + k;
+        CU(cudaStreamCreateWithFlags(&c->pipeStream[k], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->evJoin[k], cudaEventDisableTiming));
+    }
     CU(cudaFuncSetAttribute(ehb_k_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiles_smem()));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ, ehb_k_tiles, EHB_TTHREADS, tiles_smem()));
     c->occ = std::max(1, c->occ);
@@ -351,10 +412,9 @@ int ehb_ctx_destroy(ehb_ctx_t h)
     DeviceGuard guard(c->device);
     cudaDeviceSynchronize();
     for (auto& m : c->meshes) if (m.live) { cudaFree(m.verts); cudaFree(m.faces); cudaFree(m.opp); }
-    c->spill.release(); c->bbraw.release(); c->plane.release(); c->pool.release(); c->tileList.release(); c->bigRec.release(); c->units.release();
+    for (int k = 0; k < MAX_PIPES; k++) { c->sc[k].release(); cudaStreamDestroy(c->pipeStream[k]); cudaEventDestroy(c->evJoin[k]); }
+    cudaEventDestroy(c->evFork);
     c->mvpDev.release(); c->outDev.release(); c->refDev.release(); c->maskDev.release(); c->numDev.release();
-    if (c->mvpPinned) cudaFreeHost(c->mvpPinned);
-    if (c->outPinned) cudaFreeHost(c->outPinned);
     for (auto e : c->evPool) cudaEventDestroy(e);
     cudaFree(c->ctr);
     cudaFreeHost(c->ctrHost);
@@ -375,8 +435,12 @@ int ehb_ctx_reserve(ehb_ctx_t h, int n_items, int n_links, int max_faces, int H,
     Ctx* c = (Ctx*)h;
     if (!c || n_items < 1 || n_links < 1 || max_faces < 0 || H < 1 || W < 1) return fail(EHB_E_ARG, "bad reserve arguments");
     DeviceGuard guard(c->device);
-    int r = ensure_scratch(c, n_items, n_links, n_links, H, W, false);
-    if (r) return r;
+    int r = 0;
+    const int np = std::max(1, std::min(c->nPipes, n_items));
+    for (int k = 0; k < np; k++)   // every pipeline gets its share of the items (and pipeline 0 the whole, for profiling runs)
+        if ((r = ensure_scratch(c, c->sc[k], k == 0 ? n_items : (n_items + np - 1) / np, n_links, n_links, H, W,
+                                std::max(1, max_faces), false)))   // V <= 3 F
+            return r;
     if ((r = c->mvpDev.ensure((size_t)n_items * n_links * 16, false))) return r;
     if ((r = c->outDev.ensure((size_t)n_items * (1 + n_links * 16), false))) return r;
     return EHB_OK;
@@ -387,6 +451,19 @@ int ehb_ctx_grow_scratch(ehb_ctx_t h)
     Ctx* c = (Ctx*)h;
     if (!c) return fail(EHB_E_ARG, "null context");
     c->poolFactor *= 2.0;
+    return EHB_OK;
+}
+
+int ehb_ctx_debug_counters(ehb_ctx_t h, unsigned long long* out16, int reset)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || !out16) return fail(EHB_E_ARG, "null pointer argument");
+    DeviceGuard guard(c->device);
+    CU(cudaDeviceSynchronize());
+    EhbCounters hc;
+    CU(cudaMemcpy(&hc, c->ctr, sizeof hc, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 16; i++) out16[i] = hc.dbg[i];
+    if (reset) { for (int i = 0; i < 16; i++) hc.dbg[i] = 0; CU(cudaMemcpy(c->ctr, &hc, sizeof hc, cudaMemcpyHostToDevice)); }
     return EHB_OK;
 }
 
@@ -422,12 +499,22 @@ int ehb_ctx_status(ehb_ctx_t h, unsigned* flags, long long* n_need_clip)
     if (!c) return fail(EHB_E_ARG, "null context");
     DeviceGuard guard(c->device);
     CU(cudaDeviceSynchronize());
-    EhbCounters hc;
-    CU(cudaMemcpy(&hc, c->ctr, sizeof hc, cudaMemcpyDeviceToHost));
-    if (flags) *flags = hc.flags;
-    if (n_need_clip) *n_need_clip = (long long)hc.nNeedClip;
-    hc.flags = 0; hc.nNeedClip = 0;
-    CU(cudaMemcpy(c->ctr, &hc, sizeof hc, cudaMemcpyHostToDevice));
+    EhbCounters hc[MAX_PIPES];
+    CU(cudaMemcpy(hc, c->ctr, sizeof hc, cudaMemcpyDeviceToHost));
+    unsigned f = 0;
+    long long nc = 0;
+    for (int k = 0; k < MAX_PIPES; k++) { f |= hc[k].flags; nc += (long long)hc[k].nNeedClip; hc[k].flags = 0; hc[k].nNeedClip = 0; }
+    if (flags) *flags = f;
+    if (n_need_clip) *n_need_clip = nc;
+    CU(cudaMemcpy(c->ctr, hc, sizeof hc, cudaMemcpyHostToDevice));
+    return EHB_OK;
+}
+
+int ehb_ctx_set_pipelines(ehb_ctx_t h, int n)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || n < 1 || n > MAX_PIPES) return fail(EHB_E_ARG, "pipelines must be in [1, %d]", MAX_PIPES);
+    c->nPipes = n;
     return EHB_OK;
 }
 
@@ -499,9 +586,9 @@ int ehb_render_mask_fwd(ehb_ctx_t h, int mesh_id, const float* mvp_dev, int H, i
 {
     if (!out_dev) return fail(EHB_E_ARG, "null output pointer");
     Io io;
-    if (anti_aliasing) { io.masks = (float*)out_dev; return run_pass((Ctx*)h, &mesh_id, 1, 1, mvp_dev, H, W, EHB_MODE_AA_FWD, io, (cudaStream_t)stream); }
+    if (anti_aliasing) { io.masks = (float*)out_dev; return run_split((Ctx*)h, &mesh_id, 1, 1, mvp_dev, H, W, EHB_MODE_AA_FWD, io, (cudaStream_t)stream); }
     io.out_u8 = (uint8_t*)out_dev;
-    return run_pass((Ctx*)h, &mesh_id, 1, 1, mvp_dev, H, W, EHB_MODE_UNION, io, (cudaStream_t)stream);
+    return run_split((Ctx*)h, &mesh_id, 1, 1, mvp_dev, H, W, EHB_MODE_UNION, io, (cudaStream_t)stream);
 }
 
 int ehb_render_mask_bwd(ehb_ctx_t h, int mesh_id, const float* mvp_dev, int H, int W, const float* dy_dev,
@@ -518,7 +605,7 @@ int ehb_render_mask_bwd(ehb_ctx_t h, int mesh_id, const float* mvp_dev, int H, i
     }
     Io io;
     io.dy = dy_dev; io.gmvp = g_mvp_dev; io.gpos = g_pos_dev; io.do_bwd = 1;
-    return run_pass(c, &mesh_id, 1, 1, mvp_dev, H, W, EHB_MODE_AA_BWD, io, (cudaStream_t)stream);
+    return run_split(c, &mesh_id, 1, 1, mvp_dev, H, W, EHB_MODE_AA_BWD, io, (cudaStream_t)stream);
 }
 
 int ehb_render_views_fused(ehb_ctx_t h, const int* mesh_ids, int L, int B, const float* mvp_dev, const float* ref_dev,
@@ -530,7 +617,7 @@ int ehb_render_views_fused(ehb_ctx_t h, const int* mesh_ids, int L, int B, const
     Io io;
     io.ref = ref_dev; io.masks = masks_dev; io.loss = ref_dev ? loss_dev : nullptr; io.gmvp = do_bwd ? g_mvp_dev : nullptr;
     io.do_bwd = do_bwd ? 1 : 0; io.clamp = 1; io.invB = B > 0 ? 1.0f / (float)B : 1.f;
-    return run_pass((Ctx*)h, mesh_ids, L, B, mvp_dev, H, W, EHB_MODE_FUSED, io, (cudaStream_t)stream);
+    return run_split((Ctx*)h, mesh_ids, L, B, mvp_dev, H, W, EHB_MODE_FUSED, io, (cudaStream_t)stream);
 }
 
 int ehb_render_views_fused_u8(ehb_ctx_t h, const int* mesh_ids, int L, int B, const float* mvp_dev,
@@ -542,7 +629,7 @@ int ehb_render_views_fused_u8(ehb_ctx_t h, const int* mesh_ids, int L, int B, co
     Io io;
     io.ref_u8 = ref_u8_dev; io.masks = masks_dev; io.loss = loss_dev; io.gmvp = do_bwd ? g_mvp_dev : nullptr;
     io.do_bwd = do_bwd ? 1 : 0; io.clamp = 1; io.invB = B > 0 ? 1.0f / (float)B : 1.f;
-    return run_pass((Ctx*)h, mesh_ids, L, B, mvp_dev, H, W, EHB_MODE_FUSED, io, (cudaStream_t)stream);
+    return run_split((Ctx*)h, mesh_ids, L, B, mvp_dev, H, W, EHB_MODE_FUSED, io, (cudaStream_t)stream);
 }
 
 int ehb_render_binary_batch(ehb_ctx_t h, const int* mesh_ids, int L, int N, const float* mvp_dev, int H, int W,
@@ -551,7 +638,7 @@ int ehb_render_binary_batch(ehb_ctx_t h, const int* mesh_ids, int L, int N, cons
     if (!mesh_ids || !out_dev) return fail(EHB_E_ARG, "null pointer argument");
     Io io;
     io.out_u8 = out_dev;
-    return run_pass((Ctx*)h, mesh_ids, L, N, mvp_dev, H, W, EHB_MODE_UNION, io, (cudaStream_t)stream);
+    return run_split((Ctx*)h, mesh_ids, L, N, mvp_dev, H, W, EHB_MODE_UNION, io, (cudaStream_t)stream);
 }
 
 int ehb_variance_score(ehb_ctx_t h, const uint8_t* masks_dev, int Q, int C, long long n, double* score_dev, void* stream)
@@ -615,13 +702,12 @@ int ehb_solver_step_host(ehb_ctx_t h, const int* mesh_ids, int L, int B, const f
         if (r) return r;
         CU(cudaMemcpyAsync(loss_host, c->outDev.p, B * sizeof(double), cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(g_mvp_host, c->outDev.p + B, nm * sizeof(double), cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(c->ctrHost, c->ctr, sizeof(EhbCounters), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(c->ctrHost, c->ctr, MAX_PIPES * sizeof(EhbCounters), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        if (!(c->ctrHost->flags & EHB_FLAG_PAIR_OVERFLOW)) break;
+        { unsigned f = 0; for (int k = 0; k < MAX_PIPES; k++) f |= c->ctrHost[k].flags; if (!(f & EHB_FLAG_POOL_OVERFLOW)) break; }
         if (attempt >= 6) return fail(EHB_E_OVERFLOW, "plane pool overflow persists after growing");
         c->poolFactor *= 2.0;   // grow the plane pool and run the step again
-        unsigned int zero = 0;
-        CU(cudaMemcpyAsync(&c->ctr->flags, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
+        for (int k = 0; k < MAX_PIPES; k++) CU(cudaMemsetAsync(&c->ctr[k].flags, 0, sizeof(unsigned), st));
     }
     return EHB_OK;
 }
@@ -646,13 +732,12 @@ int ehb_solver_step_host_u8(ehb_ctx_t h, const int* mesh_ids, int L, int B, cons
         if (r) return r;
         CU(cudaMemcpyAsync(loss_host, c->outDev.p, B * sizeof(double), cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(g_mvp_host, c->outDev.p + B, nm * sizeof(double), cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(c->ctrHost, c->ctr, sizeof(EhbCounters), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(c->ctrHost, c->ctr, MAX_PIPES * sizeof(EhbCounters), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        if (!(c->ctrHost->flags & EHB_FLAG_PAIR_OVERFLOW)) break;
+        { unsigned f = 0; for (int k = 0; k < MAX_PIPES; k++) f |= c->ctrHost[k].flags; if (!(f & EHB_FLAG_POOL_OVERFLOW)) break; }
         if (attempt >= 6) return fail(EHB_E_OVERFLOW, "plane pool overflow persists after growing");
         c->poolFactor *= 2.0;
-        unsigned int zero = 0;
-        CU(cudaMemcpyAsync(&c->ctr->flags, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
+        for (int k = 0; k < MAX_PIPES; k++) CU(cudaMemsetAsync(&c->ctr[k].flags, 0, sizeof(unsigned), st));
     }
     return EHB_OK;
 }

@@ -4,7 +4,8 @@
 // before summing (rb_solver.py:62-68), so visibility is resolved per (item, link) -- an "item" is a camera view or
 // one render of a batch.  Each (item, link) gets a 64-bit (depth key | triangle id) plane covering only the
 // link's screen bounding box; for robot views all planes of a step are a few tens of MB and stay L2-resident.
-//   k_bbox   : one thread per (item, vertex): transform, snap -> per-(item, link) bounding box (warp reduce + atomics)
+//   k_vertex : one thread per (item, vertex): transform and snap ONCE (a vertex is shared by ~6 triangles), keep the
+//              clip-space and snapped positions (a few MB, L2-resident), reduce the per-(item, link) bounding box
 //   k_plan   : (a) one thread per plane: pixel bbox, bump allocation of the plane in the plane pool;
 //              (b) one warp per 32x32 tile: tiles no link's bbox touches are finished right here as a float4 stream
 //                  (mask = 0, loss += ref^2) -- the HBM-bound part of the frame; the others go to the tile queue
@@ -48,12 +49,14 @@ struct EhbUnit { uint32_t rec; unsigned short dx0, dy0; };   // a 64 x 32 pixel 
 struct EhbCounters {
     unsigned long long planeCursor;
     unsigned long long nNeedClip;
-    unsigned int nTiles;
+    unsigned int nTiles;     // tiles touched by >= 2 link bboxes: listed from the front of tileList (served first) ...
+    unsigned int nLight;     // ... the others from the back
     unsigned int workCursor;
     unsigned int nBigRec;    // deferred (not small) triangles: records parked in global memory ...
     unsigned int nUnits;     // ... and cut into bounded units that k_raster_big spreads over the whole chip
     unsigned int flags;      // 1: plane pool too small (results invalid, grow and rerun), 2: triangles need clipping
     unsigned int pad;
+    unsigned long long dbg[16];   // EHB_TIMING builds: cycles per phase of k_tiles (thread 0 of every CTA)
 };
 
 struct EhbParams {
@@ -63,11 +66,14 @@ struct EhbParams {
     int mode, rule, do_bwd, clamp;
     float invB;
     const float* mvp;        // [items, L, 16]
+    float4* vclip;           // [items, Vtot]  clip-space position of every vertex (written by k_vertex)
+    int2* vsnap;             // [items, Vtot]  snapped screen position (1/16 px), x = INT_MIN when not drawable
     int* bbraw;              // [items, Lp, 4]  min X, min Y, max X, max Y of the snapped vertices
     EhbPlane* plane;         // [items, Lp]
     unsigned long long* pool;
     unsigned long long poolCap;
     uint32_t* tileList;      // [items * ntiles]
+    uint32_t* touch;         // [items * ntiles]  bit l: a triangle of link l reaches into this tile's window
     struct EhbRec* bigRec;   // [bigCap]
     EhbUnit* units;          // [unitCap]
     int bigCap, unitCap;
@@ -86,7 +92,9 @@ struct EhbParams {
 
 #define EHB_RAW_MIN 0x7F7F7F7F          // memset(0x7F) / memset(0x80) patterns: "no vertex yet"
 #define EHB_RAW_MAX ((int)0x80808080)
+#ifndef EHB_SMALL_AREA
 #define EHB_SMALL_AREA 96               // triangles whose clipped bbox has more candidate samples are deferred
+#endif
 #define EHB_UNIT_W 64
 #define EHB_UNIT_H 32
 
@@ -125,8 +133,8 @@ __device__ __forceinline__ bool ehb_raw_to_pixels(const int* raw, int H, int W, 
     return x0 <= x1 && y0 <= y1;
 }
 
-// ------------------------------------------------------------------------------------------------ k_bbox
-__global__ void __launch_bounds__(256) ehb_k_bbox(const __grid_constant__ EhbRobot rb,
+// ------------------------------------------------------------------------------------------------ k_vertex
+__global__ void __launch_bounds__(256) ehb_k_vertex(const __grid_constant__ EhbRobot rb,
                                                   const __grid_constant__ EhbParams p)
 {
     const int item = blockIdx.y;
@@ -136,6 +144,7 @@ __global__ void __launch_bounds__(256) ehb_k_bbox(const __grid_constant__ EhbRob
         if (item == 0 && threadIdx.x == 0) {
             p.ctr->planeCursor = 0ull;
             p.ctr->nTiles = 0u;
+            p.ctr->nLight = 0u;
             p.ctr->workCursor = 0u;
             p.ctr->nBigRec = 0u;
             p.ctr->nUnits = 0u;
@@ -150,33 +159,25 @@ __global__ void __launch_bounds__(256) ehb_k_bbox(const __grid_constant__ EhbRob
         float m[16], c[4];
         ehb_load_mvp(p.mvp + ((size_t)item * p.L + lk) * 16, m);
         ehb_xform(__ldg(rb.link[lk].verts + (g - rb.voff[lk])), m, c);
+        int2 sn = make_int2(INT_MIN, 0);
         if (c[3] >= fabsf(c[2])) {   // only such vertices can belong to a drawable triangle
             const float r = 1.0f / c[3];
             X = ehb_rni_sat(c[0] * r * (float)(p.W * 8));
             Y = ehb_rni_sat(c[1] * r * (float)(p.H * 8));
+            sn = make_int2(X, Y);
             const int G = 1 << 28;
             if (X <= G && X >= -G && Y <= G && Y >= -G) l = p.Lp == 1 ? 0 : lk;
         }
+        p.vclip[(size_t)item * p.Vtot + g] = make_float4(c[0], c[1], c[2], c[3]);
+        p.vsnap[(size_t)item * p.Vtot + g] = sn;
     }
-    // warp-aggregate when the whole warp works on the same plane, else per-lane atomics
-    const int l0 = __shfl_sync(0xffffffffu, l, 0);
-    const bool same = __all_sync(0xffffffffu, l == l0 || l < 0);
-    if (same) {
-        int mnx = l >= 0 ? X : INT_MAX, mny = l >= 0 ? Y : INT_MAX, mxx = l >= 0 ? X : INT_MIN, mxy = l >= 0 ? Y : INT_MIN;
-        int lv = l;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-            mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o)); mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
-            lv = max(lv, __shfl_xor_sync(0xffffffffu, lv, o));
-        }
-        if (lane == 0 && lv >= 0) {
-            int* raw = p.bbraw + ((size_t)item * p.Lp + lv) * 4;
-            atomicMin(raw + 0, mnx); atomicMin(raw + 1, mny); atomicMax(raw + 2, mxx); atomicMax(raw + 3, mxy);
-        }
-    } else if (l >= 0) {
+    // one set of atomics per (warp, plane): lanes are grouped by plane with match.any, reduced with redux
+    const unsigned grp = __match_any_sync(0xffffffffu, l);
+    const int mnx = __reduce_min_sync(grp, X), mny = __reduce_min_sync(grp, Y);
+    const int mxx = __reduce_max_sync(grp, X), mxy = __reduce_max_sync(grp, Y);
+    if (l >= 0 && lane == __ffs(grp) - 1) {
         int* raw = p.bbraw + ((size_t)item * p.Lp + l) * 4;
-        atomicMin(raw + 0, X); atomicMin(raw + 1, Y); atomicMax(raw + 2, X); atomicMax(raw + 3, Y);
+        atomicMin(raw + 0, mnx); atomicMin(raw + 1, mny); atomicMax(raw + 2, mxx); atomicMax(raw + 3, mxy);
     }
 }
 
@@ -258,8 +259,13 @@ __global__ void __launch_bounds__(256) ehb_k_plan(const __grid_constant__ EhbPar
             hit = x0 <= rx1 && x1 >= rx0 && y0 <= ry1 && y1 >= ry0;
         }
     }
-    if (__any_sync(0xffffffffu, hit)) {
-        if (lane == 0) p.tileList[atomicAdd(&p.ctr->nTiles, 1u)] = (uint32_t)wid;
+    const unsigned hits = __ballot_sync(0xffffffffu, hit);
+    if (hits) {
+        // tiles with several links take several times longer in k_tiles: queue them first (front), the rest from the back
+        if (lane == 0) {
+            if (__popc(hits) >= 2) p.tileList[atomicAdd(&p.ctr->nTiles, 1u)] = (uint32_t)wid;
+            else p.tileList[(unsigned)(p.items * p.ntiles) - 1u - atomicAdd(&p.ctr->nLight, 1u)] = (uint32_t)wid;
+        }
     } else if (p.mode != EHB_MODE_UNION && p.mode != EHB_MODE_AA_BWD) {
         ehb_stream_empty_tile(p, item, tx, ty, lane);
     }
@@ -275,13 +281,17 @@ __global__ void __launch_bounds__(256) ehb_k_clear(const __grid_constant__ EhbPa
          i += (unsigned long long)gridDim.x * blockDim.x)
         p2[i] = make_ulonglong2(EHB_EMPTY, EHB_EMPTY);
     if ((total & 1ull) && blockIdx.x == 0 && threadIdx.x == 0) p.pool[total - 1] = EHB_EMPTY;
+    if (p.touch)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.items * p.ntiles; i += gridDim.x * blockDim.x) p.touch[i] = 0u;
     // the raw bounding boxes have been consumed by k_plan: reset them for the next pass
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.items * p.Lp * 4; i += gridDim.x * blockDim.x)
         p.bbraw[i] = (i & 2) ? EHB_RAW_MAX : EHB_RAW_MIN;
 }
 
 // ------------------------------------------------------------------------------------------------ k_raster
+#ifndef EHB_RWARPS
 #define EHB_RWARPS 8         // warps per raster CTA; every warp works alone on batches of 32 triangles
+#endif
 
 struct __align__(16) EhbRec {
     long long E[3];          // edge function minus its threshold at the first candidate sample (covered: >= 0)
@@ -312,86 +322,136 @@ __device__ __forceinline__ void ehb_row_span(const I R0, const I R1, const I R2,
             if (R[k] < 0) {   // smallest dx with R + ax*dx >= 0
                 int q = (int)fmin((F)w, ceil(ehb_fast_div((F)(-R[k]), (F)ax[k])));
                 q = max(q, 0);
-                while (q > 0 && R[k] + ax[k] * (I)(q - 1) >= 0) q--;
-                while (q < w && R[k] + ax[k] * (I)q < 0) q++;
+                // the estimate is within 1e-3 of the true quotient (|q| <= w <= 8192), so one exact step fixes it
+                if (q > 0 && R[k] + ax[k] * (I)(q - 1) >= 0) q--;
+                else if (q < w && R[k] + ax[k] * (I)q < 0) q++;
                 lo = max(lo, q);
             }
         } else if (ax[k] < 0) {
             if (R[k] < 0) hi = -1;
             else {            // largest dx with R + ax*dx >= 0
                 int q = (int)fmin((F)(w - 1), floor(ehb_fast_div((F)R[k], (F)(-ax[k]))));
-                while (q < w - 1 && R[k] + ax[k] * (I)(q + 1) >= 0) q++;
-                while (q >= 0 && R[k] + ax[k] * (I)q < 0) q--;
+                if (q < w - 1 && R[k] + ax[k] * (I)(q + 1) >= 0) q++;
+                else if (q >= 0 && R[k] + ax[k] * (I)q < 0) q--;
                 hi = min(hi, q);
             }
         } else if (R[k] < 0) hi = -1;
     }
 }
 
-// setup of one triangle -> record.  Returns the number of rows of its clipped bbox (0: nothing to draw).
-__device__ __forceinline__ int ehb_make_record(const EhbRobot& rb, const EhbParams& p, int item, int g, EhbRec& rc,
-                                               bool count_clip)
+// Record word layout (32 x 32-bit words): E[3] (2 words each) | ex[3] | ey[3] | x0 y0 w h | base (2) | pw | id | clip[12].
+// k_raster keeps the 32 records of a warp transposed in shared memory (word k of record t at [k*32 + t]: conflict-free
+// for "every lane its own record" and for arbitrary t); k_raster_big keeps one record as is.
+template <int TS, int KS>
+struct EhbRecView {
+    const uint32_t* b;
+    __device__ __forceinline__ uint32_t u(int t, int k) const { return b[t * TS + k * KS]; }
+    __device__ __forceinline__ int i(int t, int k) const { return (int)u(t, k); }
+    __device__ __forceinline__ float f(int t, int k) const { return __uint_as_float(u(t, k)); }
+    __device__ __forceinline__ long long ll(int t, int k) const
+    {
+        return (long long)(((unsigned long long)u(t, k + 1) << 32) | (unsigned long long)u(t, k));
+    }
+};
+typedef EhbRecView<1, 32> EhbRecSoA;
+typedef EhbRecView<32, 1> EhbRecAoS;
+
+__device__ __forceinline__ void ehb_rec_store_soa(uint32_t* b, int t, const EhbRec& rc)
+{
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        b[(2 * k) * 32 + t] = (uint32_t)(unsigned long long)rc.E[k];
+        b[(2 * k + 1) * 32 + t] = (uint32_t)((unsigned long long)rc.E[k] >> 32);
+        b[(6 + k) * 32 + t] = (uint32_t)rc.ex[k];
+        b[(9 + k) * 32 + t] = (uint32_t)rc.ey[k];
+    }
+    b[12 * 32 + t] = (uint32_t)rc.x0; b[13 * 32 + t] = (uint32_t)rc.y0; b[14 * 32 + t] = (uint32_t)rc.w; b[15 * 32 + t] = (uint32_t)rc.h;
+    b[16 * 32 + t] = (uint32_t)(unsigned long long)rc.base; b[17 * 32 + t] = (uint32_t)((unsigned long long)rc.base >> 32);
+    b[18 * 32 + t] = (uint32_t)rc.pw; b[19 * 32 + t] = rc.id;
+#pragma unroll
+    for (int k = 0; k < 12; k++) b[(20 + k) * 32 + t] = __float_as_uint(rc.clip[k]);
+}
+
+// Primitive assembly of one triangle from the pre-transformed vertices -> record.  Same tests, in the same order,
+// as ehb_tri_setup (the oracle's eho_rasterize).  Returns the number of rows of its clipped bbox (0: nothing to draw).
+__device__ __forceinline__ int ehb_make_record(const EhbRobot& rb, const EhbParams& p, int item, int g, EhbRec& rc)
 {
     const int l = ehb_find_link(rb.foff, rb.L, g);
     const int f = g - rb.foff[l];
-    float m[16];
-    ehb_load_mvp(p.mvp + ((size_t)item * p.L + l) * 16, m);
-    EhbTri s;
-    const int st = ehb_tri_setup<false>(rb.link[l], m, f, p.H, p.W, s);
-    if (st == 2 && count_clip) {
+    const EhbLink& lk = rb.link[l];
+    const int4 id = __ldg(lk.faces + f);
+    if ((unsigned)id.x >= (unsigned)lk.V || (unsigned)id.y >= (unsigned)lk.V || (unsigned)id.z >= (unsigned)lk.V) return 0;
+    const size_t vb = (size_t)item * p.Vtot + rb.voff[l];
+    const float4 c0 = p.vclip[vb + id.x], c1 = p.vclip[vb + id.y], c2 = p.vclip[vb + id.z];
+    if ((c0.w < c0.x && c1.w < c1.x && c2.w < c2.x) || (c0.w < -c0.x && c1.w < -c1.x && c2.w < -c2.x) ||
+        (c0.w < c0.y && c1.w < c1.y && c2.w < c2.y) || (c0.w < -c0.y && c1.w < -c1.y && c2.w < -c2.y) ||
+        (c0.w < c0.z && c1.w < c1.z && c2.w < c2.z) || (c0.w < -c0.z && c1.w < -c1.z && c2.w < -c2.z))
+        return 0;
+    const int2 s0 = p.vsnap[vb + id.x], s1 = p.vsnap[vb + id.y], s2 = p.vsnap[vb + id.z];
+    const int G = 1 << 28;
+    if (s0.x == INT_MIN || s1.x == INT_MIN || s2.x == INT_MIN ||   // a vertex outside the depth range: needs the clipper
+        s0.x > G || s0.x < -G || s0.y > G || s0.y < -G || s1.x > G || s1.x < -G || s1.y > G || s1.y < -G ||
+        s2.x > G || s2.x < -G || s2.y > G || s2.y < -G) {
         atomicAdd(&p.ctr->nNeedClip, 1ull);
         atomicOr(&p.ctr->flags, 2u);
+        return 0;
     }
-    if (st != 0) return 0;
+    int x0 = s0.x, y0 = s0.y, x1 = s1.x, y1 = s1.y, x2 = s2.x, y2 = s2.y;
+    const long long area = (long long)(x1 - x0) * (y2 - y0) - (long long)(y1 - y0) * (x2 - x0);
+    if (area == 0) return 0;
+    if (area < 0) { int t = x1; x1 = x2; x2 = t; t = y1; y1 = y2; y2 = t; }
+    const int bx = 8 * p.W - 8, by = 8 * p.H - 8;
+    const int pxlo = max((min(x0, min(x1, x2)) + bx + 15) >> 4, 0), pxhi = min((max(x0, max(x1, x2)) + bx) >> 4, p.W - 1);
+    const int pylo = max((min(y0, min(y1, y2)) + by + 15) >> 4, 0), pyhi = min((max(y0, max(y1, y2)) + by) >> 4, p.H - 1);
+    if (pxlo > pxhi || pylo > pyhi) return 0;
     const EhbPlane pl = p.plane[(size_t)item * p.Lp + (p.Lp == 1 ? 0 : l)];
     if (pl.w == 0) return 0;   // pool overflow: flagged, the pass is rerun
-    const int bx = 8 * p.W - 8, by = 8 * p.H - 8;
-    const int sx = 16 * s.pxlo - bx, sy = 16 * s.pylo - by;
-    const int ex0 = s.x1 - s.x0, ey0 = s.y1 - s.y0, ex1 = s.x2 - s.x1, ey1 = s.y2 - s.y1, ex2 = s.x0 - s.x2,
-              ey2 = s.y0 - s.y2;
-    rc.E[0] = (long long)ex0 * (sy - s.y0) - (long long)ey0 * (sx - s.x0) - (ehb_edge_inclusive(ex0, ey0, p.rule) ? 0 : 1);
-    rc.E[1] = (long long)ex1 * (sy - s.y1) - (long long)ey1 * (sx - s.x1) - (ehb_edge_inclusive(ex1, ey1, p.rule) ? 0 : 1);
-    rc.E[2] = (long long)ex2 * (sy - s.y2) - (long long)ey2 * (sx - s.x2) - (ehb_edge_inclusive(ex2, ey2, p.rule) ? 0 : 1);
+    const int sx = 16 * pxlo - bx, sy = 16 * pylo - by;
+    const int ex0 = x1 - x0, ey0 = y1 - y0, ex1 = x2 - x1, ey1 = y2 - y1, ex2 = x0 - x2, ey2 = y0 - y2;
+    rc.E[0] = (long long)ex0 * (sy - y0) - (long long)ey0 * (sx - x0) - (ehb_edge_inclusive(ex0, ey0, p.rule) ? 0 : 1);
+    rc.E[1] = (long long)ex1 * (sy - y1) - (long long)ey1 * (sx - x1) - (ehb_edge_inclusive(ex1, ey1, p.rule) ? 0 : 1);
+    rc.E[2] = (long long)ex2 * (sy - y2) - (long long)ey2 * (sx - x2) - (ehb_edge_inclusive(ex2, ey2, p.rule) ? 0 : 1);
     rc.ex[0] = ex0; rc.ex[1] = ex1; rc.ex[2] = ex2;
     rc.ey[0] = ey0; rc.ey[1] = ey1; rc.ey[2] = ey2;
-    rc.x0 = s.pxlo; rc.y0 = s.pylo; rc.w = s.pxhi - s.pxlo + 1; rc.h = s.pyhi - s.pylo + 1;
+    rc.x0 = pxlo; rc.y0 = pylo; rc.w = pxhi - pxlo + 1; rc.h = pyhi - pylo + 1;
     rc.base = pl.off - (long long)pl.y0 * pl.w - pl.x0;
     rc.pw = pl.w;
     rc.id = p.Lp == 1 ? (uint32_t)g : (uint32_t)f;
-#pragma unroll
-    for (int i = 0; i < 4; i++) { rc.clip[i] = s.c0[i]; rc.clip[4 + i] = s.c1[i]; rc.clip[8 + i] = s.c2[i]; }
+    rc.clip[0] = c0.x; rc.clip[1] = c0.y; rc.clip[2] = c0.z; rc.clip[3] = c0.w;
+    rc.clip[4] = c1.x; rc.clip[5] = c1.y; rc.clip[6] = c1.z; rc.clip[7] = c1.w;
+    rc.clip[8] = c2.x; rc.clip[9] = c2.y; rc.clip[10] = c2.z; rc.clip[11] = c2.w;
     return rc.h;
 }
 
-__device__ __forceinline__ void ehb_shade_global(const EhbRec& rc, int px, int py, unsigned long long* pool, float xs,
+template <class RV>
+__device__ __forceinline__ void ehb_shade_global(const RV rv, int t, int px, int py, unsigned long long* pool, float xs,
                                                  float xo, float ys, float yo)
 {
-    const float4 a = *reinterpret_cast<const float4*>(rc.clip), b = *reinterpret_cast<const float4*>(rc.clip + 4),
-                 d = *reinterpret_cast<const float4*>(rc.clip + 8);
-    const float p0[4] = {a.x, a.y, a.z, a.w}, p1[4] = {b.x, b.y, b.z, b.w}, p2[4] = {d.x, d.y, d.z, d.w};
+    const float p0[4] = {rv.f(t, 20), rv.f(t, 21), rv.f(t, 22), rv.f(t, 23)};
+    const float p1[4] = {rv.f(t, 24), rv.f(t, 25), rv.f(t, 26), rv.f(t, 27)};
+    const float p2[4] = {rv.f(t, 28), rv.f(t, 29), rv.f(t, 30), rv.f(t, 31)};
     const float fx = xs * (float)px + xo, fy = ys * (float)py + yo;
     const float zw = ehb_shade_zw(p0, p1, p2, fx, fy);
-    const unsigned long long key = ((unsigned long long)ehb_order_key(zw) << 32) | rc.id;
-    atomicMin(pool + (rc.base + (long long)py * rc.pw + px), key);
+    const unsigned long long key = ((unsigned long long)ehb_order_key(zw) << 32) | rv.u(t, 19);
+    atomicMin(pool + (rv.ll(t, 16) + (long long)py * rv.i(t, 18) + px), key);
 }
 
 // One group of up to 32 rows (one per lane): spans, then the warp shades the covered samples 32 at a time.
 // `t` = this lane's record index in recs (-1: no row), `dy` = its row inside that record's bbox.
-template <typename I, typename F>
-__device__ __forceinline__ void ehb_rows_group(const EhbRec* recs, int t, int dy, int lane, unsigned long long* pool,
+template <typename I, typename F, class RV>
+__device__ __forceinline__ void ehb_rows_group(const RV rv, int t, int dy, int lane, unsigned long long* pool,
                                                float xs, float xo, float ys, float yo, int cx0 = 0, int cx1 = 1 << 20)
 {
     int len = 0;
     uint32_t pos = 0;   // t << 26 | py << 13 | px of the first covered sample of this lane's row
     if (t >= 0) {
-        const EhbRec& rc = recs[t];
-        const I R0 = (I)rc.E[0] + (I)16 * (I)rc.ex[0] * (I)dy, R1 = (I)rc.E[1] + (I)16 * (I)rc.ex[1] * (I)dy,
-                R2 = (I)rc.E[2] + (I)16 * (I)rc.ex[2] * (I)dy;
+        const I R0 = (I)rv.ll(t, 0) + (I)16 * (I)rv.i(t, 6) * (I)dy, R1 = (I)rv.ll(t, 2) + (I)16 * (I)rv.i(t, 7) * (I)dy,
+                R2 = (I)rv.ll(t, 4) + (I)16 * (I)rv.i(t, 8) * (I)dy;
         int a, b;
-        ehb_row_span<I, F>(R0, R1, R2, (I)-16 * (I)rc.ey[0], (I)-16 * (I)rc.ey[1], (I)-16 * (I)rc.ey[2], rc.w, a, b);
+        ehb_row_span<I, F>(R0, R1, R2, (I)-16 * (I)rv.i(t, 9), (I)-16 * (I)rv.i(t, 10), (I)-16 * (I)rv.i(t, 11), rv.i(t, 14), a, b);
         a = max(a, cx0); b = min(b, cx1);   // window of a deferred triangle's unit
         len = max(0, b - a + 1);
-        pos = ((uint32_t)t << 26) | ((uint32_t)(rc.y0 + dy) << 13) | (uint32_t)(rc.x0 + a);
+        pos = ((uint32_t)t << 26) | ((uint32_t)(rv.i(t, 13) + dy) << 13) | (uint32_t)(rv.i(t, 12) + a);
     }
     int inc = len;
 #pragma unroll
@@ -414,7 +474,7 @@ __device__ __forceinline__ void ehb_rows_group(const EhbRec* recs, int t, int dy
         const int oexc = __shfl_sync(0xffffffffu, exc, o);
         if (j < total) {
             const uint32_t q = opos + (uint32_t)(j - oexc);
-            ehb_shade_global(recs[q >> 26], (int)(q & 8191u), (int)((q >> 13) & 8191u), pool, xs, xo, ys, yo);
+            ehb_shade_global(rv, (int)(q >> 26), (int)(q & 8191u), (int)((q >> 13) & 8191u), pool, xs, xo, ys, yo);
         }
     }
 }
@@ -422,20 +482,30 @@ __device__ __forceinline__ void ehb_rows_group(const EhbRec* recs, int t, int dy
 __global__ void __launch_bounds__(EHB_RWARPS * 32) ehb_k_raster(const __grid_constant__ EhbRobot rb,
                                                                 const __grid_constant__ EhbParams p)
 {
-    __shared__ EhbRec s_rec[EHB_RWARPS][32];
+    __shared__ uint32_t s_rec[EHB_RWARPS][32 * 32];   // 32 records per warp, transposed
     __shared__ int s_off[EHB_RWARPS][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int item = blockIdx.y;
     const int g = (blockIdx.x * EHB_RWARPS + warp) * 32 + lane;
     const float xs = 2.f / (float)p.W, xo = 1.f / (float)p.W - 1.f;
     const float ys = 2.f / (float)p.H, yo = 1.f / (float)p.H - 1.f;
-    EhbRec* recs = s_rec[warp];
+    const EhbRecSoA recs{s_rec[warp]};
     int* off = s_off[warp];
     int rows = 0, wide = 0;
     if (g < p.Ftot) {
-        rows = ehb_make_record(rb, p, item, g, recs[lane], true);
+        EhbRec rc;
+        rows = ehb_make_record(rb, p, item, g, rc);
+        if (rows > 0 && p.touch) {   // tell k_tiles which (tile, link) windows this triangle reaches into
+            const uint32_t bit = 1u << ehb_find_link(rb.foff, rb.L, g);
+            const int txlo = max(0, (rc.x0 - p.hhi) >> 5), txhi = min(p.ntx - 1, (rc.x0 + rc.w - 1 + p.hlo) >> 5);
+            const int tylo = max(0, (rc.y0 - p.hhi) >> 5), tyhi = min(p.nty - 1, (rc.y0 + rc.h - 1 + p.hlo) >> 5);
+            for (int ty = tylo; ty <= tyhi; ty++)
+                for (int tx = txlo; tx <= txhi; tx++) {
+                    uint32_t* w = p.touch + (size_t)item * p.ntiles + ty * p.ntx + tx;
+                    if (!(__ldcg(w) & bit)) atomicOr(w, bit);   // mostly already set: a cached load instead of an atomic
+                }
+        }
         if (rows > 0) {
-            const EhbRec& rc = recs[lane];
             const int ext = max(max(abs(rc.ex[0]), abs(rc.ex[1])), max(max(abs(rc.ex[2]), abs(rc.ey[0])), max(abs(rc.ey[1]), abs(rc.ey[2]))));
             wide = ext >= 32768;   // 32-bit edge arithmetic is exact below 2^15 sub-pixel units per edge
             if (rc.w * rc.h > EHB_SMALL_AREA) {   // not small: park the record, cut the bbox into bounded units
@@ -453,6 +523,7 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32) ehb_k_raster(const __grid_con
                     for (int i = 0; i < nux * nuy && (int)(u0 + i) < p.unitCap; i++) p.units[u0 + i] = EhbUnit{0xFFFFFFFFu, 0, 0};
                 }
             }
+            if (rows > 0) ehb_rec_store_soa(s_rec[warp], lane, rc);
         }
     }
     int inc = rows;
@@ -478,8 +549,8 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32) ehb_k_raster(const __grid_con
             }
             t = lo; dy = r - off[t];
         }
-        if (anyWide) ehb_rows_group<long long, double>(recs, t, dy, lane, p.pool, xs, xo, ys, yo);
-        else ehb_rows_group<int, float>(recs, t, dy, lane, p.pool, xs, xo, ys, yo);
+        if (anyWide) ehb_rows_group<long long, double, EhbRecSoA>(recs, t, dy, lane, p.pool, xs, xo, ys, yo);
+        else ehb_rows_group<int, float, EhbRecSoA>(recs, t, dy, lane, p.pool, xs, xo, ys, yo);
     }
 }
 
@@ -501,8 +572,9 @@ __global__ void __launch_bounds__(256) ehb_k_raster_big(const __grid_constant__ 
         const int ext = max(max(abs(rc->ex[0]), abs(rc->ex[1])), max(max(abs(rc->ex[2]), abs(rc->ey[0])), max(abs(rc->ey[1]), abs(rc->ey[2]))));
         const int dy = un.dy0 + lane;
         const int t = dy < rc->h ? 0 : -1;
-        if (ext >= 32768) ehb_rows_group<long long, double>(rc, t, dy, lane, p.pool, xs, xo, ys, yo, un.dx0, un.dx0 + EHB_UNIT_W - 1);
-        else ehb_rows_group<int, float>(rc, t, dy, lane, p.pool, xs, xo, ys, yo, un.dx0, un.dx0 + EHB_UNIT_W - 1);
+        const EhbRecAoS rv{reinterpret_cast<const uint32_t*>(rc)};
+        if (ext >= 32768) ehb_rows_group<long long, double, EhbRecAoS>(rv, t, dy, lane, p.pool, xs, xo, ys, yo, un.dx0, un.dx0 + EHB_UNIT_W - 1);
+        else ehb_rows_group<int, float, EhbRecAoS>(rv, t, dy, lane, p.pool, xs, xo, ys, yo, un.dx0, un.dx0 + EHB_UNIT_W - 1);
     }
 }
 
@@ -555,7 +627,17 @@ struct __align__(16) EhbSmem {
     int rowCnt[EHB_RS + 1];
     int nP;
     int work;
+    // reference mask of the out region, fetched with cp.async at the start of the tile so that its HBM latency is
+    // hidden behind the antialias work: f32 words, or (u8 reference) 4 pixels per word
+    uint32_t refw[(EHB_T + 1) * (EHB_T + 4)];
 };
+
+__device__ __forceinline__ void ehb_cp_async4(void* smem_dst, const void* gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void ehb_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ unsigned long long ehb_bits(int lo, int hi)   // bits lo..hi (inclusive), empty if lo > hi
 {
@@ -565,6 +647,11 @@ __device__ __forceinline__ unsigned long long ehb_bits(int lo, int hi)   // bits
     return up & ~((1ull << lo) - 1ull);
 }
 
+#ifdef EHB_TIMING
+#define EHB_TICK(k) do { if (tid == 0) { const long long now_ = clock64(); atomicAdd(&p.ctr->dbg[k], (unsigned long long)(now_ - t_last)); t_last = now_; } } while (0)
+#else
+#define EHB_TICK(k) do { } while (0)
+#endif
 #ifndef EHB_TMIN_BLOCKS
 #define EHB_TMIN_BLOCKS 4
 #endif
@@ -584,16 +671,31 @@ __global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(con
     EhbPairEnt* spill = p.pairSpill + (size_t)blockIdx.x * p.spillCap;
     auto pair_at = [&](int i) -> EhbPairEnt& { return i < EHB_PAIRCAP ? sm.pairs[i] : spill[i - EHB_PAIRCAP]; };
 
-    for (int i = tid; i < 2 * EHB_NP; i += EHB_TTHREADS) (&sm.alpha[0][0])[i] = 0.f;   // kept all-zero between uses
+    // sm.alpha is never cleared: the gather only reads positions whose pair bit is set in THIS link's hx / vy masks,
+    // and every such position is written by the blend-weight step of this link
+    const bool haveRef = p.ref != nullptr || p.ref_u8 != nullptr;
+    // u8 reference rows can be fetched 4 pixels per cp.async when every row start is 4-byte aligned
+    const bool ref8vec = p.ref_u8 != nullptr && (p.W & 3) == 0 && (((uintptr_t)p.ref_u8) & 3) == 0;
+    const unsigned nHeavy = p.ctr->nTiles, nTiles = nHeavy + p.ctr->nLight;
+    const unsigned listEnd = (unsigned)(p.items * p.ntiles) - 1u;
+    unsigned nextWork = 0;
+    if (tid == 0) nextWork = atomicAdd(&p.ctr->workCursor, 1u);
 
+#ifdef EHB_TIMING
+    long long t_last = clock64();
+#endif
     for (;;) {
+        EHB_TICK(9);
+#ifdef EHB_TIMING
+        const long long t_tile0 = clock64();
+#endif
         if (tid == 0) {
-            const unsigned w = atomicAdd(&p.ctr->workCursor, 1u);
-            sm.work = w < p.ctr->nTiles ? (int)w : -1;
+            sm.work = nextWork < nTiles ? (int)nextWork : -1;
+            if (nextWork < nTiles) nextWork = atomicAdd(&p.ctr->workCursor, 1u);   // in flight while this tile is processed
         }
         __syncthreads();
         if (sm.work < 0) break;
-        const uint32_t wid = p.tileList[sm.work];
+        const uint32_t wid = p.tileList[(unsigned)sm.work < nHeavy ? (unsigned)sm.work : listEnd - ((unsigned)sm.work - nHeavy)];
         const int item = wid / p.ntiles, tile = wid - item * p.ntiles;
         const int tx = tile % p.ntx, ty = tile / p.ntx;
         const int x0 = tx * EHB_T, y0 = ty * EHB_T;
@@ -606,7 +708,7 @@ __global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(con
             EhbPlane pl;
             if (lane < p.L) {
                 pl = p.plane[(size_t)item * p.L + lane];
-                hit = pl.w > 0 && pl.x0 <= rx1 && pl.x0 + pl.w - 1 >= rx0 && pl.y0 <= ry1 && pl.y0 + pl.h - 1 >= ry0;
+                hit = pl.w > 0 && ((p.touch[wid] >> lane) & 1u);
             }
             const unsigned b = __ballot_sync(0xffffffffu, hit);
             if (hit) {
@@ -617,6 +719,23 @@ __global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(con
             if (lane == 0) { sm.nP = __popc(b); sm.segStart[0] = 0; }
         }
         for (int i = tid; i < p.L * 16; i += EHB_TTHREADS) sm.mvp[i] = __ldg(p.mvp + (size_t)item * p.L * 16 + i);
+        if (needAA && haveRef) {   // start fetching the reference mask of the out region
+            if (p.ref) {
+                for (int qy = warp; qy < ow; qy += EHB_TWARPS) {
+                    const int py = y0 + qy;
+                    if (py >= H) continue;
+                    const float* row = p.ref + ibase + (size_t)(H - 1 - py) * W + x0;
+                    if (x0 + lane < W) ehb_cp_async4(&sm.refw[qy * (EHB_T + 4) + lane], row + lane);
+                    if (oext && lane == 0 && x0 + EHB_T < W) ehb_cp_async4(&sm.refw[qy * (EHB_T + 4) + EHB_T], row + EHB_T);
+                }
+            } else if (ref8vec) {
+                for (int q = tid; q < ow * 16; q += EHB_TTHREADS) {
+                    const int qy = q >> 4, qw = q & 15;
+                    const int px = x0 + 4 * qw, py = y0 + qy;
+                    if (qw < 9 && px < W && py < H && (qw < 8 || oext)) ehb_cp_async4(&sm.refw[qy * (EHB_T + 4) + qw], p.ref_u8 + ibase + (size_t)(H - 1 - py) * W + px);
+                }
+            }
+        }
         if (needAA)
             for (int i = tid; i < EHB_NP; i += EHB_TTHREADS) sm.sum[i] = 0.f;
         if (p.mode == EHB_MODE_AA_BWD)   // g = dL/dmask comes from the caller
@@ -628,6 +747,10 @@ __global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(con
             }
         __syncthreads();
         const int nP = sm.nP;
+        EHB_TICK(0);
+#ifdef EHB_TIMING
+        if (tid == 0) { atomicAdd(&p.ctr->dbg[10], 1ull); atomicAdd(&p.ctr->dbg[11], (unsigned long long)nP); }
+#endif
 
         for (int k = 0; k < nP; k++) {
             const int l = sm.links[k];
@@ -649,9 +772,11 @@ __global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(con
                 if (!__syncthreads_or(any)) {   // the bbox touches the window but no sample does
                     if (tid == 0) sm.segStart[k + 1] = sm.segStart[k];
                     __syncthreads();
+                    EHB_TICK(1);
                     continue;
                 }
             }
+            EHB_TICK(1);
             // ================================ row bitmasks and silhouette pairs =================================
             for (int r = warp; r < EHB_RS; r += EHB_TWARPS) {
                 const unsigned b0 = __ballot_sync(0xffffffffu, sm.plane[r * EHB_RS + lane] != EHB_EMPTY);
@@ -660,47 +785,75 @@ __global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(con
             }
             if (tid == 0) sm.cov[EHB_RS] = 0ull;
             __syncthreads();
-            unsigned long long hxm = 0ull, vym = 0ull, ownm = 0ull;
-            if (tid < EHB_RS) {
-                const int r = tid, py = ry0 + r;
-                const unsigned long long cm = sm.cov[r], cu = sm.cov[r + 1];
+            const int seg0 = sm.segStart[k];
+            if (warp == 0) {
                 // columns whose pixel is inside the image, and for which the right neighbour is too
                 const unsigned long long inX = ehb_bits(-rx0, W - 1 - rx0), inX1 = ehb_bits(-rx0, W - 2 - rx0);
-                // pairs wanted: forward = those touching a pixel of the out region; otherwise only owned ones
-                unsigned long long wantH, wantV;
-                if (needAA) {
-                    wantH = (r >= hlo && r <= hlo + ow - 1) ? ehb_bits(hlo - 1, hlo + ow - 1) : 0ull;
-                    wantV = (r >= hlo - 1 && r <= hlo + ow - 1) ? ehb_bits(hlo, hlo + ow - 1) : 0ull;
-                } else {
-                    wantH = wantV = (r >= hlo && r <= hlo + EHB_T - 1) ? ehb_bits(hlo, hlo + EHB_T - 1) : 0ull;
+                unsigned long long hm[2], vm[2], om[2];
+                int cnt[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int r = lane + 32 * h;
+                    hm[h] = vm[h] = om[h] = 0ull;
+                    if (r < EHB_RS) {
+                        const int py = ry0 + r;
+                        const unsigned long long cm = sm.cov[r], cu = sm.cov[r + 1];
+                        // pairs wanted: forward = those touching a pixel of the out region; otherwise only owned ones
+                        unsigned long long wantH, wantV;
+                        if (needAA) {
+                            wantH = (r >= hlo && r <= hlo + ow - 1) ? ehb_bits(hlo - 1, hlo + ow - 1) : 0ull;
+                            wantV = (r >= hlo - 1 && r <= hlo + ow - 1) ? ehb_bits(hlo, hlo + ow - 1) : 0ull;
+                        } else {
+                            wantH = wantV = (r >= hlo && r <= hlo + EHB_T - 1) ? ehb_bits(hlo, hlo + EHB_T - 1) : 0ull;
+                        }
+                        const bool rowIn = py >= 0 && py < H;
+                        if (rowIn) hm[h] = (cm ^ (cm >> 1)) & inX1 & wantH & ehb_bits(0, EHB_RS - 2);
+                        if (rowIn && py < H - 1 && r < EHB_RS - 1) vm[h] = (cm ^ cu) & inX & wantV;
+                        om[h] = (r >= hlo && r <= hlo + EHB_T - 1) ? ehb_bits(hlo, hlo + EHB_T - 1) : 0ull;
+                        sm.hx[r] = hm[h]; sm.vy[r] = vm[h];
+                    }
+                    cnt[h] = __popcll(hm[h]) + __popcll(vm[h]);
                 }
-                const bool rowIn = py >= 0 && py < H;
-                if (rowIn) hxm = (cm ^ (cm >> 1)) & inX1 & wantH & ehb_bits(0, EHB_RS - 2);
-                if (rowIn && py < H - 1 && r < EHB_RS - 1) vym = (cm ^ cu) & inX & wantV;
-                ownm = (r >= hlo && r <= hlo + EHB_T - 1) ? ehb_bits(hlo, hlo + EHB_T - 1) : 0ull;
-                sm.hx[r] = hxm; sm.vy[r] = vym;
-                sm.rowCnt[r] = __popcll(hxm) + __popcll(vym);
-            }
-            __syncthreads();
-            const int seg0 = sm.segStart[k];
-            if (tid < EHB_RS) {
-                int o = seg0;
-                for (int r = 0; r < tid; r++) o += sm.rowCnt[r];
-                if (tid == EHB_RS - 1) sm.segStart[k + 1] = o + sm.rowCnt[tid];
-                const uint32_t rowBase = (uint32_t)tid * EHB_RS;
-                while (hxm) {
-                    const int b = __ffsll((long long)hxm) - 1;
-                    hxm &= hxm - 1;
-                    pair_at(o++).packed = (rowBase + b) | (((ownm >> b) & 1ull) ? (1u << 12) : 0u);
+                // exclusive prefix over the 35 rows: rows 0..31 by shuffle scan, rows 32..34 after them
+                int inc = cnt[0];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
                 }
-                while (vym) {
-                    const int b = __ffsll((long long)vym) - 1;
-                    vym &= vym - 1;
-                    pair_at(o++).packed = (rowBase + b) | (1u << 11) | (((ownm >> b) & 1ull) ? (1u << 12) : 0u);
+                const int tot0 = __shfl_sync(0xffffffffu, inc, 31);
+                int inc1 = cnt[1];
+#pragma unroll
+                for (int o = 1; o < 4; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, inc1, o);
+                    if (lane >= o) inc1 += v;
+                }
+                const int tot1 = __shfl_sync(0xffffffffu, inc1, 3);
+                if (lane == 0) sm.segStart[k + 1] = seg0 + tot0 + tot1;
+                int o0 = seg0 + inc - cnt[0], o1 = seg0 + tot0 + inc1 - cnt[1];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    int o = h ? o1 : o0;
+                    unsigned long long hxm = hm[h], vym = vm[h];
+                    const uint32_t rowBase = (uint32_t)(lane + 32 * h) * EHB_RS;
+                    while (hxm) {
+                        const int b = __ffsll((long long)hxm) - 1;
+                        hxm &= hxm - 1;
+                        pair_at(o++).packed = (rowBase + b) | (((om[h] >> b) & 1ull) ? (1u << 12) : 0u);
+                    }
+                    while (vym) {
+                        const int b = __ffsll((long long)vym) - 1;
+                        vym &= vym - 1;
+                        pair_at(o++).packed = (rowBase + b) | (1u << 11) | (((om[h] >> b) & 1ull) ? (1u << 12) : 0u);
+                    }
                 }
             }
             __syncthreads();
             const int seg1 = sm.segStart[k + 1];
+            EHB_TICK(2);
+#ifdef EHB_TIMING
+            if (tid == 0) atomicAdd(&p.ctr->dbg[12], (unsigned long long)(seg1 - seg0));
+#endif
             // ================================ blend weights, all lanes busy =====================================
             for (int j = seg0 + tid; j < seg1; j += EHB_TTHREADS) {
                 EhbPairEnt& pe = pair_at(j);
@@ -719,6 +872,7 @@ __global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(con
             }
             if (needAA) {
                 __syncthreads();
+                EHB_TICK(3);
                 // ============================ gather: sum += colour + pair contributions ========================
                 // pixel (qx, qy) of the out region; column 32 (the extra one) is handled by the last pass
                 for (int q = tid; q < ow * EHB_T + (oext ? ow : 0); q += EHB_TTHREADS) {
@@ -740,19 +894,15 @@ __global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(con
                     if (v1) { a = sm.alpha[1][idx - EHB_RS]; if (!(a > 0.f) && a != 0.f) o += a * (cf - (c ? 0.f : 1.f)); }
                     sm.sum[idx] = sm.sum[idx] + o;   // links are added in link order (rb_solver.py:68); absent links add 0
                 }
-                __syncthreads();
-                for (int j = seg0 + tid; j < seg1; j += EHB_TTHREADS) {   // undo the scatter: alpha planes back to zero
-                    const uint32_t pk = pair_at(j).packed;
-                    sm.alpha[(pk >> 11) & 1][pk & 2047] = 0.f;
-                }
             }
             __syncthreads();
+            EHB_TICK(4);
         }
 
         if (needAA) {
             // S = min(sum, 1); loss; g = dL/dsum kept in sm.sum for the backward
             double lacc = 0.0;
-            const bool haveRef = p.ref != nullptr || p.ref_u8 != nullptr;
+            if (haveRef) { ehb_cp_async_wait_all(); __syncthreads(); }
             for (int q = tid; q < ow * EHB_T + (oext ? ow : 0); q += EHB_TTHREADS) {
                 int qx, qy;
                 if (q < ow * EHB_T) { qy = q >> 5; qx = q & 31; } else { qy = q - ow * EHB_T; qx = EHB_T; }
@@ -765,7 +915,10 @@ __global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(con
                 const bool interior = qx < EHB_T && qy < EHB_T;
                 if (interior && p.masks) p.masks[o] = S;
                 if (haveRef) {
-                    const float rf = p.ref ? __ldg(p.ref + o) : (__ldg(p.ref_u8 + o) ? 1.f : 0.f);
+                    float rf;
+                    if (p.ref) rf = __uint_as_float(sm.refw[qy * (EHB_T + 4) + qx]);
+                    else if (ref8vec) rf = ((sm.refw[qy * (EHB_T + 4) + (qx >> 2)] >> (8 * (qx & 3))) & 255u) ? 1.f : 0.f;
+                    else rf = __ldg(p.ref_u8 + o) ? 1.f : 0.f;
                     const float diff = S - rf;
                     if (interior) lacc += (double)(diff * diff);
                     sm.sum[idx] = (!p.clamp || s <= 1.f) ? (2.f * diff) * p.invB : 0.f;
@@ -777,6 +930,7 @@ __global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(con
             }
             __syncthreads();
         }
+        EHB_TICK(5);
 
         // ======================================= backward: walk the pair list ===================================
         if (doBwd) {
@@ -833,5 +987,14 @@ __global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(con
             }
         }
         __syncthreads();
+        EHB_TICK(6);
+#ifdef EHB_TIMING
+        if (tid == 0) {
+            const unsigned long long dt = (unsigned long long)(clock64() - t_tile0);
+            atomicMax(&p.ctr->dbg[13], dt);
+            if (dt > 50000ull) atomicAdd(&p.ctr->dbg[14], 1ull);
+            if (dt > 100000ull) atomicAdd(&p.ctr->dbg[15], 1ull);
+        }
+#endif
     }
 }

@@ -63,6 +63,9 @@ EHB_API int ehb_ctx_destroy(ehb_ctx_t ctx);
 EHB_API int ehb_ctx_reserve(ehb_ctx_t ctx, int n_items, int n_links, int max_faces, int H, int W);
 /* Tie rule for a pixel centre lying exactly on a snapped edge: 0 (default) or 1 (mirror); see DESIGN.md. */
 EHB_API int ehb_ctx_set_fill_rule(ehb_ctx_t ctx, int rule);
+/* A call's items (views / renders) are split over n (1..4, default 2) independent pipelines that run concurrently on
+ * internal streams forked from, and joined back into, the caller's stream (CUDA-graph capturable). */
+EHB_API int ehb_ctx_set_pipelines(ehb_ctx_t ctx, int n);
 /* Doubles the depth-plane pool used for later launches (call after EHB_FLAG_POOL_OVERFLOW). */
 EHB_API int ehb_ctx_grow_scratch(ehb_ctx_t ctx);
 /* Per-kernel timing for benchmarks: while enabled every pass records CUDA events around its four kernels on the
@@ -70,6 +73,8 @@ EHB_API int ehb_ctx_grow_scratch(ehb_ctx_t ctx);
  * {bbox, plan, clear, raster (+ big), tiles} (ms5[5]) over the passes recorded since the last query, and their number. */
 EHB_API int ehb_ctx_profile(ehb_ctx_t ctx, int enable);
 EHB_API int ehb_ctx_kernel_times(ehb_ctx_t ctx, double* ms5, long long* n_passes);
+/* Developer aid: 16 raw 64-bit counters that builds with -DEHB_TIMING fill (cycles per phase of the tile kernel). */
+EHB_API int ehb_ctx_debug_counters(ehb_ctx_t ctx, unsigned long long* out16, int reset);
 /* Synchronises the device, returns and clears the sticky flags, reports triangles skipped for clipping. */
 EHB_API int ehb_ctx_status(ehb_ctx_t ctx, unsigned* flags, long long* n_need_clip);
 

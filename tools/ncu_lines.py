@@ -12,7 +12,7 @@ def main():
     skip = sys.argv[3] if len(sys.argv) > 3 else "0"
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name",
-                          "regex:" + kern, "--launch-skip", skip, "--launch-count", "1"], capture_output=True,
+                          ("regex:" + kern) if not kern.startswith("=") else kern[1:], "--launch-skip", skip, "--launch-count", "1"], capture_output=True,
                          text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     cur_file, lines, total, total_inst = None, [], 0, 0
