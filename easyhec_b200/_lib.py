@@ -68,6 +68,9 @@ _PROTOS = {
                                     C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
     "ehb_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
+    "ehb_solver_step_begin_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                           C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "ehb_solver_step_end": (C.c_int, [C.c_void_p, C.c_int]),
     "ehb_launch_count": (C.c_longlong, [C.c_void_p]),
 }
 
@@ -187,11 +190,11 @@ class Context:
         _check(lib().ehb_ctx_profile(self._h, int(bool(enable))))
 
     def kernel_times(self):
-        """-> ({bbox, plan, clear, raster, tiles: summed ms}, passes) since the last query; synchronises."""
+        """-> ({vertex, plan, clear, raster (+raster_big), tiles: summed ms}, passes) since the last query; synchronises."""
         ms = (C.c_double * 5)()
         n = C.c_longlong()
         _check(lib().ehb_ctx_kernel_times(self._h, ms, C.byref(n)))
-        return dict(zip(("bbox", "plan", "clear", "raster", "tiles"), list(ms))), n.value
+        return dict(zip(("vertex", "plan", "clear", "raster", "tiles"), list(ms))), n.value
 
     def debug_counters(self, reset=True):
         out = (C.c_ulonglong * 16)()
@@ -324,3 +327,16 @@ class Context:
         cap = 0 if hist is None else hist.shape[0]
         _check(lib().ehb_adam_step(self._h, _ptr(dof), _ptr(g7), _ptr(state), lr, betas[0], betas[1], eps, weight_decay,
                                    _ptr(hist), cap, _stream(self.device)))
+
+    def solver_step_begin_u8(self, slot, mesh_ids, mvp_host, ref_u8_host, H, W, loss_host, g_mvp_host):
+        """Asynchronous host-buffer step on slot 0/1 (own stream): returns at once; pair with solver_step_end(slot)."""
+        B, L = mvp_host.shape[0], mvp_host.shape[1]
+        ids = (C.c_int * L)(*mesh_ids)
+        for t in (mvp_host, ref_u8_host, loss_host, g_mvp_host):
+            if not t.is_pinned() or not t.is_contiguous():
+                raise EhbError("host buffers of an asynchronous step must be pinned and contiguous")
+        _check(lib().ehb_solver_step_begin_u8(self._h, slot, ids, L, B, _ptr(mvp_host), _ptr(ref_u8_host), H, W,
+                                              _ptr(loss_host), _ptr(g_mvp_host)))
+
+    def solver_step_end(self, slot):
+        _check(lib().ehb_solver_step_end(self._h, slot))

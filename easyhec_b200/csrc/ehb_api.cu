@@ -63,6 +63,8 @@ struct DevBuf {
 };
 
 constexpr int MAX_PIPES = 4;
+constexpr int N_SLOTS = 2;      // in-flight host-buffer steps (ehb_solver_step_begin_u8 / _end)
+constexpr int N_SCRATCH = MAX_PIPES + N_SLOTS;
 
 // Scratch of one pipeline.  A call's items are split over up to MAX_PIPES independent pipelines that run on internal
 // streams: every kernel of the pass is latency / tail bound, so the pipelines fill each other's idle SMs.
@@ -91,11 +93,17 @@ struct Ctx {
     int rule = 0;
     int nPipes = 2;
     std::vector<Mesh> meshes;
-    Scratch sc[MAX_PIPES];
+    Scratch sc[N_SCRATCH];            // [0, MAX_PIPES): pipelines of a device-pointer call; then one per host-step slot
     cudaStream_t pipeStream[MAX_PIPES] = {};
     cudaEvent_t evFork = nullptr, evJoin[MAX_PIPES] = {};
-    EhbCounters* ctr = nullptr;       // device array [MAX_PIPES]
-    EhbCounters* ctrHost = nullptr;   // pinned mirror [MAX_PIPES]
+    EhbCounters* ctr = nullptr;       // device array [N_SCRATCH]
+    EhbCounters* ctrHost = nullptr;   // pinned mirror [N_SCRATCH]
+    cudaStream_t slotStream[N_SLOTS] = {};
+    cudaEvent_t slotDone[N_SLOTS] = {};
+    DevBuf<float> slotMvp[N_SLOTS];
+    DevBuf<double> slotOut[N_SLOTS];
+    DevBuf<uint8_t> slotRef[N_SLOTS];
+    int slotB[N_SLOTS] = {}, slotL[N_SLOTS] = {};
     // staging for the host-buffer entry points
     DevBuf<float> mvpDev;
     DevBuf<double> outDev;            // loss[B] + gmvp[B*L*16]
@@ -389,9 +397,14 @@ int ehb_ctx_create(int device, ehb_ctx_t* out)
     Ctx* c = new Ctx();
     c->device = device;
     c->nSM = prop.multiProcessorCount;
-    CU(cudaMalloc((void**)&c->ctr, MAX_PIPES * sizeof(EhbCounters)));
-    CU(cudaMemset(c->ctr, 0, MAX_PIPES * sizeof(EhbCounters)));
-    CU(cudaMallocHost((void**)&c->ctrHost, MAX_PIPES * sizeof(EhbCounters)));
+    CU(cudaMalloc((void**)&c->ctr, N_SCRATCH * sizeof(EhbCounters)));
+    CU(cudaMemset(c->ctr, 0, N_SCRATCH * sizeof(EhbCounters)));
+    CU(cudaMallocHost((void**)&c->ctrHost, N_SCRATCH * sizeof(EhbCounters)));
+    for (int k = 0; k < N_SCRATCH; k++) c->sc[k].ctr = c->ctr + k;
+    for (int k = 0; k < N_SLOTS; k++) {
+        CU(cudaStreamCreateWithFlags(&c->slotStream[k], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->slotDone[k], cudaEventDisableTiming));
+    }
     CU(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
     for (int k = 0; k < MAX_PIPES; k++) {
         c->sc[k].ctr = c->ctr + k;
@@ -412,7 +425,9 @@ int ehb_ctx_destroy(ehb_ctx_t h)
     DeviceGuard guard(c->device);
     cudaDeviceSynchronize();
     for (auto& m : c->meshes) if (m.live) { cudaFree(m.verts); cudaFree(m.faces); cudaFree(m.opp); }
-    for (int k = 0; k < MAX_PIPES; k++) { c->sc[k].release(); cudaStreamDestroy(c->pipeStream[k]); cudaEventDestroy(c->evJoin[k]); }
+    for (int k = 0; k < MAX_PIPES; k++) { cudaStreamDestroy(c->pipeStream[k]); cudaEventDestroy(c->evJoin[k]); }
+    for (int k = 0; k < N_SCRATCH; k++) c->sc[k].release();
+    for (int k = 0; k < N_SLOTS; k++) { cudaStreamDestroy(c->slotStream[k]); cudaEventDestroy(c->slotDone[k]); c->slotMvp[k].release(); c->slotOut[k].release(); c->slotRef[k].release(); }
     cudaEventDestroy(c->evFork);
     c->mvpDev.release(); c->outDev.release(); c->refDev.release(); c->maskDev.release(); c->numDev.release();
     for (auto e : c->evPool) cudaEventDestroy(e);
@@ -499,11 +514,11 @@ int ehb_ctx_status(ehb_ctx_t h, unsigned* flags, long long* n_need_clip)
     if (!c) return fail(EHB_E_ARG, "null context");
     DeviceGuard guard(c->device);
     CU(cudaDeviceSynchronize());
-    EhbCounters hc[MAX_PIPES];
+    EhbCounters hc[N_SCRATCH];
     CU(cudaMemcpy(hc, c->ctr, sizeof hc, cudaMemcpyDeviceToHost));
     unsigned f = 0;
     long long nc = 0;
-    for (int k = 0; k < MAX_PIPES; k++) { f |= hc[k].flags; nc += (long long)hc[k].nNeedClip; hc[k].flags = 0; hc[k].nNeedClip = 0; }
+    for (int k = 0; k < N_SCRATCH; k++) { f |= hc[k].flags; nc += (long long)hc[k].nNeedClip; hc[k].flags = 0; hc[k].nNeedClip = 0; }
     if (flags) *flags = f;
     if (n_need_clip) *n_need_clip = nc;
     CU(cudaMemcpy(c->ctr, hc, sizeof hc, cudaMemcpyHostToDevice));
@@ -779,6 +794,47 @@ int ehb_adam_step(ehb_ctx_t h, float* dof_dev, const float* g7_dev, float* state
     ehb_k_adam<<<1, 32, 0, (cudaStream_t)stream>>>(dof_dev, g7_dev, state_dev, lr, beta1, beta2, eps, weight_decay, hist_dev, hist_cap);
     c->launches += 1;
     CU(cudaGetLastError());
+    return EHB_OK;
+}
+
+int ehb_solver_step_begin_u8(ehb_ctx_t h, int slot, const int* mesh_ids, int L, int B, const float* mvp_host,
+                             const uint8_t* ref_u8_host, int H, int W, double* loss_host, double* g_mvp_host)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || slot < 0 || slot >= N_SLOTS || !mvp_host || !ref_u8_host || !loss_host || !g_mvp_host) return fail(EHB_E_ARG, "bad step_begin arguments");
+    if (B < 1 || L < 1) return fail(EHB_E_ARG, "empty batch");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = c->slotStream[slot];
+    int r;
+    const size_t nm = (size_t)B * L * 16, no = (size_t)B + nm, npx = (size_t)B * H * W;
+    if ((r = c->slotMvp[slot].ensure(nm, false))) return r;
+    if ((r = c->slotOut[slot].ensure(no, false))) return r;
+    if ((r = c->slotRef[slot].ensure(npx, false))) return r;
+    CU(cudaMemcpyAsync(c->slotMvp[slot].p, mvp_host, nm * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->slotRef[slot].p, ref_u8_host, npx, cudaMemcpyHostToDevice, st));
+    Io io;
+    io.ref_u8 = c->slotRef[slot].p; io.loss = c->slotOut[slot].p; io.gmvp = c->slotOut[slot].p + B;
+    io.do_bwd = 1; io.clamp = 1; io.invB = 1.0f / (float)B;
+    r = run_pass(c, c->sc[MAX_PIPES + slot], mesh_ids, L, B, c->slotMvp[slot].p, H, W, EHB_MODE_FUSED, io, st);
+    if (r) return r;
+    CU(cudaMemcpyAsync(loss_host, c->slotOut[slot].p, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(g_mvp_host, c->slotOut[slot].p + B, nm * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->ctrHost + MAX_PIPES + slot, c->ctr + MAX_PIPES + slot, sizeof(EhbCounters), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(c->slotDone[slot], st));
+    return EHB_OK;
+}
+
+int ehb_solver_step_end(ehb_ctx_t h, int slot)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || slot < 0 || slot >= N_SLOTS) return fail(EHB_E_ARG, "bad slot");
+    DeviceGuard guard(c->device);
+    CU(cudaEventSynchronize(c->slotDone[slot]));
+    if (c->ctrHost[MAX_PIPES + slot].flags & EHB_FLAG_POOL_OVERFLOW) {
+        c->poolFactor *= 2.0;
+        CU(cudaMemsetAsync(&c->ctr[MAX_PIPES + slot].flags, 0, sizeof(unsigned), c->slotStream[slot]));
+        return fail(EHB_E_OVERFLOW, "depth-plane pool was too small for this step; it has been grown, submit the step again");
+    }
     return EHB_OK;
 }
 

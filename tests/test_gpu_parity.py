@@ -191,3 +191,36 @@ def test_subpixel_square_known_answers(gpu_ctx):
         gpu_ctx.release_mesh(mid)
         assert np.array_equal(got, want)
         assert want.sum() == size * size, (off, size, want.sum())
+
+
+def test_async_host_steps_match_device_path(gpu_ctx):
+    """Two-slot asynchronous host-buffer steps (H2D masks + mvp, fused pass, D2H loss + gradient) == device path."""
+    H, W, B = 120, 160, 4
+    sets = []
+    for seed in (1, 2, 3):
+        sc = make_scene(B, H, W, links="xarm7", seed=seed)
+        packed = oracle.pack_links(sc["meshes"])
+        from easyhec_b200.scenes import perturb_pose
+        ref = oracle.union_binary(packed, scene_mvps(sc, H, W), H, W).astype(np.uint8)
+        mvp = scene_mvps(sc, H, W, perturb_pose(sc["Tc_c2b"], np.random.RandomState(seed), 0.02, 2.0))
+        sets.append((sc, mvp, ref))
+    ids = [gpu_ctx.register_mesh(m.vertices, m.faces) for m in sets[0][0]["meshes"]]
+    L = len(ids)
+    outs = []
+    bufs = [(torch.empty((B,), dtype=torch.float64).pin_memory(), torch.empty((B, L, 4, 4), dtype=torch.float64).pin_memory())
+            for _ in range(2)]
+    pinned = [(torch.from_numpy(m).pin_memory(), torch.from_numpy(r).pin_memory()) for _, m, r in sets]
+    for k in range(3):
+        gpu_ctx.solver_step_begin_u8(k & 1, ids, pinned[k][0], pinned[k][1], H, W, *bufs[k & 1])
+        if k > 0:
+            gpu_ctx.solver_step_end((k - 1) & 1)
+            outs.append((bufs[(k - 1) & 1][0].clone(), bufs[(k - 1) & 1][1].clone()))
+    gpu_ctx.solver_step_end(0)
+    outs.append((bufs[0][0].clone(), bufs[0][1].clone()))
+    for k, (sc, mvp, ref) in enumerate(sets):
+        _, loss, g = gpu_ctx.render_views_fused(ids, to_dev(mvp), to_dev(ref), H, W, backward=True, want_masks=False)
+        assert np.allclose(outs[k][0].numpy(), loss.cpu().numpy(), rtol=1e-12)
+        assert rel_err(outs[k][1].numpy(), g.cpu().numpy()) < 1e-9
+    _status_ok(gpu_ctx)
+    for i in ids:
+        gpu_ctx.release_mesh(i)
