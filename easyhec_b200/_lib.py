@@ -190,11 +190,11 @@ class Context:
         _check(lib().ehb_ctx_profile(self._h, int(bool(enable))))
 
     def kernel_times(self):
-        """-> ({vertex, plan, clear, raster (+raster_big), tiles: summed ms}, passes) since the last query; synchronises."""
-        ms = (C.c_double * 5)()
+        """-> ({vertex, plan, raster (+raster_big, + empty-tile stream), tiles: summed ms}, passes); synchronises."""
+        ms = (C.c_double * 4)()
         n = C.c_longlong()
         _check(lib().ehb_ctx_kernel_times(self._h, ms, C.byref(n)))
-        return dict(zip(("vertex", "plan", "clear", "raster", "tiles"), list(ms))), n.value
+        return dict(zip(("vertex", "plan", "raster", "tiles"), list(ms))), n.value
 
     def debug_counters(self, reset=True):
         out = (C.c_ulonglong * 16)()

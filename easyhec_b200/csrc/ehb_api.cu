@@ -74,14 +74,14 @@ struct Scratch {
     DevBuf<int> bbraw;                // raw snapped bounding boxes, kept at the "empty" sentinel between passes
     DevBuf<EhbPlane> plane;
     DevBuf<unsigned long long> pool;  // depth planes of one pass, bump-allocated
-    DevBuf<uint32_t> tileList, touch;
+    DevBuf<uint32_t> tileList, emptyList, touch;
     DevBuf<EhbRec> bigRec;
     DevBuf<EhbUnit> units;
     DevBuf<EhbPairEnt> spill;         // per k_tiles CTA: overflow of the shared-memory silhouette-pair list
     EhbCounters* ctr = nullptr;
     void release()
     {
-        vclip.release(); vsnap.release(); bbraw.release(); plane.release(); pool.release(); tileList.release();
+        vclip.release(); vsnap.release(); bbraw.release(); plane.release(); pool.release(); tileList.release(); emptyList.release();
         touch.release(); bigRec.release(); units.release(); spill.release();
     }
 };
@@ -111,7 +111,7 @@ struct Ctx {
     DevBuf<unsigned long long> numDev;
     long long launches = 0;
     bool profiling = false;           // per-kernel CUDA events (ehb_ctx_profile): forces a single pipeline
-    std::vector<cudaEvent_t> evPool;  // 6 events per profiled pass
+    std::vector<cudaEvent_t> evPool;  // 5 events per profiled pass
     size_t evUsed = 0;
     double poolFactor = 2.0;          // plane pool = items * H * W * poolFactor entries (per-link mode); grown on overflow
 };
@@ -262,6 +262,7 @@ int ensure_scratch(Ctx* c, Scratch& sc, int items, int L, int Lp, int H, int W, 
     if ((r = sc.plane.ensure((size_t)items * Lp, capturing))) return r;
     if ((r = sc.tileList.ensure((size_t)items * ntiles, capturing))) return r;
     if ((r = sc.touch.ensure((size_t)items * ntiles, capturing))) return r;
+    if ((r = sc.emptyList.ensure((size_t)items * ntiles, capturing))) return r;
     if ((r = sc.bigRec.ensure((size_t)BIG_CAP, capturing))) return r;
     if ((r = sc.units.ensure((size_t)UNIT_CAP, capturing))) return r;
     const double f = Lp == 1 ? 1.0 : std::min(c->poolFactor, (double)Lp);
@@ -300,42 +301,41 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
     p.mvp = mvp_dev;
     p.vclip = sc.vclip.p; p.vsnap = sc.vsnap.p;
     p.bbraw = sc.bbraw.p; p.plane = sc.plane.p; p.pool = sc.pool.p; p.poolCap = sc.pool.n;
-    p.tileList = sc.tileList.p; p.touch = unionMode ? nullptr : sc.touch.p; p.bigRec = sc.bigRec.p; p.units = sc.units.p; p.bigCap = BIG_CAP; p.unitCap = UNIT_CAP; p.ctr = sc.ctr;
+    p.tileList = sc.tileList.p; p.emptyList = sc.emptyList.p; p.touch = unionMode ? nullptr : sc.touch.p; p.bigRec = sc.bigRec.p; p.units = sc.units.p; p.bigCap = BIG_CAP; p.unitCap = UNIT_CAP; p.ctr = sc.ctr;
     p.ref = io.ref; p.ref_u8 = io.ref_u8; p.masks = io.masks; p.loss = io.loss; p.gmvp = io.gmvp; p.gpos = io.gpos;
     p.dy = io.dy; p.out_u8 = io.out_u8;
     p.pairSpill = sc.spill.p; p.spillCap = SPILL_PER_LINK * L;
 
     cudaEvent_t* ev = nullptr;
     if (c->profiling && !capturing) {
-        if (c->evUsed + 6 > c->evPool.size()) {
+        if (c->evUsed + 5 > c->evPool.size()) {
             const size_t old = c->evPool.size();
-            c->evPool.resize(old + 6 * 256);
+            c->evPool.resize(old + 5 * 256);
             for (size_t i = old; i < c->evPool.size(); i++) CU(cudaEventCreate(&c->evPool[i]));
         }
         ev = &c->evPool[c->evUsed];
-        c->evUsed += 6;
+        c->evUsed += 5;
     }
     if (ev) cudaEventRecord(ev[0], st);
     ehb_k_vertex<<<dim3((unsigned)std::max(1, (p.Vtot + 255) / 256), (unsigned)items), 256, 0, st>>>(rb, p);
     if (ev) cudaEventRecord(ev[1], st);
-    const int planBlocks = (items * p.Lp + 255) / 256;
+    const int clearBlocks = c->nSM;
     const long long tileWarps = unionMode ? 0 : (long long)items * p.ntiles;
-    ehb_k_plan<<<(unsigned)(planBlocks + (tileWarps * 32 + 255) / 256), 256, 0, st>>>(p, planBlocks);
+    ehb_k_plan<<<(unsigned)(clearBlocks + (tileWarps * 32 + 255) / 256), 256, 0, st>>>(p, clearBlocks);
     if (ev) cudaEventRecord(ev[2], st);
-    ehb_k_clear<<<c->nSM * 4, 256, 0, st>>>(p);
-    if (ev) cudaEventRecord(ev[3], st);
-    ehb_k_raster<<<dim3((unsigned)std::max(1, (p.Ftot + EHB_RWARPS * 32 - 1) / (EHB_RWARPS * 32)), (unsigned)items),
-                   EHB_RWARPS * 32, 0, st>>>(rb, p);
+    const int chunks = std::max(1, (p.Ftot + EHB_RWARPS * 32 - 1) / (EHB_RWARPS * 32));
+    const int streamBlocks = (unionMode || mode == EHB_MODE_AA_BWD) ? 0 : c->nSM;
+    ehb_k_raster<<<(unsigned)(streamBlocks + chunks * items), EHB_RWARPS * 32, 0, st>>>(rb, p, streamBlocks, chunks);
     ehb_k_raster_big<<<c->nSM * 4, 256, 0, st>>>(p);
-    if (ev) cudaEventRecord(ev[4], st);
+    if (ev) cudaEventRecord(ev[3], st);
     if (unionMode) {
         const int nq = ((W + 3) / 4) * H;
         ehb_k_union_out<<<dim3((unsigned)std::min((nq + 255) / 256, 4 * c->nSM), (unsigned)items), 256, 0, st>>>(p);
     } else {
         ehb_k_tiles<<<c->nSM * c->occ, EHB_TTHREADS, tiles_smem(), st>>>(rb, p);
     }
-    if (ev) cudaEventRecord(ev[5], st);
-    c->launches += 6;
+    if (ev) cudaEventRecord(ev[4], st);
+    c->launches += 5;
     CU(cudaGetLastError());
     return EHB_OK;
 }
@@ -496,14 +496,14 @@ int ehb_ctx_kernel_times(ehb_ctx_t h, double* ms4, long long* n_passes)
     if (!c || !ms4 || !n_passes) return fail(EHB_E_ARG, "null pointer argument");
     DeviceGuard guard(c->device);
     CU(cudaDeviceSynchronize());
-    for (int k = 0; k < 5; k++) ms4[k] = 0.0;
-    for (size_t i = 0; i + 6 <= c->evUsed; i += 6)
-        for (int k = 0; k < 5; k++) {
+    for (int k = 0; k < 4; k++) ms4[k] = 0.0;
+    for (size_t i = 0; i + 5 <= c->evUsed; i += 5)
+        for (int k = 0; k < 4; k++) {
             float ms = 0.f;
             CU(cudaEventElapsedTime(&ms, c->evPool[i + k], c->evPool[i + k + 1]));
             ms4[k] += ms;
         }
-    *n_passes = (long long)(c->evUsed / 6);
+    *n_passes = (long long)(c->evUsed / 5);
     c->evUsed = 0;
     return EHB_OK;
 }

@@ -6,16 +6,17 @@
 // link's screen bounding box; for robot views all planes of a step are a few tens of MB and stay L2-resident.
 //   k_vertex : one thread per (item, vertex): transform and snap ONCE (a vertex is shared by ~6 triangles), keep the
 //              clip-space and snapped positions (a few MB, L2-resident), reduce the per-(item, link) bounding box
-//   k_plan   : (a) one thread per plane: pixel bbox, bump allocation of the plane in the plane pool;
-//              (b) one warp per 32x32 tile: tiles no link's bbox touches are finished right here as a float4 stream
-//                  (mask = 0, loss += ref^2) -- the HBM-bound part of the frame; the others go to the tile queue
-//   k_clear  : planes := EMPTY (only the allocated part of the pool)
+//              and -- in the last CTA to finish -- bump-allocate the planes in the plane pool
+//   k_plan   : (a) planes := EMPTY (only the allocated part of the pool);  (b) one warp per 32x32 tile: tiles that some
+//              link's bbox touches go to the tile queue (several links first), the others to the empty-tile list
 //   k_raster : NO binning, NO block barriers: each warp takes 32 triangles (one per lane): setup -> record in the
 //              warp's shared memory; the rows of the 32 clipped bboxes form one flat space; 32 rows at a time (one per
 //              lane) get their exactly covered span (float estimate + integer fix-up == testing every sample), and
 //              the warp then shades the covered samples of those rows cooperatively, 32 at a time: z/w from the
-//              unsnapped clip positions, atomicMin (RED.MIN.U64, served by L2) into the plane.  Triangles with very
-//              many rows are deferred to k_raster_big, where free warps pull 32-row slabs from a queue.
+//              unsnapped clip positions, atomicMin (RED.MIN.U64, served by L2) into the plane.  Triangles that are not
+//              small are deferred: record parked in global memory, bbox cut into 64x32 units for k_raster_big.
+//              Spare CTAs of the same launch stream the empty tiles (mask = 0, loss += ref^2, float4): the HBM-bound
+//              part of the frame overlaps the latency-bound part instead of preceding it.
 //   k_tiles  : persistent CTAs over the non-empty tiles: per link whose bbox touches the tile: load the 35x35 window
 //              of its plane, 35 row bitmasks -> silhouette pairs by XOR -> blend weights with all lanes busy -> pair
 //              list (triangle, edge, alpha) -> gather into the per-view sum in the reference's order; then
@@ -52,6 +53,8 @@ struct EhbCounters {
     unsigned int nTiles;     // tiles touched by >= 2 link bboxes: listed from the front of tileList (served first) ...
     unsigned int nLight;     // ... the others from the back
     unsigned int workCursor;
+    unsigned int nEmpty;     // tiles no link touches: streamed (mask = 0, loss += ref^2) by spare CTAs of the raster launch
+    unsigned int vertexDone; // CTAs of k_vertex that have finished: the last one allocates the planes
     unsigned int nBigRec;    // deferred (not small) triangles: records parked in global memory ...
     unsigned int nUnits;     // ... and cut into bounded units that k_raster_big spreads over the whole chip
     unsigned int flags;      // 1: plane pool too small (results invalid, grow and rerun), 2: triangles need clipping
@@ -73,6 +76,7 @@ struct EhbParams {
     unsigned long long* pool;
     unsigned long long poolCap;
     uint32_t* tileList;      // [items * ntiles]
+    uint32_t* emptyList;     // [items * ntiles]
     uint32_t* touch;         // [items * ntiles]  bit l: a triangle of link l reaches into this tile's window
     struct EhbRec* bigRec;   // [bigCap]
     EhbUnit* units;          // [unitCap]
@@ -142,9 +146,9 @@ __global__ void __launch_bounds__(256) ehb_k_vertex(const __grid_constant__ EhbR
     const int lane = threadIdx.x & 31;
     if (blockIdx.x == 0) {
         if (item == 0 && threadIdx.x == 0) {
-            p.ctr->planeCursor = 0ull;
             p.ctr->nTiles = 0u;
             p.ctr->nLight = 0u;
+            p.ctr->nEmpty = 0u;
             p.ctr->workCursor = 0u;
             p.ctr->nBigRec = 0u;
             p.ctr->nUnits = 0u;
@@ -178,6 +182,30 @@ __global__ void __launch_bounds__(256) ehb_k_vertex(const __grid_constant__ EhbR
     if (l >= 0 && lane == __ffs(grp) - 1) {
         int* raw = p.bbraw + ((size_t)item * p.Lp + l) * 4;
         atomicMin(raw + 0, mnx); atomicMin(raw + 1, mny); atomicMax(raw + 2, mxx); atomicMax(raw + 3, mxy);
+    }
+    // the last CTA to finish sees every bounding box: it bump-allocates the planes of this pass
+    __shared__ unsigned s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&p.ctr->vertexDone, 1u) == gridDim.x * gridDim.y - 1u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) { p.ctr->vertexDone = 0u; p.ctr->planeCursor = 0ull; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.items * p.Lp; i += blockDim.x) {
+        EhbPlane pl;
+        pl.x0 = pl.y0 = pl.w = pl.h = 0; pl.off = 0; pl.pad = 0;
+        int x0, y0, x1, y1;
+        int raw[4];
+        for (int k = 0; k < 4; k++) raw[k] = __ldcg(p.bbraw + (size_t)i * 4 + k);
+        if (ehb_raw_to_pixels(raw, p.H, p.W, x0, y0, x1, y1)) {
+            const unsigned long long area = (unsigned long long)(x1 - x0 + 1) * (unsigned long long)(y1 - y0 + 1);
+            const unsigned long long off = atomicAdd(&p.ctr->planeCursor, area);
+            if (off + area <= p.poolCap) { pl.x0 = x0; pl.y0 = y0; pl.w = x1 - x0 + 1; pl.h = y1 - y0 + 1; pl.off = (long long)off; }
+            else atomicOr(&p.ctr->flags, 1u);
+        }
+        p.plane[i] = pl;
     }
 }
 
@@ -227,65 +255,45 @@ __device__ __forceinline__ void ehb_stream_empty_tile(const EhbParams& p, int it
     }
 }
 
-__global__ void __launch_bounds__(256) ehb_k_plan(const __grid_constant__ EhbParams p, int planBlocks)
+__global__ void __launch_bounds__(256) ehb_k_plan(const __grid_constant__ EhbParams p, int clearBlocks)
 {
-    if ((int)blockIdx.x < planBlocks) {   // (a) plane allocation
-        const int i = blockIdx.x * blockDim.x + threadIdx.x;
-        if (i >= p.items * p.Lp) return;
-        EhbPlane pl;
-        pl.x0 = pl.y0 = pl.w = pl.h = 0; pl.off = 0; pl.pad = 0;
-        int x0, y0, x1, y1;
-        if (ehb_raw_to_pixels(p.bbraw + (size_t)i * 4, p.H, p.W, x0, y0, x1, y1)) {
-            const unsigned long long area = (unsigned long long)(x1 - x0 + 1) * (unsigned long long)(y1 - y0 + 1);
-            const unsigned long long off = atomicAdd(&p.ctr->planeCursor, area);
-            if (off + area <= p.poolCap) { pl.x0 = x0; pl.y0 = y0; pl.w = x1 - x0 + 1; pl.h = y1 - y0 + 1; pl.off = (long long)off; }
-            else atomicOr(&p.ctr->flags, 1u);
-        }
-        p.plane[i] = pl;
+    if ((int)blockIdx.x < clearBlocks) {
+        // (a) planes := EMPTY (only the allocated part of the pool); touch bits := 0; raw bounding boxes := "none"
+        const unsigned long long total = min(p.ctr->planeCursor, p.poolCap);
+        const unsigned long long n2 = total >> 1;
+        ulonglong2* p2 = reinterpret_cast<ulonglong2*>(p.pool);
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2;
+             i += (unsigned long long)clearBlocks * blockDim.x)
+            p2[i] = make_ulonglong2(EHB_EMPTY, EHB_EMPTY);
+        if ((total & 1ull) && blockIdx.x == 0 && threadIdx.x == 0) p.pool[total - 1] = EHB_EMPTY;
+        if (p.touch)
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.items * p.ntiles; i += clearBlocks * blockDim.x) p.touch[i] = 0u;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.items * p.Lp * 4; i += clearBlocks * blockDim.x)
+            p.bbraw[i] = (i & 2) ? EHB_RAW_MAX : EHB_RAW_MIN;
         return;
     }
     // (b) tile classification: one warp per tile
-    const int wid = (((int)blockIdx.x - planBlocks) * blockDim.x + threadIdx.x) >> 5;
+    const int wid = (((int)blockIdx.x - clearBlocks) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wid >= p.items * p.ntiles) return;
     const int item = wid / p.ntiles, tile = wid - item * p.ntiles;
     const int tx = tile % p.ntx, ty = tile / p.ntx;
     bool hit = false;
     if (lane < p.Lp) {
-        int x0, y0, x1, y1;
-        if (ehb_raw_to_pixels(p.bbraw + ((size_t)item * p.Lp + lane) * 4, p.H, p.W, x0, y0, x1, y1)) {
-            const int rx0 = tx * EHB_T - p.hlo, ry0 = ty * EHB_T - p.hlo;
-            const int rx1 = tx * EHB_T + EHB_T - 1 + p.hhi, ry1 = ty * EHB_T + EHB_T - 1 + p.hhi;
-            hit = x0 <= rx1 && x1 >= rx0 && y0 <= ry1 && y1 >= ry0;
-        }
+        const EhbPlane pl = p.plane[(size_t)item * p.Lp + lane];
+        const int rx0 = tx * EHB_T - p.hlo, ry0 = ty * EHB_T - p.hlo;
+        const int rx1 = tx * EHB_T + EHB_T - 1 + p.hhi, ry1 = ty * EHB_T + EHB_T - 1 + p.hhi;
+        hit = pl.w > 0 && pl.x0 <= rx1 && pl.x0 + pl.w - 1 >= rx0 && pl.y0 <= ry1 && pl.y0 + pl.h - 1 >= ry0;
     }
     const unsigned hits = __ballot_sync(0xffffffffu, hit);
+    if (lane != 0) return;
     if (hits) {
         // tiles with several links take several times longer in k_tiles: queue them first (front), the rest from the back
-        if (lane == 0) {
-            if (__popc(hits) >= 2) p.tileList[atomicAdd(&p.ctr->nTiles, 1u)] = (uint32_t)wid;
-            else p.tileList[(unsigned)(p.items * p.ntiles) - 1u - atomicAdd(&p.ctr->nLight, 1u)] = (uint32_t)wid;
-        }
-    } else if (p.mode != EHB_MODE_UNION && p.mode != EHB_MODE_AA_BWD) {
-        ehb_stream_empty_tile(p, item, tx, ty, lane);
+        if (__popc(hits) >= 2) p.tileList[atomicAdd(&p.ctr->nTiles, 1u)] = (uint32_t)wid;
+        else p.tileList[(unsigned)(p.items * p.ntiles) - 1u - atomicAdd(&p.ctr->nLight, 1u)] = (uint32_t)wid;
+    } else if (p.mode != EHB_MODE_AA_BWD) {
+        p.emptyList[atomicAdd(&p.ctr->nEmpty, 1u)] = (uint32_t)wid;
     }
-}
-
-// ------------------------------------------------------------------------------------------------ k_clear
-__global__ void __launch_bounds__(256) ehb_k_clear(const __grid_constant__ EhbParams p)
-{
-    const unsigned long long total = min(p.ctr->planeCursor, p.poolCap);
-    const unsigned long long n2 = total >> 1;
-    ulonglong2* p2 = reinterpret_cast<ulonglong2*>(p.pool);
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2;
-         i += (unsigned long long)gridDim.x * blockDim.x)
-        p2[i] = make_ulonglong2(EHB_EMPTY, EHB_EMPTY);
-    if ((total & 1ull) && blockIdx.x == 0 && threadIdx.x == 0) p.pool[total - 1] = EHB_EMPTY;
-    if (p.touch)
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.items * p.ntiles; i += gridDim.x * blockDim.x) p.touch[i] = 0u;
-    // the raw bounding boxes have been consumed by k_plan: reset them for the next pass
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.items * p.Lp * 4; i += gridDim.x * blockDim.x)
-        p.bbraw[i] = (i & 2) ? EHB_RAW_MAX : EHB_RAW_MIN;
 }
 
 // ------------------------------------------------------------------------------------------------ k_raster
@@ -480,13 +488,26 @@ __device__ __forceinline__ void ehb_rows_group(const RV rv, int t, int dy, int l
 }
 
 __global__ void __launch_bounds__(EHB_RWARPS * 32) ehb_k_raster(const __grid_constant__ EhbRobot rb,
-                                                                const __grid_constant__ EhbParams p)
+                                                                const __grid_constant__ EhbParams p, int streamBlocks,
+                                                                int chunks)
 {
     __shared__ uint32_t s_rec[EHB_RWARPS][32 * 32];   // 32 records per warp, transposed
     __shared__ int s_off[EHB_RWARPS][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int item = blockIdx.y;
-    const int g = (blockIdx.x * EHB_RWARPS + warp) * 32 + lane;
+    if ((int)blockIdx.x < streamBlocks) {
+        // spare CTAs of this launch finish the tiles no link touches (mask = 0, loss += ref^2): pure HBM streaming that
+        // overlaps the latency-bound rasterization instead of sitting in front of it
+        const int n = (int)p.ctr->nEmpty;
+        for (int i = blockIdx.x * EHB_RWARPS + warp; i < n; i += streamBlocks * EHB_RWARPS) {
+            const int wid = (int)p.emptyList[i];
+            const int item = wid / p.ntiles, tile = wid - item * p.ntiles;
+            ehb_stream_empty_tile(p, item, tile % p.ntx, tile / p.ntx, lane);
+        }
+        return;
+    }
+    const int rb_ = (int)blockIdx.x - streamBlocks;
+    const int item = rb_ / chunks;
+    const int g = ((rb_ - item * chunks) * EHB_RWARPS + warp) * 32 + lane;
     const float xs = 2.f / (float)p.W, xo = 1.f / (float)p.W - 1.f;
     const float ys = 2.f / (float)p.H, yo = 1.f / (float)p.H - 1.f;
     const EhbRecSoA recs{s_rec[warp]};

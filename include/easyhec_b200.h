@@ -69,10 +69,11 @@ EHB_API int ehb_ctx_set_pipelines(ehb_ctx_t ctx, int n);
 /* Doubles the depth-plane pool used for later launches (call after EHB_FLAG_POOL_OVERFLOW). */
 EHB_API int ehb_ctx_grow_scratch(ehb_ctx_t ctx);
 /* Per-kernel timing for benchmarks: while enabled every pass records CUDA events around its four kernels on the
- * caller's stream.  ehb_ctx_kernel_times synchronises, returns the summed milliseconds of the five stages
- * {bbox, plan, clear, raster (+ big), tiles} (ms5[5]) over the passes recorded since the last query, and their number. */
+ * caller's stream (and runs it as a single pipeline).  ehb_ctx_kernel_times synchronises, returns the summed
+ * milliseconds of the four stages {vertex, plan, raster (+ raster_big), tiles} (ms4[4]) over the passes recorded since
+ * the last query, and their number. */
 EHB_API int ehb_ctx_profile(ehb_ctx_t ctx, int enable);
-EHB_API int ehb_ctx_kernel_times(ehb_ctx_t ctx, double* ms5, long long* n_passes);
+EHB_API int ehb_ctx_kernel_times(ehb_ctx_t ctx, double* ms4, long long* n_passes);
 /* Developer aid: 16 raw 64-bit counters that builds with -DEHB_TIMING fill (cycles per phase of the tile kernel). */
 EHB_API int ehb_ctx_debug_counters(ehb_ctx_t ctx, unsigned long long* out16, int reset);
 /* Synchronises the device, returns and clears the sticky flags, reports triangles skipped for clipping. */
