@@ -228,6 +228,25 @@ struct Io {
     int do_bwd = 0, clamp = 0; float invB = 1.f;
 };
 
+// Launch helper: kernels after the first of a pass are chained with programmatic dependent launch when EHB_PDL is on.
+template <typename... KArgs, typename... Args>
+cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool chained, Args... args)
+{
+#ifdef EHB_PDL
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = chained ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+#else
+    (void)chained;
+    kernel<<<grid, block, smem, st>>>(KArgs(args)...);
+    return cudaGetLastError();
+#endif
+}
+
 int build_robot(Ctx* c, const int* mesh_ids, int L, EhbRobot& rb)
 {
     if (L < 1 || L > EHB_MAX_LINKS) return fail(EHB_E_ARG, "number of links %d outside [1, %d]", L, EHB_MAX_LINKS);
@@ -317,22 +336,22 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
         c->evUsed += 5;
     }
     if (ev) cudaEventRecord(ev[0], st);
-    ehb_k_vertex<<<dim3((unsigned)std::max(1, (p.Vtot + 255) / 256), (unsigned)items), 256, 0, st>>>(rb, p);
+    CU(launch(ehb_k_vertex, dim3((unsigned)std::max(1, (p.Vtot + 255) / 256), (unsigned)items), dim3(256), 0, st, false, rb, p));
     if (ev) cudaEventRecord(ev[1], st);
     const int clearBlocks = c->nSM;
     const long long tileWarps = unionMode ? 0 : (long long)items * p.ntiles;
-    ehb_k_plan<<<(unsigned)(clearBlocks + (tileWarps * 32 + 255) / 256), 256, 0, st>>>(p, clearBlocks);
+    CU(launch(ehb_k_plan, dim3((unsigned)(clearBlocks + (tileWarps * 32 + 255) / 256)), dim3(256), 0, st, true, p, clearBlocks));
     if (ev) cudaEventRecord(ev[2], st);
     const int chunks = std::max(1, (p.Ftot + EHB_RWARPS * 32 - 1) / (EHB_RWARPS * 32));
     const int streamBlocks = (unionMode || mode == EHB_MODE_AA_BWD) ? 0 : c->nSM;
-    ehb_k_raster<<<(unsigned)(streamBlocks + chunks * items), EHB_RWARPS * 32, 0, st>>>(rb, p, streamBlocks, chunks);
-    ehb_k_raster_big<<<c->nSM * 4, 256, 0, st>>>(p);
+    CU(launch(ehb_k_raster, dim3((unsigned)(streamBlocks + chunks * items)), dim3(EHB_RWARPS * 32), 0, st, true, rb, p, streamBlocks, chunks));
+    CU(launch(ehb_k_raster_big, dim3(c->nSM * 4), dim3(256), 0, st, true, p));
     if (ev) cudaEventRecord(ev[3], st);
     if (unionMode) {
         const int nq = ((W + 3) / 4) * H;
-        ehb_k_union_out<<<dim3((unsigned)std::min((nq + 255) / 256, 4 * c->nSM), (unsigned)items), 256, 0, st>>>(p);
+        CU(launch(ehb_k_union_out, dim3((unsigned)std::min((nq + 255) / 256, 4 * c->nSM), (unsigned)items), dim3(256), 0, st, true, p));
     } else {
-        ehb_k_tiles<<<c->nSM * c->occ, EHB_TTHREADS, tiles_smem(), st>>>(rb, p);
+        CU(launch(ehb_k_tiles, dim3(c->nSM * c->occ), dim3(EHB_TTHREADS), tiles_smem(), st, true, rb, p));
     }
     if (ev) cudaEventRecord(ev[4], st);
     c->launches += 5;

@@ -102,6 +102,17 @@ struct EhbParams {
 #define EHB_UNIT_W 64
 #define EHB_UNIT_H 32
 
+// Programmatic dependent launch (sm_90+): the kernels of a pass are chained with the programmatic-stream-serialization
+// launch attribute.  Each kernel first lets its successor be scheduled (its CTAs take free SM slots during this kernel's
+// tail and run their prologue), then waits until its predecessor has completed and flushed.
+__device__ __forceinline__ void ehb_pdl_enter()
+{
+#ifdef EHB_PDL
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
 __device__ __forceinline__ int ehb_find_link(const int* off, int L, int g)
 {
     int l = 0;
@@ -141,6 +152,7 @@ __device__ __forceinline__ bool ehb_raw_to_pixels(const int* raw, int H, int W, 
 __global__ void __launch_bounds__(256) ehb_k_vertex(const __grid_constant__ EhbRobot rb,
                                                   const __grid_constant__ EhbParams p)
 {
+    ehb_pdl_enter();
     const int item = blockIdx.y;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -257,6 +269,7 @@ __device__ __forceinline__ void ehb_stream_empty_tile(const EhbParams& p, int it
 
 __global__ void __launch_bounds__(256) ehb_k_plan(const __grid_constant__ EhbParams p, int clearBlocks)
 {
+    ehb_pdl_enter();
     if ((int)blockIdx.x < clearBlocks) {
         // (a) planes := EMPTY (only the allocated part of the pool); touch bits := 0; raw bounding boxes := "none"
         const unsigned long long total = min(p.ctr->planeCursor, p.poolCap);
@@ -491,6 +504,7 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32) ehb_k_raster(const __grid_con
                                                                 const __grid_constant__ EhbParams p, int streamBlocks,
                                                                 int chunks)
 {
+    ehb_pdl_enter();
     __shared__ uint32_t s_rec[EHB_RWARPS][32 * 32];   // 32 records per warp, transposed
     __shared__ int s_off[EHB_RWARPS][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -578,6 +592,7 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32) ehb_k_raster(const __grid_con
 // Deferred triangles: warps stride over the unit list; one unit = a 64 x 32 pixel window of one triangle's bbox.
 __global__ void __launch_bounds__(256) ehb_k_raster_big(const __grid_constant__ EhbParams p)
 {
+    ehb_pdl_enter();
     __shared__ EhbRec s_rec[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = min((int)p.ctr->nUnits, p.unitCap);
@@ -602,6 +617,7 @@ __global__ void __launch_bounds__(256) ehb_k_raster_big(const __grid_constant__ 
 // UNION (packed robot, no antialiasing): mask = (z/w of the nearest triangle > 0), straight from the item's plane.
 __global__ void __launch_bounds__(256) ehb_k_union_out(const __grid_constant__ EhbParams p)
 {
+    ehb_pdl_enter();
     const int item = blockIdx.y;
     const EhbPlane pl = p.plane[item];
     const int H = p.H, W = p.W;
@@ -679,6 +695,7 @@ __device__ __forceinline__ unsigned long long ehb_bits(int lo, int hi)   // bits
 __global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(const __grid_constant__ EhbRobot rb,
                                                                              const __grid_constant__ EhbParams p)
 {
+    ehb_pdl_enter();
     extern __shared__ __align__(16) unsigned char ehb_smem_raw[];
     EhbSmem& sm = *reinterpret_cast<EhbSmem*>(ehb_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
