@@ -276,7 +276,7 @@ def run_b200(args):
                 ctx.solver_step_end((k - 1) & 1)
         ctx.solver_step_end((n - 1) & 1)
 
-    e2e_run(4)
+    e2e_run(16)
     e2e_steps = min(args.steps, 1000)
     barrier()
     t0 = time.perf_counter()

@@ -35,6 +35,7 @@ _PROTOS = {
     "ehb_ctx_destroy": (C.c_int, [C.c_void_p]),
     "ehb_ctx_reserve": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ehb_ctx_set_fill_rule": (C.c_int, [C.c_void_p, C.c_int]),
+    "ehb_ctx_set_pool_budget": (C.c_int, [C.c_void_p, C.c_double]),
     "ehb_ctx_set_pipelines": (C.c_int, [C.c_void_p, C.c_int]),
     "ehb_ctx_grow_scratch": (C.c_int, [C.c_void_p]),
     "ehb_ctx_profile": (C.c_int, [C.c_void_p, C.c_int]),
@@ -173,6 +174,9 @@ class Context:
 
     def set_fill_rule(self, rule: int):
         _check(lib().ehb_ctx_set_fill_rule(self._h, rule))
+
+    def set_pool_budget(self, nbytes: float):
+        _check(lib().ehb_ctx_set_pool_budget(self._h, float(nbytes)))
 
     def set_pipelines(self, n: int):
         _check(lib().ehb_ctx_set_pipelines(self._h, int(n)))

@@ -62,6 +62,7 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+constexpr double POOL_BUDGET = 8e9;  // bytes of plane pool per pipeline reserved without asking
 constexpr int MAX_PIPES = 4;
 constexpr int N_SLOTS = 2;      // in-flight host-buffer steps (ehb_solver_step_begin_u8 / _end)
 constexpr int N_SCRATCH = MAX_PIPES + N_SLOTS;
@@ -113,7 +114,8 @@ struct Ctx {
     bool profiling = false;           // per-kernel CUDA events (ehb_ctx_profile): forces a single pipeline
     std::vector<cudaEvent_t> evPool;  // 5 events per profiled pass
     size_t evUsed = 0;
-    double poolFactor = 2.0;          // plane pool = items * H * W * poolFactor entries (per-link mode); grown on overflow
+    double poolFactor = 2.0;          // beyond the budget: plane pool = items * H * W * poolFactor entries, grown on overflow
+    double poolBudget = POOL_BUDGET;
 };
 
 struct DeviceGuard {
@@ -284,7 +286,11 @@ int ensure_scratch(Ctx* c, Scratch& sc, int items, int L, int Lp, int H, int W, 
     if ((r = sc.emptyList.ensure((size_t)items * ntiles, capturing))) return r;
     if ((r = sc.bigRec.ensure((size_t)BIG_CAP, capturing))) return r;
     if ((r = sc.units.ensure((size_t)UNIT_CAP, capturing))) return r;
-    const double f = Lp == 1 ? 1.0 : std::min(c->poolFactor, (double)Lp);
+    // Plane pool: the worst case (every link's bbox is the whole screen) is items * Lp * H * W entries.  That is what is
+    // reserved while it stays under POOL_BUDGET (180 GB of HBM: 10 views x 7 links x 1280x720 is 0.5 GB) -- then the
+    // pool can never overflow; beyond it the pool holds poolFactor screens per item and grows on the overflow flag.
+    const double worst = (double)items * Lp * H * W;
+    const double f = worst * 8.0 <= c->poolBudget ? (double)Lp : std::min(std::max(c->poolFactor, c->poolBudget / (8.0 * items * H * W)), (double)Lp);
     if ((r = sc.pool.ensure((size_t)((double)items * H * W * f) + 1024, capturing))) return r;
     return EHB_OK;
 }
@@ -541,6 +547,15 @@ int ehb_ctx_status(ehb_ctx_t h, unsigned* flags, long long* n_need_clip)
     if (flags) *flags = f;
     if (n_need_clip) *n_need_clip = nc;
     CU(cudaMemcpy(c->ctr, hc, sizeof hc, cudaMemcpyHostToDevice));
+    return EHB_OK;
+}
+
+int ehb_ctx_set_pool_budget(ehb_ctx_t h, double bytes)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || !(bytes >= 0)) return fail(EHB_E_ARG, "bad context or budget");
+    c->poolBudget = bytes;
+    c->poolFactor = bytes == 0.0 ? 1.0 / 16.0 : 2.0;   // budget 0: start from the minimum so that growth is exercised
     return EHB_OK;
 }
 

@@ -66,6 +66,10 @@ EHB_API int ehb_ctx_set_fill_rule(ehb_ctx_t ctx, int rule);
 /* A call's items (views / renders) are split over n (1..4, default 2) independent pipelines that run concurrently on
  * internal streams forked from, and joined back into, the caller's stream (CUDA-graph capturable). */
 EHB_API int ehb_ctx_set_pipelines(ehb_ctx_t ctx, int n);
+/* Bytes of depth-plane pool a pipeline may reserve up front (default 8e9).  While the worst case of a call
+ * (items x links x H x W x 8 B) fits, the pool cannot overflow; beyond it the pool starts at 2 screens per item and
+ * EHB_FLAG_POOL_OVERFLOW asks for ehb_ctx_grow_scratch + a rerun. */
+EHB_API int ehb_ctx_set_pool_budget(ehb_ctx_t ctx, double bytes);
 /* Doubles the depth-plane pool used for later launches (call after EHB_FLAG_POOL_OVERFLOW). */
 EHB_API int ehb_ctx_grow_scratch(ehb_ctx_t ctx);
 /* Per-kernel timing for benchmarks: while enabled every pass records CUDA events around its four kernels on the
