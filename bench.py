@@ -192,12 +192,30 @@ def run_b200(args):
     loss = torch.empty((B,), dtype=torch.float64, device=dev)
     gmvp = torch.empty((B, L, 4, 4), dtype=torch.float64, device=dev)
     g7 = torch.zeros(7, dtype=torch.float32, device=dev)
+    collective = "none"
+    if world > 1:
+        collective = "nccl all-reduce 7xf32 per step"
+        if args.collective == "peer":
+            try:   # one-shot all-reduce through NVLink peer mailboxes (ehb_allreduce7); NCCL stays the fallback
+                ctx.comm_connect()
+                collective = "NVLink peer-mailbox all-reduce 7xf32 per step (ehb_allreduce7)"
+            except Exception as e:   # noqa: BLE001
+                if rank == 0:
+                    print("peer all-reduce unavailable (%s); using NCCL" % e, file=sys.stderr)
+        agree = torch.tensor([1.0 if collective.startswith("NVLink") else 0.0], device=dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        if agree.item() < 1.0:
+            collective = "nccl all-reduce 7xf32 per step"
+    use_peer = collective.startswith("NVLink")
 
     def step(k):
         s = k % R
         ctx.render_views_fused(ids, mvp_dev[s], ref_dev[s], H, W, backward=True, out=(masks[s], loss, gmvp))
         if world > 1:   # the solver's one exchange step: all-reduce of (g_dof[6], loss) -- trainer/base.py:349
-            dist.all_reduce(g7)
+            if use_peer:
+                ctx.allreduce7(g7)
+            else:
+                dist.all_reduce(g7)
 
     def barrier():
         torch.cuda.synchronize()
@@ -309,7 +327,7 @@ def run_b200(args):
                            "l2": "ring of %d view-sets (%.0f MB of masks+refs) > 126 MB L2" %
                                  (R, R * B * H * W * 8 / 1e6),
                            "pipelines": int(os.environ.get("EHB_PIPES", "2")),
-                           "collective": "all-reduce 7xf32 per step" if world > 1 else "none"},
+                           "collective": collective},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu, "need_clip_triangles": int(nclip)}
         print(json.dumps(line), flush=True)
@@ -324,6 +342,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"], help="N>1: how the 7 floats are all-reduced")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

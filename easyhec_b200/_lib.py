@@ -72,6 +72,9 @@ _PROTOS = {
     "ehb_solver_step_begin_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                            C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ehb_solver_step_end": (C.c_int, [C.c_void_p, C.c_int]),
+    "ehb_comm_local_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ehb_comm_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "ehb_allreduce7": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ehb_launch_count": (C.c_longlong, [C.c_void_p]),
 }
 
@@ -344,3 +347,22 @@ class Context:
 
     def solver_step_end(self, slot):
         _check(lib().ehb_solver_step_end(self._h, slot))
+
+    # -- NVLink one-shot all-reduce ----------------------------------------------------------------------------
+    def comm_connect(self, group=None):
+        """Exchange the CUDA IPC handles of the per-rank mailboxes through torch.distributed and map the peers."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        buf = (C.c_ubyte * 64)()
+        _check(lib().ehb_comm_local_handle(self._h, buf))
+        mine = torch.tensor(list(buf), dtype=torch.uint8, device=self.device)
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine, group=group)
+        flat = torch.cat(allh).cpu().numpy().tobytes()
+        _check(lib().ehb_comm_connect(self._h, rank, world, flat))
+        dist.barrier(group)
+        return rank, world
+
+    def allreduce7(self, g7):
+        _dev_check(g7, torch.float32, self.device, "g7")
+        _check(lib().ehb_allreduce7(self._h, _ptr(g7), _stream(self.device)))

@@ -116,6 +116,9 @@ struct Ctx {
     size_t evUsed = 0;
     double poolFactor = 2.0;          // beyond the budget: plane pool = items * H * W * poolFactor entries, grown on overflow
     double poolBudget = POOL_BUDGET;
+    EhbComm comm = {};                // NVLink peer mailboxes (ehb_comm_*)
+    unsigned int* commBox = nullptr;  // own mailbox (device)
+    bool commReady = false;
 };
 
 struct DeviceGuard {
@@ -869,6 +872,56 @@ int ehb_solver_step_end(ehb_ctx_t h, int slot)
         CU(cudaMemsetAsync(&c->ctr[MAX_PIPES + slot].flags, 0, sizeof(unsigned), c->slotStream[slot]));
         return fail(EHB_E_OVERFLOW, "depth-plane pool was too small for this step; it has been grown, submit the step again");
     }
+    return EHB_OK;
+}
+
+int ehb_comm_local_handle(ehb_ctx_t h, void* handle64)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || !handle64) return fail(EHB_E_ARG, "null pointer argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard guard(c->device);
+    if (!c->commBox) {
+        const size_t words = 2 * EHB_COMM_MAX * 8 + 8;
+        CU(cudaMalloc((void**)&c->commBox, words * sizeof(unsigned)));
+        CU(cudaMemset(c->commBox, 0, words * sizeof(unsigned)));
+        CU(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t hd;
+    CU(cudaIpcGetMemHandle(&hd, c->commBox));
+    memcpy(handle64, &hd, 64);
+    return EHB_OK;
+}
+
+int ehb_comm_connect(ehb_ctx_t h, int rank, int world, const void* handles)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || !handles || world < 1 || world > EHB_COMM_MAX || rank < 0 || rank >= world || !c->commBox)
+        return fail(EHB_E_ARG, "bad comm arguments (call ehb_comm_local_handle first; world <= %d)", EHB_COMM_MAX);
+    DeviceGuard guard(c->device);
+    for (int r = 0; r < world; r++) {
+        if (r == rank) { c->comm.peer[r] = c->commBox; continue; }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, (const char*)handles + 64 * r, 64);
+        void* ptr = nullptr;
+        CU(cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+        c->comm.peer[r] = (unsigned int*)ptr;
+    }
+    c->comm.step = c->commBox + 2 * EHB_COMM_MAX * 8;
+    c->comm.rank = rank; c->comm.world = world;
+    c->commReady = true;
+    return EHB_OK;
+}
+
+int ehb_allreduce7(ehb_ctx_t h, float* g7_dev, void* stream)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || !g7_dev) return fail(EHB_E_ARG, "null pointer argument");
+    if (!c->commReady) return fail(EHB_E_ARG, "peer mailboxes are not connected (ehb_comm_connect)");
+    DeviceGuard guard(c->device);
+    ehb_k_allreduce7<<<1, 32, 0, (cudaStream_t)stream>>>(c->comm, g7_dev);
+    c->launches += 1;
+    CU(cudaGetLastError());
     return EHB_OK;
 }
 

@@ -27,7 +27,7 @@ def shard_views(n_views: int, rank: int, world: int):
 class PoseSolver:
     def __init__(self, meshes, link_poses, K, masks_ref, init_Tc_c2b, H, W, lr=3e-3, weight_decay=5e-4,
                  betas=(0.9, 0.999), eps=1e-8, device=None, group=None, n_views_global=None, use_graph=True,
-                 ctx=None, history=10000):
+                 ctx=None, history=10000, peer_allreduce=True):
         """meshes: list of (verts, faces) / Mesh;  link_poses (B,L,4,4);  K (3,3);  masks_ref (B,H,W) bool/u8/f32
         -- this rank's views only;  n_views_global: total views over all ranks (defaults to B)."""
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -61,6 +61,16 @@ class PoseSolver:
         F = sum(self.ctx.mesh_info(i)[1] for i in self.mesh_ids)
         self.ctx.reserve(self.B, self.L, F, self.H, self.W)
         self.use_graph = use_graph
+        self._peer = False
+        if self.world > 1 and peer_allreduce:
+            try:   # NVLink peer-mailbox all-reduce instead of a NCCL launch on the critical path
+                self.ctx.comm_connect(group)
+                self._peer = True
+            except Exception:   # noqa: BLE001 -- e.g. GPUs without peer access: NCCL does the same job
+                self._peer = False
+            ok = torch.tensor([1.0 if self._peer else 0.0], device=dev)
+            torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN, group=group)
+            self._peer = ok.item() >= 1.0
         self._graph = None
         self.iterations = 0
 
@@ -74,7 +84,10 @@ class PoseSolver:
         c.pose_backward(self.dof, self.K, self.link_poses, self.g_mvp, self.loss_b, self.H, self.W,
                         grad_scale=self.B / self.B_global, loss_scale=1.0 / self.B_global, out=self.g7)
         if self.world > 1:
-            torch.distributed.all_reduce(self.g7, group=self.group)
+            if self._peer:
+                c.allreduce7(self.g7)
+            else:
+                torch.distributed.all_reduce(self.g7, group=self.group)
         c.adam_step(self.dof, self.g7, self.state, self.lr, self.betas, self.eps, self.wd, hist=self.hist)
 
     def _check_flags(self):

@@ -163,6 +163,17 @@ EHB_API int ehb_solver_step_begin_u8(ehb_ctx_t ctx, int slot, const int* mesh_id
                              const uint8_t* ref_u8_host, int H, int W, double* loss_host, double* g_mvp_host);
 EHB_API int ehb_solver_step_end(ehb_ctx_t ctx, int slot);
 
+/* One-shot all-reduce (sum) of the 7 floats { d loss/d dof, loss } over NVLink peer memory, for view sharding across
+ * the GPUs of one box -- the exchange DDP performs for the reference's 6-float parameter (easyhec/trainer/base.py:349).
+ *   ehb_comm_local_handle: allocates this rank's mailbox, returns its 64-byte CUDA IPC handle
+ *   ehb_comm_connect     : handles = world x 64 bytes (all ranks' handles, e.g. all-gathered with torch.distributed)
+ *   ehb_allreduce7       : one tiny kernel on `stream`: writes its 7 floats into every peer's mailbox, waits for all
+ *                          peers' values of the same step, sums in rank order (bit-identical on every rank).
+ * Every rank must call ehb_allreduce7 the same number of times. */
+EHB_API int ehb_comm_local_handle(ehb_ctx_t ctx, void* handle64);
+EHB_API int ehb_comm_connect(ehb_ctx_t ctx, int rank, int world, const void* handles);
+EHB_API int ehb_allreduce7(ehb_ctx_t ctx, float* g7_dev, void* stream);
+
 /* Number of kernels this library has launched on the context since creation (for launch accounting). */
 EHB_API long long ehb_launch_count(ehb_ctx_t ctx);
 

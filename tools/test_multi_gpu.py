@@ -1,0 +1,80 @@
+"""Multi-GPU checks (run with torchrun on a box with >= 2 GPUs; not part of the single-GPU pytest run):
+  1. ehb_allreduce7 (NVLink peer mailboxes) == NCCL all-reduce, bit for bit across ranks, over many steps;
+  2. PoseSolver with views sharded over the ranks reaches the same pose as a single-rank solve of all views.
+
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/test_multi_gpu.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from easyhec_b200._lib import Context
+    from easyhec_b200.scenes import make_scene, perturb_pose
+    from easyhec_b200.solver import PoseSolver, shard_views
+    from util import scene_mvps
+    ctx = Context(dev)
+    ctx.comm_connect()
+    g = torch.Generator(device="cpu").manual_seed(rank)
+    worst = 0.0
+    for step in range(200):
+        v = torch.randn(7, generator=g).to(dev)
+        a = v.clone(); b = v.clone()
+        ctx.allreduce7(a)
+        dist.all_reduce(b)
+        worst = max(worst, float((a - b).abs().max()))
+        gathered = [torch.empty_like(a) for _ in range(world)]
+        dist.all_gather(gathered, a)
+        assert all(torch.equal(gathered[0], t) for t in gathered), "ranks disagree"
+    assert worst < 1e-5, worst
+    # latency of the two collectives (device time, 200 back-to-back calls)
+    for name, fn in (("peer", lambda t: ctx.allreduce7(t)), ("nccl", lambda t: dist.all_reduce(t))):
+        t = torch.zeros(7, device=dev)
+        for _ in range(20):
+            fn(t)
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(200):
+            fn(t)
+        e1.record(); torch.cuda.synchronize()
+        if rank == 0:
+            print("%s all-reduce of 7 floats: %.2f us per call" % (name, 1e3 * e0.elapsed_time(e1) / 200))
+    # sharded solve vs single-rank solve
+    B, H, W = 6, 120, 160
+    sc = make_scene(B, H, W, links="xarm7", seed=21)
+    ids = [ctx.register_mesh(m.vertices, m.faces) for m in sc["meshes"]]
+    ref = ctx.render_binary_batch(ids, torch.from_numpy(scene_mvps(sc, H, W)).to(dev), H, W)
+    init = perturb_pose(sc["Tc_c2b"], np.random.RandomState(22), 0.02, 2.0)
+    mine = shard_views(B, rank, world)
+    s = PoseSolver(sc["meshes"], sc["link_poses"][mine], sc["K"], ref[mine], init, H, W, n_views_global=B, device=dev)
+    s.step(100)
+    full = PoseSolver(sc["meshes"], sc["link_poses"], sc["K"], ref, init, H, W, device=dev, group=None, peer_allreduce=False)
+    full.world = 1
+    full.step(100)
+    d = float((s.dof - full.dof).abs().max())
+    e = s.pose_error(sc["Tc_c2b"])
+    if rank == 0:
+        print("sharded vs single-rank dof max |diff| = %.2e; pose error %.3f mm / %.4f deg (peer all-reduce: %s)" %
+              (d, 1e3 * e[0], e[1], s._peer))
+    assert d < 2e-3, d
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("multi-GPU checks ok")
+
+
+if __name__ == "__main__":
+    main()
