@@ -41,6 +41,7 @@ _PROTOS = {
     "ehb_ctx_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "ehb_ctx_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "ehb_ctx_debug_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]),
+    "ehb_ctx_debug_buffer": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]),
     "ehb_ctx_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint), C.POINTER(C.c_longlong)]),
     "ehb_mesh_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "ehb_mesh_update_verts": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
@@ -197,16 +198,21 @@ class Context:
         _check(lib().ehb_ctx_profile(self._h, int(bool(enable))))
 
     def kernel_times(self):
-        """-> ({vertex, plan, raster (+raster_big, + empty-tile stream), tiles: summed ms}, passes); synchronises."""
+        """-> ({table, front (vertex | clear | classify), raster (+raster_big, + empty-tile stream), tiles: summed ms}, passes); synchronises."""
         ms = (C.c_double * 4)()
         n = C.c_longlong()
         _check(lib().ehb_ctx_kernel_times(self._h, ms, C.byref(n)))
-        return dict(zip(("vertex", "plan", "raster", "tiles"), list(ms))), n.value
+        return dict(zip(("table", "front", "raster", "tiles"), list(ms))), n.value
 
     def debug_counters(self, reset=True):
         out = (C.c_ulonglong * 16)()
         _check(lib().ehb_ctx_debug_counters(self._h, out, int(reset)))
         return list(out)
+
+    def debug_buffer(self, n_words=0):
+        out = (C.c_ulonglong * max(n_words, 1))()
+        _check(lib().ehb_ctx_debug_buffer(self._h, out, n_words))
+        return list(out)[:n_words]
 
     def launch_count(self) -> int:
         return int(lib().ehb_launch_count(self._h))

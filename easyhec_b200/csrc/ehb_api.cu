@@ -40,7 +40,8 @@ struct Mesh {
     float4* verts = nullptr;
     int4* faces = nullptr;
     int4* opp = nullptr;
-    int V = 0, F = 0;
+    float4* boxes = nullptr;          // [2 * nboxes] AABBs of contiguous vertex chunks (device, recomputed with the vertices)
+    int V = 0, F = 0, nboxes = 0;
     bool live = false;
 };
 
@@ -72,7 +73,6 @@ constexpr int N_SCRATCH = MAX_PIPES + N_SLOTS;
 struct Scratch {
     DevBuf<float4> vclip;             // pre-transformed vertices of one pass
     DevBuf<int2> vsnap;
-    DevBuf<int> bbraw;                // raw snapped bounding boxes, kept at the "empty" sentinel between passes
     DevBuf<EhbPlane> plane;
     DevBuf<unsigned long long> pool;  // depth planes of one pass, bump-allocated
     DevBuf<uint32_t> tileList, emptyList, touch;
@@ -82,7 +82,7 @@ struct Scratch {
     EhbCounters* ctr = nullptr;
     void release()
     {
-        vclip.release(); vsnap.release(); bbraw.release(); plane.release(); pool.release(); tileList.release(); emptyList.release();
+        vclip.release(); vsnap.release(); plane.release(); pool.release(); tileList.release(); emptyList.release();
         touch.release(); bigRec.release(); units.release(); spill.release();
     }
 };
@@ -119,6 +119,7 @@ struct Ctx {
     EhbComm comm = {};                // NVLink peer mailboxes (ehb_comm_*)
     unsigned int* commBox = nullptr;  // own mailbox (device)
     bool commReady = false;
+    unsigned long long* dbgbuf = nullptr;   // EHB_TIMING builds
 };
 
 struct DeviceGuard {
@@ -173,6 +174,29 @@ __global__ void ehb_k_pad_verts(const float* __restrict__ src, float4* __restric
     if (i < V) dst[i] = make_float4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 1.f);
 }
 
+// AABB of each of nb contiguous vertex chunks (one warp per chunk) -> boxes[2*b] = min, boxes[2*b+1] = max
+__global__ void ehb_k_boxes(const float4* __restrict__ verts, int V, int nb, float4* __restrict__ boxes)
+{
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const int cs = (V + nb - 1) / nb, i0 = b * cs, i1 = min(V, i0 + cs);
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int i = i0 + lane; i < i1; i += 32) {
+        const float4 v = verts[i];
+        lo[0] = fminf(lo[0], v.x); lo[1] = fminf(lo[1], v.y); lo[2] = fminf(lo[2], v.z);
+        hi[0] = fmaxf(hi[0], v.x); hi[1] = fmaxf(hi[1], v.y); hi[2] = fmaxf(hi[2], v.z);
+    }
+    for (int o = 16; o > 0; o >>= 1)
+        for (int k = 0; k < 3; k++) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+    if (lane == 0) {
+        if (i0 >= i1) { lo[0] = lo[1] = lo[2] = hi[0] = hi[1] = hi[2] = 0.f; }   // empty chunk: a point that is re-covered below
+        boxes[2 * b] = make_float4(lo[0], lo[1], lo[2], 1.f);
+        boxes[2 * b + 1] = make_float4(hi[0], hi[1], hi[2], 1.f);
+    }
+}
+
 // num[q] += sum over this block's pixels of k (C - k), k = number of cameras whose mask covers the pixel.
 // sum_px unbiased_var_c(mask) = num / (C (C - 1)) exactly, so the reduction is integer and order-free.
 __global__ void __launch_bounds__(256) ehb_k_variance(const uint8_t* __restrict__ masks, int C, long long n,
@@ -220,12 +244,6 @@ constexpr int SPILL_PER_LINK = 2 * (EHB_RS - 1) * (EHB_RS - 1);   // most silhou
 constexpr int BIG_CAP = 1 << 17;     // deferred triangles per pass (16 MB of records)
 constexpr int UNIT_CAP = 1 << 19;
 
-__global__ void ehb_k_init_raw(int* raw, size_t n)
-{
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        raw[i] = (i & 2) ? EHB_RAW_MAX : EHB_RAW_MIN;
-}
-
 struct Io {
     const float* ref = nullptr; const uint8_t* ref_u8 = nullptr;
     float* masks = nullptr; double* loss = nullptr; double* gmvp = nullptr; float* gpos = nullptr;
@@ -262,7 +280,7 @@ int build_robot(Ctx* c, const int* mesh_ids, int L, EhbRobot& rb)
         if (id < 0 || id >= (int)c->meshes.size() || !c->meshes[id].live) return fail(EHB_E_ARG, "unknown mesh id %d", id);
         const Mesh& m = c->meshes[id];
         if (m.F > (int)EHB_FACE_MASK) return fail(EHB_E_ARG, "mesh %d has too many faces", id);
-        rb.link[l].verts = m.verts; rb.link[l].faces = m.faces; rb.link[l].opp = m.opp;
+        rb.link[l].verts = m.verts; rb.link[l].faces = m.faces; rb.link[l].opp = m.opp; rb.link[l].boxes = m.boxes; rb.link[l].nboxes = m.nboxes;
         rb.link[l].V = m.V; rb.link[l].F = m.F;
         rb.foff[l + 1] = rb.foff[l] + m.F;
         rb.voff[l + 1] = rb.voff[l] + m.V;
@@ -277,12 +295,6 @@ int ensure_scratch(Ctx* c, Scratch& sc, int items, int L, int Lp, int H, int W, 
     if ((r = sc.vsnap.ensure((size_t)items * std::max(Vtot, 1), capturing))) return r;
     const int ntiles = ((W + EHB_T - 1) / EHB_T) * ((H + EHB_T - 1) / EHB_T);
     if ((r = sc.spill.ensure((size_t)c->nSM * c->occ * SPILL_PER_LINK * L, capturing))) return r;
-    const size_t nraw = (size_t)items * Lp * 4;
-    if (nraw > sc.bbraw.n) {
-        if ((r = sc.bbraw.ensure(nraw, capturing))) return r;
-        ehb_k_init_raw<<<64, 256>>>(sc.bbraw.p, sc.bbraw.n);
-        CU(cudaDeviceSynchronize());
-    }
     if ((r = sc.plane.ensure((size_t)items * Lp, capturing))) return r;
     if ((r = sc.tileList.ensure((size_t)items * ntiles, capturing))) return r;
     if ((r = sc.touch.ensure((size_t)items * ntiles, capturing))) return r;
@@ -328,11 +340,12 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
     if ((r = ensure_scratch(c, sc, items, L, p.Lp, H, W, p.Vtot, capturing))) return r;
     p.mvp = mvp_dev;
     p.vclip = sc.vclip.p; p.vsnap = sc.vsnap.p;
-    p.bbraw = sc.bbraw.p; p.plane = sc.plane.p; p.pool = sc.pool.p; p.poolCap = sc.pool.n;
+    p.plane = sc.plane.p; p.pool = sc.pool.p; p.poolCap = sc.pool.n;
     p.tileList = sc.tileList.p; p.emptyList = sc.emptyList.p; p.touch = unionMode ? nullptr : sc.touch.p; p.bigRec = sc.bigRec.p; p.units = sc.units.p; p.bigCap = BIG_CAP; p.unitCap = UNIT_CAP; p.ctr = sc.ctr;
     p.ref = io.ref; p.ref_u8 = io.ref_u8; p.masks = io.masks; p.loss = io.loss; p.gmvp = io.gmvp; p.gpos = io.gpos;
     p.dy = io.dy; p.out_u8 = io.out_u8;
     p.pairSpill = sc.spill.p; p.spillCap = SPILL_PER_LINK * L;
+    p.dbgbuf = c->dbgbuf;
 
     cudaEvent_t* ev = nullptr;
     if (c->profiling && !capturing) {
@@ -345,11 +358,13 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
         c->evUsed += 5;
     }
     if (ev) cudaEventRecord(ev[0], st);
-    CU(launch(ehb_k_vertex, dim3((unsigned)std::max(1, (p.Vtot + 255) / 256), (unsigned)items), dim3(256), 0, st, false, rb, p));
+    CU(launch(ehb_k_table, dim3((unsigned)((items * p.Lp + 7) / 8)), dim3(256), 0, st, false, rb, p));
     if (ev) cudaEventRecord(ev[1], st);
+    const int vchunks = std::max(1, (p.Vtot + 255) / 256);
     const int clearBlocks = c->nSM;
     const long long tileWarps = unionMode ? 0 : (long long)items * p.ntiles;
-    CU(launch(ehb_k_plan, dim3((unsigned)(clearBlocks + (tileWarps * 32 + 255) / 256)), dim3(256), 0, st, true, p, clearBlocks));
+    CU(launch(ehb_k_front, dim3((unsigned)(vchunks * items + clearBlocks + (tileWarps * 32 + 255) / 256)), dim3(256), 0, st, true, rb, p,
+              vchunks, clearBlocks));
     if (ev) cudaEventRecord(ev[2], st);
     const int chunks = std::max(1, (p.Ftot + EHB_RWARPS * 32 - 1) / (EHB_RWARPS * 32));
     const int streamBlocks = (unionMode || mode == EHB_MODE_AA_BWD) ? 0 : c->nSM;
@@ -452,7 +467,7 @@ int ehb_ctx_destroy(ehb_ctx_t h)
     if (!c) return EHB_OK;
     DeviceGuard guard(c->device);
     cudaDeviceSynchronize();
-    for (auto& m : c->meshes) if (m.live) { cudaFree(m.verts); cudaFree(m.faces); cudaFree(m.opp); }
+    for (auto& m : c->meshes) if (m.live) { cudaFree(m.verts); cudaFree(m.faces); cudaFree(m.opp); cudaFree(m.boxes); }
     for (int k = 0; k < MAX_PIPES; k++) { cudaStreamDestroy(c->pipeStream[k]); cudaEventDestroy(c->evJoin[k]); }
     for (int k = 0; k < N_SCRATCH; k++) c->sc[k].release();
     for (int k = 0; k < N_SLOTS; k++) { cudaStreamDestroy(c->slotStream[k]); cudaEventDestroy(c->slotDone[k]); c->slotMvp[k].release(); c->slotOut[k].release(); c->slotRef[k].release(); }
@@ -507,6 +522,18 @@ int ehb_ctx_debug_counters(ehb_ctx_t h, unsigned long long* out16, int reset)
     CU(cudaMemcpy(&hc, c->ctr, sizeof hc, cudaMemcpyDeviceToHost));
     for (int i = 0; i < 16; i++) out16[i] = hc.dbg[i];
     if (reset) { for (int i = 0; i < 16; i++) hc.dbg[i] = 0; CU(cudaMemcpy(c->ctr, &hc, sizeof hc, cudaMemcpyHostToDevice)); }
+    return EHB_OK;
+}
+
+int ehb_ctx_debug_buffer(ehb_ctx_t h, unsigned long long* out, int n_words)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c) return fail(EHB_E_ARG, "null context");
+    DeviceGuard guard(c->device);
+    const size_t words = (size_t)c->nSM * 8 * 5;
+    if (!c->dbgbuf) { CU(cudaMalloc((void**)&c->dbgbuf, words * 8)); CU(cudaMemset(c->dbgbuf, 0, words * 8)); return EHB_OK; }
+    CU(cudaDeviceSynchronize());
+    if (out && n_words > 0) CU(cudaMemcpy(out, c->dbgbuf, std::min((size_t)n_words, words) * 8, cudaMemcpyDeviceToHost));
     return EHB_OK;
 }
 
@@ -590,6 +617,12 @@ int ehb_mesh_register(ehb_ctx_t h, const float* verts, int V, const int* faces, 
     CU(cudaMemcpy(m.verts, v4.data(), v4.size() * sizeof(float4), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(m.faces, f4.data(), f4.size() * sizeof(int4), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(m.opp, opp.data(), opp.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    m.nboxes = V > 0 ? std::max(1, std::min(32, (V + 63) / 64)) : 0;
+    CU(cudaMalloc((void**)&m.boxes, 2 * 32 * sizeof(float4)));
+    if (m.nboxes > 0) {
+        ehb_k_boxes<<<m.nboxes, 32>>>(m.verts, V, m.nboxes, m.boxes);
+        CU(cudaDeviceSynchronize());
+    }
     m.live = true;
     int id = -1;
     for (size_t i = 0; i < c->meshes.size(); i++) if (!c->meshes[i].live) { id = (int)i; break; }
@@ -607,7 +640,8 @@ int ehb_mesh_update_verts(ehb_ctx_t h, int mesh_id, const float* verts_dev, int 
     if (V == 0) return EHB_OK;
     DeviceGuard guard(c->device);
     ehb_k_pad_verts<<<(V + 255) / 256, 256, 0, (cudaStream_t)stream>>>(verts_dev, m.verts, V);
-    c->launches += 1;
+    ehb_k_boxes<<<m.nboxes, 32, 0, (cudaStream_t)stream>>>(m.verts, V, m.nboxes, m.boxes);
+    c->launches += 2;
     CU(cudaGetLastError());
     return EHB_OK;
 }
@@ -619,7 +653,7 @@ int ehb_mesh_release(ehb_ctx_t h, int mesh_id)
     DeviceGuard guard(c->device);
     CU(cudaDeviceSynchronize());
     Mesh& m = c->meshes[mesh_id];
-    cudaFree(m.verts); cudaFree(m.faces); cudaFree(m.opp);
+    cudaFree(m.verts); cudaFree(m.faces); cudaFree(m.opp); cudaFree(m.boxes);
     m = Mesh();
     return EHB_OK;
 }

@@ -20,7 +20,8 @@ struct EhbLink {
     const float4* verts;  // [V]  xyz, w unused (1)
     const int4* faces;    // [F]  i0 i1 i2, w unused
     const int4* opp;      // [F]  vertex opposite to edge k in the neighbouring triangle, or -1
-    int V, F;
+    const float4* boxes;  // [2*nboxes] object-space AABBs (min, max) of nboxes contiguous vertex chunks
+    int V, F, nboxes, pad;
 };
 
 struct EhbRobot {

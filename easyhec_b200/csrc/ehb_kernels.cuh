@@ -4,11 +4,12 @@
 // before summing (rb_solver.py:62-68), so visibility is resolved per (item, link) -- an "item" is a camera view or
 // one render of a batch.  Each (item, link) gets a 64-bit (depth key | triangle id) plane covering only the
 // link's screen bounding box; for robot views all planes of a step are a few tens of MB and stay L2-resident.
-//   k_vertex : one thread per (item, vertex): transform and snap ONCE (a vertex is shared by ~6 triangles), keep the
-//              clip-space and snapped positions (a few MB, L2-resident), reduce the per-(item, link) bounding box
-//              and -- in the last CTA to finish -- bump-allocate the planes in the plane pool
-//   k_plan   : (a) planes := EMPTY (only the allocated part of the pool);  (b) one warp per 32x32 tile: tiles that some
-//              link's bbox touches go to the tile queue (several links first), the others to the empty-tile list
+//   k_table  : one warp per plane: conservative screen bbox of the link from the projected corners of its <= 32
+//              object-space chunk AABBs (256 point transforms); the last CTA to finish bump-allocates the planes
+//   k_front  : three independent jobs in one launch: (a) one thread per (item, vertex): transform and snap ONCE (a
+//              vertex is shared by ~6 triangles), keep the clip-space and snapped positions (a few MB, L2-resident);
+//              (b) planes := EMPTY (allocated part only);  (c) one warp per 32x32 tile: tiles that some link's bbox
+//              touches go to the tile queue (several links first), the others to the empty-tile list
 //   k_raster : NO binning, NO block barriers: each warp takes 32 triangles (one per lane): setup -> record in the
 //              warp's shared memory; the rows of the 32 clipped bboxes form one flat space; 32 rows at a time (one per
 //              lane) get their exactly covered span (float estimate + integer fix-up == testing every sample), and
@@ -54,7 +55,7 @@ struct EhbCounters {
     unsigned int nLight;     // ... the others from the back
     unsigned int workCursor;
     unsigned int nEmpty;     // tiles no link touches: streamed (mask = 0, loss += ref^2) by spare CTAs of the raster launch
-    unsigned int vertexDone; // CTAs of k_vertex that have finished: the last one allocates the planes
+    unsigned int vertexDone; // CTAs of k_table that have finished: the last one allocates the planes
     unsigned int nBigRec;    // deferred (not small) triangles: records parked in global memory ...
     unsigned int nUnits;     // ... and cut into bounded units that k_raster_big spreads over the whole chip
     unsigned int flags;      // 1: plane pool too small (results invalid, grow and rerun), 2: triangles need clipping
@@ -69,9 +70,8 @@ struct EhbParams {
     int mode, rule, do_bwd, clamp;
     float invB;
     const float* mvp;        // [items, L, 16]
-    float4* vclip;           // [items, Vtot]  clip-space position of every vertex (written by k_vertex)
+    float4* vclip;           // [items, Vtot]  clip-space position of every vertex (written by k_front)
     int2* vsnap;             // [items, Vtot]  snapped screen position (1/16 px), x = INT_MIN when not drawable
-    int* bbraw;              // [items, Lp, 4]  min X, min Y, max X, max Y of the snapped vertices
     EhbPlane* plane;         // [items, Lp]
     unsigned long long* pool;
     unsigned long long poolCap;
@@ -92,10 +92,9 @@ struct EhbParams {
     uint8_t* out_u8;         // [items, H, W]  UNION
     EhbPairEnt* pairSpill;   // [gridDim.x of k_tiles][spillCap] overflow of the shared-memory pair lists
     int spillCap;
+    unsigned long long* dbgbuf;   // EHB_TIMING builds: per k_tiles CTA {start ns, end ns, tiles, longest tile cycles, its links}
 };
 
-#define EHB_RAW_MIN 0x7F7F7F7F          // memset(0x7F) / memset(0x80) patterns: "no vertex yet"
-#define EHB_RAW_MAX ((int)0x80808080)
 #ifndef EHB_SMALL_AREA
 #define EHB_SMALL_AREA 96               // triangles whose clipped bbox has more candidate samples are deferred
 #endif
@@ -137,69 +136,75 @@ __device__ __forceinline__ double ehb_warp_sum(double v)
     return v;
 }
 
-// pixel bbox of a plane from the raw snapped extremes (same formulas as ehb_tri_setup's per-triangle range)
-__device__ __forceinline__ bool ehb_raw_to_pixels(const int* raw, int H, int W, int& x0, int& y0, int& x1, int& y1)
-{
-    const int mnx = raw[0], mny = raw[1], mxx = raw[2], mxy = raw[3];
-    if (mnx > mxx || mny > mxy) return false;
-    const int bx = 8 * W - 8, by = 8 * H - 8;
-    x0 = max((mnx + bx + 15) >> 4, 0); x1 = min((mxx + bx) >> 4, W - 1);
-    y0 = max((mny + by + 15) >> 4, 0); y1 = min((mxy + by) >> 4, H - 1);
-    return x0 <= x1 && y0 <= y1;
-}
-
-// ------------------------------------------------------------------------------------------------ k_vertex
-__global__ void __launch_bounds__(256) ehb_k_vertex(const __grid_constant__ EhbRobot rb,
-                                                  const __grid_constant__ EhbParams p)
+// ------------------------------------------------------------------------------------------------ k_table
+// One warp per depth plane: conservative screen bounding box of the link from the projected corners of its (up to
+// 32) object-space chunk AABBs -- 256 point transforms instead of a reduction over all vertices, and no dependency on
+// the vertex pass.  The last CTA to finish (atomic ticket) bump-allocates the planes in the pool.
+__global__ void __launch_bounds__(256) ehb_k_table(const __grid_constant__ EhbRobot rb,
+                                                   const __grid_constant__ EhbParams p)
 {
     ehb_pdl_enter();
-    const int item = blockIdx.y;
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    if (blockIdx.x == 0) {
-        if (item == 0 && threadIdx.x == 0) {
-            p.ctr->nTiles = 0u;
-            p.ctr->nLight = 0u;
-            p.ctr->nEmpty = 0u;
-            p.ctr->workCursor = 0u;
-            p.ctr->nBigRec = 0u;
-            p.ctr->nUnits = 0u;
-        }
-        if (p.loss && threadIdx.x == 0) p.loss[item] = 0.0;
-        if (p.gmvp)
-            for (int i = threadIdx.x; i < p.L * 16; i += blockDim.x) p.gmvp[(size_t)item * p.L * 16 + i] = 0.0;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        p.ctr->nTiles = 0u; p.ctr->nLight = 0u; p.ctr->nEmpty = 0u; p.ctr->workCursor = 0u;
+        p.ctr->nBigRec = 0u; p.ctr->nUnits = 0u;
     }
-    int l = -1, X = 0, Y = 0;
-    if (g < p.Vtot) {
-        const int lk = ehb_find_link(rb.voff, rb.L, g);
-        float m[16], c[4];
-        ehb_load_mvp(p.mvp + ((size_t)item * p.L + lk) * 16, m);
-        ehb_xform(__ldg(rb.link[lk].verts + (g - rb.voff[lk])), m, c);
-        int2 sn = make_int2(INT_MIN, 0);
-        if (c[3] >= fabsf(c[2])) {   // only such vertices can belong to a drawable triangle
-            const float r = 1.0f / c[3];
-            X = ehb_rni_sat(c[0] * r * (float)(p.W * 8));
-            Y = ehb_rni_sat(c[1] * r * (float)(p.H * 8));
-            sn = make_int2(X, Y);
-            const int G = 1 << 28;
-            if (X <= G && X >= -G && Y <= G && Y >= -G) l = p.Lp == 1 ? 0 : lk;
-        }
-        p.vclip[(size_t)item * p.Vtot + g] = make_float4(c[0], c[1], c[2], c[3]);
-        p.vsnap[(size_t)item * p.Vtot + g] = sn;
+    // outputs that the later kernels accumulate into
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.items; i += gridDim.x * blockDim.x) {
+        if (p.loss) p.loss[i] = 0.0;
     }
-    // one set of atomics per (warp, plane): lanes are grouped by plane with match.any, reduced with redux
-    const unsigned grp = __match_any_sync(0xffffffffu, l);
-    const int mnx = __reduce_min_sync(grp, X), mny = __reduce_min_sync(grp, Y);
-    const int mxx = __reduce_max_sync(grp, X), mxy = __reduce_max_sync(grp, Y);
-    if (l >= 0 && lane == __ffs(grp) - 1) {
-        int* raw = p.bbraw + ((size_t)item * p.Lp + l) * 4;
-        atomicMin(raw + 0, mnx); atomicMin(raw + 1, mny); atomicMax(raw + 2, mxx); atomicMax(raw + 3, mxy);
+    if (p.gmvp)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.items * p.L * 16; i += gridDim.x * blockDim.x) p.gmvp[i] = 0.0;
+    if (wid < p.items * p.Lp) {
+        const int item = wid / p.Lp, pli = wid - item * p.Lp;
+        float umin = 3.0e38f, umax = -3.0e38f, vmin = 3.0e38f, vmax = -3.0e38f;
+        bool bad = false, any = false;
+        const int l0 = p.Lp == 1 ? 0 : pli, l1 = p.Lp == 1 ? p.L : pli + 1;
+        for (int l = l0; l < l1; l++) {
+            const EhbLink& lk = rb.link[l];
+            if (lane < lk.nboxes) {
+                float m[16];
+                ehb_load_mvp(p.mvp + ((size_t)item * p.L + l) * 16, m);
+                const float4 lo = __ldg(lk.boxes + 2 * lane), hi = __ldg(lk.boxes + 2 * lane + 1);
+                any = true;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const float4 v = make_float4((k & 1) ? hi.x : lo.x, (k & 2) ? hi.y : lo.y, (k & 4) ? hi.z : lo.z, 1.f);
+                    float c[4];
+                    ehb_xform(v, m, c);
+                    if (!(c[3] > 1e-6f)) { bad = true; continue; }   // corner at or behind the camera plane: no finite bound
+                    const float u = (c[0] / c[3] + 1.f) * (0.5f * (float)p.W), w = (c[1] / c[3] + 1.f) * (0.5f * (float)p.H);
+                    umin = fminf(umin, u); umax = fmaxf(umax, u); vmin = fminf(vmin, w); vmax = fmaxf(vmax, w);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            umin = fminf(umin, __shfl_xor_sync(0xffffffffu, umin, o)); umax = fmaxf(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+            vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o)); vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        any = __any_sync(0xffffffffu, any);
+        if (lane == 0) {
+            EhbPlane pl;
+            pl.x0 = pl.y0 = pl.w = pl.h = 0; pl.off = 0; pl.pad = 0;
+            if (any) {
+                int x0 = 0, y0 = 0, x1 = p.W - 1, y1 = p.H - 1;
+                if (!bad) {   // pixel p is sampled at p + 0.5; two pixels of margin cover snapping and rounding
+                    x0 = max(0, (int)fmaxf(fminf(floorf(umin) - 2.f, 1e6f), -1e6f)); x1 = min(p.W - 1, (int)fmaxf(fminf(ceilf(umax) + 2.f, 1e6f), -1e6f));
+                    y0 = max(0, (int)fmaxf(fminf(floorf(vmin) - 2.f, 1e6f), -1e6f)); y1 = min(p.H - 1, (int)fmaxf(fminf(ceilf(vmax) + 2.f, 1e6f), -1e6f));
+                }
+                if (x0 <= x1 && y0 <= y1) { pl.x0 = x0; pl.y0 = y0; pl.w = x1 - x0 + 1; pl.h = y1 - y0 + 1; }
+            }
+            p.plane[wid] = pl;
+        }
     }
     // the last CTA to finish sees every bounding box: it bump-allocates the planes of this pass
     __shared__ unsigned s_last;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(&p.ctr->vertexDone, 1u) == gridDim.x * gridDim.y - 1u;
+    if (threadIdx.x == 0) s_last = atomicAdd(&p.ctr->vertexDone, 1u) == gridDim.x - 1u;
     __syncthreads();
     if (!s_last) return;
     __threadfence();
@@ -207,21 +212,21 @@ __global__ void __launch_bounds__(256) ehb_k_vertex(const __grid_constant__ EhbR
     __syncthreads();
     for (int i = threadIdx.x; i < p.items * p.Lp; i += blockDim.x) {
         EhbPlane pl;
-        pl.x0 = pl.y0 = pl.w = pl.h = 0; pl.off = 0; pl.pad = 0;
-        int x0, y0, x1, y1;
-        int raw[4];
-        for (int k = 0; k < 4; k++) raw[k] = __ldcg(p.bbraw + (size_t)i * 4 + k);
-        if (ehb_raw_to_pixels(raw, p.H, p.W, x0, y0, x1, y1)) {
-            const unsigned long long area = (unsigned long long)(x1 - x0 + 1) * (unsigned long long)(y1 - y0 + 1);
-            const unsigned long long off = atomicAdd(&p.ctr->planeCursor, area);
-            if (off + area <= p.poolCap) { pl.x0 = x0; pl.y0 = y0; pl.w = x1 - x0 + 1; pl.h = y1 - y0 + 1; pl.off = (long long)off; }
-            else atomicOr(&p.ctr->flags, 1u);
+        {
+            const int4 a = __ldcg(reinterpret_cast<const int4*>(&p.plane[i]));   // written by other CTAs of this launch: read at L2
+            pl.x0 = a.x; pl.y0 = a.y; pl.w = a.z; pl.h = a.w; pl.off = 0; pl.pad = 0;
         }
-        p.plane[i] = pl;
+        if (pl.w > 0) {
+            const unsigned long long area = (unsigned long long)pl.w * (unsigned long long)pl.h;
+            const unsigned long long off = atomicAdd(&p.ctr->planeCursor, area);
+            if (off + area <= p.poolCap) pl.off = (long long)off;
+            else { pl.w = pl.h = 0; atomicOr(&p.ctr->flags, 1u); }
+            p.plane[i] = pl;
+        }
     }
 }
 
-// ------------------------------------------------------------------------------------------------ k_plan
+// ------------------------------------------------------------------------------------------------ empty tiles
 // A tile no link touches: mask = 0 and loss += sum ref^2, streamed by one warp.
 __device__ __forceinline__ void ehb_stream_empty_tile(const EhbParams& p, int item, int tx, int ty, int lane)
 {
@@ -267,26 +272,45 @@ __device__ __forceinline__ void ehb_stream_empty_tile(const EhbParams& p, int it
     }
 }
 
-__global__ void __launch_bounds__(256) ehb_k_plan(const __grid_constant__ EhbParams p, int clearBlocks)
+// ------------------------------------------------------------------------------------------------ k_front
+// Three independent jobs in one launch (block ranges): (a) transform + snap every vertex once, (b) planes := EMPTY and
+// link bitmaps := 0, (c) tile classification, one warp per tile.
+__global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRobot rb,
+                                                   const __grid_constant__ EhbParams p, int vchunks, int clearBlocks)
 {
     ehb_pdl_enter();
-    if ((int)blockIdx.x < clearBlocks) {
-        // (a) planes := EMPTY (only the allocated part of the pool); touch bits := 0; raw bounding boxes := "none"
+    const int vertexBlocks = vchunks * p.items;
+    if ((int)blockIdx.x < vertexBlocks) {
+        const int item = blockIdx.x / vchunks;
+        const int g = (blockIdx.x - item * vchunks) * blockDim.x + threadIdx.x;
+        if (g >= p.Vtot) return;
+        const int lk = ehb_find_link(rb.voff, rb.L, g);
+        float m[16], c[4];
+        ehb_load_mvp(p.mvp + ((size_t)item * p.L + lk) * 16, m);
+        ehb_xform(__ldg(rb.link[lk].verts + (g - rb.voff[lk])), m, c);
+        int2 sn = make_int2(INT_MIN, 0);
+        if (c[3] >= fabsf(c[2])) {   // only such vertices can belong to a drawable triangle
+            const float r = 1.0f / c[3];
+            sn = make_int2(ehb_rni_sat(c[0] * r * (float)(p.W * 8)), ehb_rni_sat(c[1] * r * (float)(p.H * 8)));
+        }
+        p.vclip[(size_t)item * p.Vtot + g] = make_float4(c[0], c[1], c[2], c[3]);
+        p.vsnap[(size_t)item * p.Vtot + g] = sn;
+        return;
+    }
+    const int cb = (int)blockIdx.x - vertexBlocks;
+    if (cb < clearBlocks) {
         const unsigned long long total = min(p.ctr->planeCursor, p.poolCap);
         const unsigned long long n2 = total >> 1;
         ulonglong2* p2 = reinterpret_cast<ulonglong2*>(p.pool);
-        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2;
+        for (unsigned long long i = (unsigned long long)cb * blockDim.x + threadIdx.x; i < n2;
              i += (unsigned long long)clearBlocks * blockDim.x)
             p2[i] = make_ulonglong2(EHB_EMPTY, EHB_EMPTY);
-        if ((total & 1ull) && blockIdx.x == 0 && threadIdx.x == 0) p.pool[total - 1] = EHB_EMPTY;
+        if ((total & 1ull) && cb == 0 && threadIdx.x == 0) p.pool[total - 1] = EHB_EMPTY;
         if (p.touch)
-            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.items * p.ntiles; i += clearBlocks * blockDim.x) p.touch[i] = 0u;
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.items * p.Lp * 4; i += clearBlocks * blockDim.x)
-            p.bbraw[i] = (i & 2) ? EHB_RAW_MAX : EHB_RAW_MIN;
+            for (int i = cb * blockDim.x + threadIdx.x; i < p.items * p.ntiles; i += clearBlocks * blockDim.x) p.touch[i] = 0u;
         return;
     }
-    // (b) tile classification: one warp per tile
-    const int wid = (((int)blockIdx.x - clearBlocks) * blockDim.x + threadIdx.x) >> 5;
+    const int wid = ((cb - clearBlocks) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wid >= p.items * p.ntiles) return;
     const int item = wid / p.ntiles, tile = wid - item * p.ntiles;
@@ -721,6 +745,8 @@ __global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(con
 
 #ifdef EHB_TIMING
     long long t_last = clock64();
+    unsigned long long t_cta0, n_done = 0, worst = 0, worstLinks = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_cta0));
 #endif
     for (;;) {
         EHB_TICK(9);
@@ -1027,8 +1053,16 @@ __global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(con
         __syncthreads();
         EHB_TICK(6);
 #ifdef EHB_TIMING
+        if (tid == 0 && p.dbgbuf) {
+            unsigned long long t_now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+            unsigned long long* d = p.dbgbuf + (size_t)blockIdx.x * 5;
+            d[0] = t_cta0; d[1] = t_now; d[2] = n_done + 1; d[3] = worst; d[4] = worstLinks;
+        }
         if (tid == 0) {
             const unsigned long long dt = (unsigned long long)(clock64() - t_tile0);
+            n_done++;
+            if (dt > worst) { worst = dt; worstLinks = (unsigned long long)nP | ((unsigned long long)sm.segStart[nP] << 8); }
             atomicMax(&p.ctr->dbg[13], dt);
             if (dt > 50000ull) atomicAdd(&p.ctr->dbg[14], 1ull);
             if (dt > 100000ull) atomicAdd(&p.ctr->dbg[15], 1ull);

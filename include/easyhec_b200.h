@@ -74,12 +74,15 @@ EHB_API int ehb_ctx_set_pool_budget(ehb_ctx_t ctx, double bytes);
 EHB_API int ehb_ctx_grow_scratch(ehb_ctx_t ctx);
 /* Per-kernel timing for benchmarks: while enabled every pass records CUDA events around its four kernels on the
  * caller's stream (and runs it as a single pipeline).  ehb_ctx_kernel_times synchronises, returns the summed
- * milliseconds of the four stages {vertex, plan, raster (+ raster_big), tiles} (ms4[4]) over the passes recorded since
+ * milliseconds of the four stages {table, front, raster (+ raster_big), tiles} (ms4[4]) over the passes recorded since
  * the last query, and their number. */
 EHB_API int ehb_ctx_profile(ehb_ctx_t ctx, int enable);
 EHB_API int ehb_ctx_kernel_times(ehb_ctx_t ctx, double* ms4, long long* n_passes);
 /* Developer aid: 16 raw 64-bit counters that builds with -DEHB_TIMING fill (cycles per phase of the tile kernel). */
 EHB_API int ehb_ctx_debug_counters(ehb_ctx_t ctx, unsigned long long* out16, int reset);
+/* Developer aid (EHB_TIMING builds): first call allocates a per-CTA timeline buffer for the tile kernel, later calls
+ * copy up to n_words 64-bit words of it out ({start ns, end ns, tiles, longest tile cycles, links | pairs << 8} per CTA). */
+EHB_API int ehb_ctx_debug_buffer(ehb_ctx_t ctx, unsigned long long* out, int n_words);
 /* Synchronises the device, returns and clears the sticky flags, reports triangles skipped for clipping. */
 EHB_API int ehb_ctx_status(ehb_ctx_t ctx, unsigned* flags, long long* n_need_clip);
 
