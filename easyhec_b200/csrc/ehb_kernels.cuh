@@ -419,9 +419,11 @@ __device__ __forceinline__ void ehb_rec_store_soa(uint32_t* b, int t, const EhbR
 
 // Primitive assembly of one triangle from the pre-transformed vertices -> record.  Same tests, in the same order,
 // as ehb_tri_setup (the oracle's eho_rasterize).  Returns the number of rows of its clipped bbox (0: nothing to draw).
-__device__ __forceinline__ int ehb_make_record(const EhbRobot& rb, const EhbParams& p, int item, int g, EhbRec& rc)
+__device__ __forceinline__ int ehb_make_record(const EhbRobot& rb, const EhbParams& p, int item, int g, EhbRec& rc,
+                                               int& link_out)
 {
     const int l = ehb_find_link(rb.foff, rb.L, g);
+    link_out = l;
     const int f = g - rb.foff[l];
     const EhbLink& lk = rb.link[l];
     const int4 id = __ldg(lk.faces + f);
@@ -553,9 +555,10 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32) ehb_k_raster(const __grid_con
     int rows = 0, wide = 0;
     if (g < p.Ftot) {
         EhbRec rc;
-        rows = ehb_make_record(rb, p, item, g, rc);
+        int link;
+        rows = ehb_make_record(rb, p, item, g, rc, link);
         if (rows > 0 && p.touch) {   // tell k_tiles which (tile, link) windows this triangle reaches into
-            const uint32_t bit = 1u << ehb_find_link(rb.foff, rb.L, g);
+            const uint32_t bit = 1u << link;
             const int txlo = max(0, (rc.x0 - p.hhi) >> 5), txhi = min(p.ntx - 1, (rc.x0 + rc.w - 1 + p.hlo) >> 5);
             const int tylo = max(0, (rc.y0 - p.hhi) >> 5), tyhi = min(p.nty - 1, (rc.y0 + rc.h - 1 + p.hlo) >> 5);
             for (int ty = tylo; ty <= tyhi; ty++)
@@ -671,6 +674,7 @@ __global__ void __launch_bounds__(256) ehb_k_union_out(const __grid_constant__ E
 #define EHB_TTHREADS 128
 #endif
 #define EHB_TWARPS (EHB_TTHREADS / 32)
+static_assert(EHB_TTHREADS == 128, "k_tiles maps 32 rows x 4 eight-pixel segments onto its 128 threads");
 #ifndef EHB_PAIRCAP
 #define EHB_PAIRCAP 768      // pair-list entries kept in shared memory; the rest spills to a per-CTA global area
 #endif
@@ -740,8 +744,15 @@ __global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(con
     const bool ref8vec = p.ref_u8 != nullptr && (p.W & 3) == 0 && (((uintptr_t)p.ref_u8) & 3) == 0;
     const unsigned nHeavy = p.ctr->nTiles, nTiles = nHeavy + p.ctr->nLight;
     const unsigned listEnd = (unsigned)(p.items * p.ntiles) - 1u;
-    unsigned nextWork = 0;
-    if (tid == 0) nextWork = atomicAdd(&p.ctr->workCursor, 1u);
+    // thread 0 runs the tile queue two entries ahead: the atomic ticket and the tile id of the NEXT tile are fetched
+    // while the current one is processed, so no tile starts with two dependent L2 round trips
+    auto list_at = [&](unsigned w) -> uint32_t { return p.tileList[w < nHeavy ? w : listEnd - (w - nHeavy)]; };
+    unsigned nextWork = 0, nextNext = 0;
+    uint32_t nextWid = 0;
+    if (tid == 0) {
+        nextWork = atomicAdd(&p.ctr->workCursor, 1u);
+        if (nextWork < nTiles) { nextWid = list_at(nextWork); nextNext = atomicAdd(&p.ctr->workCursor, 1u); }
+    }
 
 #ifdef EHB_TIMING
     long long t_last = clock64();
@@ -754,12 +765,15 @@ __global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(con
         const long long t_tile0 = clock64();
 #endif
         if (tid == 0) {
-            sm.work = nextWork < nTiles ? (int)nextWork : -1;
-            if (nextWork < nTiles) nextWork = atomicAdd(&p.ctr->workCursor, 1u);   // in flight while this tile is processed
+            sm.work = nextWork < nTiles ? (int)nextWid : -1;
+            if (nextWork < nTiles) {
+                nextWork = nextNext;
+                if (nextWork < nTiles) { nextWid = list_at(nextWork); nextNext = atomicAdd(&p.ctr->workCursor, 1u); }
+            }
         }
         __syncthreads();
         if (sm.work < 0) break;
-        const uint32_t wid = p.tileList[(unsigned)sm.work < nHeavy ? (unsigned)sm.work : listEnd - ((unsigned)sm.work - nHeavy)];
+        const uint32_t wid = (uint32_t)sm.work;
         const int item = wid / p.ntiles, tile = wid - item * p.ntiles;
         const int tx = tile % p.ntx, ty = tile / p.ntx;
         const int x0 = tx * EHB_T, y0 = ty * EHB_T;
@@ -801,7 +815,7 @@ __global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(con
             }
         }
         if (needAA)
-            for (int i = tid; i < EHB_NP; i += EHB_TTHREADS) sm.sum[i] = 0.f;
+            for (int i = tid; i < (EHB_NP + 3) / 4; i += EHB_TTHREADS) reinterpret_cast<float4*>(sm.sum)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.mode == EHB_MODE_AA_BWD)   // g = dL/dmask comes from the caller
             for (int i = tid; i < (EHB_T + 1) * (EHB_T + 1); i += EHB_TTHREADS) {
                 const int qy = i / (EHB_T + 1), qx = i - qy * (EHB_T + 1);
@@ -820,20 +834,44 @@ __global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(con
             const int l = sm.links[k];
             const EhbLink& lk = rb.link[l];
             const float* m = sm.mvp + 16 * l;
-            // ================================ window of link k's plane -> shared memory =========================
+            // ================ window of link k's plane -> shared memory, row coverage masks by ballot ===============
             {
                 const EhbPlane pl = sm.pl[k];
-                int any = 0;
-                for (int i = tid; i < EHB_NP; i += EHB_TTHREADS) {
-                    const int ly = i / EHB_RS, lx = i - ly * EHB_RS;
-                    const int px = rx0 + lx - pl.x0, py = ry0 + ly - pl.y0;
-                    unsigned long long v = EHB_EMPTY;
-                    if (px >= 0 && py >= 0 && px < pl.w && py < pl.h && rx0 + lx <= rx1 && ry0 + ly <= ry1)
-                        v = p.pool[pl.off + (long long)py * pl.w + px];
-                    sm.plane[i] = v;
-                    any |= v != EHB_EMPTY;
+                unsigned long long anyRow = 0ull;
+                // all loads of this warp's rows are issued before the first ballot consumes one (9 rows x 2 words in flight)
+                constexpr int NR = (EHB_RS + EHB_TWARPS - 1) / EHB_TWARPS;
+                unsigned long long v0[NR], v1[NR];
+#pragma unroll
+                for (int j = 0; j < NR; j++) {
+                    const int r = warp + j * EHB_TWARPS;
+                    v0[j] = EHB_EMPTY; v1[j] = EHB_EMPTY;
+                    if (r < EHB_RS) {
+                        const int py = ry0 + r - pl.y0;
+                        const bool rowOk = py >= 0 && py < pl.h && ry0 + r <= ry1;
+                        const unsigned long long* row = p.pool + pl.off + (long long)py * pl.w - pl.x0 + rx0;
+                        const int px = rx0 + lane - pl.x0;
+                        if (rowOk && px >= 0 && px < pl.w && rx0 + lane <= rx1) v0[j] = row[lane];
+                        if (lane < EHB_RS - 32) {
+                            const int px1 = px + 32;
+                            if (rowOk && px1 >= 0 && px1 < pl.w && rx0 + 32 + lane <= rx1) v1[j] = row[32 + lane];
+                        }
+                    }
                 }
-                if (!__syncthreads_or(any)) {   // the bbox touches the window but no sample does
+#pragma unroll
+                for (int j = 0; j < NR; j++) {
+                    const int r = warp + j * EHB_TWARPS;
+                    if (r < EHB_RS) {
+                        sm.plane[r * EHB_RS + lane] = v0[j];
+                        if (lane < EHB_RS - 32) sm.plane[r * EHB_RS + 32 + lane] = v1[j];
+                        const unsigned b0 = __ballot_sync(0xffffffffu, v0[j] != EHB_EMPTY);
+                        const unsigned b1 = __ballot_sync(0xffffffffu, v1[j] != EHB_EMPTY);
+                        const unsigned long long cm = (unsigned long long)b0 | ((unsigned long long)b1 << 32);
+                        if (lane == 0) sm.cov[r] = cm;
+                        anyRow |= cm;
+                    }
+                }
+                if (tid == 0) sm.cov[EHB_RS] = 0ull;
+                if (!__syncthreads_or(anyRow != 0ull)) {   // the link reaches into the window but covers no sample of it
                     if (tid == 0) sm.segStart[k + 1] = sm.segStart[k];
                     __syncthreads();
                     EHB_TICK(1);
@@ -841,14 +879,6 @@ __global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(con
                 }
             }
             EHB_TICK(1);
-            // ================================ row bitmasks and silhouette pairs =================================
-            for (int r = warp; r < EHB_RS; r += EHB_TWARPS) {
-                const unsigned b0 = __ballot_sync(0xffffffffu, sm.plane[r * EHB_RS + lane] != EHB_EMPTY);
-                const unsigned b1 = __ballot_sync(0xffffffffu, lane < EHB_RS - 32 && sm.plane[r * EHB_RS + 32 + lane] != EHB_EMPTY);
-                if (lane == 0) sm.cov[r] = (unsigned long long)b0 | ((unsigned long long)b1 << 32);
-            }
-            if (tid == 0) sm.cov[EHB_RS] = 0ull;
-            __syncthreads();
             const int seg0 = sm.segStart[k];
             if (warp == 0) {
                 // columns whose pixel is inside the image, and for which the right neighbour is too
@@ -938,26 +968,45 @@ __global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(con
                 __syncthreads();
                 EHB_TICK(3);
                 // ============================ gather: sum += colour + pair contributions ========================
-                // pixel (qx, qy) of the out region; column 32 (the extra one) is handled by the last pass
-                for (int q = tid; q < ow * EHB_T + (oext ? ow : 0); q += EHB_TTHREADS) {
-                    int qx, qy;
-                    if (q < ow * EHB_T) { qy = q >> 5; qx = q & 31; } else { qy = q - ow * EHB_T; qx = EHB_T; }
-                    const int lx = hlo + qx, ly = hlo + qy;
-                    const unsigned long long cm = sm.cov[ly];
-                    const bool c = (cm >> lx) & 1ull;
-                    const bool h0 = (sm.hx[ly] >> lx) & 1ull, v0 = (sm.vy[ly] >> lx) & 1ull;
-                    const bool h1 = (sm.hx[ly] >> (lx - 1)) & 1ull, v1 = (sm.vy[ly - 1] >> lx) & 1ull;
-                    if (!(c | h0 | v0 | h1 | v1)) continue;
-                    const int idx = ly * EHB_RS + lx;
-                    const float cf = c ? 1.f : 0.f;
-                    float o = cf, a;
-                    // colour, pair(p,p+x), pair(p,p+y), pair(p-x,p), pair(p-y,p); the receiver is p0 when alpha > 0
-                    if (h0) { a = sm.alpha[0][idx]; if (a > 0.f) o += a * ((c ? 0.f : 1.f) - cf); }
-                    if (v0) { a = sm.alpha[1][idx]; if (a > 0.f) o += a * ((c ? 0.f : 1.f) - cf); }
-                    if (h1) { a = sm.alpha[0][idx - 1]; if (!(a > 0.f) && a != 0.f) o += a * (cf - (c ? 0.f : 1.f)); }
-                    if (v1) { a = sm.alpha[1][idx - EHB_RS]; if (!(a > 0.f) && a != 0.f) o += a * (cf - (c ? 0.f : 1.f)); }
-                    sm.sum[idx] = sm.sum[idx] + o;   // links are added in link order (rb_solver.py:68); absent links add 0
+                // each thread owns 8 consecutive pixels of one row (32 rows x 4 segments); a second short pass takes the
+                // extra row / column that exist when the backward follows.  Masks are read once per thread.
+#ifndef EHB_SKIP_GATHER
+                for (int pass = 0; pass < (oext ? 2 : 1); pass++) {
+                    int qy, qx0, n;
+                    if (pass == 0) { qy = tid >> 2; qx0 = (tid & 3) * 8; n = 8; }
+                    else if (tid < 4) { qy = EHB_T; qx0 = tid * 8; n = 8; }            // row 32
+                    else if (tid < 4 + EHB_T + 1) { qy = tid - 4; qx0 = EHB_T; n = 1; }   // column 32 (incl. the corner)
+                    else break;
+                    if (qy >= EHB_T + oext) continue;
+                    const int ly = hlo + qy, lx0 = hlo + qx0;
+                    const unsigned long long cm = sm.cov[ly], hr = sm.hx[ly], vr = sm.vy[ly], vd = sm.vy[ly - 1];
+                    // the segment's 8 flag bits of each mask, extracted once
+                    const uint32_t nm = (1u << n) - 1u;
+                    const uint32_t c8 = (uint32_t)(cm >> lx0) & nm, h08 = (uint32_t)(hr >> lx0) & nm, v08 = (uint32_t)(vr >> lx0) & nm;
+                    const uint32_t h18 = (uint32_t)(hr >> (lx0 - 1)) & nm, v18 = (uint32_t)(vd >> lx0) & nm;
+                    const uint32_t pairBits = h08 | v08 | h18 | v18;
+                    uint32_t todo = c8 | pairBits;
+                    float* srow = sm.sum + ly * EHB_RS + lx0;
+                    while (todo) {
+                        const int i = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const bool c = (c8 >> i) & 1u;
+                        const float cf = c ? 1.f : 0.f;
+                        float o = cf;
+                        if ((pairBits >> i) & 1u) {
+                            const int idx = ly * EHB_RS + lx0 + i;
+                            const float nb = c ? 0.f : 1.f;   // a pair's other pixel has the opposite coverage
+                            float a;
+                            // colour, pair(p,p+x), pair(p,p+y), pair(p-x,p), pair(p-y,p); the receiver is p0 when alpha > 0
+                            if ((h08 >> i) & 1u) { a = sm.alpha[0][idx]; if (a > 0.f) o += a * (nb - cf); }
+                            if ((v08 >> i) & 1u) { a = sm.alpha[1][idx]; if (a > 0.f) o += a * (nb - cf); }
+                            if ((h18 >> i) & 1u) { a = sm.alpha[0][idx - 1]; if (!(a > 0.f) && a != 0.f) o += a * (cf - nb); }
+                            if ((v18 >> i) & 1u) { a = sm.alpha[1][idx - EHB_RS]; if (!(a > 0.f) && a != 0.f) o += a * (cf - nb); }
+                        }
+                        srow[i] = srow[i] + o;   // links are added in link order (rb_solver.py:68); absent links add 0
+                    }
                 }
+#endif
             }
             __syncthreads();
             EHB_TICK(4);
@@ -967,25 +1016,48 @@ __global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(con
             // S = min(sum, 1); loss; g = dL/dsum kept in sm.sum for the backward
             double lacc = 0.0;
             if (haveRef) { ehb_cp_async_wait_all(); __syncthreads(); }
-            for (int q = tid; q < ow * EHB_T + (oext ? ow : 0); q += EHB_TTHREADS) {
-                int qx, qy;
-                if (q < ow * EHB_T) { qy = q >> 5; qx = q & 31; } else { qy = q - ow * EHB_T; qx = EHB_T; }
-                const int px = x0 + qx, py = y0 + qy;
-                if (px >= W || py >= H) continue;
-                const int idx = (py - ry0) * EHB_RS + (px - rx0);
-                const float s = sm.sum[idx];
-                const float S = (p.clamp && s > 1.f) ? 1.f : s;
-                const size_t o = ibase + (size_t)(H - 1 - py) * W + px;
-                const bool interior = qx < EHB_T && qy < EHB_T;
-                if (interior && p.masks) p.masks[o] = S;
-                if (haveRef) {
-                    float rf;
-                    if (p.ref) rf = __uint_as_float(sm.refw[qy * (EHB_T + 4) + qx]);
-                    else if (ref8vec) rf = ((sm.refw[qy * (EHB_T + 4) + (qx >> 2)] >> (8 * (qx & 3))) & 255u) ? 1.f : 0.f;
-                    else rf = __ldg(p.ref_u8 + o) ? 1.f : 0.f;
-                    const float diff = S - rf;
-                    if (interior) lacc += (double)(diff * diff);
-                    sm.sum[idx] = (!p.clamp || s <= 1.f) ? (2.f * diff) * p.invB : 0.f;
+            // same thread -> pixel mapping as the gather: 8 consecutive pixels of one row per thread, then the extra
+            // row / column; the 8 mask values of a segment leave as two float4 stores
+            const bool vecOut = p.masks != nullptr && (W & 3) == 0 && (((uintptr_t)p.masks) & 15) == 0;
+            for (int pass = 0; pass < (oext ? 2 : 1); pass++) {
+                int qy, qx0, n;
+                if (pass == 0) { qy = tid >> 2; qx0 = (tid & 3) * 8; n = 8; }
+                else if (tid < 4) { qy = EHB_T; qx0 = tid * 8; n = 8; }
+                else if (tid < 4 + EHB_T + 1) { qy = tid - 4; qx0 = EHB_T; n = 1; }
+                else break;
+                const int py = y0 + qy;
+                if (qy >= EHB_T + oext || py >= H) continue;
+                const size_t orow = ibase + (size_t)(H - 1 - py) * W;
+                float Sv[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    Sv[i] = 0.f;
+                    const int qx = qx0 + i, px = x0 + qx;
+                    if (i >= n || px >= W) continue;
+                    const int idx = (py - ry0) * EHB_RS + (px - rx0);
+                    const float s = sm.sum[idx];
+                    const float S = (p.clamp && s > 1.f) ? 1.f : s;
+                    Sv[i] = S;
+                    const bool interior = qx < EHB_T && qy < EHB_T;
+                    if (haveRef) {
+                        float rf;
+                        if (p.ref) rf = __uint_as_float(sm.refw[qy * (EHB_T + 4) + qx]);
+                        else if (ref8vec) rf = ((sm.refw[qy * (EHB_T + 4) + (qx >> 2)] >> (8 * (qx & 3))) & 255u) ? 1.f : 0.f;
+                        else rf = __ldg(p.ref_u8 + orow + px) ? 1.f : 0.f;
+                        const float diff = S - rf;
+                        if (interior) lacc += (double)(diff * diff);
+                        sm.sum[idx] = (!p.clamp || s <= 1.f) ? (2.f * diff) * p.invB : 0.f;
+                    }
+                }
+                if (p.masks && qy < EHB_T && qx0 < EHB_T) {
+                    if (vecOut && x0 + qx0 + 7 < W) {
+                        float4* dst = reinterpret_cast<float4*>(p.masks + orow + x0 + qx0);
+                        dst[0] = make_float4(Sv[0], Sv[1], Sv[2], Sv[3]);
+                        dst[1] = make_float4(Sv[4], Sv[5], Sv[6], Sv[7]);
+                    } else {
+                        for (int i = 0; i < n; i++)
+                            if (x0 + qx0 + i < W) p.masks[orow + x0 + qx0 + i] = Sv[i];
+                    }
                 }
             }
             if (haveRef && p.loss) {
