@@ -6,12 +6,15 @@
 // fallback: every compute entry point enqueues CUDA kernels on the caller's stream or fails.
 #include "../../include/easyhec_b200.h"
 #include "ehb_kernels.cuh"
+#include "ehb_tiles.cuh"
 #include "ehb_pose.cuh"
 
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -78,12 +81,16 @@ struct Scratch {
     DevBuf<uint32_t> tileList, emptyList, touch;
     DevBuf<EhbRec> bigRec;
     DevBuf<EhbUnit> units;
-    DevBuf<EhbPairEnt> spill;         // per k_tiles CTA: overflow of the shared-memory silhouette-pair list
+    DevBuf<EhbJob> jobs;              // image-space stage: (tile, link) windows ...
+    DevBuf<uint32_t> tileJob0;
+    DevBuf<EhbPair> pairs;            // ... their silhouette pairs ...
+    DevBuf<float> maskBuf, gBuf;      // ... per-job antialiased masks and per-tile gradient windows
     EhbCounters* ctr = nullptr;
     void release()
     {
         vclip.release(); vsnap.release(); plane.release(); pool.release(); tileList.release(); emptyList.release();
-        touch.release(); bigRec.release(); units.release(); spill.release();
+        touch.release(); bigRec.release(); units.release();
+        jobs.release(); tileJob0.release(); pairs.release(); maskBuf.release(); gBuf.release();
     }
 };
 
@@ -91,6 +98,7 @@ struct Ctx {
     int device = 0;
     int nSM = 148;
     int occ = 4;                      // resident k_tiles CTAs per SM
+    int occRaster = 4;                // resident k_raster CTAs per SM (persistent warps)
     int rule = 0;
     int nPipes = 2;
     std::vector<Mesh> meshes;
@@ -239,8 +247,18 @@ __global__ void ehb_k_variance_finish(const unsigned long long* __restrict__ num
     if (q < Q) score[q] = C > 1 ? (double)num[q] / ((double)C * (double)(C - 1)) : 0.0;
 }
 
-size_t tiles_smem() { return sizeof(EhbSmem); }
-constexpr int SPILL_PER_LINK = 2 * (EHB_RS - 1) * (EHB_RS - 1);   // most silhouette pairs one link can have in a tile
+
+// Developer knob: integer from the environment, read once per name (launch-shape experiments without a rebuild).
+int tune_int(const char* name, int dflt)
+{
+    static std::map<std::string, int> cache;
+    auto it = cache.find(name);
+    if (it != cache.end()) return it->second;
+    const char* v = getenv(name);
+    const int r = (v && *v) ? atoi(v) : dflt;
+    cache[name] = r;
+    return r;
+}
 constexpr int BIG_CAP = 1 << 17;     // deferred triangles per pass (16 MB of records)
 constexpr int UNIT_CAP = 1 << 19;
 
@@ -294,7 +312,20 @@ int ensure_scratch(Ctx* c, Scratch& sc, int items, int L, int Lp, int H, int W, 
     if ((r = sc.vclip.ensure((size_t)items * std::max(Vtot, 1), capturing))) return r;
     if ((r = sc.vsnap.ensure((size_t)items * std::max(Vtot, 1), capturing))) return r;
     const int ntiles = ((W + EHB_T - 1) / EHB_T) * ((H + EHB_T - 1) / EHB_T);
-    if ((r = sc.spill.ensure((size_t)c->nSM * c->occ * SPILL_PER_LINK * L, capturing))) return r;
+    if (Lp == L) {   // image-space stage (not needed by the packed-robot mode)
+        // Jobs: at most one per (tile, link).  That worst case is reserved while its masks stay under 1 GB; beyond it the
+        // list holds poolFactor jobs per tile and grows on the overflow flag, like the plane pool.
+        const double worstJobs = (double)items * ntiles * L;
+        const double perTile = worstJobs * EHB_MSZ * 4.0 <= 1e9 ? (double)L : std::min((double)L, std::max(2.0, c->poolFactor));
+        const size_t jobCap = std::max<size_t>(4096, (size_t)((double)items * ntiles * perTile));
+        const size_t pairCap = (size_t)((double)jobCap * 32.0 * std::max(1.0, c->poolFactor / 2.0));
+        if (jobCap > 0x7FFFFFFFull || pairCap > 0x7FFFFFFFull) return fail(EHB_E_ARG, "too many tiles for one launch");
+        if ((r = sc.jobs.ensure(jobCap, capturing))) return r;
+        if ((r = sc.tileJob0.ensure((size_t)items * ntiles, capturing))) return r;
+        if ((r = sc.pairs.ensure(pairCap, capturing))) return r;
+        if ((r = sc.maskBuf.ensure(jobCap * EHB_MSZ, capturing))) return r;
+        if ((r = sc.gBuf.ensure((size_t)items * ntiles * EHB_MSZ, capturing))) return r;
+    }
     if ((r = sc.plane.ensure((size_t)items * Lp, capturing))) return r;
     if ((r = sc.tileList.ensure((size_t)items * ntiles, capturing))) return r;
     if ((r = sc.touch.ensure((size_t)items * ntiles, capturing))) return r;
@@ -344,7 +375,8 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
     p.tileList = sc.tileList.p; p.emptyList = sc.emptyList.p; p.touch = unionMode ? nullptr : sc.touch.p; p.bigRec = sc.bigRec.p; p.units = sc.units.p; p.bigCap = BIG_CAP; p.unitCap = UNIT_CAP; p.ctr = sc.ctr;
     p.ref = io.ref; p.ref_u8 = io.ref_u8; p.masks = io.masks; p.loss = io.loss; p.gmvp = io.gmvp; p.gpos = io.gpos;
     p.dy = io.dy; p.out_u8 = io.out_u8;
-    p.pairSpill = sc.spill.p; p.spillCap = SPILL_PER_LINK * L;
+    p.jobs = sc.jobs.p; p.tileJob0 = sc.tileJob0.p; p.pairs = sc.pairs.p; p.maskBuf = sc.maskBuf.p; p.gBuf = sc.gBuf.p;
+    p.jobCap = (int)sc.jobs.n; p.pairCap = (int)sc.pairs.n;
     p.dbgbuf = c->dbgbuf;
 
     cudaEvent_t* ev = nullptr;
@@ -357,6 +389,14 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
         ev = &c->evPool[c->evUsed];
         c->evUsed += 5;
     }
+    const int chunks = std::max(1, (p.Ftot + 31) / 32);   // 32-triangle batches per item, drawn by persistent warps
+    const int streamBlocks = (unionMode || mode == EHB_MODE_AA_BWD) ? 0 : c->nSM * tune_int("EHB_STREAM_MULT", 2);
+    const long long tickets = ((long long)chunks * items + EHB_RBATCH - 1) / EHB_RBATCH;
+    long long rasterBlocks = (tickets + EHB_RWARPS - 1) / EHB_RWARPS;
+#ifdef EHB_RPERSIST
+    rasterBlocks = std::min<long long>(rasterBlocks, (long long)c->nSM * tune_int("EHB_RASTER_OCC", c->occRaster));
+#endif
+    p.rasterStart = (int)(rasterBlocks * EHB_RWARPS * EHB_RBATCH);
     if (ev) cudaEventRecord(ev[0], st);
     CU(launch(ehb_k_table, dim3((unsigned)((items * p.Lp + 7) / 8)), dim3(256), 0, st, false, rb, p));
     if (ev) cudaEventRecord(ev[1], st);
@@ -366,16 +406,19 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
     CU(launch(ehb_k_front, dim3((unsigned)(vchunks * items + clearBlocks + (tileWarps * 32 + 255) / 256)), dim3(256), 0, st, true, rb, p,
               vchunks, clearBlocks));
     if (ev) cudaEventRecord(ev[2], st);
-    const int chunks = std::max(1, (p.Ftot + EHB_RWARPS * 32 - 1) / (EHB_RWARPS * 32));
-    const int streamBlocks = (unionMode || mode == EHB_MODE_AA_BWD) ? 0 : c->nSM;
-    CU(launch(ehb_k_raster, dim3((unsigned)(streamBlocks + chunks * items)), dim3(EHB_RWARPS * 32), 0, st, true, rb, p, streamBlocks, chunks));
-    CU(launch(ehb_k_raster_big, dim3(c->nSM * 4), dim3(256), 0, st, true, p));
+    CU(launch(ehb_k_raster, dim3((unsigned)(streamBlocks + rasterBlocks)), dim3(EHB_RWARPS * 32), 0, st, true, rb, p, streamBlocks, chunks));
+    const int jobBlocks = unionMode ? 0 : 16;
+    CU(launch(ehb_k_raster_big, dim3(c->nSM * 4 + jobBlocks), dim3(256), 0, st, true, p, jobBlocks));
     if (ev) cudaEventRecord(ev[3], st);
     if (unionMode) {
         const int nq = ((W + 3) / 4) * H;
         CU(launch(ehb_k_union_out, dim3((unsigned)std::min((nq + 255) / 256, 4 * c->nSM), (unsigned)items), dim3(256), 0, st, true, p));
     } else {
-        CU(launch(ehb_k_tiles, dim3(c->nSM * c->occ), dim3(EHB_TTHREADS), tiles_smem(), st, true, rb, p));
+        const bool doBwd = (mode == EHB_MODE_FUSED && io.do_bwd) || mode == EHB_MODE_AA_BWD;
+        CU(launch(ehb_k_windows, dim3(c->nSM * tune_int("EHB_WIN_OCC", 7)), dim3(EHB_WWARPS * 32), 0, st, true, rb, p));
+        CU(launch(ehb_k_compose, dim3(c->nSM * 16), dim3(EHB_CTHREADS), 0, st, true, p));
+        if (doBwd) CU(launch(ehb_k_pairgrad, dim3(c->nSM * 2), dim3(256), 0, st, true, rb, p));
+        c->launches += doBwd ? 2 : 1;
     }
     if (ev) cudaEventRecord(ev[4], st);
     c->launches += 5;
@@ -454,9 +497,8 @@ int ehb_ctx_create(int device, ehb_ctx_t* out)
         CU(cudaStreamCreateWithFlags(&c->pipeStream[k], cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&c->evJoin[k], cudaEventDisableTiming));
     }
-    CU(cudaFuncSetAttribute(ehb_k_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiles_smem()));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ, ehb_k_tiles, EHB_TTHREADS, tiles_smem()));
-    c->occ = std::max(1, c->occ);
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occRaster, ehb_k_raster, EHB_RWARPS * 32, 0));
+    c->occRaster = std::max(1, c->occRaster);
     *out = c;
     return EHB_OK;
 }

@@ -151,7 +151,15 @@ __device__ __forceinline__ int ehb_max_idx3(float n0, float n1, float n2, float 
 
 // Blend weight of the pair whose covered pixel shows triangle t (side 0: p0 is the covered one, 1: p1).
 // Returns alpha (0 = no silhouette edge crosses the segment between the two centres); *di_out = edge index.
-__device__ __noinline__ float ehb_aa_pair(const EhbLink& lk, const float* __restrict__ m, int t, int side, int px,
+// `vc` = clip-space positions of the link's vertices for this item, as written by k_front (same ehb_xform, same matrix:
+// bit-identical to transforming the vertex again).
+__device__ __forceinline__ void ehb_clip_of(const float4* __restrict__ vc, int v, float* c)
+{
+    const float4 q = vc[v];
+    c[0] = q.x; c[1] = q.y; c[2] = q.z; c[3] = q.w;
+}
+
+__device__ __noinline__ float ehb_aa_pair(const EhbLink& lk, const float4* __restrict__ vc, int t, int side, int px,
                                           int py, int d, int H, int W, int* di_out)
 {
     const float xh = 0.5f * (float)W, yh = 0.5f * (float)H;
@@ -159,12 +167,12 @@ __device__ __noinline__ float ehb_aa_pair(const EhbLink& lk, const float* __rest
     const int4 vi = __ldg(lk.faces + t);
     const int4 oi = __ldg(lk.opp + t);
     float p0[4], p1[4], p2[4], q0[4], q1[4], q2[4];
-    ehb_xform(__ldg(lk.verts + vi.x), m, p0);
-    ehb_xform(__ldg(lk.verts + vi.y), m, p1);
-    ehb_xform(__ldg(lk.verts + vi.z), m, p2);
-    ehb_xform(__ldg(lk.verts + (oi.x < 0 ? vi.x : oi.x)), m, q0);
-    ehb_xform(__ldg(lk.verts + (oi.y < 0 ? vi.y : oi.y)), m, q1);
-    ehb_xform(__ldg(lk.verts + (oi.z < 0 ? vi.z : oi.z)), m, q2);
+    ehb_clip_of(vc, vi.x, p0);
+    ehb_clip_of(vc, vi.y, p1);
+    ehb_clip_of(vc, vi.z, p2);
+    ehb_clip_of(vc, oi.x < 0 ? vi.x : oi.x, q0);
+    ehb_clip_of(vc, oi.y < 0 ? vi.y : oi.y, q1);
+    ehb_clip_of(vc, oi.z < 0 ? vi.z : oi.z, q2);
     const float w0 = 1.f / p0[3], w1 = 1.f / p1[3], w2 = 1.f / p2[3];
     const float ow0 = 1.f / q0[3], ow1 = 1.f / q1[3], ow2 = 1.f / q2[3];
     const float fx = (float)px + .5f - xh, fy = (float)py + .5f - yh;
@@ -206,7 +214,7 @@ __device__ __noinline__ float ehb_aa_pair(const EhbLink& lk, const float* __rest
 
 // Gradient of one pair's blend w.r.t. the clip positions (x, y, w) of the two vertices of its active edge.
 // dd = dL/d(out of receiving pixel) * (c1 - c0).  Outputs the vertex indices and g1[3], g2[3] = (gx, gy, gw).
-__device__ __noinline__ void ehb_aa_pair_grad(const EhbLink& lk, const float* __restrict__ m, int t, int side, int di,
+__device__ __noinline__ void ehb_aa_pair_grad(const EhbLink& lk, const float4* __restrict__ vc, int t, int side, int di,
                                               float al, float dd, int px, int py, int d, int H, int W, int* vi1_out,
                                               int* vi2_out, float* g1, float* g2)
 {
@@ -216,8 +224,8 @@ __device__ __noinline__ void ehb_aa_pair_grad(const EhbLink& lk, const float* __
     const int vi1 = i1 == 0 ? vi.x : (i1 == 1 ? vi.y : vi.z);
     const int vi2 = i2 == 0 ? vi.x : (i2 == 1 ? vi.y : vi.z);
     float p1v[4], p2v[4];
-    ehb_xform(__ldg(lk.verts + vi1), m, p1v);
-    ehb_xform(__ldg(lk.verts + vi2), m, p2v);
+    ehb_clip_of(vc, vi1, p1v);
+    ehb_clip_of(vc, vi2, p2v);
     float pxh = 0.5f * (float)W, pyh = 0.5f * (float)H;
     float fx = (float)px + .5f - pxh, fy = (float)py + .5f - pyh;
     if (d) {

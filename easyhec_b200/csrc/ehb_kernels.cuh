@@ -34,10 +34,17 @@
 
 enum { EHB_MODE_FUSED = 0, EHB_MODE_AA_FWD = 1, EHB_MODE_AA_BWD = 2, EHB_MODE_UNION = 3 };
 
-struct EhbPairEnt {
-    uint32_t packed;         // idx (11) | d << 11 | own << 12 | side << 13 | di << 14
-    uint32_t tri;
-    float alpha;
+struct __align__(16) EhbPair {   // one silhouette pixel pair of a job (32 B, written / read as two words)
+    uint32_t packed;         // idx (11) | d << 11 | own << 12 | side << 13 | di << 14   (idx = p0 in the 35x35 window)
+    uint32_t tri;            // triangle of the covered pixel
+    float alpha;             // blend weight (0: no silhouette edge crosses the segment between the two centres)
+    uint32_t job;
+    int item, tile, link, entry;   // the job's fields, repeated so that the backward needs no second lookup
+};
+
+struct __align__(16) EhbJob {    // one (tile, link) window that some triangle of the link reaches into
+    int item, tile, link;
+    int entry;               // position of the tile in the tile list: its gradient window and first job are indexed by it
 };
 
 struct EhbPlane {            // depth plane of one (item, link): pixels [x0, x0+w) x [y0, y0+h), GL rows
@@ -48,7 +55,8 @@ struct EhbPlane {            // depth plane of one (item, link): pixels [x0, x0+
 
 struct EhbUnit { uint32_t rec; unsigned short dx0, dy0; };   // a 64 x 32 pixel window of a deferred triangle's bbox
 
-struct EhbCounters {
+struct __align__(128) EhbCounters {
+    // line 0: pass bookkeeping (one writer at a time, or a few hundred atomics per pass)
     unsigned long long planeCursor;
     unsigned long long nNeedClip;
     unsigned int nTiles;     // tiles touched by >= 2 link bboxes: listed from the front of tileList (served first) ...
@@ -56,17 +64,28 @@ struct EhbCounters {
     unsigned int workCursor;
     unsigned int nEmpty;     // tiles no link touches: streamed (mask = 0, loss += ref^2) by spare CTAs of the raster launch
     unsigned int vertexDone; // CTAs of k_table that have finished: the last one allocates the planes
+    unsigned int flags;      // 1: plane pool too small (results invalid, grow and rerun), 2: triangles need clipping
+    unsigned int pad0[22];
+    // line 1: the ticket counter of k_raster's persistent warps, alone on its line (thousands of atomics per pass)
+    unsigned int rasterCursor;
+    unsigned int pad1[31];
+    // line 2: queues of deferred triangles
     unsigned int nBigRec;    // deferred (not small) triangles: records parked in global memory ...
     unsigned int nUnits;     // ... and cut into bounded units that k_raster_big spreads over the whole chip
-    unsigned int flags;      // 1: plane pool too small (results invalid, grow and rerun), 2: triangles need clipping
-    unsigned int pad;
+    unsigned int pad2[30];
+    // line 3: job list and pair pool of the image-space stage
+    unsigned int nJobs;
+    unsigned int pairCursor;
+    unsigned int pad3[30];
     unsigned long long dbg[16];   // EHB_TIMING builds: cycles per phase of k_tiles (thread 0 of every CTA)
 };
+static_assert(sizeof(EhbCounters) % 128 == 0, "counter lines");
 
 struct EhbParams {
     int H, W, ntx, nty, ntiles;
     int items, L, Lp, Ftot, Vtot;   // Lp = planes per item: L (per-link visibility) or 1 (packed robot)
     int hlo, hhi;
+    int rasterStart;         // first ticket the persistent warps of k_raster draw (EHB_RPERSIST builds)
     int mode, rule, do_bwd, clamp;
     float invB;
     const float* mvp;        // [items, L, 16]
@@ -90,9 +109,13 @@ struct EhbParams {
     float* gpos;             // [V, 4] (AA_BWD, single link) or NULL
     const float* dy;         // [items, H, W]  AA_BWD
     uint8_t* out_u8;         // [items, H, W]  UNION
-    EhbPairEnt* pairSpill;   // [gridDim.x of k_tiles][spillCap] overflow of the shared-memory pair lists
-    int spillCap;
-    unsigned long long* dbgbuf;   // EHB_TIMING builds: per k_tiles CTA {start ns, end ns, tiles, longest tile cycles, its links}
+    EhbJob* jobs;            // [jobCap]  (tile, link) windows, the jobs of a tile consecutive and in link order
+    uint32_t* tileJob0;      // [items * ntiles]  first job of each listed tile (by list position)
+    EhbPair* pairs;          // [pairCap] silhouette pairs, the pairs of a job consecutive
+    float* maskBuf;          // [jobCap, 33, 36]  antialiased mask of each job's out region
+    float* gBuf;             // [items * ntiles, 33, 36]  dL/dsum of each listed tile's out region
+    int jobCap, pairCap;
+    unsigned long long* dbgbuf;   // unused (kept for the developer ABI)
 };
 
 #ifndef EHB_SMALL_AREA
@@ -148,7 +171,8 @@ __global__ void __launch_bounds__(256) ehb_k_table(const __grid_constant__ EhbRo
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         p.ctr->nTiles = 0u; p.ctr->nLight = 0u; p.ctr->nEmpty = 0u; p.ctr->workCursor = 0u;
-        p.ctr->nBigRec = 0u; p.ctr->nUnits = 0u;
+        p.ctr->nBigRec = 0u; p.ctr->nUnits = 0u; p.ctr->rasterCursor = (unsigned)p.rasterStart;
+        p.ctr->nJobs = 0u; p.ctr->pairCursor = 0u;
     }
     // outputs that the later kernels accumulate into
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.items; i += gridDim.x * blockDim.x) {
@@ -227,7 +251,9 @@ __global__ void __launch_bounds__(256) ehb_k_table(const __grid_constant__ EhbRo
 }
 
 // ------------------------------------------------------------------------------------------------ empty tiles
-// A tile no link touches: mask = 0 and loss += sum ref^2, streamed by one warp.
+// A tile no link touches: mask = 0 and loss += sum ref^2, streamed by one warp.  This is the HBM-bound 85 % of a frame,
+// so every load of the tile is issued before the first one is consumed (8 x 512 B in flight per warp for an f32
+// reference, the whole 1 KB tile in two 16-B loads per lane for a u8 one); the zero stores follow.
 __device__ __forceinline__ void ehb_stream_empty_tile(const EhbParams& p, int item, int tx, int ty, int lane)
 {
     const int x0 = tx * EHB_T, y0 = ty * EHB_T;
@@ -239,20 +265,54 @@ __device__ __forceinline__ void ehb_stream_empty_tile(const EhbParams& p, int it
                          (((uintptr_t)p.ref_u8) & 3) == 0;
         if (vec) {
             const int cx = x0 + 4 * (lane & 7);
+            const int pyb = y0 + (lane >> 3);
+            // image rows run downwards while py runs upwards: o(it) = o0 - it * 4 * W
+            const size_t o0 = ibase + (size_t)(H - 1 - pyb) * W + cx;
+            const size_t st = (size_t)4 * W;
+            const bool colOk = cx < W;
+            if (p.ref) {
+                float4 r[8];
 #pragma unroll
-            for (int it = 0; it < 8; it++) {
-                const int py = y0 + it * 4 + (lane >> 3);
-                if (py < H && cx < W) {
-                    const size_t o = ibase + (size_t)(H - 1 - py) * W + cx;
-                    if (p.ref) {
-                        const float4 r = __ldg(reinterpret_cast<const float4*>(p.ref + o));
-                        acc += (double)(r.x * r.x) + (double)(r.y * r.y) + (double)(r.z * r.z) + (double)(r.w * r.w);
-                    } else if (p.ref_u8) {
-                        const uchar4 r = __ldg(reinterpret_cast<const uchar4*>(p.ref_u8 + o));
-                        acc += (double)((r.x != 0) + (r.y != 0) + (r.z != 0) + (r.w != 0));
-                    }
-                    if (p.masks) *reinterpret_cast<float4*>(p.masks + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int it = 0; it < 8; it++) {
+                    r[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (colOk && pyb + it * 4 < H) r[it] = __ldg(reinterpret_cast<const float4*>(p.ref + (o0 - it * st)));
                 }
+#pragma unroll
+                for (int it = 0; it < 8; it++)
+                    acc += (double)(r[it].x * r[it].x) + (double)(r[it].y * r[it].y) + (double)(r[it].z * r[it].z) + (double)(r[it].w * r[it].w);
+            } else if (p.ref_u8) {
+                if ((W & 15) == 0 && x0 + EHB_T <= W && (((uintptr_t)p.ref_u8) & 15) == 0) {
+                    // one lane per row of the tile: its 32 bytes are two aligned 16-B words
+                    const int py = y0 + lane;
+                    if (py < H) {
+                        const uint4* src = reinterpret_cast<const uint4*>(p.ref_u8 + ibase + (size_t)(H - 1 - py) * W + x0);
+                        const uint4 a = __ldg(src), b = __ldg(src + 1);
+                        const uint32_t w8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                        int n = 0;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            // bytes != 0, counted four at a time: a byte is non-zero iff (b | (b + 0x7f)) has its top bit set
+                            const uint32_t v = w8[k];
+                            const uint32_t nz = ((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v;
+                            n += __popc(nz & 0x80808080u);
+                        }
+                        acc += (double)n;
+                    }
+                } else {
+                    uchar4 r[8];
+#pragma unroll
+                    for (int it = 0; it < 8; it++) {
+                        r[it] = make_uchar4(0, 0, 0, 0);
+                        if (colOk && pyb + it * 4 < H) r[it] = __ldg(reinterpret_cast<const uchar4*>(p.ref_u8 + (o0 - it * st)));
+                    }
+#pragma unroll
+                    for (int it = 0; it < 8; it++) acc += (double)((r[it].x != 0) + (r[it].y != 0) + (r[it].z != 0) + (r[it].w != 0));
+                }
+            }
+            if (p.masks && colOk) {
+#pragma unroll
+                for (int it = 0; it < 8; it++)
+                    if (pyb + it * 4 < H) __stcs(reinterpret_cast<float4*>(p.masks + (o0 - it * st)), make_float4(0.f, 0.f, 0.f, 0.f));
             }
         } else {
             for (int i = lane; i < EHB_T * EHB_T; i += 32) {
@@ -336,6 +396,12 @@ __global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRo
 // ------------------------------------------------------------------------------------------------ k_raster
 #ifndef EHB_RWARPS
 #define EHB_RWARPS 8         // warps per raster CTA; every warp works alone on batches of 32 triangles
+#endif
+#ifndef EHB_RBATCH
+#define EHB_RBATCH 1         // 32-triangle batches per ticket
+#endif
+#ifndef EHB_RMIN_BLOCKS
+#define EHB_RMIN_BLOCKS (1024 / (EHB_RWARPS * 32))
 #endif
 
 struct __align__(16) EhbRec {
@@ -427,14 +493,16 @@ __device__ __forceinline__ int ehb_make_record(const EhbRobot& rb, const EhbPara
     const int f = g - rb.foff[l];
     const EhbLink& lk = rb.link[l];
     const int4 id = __ldg(lk.faces + f);
+    const EhbPlane pl = p.plane[(size_t)item * p.Lp + (p.Lp == 1 ? 0 : l)];   // depends on the link only: issued with the face
     if ((unsigned)id.x >= (unsigned)lk.V || (unsigned)id.y >= (unsigned)lk.V || (unsigned)id.z >= (unsigned)lk.V) return 0;
     const size_t vb = (size_t)item * p.Vtot + rb.voff[l];
+    // all seven loads that depend on the face go out together (one L2 round trip), before the first test consumes one
     const float4 c0 = p.vclip[vb + id.x], c1 = p.vclip[vb + id.y], c2 = p.vclip[vb + id.z];
+    const int2 s0 = p.vsnap[vb + id.x], s1 = p.vsnap[vb + id.y], s2 = p.vsnap[vb + id.z];
     if ((c0.w < c0.x && c1.w < c1.x && c2.w < c2.x) || (c0.w < -c0.x && c1.w < -c1.x && c2.w < -c2.x) ||
         (c0.w < c0.y && c1.w < c1.y && c2.w < c2.y) || (c0.w < -c0.y && c1.w < -c1.y && c2.w < -c2.y) ||
         (c0.w < c0.z && c1.w < c1.z && c2.w < c2.z) || (c0.w < -c0.z && c1.w < -c1.z && c2.w < -c2.z))
         return 0;
-    const int2 s0 = p.vsnap[vb + id.x], s1 = p.vsnap[vb + id.y], s2 = p.vsnap[vb + id.z];
     const int G = 1 << 28;
     if (s0.x == INT_MIN || s1.x == INT_MIN || s2.x == INT_MIN ||   // a vertex outside the depth range: needs the clipper
         s0.x > G || s0.x < -G || s0.y > G || s0.y < -G || s1.x > G || s1.x < -G || s1.y > G || s1.y < -G ||
@@ -451,7 +519,6 @@ __device__ __forceinline__ int ehb_make_record(const EhbRobot& rb, const EhbPara
     const int pxlo = max((min(x0, min(x1, x2)) + bx + 15) >> 4, 0), pxhi = min((max(x0, max(x1, x2)) + bx) >> 4, p.W - 1);
     const int pylo = max((min(y0, min(y1, y2)) + by + 15) >> 4, 0), pyhi = min((max(y0, max(y1, y2)) + by) >> 4, p.H - 1);
     if (pxlo > pxhi || pylo > pyhi) return 0;
-    const EhbPlane pl = p.plane[(size_t)item * p.Lp + (p.Lp == 1 ? 0 : l)];
     if (pl.w == 0) return 0;   // pool overflow: flagged, the pass is rerun
     const int sx = 16 * pxlo - bx, sy = 16 * pylo - by;
     const int ex0 = x1 - x0, ey0 = y1 - y0, ex1 = x2 - x1, ey1 = y2 - y1, ex2 = x0 - x2, ey2 = y0 - y2;
@@ -526,7 +593,7 @@ __device__ __forceinline__ void ehb_rows_group(const RV rv, int t, int dy, int l
     }
 }
 
-__global__ void __launch_bounds__(EHB_RWARPS * 32) ehb_k_raster(const __grid_constant__ EhbRobot rb,
+__global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster(const __grid_constant__ EhbRobot rb,
                                                                 const __grid_constant__ EhbParams p, int streamBlocks,
                                                                 int chunks)
 {
@@ -545,47 +612,95 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32) ehb_k_raster(const __grid_con
         }
         return;
     }
-    const int rb_ = (int)blockIdx.x - streamBlocks;
-    const int item = rb_ / chunks;
-    const int g = ((rb_ - item * chunks) * EHB_RWARPS + warp) * 32 + lane;
+    // Every warp starts with the batch (32 triangles) of its own index.  EHB_RPERSIST builds launch one wave of CTAs and
+    // let the warps draw further tickets (EHB_RBATCH batches each) from a counter that k_table set to the number of
+    // warps; the default launches one warp per batch (measured faster: the tickets serialise on one L2 line).
+    const int total = chunks * p.items;   // chunks = 32-triangle batches per item
+    unsigned bcur = (unsigned)(((int)blockIdx.x - streamBlocks) * EHB_RWARPS + warp) * (unsigned)EHB_RBATCH, bnext = 0xFFFFFFFFu;
     const float xs = 2.f / (float)p.W, xo = 1.f / (float)p.W - 1.f;
     const float ys = 2.f / (float)p.H, yo = 1.f / (float)p.H - 1.f;
     const EhbRecSoA recs{s_rec[warp]};
     int* off = s_off[warp];
-    int rows = 0, wide = 0;
+    for (int sub = 0; bcur < (unsigned)total;) {
+    // a ticket is EHB_RBATCH consecutive batches; the next ticket is drawn when the last batch of this one starts
+#ifdef EHB_RPERSIST
+    if (lane == 0 && sub == EHB_RBATCH - 1) bnext = atomicAdd(&p.ctr->rasterCursor, (unsigned)EHB_RBATCH);
+#endif
+    const int item = (int)bcur / chunks;
+    const int g = ((int)bcur - item * chunks) * 32 + lane;
+    int rows = 0, wide = 0, link = 0, touchRows = 0;
+    bool big = false;
+    int4 tb = make_int4(0, 0, 0, 0);   // clipped bbox of this lane's triangle (x0, y0, w, h)
     if (g < p.Ftot) {
         EhbRec rc;
-        int link;
         rows = ehb_make_record(rb, p, item, g, rc, link);
-        if (rows > 0 && p.touch) {   // tell k_tiles which (tile, link) windows this triangle reaches into
-            const uint32_t bit = 1u << link;
-            const int txlo = max(0, (rc.x0 - p.hhi) >> 5), txhi = min(p.ntx - 1, (rc.x0 + rc.w - 1 + p.hlo) >> 5);
-            const int tylo = max(0, (rc.y0 - p.hhi) >> 5), tyhi = min(p.nty - 1, (rc.y0 + rc.h - 1 + p.hlo) >> 5);
-            for (int ty = tylo; ty <= tyhi; ty++)
-                for (int tx = txlo; tx <= txhi; tx++) {
-                    uint32_t* w = p.touch + (size_t)item * p.ntiles + ty * p.ntx + tx;
-                    if (!(__ldcg(w) & bit)) atomicOr(w, bit);   // mostly already set: a cached load instead of an atomic
-                }
-        }
+        touchRows = rows;
+        if (rows > 0) tb = make_int4(rc.x0, rc.y0, rc.w, rc.h);
         if (rows > 0) {
             const int ext = max(max(abs(rc.ex[0]), abs(rc.ex[1])), max(max(abs(rc.ex[2]), abs(rc.ey[0])), max(abs(rc.ey[1]), abs(rc.ey[2]))));
             wide = ext >= 32768;   // 32-bit edge arithmetic is exact below 2^15 sub-pixel units per edge
-            if (rc.w * rc.h > EHB_SMALL_AREA) {   // not small: park the record, cut the bbox into bounded units
-                const int nux = (rc.w + EHB_UNIT_W - 1) / EHB_UNIT_W, nuy = (rc.h + EHB_UNIT_H - 1) / EHB_UNIT_H;
-                const unsigned k = atomicAdd(&p.ctr->nBigRec, 1u);
-                const unsigned u0 = atomicAdd(&p.ctr->nUnits, (unsigned)(nux * nuy));
-                if ((int)k < p.bigCap && (int)(u0 + nux * nuy) <= p.unitCap) {
-                    p.bigRec[k] = rc;
+            big = rc.w * rc.h > EHB_SMALL_AREA;   // not small: park the record, cut the bbox into bounded units
+            ehb_rec_store_soa(s_rec[warp], lane, rc);
+        }
+    }
+    {   // deferred triangles of this batch: one pair of queue atomics per warp, records copied out by the whole warp
+        const unsigned bm = __ballot_sync(0xffffffffu, big);
+        if (bm) {
+            const int nux = big ? (tb.z + EHB_UNIT_W - 1) / EHB_UNIT_W : 0, nuy = big ? (tb.w + EHB_UNIT_H - 1) / EHB_UNIT_H : 0;
+            const int nu = nux * nuy;
+            int uinc = nu;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, uinc, o);
+                if (lane >= o) uinc += v;
+            }
+            const int utot = __shfl_sync(0xffffffffu, uinc, 31);
+            unsigned k0 = 0, ub = 0;
+            if (lane == 0) { k0 = atomicAdd(&p.ctr->nBigRec, (unsigned)__popc(bm)); ub = atomicAdd(&p.ctr->nUnits, (unsigned)utot); }
+            k0 = __shfl_sync(0xffffffffu, k0, 0); ub = __shfl_sync(0xffffffffu, ub, 0);
+            const unsigned k = k0 + (unsigned)__popc(bm & ((1u << lane) - 1u));
+            const unsigned u0 = ub + (unsigned)(uinc - nu);
+            const bool fits = (int)k < p.bigCap && (int)(u0 + nu) <= p.unitCap;
+            if (big) {
+                if (fits) {
                     for (int uy = 0; uy < nuy; uy++)
                         for (int ux = 0; ux < nux; ux++)
                             p.units[u0 + uy * nux + ux] = EhbUnit{k, (unsigned short)(ux * EHB_UNIT_W), (unsigned short)(uy * EHB_UNIT_H)};
                     rows = 0;
                 } else {
                     atomicOr(&p.ctr->flags, 4u);   // queues full: this one is drawn inline (slow but complete); its units are void
-                    for (int i = 0; i < nux * nuy && (int)(u0 + i) < p.unitCap; i++) p.units[u0 + i] = EhbUnit{0xFFFFFFFFu, 0, 0};
+                    for (int i = 0; i < nu && (int)(u0 + i) < p.unitCap; i++) p.units[u0 + i] = EhbUnit{0xFFFFFFFFu, 0, 0};
                 }
             }
-            if (rows > 0) ehb_rec_store_soa(s_rec[warp], lane, rc);
+            __syncwarp();
+            // park the records: lane w writes word w of each deferred record (one 128-B store per record)
+            unsigned todo = __ballot_sync(0xffffffffu, big && fits);
+            while (todo) {
+                const int t = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const unsigned kt = __shfl_sync(0xffffffffu, k, t);
+                reinterpret_cast<uint32_t*>(p.bigRec + kt)[lane] = s_rec[warp][lane * 32 + t];
+            }
+        }
+    }
+    if (p.touch) {
+        // Tell k_tiles which (tile, link) windows the triangles reach into.  Neighbouring triangles of a warp mostly
+        // fall into the same tile of the same link: lanes with equal (tile, link) elect one to issue the RED (no load,
+        // nothing waits for it); bboxes that straddle a tile border (halo included) set every tile they reach.
+        int txlo = 0, txhi = -1, tylo = 0, tyhi = -1;
+        if (touchRows > 0) {
+            txlo = max(0, (tb.x - p.hhi) >> 5); txhi = min(p.ntx - 1, (tb.x + tb.z - 1 + p.hlo) >> 5);
+            tylo = max(0, (tb.y - p.hhi) >> 5); tyhi = min(p.nty - 1, (tb.y + tb.w - 1 + p.hlo) >> 5);
+        }
+        const bool single = touchRows > 0 && txlo == txhi && tylo == tyhi;
+        const uint32_t key = single ? (((uint32_t)(tylo * p.ntx + txlo) << 5) | (uint32_t)link) : (0xFFFFFFE0u | (uint32_t)lane);
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        uint32_t* trow = p.touch + (size_t)item * p.ntiles;
+        if (single) {
+            if ((int)(__ffs(peers) - 1) == lane) atomicOr(trow + tylo * p.ntx + txlo, 1u << link);
+        } else {
+            for (int ty = tylo; ty <= tyhi; ty++)
+                for (int tx = txlo; tx <= txhi; tx++) atomicOr(trow + ty * p.ntx + tx, 1u << link);
         }
     }
     int inc = rows;
@@ -614,19 +729,31 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32) ehb_k_raster(const __grid_con
         if (anyWide) ehb_rows_group<long long, double, EhbRecSoA>(recs, t, dy, lane, p.pool, xs, xo, ys, yo);
         else ehb_rows_group<int, float, EhbRecSoA>(recs, t, dy, lane, p.pool, xs, xo, ys, yo);
     }
+    __syncwarp();   // the records of this batch are dead: the next one may overwrite them
+    if (++sub == EHB_RBATCH) { sub = 0; bcur = __shfl_sync(0xffffffffu, bnext, 0); }
+    else bcur++;
+    }
 }
 
 // Deferred triangles: warps stride over the unit list; one unit = a 64 x 32 pixel window of one triangle's bbox.
-__global__ void __launch_bounds__(256) ehb_k_raster_big(const __grid_constant__ EhbParams p)
+__device__ __forceinline__ void ehb_build_jobs(const EhbParams& p, int firstWarp, int nWarps, int lane);
+
+__global__ void __launch_bounds__(256) ehb_k_raster_big(const __grid_constant__ EhbParams p, int jobBlocks)
 {
     ehb_pdl_enter();
     __shared__ EhbRec s_rec[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if ((int)blockIdx.x >= (int)gridDim.x - jobBlocks) {
+        // the touch bitmap is final (k_raster has completed): spare CTAs turn it into the job list of the image-space stage
+        ehb_build_jobs(p, ((int)blockIdx.x - ((int)gridDim.x - jobBlocks)) * 8 + warp, jobBlocks * 8, lane);
+        return;
+    }
+    const int nUnitBlocks = (int)gridDim.x - jobBlocks;
     const int n = min((int)p.ctr->nUnits, p.unitCap);
     const float xs = 2.f / (float)p.W, xo = 1.f / (float)p.W - 1.f;
     const float ys = 2.f / (float)p.H, yo = 1.f / (float)p.H - 1.f;
     EhbRec* rc = &s_rec[warp];
-    for (int u = blockIdx.x * 8 + warp; u < n; u += gridDim.x * 8) {
+    for (int u = blockIdx.x * 8 + warp; u < n; u += nUnitBlocks * 8) {
         const EhbUnit un = p.units[u];
         if (un.rec == 0xFFFFFFFFu) continue;
         __syncwarp();
@@ -666,479 +793,5 @@ __global__ void __launch_bounds__(256) ehb_k_union_out(const __grid_constant__ E
         if (4 * q + 3 < W && (((uintptr_t)dst) & 3) == 0) *reinterpret_cast<uint32_t*>(dst) = v;
         else
             for (int k = 0; k < 4 && 4 * q + k < W; k++) dst[k] = (uint8_t)((v >> (8 * k)) & 1u);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ k_tiles
-#ifndef EHB_TTHREADS
-#define EHB_TTHREADS 128
-#endif
-#define EHB_TWARPS (EHB_TTHREADS / 32)
-static_assert(EHB_TTHREADS == 128, "k_tiles maps 32 rows x 4 eight-pixel segments onto its 128 threads");
-#ifndef EHB_PAIRCAP
-#define EHB_PAIRCAP 768      // pair-list entries kept in shared memory; the rest spills to a per-CTA global area
-#endif
-
-struct __align__(16) EhbSmem {
-    unsigned long long plane[EHB_NP];
-    float alpha[2][EHB_NP];
-    float sum[EHB_NP + 3];
-    EhbPairEnt pairs[EHB_PAIRCAP];
-    unsigned long long cov[EHB_RS + 1], hx[EHB_RS + 1], vy[EHB_RS + 1];
-    float mvp[EHB_MAX_LINKS * 16];
-    EhbPlane pl[EHB_MAX_LINKS];
-    int links[EHB_MAX_LINKS];
-    int segStart[EHB_MAX_LINKS + 1];
-    int rowCnt[EHB_RS + 1];
-    int nP;
-    int work;
-    // reference mask of the out region, fetched with cp.async at the start of the tile so that its HBM latency is
-    // hidden behind the antialias work: f32 words, or (u8 reference) 4 pixels per word
-    uint32_t refw[(EHB_T + 1) * (EHB_T + 4)];
-};
-
-__device__ __forceinline__ void ehb_cp_async4(void* smem_dst, const void* gmem_src)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void ehb_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-__device__ __forceinline__ unsigned long long ehb_bits(int lo, int hi)   // bits lo..hi (inclusive), empty if lo > hi
-{
-    lo = max(lo, 0); hi = min(hi, 63);
-    if (lo > hi) return 0ull;
-    const unsigned long long up = hi >= 63 ? ~0ull : ((1ull << (hi + 1)) - 1ull);
-    return up & ~((1ull << lo) - 1ull);
-}
-
-#ifdef EHB_TIMING
-#define EHB_TICK(k) do { if (tid == 0) { const long long now_ = clock64(); atomicAdd(&p.ctr->dbg[k], (unsigned long long)(now_ - t_last)); t_last = now_; } } while (0)
-#else
-#define EHB_TICK(k) do { } while (0)
-#endif
-#ifndef EHB_TMIN_BLOCKS
-#define EHB_TMIN_BLOCKS 4
-#endif
-__global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(const __grid_constant__ EhbRobot rb,
-                                                                             const __grid_constant__ EhbParams p)
-{
-    ehb_pdl_enter();
-    extern __shared__ __align__(16) unsigned char ehb_smem_raw[];
-    EhbSmem& sm = *reinterpret_cast<EhbSmem*>(ehb_smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int H = p.H, W = p.W;
-    const int hlo = p.hlo;
-    const bool needAA = p.mode == EHB_MODE_FUSED || p.mode == EHB_MODE_AA_FWD;
-    const bool doBwd = (p.mode == EHB_MODE_FUSED && p.do_bwd) || p.mode == EHB_MODE_AA_BWD;
-    // out region: interior, plus one column/row on the high side when the backward follows in this pass
-    const int oext = (p.mode == EHB_MODE_FUSED && p.do_bwd) ? 1 : 0;
-    const int ow = EHB_T + oext;
-    EhbPairEnt* spill = p.pairSpill + (size_t)blockIdx.x * p.spillCap;
-    auto pair_at = [&](int i) -> EhbPairEnt& { return i < EHB_PAIRCAP ? sm.pairs[i] : spill[i - EHB_PAIRCAP]; };
-
-    // sm.alpha is never cleared: the gather only reads positions whose pair bit is set in THIS link's hx / vy masks,
-    // and every such position is written by the blend-weight step of this link
-    const bool haveRef = p.ref != nullptr || p.ref_u8 != nullptr;
-    // u8 reference rows can be fetched 4 pixels per cp.async when every row start is 4-byte aligned
-    const bool ref8vec = p.ref_u8 != nullptr && (p.W & 3) == 0 && (((uintptr_t)p.ref_u8) & 3) == 0;
-    const unsigned nHeavy = p.ctr->nTiles, nTiles = nHeavy + p.ctr->nLight;
-    const unsigned listEnd = (unsigned)(p.items * p.ntiles) - 1u;
-    // thread 0 runs the tile queue two entries ahead: the atomic ticket and the tile id of the NEXT tile are fetched
-    // while the current one is processed, so no tile starts with two dependent L2 round trips
-    auto list_at = [&](unsigned w) -> uint32_t { return p.tileList[w < nHeavy ? w : listEnd - (w - nHeavy)]; };
-    unsigned nextWork = 0, nextNext = 0;
-    uint32_t nextWid = 0;
-    if (tid == 0) {
-        nextWork = atomicAdd(&p.ctr->workCursor, 1u);
-        if (nextWork < nTiles) { nextWid = list_at(nextWork); nextNext = atomicAdd(&p.ctr->workCursor, 1u); }
-    }
-
-#ifdef EHB_TIMING
-    long long t_last = clock64();
-    unsigned long long t_cta0, n_done = 0, worst = 0, worstLinks = 0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_cta0));
-#endif
-    for (;;) {
-        EHB_TICK(9);
-#ifdef EHB_TIMING
-        const long long t_tile0 = clock64();
-#endif
-        if (tid == 0) {
-            sm.work = nextWork < nTiles ? (int)nextWid : -1;
-            if (nextWork < nTiles) {
-                nextWork = nextNext;
-                if (nextWork < nTiles) { nextWid = list_at(nextWork); nextNext = atomicAdd(&p.ctr->workCursor, 1u); }
-            }
-        }
-        __syncthreads();
-        if (sm.work < 0) break;
-        const uint32_t wid = (uint32_t)sm.work;
-        const int item = wid / p.ntiles, tile = wid - item * p.ntiles;
-        const int tx = tile % p.ntx, ty = tile / p.ntx;
-        const int x0 = tx * EHB_T, y0 = ty * EHB_T;
-        const int rx0 = x0 - hlo, ry0 = y0 - hlo;
-        const int rx1 = x0 + EHB_T - 1 + p.hhi, ry1 = y0 + EHB_T - 1 + p.hhi;
-        const size_t ibase = (size_t)item * H * W;
-
-        if (warp == 0) {   // links whose plane touches this tile's window
-            bool hit = false;
-            EhbPlane pl;
-            if (lane < p.L) {
-                pl = p.plane[(size_t)item * p.L + lane];
-                hit = pl.w > 0 && ((p.touch[wid] >> lane) & 1u);
-            }
-            const unsigned b = __ballot_sync(0xffffffffu, hit);
-            if (hit) {
-                const int k = __popc(b & ((1u << lane) - 1u));
-                sm.links[k] = lane;
-                sm.pl[k] = pl;
-            }
-            if (lane == 0) { sm.nP = __popc(b); sm.segStart[0] = 0; }
-        }
-        for (int i = tid; i < p.L * 16; i += EHB_TTHREADS) sm.mvp[i] = __ldg(p.mvp + (size_t)item * p.L * 16 + i);
-        if (needAA && haveRef) {   // start fetching the reference mask of the out region
-            if (p.ref) {
-                for (int qy = warp; qy < ow; qy += EHB_TWARPS) {
-                    const int py = y0 + qy;
-                    if (py >= H) continue;
-                    const float* row = p.ref + ibase + (size_t)(H - 1 - py) * W + x0;
-                    if (x0 + lane < W) ehb_cp_async4(&sm.refw[qy * (EHB_T + 4) + lane], row + lane);
-                    if (oext && lane == 0 && x0 + EHB_T < W) ehb_cp_async4(&sm.refw[qy * (EHB_T + 4) + EHB_T], row + EHB_T);
-                }
-            } else if (ref8vec) {
-                for (int q = tid; q < ow * 16; q += EHB_TTHREADS) {
-                    const int qy = q >> 4, qw = q & 15;
-                    const int px = x0 + 4 * qw, py = y0 + qy;
-                    if (qw < 9 && px < W && py < H && (qw < 8 || oext)) ehb_cp_async4(&sm.refw[qy * (EHB_T + 4) + qw], p.ref_u8 + ibase + (size_t)(H - 1 - py) * W + px);
-                }
-            }
-        }
-        if (needAA)
-            for (int i = tid; i < (EHB_NP + 3) / 4; i += EHB_TTHREADS) reinterpret_cast<float4*>(sm.sum)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.mode == EHB_MODE_AA_BWD)   // g = dL/dmask comes from the caller
-            for (int i = tid; i < (EHB_T + 1) * (EHB_T + 1); i += EHB_TTHREADS) {
-                const int qy = i / (EHB_T + 1), qx = i - qy * (EHB_T + 1);
-                const int px = x0 + qx, py = y0 + qy;
-                if (px < W && py < H)
-                    sm.sum[(py - ry0) * EHB_RS + (px - rx0)] = __ldg(p.dy + ibase + (size_t)(H - 1 - py) * W + px);
-            }
-        __syncthreads();
-        const int nP = sm.nP;
-        EHB_TICK(0);
-#ifdef EHB_TIMING
-        if (tid == 0) { atomicAdd(&p.ctr->dbg[10], 1ull); atomicAdd(&p.ctr->dbg[11], (unsigned long long)nP); }
-#endif
-
-        for (int k = 0; k < nP; k++) {
-            const int l = sm.links[k];
-            const EhbLink& lk = rb.link[l];
-            const float* m = sm.mvp + 16 * l;
-            // ================ window of link k's plane -> shared memory, row coverage masks by ballot ===============
-            {
-                const EhbPlane pl = sm.pl[k];
-                unsigned long long anyRow = 0ull;
-                // all loads of this warp's rows are issued before the first ballot consumes one (9 rows x 2 words in flight)
-                constexpr int NR = (EHB_RS + EHB_TWARPS - 1) / EHB_TWARPS;
-                unsigned long long v0[NR], v1[NR];
-#pragma unroll
-                for (int j = 0; j < NR; j++) {
-                    const int r = warp + j * EHB_TWARPS;
-                    v0[j] = EHB_EMPTY; v1[j] = EHB_EMPTY;
-                    if (r < EHB_RS) {
-                        const int py = ry0 + r - pl.y0;
-                        const bool rowOk = py >= 0 && py < pl.h && ry0 + r <= ry1;
-                        const unsigned long long* row = p.pool + pl.off + (long long)py * pl.w - pl.x0 + rx0;
-                        const int px = rx0 + lane - pl.x0;
-                        if (rowOk && px >= 0 && px < pl.w && rx0 + lane <= rx1) v0[j] = row[lane];
-                        if (lane < EHB_RS - 32) {
-                            const int px1 = px + 32;
-                            if (rowOk && px1 >= 0 && px1 < pl.w && rx0 + 32 + lane <= rx1) v1[j] = row[32 + lane];
-                        }
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < NR; j++) {
-                    const int r = warp + j * EHB_TWARPS;
-                    if (r < EHB_RS) {
-                        sm.plane[r * EHB_RS + lane] = v0[j];
-                        if (lane < EHB_RS - 32) sm.plane[r * EHB_RS + 32 + lane] = v1[j];
-                        const unsigned b0 = __ballot_sync(0xffffffffu, v0[j] != EHB_EMPTY);
-                        const unsigned b1 = __ballot_sync(0xffffffffu, v1[j] != EHB_EMPTY);
-                        const unsigned long long cm = (unsigned long long)b0 | ((unsigned long long)b1 << 32);
-                        if (lane == 0) sm.cov[r] = cm;
-                        anyRow |= cm;
-                    }
-                }
-                if (tid == 0) sm.cov[EHB_RS] = 0ull;
-                if (!__syncthreads_or(anyRow != 0ull)) {   // the link reaches into the window but covers no sample of it
-                    if (tid == 0) sm.segStart[k + 1] = sm.segStart[k];
-                    __syncthreads();
-                    EHB_TICK(1);
-                    continue;
-                }
-            }
-            EHB_TICK(1);
-            const int seg0 = sm.segStart[k];
-            if (warp == 0) {
-                // columns whose pixel is inside the image, and for which the right neighbour is too
-                const unsigned long long inX = ehb_bits(-rx0, W - 1 - rx0), inX1 = ehb_bits(-rx0, W - 2 - rx0);
-                unsigned long long hm[2], vm[2], om[2];
-                int cnt[2];
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int r = lane + 32 * h;
-                    hm[h] = vm[h] = om[h] = 0ull;
-                    if (r < EHB_RS) {
-                        const int py = ry0 + r;
-                        const unsigned long long cm = sm.cov[r], cu = sm.cov[r + 1];
-                        // pairs wanted: forward = those touching a pixel of the out region; otherwise only owned ones
-                        unsigned long long wantH, wantV;
-                        if (needAA) {
-                            wantH = (r >= hlo && r <= hlo + ow - 1) ? ehb_bits(hlo - 1, hlo + ow - 1) : 0ull;
-                            wantV = (r >= hlo - 1 && r <= hlo + ow - 1) ? ehb_bits(hlo, hlo + ow - 1) : 0ull;
-                        } else {
-                            wantH = wantV = (r >= hlo && r <= hlo + EHB_T - 1) ? ehb_bits(hlo, hlo + EHB_T - 1) : 0ull;
-                        }
-                        const bool rowIn = py >= 0 && py < H;
-                        if (rowIn) hm[h] = (cm ^ (cm >> 1)) & inX1 & wantH & ehb_bits(0, EHB_RS - 2);
-                        if (rowIn && py < H - 1 && r < EHB_RS - 1) vm[h] = (cm ^ cu) & inX & wantV;
-                        om[h] = (r >= hlo && r <= hlo + EHB_T - 1) ? ehb_bits(hlo, hlo + EHB_T - 1) : 0ull;
-                        sm.hx[r] = hm[h]; sm.vy[r] = vm[h];
-                    }
-                    cnt[h] = __popcll(hm[h]) + __popcll(vm[h]);
-                }
-                // exclusive prefix over the 35 rows: rows 0..31 by shuffle scan, rows 32..34 after them
-                int inc = cnt[0];
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += v;
-                }
-                const int tot0 = __shfl_sync(0xffffffffu, inc, 31);
-                int inc1 = cnt[1];
-#pragma unroll
-                for (int o = 1; o < 4; o <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, inc1, o);
-                    if (lane >= o) inc1 += v;
-                }
-                const int tot1 = __shfl_sync(0xffffffffu, inc1, 3);
-                if (lane == 0) sm.segStart[k + 1] = seg0 + tot0 + tot1;
-                int o0 = seg0 + inc - cnt[0], o1 = seg0 + tot0 + inc1 - cnt[1];
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    int o = h ? o1 : o0;
-                    unsigned long long hxm = hm[h], vym = vm[h];
-                    const uint32_t rowBase = (uint32_t)(lane + 32 * h) * EHB_RS;
-                    while (hxm) {
-                        const int b = __ffsll((long long)hxm) - 1;
-                        hxm &= hxm - 1;
-                        pair_at(o++).packed = (rowBase + b) | (((om[h] >> b) & 1ull) ? (1u << 12) : 0u);
-                    }
-                    while (vym) {
-                        const int b = __ffsll((long long)vym) - 1;
-                        vym &= vym - 1;
-                        pair_at(o++).packed = (rowBase + b) | (1u << 11) | (((om[h] >> b) & 1ull) ? (1u << 12) : 0u);
-                    }
-                }
-            }
-            __syncthreads();
-            const int seg1 = sm.segStart[k + 1];
-            EHB_TICK(2);
-#ifdef EHB_TIMING
-            if (tid == 0) atomicAdd(&p.ctr->dbg[12], (unsigned long long)(seg1 - seg0));
-#endif
-            // ================================ blend weights, all lanes busy =====================================
-            for (int j = seg0 + tid; j < seg1; j += EHB_TTHREADS) {
-                EhbPairEnt& pe = pair_at(j);
-                const uint32_t pk = pe.packed;
-                const int idx = pk & 2047, d = (pk >> 11) & 1;
-                const int ly = idx / EHB_RS, lx = idx - ly * EHB_RS;
-                const unsigned long long ka = sm.plane[idx], kb = sm.plane[idx + (d ? EHB_RS : 1)];
-                const int side = ka != EHB_EMPTY ? 0 : 1;
-                const uint32_t t = (uint32_t)(side ? kb : ka);
-                int di;
-                const float al = ehb_aa_pair(lk, m, (int)t, side, rx0 + lx, ry0 + ly, d, H, W, &di);
-                pe.packed = pk | ((uint32_t)side << 13) | ((uint32_t)di << 14);
-                pe.tri = t;
-                pe.alpha = al;
-                if (needAA) sm.alpha[d][idx] = al;
-            }
-            if (needAA) {
-                __syncthreads();
-                EHB_TICK(3);
-                // ============================ gather: sum += colour + pair contributions ========================
-                // each thread owns 8 consecutive pixels of one row (32 rows x 4 segments); a second short pass takes the
-                // extra row / column that exist when the backward follows.  Masks are read once per thread.
-#ifndef EHB_SKIP_GATHER
-                for (int pass = 0; pass < (oext ? 2 : 1); pass++) {
-                    int qy, qx0, n;
-                    if (pass == 0) { qy = tid >> 2; qx0 = (tid & 3) * 8; n = 8; }
-                    else if (tid < 4) { qy = EHB_T; qx0 = tid * 8; n = 8; }            // row 32
-                    else if (tid < 4 + EHB_T + 1) { qy = tid - 4; qx0 = EHB_T; n = 1; }   // column 32 (incl. the corner)
-                    else break;
-                    if (qy >= EHB_T + oext) continue;
-                    const int ly = hlo + qy, lx0 = hlo + qx0;
-                    const unsigned long long cm = sm.cov[ly], hr = sm.hx[ly], vr = sm.vy[ly], vd = sm.vy[ly - 1];
-                    // the segment's 8 flag bits of each mask, extracted once
-                    const uint32_t nm = (1u << n) - 1u;
-                    const uint32_t c8 = (uint32_t)(cm >> lx0) & nm, h08 = (uint32_t)(hr >> lx0) & nm, v08 = (uint32_t)(vr >> lx0) & nm;
-                    const uint32_t h18 = (uint32_t)(hr >> (lx0 - 1)) & nm, v18 = (uint32_t)(vd >> lx0) & nm;
-                    const uint32_t pairBits = h08 | v08 | h18 | v18;
-                    uint32_t todo = c8 | pairBits;
-                    float* srow = sm.sum + ly * EHB_RS + lx0;
-                    while (todo) {
-                        const int i = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        const bool c = (c8 >> i) & 1u;
-                        const float cf = c ? 1.f : 0.f;
-                        float o = cf;
-                        if ((pairBits >> i) & 1u) {
-                            const int idx = ly * EHB_RS + lx0 + i;
-                            const float nb = c ? 0.f : 1.f;   // a pair's other pixel has the opposite coverage
-                            float a;
-                            // colour, pair(p,p+x), pair(p,p+y), pair(p-x,p), pair(p-y,p); the receiver is p0 when alpha > 0
-                            if ((h08 >> i) & 1u) { a = sm.alpha[0][idx]; if (a > 0.f) o += a * (nb - cf); }
-                            if ((v08 >> i) & 1u) { a = sm.alpha[1][idx]; if (a > 0.f) o += a * (nb - cf); }
-                            if ((h18 >> i) & 1u) { a = sm.alpha[0][idx - 1]; if (!(a > 0.f) && a != 0.f) o += a * (cf - nb); }
-                            if ((v18 >> i) & 1u) { a = sm.alpha[1][idx - EHB_RS]; if (!(a > 0.f) && a != 0.f) o += a * (cf - nb); }
-                        }
-                        srow[i] = srow[i] + o;   // links are added in link order (rb_solver.py:68); absent links add 0
-                    }
-                }
-#endif
-            }
-            __syncthreads();
-            EHB_TICK(4);
-        }
-
-        if (needAA) {
-            // S = min(sum, 1); loss; g = dL/dsum kept in sm.sum for the backward
-            double lacc = 0.0;
-            if (haveRef) { ehb_cp_async_wait_all(); __syncthreads(); }
-            // same thread -> pixel mapping as the gather: 8 consecutive pixels of one row per thread, then the extra
-            // row / column; the 8 mask values of a segment leave as two float4 stores
-            const bool vecOut = p.masks != nullptr && (W & 3) == 0 && (((uintptr_t)p.masks) & 15) == 0;
-            for (int pass = 0; pass < (oext ? 2 : 1); pass++) {
-                int qy, qx0, n;
-                if (pass == 0) { qy = tid >> 2; qx0 = (tid & 3) * 8; n = 8; }
-                else if (tid < 4) { qy = EHB_T; qx0 = tid * 8; n = 8; }
-                else if (tid < 4 + EHB_T + 1) { qy = tid - 4; qx0 = EHB_T; n = 1; }
-                else break;
-                const int py = y0 + qy;
-                if (qy >= EHB_T + oext || py >= H) continue;
-                const size_t orow = ibase + (size_t)(H - 1 - py) * W;
-                float Sv[8];
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    Sv[i] = 0.f;
-                    const int qx = qx0 + i, px = x0 + qx;
-                    if (i >= n || px >= W) continue;
-                    const int idx = (py - ry0) * EHB_RS + (px - rx0);
-                    const float s = sm.sum[idx];
-                    const float S = (p.clamp && s > 1.f) ? 1.f : s;
-                    Sv[i] = S;
-                    const bool interior = qx < EHB_T && qy < EHB_T;
-                    if (haveRef) {
-                        float rf;
-                        if (p.ref) rf = __uint_as_float(sm.refw[qy * (EHB_T + 4) + qx]);
-                        else if (ref8vec) rf = ((sm.refw[qy * (EHB_T + 4) + (qx >> 2)] >> (8 * (qx & 3))) & 255u) ? 1.f : 0.f;
-                        else rf = __ldg(p.ref_u8 + orow + px) ? 1.f : 0.f;
-                        const float diff = S - rf;
-                        if (interior) lacc += (double)(diff * diff);
-                        sm.sum[idx] = (!p.clamp || s <= 1.f) ? (2.f * diff) * p.invB : 0.f;
-                    }
-                }
-                if (p.masks && qy < EHB_T && qx0 < EHB_T) {
-                    if (vecOut && x0 + qx0 + 7 < W) {
-                        float4* dst = reinterpret_cast<float4*>(p.masks + orow + x0 + qx0);
-                        dst[0] = make_float4(Sv[0], Sv[1], Sv[2], Sv[3]);
-                        dst[1] = make_float4(Sv[4], Sv[5], Sv[6], Sv[7]);
-                    } else {
-                        for (int i = 0; i < n; i++)
-                            if (x0 + qx0 + i < W) p.masks[orow + x0 + qx0 + i] = Sv[i];
-                    }
-                }
-            }
-            if (haveRef && p.loss) {
-                lacc = ehb_warp_sum(lacc);
-                if (lane == 0 && lacc != 0.0) atomicAdd(&p.loss[item], lacc);
-            }
-            __syncthreads();
-        }
-        EHB_TICK(5);
-
-        // ======================================= backward: walk the pair list ===================================
-        if (doBwd) {
-            for (int k = 0; k < nP; k++) {
-                const int l = sm.links[k];
-                const EhbLink& lk = rb.link[l];
-                const float* m = sm.mvp + 16 * l;
-                const int seg0 = sm.segStart[k], seg1 = sm.segStart[k + 1];
-                if (seg0 + warp * 32 >= seg1) continue;   // nothing for this warp (warp-uniform)
-                double acc[12];
-#pragma unroll
-                for (int i = 0; i < 12; i++) acc[i] = 0.0;
-                bool had = false;
-                for (int j = seg0 + tid; j < seg1; j += EHB_TTHREADS) {
-                    const EhbPairEnt pe = pair_at(j);
-                    const float al = pe.alpha;
-                    if (!(pe.packed & (1u << 12)) || al == 0.f) continue;
-                    const int idx = pe.packed & 2047, d = (pe.packed >> 11) & 1, side = (pe.packed >> 13) & 1,
-                              di = (pe.packed >> 14) & 3;
-                    const int idx1 = idx + (d ? EHB_RS : 1);
-                    const int ly = idx / EHB_RS, lx = idx - ly * EHB_RS;
-                    const float g = sm.sum[al > 0.f ? idx : idx1];
-                    const float dd = g * (side ? 1.f : -1.f);   // g * (c1 - c0)
-                    if (dd == 0.f) continue;
-                    int vi1, vi2;
-                    float g1[3], g2[3];
-                    ehb_aa_pair_grad(lk, m, (int)pe.tri, side, di, al, dd, rx0 + lx, ry0 + ly, d, H, W, &vi1, &vi2, g1, g2);
-                    const float4 va = __ldg(lk.verts + vi1), vb = __ldg(lk.verts + vi2);
-                    const double ha[4] = {(double)va.x, (double)va.y, (double)va.z, 1.0};
-                    const double hb[4] = {(double)vb.x, (double)vb.y, (double)vb.z, 1.0};
-#pragma unroll
-                    for (int rr = 0; rr < 3; rr++)
-#pragma unroll
-                        for (int c = 0; c < 4; c++) acc[4 * rr + c] += (double)g1[rr] * ha[c] + (double)g2[rr] * hb[c];
-                    had = true;
-                    if (p.gpos) {
-                        atomicAdd(p.gpos + 4 * (size_t)vi1 + 0, g1[0]);
-                        atomicAdd(p.gpos + 4 * (size_t)vi1 + 1, g1[1]);
-                        atomicAdd(p.gpos + 4 * (size_t)vi1 + 3, g1[2]);
-                        atomicAdd(p.gpos + 4 * (size_t)vi2 + 0, g2[0]);
-                        atomicAdd(p.gpos + 4 * (size_t)vi2 + 1, g2[1]);
-                        atomicAdd(p.gpos + 4 * (size_t)vi2 + 3, g2[2]);
-                    }
-                }
-                if (__any_sync(0xffffffffu, had)) {
-                    double* dst = p.gmvp + ((size_t)item * p.L + l) * 16;
-#pragma unroll
-                    for (int i = 0; i < 12; i++) {
-                        const double v = ehb_warp_sum(acc[i]);
-                        // rows x (0), y (1), w (3) of d loss / d mvp; the z row carries no gradient
-                        if (lane == 0 && v != 0.0) atomicAdd(dst + (i < 8 ? i : i + 4), v);
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        EHB_TICK(6);
-#ifdef EHB_TIMING
-        if (tid == 0 && p.dbgbuf) {
-            unsigned long long t_now;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
-            unsigned long long* d = p.dbgbuf + (size_t)blockIdx.x * 5;
-            d[0] = t_cta0; d[1] = t_now; d[2] = n_done + 1; d[3] = worst; d[4] = worstLinks;
-        }
-        if (tid == 0) {
-            const unsigned long long dt = (unsigned long long)(clock64() - t_tile0);
-            n_done++;
-            if (dt > worst) { worst = dt; worstLinks = (unsigned long long)nP | ((unsigned long long)sm.segStart[nP] << 8); }
-            atomicMax(&p.ctr->dbg[13], dt);
-            if (dt > 50000ull) atomicAdd(&p.ctr->dbg[14], 1ull);
-            if (dt > 100000ull) atomicAdd(&p.ctr->dbg[15], 1ull);
-        }
-#endif
     }
 }
