@@ -81,6 +81,7 @@ struct Scratch {
     DevBuf<uint32_t> tileList, emptyList, touch;
     DevBuf<EhbRec> bigRec;
     DevBuf<EhbUnit> units;
+    DevBuf<uint32_t> batchBlk;        // parked heavy batches of k_raster
     DevBuf<EhbJob> jobs;              // image-space stage: (tile, link) windows ...
     DevBuf<uint32_t> tileJob0;
     DevBuf<EhbPair> pairs;            // ... their silhouette pairs ...
@@ -89,7 +90,7 @@ struct Scratch {
     void release()
     {
         vclip.release(); vsnap.release(); plane.release(); pool.release(); tileList.release(); emptyList.release();
-        touch.release(); bigRec.release(); units.release();
+        touch.release(); bigRec.release(); units.release(); batchBlk.release();
         jobs.release(); tileJob0.release(); pairs.release(); maskBuf.release(); gBuf.release();
     }
 };
@@ -261,6 +262,7 @@ int tune_int(const char* name, int dflt)
 }
 constexpr int BIG_CAP = 1 << 17;     // deferred triangles per pass (16 MB of records)
 constexpr int UNIT_CAP = 1 << 19;
+constexpr int BATCH_CAP = 1 << 14;   // parked heavy batches per pass (70 MB); beyond it a batch is simply drawn inline
 
 struct Io {
     const float* ref = nullptr; const uint8_t* ref_u8 = nullptr;
@@ -332,6 +334,7 @@ int ensure_scratch(Ctx* c, Scratch& sc, int items, int L, int Lp, int H, int W, 
     if ((r = sc.emptyList.ensure((size_t)items * ntiles, capturing))) return r;
     if ((r = sc.bigRec.ensure((size_t)BIG_CAP, capturing))) return r;
     if ((r = sc.units.ensure((size_t)UNIT_CAP, capturing))) return r;
+    if ((r = sc.batchBlk.ensure((size_t)BATCH_CAP * EHB_BLK_WORDS, capturing))) return r;
     // Plane pool: the worst case (every link's bbox is the whole screen) is items * Lp * H * W entries.  That is what is
     // reserved while it stays under POOL_BUDGET (180 GB of HBM: 10 views x 7 links x 1280x720 is 0.5 GB) -- then the
     // pool can never overflow; beyond it the pool holds poolFactor screens per item and grows on the overflow flag.
@@ -366,13 +369,14 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
     case EHB_MODE_AA_BWD: p.hlo = 0; p.hhi = 1; break;
     default: p.hlo = 0; p.hhi = 0; break;
     }
+    p.xs = 2.f / (float)W; p.xo = 1.f / (float)W - 1.f; p.ys = 2.f / (float)H; p.yo = 1.f / (float)H - 1.f;
     p.mode = mode; p.rule = c->rule; p.do_bwd = io.do_bwd; p.clamp = io.clamp; p.invB = io.invB;
     const bool capturing = is_capturing(st);
     if ((r = ensure_scratch(c, sc, items, L, p.Lp, H, W, p.Vtot, capturing))) return r;
     p.mvp = mvp_dev;
     p.vclip = sc.vclip.p; p.vsnap = sc.vsnap.p;
     p.plane = sc.plane.p; p.pool = sc.pool.p; p.poolCap = sc.pool.n;
-    p.tileList = sc.tileList.p; p.emptyList = sc.emptyList.p; p.touch = unionMode ? nullptr : sc.touch.p; p.bigRec = sc.bigRec.p; p.units = sc.units.p; p.bigCap = BIG_CAP; p.unitCap = UNIT_CAP; p.ctr = sc.ctr;
+    p.tileList = sc.tileList.p; p.emptyList = sc.emptyList.p; p.touch = unionMode ? nullptr : sc.touch.p; p.bigRec = sc.bigRec.p; p.units = sc.units.p; p.bigCap = BIG_CAP; p.unitCap = UNIT_CAP; p.batchBlk = tune_int("EHB_NO_OFFLOAD", 0) ? nullptr : sc.batchBlk.p; p.batchCap = BATCH_CAP; p.ctr = sc.ctr;
     p.ref = io.ref; p.ref_u8 = io.ref_u8; p.masks = io.masks; p.loss = io.loss; p.gmvp = io.gmvp; p.gpos = io.gpos;
     p.dy = io.dy; p.out_u8 = io.out_u8;
     p.jobs = sc.jobs.p; p.tileJob0 = sc.tileJob0.p; p.pairs = sc.pairs.p; p.maskBuf = sc.maskBuf.p; p.gBuf = sc.gBuf.p;

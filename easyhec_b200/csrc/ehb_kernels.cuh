@@ -72,7 +72,8 @@ struct __align__(128) EhbCounters {
     // line 2: queues of deferred triangles
     unsigned int nBigRec;    // deferred (not small) triangles: records parked in global memory ...
     unsigned int nUnits;     // ... and cut into bounded units that k_raster_big spreads over the whole chip
-    unsigned int pad2[30];
+    unsigned int nBatchBlk;  // batches with many rows: records parked, the rows beyond the inline share become units too
+    unsigned int pad2[29];
     // line 3: job list and pair pool of the image-space stage
     unsigned int nJobs;
     unsigned int pairCursor;
@@ -88,6 +89,7 @@ struct EhbParams {
     int rasterStart;         // first ticket the persistent warps of k_raster draw (EHB_RPERSIST builds)
     int mode, rule, do_bwd, clamp;
     float invB;
+    float xs, xo, ys, yo;    // NDC of a pixel centre: x = xs * px + xo, y = ys * py + yo (2/W, 1/W - 1, 2/H, 1/H - 1 in fp32)
     const float* mvp;        // [items, L, 16]
     float4* vclip;           // [items, Vtot]  clip-space position of every vertex (written by k_front)
     int2* vsnap;             // [items, Vtot]  snapped screen position (1/16 px), x = INT_MIN when not drawable
@@ -100,6 +102,8 @@ struct EhbParams {
     struct EhbRec* bigRec;   // [bigCap]
     EhbUnit* units;          // [unitCap]
     int bigCap, unitCap;
+    uint32_t* batchBlk;      // [batchCap][EHB_BLK_WORDS] parked batches: 32 records (transposed) + row prefix + flags
+    int batchCap;
     EhbCounters* ctr;
     const float* ref;        // [items, H, W]  FUSED
     const uint8_t* ref_u8;   // same, as bytes (either ref or ref_u8)
@@ -172,7 +176,7 @@ __global__ void __launch_bounds__(256) ehb_k_table(const __grid_constant__ EhbRo
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         p.ctr->nTiles = 0u; p.ctr->nLight = 0u; p.ctr->nEmpty = 0u; p.ctr->workCursor = 0u;
         p.ctr->nBigRec = 0u; p.ctr->nUnits = 0u; p.ctr->rasterCursor = (unsigned)p.rasterStart;
-        p.ctr->nJobs = 0u; p.ctr->pairCursor = 0u;
+        p.ctr->nJobs = 0u; p.ctr->pairCursor = 0u; p.ctr->nBatchBlk = 0u;
     }
     // outputs that the later kernels accumulate into
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.items; i += gridDim.x * blockDim.x) {
@@ -400,6 +404,13 @@ __global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRo
 #ifndef EHB_RBATCH
 #define EHB_RBATCH 1         // 32-triangle batches per ticket
 #endif
+#ifndef EHB_RINLINE
+#define EHB_RINLINE 2        // groups of 32 rows a warp of k_raster draws itself; the rest of a heavy batch is handed on
+#endif
+#ifndef EHB_RGROUPS
+#define EHB_RGROUPS 2        // groups of 32 rows per handed-on unit
+#endif
+#define EHB_BLK_WORDS (32 * 32 + 64)
 #ifndef EHB_RMIN_BLOCKS
 #define EHB_RMIN_BLOCKS (1024 / (EHB_RWARPS * 32))
 #endif
@@ -617,8 +628,7 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
     // warps; the default launches one warp per batch (measured faster: the tickets serialise on one L2 line).
     const int total = chunks * p.items;   // chunks = 32-triangle batches per item
     unsigned bcur = (unsigned)(((int)blockIdx.x - streamBlocks) * EHB_RWARPS + warp) * (unsigned)EHB_RBATCH, bnext = 0xFFFFFFFFu;
-    const float xs = 2.f / (float)p.W, xo = 1.f / (float)p.W - 1.f;
-    const float ys = 2.f / (float)p.H, yo = 1.f / (float)p.H - 1.f;
+    const float xs = p.xs, xo = p.xo, ys = p.ys, yo = p.yo;
     const EhbRecSoA recs{s_rec[warp]};
     int* off = s_off[warp];
     for (int sub = 0; bcur < (unsigned)total;) {
@@ -663,9 +673,24 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
             const bool fits = (int)k < p.bigCap && (int)(u0 + nu) <= p.unitCap;
             if (big) {
                 if (fits) {
+                    // A window of the bbox that lies entirely outside one edge (the edge function's maximum over the
+                    // window is negative) holds no covered sample: it becomes a void unit.  Sliver triangles have many.
+                    long long E[3]; int ex[3], ey[3];
+#pragma unroll
+                    for (int q = 0; q < 3; q++) { E[q] = recs.ll(lane, 2 * q); ex[q] = recs.i(lane, 6 + q); ey[q] = recs.i(lane, 9 + q); }
                     for (int uy = 0; uy < nuy; uy++)
-                        for (int ux = 0; ux < nux; ux++)
-                            p.units[u0 + uy * nux + ux] = EhbUnit{k, (unsigned short)(ux * EHB_UNIT_W), (unsigned short)(uy * EHB_UNIT_H)};
+                        for (int ux = 0; ux < nux; ux++) {
+                            const int dx0 = ux * EHB_UNIT_W, dx1 = min(tb.z - 1, dx0 + EHB_UNIT_W - 1);
+                            const int dy0 = uy * EHB_UNIT_H, dy1 = min(tb.w - 1, dy0 + EHB_UNIT_H - 1);
+                            bool any = true;
+#pragma unroll
+                            for (int q = 0; q < 3; q++) {
+                                const long long mx = E[q] + 16ll * ex[q] * (long long)(ex[q] > 0 ? dy1 : dy0) -
+                                                     16ll * ey[q] * (long long)(ey[q] > 0 ? dx0 : dx1);
+                                any = any && mx >= 0;
+                            }
+                            p.units[u0 + uy * nux + ux] = any ? EhbUnit{k, (unsigned short)dx0, (unsigned short)dy0} : EhbUnit{0xFFFFFFFFu, 0, 0};
+                        }
                     rows = 0;
                 } else {
                     atomicOr(&p.ctr->flags, 4u);   // queues full: this one is drawn inline (slow but complete); its units are void
@@ -713,7 +738,30 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
     if (lane == 31) off[32] = inc;
     const bool anyWide = __any_sync(0xffffffffu, wide && rows > 0);
     __syncwarp();
-    const int nRows = off[32];
+    int nRows = off[32];
+    if (nRows > 32 * EHB_RINLINE && p.batchBlk) {
+        // A heavy batch would make this warp the tail of the launch: it keeps EHB_RINLINE groups of 32 rows and hands
+        // the rest to k_raster_big, which spreads such units over the whole chip (records + row prefix parked in global).
+        const int ngroups = (nRows + 31) >> 5;
+        const int nitems = (ngroups - EHB_RINLINE + EHB_RGROUPS - 1) / EHB_RGROUPS;
+        unsigned slot = 0, u0 = 0;
+        if (lane == 0) { slot = atomicAdd(&p.ctr->nBatchBlk, 1u); u0 = atomicAdd(&p.ctr->nUnits, (unsigned)nitems); }
+        slot = __shfl_sync(0xffffffffu, slot, 0); u0 = __shfl_sync(0xffffffffu, u0, 0);
+        const bool fits = (int)slot < p.batchCap && (int)(u0 + nitems) <= p.unitCap;
+        if (fits) {
+            uint32_t* blk = p.batchBlk + (size_t)slot * EHB_BLK_WORDS;
+#pragma unroll 8
+            for (int k = 0; k < 32; k++) blk[k * 32 + lane] = s_rec[warp][k * 32 + lane];
+            blk[1024 + lane] = (uint32_t)off[lane];
+            if (lane == 0) { blk[1024 + 32] = (uint32_t)nRows; blk[1024 + 33] = anyWide ? 1u : 0u; }
+            for (int i = lane; i < nitems; i += 32)
+                p.units[u0 + i] = EhbUnit{0x80000000u | slot, (unsigned short)(EHB_RINLINE + i * EHB_RGROUPS), (unsigned short)EHB_RGROUPS};
+            nRows = 32 * EHB_RINLINE;
+        } else {   // no room: the units are void and the batch is drawn here
+            for (int i = lane; i < nitems; i += 32)
+                if ((int)(u0 + i) < p.unitCap) p.units[u0 + i] = EhbUnit{0xFFFFFFFFu, 0, 0};
+        }
+    }
     for (int r0 = 0; r0 < nRows; r0 += 32) {
         const int r = r0 + lane;
         int t = -1, dy = 0;
@@ -741,7 +789,7 @@ __device__ __forceinline__ void ehb_build_jobs(const EhbParams& p, int firstWarp
 __global__ void __launch_bounds__(256) ehb_k_raster_big(const __grid_constant__ EhbParams p, int jobBlocks)
 {
     ehb_pdl_enter();
-    __shared__ EhbRec s_rec[8];
+    __shared__ __align__(16) uint32_t s_blk[8][EHB_BLK_WORDS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if ((int)blockIdx.x >= (int)gridDim.x - jobBlocks) {
         // the touch bitmap is final (k_raster has completed): spare CTAs turn it into the job list of the image-space stage
@@ -750,14 +798,44 @@ __global__ void __launch_bounds__(256) ehb_k_raster_big(const __grid_constant__ 
     }
     const int nUnitBlocks = (int)gridDim.x - jobBlocks;
     const int n = min((int)p.ctr->nUnits, p.unitCap);
-    const float xs = 2.f / (float)p.W, xo = 1.f / (float)p.W - 1.f;
-    const float ys = 2.f / (float)p.H, yo = 1.f / (float)p.H - 1.f;
-    EhbRec* rc = &s_rec[warp];
+    const float xs = p.xs, xo = p.xo, ys = p.ys, yo = p.yo;
+    uint32_t* sb = s_blk[warp];
     for (int u = blockIdx.x * 8 + warp; u < n; u += nUnitBlocks * 8) {
         const EhbUnit un = p.units[u];
         if (un.rec == 0xFFFFFFFFu) continue;
         __syncwarp();
-        reinterpret_cast<uint32_t*>(rc)[lane] = reinterpret_cast<const uint32_t*>(p.bigRec + un.rec)[lane];   // 128 B
+        if (un.rec & 0x80000000u) {
+            // rows [32 * dx0, 32 * (dx0 + dy0)) of a parked batch: the same row-group loop as k_raster
+            const uint32_t* blk = p.batchBlk + (size_t)(un.rec & 0x7FFFFFFFu) * EHB_BLK_WORDS;
+#pragma unroll
+            for (int k = 0; k < EHB_BLK_WORDS / 32; k++) sb[k * 32 + lane] = __ldcg(blk + k * 32 + lane);
+            __syncwarp();
+            const int* off = reinterpret_cast<const int*>(sb + 1024);
+            const int nRows = off[32];
+            const bool anyWide = off[33] != 0;
+            const EhbRecSoA recs{sb};
+            for (int gi = 0; gi < (int)un.dy0; gi++) {
+                const int r0 = ((int)un.dx0 + gi) * 32;
+                if (r0 >= nRows) break;
+                const int r = r0 + lane;
+                int t = -1, dy = 0;
+                if (r < nRows) {
+                    int lo = 0, hi = 32;   // last t with off[t] <= r
+#pragma unroll
+                    for (int st = 0; st < 5; st++) {
+                        const int mid = (lo + hi) >> 1;
+                        if (off[mid] <= r) lo = mid; else hi = mid;
+                    }
+                    t = lo; dy = r - off[t];
+                }
+                if (anyWide) ehb_rows_group<long long, double, EhbRecSoA>(recs, t, dy, lane, p.pool, xs, xo, ys, yo);
+                else ehb_rows_group<int, float, EhbRecSoA>(recs, t, dy, lane, p.pool, xs, xo, ys, yo);
+            }
+            continue;
+        }
+        // a 64 x 32 window of one deferred triangle
+        EhbRec* rc = reinterpret_cast<EhbRec*>(sb);
+        sb[lane] = reinterpret_cast<const uint32_t*>(p.bigRec + un.rec)[lane];   // 128 B
         __syncwarp();
         const int ext = max(max(abs(rc->ex[0]), abs(rc->ex[1])), max(max(abs(rc->ex[2]), abs(rc->ey[0])), max(abs(rc->ey[1]), abs(rc->ey[2]))));
         const int dy = un.dy0 + lane;
