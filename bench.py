@@ -227,7 +227,7 @@ def run_b200(args):
         step(k)
     flags, nclip = ctx.status()
     assert flags & 1 == 0, "scratch overflow during warm-up"
-    # The step is a fixed launch sequence (two pipelines, fork / join events): capture one CUDA graph per ring slot and
+    # The step is a fixed launch sequence (pipelines forked / joined with events): capture one CUDA graph per ring slot and
     # replay them, so that the timed loop is not bound by the host's launch rate.  EHB_BENCH_NOGRAPH=1 keeps eager launches.
     graphs, launches_per_step = None, None
     if not os.environ.get("EHB_BENCH_NOGRAPH") and (world == 1 or use_peer):
@@ -358,7 +358,7 @@ def run_b200(args):
                            "triangles": F, "vertices": V,
                            "l2": "ring of %d view-sets (%.0f MB of masks+refs) > 126 MB L2" %
                                  (R, R * B * H * W * 8 / 1e6),
-                           "pipelines": int(os.environ.get("EHB_PIPES", "2")),
+                           "pipelines": int(os.environ.get("EHB_PIPES", "3")),
                            "launch": "CUDA graph replay, one graph per ring slot" if graphs is not None else "eager",
                            "collective": collective},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,

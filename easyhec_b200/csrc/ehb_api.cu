@@ -101,7 +101,7 @@ struct Ctx {
     int occ = 4;                      // resident k_tiles CTAs per SM
     int occRaster = 4;                // resident k_raster CTAs per SM (persistent warps)
     int rule = 0;
-    int nPipes = 2;
+    int nPipes = 3;
     std::vector<Mesh> meshes;
     Scratch sc[N_SCRATCH];            // [0, MAX_PIPES): pipelines of a device-pointer call; then one per host-step slot
     cudaStream_t pipeStream[MAX_PIPES] = {};
@@ -318,9 +318,11 @@ int ensure_scratch(Ctx* c, Scratch& sc, int items, int L, int Lp, int H, int W, 
         // Jobs: at most one per (tile, link).  That worst case is reserved while its masks stay under 1 GB; beyond it the
         // list holds poolFactor jobs per tile and grows on the overflow flag, like the plane pool.
         const double worstJobs = (double)items * ntiles * L;
-        const double perTile = worstJobs * EHB_MSZ * 4.0 <= 1e9 ? (double)L : std::min((double)L, std::max(2.0, c->poolFactor));
-        const size_t jobCap = std::max<size_t>(4096, (size_t)((double)items * ntiles * perTile));
-        const size_t pairCap = (size_t)((double)jobCap * 32.0 * std::max(1.0, c->poolFactor / 2.0));
+        const bool tiny = c->poolBudget == 0.0;   // test mode: start from the minimum so that growth is exercised
+        const double perTile = tiny ? std::min((double)L, c->poolFactor)
+                                    : (worstJobs * EHB_MSZ * 4.0 <= 1e9 ? (double)L : std::min((double)L, std::max(2.0, c->poolFactor)));
+        const size_t jobCap = std::max<size_t>(tiny ? 16 : 4096, (size_t)((double)items * ntiles * perTile));
+        const size_t pairCap = (size_t)((double)jobCap * (tiny ? 4.0 : 32.0) * std::max(1.0, c->poolFactor / 2.0));
         if (jobCap > 0x7FFFFFFFull || pairCap > 0x7FFFFFFFull) return fail(EHB_E_ARG, "too many tiles for one launch");
         if ((r = sc.jobs.ensure(jobCap, capturing))) return r;
         if ((r = sc.tileJob0.ensure((size_t)items * ntiles, capturing))) return r;

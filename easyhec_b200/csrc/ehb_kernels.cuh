@@ -15,15 +15,13 @@
 //              lane) get their exactly covered span (float estimate + integer fix-up == testing every sample), and
 //              the warp then shades the covered samples of those rows cooperatively, 32 at a time: z/w from the
 //              unsnapped clip positions, atomicMin (RED.MIN.U64, served by L2) into the plane.  Triangles that are not
-//              small are deferred: record parked in global memory, bbox cut into 64x32 units for k_raster_big.
+//              small are deferred (record parked in global memory, bbox cut into 64x32 units), and a batch with many
+//              rows keeps only its first groups (records + row prefix parked): both go to k_raster_big.
 //              Spare CTAs of the same launch stream the empty tiles (mask = 0, loss += ref^2, float4): the HBM-bound
-//              part of the frame overlaps the latency-bound part instead of preceding it.
-//   k_tiles  : persistent CTAs over the non-empty tiles: per link whose bbox touches the tile: load the 35x35 window
-//              of its plane, 35 row bitmasks -> silhouette pairs by XOR -> blend weights with all lanes busy -> pair
-//              list (triangle, edge, alpha) -> gather into the per-view sum in the reference's order; then
-//              S = min(sum, 1), mask write, (S - ref)^2, g = dL/dsum; the backward walks the pair list, contracts
-//              the analytic vertex gradients with [x y z 1] on the fly, warp-shuffle reduce, fp64 atomicAdd into
-//              d loss / d mvp[item, link].
+//              part of the frame overlaps the instruction-bound part instead of preceding it.
+//   k_raster_big : warps stride over the units (bounded work each, spread over the whole chip); spare CTAs build the
+//              job list of the image-space stage from the touch bitmap.
+// The image-space stage (antialias, compose, loss, backward) is in ehb_tiles.cuh.
 // No intermediate image (rast, colour, antialias work queue, clip-space vertex buffer) is ever written.
 #pragma once
 #include "ehb_device.cuh"
@@ -42,9 +40,12 @@ struct __align__(16) EhbPair {   // one silhouette pixel pair of a job (32 B, wr
     int item, tile, link, entry;   // the job's fields, repeated so that the backward needs no second lookup
 };
 
-struct __align__(16) EhbJob {    // one (tile, link) window that some triangle of the link reaches into
+struct __align__(16) EhbJob {    // one (tile, link) window that some triangle of the link reaches into (48 B)
     int item, tile, link;
     int entry;               // position of the tile in the tile list: its gradient window and first job are indexed by it
+    int x0, y0, w, h;        // the link's depth plane (copied from EhbPlane: the window load needs no second lookup)
+    long long off;
+    long long pad;
 };
 
 struct EhbPlane {            // depth plane of one (item, link): pixels [x0, x0+w) x [y0, y0+h), GL rows
@@ -134,7 +135,11 @@ struct EhbParams {
 __device__ __forceinline__ void ehb_pdl_enter()
 {
 #ifdef EHB_PDL
+#if EHB_PDL == 2
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+    // EHB_PDL == 1: no early trigger -- the dependent grid is released when the CTAs of this one exit, so it never
+    // competes with this grid's own unscheduled CTAs for SM slots; only its launch latency is hidden
     asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
 }

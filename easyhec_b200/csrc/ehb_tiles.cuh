@@ -80,8 +80,10 @@ __device__ __forceinline__ void ehb_build_jobs(const EhbParams& p, int firstWarp
             while (bits) {
                 const int l = __ffs(bits) - 1;
                 bits &= bits - 1;
+                const EhbPlane pl = p.plane[(size_t)item * p.L + l];
                 EhbJob jb;
                 jb.item = item; jb.tile = tile; jb.link = l; jb.entry = (int)e;
+                jb.x0 = pl.x0; jb.y0 = pl.y0; jb.w = pl.w; jb.h = pl.h; jb.off = pl.off; jb.pad = 0;
                 if (j < (unsigned)p.jobCap) p.jobs[j] = jb;
                 j++;
             }
@@ -118,7 +120,8 @@ __global__ void __launch_bounds__(EHB_WWARPS * 32) ehb_k_windows(const __grid_co
         const int tx = jb.tile % p.ntx, ty = jb.tile / p.ntx;
         const int rx0 = tx * EHB_T - hlo, ry0 = ty * EHB_T - hlo;
         const int wcols = EHB_T + hlo + p.hhi, wrows = wcols;   // window size: 34 or 35 (33 for the operator backward)
-        const EhbPlane pl = p.plane[(size_t)item * p.L + l];
+        EhbPlane pl;
+        pl.x0 = jb.x0; pl.y0 = jb.y0; pl.w = jb.w; pl.h = jb.h; pl.off = jb.off;
         const EhbLink& lk = rb.link[l];
         const float4* vc = p.vclip + (size_t)item * p.Vtot + rb.voff[l];
         __syncwarp();   // the previous job of this warp is done with ws
