@@ -1,4 +1,4 @@
-"""Run BASELINE.json's configs 2-4 on one B200 and print one JSON line each (kept under profiles/).
+"""Run BASELINE.json's configs 2-5 on one B200 and print one JSON line each (kept under profiles/).
 
   cfg2  xArm7 links 1-7, 10 views 640x480, RBSolver pose optimisation, 200 Adam iterations (lr 3e-3, wd 5e-4):
         iterations/s of the CUDA-graph PoseSolver and the converged pose error against the generating pose
@@ -7,6 +7,7 @@
   cfg4  space exploration: 256 candidate joint configurations x 4 camera poses, xArm7 base + links 1-7
         (41,096 triangles), 1920x1080, binary render + variance score: candidates/s on ONE GPU (the path shards
         over ranks with one all-gather of the scores)
+  cfg5  resolution (256^2 .. 2048^2) x views (1 .. 128) sweep, Franka-sized robot, fwd+bwd: frames/s, algorithmic GB/s
 """
 import json
 import os
@@ -110,7 +111,45 @@ def cfg4():
             "best_candidate": int(score.argmax()), "score_min_max": [float(score.min()), float(score.max())]}
 
 
+def cfg5(resolutions=(256, 512, 1024, 2048), views=(1, 8, 32, 128)):
+    """Resolution / batch sweep, Franka-sized robot, fused forward + backward: frames/s and algorithmic GB/s
+    (8 H W + 40 V + 24 F bytes per frame) on one GPU.  The scratch pools start from their expected
+    size at the large points; a raised overflow flag grows them and the step is run again (counted in `grows`)."""
+    out = []
+    for res in resolutions:
+        for B in views:
+            H = W = res
+            sc = make_scene(B, H, W, links="franka_like", seed=0)
+            ctx = Context("cuda:0")
+            ids = [ctx.register_mesh(m.vertices, m.faces) for m in sc["meshes"]]
+            L = len(ids)
+            V = sum(len(m.vertices) for m in sc["meshes"]); F = sum(len(m.faces) for m in sc["meshes"])
+            mvp_gt = torch.from_numpy(scene_mvps(sc, H, W)).cuda()
+            mvp = torch.from_numpy(scene_mvps(sc, H, W, perturb_pose(sc["Tc_c2b"], np.random.RandomState(1), 0.03, 3.0))).cuda()
+            ref = ctx.render_binary_batch(ids, mvp_gt, H, W).float()
+            out_t = (torch.empty((B, H, W), device="cuda"), torch.empty(B, dtype=torch.float64, device="cuda"),
+                     torch.empty((B, L, 4, 4), dtype=torch.float64, device="cuda"))
+            grows = 0
+            while True:
+                ctx.render_views_fused(ids, mvp, ref, H, W, backward=True, out=out_t)
+                flags, _ = ctx.status()
+                if not flags & 1:
+                    break
+                ctx.grow_scratch(); grows += 1
+                assert grows < 8
+            n = max(5, min(200, int(2000 / B)))
+            ms = timed(lambda: ctx.render_views_fused(ids, mvp, ref, H, W, backward=True, out=out_t), n)
+            flags, _ = ctx.status()
+            alg = (8 * H * W + 40 * V + 24 * F) * B
+            out.append({"res": res, "views": B, "ms_per_step": round(ms, 4), "frames_per_s": round(B / (ms * 1e-3), 1),
+                        "algorithmic_GBps": round(alg / (ms * 1e-3) / 1e9, 1), "flags": flags, "grows": grows})
+            ctx.close()
+            del ref, out_t, mvp, mvp_gt
+            torch.cuda.empty_cache()
+    return {"config": "cfg5 sweep: Franka-sized robot (132k triangles, 9 links), fwd+bwd, 1 GPU", "points": out}
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["cfg2", "cfg3", "cfg4"]
+    which = sys.argv[1:] or ["cfg2", "cfg3", "cfg4", "cfg5"]
     for w in which:
         print(json.dumps(globals()[w]()), flush=True)
