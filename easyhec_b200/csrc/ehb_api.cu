@@ -308,7 +308,7 @@ int build_robot(Ctx* c, const int* mesh_ids, int L, EhbRobot& rb)
     return EHB_OK;
 }
 
-int ensure_scratch(Ctx* c, Scratch& sc, int items, int L, int Lp, int H, int W, int Vtot, bool capturing)
+int ensure_scratch(Ctx* c, Scratch& sc, int items, int L, int Lp, int H, int W, int Vtot, int Ftot, bool capturing)
 {
     int r;
     if ((r = sc.vclip.ensure((size_t)items * std::max(Vtot, 1), capturing))) return r;
@@ -334,8 +334,10 @@ int ensure_scratch(Ctx* c, Scratch& sc, int items, int L, int Lp, int H, int W, 
     if ((r = sc.tileList.ensure((size_t)items * ntiles, capturing))) return r;
     if ((r = sc.touch.ensure((size_t)items * ntiles, capturing))) return r;
     if ((r = sc.emptyList.ensure((size_t)items * ntiles, capturing))) return r;
-    if ((r = sc.bigRec.ensure((size_t)BIG_CAP, capturing))) return r;
-    if ((r = sc.units.ensure((size_t)UNIT_CAP, capturing))) return r;
+    // queues of deferred triangles: a quarter of the pass's triangles may be parked, four units each on average
+    const size_t bigCap = std::max<size_t>(BIG_CAP, std::min<size_t>((size_t)items * (size_t)std::max(Ftot, 1) / 4, (size_t)1 << 24));
+    if ((r = sc.bigRec.ensure(bigCap, capturing))) return r;
+    if ((r = sc.units.ensure(std::max<size_t>(UNIT_CAP, 4 * bigCap), capturing))) return r;
     if ((r = sc.batchBlk.ensure((size_t)BATCH_CAP * EHB_BLK_WORDS, capturing))) return r;
     // Plane pool: the worst case (every link's bbox is the whole screen) is items * Lp * H * W entries.  That is what is
     // reserved while it stays under POOL_BUDGET (180 GB of HBM: 10 views x 7 links x 1280x720 is 0.5 GB) -- then the
@@ -374,11 +376,11 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
     p.xs = 2.f / (float)W; p.xo = 1.f / (float)W - 1.f; p.ys = 2.f / (float)H; p.yo = 1.f / (float)H - 1.f;
     p.mode = mode; p.rule = c->rule; p.do_bwd = io.do_bwd; p.clamp = io.clamp; p.invB = io.invB;
     const bool capturing = is_capturing(st);
-    if ((r = ensure_scratch(c, sc, items, L, p.Lp, H, W, p.Vtot, capturing))) return r;
+    if ((r = ensure_scratch(c, sc, items, L, p.Lp, H, W, p.Vtot, p.Ftot, capturing))) return r;
     p.mvp = mvp_dev;
     p.vclip = sc.vclip.p; p.vsnap = sc.vsnap.p;
     p.plane = sc.plane.p; p.pool = sc.pool.p; p.poolCap = sc.pool.n;
-    p.tileList = sc.tileList.p; p.emptyList = sc.emptyList.p; p.touch = unionMode ? nullptr : sc.touch.p; p.bigRec = sc.bigRec.p; p.units = sc.units.p; p.bigCap = BIG_CAP; p.unitCap = UNIT_CAP; p.batchBlk = tune_int("EHB_NO_OFFLOAD", 0) ? nullptr : sc.batchBlk.p; p.batchCap = BATCH_CAP; p.ctr = sc.ctr;
+    p.tileList = sc.tileList.p; p.emptyList = sc.emptyList.p; p.touch = unionMode ? nullptr : sc.touch.p; p.bigRec = sc.bigRec.p; p.units = sc.units.p; p.bigCap = (int)sc.bigRec.n; p.unitCap = (int)sc.units.n; p.batchBlk = tune_int("EHB_NO_OFFLOAD", 0) ? nullptr : sc.batchBlk.p; p.batchCap = BATCH_CAP; p.ctr = sc.ctr;
     p.ref = io.ref; p.ref_u8 = io.ref_u8; p.masks = io.masks; p.loss = io.loss; p.gmvp = io.gmvp; p.gpos = io.gpos;
     p.dy = io.dy; p.out_u8 = io.out_u8;
     p.jobs = sc.jobs.p; p.tileJob0 = sc.tileJob0.p; p.pairs = sc.pairs.p; p.maskBuf = sc.maskBuf.p; p.gBuf = sc.gBuf.p;
@@ -545,7 +547,7 @@ int ehb_ctx_reserve(ehb_ctx_t h, int n_items, int n_links, int max_faces, int H,
     const int np = std::max(1, std::min(c->nPipes, n_items));
     for (int k = 0; k < np; k++)   // every pipeline gets its share of the items (and pipeline 0 the whole, for profiling runs)
         if ((r = ensure_scratch(c, c->sc[k], k == 0 ? n_items : (n_items + np - 1) / np, n_links, n_links, H, W,
-                                std::max(1, max_faces), false)))   // V <= 3 F
+                                std::max(1, max_faces), std::max(1, max_faces), false)))   // V <= 3 F
             return r;
     if ((r = c->mvpDev.ensure((size_t)n_items * n_links * 16, false))) return r;
     if ((r = c->outDev.ensure((size_t)n_items * (1 + n_links * 16), false))) return r;

@@ -146,6 +146,6 @@ class PoseSolver:
         """(translation error in metres, rotation error in degrees) against a ground-truth pose."""
         T = self.Tc_c2b().double().numpy()
         G = np.asarray(gt_Tc_c2b, dtype=np.float64)
-        dR = T[:3, :3].T @ G[:3, :3]
-        ang = np.degrees(np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1)))
+        # ||R_T - R_G||_F = 2 sqrt(2) sin(angle / 2): well conditioned near zero, unlike arccos((trace - 1) / 2)
+        ang = np.degrees(2.0 * np.arcsin(min(1.0, np.linalg.norm(T[:3, :3] - G[:3, :3]) / (2.0 * np.sqrt(2.0)))))
         return float(np.linalg.norm(T[:3, 3] - G[:3, 3])), float(ang)
