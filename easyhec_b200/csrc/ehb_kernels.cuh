@@ -433,36 +433,35 @@ struct __align__(16) EhbRec {
 __device__ __forceinline__ float ehb_fast_div(float a, float b) { return __fdividef(a, b); }
 __device__ __forceinline__ double ehb_fast_div(double a, double b) { return a / b; }
 
+__device__ __forceinline__ int ehb_floor_to_int(float x) { return __float2int_rd(x); }
+__device__ __forceinline__ int ehb_floor_to_int(double x) { return __double2int_rd(x); }
+
 // Exact span of covered samples in one row of a triangle's clipped bbox.  Edge k along the row is
 // C_k(dx) = R_k + ax_k * dx (threshold folded in: covered <=> C_k >= 0 for all k), monotone in dx, so the
-// covered set is an interval [lo, hi].  Each bound is estimated with one float division and then fixed up with
-// exact integer evaluations, so the result equals the brute-force test of every sample.
+// covered set is an interval [lo, hi] (empty when lo > hi).  With a = |ax|:  ax < 0 bounds dx <= floor(R / a),
+// ax > 0 bounds dx >= ceil(-R / a) = -floor(R / a), ax == 0 is all or nothing.  floor(R / a) is estimated with one
+// float division (within 0.004 of the quotient for |quotient| <= w + 1 <= 8193; clamped beyond, where either answer
+// lies outside the row) and fixed up with one exact integer remainder, so the result equals the brute-force test of
+// every sample.  No branch depends on the edge's orientation: the lanes of a warp hold rows of different triangles.
 template <typename I, typename F>
 __device__ __forceinline__ void ehb_row_span(const I R0, const I R1, const I R2, const I ax0, const I ax1, const I ax2,
                                              int w, int& lo, int& hi)
 {
     lo = 0; hi = w - 1;
     const I R[3] = {R0, R1, R2}, ax[3] = {ax0, ax1, ax2};
+    const F lim = (F)(w + 1);
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        if (ax[k] > 0) {
-            if (R[k] < 0) {   // smallest dx with R + ax*dx >= 0
-                int q = (int)fmin((F)w, ceil(ehb_fast_div((F)(-R[k]), (F)ax[k])));
-                q = max(q, 0);
-                // the estimate is within 1e-3 of the true quotient (|q| <= w <= 8192), so one exact step fixes it
-                if (q > 0 && R[k] + ax[k] * (I)(q - 1) >= 0) q--;
-                else if (q < w && R[k] + ax[k] * (I)q < 0) q++;
-                lo = max(lo, q);
-            }
-        } else if (ax[k] < 0) {
-            if (R[k] < 0) hi = -1;
-            else {            // largest dx with R + ax*dx >= 0
-                int q = (int)fmin((F)(w - 1), floor(ehb_fast_div((F)R[k], (F)(-ax[k]))));
-                if (q < w - 1 && R[k] + ax[k] * (I)(q + 1) >= 0) q++;
-                else if (q >= 0 && R[k] + ax[k] * (I)q < 0) q--;
-                hi = min(hi, q);
-            }
-        } else if (R[k] < 0) hi = -1;
+        const I a = ax[k] < 0 ? -ax[k] : ax[k];
+        const I a1 = a > 0 ? a : (I)1;
+        F q = ehb_fast_div((F)R[k], (F)a1);
+        q = fmin(fmax(q, -lim), lim);
+        int fl = ehb_floor_to_int(q);
+        const I rem = R[k] - a1 * (I)fl;
+        fl += (rem >= a1 ? 1 : 0) - (rem < 0 ? 1 : 0);
+        const int hik = ax[k] < 0 ? fl : ((ax[k] == 0 && R[k] < 0) ? -1 : w - 1);
+        const int lok = ax[k] > 0 ? -fl : 0;
+        hi = min(hi, hik); lo = max(lo, lok);
     }
 }
 

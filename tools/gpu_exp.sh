@@ -14,10 +14,9 @@ echo "== default"; timeout 300 python bench.py --steps 1000 --no-cpu 2>&1 | summ
 for V in $2; do
   echo "== $V"; EHB_LIB=$PWD/easyhec_b200/libehb_$V.so timeout 300 python bench.py --steps 1000 --no-cpu 2>&1 | summ
 done
-echo "== pipes 3"; EHB_PIPES=3 timeout 300 python bench.py --steps 1000 --no-cpu 2>&1 | summ
-echo "== pipes 1"; EHB_PIPES=1 timeout 300 python bench.py --steps 1000 --no-cpu 2>&1 | summ
+echo "== pipes 2"; EHB_PIPES=2 timeout 300 python bench.py --steps 1000 --no-cpu 2>&1 | summ
 for K in $3; do
-  EHB_PIPES=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ehb_k_$K\$ -s 14 -c 1 -f -o $O/$K \
+  EHB_PIPES=1 EHB_BENCH_NOGRAPH=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ehb_k_$K\$ -s 14 -c 1 -f -o $O/$K \
     python bench.py --steps 4 --warmup 3 --no-cpu > $O/ncu_$K.log 2>&1
 done
 ls -la $O
