@@ -83,7 +83,7 @@ struct Scratch {
     DevBuf<EhbUnit> units;
     DevBuf<uint32_t> batchBlk;        // parked heavy batches of k_raster
     DevBuf<EhbJob> jobs;              // image-space stage: (tile, link) windows ...
-    DevBuf<uint32_t> tileJob0;
+    DevBuf<uint4> tileEnt;
     DevBuf<EhbPair> pairs;            // ... their silhouette pairs ...
     DevBuf<float> maskBuf, gBuf;      // ... per-job antialiased masks and per-tile gradient windows
     EhbCounters* ctr = nullptr;
@@ -91,7 +91,7 @@ struct Scratch {
     {
         vclip.release(); vsnap.release(); plane.release(); pool.release(); tileList.release(); emptyList.release();
         touch.release(); bigRec.release(); units.release(); batchBlk.release();
-        jobs.release(); tileJob0.release(); pairs.release(); maskBuf.release(); gBuf.release();
+        jobs.release(); tileEnt.release(); pairs.release(); maskBuf.release(); gBuf.release();
     }
 };
 
@@ -325,7 +325,7 @@ int ensure_scratch(Ctx* c, Scratch& sc, int items, int L, int Lp, int H, int W, 
         const size_t pairCap = (size_t)((double)jobCap * (tiny ? 4.0 : 32.0) * std::max(1.0, c->poolFactor / 2.0));
         if (jobCap > 0x7FFFFFFFull || pairCap > 0x7FFFFFFFull) return fail(EHB_E_ARG, "too many tiles for one launch");
         if ((r = sc.jobs.ensure(jobCap, capturing))) return r;
-        if ((r = sc.tileJob0.ensure((size_t)items * ntiles, capturing))) return r;
+        if ((r = sc.tileEnt.ensure((size_t)items * ntiles, capturing))) return r;
         if ((r = sc.pairs.ensure(pairCap, capturing))) return r;
         if ((r = sc.maskBuf.ensure(jobCap * EHB_MSZ, capturing))) return r;
         if ((r = sc.gBuf.ensure((size_t)items * ntiles * EHB_MSZ, capturing))) return r;
@@ -383,7 +383,7 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
     p.tileList = sc.tileList.p; p.emptyList = sc.emptyList.p; p.touch = unionMode ? nullptr : sc.touch.p; p.bigRec = sc.bigRec.p; p.units = sc.units.p; p.bigCap = (int)sc.bigRec.n; p.unitCap = (int)sc.units.n; p.batchBlk = tune_int("EHB_NO_OFFLOAD", 0) ? nullptr : sc.batchBlk.p; p.batchCap = BATCH_CAP; p.ctr = sc.ctr;
     p.ref = io.ref; p.ref_u8 = io.ref_u8; p.masks = io.masks; p.loss = io.loss; p.gmvp = io.gmvp; p.gpos = io.gpos;
     p.dy = io.dy; p.out_u8 = io.out_u8;
-    p.jobs = sc.jobs.p; p.tileJob0 = sc.tileJob0.p; p.pairs = sc.pairs.p; p.maskBuf = sc.maskBuf.p; p.gBuf = sc.gBuf.p;
+    p.jobs = sc.jobs.p; p.tileEnt = sc.tileEnt.p; p.pairs = sc.pairs.p; p.maskBuf = sc.maskBuf.p; p.gBuf = sc.gBuf.p;
     p.jobCap = (int)sc.jobs.n; p.pairCap = (int)sc.pairs.n;
     p.dbgbuf = c->dbgbuf;
 

@@ -115,7 +115,7 @@ struct EhbParams {
     const float* dy;         // [items, H, W]  AA_BWD
     uint8_t* out_u8;         // [items, H, W]  UNION
     EhbJob* jobs;            // [jobCap]  (tile, link) windows, the jobs of a tile consecutive and in link order
-    uint32_t* tileJob0;      // [items * ntiles]  first job of each listed tile (by list position)
+    uint4* tileEnt;          // [items * ntiles]  per listed tile (by list position): {tile id, link bits, first job, -}
     EhbPair* pairs;          // [pairCap] silhouette pairs, the pairs of a job consecutive
     float* maskBuf;          // [jobCap, 33, 36]  antialiased mask of each job's out region
     float* gBuf;             // [items * ntiles, 33, 36]  dL/dsum of each listed tile's out region
@@ -742,14 +742,35 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
     if (lane == 31) off[32] = inc;
     const bool anyWide = __any_sync(0xffffffffu, wide && rows > 0);
     __syncwarp();
-    int nRows = off[32];
-    if (nRows > 32 * EHB_RINLINE && p.batchBlk) {
-        // A heavy batch would make this warp the tail of the launch: it keeps EHB_RINLINE groups of 32 rows and hands
-        // the rest to k_raster_big, which spreads such units over the whole chip (records + row prefix parked in global).
-        const int ngroups = (nRows + 31) >> 5;
-        const int nitems = (ngroups - EHB_RINLINE + EHB_RGROUPS - 1) / EHB_RGROUPS;
-        unsigned slot = 0, u0 = 0;
-        if (lane == 0) { slot = atomicAdd(&p.ctr->nBatchBlk, 1u); u0 = atomicAdd(&p.ctr->nUnits, (unsigned)nitems); }
+    const int nRowsAll = off[32];
+    // A heavy batch would make this warp the tail of the launch: it keeps EHB_RINLINE groups of 32 rows and hands the
+    // rest to k_raster_big, which spreads such units over the whole chip (records + row prefix parked in global).  The
+    // queue tickets are drawn before the inline groups and used after them, so nothing waits for the atomics.
+    const bool heavy = nRowsAll > 32 * EHB_RINLINE && p.batchBlk != nullptr;
+    const int ngroups = (nRowsAll + 31) >> 5;
+    const int nitems = heavy ? (ngroups - EHB_RINLINE + EHB_RGROUPS - 1) / EHB_RGROUPS : 0;
+    unsigned slot = 0, u0 = 0;
+    if (heavy && lane == 0) { slot = atomicAdd(&p.ctr->nBatchBlk, 1u); u0 = atomicAdd(&p.ctr->nUnits, (unsigned)nitems); }
+    const int nInline = heavy ? 32 * EHB_RINLINE : nRowsAll;
+    auto draw_rows = [&](int rBegin, int rEnd) {
+        for (int r0 = rBegin; r0 < rEnd; r0 += 32) {
+            const int r = r0 + lane;
+            int t = -1, dy = 0;
+            if (r < rEnd) {
+                int lo = 0, hi = 32;   // last t with off[t] <= r
+#pragma unroll
+                for (int st = 0; st < 5; st++) {
+                    const int mid = (lo + hi) >> 1;
+                    if (off[mid] <= r) lo = mid; else hi = mid;
+                }
+                t = lo; dy = r - off[t];
+            }
+            if (anyWide) ehb_rows_group<long long, double, EhbRecSoA>(recs, t, dy, lane, p.pool, xs, xo, ys, yo);
+            else ehb_rows_group<int, float, EhbRecSoA>(recs, t, dy, lane, p.pool, xs, xo, ys, yo);
+        }
+    };
+    draw_rows(0, nInline);
+    if (heavy) {
         slot = __shfl_sync(0xffffffffu, slot, 0); u0 = __shfl_sync(0xffffffffu, u0, 0);
         const bool fits = (int)slot < p.batchCap && (int)(u0 + nitems) <= p.unitCap;
         if (fits) {
@@ -757,29 +778,14 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
 #pragma unroll 8
             for (int k = 0; k < 32; k++) blk[k * 32 + lane] = s_rec[warp][k * 32 + lane];
             blk[1024 + lane] = (uint32_t)off[lane];
-            if (lane == 0) { blk[1024 + 32] = (uint32_t)nRows; blk[1024 + 33] = anyWide ? 1u : 0u; }
+            if (lane == 0) { blk[1024 + 32] = (uint32_t)nRowsAll; blk[1024 + 33] = anyWide ? 1u : 0u; }
             for (int i = lane; i < nitems; i += 32)
                 p.units[u0 + i] = EhbUnit{0x80000000u | slot, (unsigned short)(EHB_RINLINE + i * EHB_RGROUPS), (unsigned short)EHB_RGROUPS};
-            nRows = 32 * EHB_RINLINE;
-        } else {   // no room: the units are void and the batch is drawn here
+        } else {   // no room: the units are void and the rest of the batch is drawn here
             for (int i = lane; i < nitems; i += 32)
                 if ((int)(u0 + i) < p.unitCap) p.units[u0 + i] = EhbUnit{0xFFFFFFFFu, 0, 0};
+            draw_rows(nInline, nRowsAll);
         }
-    }
-    for (int r0 = 0; r0 < nRows; r0 += 32) {
-        const int r = r0 + lane;
-        int t = -1, dy = 0;
-        if (r < nRows) {
-            int lo = 0, hi = 32;   // last t with off[t] <= r
-#pragma unroll
-            for (int st = 0; st < 5; st++) {
-                const int mid = (lo + hi) >> 1;
-                if (off[mid] <= r) lo = mid; else hi = mid;
-            }
-            t = lo; dy = r - off[t];
-        }
-        if (anyWide) ehb_rows_group<long long, double, EhbRecSoA>(recs, t, dy, lane, p.pool, xs, xo, ys, yo);
-        else ehb_rows_group<int, float, EhbRecSoA>(recs, t, dy, lane, p.pool, xs, xo, ys, yo);
     }
     __syncwarp();   // the records of this batch are dead: the next one may overwrite them
     if (++sub == EHB_RBATCH) { sub = 0; bcur = __shfl_sync(0xffffffffu, bnext, 0); }

@@ -74,7 +74,7 @@ __device__ __forceinline__ void ehb_build_jobs(const EhbParams& p, int firstWarp
         base = __shfl_sync(0xffffffffu, base, 0);
         if (e < nEntries) {
             unsigned j = base + (unsigned)(inc - n);
-            p.tileJob0[e] = j;
+            p.tileEnt[e] = make_uint4(wid, bits, j, 0u);
             const int item = (int)(wid / (uint32_t)p.ntiles), tile = (int)(wid - (uint32_t)item * (uint32_t)p.ntiles);
             if (n && j + (unsigned)n > (unsigned)p.jobCap) atomicOr(&p.ctr->flags, 1u);   // job list too small: grow and rerun
             while (bits) {
@@ -113,9 +113,12 @@ __global__ void __launch_bounds__(EHB_WWARPS * 32) ehb_k_windows(const __grid_co
     const bool needAA = p.mode == EHB_MODE_FUSED || p.mode == EHB_MODE_AA_FWD;
     const int oext = (p.mode == EHB_MODE_FUSED && p.do_bwd) ? 1 : 0;
     const int ow = EHB_T + oext;
+    // the first job record is fetched together with the job counter (one L2 round trip instead of two)
+    const unsigned jFirst = blockIdx.x * EHB_WWARPS + warp;
+    const EhbJob jbFirst = p.jobs[min(jFirst, (unsigned)p.jobCap - 1u)];
     const unsigned nJobs = min(p.ctr->nJobs, (unsigned)p.jobCap);
-    for (unsigned j = blockIdx.x * EHB_WWARPS + warp; j < nJobs; j += gridDim.x * EHB_WWARPS) {
-        const EhbJob jb = p.jobs[j];
+    for (unsigned j = jFirst; j < nJobs; j += gridDim.x * EHB_WWARPS) {
+        const EhbJob jb = j == jFirst ? jbFirst : p.jobs[j];
         const int item = jb.item, l = jb.link;
         const int tx = jb.tile % p.ntx, ty = jb.tile / p.ntx;
         const int rx0 = tx * EHB_T - hlo, ry0 = ty * EHB_T - hlo;
@@ -233,15 +236,26 @@ __global__ void __launch_bounds__(EHB_WWARPS * 32) ehb_k_windows(const __grid_co
         const int tot1 = __shfl_sync(0xffffffffu, inc1, 3);
         nPairs = tot0 + tot1;
         const int o0 = inc - cnt[0], o1 = tot0 + inc1 - cnt[1];
-        // the list of this job in the global pair pool
-        unsigned pairOff = 0;
-        if (lane == 0 && nPairs > 0) pairOff = atomicAdd(&p.ctr->pairCursor, (unsigned)nPairs);
-        pairOff = __shfl_sync(0xffffffffu, pairOff, 0);
-        if ((unsigned long long)pairOff + (unsigned long long)nPairs > (unsigned long long)p.pairCap) {
-            if (lane == 0) atomicOr(&p.ctr->flags, 1u);   // pair pool too small: results invalid, grow and rerun
-            nPairs = 0;
+        // The list of this job in the global pair pool.  The ticket is drawn now and used after the blend weights are
+        // known (they only need shared memory), so the atomic's round trip hides behind the weights' own loads; only a
+        // job with more pairs than the shared-memory arrays hold waits for it right away.
+        unsigned ticket = 0;
+        if (lane == 0 && nPairs > 0) ticket = atomicAdd(&p.ctr->pairCursor, (unsigned)nPairs);
+        EhbPair* mine = nullptr;
+        bool resolved = false;
+        auto resolve = [&]() {
+            const unsigned pairOff = __shfl_sync(0xffffffffu, ticket, 0);
+            resolved = true;
+            mine = p.pairs + pairOff;
+            if ((unsigned long long)pairOff + (unsigned long long)nPairs > (unsigned long long)p.pairCap) {
+                if (lane == 0) atomicOr(&p.ctr->flags, 1u);   // pair pool too small: results invalid, grow and rerun
+                mine = nullptr;
+            }
+        };
+        if (nPairs > EHB_WPAIRS) {
+            resolve();
+            if (!mine) nPairs = 0;
         }
-        EhbPair* mine = p.pairs + pairOff;
         if (nPairs > 0) {
 #pragma unroll
             for (int h = 0; h < 2; h++) {
@@ -266,20 +280,37 @@ __global__ void __launch_bounds__(EHB_WWARPS * 32) ehb_k_windows(const __grid_co
         }
         __syncwarp();
         // ================================ blend weights, one pair per lane =====================================
+        auto store_entry = [&](int i, uint32_t pk2, uint32_t t, float al) {
+            uint4* e = reinterpret_cast<uint4*>(mine + i);
+            e[0] = make_uint4(pk2, t, __float_as_uint(al), j);
+            e[1] = make_uint4((uint32_t)item, (uint32_t)jb.tile, (uint32_t)l, (uint32_t)jb.entry);
+        };
+        auto tri_of = [&](uint32_t pk, int& side) -> uint32_t {
+            const int idx = pk & 2047, d = (pk >> 11) & 1;
+            const uint32_t ka = ws.plane[idx], kb = ws.plane[idx + (d ? EHB_RS : 1)];
+            side = ka != 0xFFFFFFFFu ? 0 : 1;
+            return side ? kb : ka;
+        };
         for (int i = lane; i < nPairs; i += 32) {
             const uint32_t pk = i < EHB_WPAIRS ? (uint32_t)ws.pk[i] : __ldcg(&mine[i].packed);
             const int idx = pk & 2047, d = (pk >> 11) & 1;
             const int ly = idx / EHB_RS, lx = idx - ly * EHB_RS;
-            const uint32_t ka = ws.plane[idx], kb = ws.plane[idx + (d ? EHB_RS : 1)];
-            const int side = ka != 0xFFFFFFFFu ? 0 : 1;
-            const uint32_t t = side ? kb : ka;
-            int di;
+            int side, di;
+            const uint32_t t = tri_of(pk, side);
             const float al = ehb_aa_pair(lk, vc, (int)t, side, rx0 + lx, ry0 + ly, d, H, W, &di);
             const uint32_t pk2 = pk | ((uint32_t)side << 13) | ((uint32_t)di << 14);
-            uint4* e = reinterpret_cast<uint4*>(mine + i);
-            e[0] = make_uint4(pk2, t, __float_as_uint(al), j);
-            e[1] = make_uint4((uint32_t)item, (uint32_t)jb.tile, (uint32_t)l, (uint32_t)jb.entry);
+            if (resolved) store_entry(i, pk2, t, al);
             if (i < EHB_WPAIRS) { ws.alpha[i] = al; ws.pk[i] = (unsigned short)(pk2 & 0xFFFFu); }
+        }
+        if (!resolved && nPairs > 0) {   // nPairs <= EHB_WPAIRS: everything is in shared memory; (each lane re-reads its own entries)
+            resolve();
+            if (mine)
+                for (int i = lane; i < nPairs; i += 32) {
+                    const uint32_t pk2 = ws.pk[i];
+                    int side;
+                    const uint32_t t = tri_of(pk2, side);
+                    store_entry(i, pk2, t, ws.alpha[i]);
+                }
         }
         if (!needAA) continue;
         __syncwarp();
@@ -344,8 +375,11 @@ __global__ void __launch_bounds__(EHB_CTHREADS) ehb_k_compose(const __grid_const
     const bool vecOut = p.masks != nullptr && (W & 3) == 0 && (((uintptr_t)p.masks) & 15) == 0;
     const bool vecRef = p.ref != nullptr && (W & 3) == 0 && (((uintptr_t)p.ref) & 15) == 0;
     const bool vecRef8 = p.ref_u8 != nullptr && (W & 7) == 0 && (((uintptr_t)p.ref_u8) & 7) == 0;
-    for (unsigned e = blockIdx.x; e < nEntries; e += gridDim.x) {
-        const uint32_t wid = ehb_list_at(p, e, nHeavy);
+    const unsigned eFirst = blockIdx.x;
+    const uint4 teFirst = p.tileEnt[min(eFirst, (unsigned)(p.items * p.ntiles) - 1u)];   // fetched together with the counters
+    for (unsigned e = eFirst; e < nEntries; e += gridDim.x) {
+        const uint4 te = e == eFirst ? teFirst : p.tileEnt[e];   // {wid, link bits, first job, -}, written by the job builder
+        const uint32_t wid = te.x;
         const int item = (int)(wid / (uint32_t)p.ntiles), tile = (int)(wid - (uint32_t)item * (uint32_t)p.ntiles);
         const int x0 = (tile % p.ntx) * EHB_T, y0 = (tile / p.ntx) * EHB_T;
         const size_t ibase = (size_t)item * H * W;
@@ -358,8 +392,8 @@ __global__ void __launch_bounds__(EHB_CTHREADS) ehb_k_compose(const __grid_const
             }
             continue;
         }
-        const uint32_t bits = p.touch[wid] & (p.L >= 32 ? 0xFFFFFFFFu : ((1u << p.L) - 1u));
-        const unsigned j0 = p.tileJob0[e];
+        const uint32_t bits = te.y;
+        const unsigned j0 = te.z;
         const int nP = min(__popc(bits), (int)max(0ll, (long long)p.jobCap - (long long)j0));   // (overflow: flagged, rerun)
         const float* m0 = p.maskBuf + (size_t)j0 * EHB_MSZ;
         double lacc = 0.0;
@@ -471,7 +505,11 @@ __global__ void __launch_bounds__(256) ehb_k_pairgrad(const __grid_constant__ Eh
             const uint4 e = __ldcg(reinterpret_cast<const uint4*>(p.pairs + i));
             const uint4 jq = __ldcg(reinterpret_cast<const uint4*>(p.pairs + i) + 1);   // item, tile, link, entry
             const float al = __uint_as_float(e.z);
-            if ((e.x & (1u << 12)) && al != 0.f) {
+            // (after a pool overflow -- flagged, the pass is rerun -- the tail of the pool may hold stale entries: never
+            // follow an index that is out of range)
+            const bool sane = jq.x < (unsigned)p.items && jq.y < (unsigned)p.ntiles && jq.z < (unsigned)p.L &&
+                              jq.w < (unsigned)(p.items * p.ntiles) && e.y < (unsigned)rb.link[min(jq.z, (unsigned)p.L - 1u)].F;
+            if (sane && (e.x & (1u << 12)) && al != 0.f) {
                 const int jitem = (int)jq.x, jtile = (int)jq.y, jlink = (int)jq.z, jentry = (int)jq.w;
                 const int idx = e.x & 2047, d = (e.x >> 11) & 1, side = (e.x >> 13) & 1, di = (e.x >> 14) & 3;
                 const int idx1 = idx + (d ? EHB_RS : 1);
