@@ -78,10 +78,11 @@ EHB_API int ehb_ctx_grow_scratch(ehb_ctx_t ctx);
  * the last query, and their number. */
 EHB_API int ehb_ctx_profile(ehb_ctx_t ctx, int enable);
 EHB_API int ehb_ctx_kernel_times(ehb_ctx_t ctx, double* ms4, long long* n_passes);
-/* Developer aid: 16 raw 64-bit counters that builds with -DEHB_TIMING fill (cycles per phase of the tile kernel). */
+/* Per-kernel timing covers the stages {table, front, raster (+ raster_big), tiles (= windows + compose + pairgrad)}. */
+/* Developer aid: 16 raw 64-bit scratch counters of the first pipeline (zero unless a debug build fills them). */
 EHB_API int ehb_ctx_debug_counters(ehb_ctx_t ctx, unsigned long long* out16, int reset);
-/* Developer aid (EHB_TIMING builds): first call allocates a per-CTA timeline buffer for the tile kernel, later calls
- * copy up to n_words 64-bit words of it out ({start ns, end ns, tiles, longest tile cycles, links | pairs << 8} per CTA). */
+/* Developer aid: first call allocates a device scratch buffer that debug builds may fill, later calls copy up to
+ * n_words 64-bit words of it out. */
 EHB_API int ehb_ctx_debug_buffer(ehb_ctx_t ctx, unsigned long long* out, int n_words);
 /* Synchronises the device, returns and clears the sticky flags, reports triangles skipped for clipping. */
 EHB_API int ehb_ctx_status(ehb_ctx_t ctx, unsigned* flags, long long* n_need_clip);
