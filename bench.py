@@ -312,19 +312,21 @@ def run_b200(args):
 
     # ---- end to end: host buffers through the C ABI, copies inside the timed region ----------------------
     # every step: H2D of that step's reference masks (u8, what the dataset holds before .float()) and matrices from
-    # pinned host memory, the fused pass, D2H of loss + gradient; two slots so one step's copies overlap the other's
-    # kernels.  Each step's result is complete on the host when its _end returns.
+    # pinned host memory, the fused pass, D2H of loss + gradient; up to four steps in flight so that one step's copies
+    # overlap the others' kernels and the PCIe link never waits for the host.  Each step's result is complete on the host when its _end returns.
     mvp_host = [torch.from_numpy(s["mvp"]).pin_memory() for s in sets]
     ref_host = [r.to(torch.uint8).cpu().pin_memory() for r in ref_dev]
-    loss_host = [torch.empty((B,), dtype=torch.float64).pin_memory() for _ in range(2)]
-    gmvp_host = [torch.empty((B, L, 4, 4), dtype=torch.float64).pin_memory() for _ in range(2)]
+    S = max(2, min(4, int(os.environ.get("EHB_E2E_SLOTS", "4"))))   # steps in flight: the next H2D is always queued
+    loss_host = [torch.empty((B,), dtype=torch.float64).pin_memory() for _ in range(S)]
+    gmvp_host = [torch.empty((B, L, 4, 4), dtype=torch.float64).pin_memory() for _ in range(S)]
 
     def e2e_run(n):
         for k in range(n):
-            ctx.solver_step_begin_u8(k & 1, ids, mvp_host[k % R], ref_host[k % R], H, W, loss_host[k & 1], gmvp_host[k & 1])
-            if k > 0:
-                ctx.solver_step_end((k - 1) & 1)
-        ctx.solver_step_end((n - 1) & 1)
+            ctx.solver_step_begin_u8(k % S, ids, mvp_host[k % R], ref_host[k % R], H, W, loss_host[k % S], gmvp_host[k % S])
+            if k >= S - 1:
+                ctx.solver_step_end((k - S + 1) % S)
+        for k in range(max(n - S + 1, 0), n):
+            ctx.solver_step_end(k % S)
 
     e2e_run(16)
     e2e_steps = min(args.steps, 1000)
@@ -339,7 +341,7 @@ def run_b200(args):
         ms_e2e = float(t.item())
     e2e = {"value": B * e2e_steps * world / (ms_e2e * 1e-3), "unit": "frames/s",
            "h2d_bytes_per_step": int(B * H * W + B * L * 64), "d2h_bytes_per_step": int(8 * B + 128 * B * L + 176),
-           "steps": e2e_steps, "api": "ehb_solver_step_begin_u8 / _end, 2 slots (pinned host masks u8 + mvp in, "
+           "steps": e2e_steps, "api": "ehb_solver_step_begin_u8 / _end, %d slots (pinned host masks u8 + mvp in, " % S +
                                       "loss + g_mvp out, host-visible result every step)"}
 
     if rank == 0:

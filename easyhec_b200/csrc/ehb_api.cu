@@ -68,7 +68,7 @@ struct DevBuf {
 
 constexpr double POOL_BUDGET = 8e9;  // bytes of plane pool per pipeline reserved without asking
 constexpr int MAX_PIPES = 4;
-constexpr int N_SLOTS = 2;      // in-flight host-buffer steps (ehb_solver_step_begin_u8 / _end)
+constexpr int N_SLOTS = 4;      // in-flight host-buffer steps (ehb_solver_step_begin_u8 / _end)
 constexpr int N_SCRATCH = MAX_PIPES + N_SLOTS;
 
 // Scratch of one pipeline.  A call's items are split over up to MAX_PIPES independent pipelines that run on internal

@@ -159,8 +159,8 @@ EHB_API int ehb_pose_backward(ehb_ctx_t ctx, const float* dof_dev, const float* 
 EHB_API int ehb_adam_step(ehb_ctx_t ctx, float* dof_dev, const float* g7_dev, float* state_dev, float lr, float beta1,
                   float beta2, float eps, float weight_decay, float* hist_dev, int hist_cap, void* stream);
 
-/* Asynchronous form of ehb_solver_step_host_u8 with two slots, so that the host<->device copies of one step overlap
- * the kernels of the other: _begin enqueues H2D(mvp, masks) -> fused step -> D2H(loss, g_mvp) on the slot's own
+/* Asynchronous form of ehb_solver_step_host_u8 with four slots (slot = 0..3), so that the host<->device copies of one
+ * step overlap the kernels of the others and the next copy is always queued behind the running one: _begin enqueues H2D(mvp, masks) -> fused step -> D2H(loss, g_mvp) on the slot's own
  * stream and returns; _end waits for that slot (the host buffers must stay valid and pinned until then).
  * _end returns EHB_E_OVERFLOW after growing the scratch if the step has to be submitted again. */
 EHB_API int ehb_solver_step_begin_u8(ehb_ctx_t ctx, int slot, const int* mesh_ids, int L, int B, const float* mvp_host,
