@@ -18,6 +18,7 @@ _lib = None
 
 EHB_FLAG_PAIR_OVERFLOW = 1
 EHB_FLAG_NEEDS_CLIP = 2
+EHB_FLAG_QUEUES_FULL = 4
 
 
 class EhbError(RuntimeError):

@@ -44,6 +44,7 @@ struct Mesh {
     int4* faces = nullptr;
     int4* opp = nullptr;
     float4* boxes = nullptr;          // [2 * nboxes] AABBs of contiguous vertex chunks (device, recomputed with the vertices)
+    float4* fboxes = nullptr;         // [2 * ceil(F/32)] AABBs of the 32-face batches (device, recomputed with the vertices)
     int V = 0, F = 0, nboxes = 0;
     bool live = false;
 };
@@ -206,6 +207,33 @@ __global__ void ehb_k_boxes(const float4* __restrict__ verts, int V, int nb, flo
     }
 }
 
+// AABB of each batch of 32 consecutive faces (one warp per batch, one face per lane)
+__global__ void ehb_k_face_boxes(const float4* __restrict__ verts, int V, const int4* __restrict__ faces, int F,
+                                 float4* __restrict__ fboxes)
+{
+    const int b = blockIdx.x, lane = threadIdx.x, f = b * 32 + lane;
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    if (f < F) {
+        const int4 id = faces[f];
+        const int vi[3] = {id.x, id.y, id.z};
+        for (int k = 0; k < 3; k++)
+            if ((unsigned)vi[k] < (unsigned)V) {   // faces with an invalid index are never drawn
+                const float4 v = verts[vi[k]];
+                lo[0] = fminf(lo[0], v.x); lo[1] = fminf(lo[1], v.y); lo[2] = fminf(lo[2], v.z);
+                hi[0] = fmaxf(hi[0], v.x); hi[1] = fmaxf(hi[1], v.y); hi[2] = fmaxf(hi[2], v.z);
+            }
+    }
+    for (int o = 16; o > 0; o >>= 1)
+        for (int k = 0; k < 3; k++) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+    if (lane == 0) {
+        fboxes[2 * b] = make_float4(lo[0], lo[1], lo[2], 1.f);       // an empty batch keeps lo > hi: culled
+        fboxes[2 * b + 1] = make_float4(hi[0], hi[1], hi[2], 1.f);
+    }
+}
+
 // num[q] += sum over this block's pixels of k (C - k), k = number of cameras whose mask covers the pixel.
 // sum_px unbiased_var_c(mask) = num / (C (C - 1)) exactly, so the reduction is integer and order-free.
 __global__ void __launch_bounds__(256) ehb_k_variance(const uint8_t* __restrict__ masks, int C, long long n,
@@ -300,10 +328,11 @@ int build_robot(Ctx* c, const int* mesh_ids, int L, EhbRobot& rb)
         if (id < 0 || id >= (int)c->meshes.size() || !c->meshes[id].live) return fail(EHB_E_ARG, "unknown mesh id %d", id);
         const Mesh& m = c->meshes[id];
         if (m.F > (int)EHB_FACE_MASK) return fail(EHB_E_ARG, "mesh %d has too many faces", id);
-        rb.link[l].verts = m.verts; rb.link[l].faces = m.faces; rb.link[l].opp = m.opp; rb.link[l].boxes = m.boxes; rb.link[l].nboxes = m.nboxes;
+        rb.link[l].verts = m.verts; rb.link[l].faces = m.faces; rb.link[l].opp = m.opp; rb.link[l].boxes = m.boxes; rb.link[l].nboxes = m.nboxes; rb.link[l].fboxes = m.fboxes;
         rb.link[l].V = m.V; rb.link[l].F = m.F;
         rb.foff[l + 1] = rb.foff[l] + m.F;
         rb.voff[l + 1] = rb.voff[l] + m.V;
+        rb.boff[l + 1] = rb.boff[l] + (m.F + 31) / 32;
     }
     return EHB_OK;
 }
@@ -335,9 +364,12 @@ int ensure_scratch(Ctx* c, Scratch& sc, int items, int L, int Lp, int H, int W, 
     if ((r = sc.touch.ensure((size_t)items * ntiles, capturing))) return r;
     if ((r = sc.emptyList.ensure((size_t)items * ntiles, capturing))) return r;
     // queues of deferred triangles: a quarter of the pass's triangles may be parked, four units each on average
-    const size_t bigCap = std::max<size_t>(BIG_CAP, std::min<size_t>((size_t)items * (size_t)std::max(Ftot, 1) / 4, (size_t)1 << 24));
-    if ((r = sc.bigRec.ensure(bigCap, capturing))) return r;
-    if ((r = sc.units.ensure(std::max<size_t>(UNIT_CAP, 4 * bigCap), capturing))) return r;
+    // (test mode, pool budget 0: queues so small that the inline fallbacks of k_raster run -- slower, same result)
+    const bool tinyQ = c->poolBudget == 0.0;
+    // (capacities are per sub-queue, EHB_NQ of them: a warp's batches go to the sub-queue of its index, so they fill evenly)
+    const size_t bigCap = tinyQ ? 1 : std::max<size_t>(BIG_CAP, std::min<size_t>((size_t)items * (size_t)std::max(Ftot, 1) / 4, (size_t)1 << 24)) / EHB_NQ;
+    if ((r = sc.bigRec.ensure(bigCap * EHB_NQ, capturing))) return r;
+    if ((r = sc.units.ensure((tinyQ ? 4 : std::max<size_t>(UNIT_CAP / EHB_NQ, 4 * bigCap)) * EHB_NQ, capturing))) return r;
     if ((r = sc.batchBlk.ensure((size_t)BATCH_CAP * EHB_BLK_WORDS, capturing))) return r;
     // Plane pool: the worst case (every link's bbox is the whole screen) is items * Lp * H * W entries.  That is what is
     // reserved while it stays under POOL_BUDGET (180 GB of HBM: 10 views x 7 links x 1280x720 is 0.5 GB) -- then the
@@ -380,7 +412,7 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
     p.mvp = mvp_dev;
     p.vclip = sc.vclip.p; p.vsnap = sc.vsnap.p;
     p.plane = sc.plane.p; p.pool = sc.pool.p; p.poolCap = sc.pool.n;
-    p.tileList = sc.tileList.p; p.emptyList = sc.emptyList.p; p.touch = unionMode ? nullptr : sc.touch.p; p.bigRec = sc.bigRec.p; p.units = sc.units.p; p.bigCap = (int)sc.bigRec.n; p.unitCap = (int)sc.units.n; p.batchBlk = tune_int("EHB_NO_OFFLOAD", 0) ? nullptr : sc.batchBlk.p; p.batchCap = BATCH_CAP; p.ctr = sc.ctr;
+    p.tileList = sc.tileList.p; p.emptyList = sc.emptyList.p; p.touch = unionMode ? nullptr : sc.touch.p; p.bigRec = sc.bigRec.p; p.units = sc.units.p; p.bigCap = (int)(sc.bigRec.n / EHB_NQ); p.unitCap = (int)(sc.units.n / EHB_NQ); p.batchBlk = tune_int("EHB_NO_OFFLOAD", 0) ? nullptr : sc.batchBlk.p; p.batchCap = c->poolBudget == 0.0 ? 1 : BATCH_CAP / EHB_NQ; p.ctr = sc.ctr;
     p.ref = io.ref; p.ref_u8 = io.ref_u8; p.masks = io.masks; p.loss = io.loss; p.gmvp = io.gmvp; p.gpos = io.gpos;
     p.dy = io.dy; p.out_u8 = io.out_u8;
     p.jobs = sc.jobs.p; p.tileEnt = sc.tileEnt.p; p.pairs = sc.pairs.p; p.maskBuf = sc.maskBuf.p; p.gBuf = sc.gBuf.p;
@@ -397,7 +429,7 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
         ev = &c->evPool[c->evUsed];
         c->evUsed += 5;
     }
-    const int chunks = std::max(1, (p.Ftot + 31) / 32);   // 32-triangle batches per item, drawn by persistent warps
+    const int chunks = std::max(1, rb.boff[L]);   // 32-triangle batches per item (a batch never straddles two links)
     const int streamBlocks = (unionMode || mode == EHB_MODE_AA_BWD) ? 0 : c->nSM * tune_int("EHB_STREAM_MULT", 2);
     const long long tickets = ((long long)chunks * items + EHB_RBATCH - 1) / EHB_RBATCH;
     long long rasterBlocks = (tickets + EHB_RWARPS - 1) / EHB_RWARPS;
@@ -410,8 +442,8 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
     if (ev) cudaEventRecord(ev[1], st);
     const int vchunks = std::max(1, (p.Vtot + 255) / 256);
     const int clearBlocks = c->nSM;
-    const long long tileWarps = unionMode ? 0 : (long long)items * p.ntiles;
-    CU(launch(ehb_k_front, dim3((unsigned)(vchunks * items + clearBlocks + (tileWarps * 32 + 255) / 256)), dim3(256), 0, st, true, rb, p,
+    const long long tileThreads = unionMode ? 0 : (long long)items * p.ntiles;   // one lane per tile
+    CU(launch(ehb_k_front, dim3((unsigned)(vchunks * items + clearBlocks + (tileThreads + 255) / 256)), dim3(256), 0, st, true, rb, p,
               vchunks, clearBlocks));
     if (ev) cudaEventRecord(ev[2], st);
     CU(launch(ehb_k_raster, dim3((unsigned)(streamBlocks + rasterBlocks)), dim3(EHB_RWARPS * 32), 0, st, true, rb, p, streamBlocks, chunks));
@@ -517,7 +549,7 @@ int ehb_ctx_destroy(ehb_ctx_t h)
     if (!c) return EHB_OK;
     DeviceGuard guard(c->device);
     cudaDeviceSynchronize();
-    for (auto& m : c->meshes) if (m.live) { cudaFree(m.verts); cudaFree(m.faces); cudaFree(m.opp); cudaFree(m.boxes); }
+    for (auto& m : c->meshes) if (m.live) { cudaFree(m.verts); cudaFree(m.faces); cudaFree(m.opp); cudaFree(m.boxes); cudaFree(m.fboxes); }
     for (int k = 0; k < MAX_PIPES; k++) { cudaStreamDestroy(c->pipeStream[k]); cudaEventDestroy(c->evJoin[k]); }
     for (int k = 0; k < N_SCRATCH; k++) c->sc[k].release();
     for (int k = 0; k < N_SLOTS; k++) { cudaStreamDestroy(c->slotStream[k]); cudaEventDestroy(c->slotDone[k]); c->slotMvp[k].release(); c->slotOut[k].release(); c->slotRef[k].release(); }
@@ -669,10 +701,10 @@ int ehb_mesh_register(ehb_ctx_t h, const float* verts, int V, const int* faces, 
     CU(cudaMemcpy(m.opp, opp.data(), opp.size() * sizeof(int4), cudaMemcpyHostToDevice));
     m.nboxes = V > 0 ? std::max(1, std::min(32, (V + 63) / 64)) : 0;
     CU(cudaMalloc((void**)&m.boxes, 2 * 32 * sizeof(float4)));
-    if (m.nboxes > 0) {
-        ehb_k_boxes<<<m.nboxes, 32>>>(m.verts, V, m.nboxes, m.boxes);
-        CU(cudaDeviceSynchronize());
-    }
+    CU(cudaMalloc((void**)&m.fboxes, 2 * (size_t)std::max(1, (F + 31) / 32) * sizeof(float4)));
+    if (m.nboxes > 0) ehb_k_boxes<<<m.nboxes, 32>>>(m.verts, V, m.nboxes, m.boxes);
+    if (F > 0) ehb_k_face_boxes<<<(F + 31) / 32, 32>>>(m.verts, V, m.faces, F, m.fboxes);
+    CU(cudaDeviceSynchronize());
     m.live = true;
     int id = -1;
     for (size_t i = 0; i < c->meshes.size(); i++) if (!c->meshes[i].live) { id = (int)i; break; }
@@ -691,7 +723,8 @@ int ehb_mesh_update_verts(ehb_ctx_t h, int mesh_id, const float* verts_dev, int 
     DeviceGuard guard(c->device);
     ehb_k_pad_verts<<<(V + 255) / 256, 256, 0, (cudaStream_t)stream>>>(verts_dev, m.verts, V);
     ehb_k_boxes<<<m.nboxes, 32, 0, (cudaStream_t)stream>>>(m.verts, V, m.nboxes, m.boxes);
-    c->launches += 2;
+    if (m.F > 0) ehb_k_face_boxes<<<(m.F + 31) / 32, 32, 0, (cudaStream_t)stream>>>(m.verts, V, m.faces, m.F, m.fboxes);
+    c->launches += 3;
     CU(cudaGetLastError());
     return EHB_OK;
 }
@@ -703,7 +736,7 @@ int ehb_mesh_release(ehb_ctx_t h, int mesh_id)
     DeviceGuard guard(c->device);
     CU(cudaDeviceSynchronize());
     Mesh& m = c->meshes[mesh_id];
-    cudaFree(m.verts); cudaFree(m.faces); cudaFree(m.opp); cudaFree(m.boxes);
+    cudaFree(m.verts); cudaFree(m.faces); cudaFree(m.opp); cudaFree(m.boxes); cudaFree(m.fboxes);
     m = Mesh();
     return EHB_OK;
 }

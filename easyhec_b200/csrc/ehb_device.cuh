@@ -21,6 +21,7 @@ struct EhbLink {
     const int4* faces;    // [F]  i0 i1 i2, w unused
     const int4* opp;      // [F]  vertex opposite to edge k in the neighbouring triangle, or -1
     const float4* boxes;  // [2*nboxes] object-space AABBs (min, max) of nboxes contiguous vertex chunks
+    const float4* fboxes; // [2*ceil(F/32)] object-space AABBs of the batches of 32 consecutive faces (k_raster's unit of work)
     int V, F, nboxes, pad;
 };
 
@@ -28,6 +29,7 @@ struct EhbRobot {
     EhbLink link[EHB_MAX_LINKS];
     int foff[EHB_MAX_LINKS + 1];  // prefix sum of F over links
     int voff[EHB_MAX_LINKS + 1];  // prefix sum of V over links
+    int boff[EHB_MAX_LINKS + 1];  // prefix sum of ceil(F / 32) over links: a batch of k_raster never straddles two links
     int L;
 };
 

@@ -70,11 +70,16 @@ struct __align__(128) EhbCounters {
     // line 1: the ticket counter of k_raster's persistent warps, alone on its line (thousands of atomics per pass)
     unsigned int rasterCursor;
     unsigned int pad1[31];
-    // line 2: queues of deferred triangles
-    unsigned int nBigRec;    // deferred (not small) triangles: records parked in global memory ...
-    unsigned int nUnits;     // ... and cut into bounded units that k_raster_big spreads over the whole chip
-    unsigned int nBatchBlk;  // batches with many rows: records parked, the rows beyond the inline share become units too
-    unsigned int pad2[29];
+    unsigned int pad2[32];
+    // lines 4..35: the queues of deferred work, split into EHB_NQ sub-queues with their counters on separate lines --
+    // thousands of same-address atomics per pass would serialise on one L2 line (measured: a third of k_raster's
+    // warp-time waiting for them); a warp uses the sub-queue of its index
+    struct Q {
+        unsigned int nBigRec;    // deferred (not small) triangles: records parked in global memory ...
+        unsigned int nUnits;     // ... and cut into bounded units that k_raster_big spreads over the whole chip
+        unsigned int nBatchBlk;  // batches with many rows: records parked, the rows beyond the inline share become units too
+        unsigned int pad[29];
+    } q[32];
     // line 3: job list and pair pool of the image-space stage
     unsigned int nJobs;
     unsigned int pairCursor;
@@ -102,9 +107,9 @@ struct EhbParams {
     uint32_t* touch;         // [items * ntiles]  bit l: a triangle of link l reaches into this tile's window
     struct EhbRec* bigRec;   // [bigCap]
     EhbUnit* units;          // [unitCap]
-    int bigCap, unitCap;
+    int bigCap, unitCap;     // per sub-queue (the arrays hold EHB_NQ times as many)
     uint32_t* batchBlk;      // [batchCap][EHB_BLK_WORDS] parked batches: 32 records (transposed) + row prefix + flags
-    int batchCap;
+    int batchCap;            // per sub-queue
     EhbCounters* ctr;
     const float* ref;        // [items, H, W]  FUSED
     const uint8_t* ref_u8;   // same, as bytes (either ref or ref_u8)
@@ -126,6 +131,7 @@ struct EhbParams {
 #ifndef EHB_SMALL_AREA
 #define EHB_SMALL_AREA 96               // triangles whose clipped bbox has more candidate samples are deferred
 #endif
+#define EHB_NQ 32
 #define EHB_UNIT_W 64
 #define EHB_UNIT_H 32
 
@@ -180,8 +186,11 @@ __global__ void __launch_bounds__(256) ehb_k_table(const __grid_constant__ EhbRo
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         p.ctr->nTiles = 0u; p.ctr->nLight = 0u; p.ctr->nEmpty = 0u; p.ctr->workCursor = 0u;
-        p.ctr->nBigRec = 0u; p.ctr->nUnits = 0u; p.ctr->rasterCursor = (unsigned)p.rasterStart;
-        p.ctr->nJobs = 0u; p.ctr->pairCursor = 0u; p.ctr->nBatchBlk = 0u;
+        p.ctr->rasterCursor = (unsigned)p.rasterStart;
+        p.ctr->nJobs = 0u; p.ctr->pairCursor = 0u;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < EHB_NQ) {
+        p.ctr->q[threadIdx.x].nBigRec = 0u; p.ctr->q[threadIdx.x].nUnits = 0u; p.ctr->q[threadIdx.x].nBatchBlk = 0u;
     }
     // outputs that the later kernels accumulate into
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.items; i += gridDim.x * blockDim.x) {
@@ -379,27 +388,36 @@ __global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRo
             for (int i = cb * blockDim.x + threadIdx.x; i < p.items * p.ntiles; i += clearBlocks * blockDim.x) p.touch[i] = 0u;
         return;
     }
-    const int wid = ((cb - clearBlocks) * blockDim.x + threadIdx.x) >> 5;
+    // (c) one LANE per tile; the three list counters get one atomic per warp each (a tile per warp meant ten thousand
+    // same-address atomics per pass, which serialise on their L2 line)
+    const int wid = (cb - clearBlocks) * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    if (wid >= p.items * p.ntiles) return;
-    const int item = wid / p.ntiles, tile = wid - item * p.ntiles;
-    const int tx = tile % p.ntx, ty = tile / p.ntx;
-    bool hit = false;
-    if (lane < p.Lp) {
-        const EhbPlane pl = p.plane[(size_t)item * p.Lp + lane];
+    const bool valid = wid < p.items * p.ntiles;
+    int nhit = 0;
+    if (valid) {
+        const int item = wid / p.ntiles, tile = wid - item * p.ntiles;
+        const int tx = tile % p.ntx, ty = tile / p.ntx;
         const int rx0 = tx * EHB_T - p.hlo, ry0 = ty * EHB_T - p.hlo;
         const int rx1 = tx * EHB_T + EHB_T - 1 + p.hhi, ry1 = ty * EHB_T + EHB_T - 1 + p.hhi;
-        hit = pl.w > 0 && pl.x0 <= rx1 && pl.x0 + pl.w - 1 >= rx0 && pl.y0 <= ry1 && pl.y0 + pl.h - 1 >= ry0;
+        for (int l = 0; l < p.Lp; l++) {
+            const int4 pl = *reinterpret_cast<const int4*>(&p.plane[(size_t)item * p.Lp + l]);   // x0, y0, w, h
+            nhit += pl.z > 0 && pl.x <= rx1 && pl.x + pl.z - 1 >= rx0 && pl.y <= ry1 && pl.y + pl.w - 1 >= ry0;
+        }
     }
-    const unsigned hits = __ballot_sync(0xffffffffu, hit);
-    if (lane != 0) return;
-    if (hits) {
-        // tiles with several links take several times longer in k_tiles: queue them first (front), the rest from the back
-        if (__popc(hits) >= 2) p.tileList[atomicAdd(&p.ctr->nTiles, 1u)] = (uint32_t)wid;
-        else p.tileList[(unsigned)(p.items * p.ntiles) - 1u - atomicAdd(&p.ctr->nLight, 1u)] = (uint32_t)wid;
-    } else if (p.mode != EHB_MODE_AA_BWD) {
-        p.emptyList[atomicAdd(&p.ctr->nEmpty, 1u)] = (uint32_t)wid;
+    // tiles with several links take several times longer downstream: listed first (front), the rest from the back
+    const bool heavy = valid && nhit >= 2, light = valid && nhit == 1, empty = valid && nhit == 0 && p.mode != EHB_MODE_AA_BWD;
+    const unsigned bh = __ballot_sync(0xffffffffu, heavy), bl = __ballot_sync(0xffffffffu, light), be = __ballot_sync(0xffffffffu, empty);
+    unsigned baseH = 0, baseL = 0, baseE = 0;
+    if (lane == 0) {
+        if (bh) baseH = atomicAdd(&p.ctr->nTiles, (unsigned)__popc(bh));
+        if (bl) baseL = atomicAdd(&p.ctr->nLight, (unsigned)__popc(bl));
+        if (be) baseE = atomicAdd(&p.ctr->nEmpty, (unsigned)__popc(be));
     }
+    baseH = __shfl_sync(0xffffffffu, baseH, 0); baseL = __shfl_sync(0xffffffffu, baseL, 0); baseE = __shfl_sync(0xffffffffu, baseE, 0);
+    const unsigned below = (1u << lane) - 1u;
+    if (heavy) p.tileList[baseH + __popc(bh & below)] = (uint32_t)wid;
+    else if (light) p.tileList[(unsigned)(p.items * p.ntiles) - 1u - (baseL + __popc(bl & below))] = (uint32_t)wid;
+    else if (empty) p.emptyList[baseE + __popc(be & below)] = (uint32_t)wid;
 }
 
 // ------------------------------------------------------------------------------------------------ k_raster
@@ -500,12 +518,9 @@ __device__ __forceinline__ void ehb_rec_store_soa(uint32_t* b, int t, const EhbR
 
 // Primitive assembly of one triangle from the pre-transformed vertices -> record.  Same tests, in the same order,
 // as ehb_tri_setup (the oracle's eho_rasterize).  Returns the number of rows of its clipped bbox (0: nothing to draw).
-__device__ __forceinline__ int ehb_make_record(const EhbRobot& rb, const EhbParams& p, int item, int g, EhbRec& rc,
-                                               int& link_out)
+__device__ __forceinline__ int ehb_make_record(const EhbRobot& rb, const EhbParams& p, int item, int l, int f, EhbRec& rc)
 {
-    const int l = ehb_find_link(rb.foff, rb.L, g);
-    link_out = l;
-    const int f = g - rb.foff[l];
+    const int g = rb.foff[l] + f;
     const EhbLink& lk = rb.link[l];
     const int4 id = __ldg(lk.faces + f);
     const EhbPlane pl = p.plane[(size_t)item * p.Lp + (p.Lp == 1 ? 0 : l)];   // depends on the link only: issued with the face
@@ -640,14 +655,39 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
 #ifdef EHB_RPERSIST
     if (lane == 0 && sub == EHB_RBATCH - 1) bnext = atomicAdd(&p.ctr->rasterCursor, (unsigned)EHB_RBATCH);
 #endif
+    const int qi = (int)(bcur & (EHB_NQ - 1));            // this batch's sub-queue
+    EhbCounters::Q& myq = p.ctr->q[qi];
     const int item = (int)bcur / chunks;
-    const int g = ((int)bcur - item * chunks) * 32 + lane;
-    int rows = 0, wide = 0, link = 0, touchRows = 0;
+    const int bl = (int)bcur - item * chunks;             // batch of the item: 32 consecutive faces of ONE link
+    const int link = ehb_find_link(rb.boff, rb.L, bl);    // (warp-uniform)
+    const int f = (bl - rb.boff[link]) * 32 + lane;
+    int rows = 0, wide = 0, touchRows = 0;
     bool big = false;
     int4 tb = make_int4(0, 0, 0, 0);   // clipped bbox of this lane's triangle (x0, y0, w, h)
-    if (g < p.Ftot) {
+    // Frustum cull of the whole batch: the 8 corners of its object-space AABB, one per lane.  When every corner is in
+    // front of the camera and all of them lie beyond one side of the screen (two pixels of margin for snapping and
+    // rounding), every vertex of the batch does too (projection keeps convex hulls when w > 0), so each of its triangles
+    // would fail the per-triangle tests: nothing to load, nothing to set up.
+    bool visible = true;
+    {
+        const float4* fb = rb.link[link].fboxes + 2 * (bl - rb.boff[link]);
+        const float4 lo = __ldg(fb), hi = __ldg(fb + 1);
+        float m[16], c[4];
+        ehb_load_mvp(p.mvp + ((size_t)item * p.L + link) * 16, m);
+        const int k = lane & 7;
+        ehb_xform(make_float4((k & 1) ? hi.x : lo.x, (k & 2) ? hi.y : lo.y, (k & 4) ? hi.z : lo.z, 1.f), m, c);
+        const bool front = c[3] > 1e-6f;
+        const float mx = 4.f / (float)p.W, my = 4.f / (float)p.H;
+        const float xr = c[0] - (1.f + mx) * c[3], xl = -c[0] - (1.f + mx) * c[3];   // > 0: beyond the right / left side
+        const float yt = c[1] - (1.f + my) * c[3], yb = -c[1] - (1.f + my) * c[3];
+        const bool allFront = __all_sync(0xffffffffu, front);
+        const bool out = __all_sync(0xffffffffu, xr > 0.f) || __all_sync(0xffffffffu, xl > 0.f) ||
+                         __all_sync(0xffffffffu, yt > 0.f) || __all_sync(0xffffffffu, yb > 0.f);
+        visible = !(allFront && out) && !(lo.x > hi.x);
+    }
+    if (visible && f < rb.link[link].F) {
         EhbRec rc;
-        rows = ehb_make_record(rb, p, item, g, rc, link);
+        rows = ehb_make_record(rb, p, item, link, f, rc);
         touchRows = rows;
         if (rows > 0) tb = make_int4(rc.x0, rc.y0, rc.w, rc.h);
         if (rows > 0) {
@@ -670,11 +710,13 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
             }
             const int utot = __shfl_sync(0xffffffffu, uinc, 31);
             unsigned k0 = 0, ub = 0;
-            if (lane == 0) { k0 = atomicAdd(&p.ctr->nBigRec, (unsigned)__popc(bm)); ub = atomicAdd(&p.ctr->nUnits, (unsigned)utot); }
+            if (lane == 0) { k0 = atomicAdd(&myq.nBigRec, (unsigned)__popc(bm)); ub = atomicAdd(&myq.nUnits, (unsigned)utot); }
             k0 = __shfl_sync(0xffffffffu, k0, 0); ub = __shfl_sync(0xffffffffu, ub, 0);
-            const unsigned k = k0 + (unsigned)__popc(bm & ((1u << lane) - 1u));
-            const unsigned u0 = ub + (unsigned)(uinc - nu);
-            const bool fits = (int)k < p.bigCap && (int)(u0 + nu) <= p.unitCap;
+            const unsigned kq = k0 + (unsigned)__popc(bm & ((1u << lane) - 1u));   // index in the sub-queue
+            const unsigned uq = ub + (unsigned)(uinc - nu);
+            const bool fits = (int)kq < p.bigCap && (int)(uq + nu) <= p.unitCap;
+            const unsigned k = (unsigned)qi * (unsigned)p.bigCap + kq;             // index in the arrays
+            const unsigned u0 = (unsigned)qi * (unsigned)p.unitCap + uq;
             if (big) {
                 if (fits) {
                     // A window of the bbox that lies entirely outside one edge (the edge function's maximum over the
@@ -698,7 +740,7 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
                     rows = 0;
                 } else {
                     atomicOr(&p.ctr->flags, 4u);   // queues full: this one is drawn inline (slow but complete); its units are void
-                    for (int i = 0; i < nu && (int)(u0 + i) < p.unitCap; i++) p.units[u0 + i] = EhbUnit{0xFFFFFFFFu, 0, 0};
+                    for (int i = 0; i < nu && (int)(uq + i) < p.unitCap; i++) p.units[u0 + i] = EhbUnit{0xFFFFFFFFu, 0, 0};
                 }
             }
             __syncwarp();
@@ -750,7 +792,7 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
     const int ngroups = (nRowsAll + 31) >> 5;
     const int nitems = heavy ? (ngroups - EHB_RINLINE + EHB_RGROUPS - 1) / EHB_RGROUPS : 0;
     unsigned slot = 0, u0 = 0;
-    if (heavy && lane == 0) { slot = atomicAdd(&p.ctr->nBatchBlk, 1u); u0 = atomicAdd(&p.ctr->nUnits, (unsigned)nitems); }
+    if (heavy && lane == 0) { slot = atomicAdd(&myq.nBatchBlk, 1u); u0 = atomicAdd(&myq.nUnits, (unsigned)nitems); }
     const int nInline = heavy ? 32 * EHB_RINLINE : nRowsAll;
     auto draw_rows = [&](int rBegin, int rEnd) {
         for (int r0 = rBegin; r0 < rEnd; r0 += 32) {
@@ -773,6 +815,8 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
     if (heavy) {
         slot = __shfl_sync(0xffffffffu, slot, 0); u0 = __shfl_sync(0xffffffffu, u0, 0);
         const bool fits = (int)slot < p.batchCap && (int)(u0 + nitems) <= p.unitCap;
+        const unsigned uBase = (unsigned)qi * (unsigned)p.unitCap + u0;
+        slot += (unsigned)qi * (unsigned)p.batchCap;
         if (fits) {
             uint32_t* blk = p.batchBlk + (size_t)slot * EHB_BLK_WORDS;
 #pragma unroll 8
@@ -780,10 +824,10 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
             blk[1024 + lane] = (uint32_t)off[lane];
             if (lane == 0) { blk[1024 + 32] = (uint32_t)nRowsAll; blk[1024 + 33] = anyWide ? 1u : 0u; }
             for (int i = lane; i < nitems; i += 32)
-                p.units[u0 + i] = EhbUnit{0x80000000u | slot, (unsigned short)(EHB_RINLINE + i * EHB_RGROUPS), (unsigned short)EHB_RGROUPS};
+                p.units[uBase + i] = EhbUnit{0x80000000u | slot, (unsigned short)(EHB_RINLINE + i * EHB_RGROUPS), (unsigned short)EHB_RGROUPS};
         } else {   // no room: the units are void and the rest of the batch is drawn here
             for (int i = lane; i < nitems; i += 32)
-                if ((int)(u0 + i) < p.unitCap) p.units[u0 + i] = EhbUnit{0xFFFFFFFFu, 0, 0};
+                if ((int)(u0 + i) < p.unitCap) p.units[uBase + i] = EhbUnit{0xFFFFFFFFu, 0, 0};
             draw_rows(nInline, nRowsAll);
         }
     }
@@ -807,11 +851,26 @@ __global__ void __launch_bounds__(256) ehb_k_raster_big(const __grid_constant__ 
         return;
     }
     const int nUnitBlocks = (int)gridDim.x - jobBlocks;
-    const int n = min((int)p.ctr->nUnits, p.unitCap);
+    // units of all sub-queues as one list: lane s holds the (inclusive) prefix of the sub-queue sizes
+    int qn = min((int)p.ctr->q[lane].nUnits, p.unitCap), qinc = qn;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, qinc, o);
+        if (lane >= o) qinc += v;
+    }
+    const int n = __shfl_sync(0xffffffffu, qinc, 31);
     const float xs = p.xs, xo = p.xo, ys = p.ys, yo = p.yo;
     uint32_t* sb = s_blk[warp];
     for (int u = blockIdx.x * 8 + warp; u < n; u += nUnitBlocks * 8) {
-        const EhbUnit un = p.units[u];
+        int sq = 0;   // sub-queue of unit u = number of sub-queues whose inclusive prefix is <= u
+#pragma unroll
+        for (int st = 16; st >= 1; st >>= 1) {
+            const int v = __shfl_sync(0xffffffffu, qinc, sq + st - 1);
+            if (v <= u) sq += st;
+        }
+        sq = min(sq, 31);
+        const int before = __shfl_sync(0xffffffffu, qinc - qn, sq);
+        const EhbUnit un = p.units[(size_t)sq * p.unitCap + (u - before)];
         if (un.rec == 0xFFFFFFFFu) continue;
         __syncwarp();
         if (un.rec & 0x80000000u) {

@@ -46,9 +46,12 @@ extern "C" {
 #define EHB_E_OVERFLOW (-4) /* the depth-plane pool stayed too small after growing (see ehb_ctx_status) */
 
 /* bits of *flags from ehb_ctx_status */
-#define EHB_FLAG_POOL_OVERFLOW 1u /* depth-plane pool too small: results of that launch are incomplete */
+#define EHB_FLAG_POOL_OVERFLOW 1u /* a scratch pool (depth planes, jobs, silhouette pairs) was too small: results of that
+                                     launch are incomplete */
 #define EHB_FLAG_PAIR_OVERFLOW EHB_FLAG_POOL_OVERFLOW
 #define EHB_FLAG_NEEDS_CLIP 2u    /* triangles crossing the near/far plane were skipped (not supported yet) */
+#define EHB_FLAG_QUEUES_FULL 4u   /* informational: the deferred-triangle queues were full, some large triangles were drawn
+                                     inline (slower, results complete) */
 
 typedef void* ehb_ctx_t;
 
@@ -70,7 +73,7 @@ EHB_API int ehb_ctx_set_pipelines(ehb_ctx_t ctx, int n);
  * (items x links x H x W x 8 B) fits, the pool cannot overflow; beyond it the pool starts at 2 screens per item and
  * EHB_FLAG_POOL_OVERFLOW asks for ehb_ctx_grow_scratch + a rerun. */
 EHB_API int ehb_ctx_set_pool_budget(ehb_ctx_t ctx, double bytes);
-/* Doubles the depth-plane pool used for later launches (call after EHB_FLAG_POOL_OVERFLOW). */
+/* Doubles the scratch pools used for later launches (call after EHB_FLAG_POOL_OVERFLOW). */
 EHB_API int ehb_ctx_grow_scratch(ehb_ctx_t ctx);
 /* Per-kernel timing for benchmarks: while enabled every pass records CUDA events around its four kernels on the
  * caller's stream (and runs it as a single pipeline).  ehb_ctx_kernel_times synchronises, returns the summed

@@ -251,6 +251,9 @@ def test_pool_overflow_is_flagged_and_recovers():
         ctx.grow_scratch()
         assert tries < 8
     assert tries >= 1, "the test is meant to exercise the overflow path"
+    # budget 0 also makes the deferred-triangle / heavy-batch queues tiny: the inline fallbacks of k_raster drew most of
+    # the large triangles of the final pass (flag 4 = queues full, results complete)
+    assert flags & 4, "the test is meant to exercise the queue-full fallback"
     assert np.array_equal(masks.cpu().numpy(), want["masks"])
     assert rel_err(g.cpu().numpy(), want["g_mvp"]) < 1e-9
     ctx.close()
