@@ -448,7 +448,7 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
     if (ev) cudaEventRecord(ev[2], st);
     CU(launch(ehb_k_raster, dim3((unsigned)(streamBlocks + rasterBlocks)), dim3(EHB_RWARPS * 32), 0, st, true, rb, p, streamBlocks, chunks));
     const int jobBlocks = unionMode ? 0 : 16;
-    CU(launch(ehb_k_raster_big, dim3(c->nSM * 4 + jobBlocks), dim3(256), 0, st, true, p, jobBlocks));
+    CU(launch(ehb_k_raster_big, dim3(c->nSM * EHB_BMIN_BLOCKS + jobBlocks), dim3(256), 0, st, true, p, jobBlocks));
     if (ev) cudaEventRecord(ev[3], st);
     if (unionMode) {
         const int nq = ((W + 3) / 4) * H;

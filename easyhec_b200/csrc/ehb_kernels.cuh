@@ -840,7 +840,10 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
 // Deferred triangles: warps stride over the unit list; one unit = a 64 x 32 pixel window of one triangle's bbox.
 __device__ __forceinline__ void ehb_build_jobs(const EhbParams& p, int firstWarp, int nWarps, int lane);
 
-__global__ void __launch_bounds__(256) ehb_k_raster_big(const __grid_constant__ EhbParams p, int jobBlocks)
+#ifndef EHB_BMIN_BLOCKS
+#define EHB_BMIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, EHB_BMIN_BLOCKS) ehb_k_raster_big(const __grid_constant__ EhbParams p, int jobBlocks)
 {
     ehb_pdl_enter();
     __shared__ __align__(16) uint32_t s_blk[8][EHB_BLK_WORDS];
