@@ -155,3 +155,24 @@ def test_weld_and_adjacency():
     opp = oracle.build_adjacency(m.faces, 4)
     # shared edge (1,2): opposite vertices are 3 and 0; boundary edges have none
     assert opp[0].tolist() == [3, -1, -1] and opp[1].tolist() == [-1, 0, -1]
+
+
+def test_config1_plumbing_zero_pose_mask_and_iou(xarm):
+    """BASELINE config 1: xArm7 zero pose (the content of assets/xarm7_zeropos.ply: 20,525 vertices /
+    41,096 triangles), one view 128x128, K = (90.68, 90.67, 64, 64), Tc_c2b = the sample pose of
+    nvdiffrast_renderer.py:77-80; CPU only: mask, mask-L2 loss and IoU against a displaced camera."""
+    m = zero_pose_robot(xarm)
+    assert len(m.faces) == 41096
+    Hh = Ww = 128
+    K = np.array([[90.68, 0, 64.0], [0, 90.67, 64.0], [0, 0, 1]], np.float32)
+    ref = oracle.render_mask(m.vertices, m.faces, mvp_of(K, Hh, Ww, SAMPLE_POSE), Hh, Ww, anti_aliasing=False)
+    assert 0.03 < ref.mean() < 0.5 and ref[:, 0].sum() == 0 and ref[:, -1].sum() == 0      # the arm, fully in view
+    aa = oracle.render_mask(m.vertices, m.faces, mvp_of(K, Hh, Ww, SAMPLE_POSE), Hh, Ww, anti_aliasing=True)
+    assert aa.min() >= 0.0 and aa.max() <= 1.0 + 1e-6
+    assert np.abs(aa - ref).max() <= 1.0 and (np.abs(aa - ref) > 0).mean() < 0.2            # they differ on the silhouette only
+    moved = SAMPLE_POSE.copy(); moved[0, 3] += 0.03
+    other = oracle.render_mask(m.vertices, m.faces, mvp_of(K, Hh, Ww, moved), Hh, Ww, anti_aliasing=True)
+    iou = lambda a, b: float(np.minimum(a, b).sum() / np.maximum(a, b).sum())
+    assert iou(aa, aa) == 1.0 and 0.3 < iou(aa, other) < 0.98
+    loss_same, loss_moved = float(((aa - ref) ** 2).sum()), float(((other - ref) ** 2).sum())
+    assert loss_same < 0.2 * loss_moved
