@@ -158,12 +158,35 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
+class JsonStdout:
+    """Under torchrun, libraries print to stdout while they initialise (NCCL prints its version from rank 0).  The
+    contract is ONE JSON line on stdout: file descriptor 1 is pointed at stderr for the duration of the run and the
+    line is written to the saved descriptor at the end."""
+
+    def __init__(self, active):
+        self.fd = None
+        if active:
+            sys.stdout.flush()
+            self.fd = os.dup(1)
+            os.dup2(2, 1)
+
+    def emit(self, obj):
+        data = (json.dumps(obj) + "\n").encode()
+        sys.stdout.flush()
+        if self.fd is None:
+            sys.stdout.write(data.decode())
+            sys.stdout.flush()
+        else:
+            os.write(self.fd, data)
+
+
 def run_b200(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    out = JsonStdout(world > 1)
     import torch
     import torch.distributed as dist
     from easyhec_b200._lib import Context
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -365,7 +388,7 @@ def run_b200(args):
                            "collective": collective},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu, "need_clip_triangles": int(nclip)}
-        print(json.dumps(line), flush=True)
+        out.emit(line)
     if world > 1:
         dist.destroy_process_group()
 
