@@ -1,0 +1,64 @@
+"""Space-exploration scoring on the device.
+
+The reference scores every candidate joint configuration by rendering the whole robot from each camera pose sampled
+so far and summing the per-pixel variance of the binary masks over those cameras
+(easyhec/modeling/models/rb_solve/space_explorer.py:152-165, easyhec/utils/render_api.py:70-96,179-192): one URDF
+forward kinematics + mesh re-pack + upload + render per (candidate, camera), ten thousand sequential renders per round.
+Here the forward kinematics of ALL candidates is one batched torch evaluation (``URDFKinematics``, on the device when
+the inputs are), the model-view-projection matrices of every (candidate, camera, link) are one broadcast product, and
+``ehb_explore_scores`` renders and scores them without a mask ever leaving the GPU.  Collision / reachability filters
+of the reference (planner, max-distance constraint) stay on the host and enter as ``valid``: rejected candidates score
+0, exactly like the reference's ``variances.append(0)``.
+"""
+import numpy as np
+import torch
+
+from .projection import K_to_projection, opencv2gl
+
+__all__ = ["candidate_mvps", "score_candidates", "select_next_qpos"]
+
+
+def candidate_mvps(kin, links, qposes, cam_poses, K, H, W, pad_left=0, pad_right=0, dtype=torch.float32):
+    """(Q, dof') candidate joint positions x (C, 4, 4) camera poses (``Tc_c2b`` of each camera: base -> camera, i.e. the
+    ``np.linalg.inv(cam_pose)`` the reference hands to the renderer, space_explorer.py:153-155) -> mvp (Q, C, L, 4, 4).
+
+    mvp[q, c, l] = K_to_projection(K) @ diag(1,-1,-1,1) @ Tc_c2b[c] @ FK(qpos_q)[links[l]]  (nvdiffrast_renderer.py:33-37).
+    ``pad_left`` / ``pad_right`` zeros are added around every qpos like ``qpos_choices_pad_left/right``
+    (space_explorer.py:103)."""
+    q = torch.as_tensor(np.asarray(qposes) if not isinstance(qposes, torch.Tensor) else qposes)
+    if not q.is_floating_point():
+        q = q.double()
+    if q.ndim == 1:
+        q = q[None]
+    if pad_left or pad_right:
+        q = torch.cat([q.new_zeros(q.shape[0], pad_left), q, q.new_zeros(q.shape[0], pad_right)], 1)
+    link_poses = kin.forward(q, links=links)                                   # (Q, L, 4, 4), same device as q
+    cams = torch.as_tensor(np.asarray(cam_poses) if not isinstance(cam_poses, torch.Tensor) else cam_poses)
+    cams = cams.to(device=link_poses.device, dtype=link_poses.dtype)
+    if cams.ndim == 2:
+        cams = cams[None]
+    Kt = torch.as_tensor(np.asarray(K) if not isinstance(K, torch.Tensor) else K).float()
+    P = (K_to_projection(Kt, H, W) @ opencv2gl()).to(device=link_poses.device, dtype=link_poses.dtype)
+    mvp = P[None, None, None] @ (cams[None, :, None] @ link_poses[:, None])    # (Q, C, L, 4, 4)
+    return mvp.to(dtype).contiguous()
+
+
+def score_candidates(ctx, mesh_ids, kin, links, qposes, cam_poses, K, H, W, valid=None, pad_left=0, pad_right=0):
+    """Variance score of every candidate (space_explorer.py:163-164: ``torch.var(masks, dim=0).sum()``, unbiased) as a
+    (Q,) float64 tensor on the context's device; candidates with ``valid[q] == False`` score 0."""
+    mvp = candidate_mvps(kin, links, qposes, cam_poses, K, H, W, pad_left, pad_right).to(ctx.device)
+    scores = ctx.explore_scores(mesh_ids, mvp, H, W)
+    if valid is not None:
+        scores = torch.where(torch.as_tensor(np.asarray(valid), dtype=torch.bool, device=scores.device), scores,
+                             torch.zeros_like(scores))
+    return scores
+
+
+def select_next_qpos(scores, history=None):
+    """Index of the best candidate that has not been selected before (space_explorer.py:171-180 keeps a history of the
+    chosen candidates), and its score."""
+    s = scores.detach().clone()
+    if history:
+        s[torch.as_tensor(list(history), dtype=torch.long, device=s.device)] = -1.0
+    i = int(torch.argmax(s).item())
+    return i, float(s[i].item())
