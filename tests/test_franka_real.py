@@ -76,7 +76,7 @@ def test_gpu_solver_tracks_the_oracle_driven_solve_on_real_data():
     samples of the same noisy descent: the matrices differ in their last bits (different fp32 composition order), a
     handful of silhouette pixels flip, the gradient moves by ~1e-3 relative and Adam (3 mm / 0.17 deg per step at lr
     3e-3) amplifies it -- measured on the B200: 0.2 mm at iteration 5, 2.4 mm / 0.34 deg at 50, 0.8 mm / 0.19 deg at
-    100.  The bound is a few optimiser steps; the loss levels agree."""
+    100.  The bound is a few optimiser steps (8 mm / 1 deg; 3 mm / 0.1 deg up to iteration 10); the loss levels agree."""
     from easyhec_b200.solver import PoseSolver
     d, meshes, masks, H, W = load_fixture()
     s = PoseSolver(meshes, d["link_poses"], d["K"], masks, d["start_Tc_c2b"], H, W)
@@ -89,7 +89,9 @@ def test_gpu_solver_tracks_the_oracle_driven_solve_on_real_data():
         e = pose_err(dof_to_matrix(torch.as_tensor(got)).numpy(), dof_to_matrix(torch.as_tensor(want)).numpy())
         if k <= 2:
             assert e[0] < 2e-5 and e[1] < 2e-3, (k, e)
-        assert e[0] < 6e-3 and e[1] < 0.7, (k, e)
+        if k <= 10:
+            assert e[0] < 3e-3 and e[1] < 0.1, (k, e)
+        assert e[0] < 8e-3 and e[1] < 1.0, (k, e)
     loss_end = float(s.loss)
     ref_end = float(d["loss_values"][-1])
     assert abs(loss_end - ref_end) < 0.05 * ref_end, (loss_end, ref_end)
