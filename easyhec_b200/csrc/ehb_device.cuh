@@ -11,8 +11,7 @@
 #include <stdint.h>
 
 #define EHB_MAX_LINKS 32
-#define EHB_LINK_SHIFT 26
-#define EHB_FACE_MASK ((1u << EHB_LINK_SHIFT) - 1u)
+#define EHB_FACE_MASK ((1u << 26) - 1u)   // triangle ids of a link fit in 26 bits
 #define EHB_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define EHB_F32_MAX 3.402823466e+38f
 
@@ -31,12 +30,6 @@ struct EhbRobot {
     int voff[EHB_MAX_LINKS + 1];  // prefix sum of V over links
     int boff[EHB_MAX_LINKS + 1];  // prefix sum of ceil(F / 32) over links: a batch of k_raster never straddles two links
     int L;
-};
-
-struct EhbTri {
-    float c0[4], c1[4], c2[4];  // clip-space positions of the face's vertices, original order
-    int x0, y0, x1, y1, x2, y2; // snapped (1/16 px, origin at viewport centre), counter-clockwise
-    int pxlo, pxhi, pylo, pyhi; // inclusive range of pixels whose centre can be covered (GL rows)
 };
 
 __device__ __forceinline__ void ehb_xform(const float4 v, const float* __restrict__ m, float* c)
@@ -62,53 +55,6 @@ __device__ __forceinline__ uint32_t ehb_order_key(float f)
 {
     uint32_t b = __float_as_uint(f);
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-
-// 0: drawable, 1: culled, 2: needs the near/far clipper or lies outside the guard band (skipped, counted).
-// TRUSTED: the triangle already passed this function for the same mvp (it was binned by k_count), so the
-// index / frustum / depth-range / guard-band tests are skipped; the arithmetic that is kept is identical.
-template <bool TRUSTED = false>
-__device__ __forceinline__ int ehb_tri_setup(const EhbLink& lk, const float* __restrict__ m, int f, int H, int W,
-                                             EhbTri& s)
-{
-    const int4 id = __ldg(lk.faces + f);
-    if (!TRUSTED && ((unsigned)id.x >= (unsigned)lk.V || (unsigned)id.y >= (unsigned)lk.V || (unsigned)id.z >= (unsigned)lk.V))
-        return 1;
-    ehb_xform(__ldg(lk.verts + id.x), m, s.c0);
-    ehb_xform(__ldg(lk.verts + id.y), m, s.c1);
-    ehb_xform(__ldg(lk.verts + id.z), m, s.c2);
-    const float *v0 = s.c0, *v1 = s.c1, *v2 = s.c2;
-    if (!TRUSTED)
-    if ((v0[3] < v0[0] && v1[3] < v1[0] && v2[3] < v2[0]) || (v0[3] < -v0[0] && v1[3] < -v1[0] && v2[3] < -v2[0]) ||
-        (v0[3] < v0[1] && v1[3] < v1[1] && v2[3] < v2[1]) || (v0[3] < -v0[1] && v1[3] < -v1[1] && v2[3] < -v2[1]) ||
-        (v0[3] < v0[2] && v1[3] < v1[2] && v2[3] < v2[2]) || (v0[3] < -v0[2] && v1[3] < -v1[2] && v2[3] < -v2[2]))
-        return 1;
-    if (!TRUSTED && !(v0[3] >= fabsf(v0[2]) && v1[3] >= fabsf(v1[2]) && v2[3] >= fabsf(v2[2]))) return 2;
-    const float vsx = (float)(W * 8), vsy = (float)(H * 8);
-    const float r0 = 1.0f / v0[3], r1 = 1.0f / v1[3], r2 = 1.0f / v2[3];
-    int x0 = ehb_rni_sat(v0[0] * r0 * vsx), y0 = ehb_rni_sat(v0[1] * r0 * vsy);
-    int x1 = ehb_rni_sat(v1[0] * r1 * vsx), y1 = ehb_rni_sat(v1[1] * r1 * vsy);
-    int x2 = ehb_rni_sat(v2[0] * r2 * vsx), y2 = ehb_rni_sat(v2[1] * r2 * vsy);
-    const int G = 1 << 28;
-    if (!TRUSTED)
-    if (x0 > G || x0 < -G || y0 > G || y0 < -G || x1 > G || x1 < -G || y1 > G || y1 < -G || x2 > G || x2 < -G ||
-        y2 > G || y2 < -G)
-        return 2;
-    const long long area = (long long)(x1 - x0) * (y2 - y0) - (long long)(y1 - y0) * (x2 - x0);
-    if (area == 0) return 1;
-    if (area < 0) { int t = x1; x1 = x2; x2 = t; t = y1; y1 = y2; y2 = t; }
-    const int lox = min(x0, min(x1, x2)), hix = max(x0, max(x1, x2));
-    const int loy = min(y0, min(y1, y2)), hiy = max(y0, max(y1, y2));
-    // samples sit at 16*p + 8 - 8*W : p >= ceil((lo + 8W - 8)/16), p <= floor((hi + 8W - 8)/16)
-    const int bx = 8 * W - 8, by = 8 * H - 8;
-    int pxlo = (lox + bx + 15) >> 4, pxhi = (hix + bx) >> 4;
-    int pylo = (loy + by + 15) >> 4, pyhi = (hiy + by) >> 4;
-    pxlo = max(pxlo, 0); pylo = max(pylo, 0);
-    pxhi = min(pxhi, W - 1); pyhi = min(pyhi, H - 1);
-    if (pxlo > pxhi || pylo > pyhi) return 1;
-    s.x0 = x0; s.y0 = y0; s.x1 = x1; s.y1 = y1; s.x2 = x2; s.y2 = y2;
-    s.pxlo = pxlo; s.pxhi = pxhi; s.pylo = pylo; s.pyhi = pyhi;
-    return 0;
 }
 
 // Tie rule for a sample exactly on a snapped edge (dx,dy = direction of the counter-clockwise edge).

@@ -517,7 +517,7 @@ __device__ __forceinline__ void ehb_rec_store_soa(uint32_t* b, int t, const EhbR
 }
 
 // Primitive assembly of one triangle from the pre-transformed vertices -> record.  Same tests, in the same order,
-// as ehb_tri_setup (the oracle's eho_rasterize).  Returns the number of rows of its clipped bbox (0: nothing to draw).
+// as the oracle's eho_rasterize.  Returns the number of rows of its clipped bbox (0: nothing to draw).
 __device__ __forceinline__ int ehb_make_record(const EhbRobot& rb, const EhbParams& p, int item, int l, int f, EhbRec& rc)
 {
     const int g = rb.foff[l] + f;
