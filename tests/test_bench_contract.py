@@ -1,0 +1,46 @@
+"""Host-side pieces of bench.py's contract that can be checked without a GPU."""
+import json
+import os
+import subprocess
+import sys
+import textwrap
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _bench():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    return b
+
+
+def test_algorithmic_bytes_match_the_survey():
+    b = _bench()
+    # 8 H W + 40 V + 24 F; xArm7 links 1-7 @1280x720 = 8.91 MB / frame
+    assert b.algorithmic_bytes_per_frame(720, 1280, 17504, 35002) == 7372800 + 700160 + 840048 == 8913008
+    assert b.WORKLOAD["B"] == 10 and (b.WORKLOAD["H"], b.WORKLOAD["W"]) == (720, 1280)
+    assert b.WORKLOAD["ring"] * b.WORKLOAD["B"] * 720 * 1280 * 8 > 126e6       # masks + refs of the ring exceed the L2
+
+
+def test_exactly_one_json_line_on_stdout_under_torchrun():
+    code = textwrap.dedent('''
+        import os, sys, importlib.util
+        spec = importlib.util.spec_from_file_location("bench", %r); b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
+        o = b.JsonStdout(True)
+        os.write(1, b"NCCL version 2.28.9+cuda12.9\\n")      # what a C library prints while it initialises
+        print("python-level chatter")
+        o.emit({"metric": "m", "value": 1.5})
+    ''' % os.path.join(ROOT, "bench.py"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True)
+    lines = r.stdout.splitlines()
+    assert len(lines) == 1 and json.loads(lines[0]) == {"metric": "m", "value": 1.5}
+    assert "NCCL version" in r.stderr and "python-level chatter" in r.stderr
+
+
+def test_reference_arm_exits_quietly_on_non_zero_ranks():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
