@@ -3,11 +3,13 @@
 
 One step = one pass of the hot path over one batch: B = 10 views of the xArm7 arm (links 1..7, 35,002
 triangles), 1280x720, forward (per-link antialiased masks, sum, clamp, L2 loss against the reference masks)
-+ backward (d loss / d mvp of every (view, link)).  value = frames/s with inputs resident in HBM;
-e2e = the same through the host-buffer C-ABI call (H2D of the step's masks + matrices, D2H of loss and
-gradient inside the timed region).  See DESIGN.md "Measurement" for the byte accounting.
++ backward to the 6-DoF pose gradient (d loss / d mvp of every (view, link), chained to d loss / d dof) --
+SURVEY.md 8(d): "one frame = one view, all links, forward + backward to g_dof".
+value = frames/s with inputs resident in HBM; e2e = the same through the host-buffer C-ABI call (host -> device
+copy of the step's inputs, device -> host copy of loss and gradient inside the timed region).
+See DESIGN.md "Measurement" for the byte accounting.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload headline|inview|explore]
   torchrun --nproc-per-node N bench.py --gpus N ...      (one rank per GPU, weak scaling: B views per rank)
 """
 import argparse
@@ -23,8 +25,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-WORKLOAD = dict(name="xarm7_links1-7_B10_1280x720_fwd+bwd", B=10, H=720, W=1280, links="xarm7", ring=4)
+# headline: the reference renderer's own demo pose (nvdiffrast_renderer.py:77-80) with random joints -- about half of
+#           the arm's vertices project off screen.  inview: same robot, joints and intrinsics, the camera translated so
+#           that >= 95 % of the vertices are on screen (scenes.fit_camera): twice the triangles to draw.
+WORKLOADS = {
+    "headline": dict(name="xarm7_links1-7_B10_1280x720_fwd+bwd", B=10, H=720, W=1280, links="xarm7", ring=4, camera="sample"),
+    "inview": dict(name="xarm7_links1-7_B10_1280x720_fwd+bwd_inview", B=10, H=720, W=1280, links="xarm7", ring=4, camera="fit"),
+}
+WORKLOAD = WORKLOADS["headline"]
+EXPLORE = dict(name="explore_xarm7_all_Q256xC4_1920x1080", Q=256, C=4, H=1080, W=1920)   # BASELINE.json configs[3]
 METRIC = "silhouette render+grad frames/sec @1280x720 xArm7 mesh"
+MIN_TIMED_MS = 200.0   # the K-step timed region is repeated until this much device time has been measured
 
 
 def algorithmic_bytes_per_frame(H, W, V, F):
@@ -32,17 +43,26 @@ def algorithmic_bytes_per_frame(H, W, V, F):
     return 8 * H * W + 40 * V + 24 * F
 
 
-def build_sets(wl, rank, n_sets):
-    """n_sets independent batches of B views: (meshes, [mvp (B,L,4,4) f32], link_poses) -- numpy, host side."""
-    from easyhec_b200.scenes import make_scene, perturb_pose
+def algorithmic_bytes_per_render(H, W, V, F):
+    """SURVEY.md 8(d), forward-only binary render: 4HW + 12V + 12F."""
+    return 4 * H * W + 12 * V + 12 * F
+
+
+def build_sets(wl, rank, n_sets, same_on_every_rank=False):
+    """n_sets independent batches of B views: dicts(scene, mvp_gt, mvp (B,L,4,4) f32, Tc (4,4) perturbed pose) -- numpy."""
+    from easyhec_b200.scenes import fit_camera, make_scene, perturb_pose
     from util import scene_mvps
     sets = []
+    r = 0 if same_on_every_rank else rank
     for s in range(n_sets):
-        sc = make_scene(wl["B"], wl["H"], wl["W"], links=wl["links"], seed=1000 * rank + s)
-        rng = np.random.RandomState(77 + 1000 * rank + s)
+        sc = make_scene(wl["B"], wl["H"], wl["W"], links=wl["links"], seed=1000 * r + s)
+        if wl.get("camera") == "fit":
+            sc["Tc_c2b"] = fit_camera(sc, wl["H"], wl["W"], keep=0.96)
+        rng = np.random.RandomState(77 + 1000 * r + s)
         mvp_gt = scene_mvps(sc, wl["H"], wl["W"])
-        mvp = scene_mvps(sc, wl["H"], wl["W"], perturb_pose(sc["Tc_c2b"], rng, 0.03, 3.0))
-        sets.append(dict(scene=sc, mvp_gt=mvp_gt, mvp=mvp))
+        Tc = perturb_pose(sc["Tc_c2b"], rng, 0.03, 3.0)
+        mvp = scene_mvps(sc, wl["H"], wl["W"], Tc)
+        sets.append(dict(scene=sc, mvp_gt=mvp_gt, mvp=mvp, Tc=Tc))
     return sets
 
 
@@ -105,56 +125,147 @@ def physical_gpu_index(local_rank):
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_run(wl, n_views, steps, warmup, threads=None):
-    """Times oracle.render_views (the CPU restatement of the path) on n_views views of the workload.
-    Returns (frames_per_s, ms_per_step, threads)."""
+def host_threads():
+    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1: not inherited here)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_reference_run(wl, sets, steps, warmup):
+    """Times oracle.render_views (the CPU restatement of the path) on the views of `sets`, one set per step in turn, with
+    every host thread.  Returns (frames_per_s, ms_per_step, threads, results of the last pass over every set)."""
     from oracle import oracle
-    from util import scene_mvps  # noqa: F401
-    from easyhec_b200.scenes import make_scene, perturb_pose
-    B = wl["B"]
-    nsets = (n_views + B - 1) // B
-    sets = build_sets(wl, 0, nsets)
+    threads = oracle.set_num_threads(host_threads())
     packed = oracle.pack_links(sets[0]["scene"]["meshes"])
-    mvp = np.concatenate([s["mvp"] for s in sets])[:n_views]
-    mvp_gt = np.concatenate([s["mvp_gt"] for s in sets])[:n_views]
-    ref = oracle.union_binary(packed, mvp_gt, wl["H"], wl["W"]).astype(np.float32)
-    for _ in range(warmup):
-        oracle.render_views(packed, mvp, ref, wl["H"], wl["W"])
+    refs = [oracle.union_binary(packed, s["mvp_gt"], wl["H"], wl["W"]).astype(np.float32) for s in sets]
+    last = [None] * len(sets)
+    for k in range(warmup):
+        oracle.render_views(packed, sets[k % len(sets)]["mvp"], refs[k % len(sets)], wl["H"], wl["W"])
     t0 = time.perf_counter()
-    for _ in range(steps):
-        oracle.render_views(packed, mvp, ref, wl["H"], wl["W"])
+    for k in range(steps):
+        i = k % len(sets)
+        last[i] = oracle.render_views(packed, sets[i]["mvp"], refs[i], wl["H"], wl["W"])
     dt = time.perf_counter() - t0
-    return n_views * steps / dt, 1e3 * dt / max(steps, 1), oracle.num_threads()
+    return wl["B"] * steps / dt, 1e3 * dt / max(steps, 1), threads, last
 
 
 def run_reference(args):
     """--impl reference: the CPU implementation of the path on the host cores.  nvdiffrast (the reference's GPU
     arithmetic) is not vendored in the reference tree and cannot be installed offline, so this arm times the
-    oracle port (kind "port") with all host threads; each step is a bounded sample of the workload."""
+    oracle port (kind "port") with all host threads on the GPU arm's own config: every step is the same B views."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wl = WORKLOAD
+    wl = WORKLOADS.get(args.workload, WORKLOAD)
     from oracle import oracle
     oracle.build()
-    threads = oracle.num_threads()
-    # calibrate: one view-step
-    t_one, _, _ = cpu_reference_run(wl, max(1, min(threads, 4)), 1, 0)
-    budget = 150.0
-    total_steps = args.steps + args.warmup
-    views = int(max(1, min(4 * threads, budget * t_one / max(total_steps, 1))))
-    fps, ms, threads = cpu_reference_run(wl, views, args.steps, args.warmup)
+    sets = build_sets(wl, 0, wl["ring"])
+    # bounded: the whole run (warm-up + K steps) stays within a few minutes on any host
+    t_probe = cpu_reference_run(wl, sets[:1], 1, 0)[1] * 1e-3
+    steps = int(max(1, min(args.steps, 150.0 / max(t_probe, 1e-3))))
+    warm = int(min(args.warmup, max(0, 30.0 / max(t_probe, 1e-3))))
+    fps, ms, threads, _ = cpu_reference_run(wl, sets, steps, warm)
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"], "views_per_step": views, "H": wl["H"], "W": wl["W"]},
+            "config": {"workload": wl["name"], "views_per_step_per_gpu": wl["B"], "H": wl["H"], "W": wl["W"],
+                       "steps_timed": steps},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                             "sample": "%d views of the workload per step, OpenMP over views" % views},
+                             "sample": "%d views of the workload per step (the GPU arm's batch), %d steps, OpenMP over "
+                                       "views, %d threads set explicitly" % (wl["B"], steps, threads)},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "reference's own GPU arithmetic (nvdiffrast) is not in the reference tree / not installable "
                     "offline; this is the CPU restatement in oracle/ (parity unpinned, see DESIGN.md)"}
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- baselines beside the GPU arm
+def time_proxy(wl, sets, ids_unused, dev, iters=3):
+    """Structural proxy of the reference's call pattern -- NOT nvdiffrast: RBSolver(fused=False) calls the drop-in
+    operator once per (view, link) (rb_solver.py:60-67), sums / clamps / takes the loss with torch ops and lets torch
+    autograd drive one operator backward per call.  Same kernels as the fused path, none of its fusion."""
+    import torch
+    from easyhec_b200.rb_solver import RBSolver
+    s = sets[0]
+    sc = s["scene"]
+    m = RBSolver(meshes=sc["meshes"], init_Tc_c2b=s["Tc"], H=wl["H"], W=wl["W"], fused=False, device=dev,
+                 want_outputs=False)
+    ctx = m.renderer.ctx
+    ref = ctx.render_binary_batch(m.mesh_ids, torch.from_numpy(s["mvp_gt"]).to(dev), wl["H"], wl["W"]).float()
+    dps = {"mask": ref, "link_poses": torch.from_numpy(sc["link_poses"]).to(dev), "K": torch.from_numpy(sc["K"]).to(dev)[None],
+           "global_step": 0}
+
+    def one():
+        m.zero_grad(set_to_none=True)
+        _, ld = m(dps)
+        ld["mask_loss"].backward()
+
+    one()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        one()
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    ctx.close()
+    return {"kind": "unfused per-(view, link) operator loop over this repo's own kernels + torch autograd -- NOT nvdiffrast",
+            "value": wl["B"] * iters / dt, "unit": "frames/s", "steps": iters, "calls_per_step": 2 * wl["B"] * len(sc["meshes"])}
+
+
+def time_nvdiffrast(wl, sets, dev, iters=3):
+    """The reference's own GPU path (nvdiffrast_renderer.py:25-48 driven as rb_solver.py:60-72), timed iff nvdiffrast
+    imports on this box."""
+    try:
+        import nvdiffrast.torch as dr
+    except Exception as e:   # noqa: BLE001
+        return "unavailable: %s" % type(e).__name__
+    import torch
+    from easyhec_b200.projection import K_to_projection, opencv2gl
+    s = sets[0]
+    sc = s["scene"]
+    H, W = wl["H"], wl["W"]
+    glctx = dr.RasterizeCudaContext()
+    verts = [torch.from_numpy(np.asarray(m.vertices, np.float32)).to(dev) for m in sc["meshes"]]
+    faces = [torch.from_numpy(np.asarray(m.faces, np.int32)).to(dev) for m in sc["meshes"]]
+    K = torch.from_numpy(sc["K"]).to(dev)
+    lp = torch.from_numpy(sc["link_poses"]).to(dev)
+    Tc = torch.tensor(s["Tc"], dtype=torch.float32, device=dev, requires_grad=True)
+    flip = opencv2gl(dev)
+    ref = torch.zeros((wl["B"], H, W), device=dev)
+
+    def render_mask(v, f, pose):
+        proj = K_to_projection(K, H, W).to(dev)
+        pos = torch.cat([v, torch.ones_like(v[:, :1])], 1) @ (proj @ (flip @ pose)).T
+        rast, _ = dr.rasterize(glctx, pos[None], f, resolution=[H, W])
+        col, _ = dr.interpolate(torch.ones_like(v)[None], rast, f)
+        col = dr.antialias(col, rast, pos[None], f)
+        return torch.flip(col[0, :, :, 0], dims=[0])
+
+    def one():
+        losses = []
+        for b in range(wl["B"]):
+            si = torch.stack([render_mask(verts[l], faces[l], Tc @ lp[b, l]) for l in range(len(verts))]).sum(0).clamp(max=1)
+            losses.append(torch.sum((si - ref[b]) ** 2))
+        torch.stack(losses).mean().backward()
+
+    one()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        one()
+    torch.cuda.synchronize(dev)
+    return {"value": wl["B"] * iters / (time.perf_counter() - t0), "unit": "frames/s", "steps": iters}
+
+
+def probe_pytorch3d():
+    try:
+        import pytorch3d  # noqa: F401
+        return "importable but not timed (CPU soft rasterizer of north_star; see DESIGN.md)"
+    except Exception as e:   # noqa: BLE001
+        return "unavailable: %s" % type(e).__name__
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
@@ -180,12 +291,40 @@ class JsonStdout:
             os.write(self.fd, data)
 
 
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def timed_regions(step, steps, barrier, torch, min_ms=MIN_TIMED_MS, max_repeats=400):
+    """Times EXACTLY `steps` steps between two CUDA events, bracketed by barrier + synchronize on both sides; the region is
+    repeated until `min_ms` of device time has been measured (a 20-step region of a 0.1 ms step is 2 ms: one region is
+    noise).  Returns (median ms per region, all region times)."""
+    regions = []
+    k0 = 0
+    while True:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(steps):
+            step(k0 + k)
+        e1.record()
+        barrier()
+        regions.append(e0.elapsed_time(e1))
+        k0 += steps
+        if sum(regions) >= min_ms or len(regions) >= max_repeats:
+            break
+    return float(np.median(regions)), regions
+
+
 def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     out = JsonStdout(world > 1)
     import torch
     import torch.distributed as dist
     from easyhec_b200._lib import Context
+    from easyhec_b200.scenes import onscreen_fraction
+    from easyhec_b200.se3 import matrix_to_dof
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -193,12 +332,14 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    wl = WORKLOAD
+    wl = WORKLOADS[args.workload]
     B, H, W, R = wl["B"], wl["H"], wl["W"], wl["ring"]
     ctx = Context(dev)
     if os.environ.get("EHB_PIPES"):
         ctx.set_pipelines(int(os.environ["EHB_PIPES"]))
-    sets = build_sets(wl, rank, R)
+    # every rank renders the SAME scenes (weak scaling: B views per rank): the ranks' work is balanced by construction, so
+    # what the N-GPU line shows is the cost of the exchange, not of unequal scenes
+    sets = build_sets(wl, rank, R, same_on_every_rank=True)
     meshes = sets[0]["scene"]["meshes"]
     ids = [ctx.register_mesh(m.vertices, m.faces) for m in meshes]
     L = len(ids)
@@ -211,10 +352,18 @@ def run_b200(args):
     for s in sets:
         m = ctx.render_binary_batch(ids, torch.from_numpy(s["mvp_gt"]).to(dev), H, W)
         ref_dev.append(m.to(torch.float32))
+    coverage = float(torch.stack([r.mean() for r in ref_dev]).mean().item())
+    onscreen = float(np.mean([onscreen_fraction(s["scene"], H, W) for s in sets]))
     masks = [torch.empty((B, H, W), dtype=torch.float32, device=dev) for _ in range(R)]
     loss = torch.empty((B,), dtype=torch.float64, device=dev)
     gmvp = torch.empty((B, L, 4, 4), dtype=torch.float64, device=dev)
+    # the pose chain behind the rasterizer: d loss/d mvp -> d loss/d dof (+ loss) = the 7 floats a data-parallel run exchanges
+    dof_dev = [matrix_to_dof(torch.tensor(s["Tc"], dtype=torch.float32)).to(dev).contiguous() for s in sets]
+    K_dev = torch.from_numpy(sets[0]["scene"]["K"]).to(dev).contiguous()
+    lp_dev = [torch.from_numpy(s["scene"]["link_poses"]).to(dev).contiguous() for s in sets]
     g7 = torch.zeros(7, dtype=torch.float32, device=dev)
+    dof_scratch = dof_dev[0].clone()       # Adam runs on a scratch copy: the rendered poses stay those of the ring
+    adam_state = torch.zeros(13, dtype=torch.float32, device=dev)
     collective = "none"
     if world > 1:
         collective = "nccl all-reduce 7xf32 per step"
@@ -234,11 +383,14 @@ def run_b200(args):
     def step(k):
         s = k % R
         ctx.render_views_fused(ids, mvp_dev[s], ref_dev[s], H, W, backward=True, out=(masks[s], loss, gmvp))
-        if world > 1:   # the solver's one exchange step: all-reduce of (g_dof[6], loss) -- trainer/base.py:349
+        ctx.pose_backward(dof_dev[s], K_dev, lp_dev[s], gmvp, loss, H, W, grad_scale=1.0 / world,
+                          loss_scale=1.0 / (B * world), out=g7)
+        if world > 1:   # the solver's one exchange step: all-reduce of (g_dof[6], loss) -- trainer/base.py:349 -- then Adam
             if use_peer:
                 ctx.allreduce7(g7)
             else:
                 dist.all_reduce(g7)
+            ctx.adam_step(dof_scratch, g7, adam_state, 3e-3, weight_decay=5e-4)
 
     def barrier():
         torch.cuda.synchronize()
@@ -285,15 +437,9 @@ def run_b200(args):
     barrier()
     sampler.start()
     l0 = ctx.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for k in range(args.steps):
-        step(k)
-    e1.record()
-    barrier()
+    ms, regions = timed_regions(step, args.steps, barrier, torch)
     clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
-    launches = ctx.launch_count() - l0
+    launches = (ctx.launch_count() - l0) // max(len(regions), 1)
     if graphs is not None:
         launches = launches_per_step * args.steps
     if world > 1:
@@ -303,10 +449,17 @@ def run_b200(args):
     frames = B * args.steps * world
     value = frames / (ms * 1e-3)
 
+    # ---- parity of what was just timed: GPU results of every ring slot, checked by the CPU leg below -------------
+    gpu_results = []
+    if rank == 0 and world == 1 and not args.no_cpu:
+        for s in range(R):
+            eager_step(s)
+            gpu_results.append((masks[s].cpu().numpy(), loss.cpu().numpy().copy(), gmvp.cpu().numpy().copy()))
+
     # ---- per-kernel pass (CUDA events around each kernel, on the launching stream) ----------------------
     ctx.profile(True)
     ctx.kernel_times()
-    nprof = min(args.steps, 200)
+    nprof = min(max(args.steps, 50), 200)
     for k in range(nprof):
         eager_step(k)
     kt, npass = ctx.kernel_times()
@@ -328,10 +481,12 @@ def run_b200(args):
     achieved = alg / (kavg_us[dom] * 1e-6) / 1e9
     roofline = {"bound": "hbm", "kernel": "ehb_k_" + dom + ("(+ehb_k_raster_big)" if dom == "raster" else ""), "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": "ncu --set full capture of the same command, committed as profiles/traffic.json",
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "algorithmic_bytes_per_launch": alg, "kernel_us": kavg_us,
                 "kernel_us_note": "CUDA events around each stage, single pipeline; the timed region overlaps pipelines",
-                "step_frac": (alg / (sum(kavg_us.values()) * 1e-6) / 1e9) / peak}
+                "step_frac": (alg / (sum(kavg_us.values()) * 1e-6) / 1e9) / peak,
+                "timed_step_frac": (alg / (ms / max(args.steps, 1) * 1e-3) / 1e9) / peak}
 
     # ---- end to end: host buffers through the C ABI, copies inside the timed region ----------------------
     # every step: H2D of that step's reference masks (u8, what the dataset holds before .float()) and matrices from
@@ -352,7 +507,7 @@ def run_b200(args):
             ctx.solver_step_end(k % S)
 
     e2e_run(16)
-    e2e_steps = min(args.steps, 1000)
+    e2e_steps = min(max(args.steps, 200), 1000)
     barrier()
     t0 = time.perf_counter()
     e2e_run(e2e_steps)
@@ -368,26 +523,48 @@ def run_b200(args):
                                       "loss + g_mvp out, host-visible result every step)"}
 
     if rank == 0:
-        cpu = None
+        cpu, parity, proxy, nvd = None, None, None, None
         if world == 1 and not args.no_cpu:
             from oracle import oracle
             oracle.build()
-            nv = max(1, min(oracle.num_threads(), 16))
-            fps, cms, threads = cpu_reference_run(wl, nv, 2, 1)
+            # CPU leg: the oracle on the very views that were timed (every ring slot), 5 passes over the ring; its
+            # results are the checker of the GPU results above
+            fps, cms, threads, last = cpu_reference_run(wl, sets, 5 * R, R)
             cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                   "sample": "%d views of the workload x 2 steps (+1 warm-up), OpenMP over views" % nv}
+                   "sample": "the %d ring slots (%d views each) x 5 passes (+1 warm-up pass), OpenMP over views" % (R, B)}
+            ok, worst_g, worst_l = True, 0.0, 0.0
+            for s in range(R):
+                gm, gl, gg = gpu_results[s]
+                w = last[s]
+                ok &= bool(np.array_equal(gm, w["masks"]))
+                worst_l = max(worst_l, rel_err(gl, w["loss_per_view"]))
+                worst_g = max(worst_g, rel_err(gg, w["g_mvp"]))
+            ok &= worst_l < 1e-12 and worst_g < 1e-6
+            parity = {"ok": bool(ok), "slots": R, "masks": "bit-exact" if ok else "MISMATCH", "loss_rel_err": worst_l,
+                      "g_mvp_rel_err": worst_g, "checker": "oracle.render_views on the timed inputs (outside the timed region)"}
+            if not args.no_proxy:
+                try:
+                    proxy = time_proxy(wl, sets, ids, dev)
+                except Exception as e:   # noqa: BLE001
+                    proxy = "failed: %s" % str(e)[:200]
+                nvd = time_nvdiffrast(wl, sets, dev)
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl["name"], "views_per_step_per_gpu": B, "H": H, "W": W, "links": L,
-                           "triangles": F, "vertices": V,
+                           "triangles": F, "vertices": V, "onscreen_frac": onscreen, "coverage": coverage,
+                           "step": "fused render + loss + backward to d loss/d mvp, pose chain to d loss/d dof" +
+                                   (", all-reduce of 7 floats, Adam" if world > 1 else ""),
                            "l2": "ring of %d view-sets (%.0f MB of masks+refs) > 126 MB L2" %
                                  (R, R * B * H * W * 8 / 1e6),
                            "pipelines": int(os.environ.get("EHB_PIPES", "3")),
                            "launch": "CUDA graph replay, one graph per ring slot" if graphs is not None else "eager",
-                           "collective": collective},
+                           "scenes": "identical on every rank", "collective": collective,
+                           "timed_regions": len(regions), "timed_region_ms": ms},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu, "need_clip_triangles": int(nclip)}
+                "cpu_baseline": cpu, "parity_checked": bool(parity and parity["ok"]), "parity": parity,
+                "proxy": proxy, "nvdiffrast": nvd, "pytorch3d": probe_pytorch3d(),
+                "need_clip_triangles": int(nclip)}
         out.emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -399,13 +576,21 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS) + ["explore"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity / proxy legs")
+    ap.add_argument("--no-proxy", action="store_true", help="skip the unfused-loop proxy and the nvdiffrast probe")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"], help="N>1: how the 7 floats are all-reduced")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "explore":
+        run_explore(args)
     else:
         run_b200(args)
+
+
+def run_explore(args):   # filled in with the sharded exploration scorer (BASELINE.json configs[3])
+    raise SystemExit("--workload explore: not built yet")
 
 
 if __name__ == "__main__":

@@ -11,7 +11,7 @@ import numpy as np
 from .meshio import Mesh, synthetic_links
 
 __all__ = ["SAMPLE_POSE", "XARM_K", "FRANKA_K", "load_xarm7", "chain_fk", "scaled_K", "perturb_pose", "make_scene",
-           "franka_like_links", "FRANKA_FACE_COUNTS"]
+           "franka_like_links", "FRANKA_FACE_COUNTS", "fit_camera", "onscreen_fraction", "franka_cfg3_scene"]
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -105,3 +105,63 @@ def make_scene(B, H, W, links="xarm7", seed=0, K_base=XARM_K, joint_range=0.6):
         link_poses[:, 8] = link_poses[:, 8] @ off
     return dict(meshes=meshes, link_poses=link_poses.astype(np.float32), K=scaled_K(H, W, K_base),
                 Tc_c2b=SAMPLE_POSE.copy(), qpos=qpos)
+
+
+def _scene_points(sc, stride=4):
+    """Vertices of every (view, link) in the robot base frame, subsampled: (N, 3) float64."""
+    pts = []
+    for b in range(sc["link_poses"].shape[0]):
+        for l, m in enumerate(sc["meshes"]):
+            T = sc["link_poses"][b, l].astype(np.float64)
+            v = np.asarray(m.vertices[::stride], np.float64)
+            pts.append(v @ T[:3, :3].T + T[:3, 3])
+    return np.concatenate(pts)
+
+
+def onscreen_fraction(sc, H, W, Tc_c2b=None, stride=4):
+    """Fraction of the scene's vertices (all views, all links) that project inside the image and lie in front of the camera."""
+    T = np.asarray(sc["Tc_c2b"] if Tc_c2b is None else Tc_c2b, np.float64)
+    p = _scene_points(sc, stride) @ T[:3, :3].T + T[:3, 3]
+    K = np.asarray(sc["K"], np.float64)
+    z = np.maximum(p[:, 2], 1e-9)
+    u, v = K[0, 0] * p[:, 0] / z + K[0, 2], K[1, 1] * p[:, 1] / z + K[1, 2]
+    return float(((p[:, 2] > 0) & (u >= 0) & (u < W) & (v >= 0) & (v < H)).mean())
+
+
+def fit_camera(sc, H, W, fill=1.0, keep=0.95, iters=60):
+    """A camera pose with SAMPLE_POSE's orientation, translated so that the robot of EVERY view of the scene lies inside
+    the image (the central `keep` percentile box of the projected vertices fills `fill` of the tighter image dimension,
+    so about `keep` of the vertices are on screen).
+    One pose for all views, as RBSolver solves for a single Tc_c2b (rb_solver.py:52)."""
+    T = np.asarray(sc["Tc_c2b"], np.float64).copy()
+    K = np.asarray(sc["K"], np.float64)
+    X = _scene_points(sc, 4) @ T[:3, :3].T
+    for _ in range(iters):
+        p = X + T[:3, 3]
+        z = np.maximum(p[:, 2], 1e-3)
+        u, v = K[0, 0] * p[:, 0] / z + K[0, 2], K[1, 1] * p[:, 1] / z + K[1, 2]
+        q = [50.0 * (1.0 - keep), 100.0 - 50.0 * (1.0 - keep)]
+        u0, u1 = np.percentile(u, q); v0, v1 = np.percentile(v, q)
+        zm = float(np.median(z))
+        T[0, 3] += (W / 2 - (u0 + u1) / 2) * zm / K[0, 0]
+        T[1, 3] += (H / 2 - (v0 + v1) / 2) * zm / K[1, 1]
+        r = max((u1 - u0) / (fill * W), (v1 - v0) / (fill * H))
+        T[2, 3] += zm * (r - 1.0) * 0.7
+    return T
+
+
+def franka_cfg3_scene(H=720, W=1280, views=20):
+    """BASELINE.json config 3 on the REAL Franka visual meshes (link0-7 + hand, 133,676 triangles: welded DAE assets of
+    configs/franka/example_franka_offline.yaml:9-19, carried in tests/golden/franka_offline.npz), 20 views with
+    qpos ~ U(joint limits) (tests/golden/franka_cfg3.npz), K = the xArm default scaled to (H, W), camera = the YAML's
+    init_Tc_c2b (configs/franka/example_franka_offline.yaml:5-8)."""
+    g = os.path.join(_ROOT, "tests", "golden")
+    d = np.load(os.path.join(g, "franka_offline.npz"))
+    c = np.load(os.path.join(g, "franka_cfg3.npz"))
+    meshes = [Mesh(d[str(n) + "_v"], d[str(n) + "_f"]) for n in d["names"]]
+    T = np.asarray(d["yaml_init_Tc_c2b"], np.float64).copy()
+    u, _, vt = np.linalg.svd(T[:3, :3])
+    T[:3, :3] = u @ vt
+    idx = np.arange(views) % len(c["link_poses"])     # more than 20 views: the joint configurations repeat
+    return dict(meshes=meshes, link_poses=c["link_poses"][idx].astype(np.float32), K=scaled_K(H, W), Tc_c2b=T,
+                qpos=c["qpos"][idx])

@@ -80,6 +80,17 @@ EHO_API int eho_num_threads(void)
 #endif
 }
 
+/* Thread count of the view-parallel loops below.  Launchers such as torchrun export OMP_NUM_THREADS=1; the timed CPU
+ * baseline sets the count explicitly instead of inheriting that. */
+EHO_API void eho_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* clip[v] = [x y z 1] * mvp^T, accumulate k = 0..3 the way an fp32 GEMM inner loop does:
  * c = x*m0; c = fma(y,m1,c); c = fma(z,m2,c); c = c + m3. */
 EHO_API void eho_transform(const float* verts, int V, const float* mvp, float* clip)

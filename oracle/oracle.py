@@ -11,7 +11,7 @@ import subprocess
 
 import numpy as np
 
-__all__ = ["build", "lib", "num_threads", "transform", "build_adjacency", "rasterize", "render_mask",
+__all__ = ["build", "lib", "num_threads", "set_num_threads", "transform", "build_adjacency", "rasterize", "render_mask",
            "render_mask_bwd", "render_views", "union_binary", "variance_scores", "pack_links", "FILL_RULE"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -52,6 +52,12 @@ def _i32(a):
 
 def num_threads() -> int:
     return int(lib().eho_num_threads())
+
+
+def set_num_threads(n: int) -> int:
+    """Threads of the view-parallel loops (OpenMP); returns the count now in effect."""
+    lib().eho_set_num_threads(C.c_int(int(n)))
+    return num_threads()
 
 
 def transform(verts, mvp):

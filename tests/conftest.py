@@ -10,6 +10,20 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "multigpu: needs at least two CUDA devices (spawns one process per GPU)")
+
+
+def pytest_collection_modifyitems(config, items):
+    """Tests marked `gpu` are skipped (not failed) on a machine without a CUDA device."""
+    import torch
+    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    no_gpu = pytest.mark.skip(reason="no CUDA device")
+    one_gpu = pytest.mark.skip(reason="needs >= 2 CUDA devices")
+    for it in items:
+        if "gpu" in it.keywords and n == 0:
+            it.add_marker(no_gpu)
+        elif "multigpu" in it.keywords and n < 2:
+            it.add_marker(one_gpu)
 
 
 @pytest.fixture(scope="session")

@@ -62,3 +62,16 @@ def test_score_candidates_masks_invalid_and_selection_skips_history(tmp_path):
     assert s.tolist() == [1.0, 2.0, 0.0, 4.0]                 # rejected candidates score 0 (space_explorer.py:109,120,135)
     assert select_next_qpos(s) == (3, 4.0)
     assert select_next_qpos(s, history=[3]) == (1, 2.0)
+
+
+def test_xarm_chain_urdf_reproduces_the_fixture_kinematics(tmp_path):
+    """The URDF that the config-4 GPU test builds from the fixture's joint origins gives the chain's own poses."""
+    from easyhec_b200.scenes import chain_fk, load_xarm7
+    from util import xarm_urdf
+    fx = load_xarm7()
+    kin = xarm_urdf(tmp_path, fx)
+    assert kin.dof == 7 and kin.link_names == list(fx["names"])
+    q = np.random.RandomState(3).uniform(-2, 2, size=(4, 7))
+    got = kin.forward(q).numpy()
+    for i in range(4):
+        assert np.allclose(got[i], chain_fk(fx["joint_origin"], fx["joint_axis"], q[i]), atol=1e-9)

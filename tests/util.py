@@ -44,3 +44,25 @@ def to_dev(a, dtype=None):
 def rel_err(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def xarm_urdf(tmp_path, fx):
+    """URDF of the xArm7 serial chain rebuilt from the fixture's joint origins / axes (link_base, link1..link7) ->
+    URDFKinematics.  rpy is fixed-axis XYZ: R = Rz(y) Ry(p) Rx(r)."""
+    from easyhec_b200.urdf_fk import URDFKinematics
+    names = fx["names"]
+    out = ['<robot name="xarm7_chain">'] + ['<link name="%s"/>' % n for n in names]
+    for i in range(len(names) - 1):
+        T = np.asarray(fx["joint_origin"][i], np.float64)
+        R = T[:3, :3]
+        p = np.arcsin(-R[2, 0])
+        r = np.arctan2(R[2, 1], R[2, 2])
+        y = np.arctan2(R[1, 0], R[0, 0])
+        lo, hi = fx["joint_limits"][i]
+        out.append('<joint name="joint%d" type="revolute"><origin rpy="%.17g %.17g %.17g" xyz="%.17g %.17g %.17g"/>'
+                   '<parent link="%s"/><child link="%s"/><axis xyz="%.17g %.17g %.17g"/><limit lower="%.17g" upper="%.17g"/>'
+                   '</joint>' % ((i + 1, r, p, y) + tuple(T[:3, 3]) + (names[i], names[i + 1]) + tuple(fx["joint_axis"][i]) + (lo, hi)))
+    out.append("</robot>")
+    path = tmp_path / "xarm7_chain.urdf"
+    path.write_text("\n".join(out))
+    return URDFKinematics(str(path))

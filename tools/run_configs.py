@@ -2,12 +2,12 @@
 
   cfg2  xArm7 links 1-7, 10 views 640x480, RBSolver pose optimisation, 200 Adam iterations (lr 3e-3, wd 5e-4):
         iterations/s of the CUDA-graph PoseSolver and the converged pose error against the generating pose
-  cfg3  Franka-sized robot (9 procedural links with the Franka's 133,676 triangles; the DAE assets are not shipped),
-        20 views 1280x720, fused render + loss + backward: frames/s
+  cfg3  the real Franka visual meshes (link0-7 + hand, 133,676 triangles: tests/golden/franka_offline.npz), 20 views
+        1280x720 with qpos ~ U(joint limits) (tests/golden/franka_cfg3.npz), fused render + loss + backward: frames/s
   cfg4  space exploration: 256 candidate joint configurations x 4 camera poses, xArm7 base + links 1-7
         (41,096 triangles), 1920x1080, binary render + variance score: candidates/s on ONE GPU (the path shards
         over ranks with one all-gather of the scores)
-  cfg5  resolution (256^2 .. 2048^2) x views (1 .. 128) sweep, Franka-sized robot, fwd+bwd: frames/s, algorithmic GB/s
+  cfg5  resolution (256^2 .. 2048^2) x views (1 .. 128) sweep, real Franka meshes, fwd+bwd: frames/s, algorithmic GB/s
 """
 import json
 import os
@@ -22,7 +22,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from easyhec_b200._lib import Context  # noqa: E402
-from easyhec_b200.scenes import FRANKA_K, chain_fk, load_xarm7, make_scene, perturb_pose, scaled_K  # noqa: E402
+from easyhec_b200.scenes import (FRANKA_K, chain_fk, franka_cfg3_scene, load_xarm7, make_scene, onscreen_fraction,  # noqa: E402
+                                  perturb_pose, scaled_K)
 from easyhec_b200.solver import PoseSolver  # noqa: E402
 from util import scene_mvps  # noqa: E402
 
@@ -73,7 +74,7 @@ def cfg2():
 
 def cfg3():
     B, H, W = 20, 720, 1280
-    sc = make_scene(B, H, W, links="franka_like", seed=0)
+    sc = franka_cfg3_scene(H, W, B)
     ctx = Context("cuda:0")
     ids = [ctx.register_mesh(m.vertices, m.faces) for m in sc["meshes"]]
     mvp_gt = torch.from_numpy(scene_mvps(sc, H, W)).cuda()
@@ -84,9 +85,11 @@ def cfg3():
              torch.empty((B, L, 4, 4), dtype=torch.float64, device="cuda"))
     ms = timed(lambda: ctx.render_views_fused(ids, mvp, ref, H, W, backward=True, out=out_t), 100)
     flags, _ = ctx.status()
-    F = sum(len(m.faces) for m in sc["meshes"])
-    return {"config": "cfg3 Franka-sized robot (procedural, %d triangles, 9 links), 20 views 1280x720, fwd+bwd" % F,
-            "frames_per_s": B / (ms * 1e-3), "ms_per_step": ms, "flags": flags, "coverage": float(ref.mean())}
+    V = sum(len(m.vertices) for m in sc["meshes"]); F = sum(len(m.faces) for m in sc["meshes"])
+    alg = (8 * H * W + 40 * V + 24 * F) * B
+    return {"config": "cfg3 real Franka visual meshes (%d triangles, 9 links), 20 views 1280x720, fwd+bwd" % F,
+            "frames_per_s": B / (ms * 1e-3), "ms_per_step": ms, "flags": flags, "coverage": float(ref.mean()),
+            "onscreen_frac": onscreen_fraction(sc, H, W), "algorithmic_GBps": alg / (ms * 1e-3) / 1e9}
 
 
 def cfg4():
@@ -119,7 +122,8 @@ def cfg5(resolutions=(256, 512, 1024, 2048), views=(1, 8, 32, 128)):
     for res in resolutions:
         for B in views:
             H = W = res
-            sc = make_scene(B, H, W, links="franka_like", seed=0)
+            sc = franka_cfg3_scene(H, W, B)
+            sc["K"] = scaled_K(H, W)
             ctx = Context("cuda:0")
             ids = [ctx.register_mesh(m.vertices, m.faces) for m in sc["meshes"]]
             L = len(ids)
@@ -146,7 +150,7 @@ def cfg5(resolutions=(256, 512, 1024, 2048), views=(1, 8, 32, 128)):
             ctx.close()
             del ref, out_t, mvp, mvp_gt
             torch.cuda.empty_cache()
-    return {"config": "cfg5 sweep: Franka-sized robot (132k triangles, 9 links), fwd+bwd, 1 GPU", "points": out}
+    return {"config": "cfg5 sweep: real Franka visual meshes (133,676 triangles, 9 links), fwd+bwd, 1 GPU", "points": out}
 
 
 if __name__ == "__main__":
