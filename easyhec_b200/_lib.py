@@ -10,7 +10,7 @@ import os
 import numpy as np
 import torch
 
-__all__ = ["EhbError", "lib", "Context", "library_path"]
+__all__ = ["EhbError", "lib", "Context", "RefMasks", "library_path"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.environ.get("EHB_LIB") or os.path.join(_HERE, "libehb.so")
@@ -56,6 +56,10 @@ _PROTOS = {
                                          C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ehb_render_views_fused_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                             C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ehb_ref_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "ehb_ref_release": (C.c_int, [C.c_void_p, C.c_int]),
+    "ehb_render_views_fused_ref": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ehb_render_binary_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                           C.c_void_p, C.c_void_p]),
     "ehb_variance_score": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
@@ -74,6 +78,8 @@ _PROTOS = {
     "ehb_solver_step_begin_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                            C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ehb_solver_step_end": (C.c_int, [C.c_void_p, C.c_int]),
+    "ehb_solver_step_begin_ref": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                            C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ehb_comm_local_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ehb_comm_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ehb_allreduce7": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -120,6 +126,26 @@ def _dev_check(t, dtype, device, name):
         raise EhbError("%s must have dtype %s, got %s" % (name, dtype, t.dtype))
     if not t.is_contiguous():
         raise EhbError("%s must be contiguous" % name)
+
+
+class RefMasks:
+    """Reference masks registered once with a context (`Context.register_ref`): bit-packed on the device.  `first` / `n`
+    select a run of its views (`ref[2:6]` = views 2..5), so one registration serves sharded or sliced calls."""
+
+    def __init__(self, ctx, ref_id, n, H, W, first=0):
+        self.ctx, self.ref_id, self.n, self.H, self.W, self.first = ctx, ref_id, int(n), int(H), int(W), int(first)
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, sl):
+        if not isinstance(sl, slice) or sl.step not in (None, 1):
+            raise EhbError("registered reference masks can only be sliced into contiguous runs of views")
+        a, b, _ = sl.indices(self.n)
+        return RefMasks(self.ctx, self.ref_id, max(b - a, 0), self.H, self.W, self.first + a)
+
+    def release(self):
+        self.ctx.release_ref(self)
 
 
 class Context:
@@ -172,6 +198,29 @@ class Context:
         V, F = C.c_int(), C.c_int()
         _check(lib().ehb_mesh_info(self._h, mesh_id, C.byref(V), C.byref(F)))
         return V.value, F.value
+
+    # -- reference masks -----------------------------------------------------------------------------------
+    def register_ref(self, masks) -> RefMasks:
+        """masks (B,H,W) bool / uint8 / float32 (values 0 or 1), numpy or torch, host or device -> RefMasks handle."""
+        if isinstance(masks, np.ndarray):
+            masks = torch.from_numpy(np.ascontiguousarray(masks))
+        if masks.dtype == torch.bool:
+            masks = masks.to(torch.uint8)
+        if masks.dtype not in (torch.uint8, torch.float32):
+            masks = masks.to(torch.float32)
+        if masks.dim() != 3:
+            raise EhbError("reference masks must have shape (B, H, W)")
+        masks = masks.contiguous()
+        if masks.is_cuda and masks.device != self.device:
+            raise EhbError("reference masks live on %s, the context on %s" % (masks.device, self.device))
+        B, H, W = masks.shape
+        rid = C.c_int(-1)
+        _check(lib().ehb_ref_register(self._h, _ptr(masks), 1 if masks.dtype == torch.float32 else 0, int(masks.is_cuda),
+                                      B, H, W, C.byref(rid)))
+        return RefMasks(self, rid.value, B, H, W)
+
+    def release_ref(self, ref: RefMasks):
+        _check(lib().ehb_ref_release(self._h, ref.ref_id))
 
     # -- control -----------------------------------------------------------------------------------------
     def reserve(self, n_items, n_links, max_faces, H, W):
@@ -239,7 +288,7 @@ class Context:
         return g_mvp, g_pos
 
     def render_views_fused(self, mesh_ids, mvp, ref, H, W, backward=True, want_masks=True, out=None):
-        """mvp (B,L,4,4) f32, ref (B,H,W) f32 or u8 (or None) -> masks (B,H,W) f32 | None, loss (B,) f64,
+        """mvp (B,L,4,4) f32, ref (B,H,W) f32 or u8, a RefMasks handle, or None -> masks (B,H,W) f32 | None, loss (B,) f64,
         g_mvp (B,L,4,4) f64 | None.  `out` = (masks, loss, g_mvp) pre-allocated tensors to reuse."""
         _dev_check(mvp, torch.float32, self.device, "mvp")
         B, L = mvp.shape[0], mvp.shape[1]
@@ -250,7 +299,13 @@ class Context:
             masks = torch.empty((B, H, W), dtype=torch.float32, device=self.device) if want_masks else None
             loss = torch.empty((B,), dtype=torch.float64, device=self.device) if ref is not None else None
             g_mvp = torch.empty((B, L, 4, 4), dtype=torch.float64, device=self.device) if backward else None
-        if ref is not None and ref.dtype == torch.uint8:
+        if isinstance(ref, RefMasks):
+            if ref.ctx is not self or len(ref) != B or (ref.H, ref.W) != (H, W):
+                raise EhbError("registered reference: %d views of %dx%d on another context or of another shape" % (len(ref), ref.H, ref.W))
+            _check(lib().ehb_render_views_fused_ref(self._h, ids, L, B, _ptr(mvp), ref.ref_id, ref.first, H, W,
+                                                    int(bool(backward)), _ptr(masks), _ptr(loss), _ptr(g_mvp),
+                                                    _stream(self.device)))
+        elif ref is not None and ref.dtype == torch.uint8:
             _dev_check(ref, torch.uint8, self.device, "ref")
             _check(lib().ehb_render_views_fused_u8(self._h, ids, L, B, _ptr(mvp), _ptr(ref), H, W, int(bool(backward)),
                                                    _ptr(masks), _ptr(loss), _ptr(g_mvp), _stream(self.device)))
@@ -351,6 +406,18 @@ class Context:
                 raise EhbError("host buffers of an asynchronous step must be pinned and contiguous")
         _check(lib().ehb_solver_step_begin_u8(self._h, slot, ids, L, B, _ptr(mvp_host), _ptr(ref_u8_host), H, W,
                                               _ptr(loss_host), _ptr(g_mvp_host)))
+
+    def solver_step_begin_ref(self, slot, mesh_ids, mvp_host, ref: RefMasks, H, W, loss_host, g_mvp_host):
+        """Asynchronous host-buffer step against registered reference masks: only the matrices go up."""
+        B, L = mvp_host.shape[0], mvp_host.shape[1]
+        ids = (C.c_int * L)(*mesh_ids)
+        for t in (mvp_host, loss_host, g_mvp_host):
+            if not t.is_pinned() or not t.is_contiguous():
+                raise EhbError("host buffers of an asynchronous step must be pinned and contiguous")
+        if len(ref) != B:
+            raise EhbError("registered reference has %d views, the step %d" % (len(ref), B))
+        _check(lib().ehb_solver_step_begin_ref(self._h, slot, ids, L, B, _ptr(mvp_host), ref.ref_id, ref.first, H, W,
+                                               _ptr(loss_host), _ptr(g_mvp_host)))
 
     def solver_step_end(self, slot):
         _check(lib().ehb_solver_step_end(self._h, slot))

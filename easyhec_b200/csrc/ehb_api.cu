@@ -39,6 +39,14 @@ int fail(int code, const char* fmt, ...)
         if (e_ != cudaSuccess) return fail(EHB_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+struct Ref {                           // reference masks registered once (ehb_ref_register)
+    uint32_t* bits = nullptr;          // [B, H, ntx]  one bit per pixel, GL rows
+    uint32_t* cnt = nullptr;           // [B, ntiles]
+    unsigned long long* total = nullptr;   // [B]
+    int B = 0, H = 0, W = 0, ntx = 0, ntiles = 0;
+    bool live = false;
+};
+
 struct Mesh {
     float4* verts = nullptr;
     int4* faces = nullptr;
@@ -83,16 +91,11 @@ struct Scratch {
     DevBuf<EhbRec> bigRec;
     DevBuf<EhbUnit> units;
     DevBuf<uint32_t> batchBlk;        // parked heavy batches of k_raster
-    DevBuf<EhbJob> jobs;              // image-space stage: (tile, link) windows ...
-    DevBuf<uint4> tileEnt;
-    DevBuf<EhbPair> pairs;            // ... their silhouette pairs ...
-    DevBuf<float> maskBuf, gBuf;      // ... per-job antialiased masks and per-tile gradient windows
     EhbCounters* ctr = nullptr;
     void release()
     {
         vclip.release(); vsnap.release(); plane.release(); pool.release(); tileList.release(); emptyList.release();
         touch.release(); bigRec.release(); units.release(); batchBlk.release();
-        jobs.release(); tileEnt.release(); pairs.release(); maskBuf.release(); gBuf.release();
     }
 };
 
@@ -104,6 +107,7 @@ struct Ctx {
     int rule = 0;
     int nPipes = 3;
     std::vector<Mesh> meshes;
+    std::vector<Ref> refs;
     Scratch sc[N_SCRATCH];            // [0, MAX_PIPES): pipelines of a device-pointer call; then one per host-step slot
     cudaStream_t pipeStream[MAX_PIPES] = {};
     cudaEvent_t evFork = nullptr, evJoin[MAX_PIPES] = {};
@@ -277,6 +281,37 @@ __global__ void ehb_k_variance_finish(const unsigned long long* __restrict__ num
 }
 
 
+// Reference masks -> one bit per pixel (GL rows, a 32-bit word per (row, tile column)), set bits per tile interior and per
+// item.  One warp per word, lane = pixel; image row r holds GL row H - 1 - r.  nonBinary counts f32 values outside {0, 1}.
+template <typename T>
+__global__ void ehb_k_pack_ref(const T* __restrict__ ref, int B, int H, int W, int ntx, uint32_t* __restrict__ bits,
+                               uint32_t* __restrict__ cnt, unsigned long long* __restrict__ total,
+                               unsigned long long* __restrict__ nonBinary)
+{
+    const long long word = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (word >= (long long)B * H * ntx) return;
+    const int tx = (int)(word % ntx);
+    const long long t = word / ntx;
+    const int py = (int)(t % H), item = (int)(t / H);
+    const int px = tx * EHB_T + lane;
+    bool on = false, odd = false;
+    if (px < W) {
+        const T v = ref[((size_t)item * H + (H - 1 - py)) * W + px];
+        on = v != (T)0;
+        odd = on && v != (T)1;
+    }
+    const unsigned w = __ballot_sync(0xffffffffu, on), o = __ballot_sync(0xffffffffu, odd);
+    if (lane == 0) {
+        bits[word] = w;
+        if (w) {
+            atomicAdd(cnt + (size_t)item * ntx * ((H + EHB_T - 1) / EHB_T) + (size_t)(py / EHB_T) * ntx + tx, (unsigned)__popc(w));
+            atomicAdd(total + item, (unsigned long long)__popc(w));
+        }
+        if (o && nonBinary && sizeof(T) == 4) atomicAdd(nonBinary, (unsigned long long)__popc(o));
+    }
+}
+
 // Developer knob: integer from the environment, read once per name (launch-shape experiments without a rebuild).
 int tune_int(const char* name, int dflt)
 {
@@ -297,7 +332,50 @@ struct Io {
     float* masks = nullptr; double* loss = nullptr; double* gmvp = nullptr; float* gpos = nullptr;
     const float* dy = nullptr; uint8_t* out_u8 = nullptr; float* score = nullptr; int C = 0;
     int do_bwd = 0, clamp = 0; float invB = 1.f;
+    const uint32_t* refBits = nullptr; const uint32_t* refCnt = nullptr; const unsigned long long* refTotal = nullptr;
 };
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// masks f32 [items][H][W] as a 3-D tensor with 32 x 32 x 1 boxes.  false: not expressible (pitch / alignment) -> plain stores.
+bool make_mask_map(CUtensorMap* map, float* masks, int items, int H, int W)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || !masks || (W & 3) != 0 || (((uintptr_t)masks) & 15) != 0 || tune_int("EHB_NO_TMA", 0)) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)items};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * 4 * (cuuint64_t)H};
+    const cuuint32_t box[3] = {EHB_T, EHB_T, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, masks, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// pair capacity of a tile's shared-memory arrays: 1536 by default; the scratch-growth factor raises it to the maximum a
+// single window can produce (test mode, pool budget 0: starts tiny so that the multi-round path and the growth run)
+int tile_pair_cap(double poolFactor)
+{
+    const int cap = (int)(768.0 * poolFactor);
+    return std::max(64, std::min(2432, (cap + 15) & ~15));
+}
 
 // Launch helper: kernels after the first of a pass are chained with programmatic dependent launch when EHB_PDL is on.
 template <typename... KArgs, typename... Args>
@@ -343,22 +421,6 @@ int ensure_scratch(Ctx* c, Scratch& sc, int items, int L, int Lp, int H, int W, 
     if ((r = sc.vclip.ensure((size_t)items * std::max(Vtot, 1), capturing))) return r;
     if ((r = sc.vsnap.ensure((size_t)items * std::max(Vtot, 1), capturing))) return r;
     const int ntiles = ((W + EHB_T - 1) / EHB_T) * ((H + EHB_T - 1) / EHB_T);
-    if (Lp == L) {   // image-space stage (not needed by the packed-robot mode)
-        // Jobs: at most one per (tile, link).  That worst case is reserved while its masks stay under 1 GB; beyond it the
-        // list holds poolFactor jobs per tile and grows on the overflow flag, like the plane pool.
-        const double worstJobs = (double)items * ntiles * L;
-        const bool tiny = c->poolBudget == 0.0;   // test mode: start from the minimum so that growth is exercised
-        const double perTile = tiny ? std::min((double)L, c->poolFactor)
-                                    : (worstJobs * EHB_MSZ * 4.0 <= 1e9 ? (double)L : std::min((double)L, std::max(2.0, c->poolFactor)));
-        const size_t jobCap = std::max<size_t>(tiny ? 16 : 4096, (size_t)((double)items * ntiles * perTile));
-        const size_t pairCap = (size_t)((double)jobCap * (tiny ? 4.0 : 32.0) * std::max(1.0, c->poolFactor / 2.0));
-        if (jobCap > 0x7FFFFFFFull || pairCap > 0x7FFFFFFFull) return fail(EHB_E_ARG, "too many tiles for one launch");
-        if ((r = sc.jobs.ensure(jobCap, capturing))) return r;
-        if ((r = sc.tileEnt.ensure((size_t)items * ntiles, capturing))) return r;
-        if ((r = sc.pairs.ensure(pairCap, capturing))) return r;
-        if ((r = sc.maskBuf.ensure(jobCap * EHB_MSZ, capturing))) return r;
-        if ((r = sc.gBuf.ensure((size_t)items * ntiles * EHB_MSZ, capturing))) return r;
-    }
     if ((r = sc.plane.ensure((size_t)items * Lp, capturing))) return r;
     if ((r = sc.tileList.ensure((size_t)items * ntiles, capturing))) return r;
     if ((r = sc.touch.ensure((size_t)items * ntiles, capturing))) return r;
@@ -415,8 +477,8 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
     p.tileList = sc.tileList.p; p.emptyList = sc.emptyList.p; p.touch = unionMode ? nullptr : sc.touch.p; p.bigRec = sc.bigRec.p; p.units = sc.units.p; p.bigCap = (int)(sc.bigRec.n / EHB_NQ); p.unitCap = (int)(sc.units.n / EHB_NQ); p.batchBlk = tune_int("EHB_NO_OFFLOAD", 0) ? nullptr : sc.batchBlk.p; p.batchCap = c->poolBudget == 0.0 ? 1 : BATCH_CAP / EHB_NQ; p.ctr = sc.ctr;
     p.ref = io.ref; p.ref_u8 = io.ref_u8; p.masks = io.masks; p.loss = io.loss; p.gmvp = io.gmvp; p.gpos = io.gpos;
     p.dy = io.dy; p.out_u8 = io.out_u8;
-    p.jobs = sc.jobs.p; p.tileEnt = sc.tileEnt.p; p.pairs = sc.pairs.p; p.maskBuf = sc.maskBuf.p; p.gBuf = sc.gBuf.p;
-    p.jobCap = (int)sc.jobs.n; p.pairCap = (int)sc.pairs.n;
+    p.refBits = io.refBits; p.refCnt = io.refCnt; p.refTotal = io.refTotal;
+    p.useTma = (!unionMode && io.masks && make_mask_map(&p.tmMask, io.masks, items, H, W)) ? 1 : 0;
     p.dbgbuf = c->dbgbuf;
 
     cudaEvent_t* ev = nullptr;
@@ -430,7 +492,11 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
         c->evUsed += 5;
     }
     const int chunks = std::max(1, rb.boff[L]);   // 32-triangle batches per item (a batch never straddles two links)
-    const int streamBlocks = (unionMode || mode == EHB_MODE_AA_BWD) ? 0 : c->nSM * tune_int("EHB_STREAM_MULT", 2);
+    // spare CTAs of the raster launch finish the tiles no link touches; with registered reference masks (or none) that is
+    // only the zero fill of the masks -- nothing to do at all when no masks are wanted
+    const bool legacyStream = mode == EHB_MODE_FUSED && (io.ref || io.ref_u8);
+    const int streamBlocks = (unionMode || mode == EHB_MODE_AA_BWD || (!legacyStream && !io.masks)) ? 0
+                             : c->nSM * ((legacyStream || !p.useTma) ? tune_int("EHB_STREAM_MULT", 2) : 1);
     const long long tickets = ((long long)chunks * items + EHB_RBATCH - 1) / EHB_RBATCH;
     long long rasterBlocks = (tickets + EHB_RWARPS - 1) / EHB_RWARPS;
 #ifdef EHB_RPERSIST
@@ -447,21 +513,19 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
               vchunks, clearBlocks));
     if (ev) cudaEventRecord(ev[2], st);
     CU(launch(ehb_k_raster, dim3((unsigned)(streamBlocks + rasterBlocks)), dim3(EHB_RWARPS * 32), 0, st, true, rb, p, streamBlocks, chunks));
-    const int jobBlocks = unionMode ? 0 : 16;
-    CU(launch(ehb_k_raster_big, dim3(c->nSM * EHB_BMIN_BLOCKS + jobBlocks), dim3(256), 0, st, true, p, jobBlocks));
+    CU(launch(ehb_k_raster_big, dim3(c->nSM * EHB_BMIN_BLOCKS), dim3(256), 0, st, true, p));
     if (ev) cudaEventRecord(ev[3], st);
     if (unionMode) {
         const int nq = ((W + 3) / 4) * H;
         CU(launch(ehb_k_union_out, dim3((unsigned)std::min((nq + 255) / 256, 4 * c->nSM), (unsigned)items), dim3(256), 0, st, true, p));
     } else {
-        const bool doBwd = (mode == EHB_MODE_FUSED && io.do_bwd) || mode == EHB_MODE_AA_BWD;
-        CU(launch(ehb_k_windows, dim3(c->nSM * tune_int("EHB_WIN_OCC", 7)), dim3(EHB_WWARPS * 32), 0, st, true, rb, p));
-        CU(launch(ehb_k_compose, dim3(c->nSM * 16), dim3(EHB_CTHREADS), 0, st, true, p));
-        if (doBwd) CU(launch(ehb_k_pairgrad, dim3(c->nSM * 2), dim3(256), 0, st, true, rb, p));
-        c->launches += doBwd ? 2 : 1;
+        const int cap = tile_pair_cap(c->poolFactor);
+        const long long maxTiles = (long long)items * p.ntiles;
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(maxTiles, (long long)c->nSM * tune_int("EHB_TILE_CTAS", 8)));
+        CU(launch(ehb_k_tiles, dim3(grid), dim3(EHB_TTHREADS), ehb_tile_smem_bytes(cap), st, true, rb, p, cap));
     }
     if (ev) cudaEventRecord(ev[4], st);
-    c->launches += 5;
+    c->launches += 5;   // table, front, raster, raster_big, tiles | union_out
     CU(cudaGetLastError());
     return EHB_OK;
 }
@@ -487,6 +551,10 @@ int run_split(Ctx* c, const int* mesh_ids, int L, int items, const float* mvp_de
         if (s.out_u8) s.out_u8 += first * px;
         if (s.loss) s.loss += first;
         if (s.gmvp) s.gmvp += (size_t)first * L * 16;
+        if (s.refBits) {
+            const int ntx = (W + EHB_T - 1) / EHB_T, nty = (H + EHB_T - 1) / EHB_T;
+            s.refBits += (size_t)first * H * ntx; s.refCnt += (size_t)first * ntx * nty; s.refTotal += first;
+        }
         cudaStream_t sk = k == 0 ? st : c->pipeStream[k];
         if (k > 0) CU(cudaStreamWaitEvent(sk, c->evFork, 0));
         const int r = run_pass(c, c->sc[k], mesh_ids, L, cnt, mvp_dev + (size_t)first * L * 16, H, W, mode, s, sk);
@@ -537,6 +605,7 @@ int ehb_ctx_create(int device, ehb_ctx_t* out)
         CU(cudaStreamCreateWithFlags(&c->pipeStream[k], cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&c->evJoin[k], cudaEventDisableTiming));
     }
+    CU(cudaFuncSetAttribute(ehb_k_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ehb_tile_smem_bytes(2432)));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occRaster, ehb_k_raster, EHB_RWARPS * 32, 0));
     c->occRaster = std::max(1, c->occRaster);
     *out = c;
@@ -550,6 +619,7 @@ int ehb_ctx_destroy(ehb_ctx_t h)
     DeviceGuard guard(c->device);
     cudaDeviceSynchronize();
     for (auto& m : c->meshes) if (m.live) { cudaFree(m.verts); cudaFree(m.faces); cudaFree(m.opp); cudaFree(m.boxes); cudaFree(m.fboxes); }
+    for (auto& r : c->refs) if (r.live) { cudaFree(r.bits); cudaFree(r.cnt); cudaFree(r.total); }
     for (int k = 0; k < MAX_PIPES; k++) { cudaStreamDestroy(c->pipeStream[k]); cudaEventDestroy(c->evJoin[k]); }
     for (int k = 0; k < N_SCRATCH; k++) c->sc[k].release();
     for (int k = 0; k < N_SLOTS; k++) { cudaStreamDestroy(c->slotStream[k]); cudaEventDestroy(c->slotDone[k]); c->slotMvp[k].release(); c->slotOut[k].release(); c->slotRef[k].release(); }
@@ -801,6 +871,91 @@ int ehb_render_views_fused_u8(ehb_ctx_t h, const int* mesh_ids, int L, int B, co
     return run_split((Ctx*)h, mesh_ids, L, B, mvp_dev, H, W, EHB_MODE_FUSED, io, (cudaStream_t)stream);
 }
 
+
+int ehb_ref_register(ehb_ctx_t h, const void* ref, int dtype, int on_device, int B, int H, int W, int* ref_id)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || !ref || !ref_id || B < 1 || H < 1 || W < 1 || H > 8160 || W > 8160 || (dtype != EHB_REF_U8 && dtype != EHB_REF_F32))
+        return fail(EHB_E_ARG, "bad reference-mask arguments");
+    DeviceGuard guard(c->device);
+    const size_t esz = dtype == EHB_REF_F32 ? 4 : 1, n = (size_t)B * H * W;
+    void* tmp = nullptr;
+    const void* src = ref;
+    if (!on_device) {
+        CU(cudaMalloc(&tmp, n * esz));
+        if (cudaMemcpy(tmp, ref, n * esz, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(tmp); return fail(EHB_E_CUDA, "copy of the reference masks failed"); }
+        src = tmp;
+    }
+    Ref r;
+    r.B = B; r.H = H; r.W = W; r.ntx = (W + EHB_T - 1) / EHB_T; r.ntiles = r.ntx * ((H + EHB_T - 1) / EHB_T);
+    const size_t nw = (size_t)B * H * r.ntx;
+    unsigned long long* bad = nullptr;
+    CU(cudaMalloc((void**)&r.bits, nw * 4));
+    CU(cudaMalloc((void**)&r.cnt, (size_t)B * r.ntiles * 4));
+    CU(cudaMalloc((void**)&r.total, (size_t)B * 8));
+    CU(cudaMalloc((void**)&bad, 8));
+    CU(cudaMemset(r.cnt, 0, (size_t)B * r.ntiles * 4));
+    CU(cudaMemset(r.total, 0, (size_t)B * 8));
+    CU(cudaMemset(bad, 0, 8));
+    const unsigned blocks = (unsigned)((nw * 32 + 255) / 256);
+    if (dtype == EHB_REF_F32) ehb_k_pack_ref<float><<<blocks, 256>>>((const float*)src, B, H, W, r.ntx, r.bits, r.cnt, r.total, bad);
+    else ehb_k_pack_ref<uint8_t><<<blocks, 256>>>((const uint8_t*)src, B, H, W, r.ntx, r.bits, r.cnt, r.total, bad);
+    unsigned long long nbad = 0;
+    cudaError_t e = cudaMemcpy(&nbad, bad, 8, cudaMemcpyDeviceToHost);
+    cudaFree(bad);
+    if (tmp) cudaFree(tmp);
+    c->launches += 1;
+    if (e != cudaSuccess || nbad) {
+        cudaFree(r.bits); cudaFree(r.cnt); cudaFree(r.total);
+        if (e != cudaSuccess) return fail(EHB_E_CUDA, "packing the reference masks failed: %s", cudaGetErrorString(e));
+        return fail(EHB_E_ARG, "%llu reference-mask values are neither 0 nor 1: only binary masks can be registered "
+                               "(use ehb_render_views_fused for soft references)", nbad);
+    }
+    r.live = true;
+    int id = -1;
+    for (size_t i = 0; i < c->refs.size(); i++) if (!c->refs[i].live) { id = (int)i; break; }
+    if (id < 0) { id = (int)c->refs.size(); c->refs.push_back(r); } else c->refs[id] = r;
+    *ref_id = id;
+    return EHB_OK;
+}
+
+int ehb_ref_release(ehb_ctx_t h, int ref_id)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || ref_id < 0 || ref_id >= (int)c->refs.size() || !c->refs[ref_id].live) return fail(EHB_E_ARG, "unknown reference id %d", ref_id);
+    DeviceGuard guard(c->device);
+    CU(cudaDeviceSynchronize());
+    Ref& r = c->refs[ref_id];
+    cudaFree(r.bits); cudaFree(r.cnt); cudaFree(r.total);
+    r = Ref();
+    return EHB_OK;
+}
+
+static int ref_io(Ctx* c, int ref_id, int first, int B, int H, int W, Io& io)
+{
+    if (!c || ref_id < 0 || ref_id >= (int)c->refs.size() || !c->refs[ref_id].live) return fail(EHB_E_ARG, "unknown reference id %d", ref_id);
+    const Ref& r = c->refs[ref_id];
+    if (r.H != H || r.W != W) return fail(EHB_E_ARG, "reference masks are %dx%d, the call renders %dx%d", r.H, r.W, H, W);
+    if (first < 0 || B < 0 || first + B > r.B) return fail(EHB_E_ARG, "views [%d, %d) outside the %d registered reference masks", first, first + B, r.B);
+    io.refBits = r.bits + (size_t)first * H * r.ntx;
+    io.refCnt = r.cnt + (size_t)first * r.ntiles;
+    io.refTotal = r.total + first;
+    return EHB_OK;
+}
+
+int ehb_render_views_fused_ref(ehb_ctx_t h, const int* mesh_ids, int L, int B, const float* mvp_dev, int ref_id, int first_view,
+                               int H, int W, int do_bwd, float* masks_dev, double* loss_dev, double* g_mvp_dev, void* stream)
+{
+    if (!mesh_ids) return fail(EHB_E_ARG, "null mesh id list");
+    if (!loss_dev || (do_bwd && !g_mvp_dev)) return fail(EHB_E_ARG, "null pointer argument");
+    Io io;
+    int r = ref_io((Ctx*)h, ref_id, first_view, B, H, W, io);
+    if (r) return r;
+    io.masks = masks_dev; io.loss = loss_dev; io.gmvp = do_bwd ? g_mvp_dev : nullptr;
+    io.do_bwd = do_bwd ? 1 : 0; io.clamp = 1; io.invB = B > 0 ? 1.0f / (float)B : 1.f;
+    return run_split((Ctx*)h, mesh_ids, L, B, mvp_dev, H, W, EHB_MODE_FUSED, io, (cudaStream_t)stream);
+}
+
 int ehb_render_binary_batch(ehb_ctx_t h, const int* mesh_ids, int L, int N, const float* mvp_dev, int H, int W,
                             uint8_t* out_dev, void* stream)
 {
@@ -968,6 +1123,33 @@ int ehb_solver_step_begin_u8(ehb_ctx_t h, int slot, const int* mesh_ids, int L, 
     CU(cudaMemcpyAsync(c->slotRef[slot].p, ref_u8_host, npx, cudaMemcpyHostToDevice, st));
     Io io;
     io.ref_u8 = c->slotRef[slot].p; io.loss = c->slotOut[slot].p; io.gmvp = c->slotOut[slot].p + B;
+    io.do_bwd = 1; io.clamp = 1; io.invB = 1.0f / (float)B;
+    r = run_pass(c, c->sc[MAX_PIPES + slot], mesh_ids, L, B, c->slotMvp[slot].p, H, W, EHB_MODE_FUSED, io, st);
+    if (r) return r;
+    CU(cudaMemcpyAsync(loss_host, c->slotOut[slot].p, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(g_mvp_host, c->slotOut[slot].p + B, nm * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->ctrHost + MAX_PIPES + slot, c->ctr + MAX_PIPES + slot, sizeof(EhbCounters), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(c->slotDone[slot], st));
+    return EHB_OK;
+}
+
+
+int ehb_solver_step_begin_ref(ehb_ctx_t h, int slot, const int* mesh_ids, int L, int B, const float* mvp_host, int ref_id,
+                              int first_view, int H, int W, double* loss_host, double* g_mvp_host)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || slot < 0 || slot >= N_SLOTS || !mvp_host || !loss_host || !g_mvp_host) return fail(EHB_E_ARG, "bad step_begin arguments");
+    if (B < 1 || L < 1) return fail(EHB_E_ARG, "empty batch");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = c->slotStream[slot];
+    int r;
+    const size_t nm = (size_t)B * L * 16, no = (size_t)B + nm;
+    if ((r = c->slotMvp[slot].ensure(nm, false))) return r;
+    if ((r = c->slotOut[slot].ensure(no, false))) return r;
+    Io io;
+    if ((r = ref_io(c, ref_id, first_view, B, H, W, io))) return r;
+    CU(cudaMemcpyAsync(c->slotMvp[slot].p, mvp_host, nm * sizeof(float), cudaMemcpyHostToDevice, st));
+    io.loss = c->slotOut[slot].p; io.gmvp = c->slotOut[slot].p + B;
     io.do_bwd = 1; io.clamp = 1; io.invB = 1.0f / (float)B;
     r = run_pass(c, c->sc[MAX_PIPES + slot], mesh_ids, L, B, c->slotMvp[slot].p, H, W, EHB_MODE_FUSED, io, st);
     if (r) return r;

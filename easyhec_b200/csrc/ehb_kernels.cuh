@@ -25,28 +25,13 @@
 // No intermediate image (rast, colour, antialias work queue, clip-space vertex buffer) is ever written.
 #pragma once
 #include "ehb_device.cuh"
+#include "ehb_tma.cuh"
 
 #define EHB_T 32            // tile interior
 #define EHB_RS 35           // window row stride = T + max halo (1 low, 2 high)
 #define EHB_NP (EHB_RS * EHB_RS)
 
 enum { EHB_MODE_FUSED = 0, EHB_MODE_AA_FWD = 1, EHB_MODE_AA_BWD = 2, EHB_MODE_UNION = 3 };
-
-struct __align__(16) EhbPair {   // one silhouette pixel pair of a job (32 B, written / read as two words)
-    uint32_t packed;         // idx (11) | d << 11 | own << 12 | side << 13 | di << 14   (idx = p0 in the 35x35 window)
-    uint32_t tri;            // triangle of the covered pixel
-    float alpha;             // blend weight (0: no silhouette edge crosses the segment between the two centres)
-    uint32_t job;
-    int item, tile, link, entry;   // the job's fields, repeated so that the backward needs no second lookup
-};
-
-struct __align__(16) EhbJob {    // one (tile, link) window that some triangle of the link reaches into (48 B)
-    int item, tile, link;
-    int entry;               // position of the tile in the tile list: its gradient window and first job are indexed by it
-    int x0, y0, w, h;        // the link's depth plane (copied from EhbPlane: the window load needs no second lookup)
-    long long off;
-    long long pad;
-};
 
 struct EhbPlane {            // depth plane of one (item, link): pixels [x0, x0+w) x [y0, y0+h), GL rows
     int x0, y0, w, h;
@@ -80,15 +65,15 @@ struct __align__(128) EhbCounters {
         unsigned int nBatchBlk;  // batches with many rows: records parked, the rows beyond the inline share become units too
         unsigned int pad[29];
     } q[32];
-    // line 3: job list and pair pool of the image-space stage
-    unsigned int nJobs;
-    unsigned int pairCursor;
-    unsigned int pad3[30];
+    // (one spare line)
+    unsigned int pad3[32];
     unsigned long long dbg[16];   // EHB_TIMING builds: cycles per phase of k_tiles (thread 0 of every CTA)
 };
 static_assert(sizeof(EhbCounters) % 128 == 0, "counter lines");
 
 struct EhbParams {
+    CUtensorMap tmMask;      // masks as a [items][H][W] f32 tensor, box 32 x 32 x 1 (valid when useTma)
+    int useTma;
     int H, W, ntx, nty, ntiles;
     int items, L, Lp, Ftot, Vtot;   // Lp = planes per item: L (per-link visibility) or 1 (packed robot)
     int hlo, hhi;
@@ -119,12 +104,12 @@ struct EhbParams {
     float* gpos;             // [V, 4] (AA_BWD, single link) or NULL
     const float* dy;         // [items, H, W]  AA_BWD
     uint8_t* out_u8;         // [items, H, W]  UNION
-    EhbJob* jobs;            // [jobCap]  (tile, link) windows, the jobs of a tile consecutive and in link order
-    uint4* tileEnt;          // [items * ntiles]  per listed tile (by list position): {tile id, link bits, first job, -}
-    EhbPair* pairs;          // [pairCap] silhouette pairs, the pairs of a job consecutive
-    float* maskBuf;          // [jobCap, 33, 36]  antialiased mask of each job's out region
-    float* gBuf;             // [items * ntiles, 33, 36]  dL/dsum of each listed tile's out region
-    int jobCap, pairCap;
+    // reference masks registered once (ehb_ref_register): one bit per pixel, GL rows, a 32-bit word per (row, tile column);
+    // refCnt = set bits of every tile's interior, refTotal = set bits of the item.  loss[item] starts at refTotal and every
+    // listed tile adds (its loss - its refCnt): the tiles no link touches are never read.
+    const uint32_t* refBits; // [items, H, ntx]
+    const uint32_t* refCnt;  // [items, ntiles]
+    const unsigned long long* refTotal;   // [items]
     unsigned long long* dbgbuf;   // unused (kept for the developer ABI)
 };
 
@@ -187,14 +172,13 @@ __global__ void __launch_bounds__(256) ehb_k_table(const __grid_constant__ EhbRo
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         p.ctr->nTiles = 0u; p.ctr->nLight = 0u; p.ctr->nEmpty = 0u; p.ctr->workCursor = 0u;
         p.ctr->rasterCursor = (unsigned)p.rasterStart;
-        p.ctr->nJobs = 0u; p.ctr->pairCursor = 0u;
     }
     if (blockIdx.x == 0 && threadIdx.x < EHB_NQ) {
         p.ctr->q[threadIdx.x].nBigRec = 0u; p.ctr->q[threadIdx.x].nUnits = 0u; p.ctr->q[threadIdx.x].nBatchBlk = 0u;
     }
     // outputs that the later kernels accumulate into
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.items; i += gridDim.x * blockDim.x) {
-        if (p.loss) p.loss[i] = 0.0;
+        if (p.loss) p.loss[i] = p.refTotal ? (double)p.refTotal[i] : 0.0;
     }
     if (p.gmvp)
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.items * p.L * 16; i += gridDim.x * blockDim.x) p.gmvp[i] = 0.0;
@@ -628,13 +612,33 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
                                                                 int chunks)
 {
     ehb_pdl_enter();
-    __shared__ uint32_t s_rec[EHB_RWARPS][32 * 32];   // 32 records per warp, transposed
+    __shared__ __align__(128) uint32_t s_rec[EHB_RWARPS][32 * 32];   // 32 records per warp, transposed
     __shared__ int s_off[EHB_RWARPS][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if ((int)blockIdx.x < streamBlocks) {
-        // spare CTAs of this launch finish the tiles no link touches (mask = 0, loss += ref^2): pure HBM streaming that
-        // overlaps the latency-bound rasterization instead of sitting in front of it
+        // spare CTAs of this launch finish the tiles no link touches: pure HBM streaming that overlaps the
+        // instruction-bound rasterization instead of sitting in front of it
         const int n = (int)p.ctr->nEmpty;
+        const bool legacy = (p.mode == EHB_MODE_FUSED && (p.ref || p.ref_u8)) || !p.useTma;
+        if (!legacy) {
+            // mask = 0 with ONE bulk tensor store per tile (UTMASTG) from a zeroed 4 KB shared-memory tile; out-of-image
+            // parts of a tile are clipped by the hardware.  (Registered reference masks: the loss of these tiles is part of
+            // refTotal, nothing is read.)
+            float* zero = reinterpret_cast<float*>(&s_rec[0][0]);
+            for (int i = threadIdx.x; i < EHB_T * EHB_T; i += blockDim.x) zero[i] = 0.f;
+            ehb_fence_proxy_async();
+            __syncthreads();
+            if (lane == 0) {
+                for (int i = blockIdx.x * EHB_RWARPS + warp; i < n; i += streamBlocks * EHB_RWARPS) {
+                    const int wid = (int)p.emptyList[i];
+                    const int item = wid / p.ntiles, tile = wid - item * p.ntiles;
+                    ehb_tma_store_3d(&p.tmMask, zero, (tile % p.ntx) * EHB_T, p.H - EHB_T - (tile / p.ntx) * EHB_T, item);
+                }
+                ehb_bulk_commit();
+                ehb_bulk_wait_read();
+            }
+            return;
+        }
         for (int i = blockIdx.x * EHB_RWARPS + warp; i < n; i += streamBlocks * EHB_RWARPS) {
             const int wid = (int)p.emptyList[i];
             const int item = wid / p.ntiles, tile = wid - item * p.ntiles;
@@ -838,22 +842,16 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
 }
 
 // Deferred triangles: warps stride over the unit list; one unit = a 64 x 32 pixel window of one triangle's bbox.
-__device__ __forceinline__ void ehb_build_jobs(const EhbParams& p, int firstWarp, int nWarps, int lane);
 
 #ifndef EHB_BMIN_BLOCKS
 #define EHB_BMIN_BLOCKS 4
 #endif
-__global__ void __launch_bounds__(256, EHB_BMIN_BLOCKS) ehb_k_raster_big(const __grid_constant__ EhbParams p, int jobBlocks)
+__global__ void __launch_bounds__(256, EHB_BMIN_BLOCKS) ehb_k_raster_big(const __grid_constant__ EhbParams p)
 {
     ehb_pdl_enter();
     __shared__ __align__(16) uint32_t s_blk[8][EHB_BLK_WORDS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if ((int)blockIdx.x >= (int)gridDim.x - jobBlocks) {
-        // the touch bitmap is final (k_raster has completed): spare CTAs turn it into the job list of the image-space stage
-        ehb_build_jobs(p, ((int)blockIdx.x - ((int)gridDim.x - jobBlocks)) * 8 + warp, jobBlocks * 8, lane);
-        return;
-    }
-    const int nUnitBlocks = (int)gridDim.x - jobBlocks;
+    const int nUnitBlocks = (int)gridDim.x;
     // units of all sub-queues as one list: lane s holds the (inclusive) prefix of the sub-queue sizes
     int qn = min((int)p.ctr->q[lane].nUnits, p.unitCap), qinc = qn;
 #pragma unroll

@@ -1,40 +1,38 @@
-// ehb_tiles.cuh -- the image-space half of a pass: antialias, compose, loss, backward.
+// ehb_tiles.cuh -- the image-space half of a pass: antialias, compose, loss, backward -- ONE kernel.
 //
 // The reference antialiases every link on its own, sums the per-link masks and clamps (rb_solver.py:62-68), and its
-// backward scatters one gradient per silhouette pixel pair (dr.antialias).  On the chip this work is a
-// few thousand small, latency-bound jobs per pass; what matters is that ALL of them are in flight at once and that no
-// job waits for another.  So the stage is three flat kernels over three work lists instead of one CTA per tile that
-// walks its links, its phases and its pairs in sequence:
-//   (jobs)     a job = one (tile, link) window that some triangle of the link reaches into; listed by spare CTAs of
-//              k_raster_big from the touch bitmap, the jobs of a tile are consecutive and in link order
-//   k_windows  one WARP per job, no block barrier: 35x35 window of the link's depth plane -> row coverage masks by
-//              ballot -> silhouette pairs by XOR of neighbouring masks -> blend weights (one pair per lane) -> the
-//              link's antialiased mask of the tile's out region (33 x 33, L2-resident scratch) + the pair entries
-//   k_compose  one warp per tile: S = min(sum of its jobs' masks in link order, 1), mask write, (S - ref)^2,
-//              g = dL/dsum into the tile's gradient window
-//   k_pairgrad one THREAD per pair entry: analytic vertex gradients contracted with [x y z 1] on the fly, warp-shuffle
-//              reduction per (item, link), fp64 atomicAdd into d loss / d mvp
+// backward scatters one gradient per silhouette pixel pair (dr.antialias).  Here one CTA owns one listed
+// 32x32 tile and keeps everything of it in shared memory, so that no intermediate (per-link mask, gradient window,
+// pair list) ever goes to L2 / HBM and the whole stage is a single launch:
+//   A  windows   35x35 window of every link's depth plane that reaches into the tile -> triangle ids in shared memory
+//                (all 256 threads load, every load of the phase in flight at once), row coverage masks by ballot
+//   B  pairs     silhouette pixel pairs by XOR of neighbouring coverage masks (one warp per link, lane = row) -> ONE pair
+//                list for the tile
+//   C  weights   blend weight of every pair (ehb_aa_pair), all threads stride over the tile's list: the work of a tile is
+//                balanced over its 8 warps whatever its links look like
+//   D  masks     per link: coverage as floats + the four contribution kinds in the reference's order
+//   E  compose   S = min(sum of the link masks in link order, 1) -> staging tile -> ONE TMA tensor store (UTMASTG);
+//                (S - ref)^2 -> loss; g = dL/dsum of the out region stays in shared memory
+//   F  backward  every owned pair with a non-zero weight: analytic gradient of its two edge vertices
+//                (ehb_aa_pair_grad), contracted with [x y z 1] on the fly (fp64), reduced per link by shuffles and
+//                shared-memory accumulators, 12 fp64 atomics per (tile, link) into d loss / d mvp
+// Links are processed in rounds of at most EHB_RL (their windows' storage), a round's pairs must fit the pair arrays
+// (capacity = a launch parameter): a tile that needs several rounds runs A-D per round for the forward, and A-C again
+// per round for the backward (g is only known once every link has been composed).  Tiles of a robot arm need one round.
 #pragma once
 #include "ehb_kernels.cuh"
 
 #define EHB_MROWS (EHB_T + 1)            // out region of a tile: interior + one row / column on the high side
-#define EHB_MW 36                        // row pitch (floats) of a job mask / gradient window: 16-byte aligned rows
+#define EHB_MW 36                        // row pitch (floats) of a link mask / the S / g window
 #define EHB_MSZ (EHB_MROWS * EHB_MW)
-#define EHB_NSEG (EHB_T * 4)             // out region: 32 rows x 4 eight-pixel segments ...
-#define EHB_NSEG_EXT (4 + EHB_T + 1)     // ... + row 32 (4 segments) + column 32 (33 single pixels) when the backward follows
-#ifndef EHB_WWARPS
-#define EHB_WWARPS 4                     // warps (jobs in flight) per k_windows CTA
+#ifndef EHB_RL
+#define EHB_RL 5                         // links whose windows are resident at a time
 #endif
-#define EHB_WPAIRS 256                   // pairs of a job whose packed word / blend weight stay in shared memory
-
-// Out-region work item s -> (row qy, first column qx0, pixels n): eight consecutive pixels of one row, then the extra
-// row / column that exist when the backward follows in the same pass.
-__device__ __forceinline__ void ehb_out_segment(int s, int& qy, int& qx0, int& n)
-{
-    if (s < EHB_NSEG) { qy = s >> 2; qx0 = (s & 3) * 8; n = 8; }
-    else if (s < EHB_NSEG + 4) { qy = EHB_T; qx0 = (s - EHB_NSEG) * 8; n = 8; }
-    else { qy = s - EHB_NSEG - 4; qx0 = EHB_T; n = 1; }   // column 32, corner included
-}
+#define EHB_TTHREADS 256
+#define EHB_TWARPS (EHB_TTHREADS / 32)
+#define EHB_IDS_WORDS (EHB_NP + 3)       // ids of one window (35 x 35); the same storage later holds the link's mask
+static_assert(EHB_IDS_WORDS >= EHB_MSZ, "the mask of a link reuses its window's storage");
+static_assert(EHB_RL <= EHB_TWARPS, "one warp per resident link in the per-link phases");
 
 __device__ __forceinline__ unsigned long long ehb_bits(int lo, int hi)   // bits lo..hi (inclusive), empty if lo > hi
 {
@@ -49,164 +47,150 @@ __device__ __forceinline__ uint32_t ehb_list_at(const EhbParams& p, unsigned e, 
     return p.tileList[e < nHeavy ? e : (unsigned)(p.items * p.ntiles) - 1u - (e - nHeavy)];
 }
 
-// ------------------------------------------------------------------------------------------------ job list
-// One lane per listed tile: its touch bits become consecutive jobs (link order); one queue atomic per warp.
-__device__ __forceinline__ void ehb_build_jobs(const EhbParams& p, int firstWarp, int nWarps, int lane)
+struct EhbSlot {                         // one resident link of the tile
+    int link;
+    int x0, y0, w, h;                    // its depth plane
+    long long off;
+    int pairBase, nPairs;                // its part of the tile's pair list
+};
+
+// dynamic shared memory of a CTA (byte offsets; every block 16-byte aligned, the staging tile 128-byte aligned)
+struct EhbTileSmem {
+    float* stage;                        // [32][32]   composed tile, source of the TMA store
+    float* S;                            // [33][36]   running sum of the link masks, then g = dL/dsum
+    uint32_t* ids;                       // [RL][IDS_WORDS]
+    unsigned long long* cov;             // [RL][36]
+    float* alpha;                        // [cap]
+    uint32_t* ptri;                      // [cap]
+    unsigned short* pk;                  // [cap]  idx (11) | d << 11 | own << 12 | side << 13 | di << 14
+    unsigned char* pslot;                // [cap]
+    double* gacc;                        // [RL][12]
+    EhbSlot* slot;                       // [RL]
+    double* lsum;                        // [TWARPS]
+    int* misc;                           // [8]
+};
+__host__ __device__ inline size_t ehb_tile_smem_bytes(int cap)
 {
-    const unsigned nHeavy = p.ctr->nTiles, nEntries = nHeavy + p.ctr->nLight;
-    for (unsigned e0 = (unsigned)firstWarp * 32u; e0 < nEntries; e0 += (unsigned)nWarps * 32u) {
-        const unsigned e = e0 + (unsigned)lane;
-        uint32_t wid = 0, bits = 0;
-        if (e < nEntries) {
-            wid = ehb_list_at(p, e, nHeavy);
-            bits = p.touch[wid] & (p.L >= 32 ? 0xFFFFFFFFu : ((1u << p.L) - 1u));
-        }
-        const int n = __popc(bits);
-        int inc = n;
+    size_t n = 4096 + EHB_MSZ * 4 + (size_t)EHB_RL * EHB_IDS_WORDS * 4 + (size_t)EHB_RL * 36 * 8;
+    n = (n + 15) & ~(size_t)15;
+    n += (size_t)cap * (4 + 4 + 2 + 1);
+    n = (n + 15) & ~(size_t)15;
+    n += EHB_RL * 12 * 8 + EHB_RL * sizeof(EhbSlot) + EHB_TWARPS * 8 + 8 * 4 + 64;
+    return n + 128;                      // slack for the 128-byte alignment of the base
+}
+__device__ __forceinline__ EhbTileSmem ehb_tile_smem(unsigned char* base, int cap)
+{
+    base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(base) + 127) & ~(uintptr_t)127);
+    EhbTileSmem s;
+    s.stage = reinterpret_cast<float*>(base); base += 4096;
+    s.S = reinterpret_cast<float*>(base); base += EHB_MSZ * 4;
+    s.ids = reinterpret_cast<uint32_t*>(base); base += (size_t)EHB_RL * EHB_IDS_WORDS * 4;
+    s.cov = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(base) + 7) & ~(uintptr_t)7);
+    base = reinterpret_cast<unsigned char*>(s.cov) + (size_t)EHB_RL * 36 * 8;
+    base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(base) + 15) & ~(uintptr_t)15);
+    s.alpha = reinterpret_cast<float*>(base); base += (size_t)cap * 4;
+    s.ptri = reinterpret_cast<uint32_t*>(base); base += (size_t)cap * 4;
+    s.pk = reinterpret_cast<unsigned short*>(base); base += (size_t)cap * 2;
+    s.pslot = base; base += (size_t)cap;
+    base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(base) + 15) & ~(uintptr_t)15);
+    s.gacc = reinterpret_cast<double*>(base); base += EHB_RL * 12 * 8;
+    s.slot = reinterpret_cast<EhbSlot*>(base); base += EHB_RL * sizeof(EhbSlot);
+    base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(base) + 7) & ~(uintptr_t)7);
+    s.lsum = reinterpret_cast<double*>(base); base += EHB_TWARPS * 8;
+    s.misc = reinterpret_cast<int*>(base);
+    return s;
+}
+
+// link index of the k-th set bit of `bits`
+__device__ __forceinline__ int ehb_nth_bit(uint32_t bits, int k) { return (int)__fns(bits, 0, k + 1); }
+
+// Everything a CTA knows about the tile it is working on.
+struct EhbTileCtx {
+    EhbTileSmem sm;
+    int cap, tid, lane, warp;
+    int item, tile, x0, y0, rx0, ry0, nl;
+    uint32_t bits;
+    bool needAA;
+    int ow;
+};
+
+// A + B + C for the links [lNext, lNext + take) of the tile (in link order).  On return `take` is the number of links
+// that fit the pair arrays (>= 1) and the pair list holds their `nPairsRound` pairs with weights.
+__device__ __forceinline__ void ehb_tile_round(const EhbRobot& rb, const EhbParams& p, const EhbTileCtx& c, int lNext, int& take,
+                                               int& nPairsRound)
+{
+    const EhbTileSmem& sm = c.sm;
+    const int tid = c.tid, lane = c.lane, warp = c.warp, cap = c.cap;
+    const int H = p.H, W = p.W, hlo = 1, ow = c.ow;
+    __syncthreads();                                     // the previous round / tile is done with the arrays
+    take = min(EHB_RL, c.nl - lNext);
+    // ================================ A: slots, windows, coverage ================================
+    if (tid < take) {
+        const int l = ehb_nth_bit(c.bits, lNext + tid);
+        const EhbPlane pl = p.plane[(size_t)c.item * p.L + l];
+        EhbSlot s;
+        s.link = l; s.x0 = pl.x0; s.y0 = pl.y0; s.w = pl.w; s.h = pl.h; s.off = pl.off; s.pairBase = 0; s.nPairs = 0;
+        sm.slot[tid] = s;
+    }
+    __syncthreads();
+    {
+        const int total = take * EHB_NP;
+        for (int e0 = tid; e0 < total; e0 += 6 * EHB_TTHREADS) {
+            unsigned long long v[6];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
-        }
-        const int tot = __shfl_sync(0xffffffffu, inc, 31);
-        unsigned base = 0;
-        if (lane == 0 && tot > 0) base = atomicAdd(&p.ctr->nJobs, (unsigned)tot);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (e < nEntries) {
-            unsigned j = base + (unsigned)(inc - n);
-            p.tileEnt[e] = make_uint4(wid, bits, j, 0u);
-            const int item = (int)(wid / (uint32_t)p.ntiles), tile = (int)(wid - (uint32_t)item * (uint32_t)p.ntiles);
-            if (n && j + (unsigned)n > (unsigned)p.jobCap) atomicOr(&p.ctr->flags, 1u);   // job list too small: grow and rerun
-            while (bits) {
-                const int l = __ffs(bits) - 1;
-                bits &= bits - 1;
-                const EhbPlane pl = p.plane[(size_t)item * p.L + l];
-                EhbJob jb;
-                jb.item = item; jb.tile = tile; jb.link = l; jb.entry = (int)e;
-                jb.x0 = pl.x0; jb.y0 = pl.y0; jb.w = pl.w; jb.h = pl.h; jb.off = pl.off; jb.pad = 0;
-                if (j < (unsigned)p.jobCap) p.jobs[j] = jb;
-                j++;
+            for (int k = 0; k < 6; k++) {       // every load of the batch is issued before the first is consumed
+                v[k] = EHB_EMPTY;
+                const int ee = e0 + k * EHB_TTHREADS;
+                if (ee < total) {
+                    const int s = ee / EHB_NP, i = ee - s * EHB_NP;
+                    const int r = i / EHB_RS, cc = i - r * EHB_RS;
+                    const EhbSlot& sl = sm.slot[s];
+                    const int cx = c.rx0 + cc - sl.x0, cy = c.ry0 + r - sl.y0;
+                    if ((unsigned)cx < (unsigned)sl.w && (unsigned)cy < (unsigned)sl.h)
+                        v[k] = p.pool[sl.off + (long long)cy * sl.w + cx];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                const int ee = e0 + k * EHB_TTHREADS;
+                if (ee < total) {
+                    const int s = ee / EHB_NP, i = ee - s * EHB_NP;
+                    sm.ids[s * EHB_IDS_WORDS + i] = (uint32_t)v[k];   // low word = triangle id (all ones: empty)
+                }
             }
         }
     }
-}
-
-// ------------------------------------------------------------------------------------------------ k_windows
-struct __align__(16) EhbWarpSm {
-    unsigned long long cov[EHB_RS + 1];
-    // triangle id of the nearest sample of the link (0xFFFFFFFF = not covered); once the blend weights are known the
-    // same storage holds the job's antialiased mask (33 rows x 36 floats)
-    uint32_t plane[EHB_NP + 3];
-    float alpha[EHB_WPAIRS];
-    unsigned short pk[EHB_WPAIRS];
-};
-static_assert(EHB_NP + 3 >= EHB_MSZ, "the mask of a job reuses the window's storage");
-
-__global__ void __launch_bounds__(EHB_WWARPS * 32) ehb_k_windows(const __grid_constant__ EhbRobot rb,
-                                                                const __grid_constant__ EhbParams p)
-{
-    ehb_pdl_enter();
-    __shared__ EhbWarpSm s_w[EHB_WWARPS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    EhbWarpSm& ws = s_w[warp];
-    const int H = p.H, W = p.W, hlo = p.hlo;
-    const bool needAA = p.mode == EHB_MODE_FUSED || p.mode == EHB_MODE_AA_FWD;
-    const int oext = (p.mode == EHB_MODE_FUSED && p.do_bwd) ? 1 : 0;
-    const int ow = EHB_T + oext;
-    // the first job record is fetched together with the job counter (one L2 round trip instead of two)
-    const unsigned jFirst = blockIdx.x * EHB_WWARPS + warp;
-    const EhbJob jbFirst = p.jobs[min(jFirst, (unsigned)p.jobCap - 1u)];
-    const unsigned nJobs = min(p.ctr->nJobs, (unsigned)p.jobCap);
-    for (unsigned j = jFirst; j < nJobs; j += gridDim.x * EHB_WWARPS) {
-        const EhbJob jb = j == jFirst ? jbFirst : p.jobs[j];
-        const int item = jb.item, l = jb.link;
-        const int tx = jb.tile % p.ntx, ty = jb.tile / p.ntx;
-        const int rx0 = tx * EHB_T - hlo, ry0 = ty * EHB_T - hlo;
-        const int wcols = EHB_T + hlo + p.hhi, wrows = wcols;   // window size: 34 or 35 (33 for the operator backward)
-        EhbPlane pl;
-        pl.x0 = jb.x0; pl.y0 = jb.y0; pl.w = jb.w; pl.h = jb.h; pl.off = jb.off;
-        const EhbLink& lk = rb.link[l];
-        const float4* vc = p.vclip + (size_t)item * p.Vtot + rb.voff[l];
-        __syncwarp();   // the previous job of this warp is done with ws
-        // ================ window of the link's plane -> shared memory, row coverage masks by ballot ================
-        unsigned long long myCov = 0ull;   // lane r: coverage mask of window row r (rows 32.. : lanes 0..2, second word)
-        unsigned long long myCov2 = 0ull;
-        {
-            const int cx = rx0 + lane - pl.x0;
-            const bool colOk = pl.w > 0 && cx >= 0 && cx < pl.w && lane < wcols;
-            const unsigned long long* base = p.pool + pl.off + cx;
-            const int pyBase = ry0 - pl.y0;
-            // columns 0..31 of every row: the loads of NRC rows are issued before the first ballot consumes one
-            constexpr int NRC = 12;
-#pragma unroll
-            for (int rbase = 0; rbase < 36; rbase += NRC) {
-                unsigned long long v[NRC];
-#pragma unroll
-                for (int k = 0; k < NRC; k++) {
-                    const int r = rbase + k, py = pyBase + r;
-                    v[k] = EHB_EMPTY;
-                    if (r < EHB_RS && colOk && (unsigned)py < (unsigned)pl.h && r < wrows) v[k] = base[(long long)py * pl.w];
-                }
-#pragma unroll
-                for (int k = 0; k < NRC; k++) {
-                    const int r = rbase + k;
-                    if (r < EHB_RS) {
-                        ws.plane[r * EHB_RS + lane] = (uint32_t)v[k];   // low word = triangle id (all ones when empty)
-                        const unsigned b = __ballot_sync(0xffffffffu, v[k] != EHB_EMPTY);
-                        if (r < 32) { if (lane == r) myCov = (unsigned long long)b; }
-                        else if (lane == r - 32) myCov2 = (unsigned long long)b;
-                    }
-                }
-            }
-            // columns 32..34: the 105 elements as one flat list (4 loads instead of 35 mostly idle ones)
-            unsigned bx[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int i = k * 32 + lane;
-                const int r = i / 3, c = 32 + (i - r * 3);
-                unsigned long long v = EHB_EMPTY;
-                if (i < 3 * EHB_RS) {
-                    const int py = pyBase + r, cxx = rx0 + c - pl.x0;
-                    if (pl.w > 0 && cxx >= 0 && cxx < pl.w && c < wcols && (unsigned)py < (unsigned)pl.h && r < wrows)
-                        v = p.pool[pl.off + (long long)py * pl.w + cxx];
-                    ws.plane[r * EHB_RS + c] = (uint32_t)v;
-                }
-                bx[k] = __ballot_sync(0xffffffffu, v != EHB_EMPTY);
-            }
-            // row r owns bits 3r .. 3r+2 of the 128-bit string bx[3]:bx[2]:bx[1]:bx[0]
-            {
-                const unsigned long long lo = (unsigned long long)bx[0] | ((unsigned long long)bx[1] << 32);
-                const unsigned long long hi = (unsigned long long)bx[2] | ((unsigned long long)bx[3] << 32);
-                auto three = [&](int r) -> unsigned long long {
-                    const int s = 3 * r;
-                    unsigned long long w = s < 64 ? (lo >> s) : (hi >> (s - 64));
-                    if (s < 64 && s > 61) w |= hi << (64 - s);
-                    return w & 7ull;
-                };
-                myCov |= three(lane) << 32;
-                if (lane < EHB_RS - 32) myCov2 |= three(lane + 32) << 32;
-            }
-            ws.cov[lane] = myCov;
-            if (lane < EHB_RS - 32) ws.cov[lane + 32] = myCov2;
-            if (lane == EHB_RS - 32) ws.cov[EHB_RS] = 0ull;
+    __syncthreads();
+    // row coverage masks: (slot, row) pairs over the warps; bits 0..31 from one ballot, 32..34 from a second
+    for (int sr = warp; sr < take * (EHB_RS + 1); sr += EHB_TWARPS) {
+        const int s = sr / (EHB_RS + 1), r = sr - s * (EHB_RS + 1);
+        unsigned long long m = 0ull;
+        if (r < EHB_RS) {
+            const uint32_t* row = sm.ids + s * EHB_IDS_WORDS + r * EHB_RS;
+            const unsigned b0 = __ballot_sync(0xffffffffu, row[lane] != 0xFFFFFFFFu);
+            const unsigned b1 = __ballot_sync(0xffffffffu, lane < EHB_RS - 32 && row[32 + lane] != 0xFFFFFFFFu);
+            m = (unsigned long long)b0 | ((unsigned long long)b1 << 32);
         }
-        __syncwarp();
-        // ================================ silhouette pairs: lane = window row ====================================
-        int nPairs;
-        // columns whose pixel is inside the image, and for which the right neighbour is too
-        const unsigned long long inX = ehb_bits(-rx0, W - 1 - rx0), inX1 = ehb_bits(-rx0, W - 2 - rx0);
-        unsigned long long hm[2], vm[2], om[2];
+        if (lane == 0) sm.cov[s * 36 + r] = m;
+    }
+    __syncthreads();
+    // ================================ B: silhouette pairs, one warp per slot, lane = window row ================================
+    // columns whose pixel is inside the image, and for which the right neighbour is too
+    const unsigned long long inX = ehb_bits(-c.rx0, W - 1 - c.rx0), inX1 = ehb_bits(-c.rx0, W - 2 - c.rx0);
+    unsigned long long hm[2] = {0ull, 0ull}, vm[2] = {0ull, 0ull}, om[2] = {0ull, 0ull};
+    int o0 = 0, o1 = 0;
+    if (warp < take) {
+        const unsigned long long* cv = sm.cov + warp * 36;
         int cnt[2];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int r = lane + 32 * h;
-            hm[h] = vm[h] = om[h] = 0ull;
             if (r < EHB_RS) {
-                const int py = ry0 + r;
-                const unsigned long long cm = h ? myCov2 : myCov, cu = ws.cov[r + 1];
+                const int py = c.ry0 + r;
+                const unsigned long long cm = cv[r], cu = cv[r + 1];
                 // pairs wanted: forward = those touching a pixel of the out region; otherwise only owned ones
                 unsigned long long wantH, wantV;
-                if (needAA) {
+                if (c.needAA) {
                     wantH = (r >= hlo && r <= hlo + ow - 1) ? ehb_bits(hlo - 1, hlo + ow - 1) : 0ull;
                     wantV = (r >= hlo - 1 && r <= hlo + ow - 1) ? ehb_bits(hlo, hlo + ow - 1) : 0ull;
                 } else {
@@ -219,7 +203,6 @@ __global__ void __launch_bounds__(EHB_WWARPS * 32) ehb_k_windows(const __grid_co
             }
             cnt[h] = __popcll(hm[h]) + __popcll(vm[h]);
         }
-        // exclusive prefix over the 35 rows: rows 0..31 by shuffle scan, rows 32..34 after them
         int inc = cnt[0];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -234,109 +217,101 @@ __global__ void __launch_bounds__(EHB_WWARPS * 32) ehb_k_windows(const __grid_co
             if (lane >= o) inc1 += v;
         }
         const int tot1 = __shfl_sync(0xffffffffu, inc1, 3);
-        nPairs = tot0 + tot1;
-        const int o0 = inc - cnt[0], o1 = tot0 + inc1 - cnt[1];
-        // The list of this job in the global pair pool.  The ticket is drawn now and used after the blend weights are
-        // known (they only need shared memory), so the atomic's round trip hides behind the weights' own loads; only a
-        // job with more pairs than the shared-memory arrays hold waits for it right away.
-        unsigned ticket = 0;
-        if (lane == 0 && nPairs > 0) ticket = atomicAdd(&p.ctr->pairCursor, (unsigned)nPairs);
-        EhbPair* mine = nullptr;
-        bool resolved = false;
-        auto resolve = [&]() {
-            const unsigned pairOff = __shfl_sync(0xffffffffu, ticket, 0);
-            resolved = true;
-            mine = p.pairs + pairOff;
-            if ((unsigned long long)pairOff + (unsigned long long)nPairs > (unsigned long long)p.pairCap) {
-                if (lane == 0) atomicOr(&p.ctr->flags, 1u);   // pair pool too small: results invalid, grow and rerun
-                mine = nullptr;
-            }
-        };
-        if (nPairs > EHB_WPAIRS) {
-            resolve();
-            if (!mine) nPairs = 0;
-        }
-        if (nPairs > 0) {
+        o0 = inc - cnt[0]; o1 = tot0 + inc1 - cnt[1];
+        if (lane == 0) sm.slot[warp].nPairs = tot0 + tot1;
+    }
+    __syncthreads();
+    // fit the round into the pair arrays: the longest prefix of slots whose pairs fit (at least one slot)
+    nPairsRound = 0;
+    int fit = 0;
+    for (int s = 0; s < take; s++) {
+        const int n = sm.slot[s].nPairs;
+        if (s > 0 && nPairsRound + n > cap) break;
+        nPairsRound += n; fit = s + 1;
+    }
+    if (nPairsRound > cap) {          // one window with more pairs than the arrays hold: flagged, grow and rerun
+        if (tid == 0) atomicOr(&p.ctr->flags, 1u);
+        nPairsRound = cap;
+    }
+    take = fit;
+    __syncthreads();
+    if (tid == 0) {
+        int b = 0;
+        for (int s = 0; s < take; s++) { sm.slot[s].pairBase = b; b += sm.slot[s].nPairs; }
+    }
+    __syncthreads();
+    if (warp < take) {
+        const int base = sm.slot[warp].pairBase;
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                int o = h ? o1 : o0;
-                unsigned long long hxm = hm[h], vym = vm[h];
-                const uint32_t rowBase = (uint32_t)(lane + 32 * h) * EHB_RS;
-                while (hxm) {
-                    const int b = __ffsll((long long)hxm) - 1;
-                    hxm &= hxm - 1;
-                    const uint32_t pk = (rowBase + b) | (((om[h] >> b) & 1ull) ? (1u << 12) : 0u);
-                    if (o < EHB_WPAIRS) ws.pk[o] = (unsigned short)pk; else mine[o].packed = pk;
-                    o++;
+        for (int h = 0; h < 2; h++) {
+            int o = base + (h ? o1 : o0);
+            unsigned long long hxm = hm[h], vym = vm[h];
+            const uint32_t rowBase = (uint32_t)(lane + 32 * h) * EHB_RS;
+            while (hxm) {
+                const int b = __ffsll((long long)hxm) - 1;
+                hxm &= hxm - 1;
+                if (o < cap) {
+                    sm.pk[o] = (unsigned short)((rowBase + b) | (((om[h] >> b) & 1ull) ? (1u << 12) : 0u));
+                    sm.pslot[o] = (unsigned char)warp;
                 }
-                while (vym) {
-                    const int b = __ffsll((long long)vym) - 1;
-                    vym &= vym - 1;
-                    const uint32_t pk = (rowBase + b) | (1u << 11) | (((om[h] >> b) & 1ull) ? (1u << 12) : 0u);
-                    if (o < EHB_WPAIRS) ws.pk[o] = (unsigned short)pk; else mine[o].packed = pk;
-                    o++;
+                o++;
+            }
+            while (vym) {
+                const int b = __ffsll((long long)vym) - 1;
+                vym &= vym - 1;
+                if (o < cap) {
+                    sm.pk[o] = (unsigned short)((rowBase + b) | (1u << 11) | (((om[h] >> b) & 1ull) ? (1u << 12) : 0u));
+                    sm.pslot[o] = (unsigned char)warp;
                 }
+                o++;
             }
         }
-        __syncwarp();
-        // ================================ blend weights, one pair per lane =====================================
-        auto store_entry = [&](int i, uint32_t pk2, uint32_t t, float al) {
-            uint4* e = reinterpret_cast<uint4*>(mine + i);
-            e[0] = make_uint4(pk2, t, __float_as_uint(al), j);
-            e[1] = make_uint4((uint32_t)item, (uint32_t)jb.tile, (uint32_t)l, (uint32_t)jb.entry);
-        };
-        auto tri_of = [&](uint32_t pk, int& side) -> uint32_t {
-            const int idx = pk & 2047, d = (pk >> 11) & 1;
-            const uint32_t ka = ws.plane[idx], kb = ws.plane[idx + (d ? EHB_RS : 1)];
-            side = ka != 0xFFFFFFFFu ? 0 : 1;
-            return side ? kb : ka;
-        };
-        for (int i = lane; i < nPairs; i += 32) {
-            const uint32_t pk = i < EHB_WPAIRS ? (uint32_t)ws.pk[i] : __ldcg(&mine[i].packed);
-            const int idx = pk & 2047, d = (pk >> 11) & 1;
-            const int ly = idx / EHB_RS, lx = idx - ly * EHB_RS;
-            int side, di;
-            const uint32_t t = tri_of(pk, side);
-            const float al = ehb_aa_pair(lk, vc, (int)t, side, rx0 + lx, ry0 + ly, d, H, W, &di);
-            const uint32_t pk2 = pk | ((uint32_t)side << 13) | ((uint32_t)di << 14);
-            if (resolved) store_entry(i, pk2, t, al);
-            if (i < EHB_WPAIRS) { ws.alpha[i] = al; ws.pk[i] = (unsigned short)(pk2 & 0xFFFFu); }
+    }
+    __syncthreads();
+    // ================================ C: blend weights, all threads over the tile's pair list ================================
+    for (int i = tid; i < nPairsRound; i += EHB_TTHREADS) {
+        const uint32_t pk = sm.pk[i];
+        const int s = sm.pslot[i];
+        const int l = sm.slot[s].link;
+        const int idx = pk & 2047, d = (pk >> 11) & 1;
+        const int ly = idx / EHB_RS, lx = idx - ly * EHB_RS;
+        const uint32_t* idw = sm.ids + s * EHB_IDS_WORDS;
+        const uint32_t ka = idw[idx], kb = idw[idx + (d ? EHB_RS : 1)];
+        const int side = ka != 0xFFFFFFFFu ? 0 : 1;
+        const uint32_t t = side ? kb : ka;
+        int di;
+        const float al = ehb_aa_pair(rb.link[l], p.vclip + (size_t)c.item * p.Vtot + rb.voff[l], (int)t, side, c.rx0 + lx, c.ry0 + ly, d,
+                                     H, W, &di);
+        sm.alpha[i] = al;
+        sm.ptri[i] = t;
+        sm.pk[i] = (unsigned short)(pk | ((uint32_t)side << 13) | ((uint32_t)di << 14));
+    }
+    __syncthreads();
+}
+
+// D: the antialiased masks of the round's links (out region), then the running sum in link order.
+__device__ __forceinline__ void ehb_tile_masks(const EhbTileCtx& c, int take, bool first)
+{
+    const EhbTileSmem& sm = c.sm;
+    const int lane = c.lane, warp = c.warp, hlo = 1, ow = c.ow;
+    // colour = coverage as floats (the window's ids are dead: their storage becomes the mask), then the pair
+    // contributions.  A pixel receives at most one contribution of each kind and the reference adds them in the order
+    // pair(p,p+x), pair(p,p+y), pair(p-x,p), pair(p-y,p): four sweeps over the link's pairs, one kind each (receiver = p0
+    // when alpha > 0, p1 otherwise; the contribution is alpha * (colour[p1] - colour[p0])).
+    if (warp < take) {
+        float* ot = reinterpret_cast<float*>(sm.ids + warp * EHB_IDS_WORDS);
+        const unsigned long long* cv = sm.cov + warp * 36;
+        for (int i = lane; i < ow * EHB_MW; i += 32) {
+            const int qy = i / EHB_MW, qx = i - qy * EHB_MW;
+            ot[i] = (qx < ow && ((cv[hlo + qy] >> (hlo + qx)) & 1ull)) ? 1.f : 0.f;
         }
-        if (!resolved && nPairs > 0) {   // nPairs <= EHB_WPAIRS: everything is in shared memory; (each lane re-reads its own entries)
-            resolve();
-            if (mine)
-                for (int i = lane; i < nPairs; i += 32) {
-                    const uint32_t pk2 = ws.pk[i];
-                    int side;
-                    const uint32_t t = tri_of(pk2, side);
-                    store_entry(i, pk2, t, ws.alpha[i]);
-                }
-        }
-        if (!needAA) continue;
-        __syncwarp();
-        // ================= the link's antialiased mask of the out region: colour, then the pair contributions ============
-        // (the window's triangle ids are dead: their storage becomes the mask)
-        float* ot = reinterpret_cast<float*>(ws.plane);
-        for (int sg = lane; sg < EHB_NSEG + (oext ? EHB_NSEG_EXT : 0); sg += 32) {
-            int qy, qx0, n;
-            ehb_out_segment(sg, qy, qx0, n);
-            const uint32_t c8 = (uint32_t)(ws.cov[hlo + qy] >> (hlo + qx0));
-            float* dst = ot + qy * EHB_MW + qx0;
-            if (n == 8) {
-                reinterpret_cast<float4*>(dst)[0] = make_float4((c8 & 1u) ? 1.f : 0.f, (c8 & 2u) ? 1.f : 0.f, (c8 & 4u) ? 1.f : 0.f, (c8 & 8u) ? 1.f : 0.f);
-                reinterpret_cast<float4*>(dst)[1] = make_float4((c8 & 16u) ? 1.f : 0.f, (c8 & 32u) ? 1.f : 0.f, (c8 & 64u) ? 1.f : 0.f, (c8 & 128u) ? 1.f : 0.f);
-            } else dst[0] = (c8 & 1u) ? 1.f : 0.f;
-        }
-        // A pixel receives at most one contribution of each kind, and the reference adds them in the order
-        // pair(p,p+x), pair(p,p+y), pair(p-x,p), pair(p-y,p): four sweeps over the pair list, one kind each
-        // (receiver = p0 when alpha > 0, p1 otherwise; the contribution is alpha * (colour[p1] - colour[p0])).
+        const int pb = sm.slot[warp].pairBase, pn = max(0, min(sm.slot[warp].nPairs, c.cap - pb));
 #pragma unroll 1
         for (int kind = 0; kind < 4; kind++) {
             __syncwarp();
-            for (int i = lane; i < nPairs; i += 32) {
-                uint32_t pk; float al;
-                if (i < EHB_WPAIRS) { pk = ws.pk[i]; al = ws.alpha[i]; }
-                else { const uint4 e = __ldcg(reinterpret_cast<const uint4*>(mine + i)); pk = e.x; al = __uint_as_float(e.z); }
+            for (int i = pb + lane; i < pb + pn; i += 32) {
+                const uint32_t pk = sm.pk[i];
+                const float al = sm.alpha[i];
                 const int d = (pk >> 11) & 1;
                 const bool pos = al > 0.f;
                 if (al == 0.f || d != (kind & 1) || pos != (kind < 2)) continue;
@@ -349,190 +324,58 @@ __global__ void __launch_bounds__(EHB_WWARPS * 32) ehb_k_windows(const __grid_co
                 ot[qy * EHB_MW + qx] += al * delta;
             }
         }
-        __syncwarp();
-        {   // mask -> the job's slot (coalesced 16-byte stores)
-            float4* dst = reinterpret_cast<float4*>(p.maskBuf + (size_t)j * EHB_MSZ);
-            const float4* src = reinterpret_cast<const float4*>(ot);
-            const int n4 = (EHB_T + oext) * (EHB_MW / 4);
-            for (int i = lane; i < n4; i += 32) dst[i] = src[i];
+    }
+    __syncthreads();
+    // running sum in link order (rb_solver.py:68): S = m_first, then S = S + m_l
+    for (int i = c.tid; i < ow * EHB_MW; i += EHB_TTHREADS) {
+        float s = first ? 0.f : sm.S[i];
+        for (int k = 0; k < take; k++) {
+            const float m = reinterpret_cast<const float*>(sm.ids + k * EHB_IDS_WORDS)[i];
+            s = (first && k == 0) ? m : s + m;
         }
+        sm.S[i] = s;
     }
 }
 
-// ------------------------------------------------------------------------------------------------ k_compose
-// One 128-thread CTA per listed tile, one out-region segment (8 pixels) per thread: sum of the tile's job masks in link
-// order (rb_solver.py:68), clamp, mask write, loss, dL/dsum.  Every load of a thread is issued before the first is used.
-#define EHB_CTHREADS 128
-__global__ void __launch_bounds__(EHB_CTHREADS) ehb_k_compose(const __grid_constant__ EhbParams p)
+// F: backward of the resident pairs (sm.S holds g = dL/dsum of the out region).
+__device__ __forceinline__ void ehb_tile_backward(const EhbRobot& rb, const EhbParams& p, const EhbTileCtx& c, int take, int nPairsRound)
 {
-    ehb_pdl_enter();
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int H = p.H, W = p.W;
-    const bool fused = p.mode == EHB_MODE_FUSED;
-    const int oext = (fused && p.do_bwd) ? 1 : 0;
-    const bool haveRef = p.ref != nullptr || p.ref_u8 != nullptr;
-    const unsigned nHeavy = p.ctr->nTiles, nEntries = nHeavy + p.ctr->nLight;
-    const bool vecOut = p.masks != nullptr && (W & 3) == 0 && (((uintptr_t)p.masks) & 15) == 0;
-    const bool vecRef = p.ref != nullptr && (W & 3) == 0 && (((uintptr_t)p.ref) & 15) == 0;
-    const bool vecRef8 = p.ref_u8 != nullptr && (W & 7) == 0 && (((uintptr_t)p.ref_u8) & 7) == 0;
-    const unsigned eFirst = blockIdx.x;
-    const uint4 teFirst = p.tileEnt[min(eFirst, (unsigned)(p.items * p.ntiles) - 1u)];   // fetched together with the counters
-    for (unsigned e = eFirst; e < nEntries; e += gridDim.x) {
-        const uint4 te = e == eFirst ? teFirst : p.tileEnt[e];   // {wid, link bits, first job, -}, written by the job builder
-        const uint32_t wid = te.x;
-        const int item = (int)(wid / (uint32_t)p.ntiles), tile = (int)(wid - (uint32_t)item * (uint32_t)p.ntiles);
-        const int x0 = (tile % p.ntx) * EHB_T, y0 = (tile / p.ntx) * EHB_T;
-        const size_t ibase = (size_t)item * H * W;
-        float* gwin = p.gBuf + (size_t)e * EHB_MSZ;
-        if (p.mode == EHB_MODE_AA_BWD) {   // g = dL/dmask comes from the caller
-            for (int i = tid; i < EHB_MROWS * EHB_MROWS; i += EHB_CTHREADS) {
-                const int qy = i / EHB_MROWS, qx = i - qy * EHB_MROWS;
-                const int px = x0 + qx, py = y0 + qy;
-                gwin[qy * EHB_MW + qx] = (px < W && py < H) ? __ldg(p.dy + ibase + (size_t)(H - 1 - py) * W + px) : 0.f;
-            }
-            continue;
-        }
-        const uint32_t bits = te.y;
-        const unsigned j0 = te.z;
-        const int nP = min(__popc(bits), (int)max(0ll, (long long)p.jobCap - (long long)j0));   // (overflow: flagged, rerun)
-        const float* m0 = p.maskBuf + (size_t)j0 * EHB_MSZ;
-        double lacc = 0.0;
-        for (int sg = tid; sg < EHB_NSEG + (oext ? EHB_NSEG_EXT : 0); sg += EHB_CTHREADS) {
-            int qy, qx0, n;
-            ehb_out_segment(sg, qy, qx0, n);
-            const int py = y0 + qy;
-            if (py >= H) continue;
-            const size_t orow = ibase + (size_t)(H - 1 - py) * W;
-            const int px0 = x0 + qx0;
-            // reference of the segment (issued before the masks are consumed)
-            float rf[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) rf[i] = 0.f;
-            if (fused && haveRef) {
-                if (n == 8 && px0 + 7 < W && vecRef) {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(p.ref + orow + px0));
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.ref + orow + px0) + 1);
-                    rf[0] = a.x; rf[1] = a.y; rf[2] = a.z; rf[3] = a.w; rf[4] = b.x; rf[5] = b.y; rf[6] = b.z; rf[7] = b.w;
-                } else if (n == 8 && px0 + 7 < W && vecRef8) {
-                    const uint2 a = __ldg(reinterpret_cast<const uint2*>(p.ref_u8 + orow + px0));
-#pragma unroll
-                    for (int i = 0; i < 8; i++) rf[i] = (((i < 4 ? a.x : a.y) >> (8 * (i & 3))) & 255u) ? 1.f : 0.f;
-                } else {
-                    for (int i = 0; i < n; i++)
-                        if (px0 + i < W) rf[i] = p.ref ? __ldg(p.ref + orow + px0 + i) : (__ldg(p.ref_u8 + orow + px0 + i) ? 1.f : 0.f);
-                }
-            }
-            float s[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) s[i] = 0.f;
-            const float* src = m0 + qy * EHB_MW + qx0;
-            if (n == 8) {
-                int k = 0;
-                for (; k + 1 < nP; k += 2) {   // links are added in link order; two jobs' loads in flight at a time
-                    const float4 a0 = __ldcg(reinterpret_cast<const float4*>(src + (size_t)k * EHB_MSZ));
-                    const float4 b0 = __ldcg(reinterpret_cast<const float4*>(src + (size_t)k * EHB_MSZ) + 1);
-                    const float4 a1 = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(k + 1) * EHB_MSZ));
-                    const float4 b1 = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(k + 1) * EHB_MSZ) + 1);
-                    s[0] = (s[0] + a0.x) + a1.x; s[1] = (s[1] + a0.y) + a1.y; s[2] = (s[2] + a0.z) + a1.z; s[3] = (s[3] + a0.w) + a1.w;
-                    s[4] = (s[4] + b0.x) + b1.x; s[5] = (s[5] + b0.y) + b1.y; s[6] = (s[6] + b0.z) + b1.z; s[7] = (s[7] + b0.w) + b1.w;
-                }
-                if (k < nP) {
-                    const float4 a = __ldcg(reinterpret_cast<const float4*>(src + (size_t)k * EHB_MSZ));
-                    const float4 b = __ldcg(reinterpret_cast<const float4*>(src + (size_t)k * EHB_MSZ) + 1);
-                    s[0] = s[0] + a.x; s[1] = s[1] + a.y; s[2] = s[2] + a.z; s[3] = s[3] + a.w;
-                    s[4] = s[4] + b.x; s[5] = s[5] + b.y; s[6] = s[6] + b.z; s[7] = s[7] + b.w;
-                }
-            } else {
-                for (int k = 0; k < nP; k++) s[0] = s[0] + __ldcg(src + (size_t)k * EHB_MSZ);
-            }
-            float Sv[8], gv[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                Sv[i] = 0.f; gv[i] = 0.f;
-                if (i >= n || px0 + i >= W) continue;
-                const float S = (p.clamp && s[i] > 1.f) ? 1.f : s[i];
-                Sv[i] = S;
-                if (fused && haveRef) {
-                    const float diff = S - rf[i];
-                    if (qx0 + i < EHB_T && qy < EHB_T) lacc += (double)(diff * diff);
-                    gv[i] = (!p.clamp || s[i] <= 1.f) ? (2.f * diff) * p.invB : 0.f;
-                }
-            }
-            if (oext) {
-                float* gd = gwin + qy * EHB_MW + qx0;
-                if (n == 8) {
-                    reinterpret_cast<float4*>(gd)[0] = make_float4(gv[0], gv[1], gv[2], gv[3]);
-                    reinterpret_cast<float4*>(gd)[1] = make_float4(gv[4], gv[5], gv[6], gv[7]);
-                } else gd[0] = gv[0];
-            }
-            if (p.masks && qy < EHB_T && qx0 < EHB_T) {
-                if (vecOut && px0 + 7 < W) {
-                    float4* dst = reinterpret_cast<float4*>(p.masks + orow + px0);
-                    dst[0] = make_float4(Sv[0], Sv[1], Sv[2], Sv[3]);
-                    dst[1] = make_float4(Sv[4], Sv[5], Sv[6], Sv[7]);
-                } else {
-                    for (int i = 0; i < n; i++)
-                        if (px0 + i < W) p.masks[orow + px0 + i] = Sv[i];
-                }
-            }
-        }
-        if (fused && haveRef && p.loss) {
-            lacc = ehb_warp_sum(lacc);
-            if (lane == 0 && lacc != 0.0) atomicAdd(&p.loss[item], lacc);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ k_pairgrad
-// One thread per pair entry.  Owned pairs (p0 inside the tile's interior) with a non-zero weight and a non-zero upstream
-// gradient at their receiving pixel contribute; everything of a warp that belongs to one (item, link) is reduced by
-// shuffles before the fp64 atomics.
-__global__ void __launch_bounds__(256) ehb_k_pairgrad(const __grid_constant__ EhbRobot rb, const __grid_constant__ EhbParams p)
-{
-    ehb_pdl_enter();
-    const int lane = threadIdx.x & 31;
-    const unsigned nPairs = min(p.ctr->pairCursor, (unsigned)p.pairCap);
-    const unsigned stride = gridDim.x * blockDim.x;
-    const unsigned nIter = (nPairs + stride - 1) / stride;
-    const int hlo = p.hlo;
-    for (unsigned it = 0; it < nIter; it++) {
-        const unsigned i = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+    const EhbTileSmem& sm = c.sm;
+    const int tid = c.tid, lane = c.lane, hlo = 1;
+    if (tid < EHB_RL * 12) sm.gacc[tid] = 0.0;
+    __syncthreads();                                     // ... and g / the pair weights are complete
+    for (int i0 = 0; i0 < nPairsRound; i0 += EHB_TTHREADS) {
+        const int i = i0 + tid;
         double acc[12];
 #pragma unroll
         for (int k = 0; k < 12; k++) acc[k] = 0.0;
         int key = -1;
-        if (i < nPairs) {
-            const uint4 e = __ldcg(reinterpret_cast<const uint4*>(p.pairs + i));
-            const uint4 jq = __ldcg(reinterpret_cast<const uint4*>(p.pairs + i) + 1);   // item, tile, link, entry
-            const float al = __uint_as_float(e.z);
-            // (after a pool overflow -- flagged, the pass is rerun -- the tail of the pool may hold stale entries: never
-            // follow an index that is out of range)
-            const bool sane = jq.x < (unsigned)p.items && jq.y < (unsigned)p.ntiles && jq.z < (unsigned)p.L &&
-                              jq.w < (unsigned)(p.items * p.ntiles) && e.y < (unsigned)rb.link[min(jq.z, (unsigned)p.L - 1u)].F;
-            if (sane && (e.x & (1u << 12)) && al != 0.f) {
-                const int jitem = (int)jq.x, jtile = (int)jq.y, jlink = (int)jq.z, jentry = (int)jq.w;
-                const int idx = e.x & 2047, d = (e.x >> 11) & 1, side = (e.x >> 13) & 1, di = (e.x >> 14) & 3;
-                const int idx1 = idx + (d ? EHB_RS : 1);
-                const int ridx = al > 0.f ? idx : idx1;
+        if (i < nPairsRound) {
+            const uint32_t pk = sm.pk[i];
+            const float al = sm.alpha[i];
+            if ((pk & (1u << 12)) && al != 0.f) {        // owned (p0 inside the tile's interior) with a non-zero weight
+                const int idx = pk & 2047, d = (pk >> 11) & 1, side = (pk >> 13) & 1, di = (pk >> 14) & 3;
+                const int ridx = al > 0.f ? idx : idx + (d ? EHB_RS : 1);
                 const int ry = ridx / EHB_RS, rxw = ridx - ry * EHB_RS;
-                const float g = __ldcg(p.gBuf + (size_t)jentry * EHB_MSZ + (ry - hlo) * EHB_MW + (rxw - hlo));
+                const float g = sm.S[(ry - hlo) * EHB_MW + (rxw - hlo)];
                 const float dd = g * (side ? 1.f : -1.f);   // g * (c1 - c0)
                 if (dd != 0.f) {
+                    const int s = sm.pslot[i];
+                    const int l = sm.slot[s].link;
                     const int ly = idx / EHB_RS, lx = idx - ly * EHB_RS;
-                    const int rx0 = (jtile % p.ntx) * EHB_T - hlo, ry0 = (jtile / p.ntx) * EHB_T - hlo;
-                    const EhbLink& lk = rb.link[jlink];
-                    const float4* vc = p.vclip + (size_t)jitem * p.Vtot + rb.voff[jlink];
+                    const EhbLink& lk = rb.link[l];
                     int vi1, vi2;
                     float g1[3], g2[3];
-                    ehb_aa_pair_grad(lk, vc, (int)e.y, side, di, al, dd, rx0 + lx, ry0 + ly, d, p.H, p.W, &vi1, &vi2, g1, g2);
+                    ehb_aa_pair_grad(lk, p.vclip + (size_t)c.item * p.Vtot + rb.voff[l], (int)sm.ptri[i], side, di, al, dd, c.rx0 + lx,
+                                     c.ry0 + ly, d, p.H, p.W, &vi1, &vi2, g1, g2);
                     const float4 va = __ldg(lk.verts + vi1), vb = __ldg(lk.verts + vi2);
                     const double ha[4] = {(double)va.x, (double)va.y, (double)va.z, 1.0};
                     const double hb[4] = {(double)vb.x, (double)vb.y, (double)vb.z, 1.0};
 #pragma unroll
                     for (int rr = 0; rr < 3; rr++)
 #pragma unroll
-                        for (int c = 0; c < 4; c++) acc[4 * rr + c] = (double)g1[rr] * ha[c] + (double)g2[rr] * hb[c];
-                    key = jitem * p.L + jlink;
+                        for (int cc = 0; cc < 4; cc++) acc[4 * rr + cc] = (double)g1[rr] * ha[cc] + (double)g2[rr] * hb[cc];
+                    key = s;
                     if (p.gpos) {
                         atomicAdd(p.gpos + 4 * (size_t)vi1 + 0, g1[0]);
                         atomicAdd(p.gpos + 4 * (size_t)vi1 + 1, g1[1]);
@@ -544,19 +387,159 @@ __global__ void __launch_bounds__(256) ehb_k_pairgrad(const __grid_constant__ Eh
                 }
             }
         }
+        // everything of a warp that belongs to one link: reduced by shuffles, then one shared-memory atomic per component
         unsigned todo = __ballot_sync(0xffffffffu, key >= 0);
         while (todo) {
             const int leader = __ffs(todo) - 1;
             const int k0 = __shfl_sync(0xffffffffu, key, leader);
             const bool mine = key == k0;
             todo &= ~__ballot_sync(0xffffffffu, mine);
-            double* dst = p.gmvp + (size_t)k0 * 16;
 #pragma unroll
             for (int k = 0; k < 12; k++) {
                 const double v = ehb_warp_sum(mine ? acc[k] : 0.0);
-                // rows x (0), y (1), w (3) of d loss / d mvp; the z row carries no gradient
-                if (lane == 0 && v != 0.0) atomicAdd(dst + (k < 8 ? k : k + 4), v);
+                if (lane == 0 && v != 0.0) atomicAdd(sm.gacc + k0 * 12 + k, v);
             }
         }
     }
+    __syncthreads();
+    if (tid < take * 12 && p.gmvp) {
+        const int s = tid / 12, k = tid - s * 12;
+        const double v = sm.gacc[tid];
+        // rows x (0), y (1), w (3) of d loss / d mvp; the z row carries no gradient
+        if (v != 0.0) atomicAdd(p.gmvp + ((size_t)c.item * p.L + sm.slot[s].link) * 16 + (k < 8 ? k : k + 4), v);
+    }
+}
+
+__global__ void __launch_bounds__(EHB_TTHREADS) ehb_k_tiles(const __grid_constant__ EhbRobot rb,
+                                                            const __grid_constant__ EhbParams p, int cap)
+{
+    ehb_pdl_enter();
+    extern __shared__ unsigned char ehb_dsm[];
+    EhbTileCtx c;
+    c.sm = ehb_tile_smem(ehb_dsm, cap);
+    c.cap = cap;
+    c.tid = threadIdx.x; c.lane = c.tid & 31; c.warp = c.tid >> 5;
+    const EhbTileSmem& sm = c.sm;
+    const int tid = c.tid, lane = c.lane, warp = c.warp;
+    const int H = p.H, W = p.W;
+    const bool fused = p.mode == EHB_MODE_FUSED;
+    c.needAA = fused || p.mode == EHB_MODE_AA_FWD;
+    const bool doBwd = (fused && p.do_bwd) || p.mode == EHB_MODE_AA_BWD;
+    const int oext = (fused && p.do_bwd) ? 1 : 0;
+    c.ow = EHB_T + oext;                                 // out region whose S is needed
+    const int ow = c.ow;
+    const int refKind = !fused ? 0 : (p.refBits ? 3 : (p.ref ? 1 : (p.ref_u8 ? 2 : 0)));
+    const unsigned nHeavy = p.ctr->nTiles, nEntries = nHeavy + p.ctr->nLight;
+    const uint32_t linkMask = p.L >= 32 ? 0xFFFFFFFFu : ((1u << p.L) - 1u);
+    const bool tma = p.masks != nullptr && p.useTma;
+    bool storePending = false;                           // thread 0: a TMA store may still be reading the staging tile
+
+    for (unsigned e = blockIdx.x; e < nEntries; e += gridDim.x) {
+        const uint32_t wid = ehb_list_at(p, e, nHeavy);
+        c.item = (int)(wid / (uint32_t)p.ntiles); c.tile = (int)(wid - (uint32_t)c.item * (uint32_t)p.ntiles);
+        c.x0 = (c.tile % p.ntx) * EHB_T; c.y0 = (c.tile / p.ntx) * EHB_T;
+        c.rx0 = c.x0 - 1; c.ry0 = c.y0 - 1;              // window = tile + 1 low / 2 high halo pixels (35 x 35), all modes
+        c.bits = p.touch[wid] & linkMask;
+        c.nl = __popc(c.bits);
+        const int item = c.item, x0 = c.x0, y0 = c.y0, nl = c.nl;
+        const size_t ibase = (size_t)item * H * W;
+        // ---- reference values of this thread's out-region pixels: issued now, consumed in E -------------------------
+        // pixel k of a thread: i = tid + k * 256 over the 33 x 33 out region (row-major), 5 per thread at most
+        float rf[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            rf[k] = 0.f;
+            const int i = tid + k * EHB_TTHREADS;
+            if (refKind && i < EHB_MROWS * EHB_MROWS) {
+                const int qy = i / EHB_MROWS, qx = i - qy * EHB_MROWS;
+                const int px = x0 + qx, py = y0 + qy;
+                if (px < W && py < H && qy < ow && qx < ow) {
+                    if (refKind == 3) {
+                        const uint32_t wbits = __ldg(p.refBits + ((size_t)item * H + py) * p.ntx + (px >> 5));
+                        rf[k] = ((wbits >> (px & 31)) & 1u) ? 1.f : 0.f;
+                    } else {
+                        const size_t o = ibase + (size_t)(H - 1 - py) * W + px;
+                        rf[k] = refKind == 1 ? __ldg(p.ref + o) : (__ldg(p.ref_u8 + o) ? 1.f : 0.f);
+                    }
+                }
+            }
+        }
+        __syncthreads();                                 // the previous tile is done with S
+        if (p.mode == EHB_MODE_AA_BWD) {                 // g = dL/dmask comes from the caller
+            for (int i = tid; i < EHB_MROWS * EHB_MROWS; i += EHB_TTHREADS) {
+                const int qy = i / EHB_MROWS, qx = i - qy * EHB_MROWS;
+                const int px = x0 + qx, py = y0 + qy;
+                sm.S[qy * EHB_MW + qx] = (px < W && py < H) ? __ldg(p.dy + ibase + (size_t)(H - 1 - py) * W + px) : 0.f;
+            }
+        }
+        // ---- rounds over the tile's links (one round for the tiles of a robot arm) -------------------------------------
+        int lNext = 0, rounds = 0, take = 0, nPairsRound = 0;
+        bool first = true;
+        while (lNext < nl) {
+            ehb_tile_round(rb, p, c, lNext, take, nPairsRound);
+            if (c.needAA) ehb_tile_masks(c, take, first);
+            else ehb_tile_backward(rb, p, c, take, nPairsRound);          // operator backward: g is already there
+            lNext += take; first = false; rounds++;
+        }
+        if (!c.needAA) continue;
+        // ================================ E: compose, loss, dL/dsum ================================
+        __syncthreads();
+        if (tid == 0 && storePending) { ehb_bulk_wait_read(); storePending = false; }
+        __syncthreads();
+        double lacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const int i = tid + k * EHB_TTHREADS;
+            if (i >= EHB_MROWS * EHB_MROWS) continue;
+            const int qy = i / EHB_MROWS, qx = i - qy * EHB_MROWS;
+            if (qy >= ow || qx >= ow) continue;
+            const int px = x0 + qx, py = y0 + qy;
+            const bool inImg = px < W && py < H;
+            const float s = nl > 0 ? sm.S[qy * EHB_MW + qx] : 0.f;
+            const float Sv = (p.clamp && s > 1.f) ? 1.f : s;
+            float gv = 0.f;
+            if (refKind && inImg) {
+                const float diff = Sv - rf[k];
+                if (qx < EHB_T && qy < EHB_T) lacc += (double)(diff * diff);
+                gv = (!p.clamp || s <= 1.f) ? (2.f * diff) * p.invB : 0.f;
+            }
+            if (qx < EHB_T && qy < EHB_T && p.masks) {
+                if (tma) sm.stage[(EHB_T - 1 - qy) * EHB_T + qx] = Sv;          // image rows run downwards
+                else if (inImg) p.masks[ibase + (size_t)(H - 1 - py) * W + px] = Sv;
+            }
+            if (oext) sm.S[qy * EHB_MW + qx] = gv;      // (a thread rewrites only the pixels it has just read)
+        }
+        if (refKind && p.loss) {
+            lacc = ehb_warp_sum(lacc);
+            if (lane == 0) sm.lsum[warp] = lacc;
+        }
+        if (tma) ehb_fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            if (tma) {
+                // the tile's image rows: H - 32 - y0 .. H - 1 - y0 (negative start for the top row of tiles: clipped)
+                ehb_tma_store_3d(&p.tmMask, sm.stage, x0, H - EHB_T - y0, item);
+                ehb_bulk_commit();
+                storePending = true;
+            }
+            if (refKind && p.loss) {
+                double t = 0.0;
+                for (int w = 0; w < EHB_TWARPS; w++) t += sm.lsum[w];
+                if (refKind == 3) t -= (double)__ldg(p.refCnt + (size_t)item * p.ntiles + c.tile);   // loss[item] starts at sum(ref)
+                if (t != 0.0) atomicAdd(&p.loss[item], t);
+            }
+        }
+        if (!doBwd || nl == 0) continue;
+        if (rounds == 1) {
+            ehb_tile_backward(rb, p, c, take, nPairsRound);          // the pairs of the forward are still resident
+        } else {
+            lNext = 0;
+            while (lNext < nl) {                                      // g is known now: rebuild each round's pairs for the backward
+                ehb_tile_round(rb, p, c, lNext, take, nPairsRound);
+                ehb_tile_backward(rb, p, c, take, nPairsRound);
+                lNext += take;
+            }
+        }
+    }
+    if (tid == 0 && storePending) ehb_bulk_wait_read();
 }

@@ -4,7 +4,7 @@ The reference runs one Adam step per "epoch": zero_grad -> RBSolver.forward (B x
 backward -> Adam (easyhec/trainer/rbsolver.py:29-43, easyhec/solver/build.py:12-29: lr 3e-3, weight decay 5e-4
 as L2 on ``dof``).  Here one iteration is a fixed sequence of kernels
 
-    pose_compose -> [memset, count, alloc, fill, raster] -> pose_backward -> (all-reduce 7 floats) -> adam
+    pose_compose -> [table, front, raster, raster_big, tiles] -> pose_backward -> (all-reduce 7 floats) -> adam
 
 captured once into a CUDA graph and replayed; nothing returns to the host inside the loop.  When views are sharded
 over ranks (``torch.distributed``), each rank renders its own views and the only exchange is the 7-float
@@ -13,7 +13,7 @@ all-reduce of (d loss/d dof, loss) -- the collective DDP performs for the refere
 import numpy as np
 import torch
 
-from ._lib import Context
+from ._lib import Context, EhbError
 from .se3 import dof_to_matrix, matrix_to_dof
 
 __all__ = ["PoseSolver", "shard_views"]
@@ -43,7 +43,12 @@ class PoseSolver:
             ref = ref.to(torch.uint8)
         if ref.dtype not in (torch.uint8, torch.float32):
             ref = ref.float()
-        self.ref = ref.to(dev).contiguous()
+        # the reference masks do not change during a solve: registered once (bit-packed, per-tile counts); soft (non-binary)
+        # masks cannot be packed and stay a plain f32 tensor
+        try:
+            self.ref = self.ctx.register_ref(ref)
+        except EhbError:
+            self.ref = ref.to(dev).float().contiguous()
         self.B, self.L = self.link_poses.shape[0], self.link_poses.shape[1]
         self.B_global = int(n_views_global or self.B)
         self.group = group

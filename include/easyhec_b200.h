@@ -122,6 +122,21 @@ EHB_API int ehb_render_views_fused_u8(ehb_ctx_t ctx, const int* mesh_ids, int L,
                               const uint8_t* ref_u8_dev, int H, int W, int do_bwd, float* masks_dev,
                               double* loss_dev, double* g_mvp_dev, void* stream);
 
+/* Reference masks registered ONCE (they do not change during a solve; the reference trainer re-uploads them every step,
+ * easyhec/trainer/rbsolver.py:31 `to_cuda(batch)`): binary masks (non-zero = 1; cv2.imread(path, 2) > 0,
+ * easyhec/data/datasets/xarm_real.py:36,40) are bit-packed on the device together with their per-tile pixel counts, so a
+ * fused step reads one bit per pixel of the tiles the robot touches and nothing of the others.
+ *   ref: B*H*W values, image rows; dtype EHB_REF_U8 / EHB_REF_F32 (f32 values must be exactly 0 or 1);
+ *   on_device != 0: `ref` is a device pointer.  Synchronous. */
+#define EHB_REF_U8 0
+#define EHB_REF_F32 1
+EHB_API int ehb_ref_register(ehb_ctx_t ctx, const void* ref, int dtype, int on_device, int B, int H, int W, int* ref_id);
+EHB_API int ehb_ref_release(ehb_ctx_t ctx, int ref_id);
+/* ehb_render_views_fused against views [first_view, first_view + B) of a registered reference. */
+EHB_API int ehb_render_views_fused_ref(ehb_ctx_t ctx, const int* mesh_ids, int L, int B, const float* mvp_dev, int ref_id,
+                               int first_view, int H, int W, int do_bwd, float* masks_dev, double* loss_dev,
+                               double* g_mvp_dev, void* stream);
+
 /* N renders of the packed robot (all L links into one depth buffer, no anti-aliasing) -> out_dev u8[N*H*W]. */
 EHB_API int ehb_render_binary_batch(ehb_ctx_t ctx, const int* mesh_ids, int L, int N, const float* mvp_dev, int H, int W,
                             uint8_t* out_dev, void* stream);
@@ -169,6 +184,9 @@ EHB_API int ehb_adam_step(ehb_ctx_t ctx, float* dof_dev, const float* g7_dev, fl
 EHB_API int ehb_solver_step_begin_u8(ehb_ctx_t ctx, int slot, const int* mesh_ids, int L, int B, const float* mvp_host,
                              const uint8_t* ref_u8_host, int H, int W, double* loss_host, double* g_mvp_host);
 EHB_API int ehb_solver_step_end(ehb_ctx_t ctx, int slot);
+/* The same against a registered reference: per step only the matrices go up (B*L*64 bytes) and loss + gradient come down. */
+EHB_API int ehb_solver_step_begin_ref(ehb_ctx_t ctx, int slot, const int* mesh_ids, int L, int B, const float* mvp_host,
+                              int ref_id, int first_view, int H, int W, double* loss_host, double* g_mvp_host);
 
 /* One-shot all-reduce (sum) of the 7 floats { d loss/d dof, loss } over NVLink peer memory, for view sharding across
  * the GPUs of one box -- the exchange DDP performs for the reference's 6-float parameter (easyhec/trainer/base.py:349).

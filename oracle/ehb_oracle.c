@@ -559,16 +559,18 @@ EHO_API int eho_union_binary(int N, int L, const float* verts, const int* voff, 
     return total_clip;
 }
 
-/* masks[Q*C*H*W] bool -> score[q] = sum_px var_c(mask) (unbiased, torch.var default). */
+/* masks[Q*C*H*W] bool -> score[q] = sum_px var_c(mask) (unbiased, torch.var default).  For 0/1 samples the unbiased
+ * variance of a pixel with k ones out of C is k (C - k) / (C (C - 1)), so the sum over pixels is an integer divided by
+ * C (C - 1): accumulated exactly (the reference sums fp32 variances; its value carries ~1e-7 relative rounding). */
 EHO_API void eho_variance_scores(const uint8_t* masks, int Q, int C, long n, double* score)
 {
     for (int q = 0; q < Q; q++) {
-        double acc = 0.0;
+        unsigned long long acc = 0;
         for (long p = 0; p < n; p++) {
             int k = 0;
-            for (int c = 0; c < C; c++) k += masks[((long)q * C + c) * n + p];
-            if (C > 1) acc += ((double)k - (double)k * k / C) / (C - 1);
+            for (int c = 0; c < C; c++) k += masks[((long)q * C + c) * n + p] != 0;
+            acc += (unsigned long long)(k * (C - k));
         }
-        score[q] = acc;
+        score[q] = C > 1 ? (double)acc / ((double)C * (double)(C - 1)) : 0.0;
     }
 }

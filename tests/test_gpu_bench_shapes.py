@@ -36,6 +36,17 @@ def _check_fused(ctx, ids, packed, mvp, ref, H, W, u8=False):
     assert want["loss"] > 0 and np.abs(want["g_mvp"]).max() > 0
     assert rel_err(g_mvp.cpu().numpy(), want["g_mvp"]) < 1e-9
     assert nclip == want["n_need_clip"]
+    # the same against REGISTERED reference masks (bit-packed once, per-tile counts): identical results
+    h = ctx.register_ref(ref.astype(np.uint8) if u8 else ref)
+    masks2, loss2, g2 = ctx.render_views_fused(ids, to_dev(mvp), h, H, W, backward=True)
+    _, loss3, g3 = ctx.render_views_fused(ids, to_dev(mvp), h, H, W, backward=True, want_masks=False)
+    flags, _ = ctx.status()
+    assert flags & 1 == 0
+    assert np.array_equal(masks2.cpu().numpy(), want["masks"])
+    for l_, g_ in ((loss2, g2), (loss3, g3)):
+        assert np.allclose(l_.cpu().numpy(), want["loss_per_view"], rtol=1e-12, atol=0)
+        assert rel_err(g_.cpu().numpy(), want["g_mvp"]) < 1e-9
+    h.release()
     return want
 
 

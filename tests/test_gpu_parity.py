@@ -257,3 +257,34 @@ def test_pool_overflow_is_flagged_and_recovers():
     assert np.array_equal(masks.cpu().numpy(), want["masks"])
     assert rel_err(g.cpu().numpy(), want["g_mvp"]) < 1e-9
     ctx.close()
+
+
+def test_registered_reference_masks(gpu_ctx):
+    """ehb_ref_register: bit-packed masks + per-tile counts give the results of the f32 path; slices of a registration
+    address runs of views; sizes that are not multiples of 32 / 4 (no TMA tensor map) work; soft masks are rejected."""
+    from easyhec_b200._lib import EhbError
+    from easyhec_b200.scenes import perturb_pose
+    for (B, H, W) in [(4, 120, 160), (3, 101, 67), (2, 75, 130)]:
+        sc = make_scene(B, H, W, links="xarm7", seed=8)
+        packed = oracle.pack_links(sc["meshes"])
+        ref = oracle.union_binary(packed, scene_mvps(sc, H, W), H, W)
+        ref[:, : H // 3, :] = True                       # reference pixels far away from the robot: tiles no link touches
+        mvp = scene_mvps(sc, H, W, perturb_pose(sc["Tc_c2b"], np.random.RandomState(5), 0.02, 2.0))
+        want = oracle.render_views(packed, mvp, ref.astype(np.float32), H, W)
+        ids = [gpu_ctx.register_mesh(m.vertices, m.faces) for m in sc["meshes"]]
+        for host in (True, False):
+            h = gpu_ctx.register_ref(ref if host else to_dev(ref.astype(np.float32)))
+            masks, loss, g = gpu_ctx.render_views_fused(ids, to_dev(mvp), h, H, W, backward=True)
+            assert np.array_equal(masks.cpu().numpy(), want["masks"])
+            assert np.allclose(loss.cpu().numpy(), want["loss_per_view"], rtol=1e-12, atol=0)
+            assert rel_err(g.cpu().numpy(), want["g_mvp"]) < 1e-9
+            if B >= 3:                                   # views 1..2 of the registration, as a sharded caller would use it
+                _, l2, g2 = gpu_ctx.render_views_fused(ids, to_dev(mvp[1:3]), h[1:3], H, W, backward=True, want_masks=False)
+                assert np.allclose(l2.cpu().numpy(), want["loss_per_view"][1:3], rtol=1e-12, atol=0)
+                assert rel_err(g2.cpu().numpy() * 2.0 / B, want["g_mvp"][1:3]) < 1e-9      # scaled by 1 / views of the call
+            h.release()
+        _status_ok(gpu_ctx)
+        with pytest.raises(EhbError):
+            gpu_ctx.register_ref(np.full((1, H, W), 0.5, np.float32))
+        for i in ids:
+            gpu_ctx.release_mesh(i)
