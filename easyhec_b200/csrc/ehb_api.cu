@@ -91,11 +91,12 @@ struct Scratch {
     DevBuf<EhbRec> bigRec;
     DevBuf<EhbUnit> units;
     DevBuf<uint32_t> batchBlk;        // parked heavy batches of k_raster
+    DevBuf<unsigned char> pairPool;   // slabs for tiles whose silhouette pairs do not fit shared memory (k_tiles)
     EhbCounters* ctr = nullptr;
     void release()
     {
         vclip.release(); vsnap.release(); plane.release(); pool.release(); tileList.release(); emptyList.release();
-        touch.release(); bigRec.release(); units.release(); batchBlk.release();
+        touch.release(); bigRec.release(); units.release(); batchBlk.release(); pairPool.release();
     }
 };
 
@@ -356,25 +357,17 @@ EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
-// masks f32 [items][H][W] as a 3-D tensor with 32 x 32 x 1 boxes.  false: not expressible (pitch / alignment) -> plain stores.
-bool make_mask_map(CUtensorMap* map, float* masks, int items, int H, int W)
+// masks f32 [items][H][W] as a 3-D tensor with 32 x `rows` x 1 boxes.  false: not expressible (pitch / alignment) -> plain stores.
+bool make_mask_map(CUtensorMap* map, float* masks, int items, int H, int W, int rows)
 {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn || !masks || (W & 3) != 0 || (((uintptr_t)masks) & 15) != 0 || tune_int("EHB_NO_TMA", 0)) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)items};
     const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * 4 * (cuuint64_t)H};
-    const cuuint32_t box[3] = {EHB_T, EHB_T, 1};
+    const cuuint32_t box[3] = {EHB_T, (cuuint32_t)rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, masks, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-// pair capacity of a tile's shared-memory arrays: 1536 by default; the scratch-growth factor raises it to the maximum a
-// single window can produce (test mode, pool budget 0: starts tiny so that the multi-round path and the growth run)
-int tile_pair_cap(double poolFactor)
-{
-    const int cap = (int)(768.0 * poolFactor);
-    return std::max(64, std::min(2432, (cap + 15) & ~15));
 }
 
 // Launch helper: kernels after the first of a pass are chained with programmatic dependent launch when EHB_PDL is on.
@@ -421,6 +414,11 @@ int ensure_scratch(Ctx* c, Scratch& sc, int items, int L, int Lp, int H, int W, 
     if ((r = sc.vclip.ensure((size_t)items * std::max(Vtot, 1), capturing))) return r;
     if ((r = sc.vsnap.ensure((size_t)items * std::max(Vtot, 1), capturing))) return r;
     const int ntiles = ((W + EHB_T - 1) / EHB_T) * ((H + EHB_T - 1) / EHB_T);
+    if (Lp == L) {   // image-space stage: pair pool (test mode, pool budget 0: one slab, so that the growth path runs)
+        const size_t nSlabs = c->poolBudget == 0.0 ? (size_t)std::max(1.0, 16.0 * c->poolFactor)
+                                                   : (size_t)(64.0 * std::max(1.0, c->poolFactor / 2.0));
+        if ((r = sc.pairPool.ensure(nSlabs * EHB_SLAB_BYTES, capturing))) return r;
+    }
     if ((r = sc.plane.ensure((size_t)items * Lp, capturing))) return r;
     if ((r = sc.tileList.ensure((size_t)items * ntiles, capturing))) return r;
     if ((r = sc.touch.ensure((size_t)items * ntiles, capturing))) return r;
@@ -478,7 +476,9 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
     p.ref = io.ref; p.ref_u8 = io.ref_u8; p.masks = io.masks; p.loss = io.loss; p.gmvp = io.gmvp; p.gpos = io.gpos;
     p.dy = io.dy; p.out_u8 = io.out_u8;
     p.refBits = io.refBits; p.refCnt = io.refCnt; p.refTotal = io.refTotal;
-    p.useTma = (!unionMode && io.masks && make_mask_map(&p.tmMask, io.masks, items, H, W)) ? 1 : 0;
+    p.pairPool = sc.pairPool.p; p.nSlabs = (int)(sc.pairPool.n / EHB_SLAB_BYTES);
+    p.useTma = (!unionMode && io.masks && make_mask_map(&p.tmMask, io.masks, items, H, W, EHB_T) &&
+                ((H % EHB_T) == 0 || make_mask_map(&p.tmMaskTop, io.masks, items, H, W, H % EHB_T))) ? 1 : 0;
     p.dbgbuf = c->dbgbuf;
 
     cudaEvent_t* ev = nullptr;
@@ -519,10 +519,10 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
         const int nq = ((W + 3) / 4) * H;
         CU(launch(ehb_k_union_out, dim3((unsigned)std::min((nq + 255) / 256, 4 * c->nSM), (unsigned)items), dim3(256), 0, st, true, p));
     } else {
-        const int cap = tile_pair_cap(c->poolFactor);
         const long long maxTiles = (long long)items * p.ntiles;
-        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(maxTiles, (long long)c->nSM * tune_int("EHB_TILE_CTAS", 8)));
-        CU(launch(ehb_k_tiles, dim3(grid), dim3(EHB_TTHREADS), ehb_tile_smem_bytes(cap), st, true, rb, p, cap));
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(maxTiles, (long long)c->nSM * tune_int("EHB_TILE_CTAS", 14)));
+        const int refKind = mode != EHB_MODE_FUSED ? 0 : (io.refBits ? 3 : (io.ref ? 1 : (io.ref_u8 ? 2 : 0)));
+        CU(launch(ehb_tiles_kernel(mode, refKind, io.do_bwd != 0), dim3(grid), dim3(EHB_TTHREADS), 0, st, true, rb, p));
     }
     if (ev) cudaEventRecord(ev[4], st);
     c->launches += 5;   // table, front, raster, raster_big, tiles | union_out
@@ -605,7 +605,15 @@ int ehb_ctx_create(int device, ehb_ctx_t* out)
         CU(cudaStreamCreateWithFlags(&c->pipeStream[k], cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&c->evJoin[k], cudaEventDisableTiming));
     }
-    CU(cudaFuncSetAttribute(ehb_k_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ehb_tile_smem_bytes(2432)));
+    // the kernels of a pass run concurrently (pipelines) and want 130 - 210 KB of shared memory per SM for their resident
+    // CTAs: ask for the largest carveout everywhere (left to the driver's heuristic, k_tiles ran one CTA per SM)
+    for (int m = 0; m < 2; m++)
+        for (int rk = 0; rk < 4; rk++)
+            for (int b = 0; b < 2; b++)
+                CU(cudaFuncSetAttribute(ehb_tiles_kernel(m ? EHB_MODE_AA_BWD : EHB_MODE_FUSED, rk, b != 0),
+                                        cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(ehb_k_raster, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(ehb_k_raster_big, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occRaster, ehb_k_raster, EHB_RWARPS * 32, 0));
     c->occRaster = std::max(1, c->occRaster);
     *out = c;
@@ -1073,9 +1081,9 @@ int ehb_pose_compose(ehb_ctx_t h, const float* dof_dev, const float* K_dev, cons
     if (!c || !dof_dev || !K_dev || !link_poses_dev || !mvp_dev || B < 1 || L < 1) return fail(EHB_E_ARG, "bad pose_compose arguments");
     DeviceGuard guard(c->device);
     const int n = B * L;
-    ehb_k_pose_compose<<<std::min((n + 127) / 128, 64), 128, 0, (cudaStream_t)stream>>>(dof_dev, K_dev, link_poses_dev, n, H, W, mvp_dev);
+    CU(launch(ehb_k_pose_compose, dim3(std::min((n + 127) / 128, 64)), dim3(128), 0, (cudaStream_t)stream, true, dof_dev, K_dev,
+              link_poses_dev, n, H, W, mvp_dev));
     c->launches += 1;
-    CU(cudaGetLastError());
     return EHB_OK;
 }
 
@@ -1087,10 +1095,9 @@ int ehb_pose_backward(ehb_ctx_t h, const float* dof_dev, const float* K_dev, con
     if (!c || !dof_dev || !K_dev || !link_poses_dev || !g_mvp_dev || !loss_dev || !out7_dev || B < 1 || L < 1)
         return fail(EHB_E_ARG, "bad pose_backward arguments");
     DeviceGuard guard(c->device);
-    ehb_k_pose_backward<<<1, 256, 0, (cudaStream_t)stream>>>(dof_dev, K_dev, link_poses_dev, g_mvp_dev, loss_dev, B, L, H, W,
-                                                             grad_scale, loss_scale, out7_dev);
+    CU(launch(ehb_k_pose_backward, dim3(1), dim3(256), 0, (cudaStream_t)stream, true, dof_dev, K_dev, link_poses_dev, g_mvp_dev,
+              loss_dev, B, L, H, W, grad_scale, loss_scale, out7_dev));
     c->launches += 1;
-    CU(cudaGetLastError());
     return EHB_OK;
 }
 
@@ -1100,9 +1107,9 @@ int ehb_adam_step(ehb_ctx_t h, float* dof_dev, const float* g7_dev, float* state
     Ctx* c = (Ctx*)h;
     if (!c || !dof_dev || !g7_dev || !state_dev) return fail(EHB_E_ARG, "bad adam arguments");
     DeviceGuard guard(c->device);
-    ehb_k_adam<<<1, 32, 0, (cudaStream_t)stream>>>(dof_dev, g7_dev, state_dev, lr, beta1, beta2, eps, weight_decay, hist_dev, hist_cap);
+    CU(launch(ehb_k_adam, dim3(1), dim3(32), 0, (cudaStream_t)stream, true, dof_dev, g7_dev, state_dev, lr, beta1, beta2, eps,
+              weight_decay, hist_dev, hist_cap));
     c->launches += 1;
-    CU(cudaGetLastError());
     return EHB_OK;
 }
 

@@ -65,14 +65,19 @@ struct __align__(128) EhbCounters {
         unsigned int nBatchBlk;  // batches with many rows: records parked, the rows beyond the inline share become units too
         unsigned int pad[29];
     } q[32];
-    // (one spare line)
-    unsigned int pad3[32];
+    // pair pool of the image-space stage: slabs handed to the rare tile whose pairs do not fit shared memory
+    unsigned int slabCursor;
+    unsigned int pad3[31];
     unsigned long long dbg[16];   // EHB_TIMING builds: cycles per phase of k_tiles (thread 0 of every CTA)
 };
 static_assert(sizeof(EhbCounters) % 128 == 0, "counter lines");
 
 struct EhbParams {
-    CUtensorMap tmMask;      // masks as a [items][H][W] f32 tensor, box 32 x 32 x 1 (valid when useTma)
+    // masks as a [items][H][W] f32 tensor (valid when useTma): box 32 x 32 x 1, and box 32 x (H % 32) x 1 for the top row
+    // of tiles when H is not a multiple of 32 -- a tile store may stick out of the tensor on the high side (clipped by the
+    // hardware) but must not start at a negative coordinate (measured: illegal instruction), so the partial tiles at the
+    // top of the image get their own, shorter box that starts at image row 0
+    CUtensorMap tmMask, tmMaskTop;
     int useTma;
     int H, W, ntx, nty, ntiles;
     int items, L, Lp, Ftot, Vtot;   // Lp = planes per item: L (per-link visibility) or 1 (packed robot)
@@ -107,6 +112,8 @@ struct EhbParams {
     // reference masks registered once (ehb_ref_register): one bit per pixel, GL rows, a 32-bit word per (row, tile column);
     // refCnt = set bits of every tile's interior, refTotal = set bits of the item.  loss[item] starts at refTotal and every
     // listed tile adds (its loss - its refCnt): the tiles no link touches are never read.
+    unsigned char* pairPool; // [nSlabs][EHB_SLAB_BYTES]  pair lists that do not fit a CTA's shared memory (ehb_tiles.cuh)
+    int nSlabs;
     const uint32_t* refBits; // [items, H, ntx]
     const uint32_t* refCnt;  // [items, ntiles]
     const unsigned long long* refTotal;   // [items]
@@ -172,6 +179,7 @@ __global__ void __launch_bounds__(256) ehb_k_table(const __grid_constant__ EhbRo
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         p.ctr->nTiles = 0u; p.ctr->nLight = 0u; p.ctr->nEmpty = 0u; p.ctr->workCursor = 0u;
         p.ctr->rasterCursor = (unsigned)p.rasterStart;
+        p.ctr->slabCursor = 0u;
     }
     if (blockIdx.x == 0 && threadIdx.x < EHB_NQ) {
         p.ctr->q[threadIdx.x].nBigRec = 0u; p.ctr->q[threadIdx.x].nUnits = 0u; p.ctr->q[threadIdx.x].nBatchBlk = 0u;
@@ -632,7 +640,8 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
                 for (int i = blockIdx.x * EHB_RWARPS + warp; i < n; i += streamBlocks * EHB_RWARPS) {
                     const int wid = (int)p.emptyList[i];
                     const int item = wid / p.ntiles, tile = wid - item * p.ntiles;
-                    ehb_tma_store_3d(&p.tmMask, zero, (tile % p.ntx) * EHB_T, p.H - EHB_T - (tile / p.ntx) * EHB_T, item);
+                    const int row0 = p.H - EHB_T - (tile / p.ntx) * EHB_T;   // first image row of the tile (negative: top row of tiles)
+                    ehb_tma_store_3d(row0 < 0 ? &p.tmMaskTop : &p.tmMask, zero, (tile % p.ntx) * EHB_T, max(row0, 0), item);
                 }
                 ehb_bulk_commit();
                 ehb_bulk_wait_read();

@@ -10,6 +10,14 @@
 #pragma once
 #include <cuda_runtime.h>
 
+// programmatic dependent launch: see ehb_pdl_enter (ehb_kernels.cuh); the pose kernels are chained the same way
+__device__ __forceinline__ void ehb_pose_pdl_enter()
+{
+#ifdef EHB_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
 struct EhbDual { double v, d; };
 __device__ __forceinline__ EhbDual operator+(EhbDual a, EhbDual b) { return {a.v + b.v, a.d + b.d}; }
 __device__ __forceinline__ EhbDual operator-(EhbDual a, EhbDual b) { return {a.v - b.v, a.d - b.d}; }
@@ -72,6 +80,7 @@ __device__ __forceinline__ void ehb_projection(const float* K, int H, int W, flo
 __global__ void ehb_k_pose_compose(const float* __restrict__ dof, const float* __restrict__ K,
                                    const float* __restrict__ lp, int n, int H, int W, float* __restrict__ mvp)
 {
+    ehb_pose_pdl_enter();
     __shared__ float M[16];   // P @ [Tc; 0 0 0 1] is NOT pre-multiplied: the reference composes P @ (Tc @ lp)
     __shared__ float Tc[16];
     if (threadIdx.x == 0) {
@@ -107,13 +116,17 @@ __global__ void ehb_k_pose_compose(const float* __restrict__ dof, const float* _
     }
 }
 
-// one block of 256 threads.  out7 = { d loss / d dof [6], loss } with the caller's scales applied.
+// one block of 256 threads.  out7 = { d loss / d dof [6], loss } with the caller's scales applied.  The tail is spread over
+// threads (12 for P^T S, 6 for the six dual-number evaluations of the exp map): fp64 on one thread was 6 us of pure latency.
 __global__ void __launch_bounds__(256) ehb_k_pose_backward(const float* __restrict__ dof, const float* __restrict__ K,
                                                            const float* __restrict__ lp, const double* __restrict__ gmvp,
                                                            const double* __restrict__ loss, int B, int L, int H, int W,
                                                            double grad_scale, double loss_scale, float* __restrict__ out7)
 {
+    ehb_pose_pdl_enter();
     __shared__ double S[8][17];
+    __shared__ double T[17];
+    __shared__ double G[12];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // S = sum_{b,l} g_mvp[b,l] @ lp[b,l]^T ;  S[16] = sum_b loss_b
     double acc[17];
@@ -135,27 +148,30 @@ __global__ void __launch_bounds__(256) ehb_k_pose_backward(const float* __restri
         if (lane == 0) S[warp][i] = v;
     }
     __syncthreads();
-    if (tid == 0) {
-        double T[17];
-        for (int i = 0; i < 17; i++) { T[i] = 0.0; for (int w = 0; w < 8; w++) T[i] += S[w][i]; }
+    if (tid < 17) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += S[w][tid];
+        T[tid] = t;
+    }
+    __syncthreads();
+    if (tid < 12) {   // top three rows of P^T @ S
         float k[9], P[16];
         for (int i = 0; i < 9; i++) k[i] = K[i];
         ehb_projection(k, H, W, P);
-        double G[12];   // top three rows of P^T @ S
-        for (int r = 0; r < 3; r++)
-            for (int c = 0; c < 4; c++) {
-                double s = 0.0;
-                for (int q = 0; q < 4; q++) s += (double)P[4 * q + r] * T[4 * q + c];
-                G[4 * r + c] = s;
-            }
-        for (int i = 0; i < 6; i++) {
-            EhbDual d[6], t[12];
-            for (int j = 0; j < 6; j++) d[j] = {(double)dof[j], j == i ? 1.0 : 0.0};
-            ehb_se3_exp<EhbDual>(d, t, 1e-4);
-            double s = 0.0;
-            for (int j = 0; j < 12; j++) s += G[j] * t[j].d;
-            out7[i] = (float)(s * grad_scale);
-        }
+        const int r = tid >> 2, c = tid & 3;
+        double s = 0.0;
+        for (int q = 0; q < 4; q++) s += (double)P[4 * q + r] * T[4 * q + c];
+        G[tid] = s;
+    }
+    __syncthreads();
+    if (tid < 6) {
+        EhbDual d[6], t[12];
+        for (int j = 0; j < 6; j++) d[j] = {(double)dof[j], j == tid ? 1.0 : 0.0};
+        ehb_se3_exp<EhbDual>(d, t, 1e-4);
+        double s = 0.0;
+        for (int j = 0; j < 12; j++) s += G[j] * t[j].d;
+        out7[tid] = (float)(s * grad_scale);
+    } else if (tid == 6) {
         out7[6] = (float)(T[16] * loss_scale);
     }
 }
@@ -164,6 +180,7 @@ __global__ void __launch_bounds__(256) ehb_k_pose_backward(const float* __restri
 __global__ void ehb_k_adam(float* __restrict__ dof, const float* __restrict__ g7, float* __restrict__ state, float lr,
                            float beta1, float beta2, float eps, float wd, float* __restrict__ hist, int hist_cap)
 {
+    ehb_pose_pdl_enter();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int t = (int)state[12] + 1;
     if (hist && t - 1 < hist_cap)

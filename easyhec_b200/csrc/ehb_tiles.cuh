@@ -1,24 +1,26 @@
 // ehb_tiles.cuh -- the image-space half of a pass: antialias, compose, loss, backward -- ONE kernel.
 //
 // The reference antialiases every link on its own, sums the per-link masks and clamps (rb_solver.py:62-68), and its
-// backward scatters one gradient per silhouette pixel pair (dr.antialias).  Here one CTA owns one listed
-// 32x32 tile and keeps everything of it in shared memory, so that no intermediate (per-link mask, gradient window,
-// pair list) ever goes to L2 / HBM and the whole stage is a single launch:
+// backward scatters one gradient per silhouette pixel pair (dr.antialias).  Here one small CTA (4 warps)
+// owns one listed 32x32 tile and keeps everything of it in shared memory, so that no intermediate (per-link mask,
+// gradient window, pair list) ever goes to L2 / HBM and the whole stage is a single launch with every tile of the pass
+// resident at once (7 CTAs per SM):
 //   A  windows   35x35 window of every link's depth plane that reaches into the tile -> triangle ids in shared memory
-//                (all 256 threads load, every load of the phase in flight at once), row coverage masks by ballot
+//                (all threads load, every load of a batch in flight at once), row coverage masks by ballot
 //   B  pairs     silhouette pixel pairs by XOR of neighbouring coverage masks (one warp per link, lane = row) -> ONE pair
 //                list for the tile
-//   C  weights   blend weight of every pair (ehb_aa_pair), all threads stride over the tile's list: the work of a tile is
-//                balanced over its 8 warps whatever its links look like
+//   C  weights   blend weight of every pair (ehb_aa_pair), all threads stride over the tile's list
 //   D  masks     per link: coverage as floats + the four contribution kinds in the reference's order
 //   E  compose   S = min(sum of the link masks in link order, 1) -> staging tile -> ONE TMA tensor store (UTMASTG);
 //                (S - ref)^2 -> loss; g = dL/dsum of the out region stays in shared memory
 //   F  backward  every owned pair with a non-zero weight: analytic gradient of its two edge vertices
 //                (ehb_aa_pair_grad), contracted with [x y z 1] on the fly (fp64), reduced per link by shuffles and
 //                shared-memory accumulators, 12 fp64 atomics per (tile, link) into d loss / d mvp
-// Links are processed in rounds of at most EHB_RL (their windows' storage), a round's pairs must fit the pair arrays
-// (capacity = a launch parameter): a tile that needs several rounds runs A-D per round for the forward, and A-C again
-// per round for the backward (g is only known once every link has been composed).  Tiles of a robot arm need one round.
+// Listed tiles that no triangle reaches (a link's bounding box overlaps them, nothing more) are a zero tile: one TMA store.
+// Links are processed in rounds of at most EHB_RL (their windows' storage); a round's pairs live in shared memory
+// (EHB_CAPS) or, for the rare window with more, in a slab of the context's pair pool in global memory.  A tile that needs
+// several rounds runs A-D per round for the forward and A-C again per round for the backward (g is only known once every
+// link has been composed).  Tiles of a robot arm need one round.
 #pragma once
 #include "ehb_kernels.cuh"
 
@@ -26,12 +28,18 @@
 #define EHB_MW 36                        // row pitch (floats) of a link mask / the S / g window
 #define EHB_MSZ (EHB_MROWS * EHB_MW)
 #ifndef EHB_RL
-#define EHB_RL 5                         // links whose windows are resident at a time
+#define EHB_RL 3                         // links whose windows are resident at a time
 #endif
-#define EHB_TTHREADS 256
+#define EHB_TTHREADS 128
 #define EHB_TWARPS (EHB_TTHREADS / 32)
 #define EHB_IDS_WORDS (EHB_NP + 3)       // ids of one window (35 x 35); the same storage later holds the link's mask
+#ifndef EHB_CAPS
+#define EHB_CAPS 512                     // pairs of a round that fit shared memory
+#endif
+#define EHB_CAPG 2432                    // pairs of a slab in global memory (>= the 2380 pairs one window can have)
+#define EHB_SLAB_BYTES (EHB_CAPG * 12)   // alpha f32 | tri u32 | pk u16 | slot u8 (+ 1 pad)
 static_assert(EHB_IDS_WORDS >= EHB_MSZ, "the mask of a link reuses its window's storage");
+static_assert(EHB_IDS_WORDS * 4 >= EHB_T * EHB_T * 4, "the staging tile of the TMA store reuses the first window's storage");
 static_assert(EHB_RL <= EHB_TWARPS, "one warp per resident link in the per-link phases");
 
 __device__ __forceinline__ unsigned long long ehb_bits(int lo, int hi)   // bits lo..hi (inclusive), empty if lo > hi
@@ -49,138 +57,119 @@ __device__ __forceinline__ uint32_t ehb_list_at(const EhbParams& p, unsigned e, 
 
 struct EhbSlot {                         // one resident link of the tile
     int link;
-    int x0, y0, w, h;                    // its depth plane
-    long long off;
     int pairBase, nPairs;                // its part of the tile's pair list
+    int pad;
 };
 
-// dynamic shared memory of a CTA (byte offsets; every block 16-byte aligned, the staging tile 128-byte aligned)
-struct EhbTileSmem {
-    float* stage;                        // [32][32]   composed tile, source of the TMA store
-    float* S;                            // [33][36]   running sum of the link masks, then g = dL/dsum
-    uint32_t* ids;                       // [RL][IDS_WORDS]
-    unsigned long long* cov;             // [RL][36]
-    float* alpha;                        // [cap]
-    uint32_t* ptri;                      // [cap]
-    unsigned short* pk;                  // [cap]  idx (11) | d << 11 | own << 12 | side << 13 | di << 14
-    unsigned char* pslot;                // [cap]
-    double* gacc;                        // [RL][12]
-    EhbSlot* slot;                       // [RL]
-    double* lsum;                        // [TWARPS]
-    int* misc;                           // [8]
+struct __align__(128) EhbTileSm {
+    uint32_t ids[EHB_RL][EHB_IDS_WORDS];         // [0] doubles as the 32 x 32 staging tile of the TMA store (128-byte aligned)
+    float S[EHB_MSZ];                            // running sum of the link masks, then g = dL/dsum
+    unsigned long long cov[EHB_RL][36];
+    float alpha[EHB_CAPS];
+    uint32_t ptri[EHB_CAPS];
+    unsigned short pk[EHB_CAPS];                 // idx (11) | d << 11 | own << 12 | side << 13 | di << 14
+    unsigned char pslot[EHB_CAPS];
+    double gacc[EHB_RL][12];
+    double lsum[EHB_TWARPS];
+    EhbPlane planes[EHB_MAX_LINKS];              // the item's depth planes, fetched together with the tile's link bits
+    EhbSlot slot[EHB_RL];
+    uint32_t rbits[EHB_MROWS][2];                // registered reference: bits of the out region's rows
+    uint32_t bits, refCnt;
+    int slab;                                    // index of the CTA's slab in the pair pool (-1: none yet)
 };
-__host__ __device__ inline size_t ehb_tile_smem_bytes(int cap)
-{
-    size_t n = 4096 + EHB_MSZ * 4 + (size_t)EHB_RL * EHB_IDS_WORDS * 4 + (size_t)EHB_RL * 36 * 8;
-    n = (n + 15) & ~(size_t)15;
-    n += (size_t)cap * (4 + 4 + 2 + 1);
-    n = (n + 15) & ~(size_t)15;
-    n += EHB_RL * 12 * 8 + EHB_RL * sizeof(EhbSlot) + EHB_TWARPS * 8 + 8 * 4 + 64;
-    return n + 128;                      // slack for the 128-byte alignment of the base
-}
-__device__ __forceinline__ EhbTileSmem ehb_tile_smem(unsigned char* base, int cap)
-{
-    base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(base) + 127) & ~(uintptr_t)127);
-    EhbTileSmem s;
-    s.stage = reinterpret_cast<float*>(base); base += 4096;
-    s.S = reinterpret_cast<float*>(base); base += EHB_MSZ * 4;
-    s.ids = reinterpret_cast<uint32_t*>(base); base += (size_t)EHB_RL * EHB_IDS_WORDS * 4;
-    s.cov = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(base) + 7) & ~(uintptr_t)7);
-    base = reinterpret_cast<unsigned char*>(s.cov) + (size_t)EHB_RL * 36 * 8;
-    base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(base) + 15) & ~(uintptr_t)15);
-    s.alpha = reinterpret_cast<float*>(base); base += (size_t)cap * 4;
-    s.ptri = reinterpret_cast<uint32_t*>(base); base += (size_t)cap * 4;
-    s.pk = reinterpret_cast<unsigned short*>(base); base += (size_t)cap * 2;
-    s.pslot = base; base += (size_t)cap;
-    base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(base) + 15) & ~(uintptr_t)15);
-    s.gacc = reinterpret_cast<double*>(base); base += EHB_RL * 12 * 8;
-    s.slot = reinterpret_cast<EhbSlot*>(base); base += EHB_RL * sizeof(EhbSlot);
-    base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(base) + 7) & ~(uintptr_t)7);
-    s.lsum = reinterpret_cast<double*>(base); base += EHB_TWARPS * 8;
-    s.misc = reinterpret_cast<int*>(base);
-    return s;
-}
 
-// link index of the k-th set bit of `bits`
-__device__ __forceinline__ int ehb_nth_bit(uint32_t bits, int k) { return (int)__fns(bits, 0, k + 1); }
+// the pair arrays of a round: shared memory, or a slab in global memory
+struct EhbPairs {
+    float* alpha; uint32_t* ptri; unsigned short* pk; unsigned char* pslot;
+};
+
+// EHB_STATS builds: thread 0 of every CTA adds the cycles it spent per phase to the developer counters (ehb_ctx_debug_counters):
+// [0] tiles, [1] links, [2] tiles without links, [3] pairs, [4] tiles with several rounds, [5] A windows, [6] B pairs,
+// [7] C weights, [8] D masks, [9] E compose, [10] F backward, [11] whole tile, [12] rounds in a global slab
+#ifdef EHB_STATS
+#define EHB_STAT_T(var) const long long var = clock64()
+#define EHB_STAT_ADD(i, v) do { if (threadIdx.x == 0) atomicAdd(&p.ctr->dbg[i], (unsigned long long)(v)); } while (0)
+#else
+#define EHB_STAT_T(var)
+#define EHB_STAT_ADD(i, v)
+#endif
 
 // Everything a CTA knows about the tile it is working on.
 struct EhbTileCtx {
-    EhbTileSmem sm;
-    int cap, tid, lane, warp;
+    int tid, lane, warp;
     int item, tile, x0, y0, rx0, ry0, nl;
     uint32_t bits;
-    bool needAA;
-    int ow;
 };
 
 // A + B + C for the links [lNext, lNext + take) of the tile (in link order).  On return `take` is the number of links
-// that fit the pair arrays (>= 1) and the pair list holds their `nPairsRound` pairs with weights.
-__device__ __forceinline__ void ehb_tile_round(const EhbRobot& rb, const EhbParams& p, const EhbTileCtx& c, int lNext, int& take,
-                                               int& nPairsRound)
+// whose pairs fit one list (>= 1), `pr` the list (shared memory or a global slab) with the `nPairsRound` pairs and weights.
+template <bool NEEDAA, int OW>
+__device__ __forceinline__ void ehb_tile_round(const EhbRobot& rb, const EhbParams& p, EhbTileSm& sm, const EhbTileCtx& c, int lNext,
+                                               int& take, int& nPairsRound, EhbPairs& pr)
 {
-    const EhbTileSmem& sm = c.sm;
-    const int tid = c.tid, lane = c.lane, warp = c.warp, cap = c.cap;
-    const int H = p.H, W = p.W, hlo = 1, ow = c.ow;
+    const int tid = c.tid, lane = c.lane, warp = c.warp;
+    const int H = p.H, W = p.W, hlo = 1, ow = OW;
     __syncthreads();                                     // the previous round / tile is done with the arrays
+    EHB_STAT_T(tA);
     take = min(EHB_RL, c.nl - lNext);
-    // ================================ A: slots, windows, coverage ================================
-    if (tid < take) {
-        const int l = ehb_nth_bit(c.bits, lNext + tid);
-        const EhbPlane pl = p.plane[(size_t)c.item * p.L + l];
-        EhbSlot s;
-        s.link = l; s.x0 = pl.x0; s.y0 = pl.y0; s.w = pl.w; s.h = pl.h; s.off = pl.off; s.pairBase = 0; s.nPairs = 0;
-        sm.slot[tid] = s;
-    }
-    __syncthreads();
+    // ================================ A: windows, coverage ================================
+    // One window row per warp and step, lane = column (columns 32..34 by lanes 0..2), four rows of loads in flight per
+    // warp; the coverage bits of a row come straight from the loaded values by ballot.
+    int lk[EHB_RL];                                  // links of the round's slots (link order)
     {
-        const int total = take * EHB_NP;
-        for (int e0 = tid; e0 < total; e0 += 6 * EHB_TTHREADS) {
-            unsigned long long v[6];
+        uint32_t b = c.bits;
+        for (int q = 0; q < lNext; q++) b &= b - 1;
 #pragma unroll
-            for (int k = 0; k < 6; k++) {       // every load of the batch is issued before the first is consumed
-                v[k] = EHB_EMPTY;
-                const int ee = e0 + k * EHB_TTHREADS;
-                if (ee < total) {
-                    const int s = ee / EHB_NP, i = ee - s * EHB_NP;
-                    const int r = i / EHB_RS, cc = i - r * EHB_RS;
-                    const EhbSlot& sl = sm.slot[s];
-                    const int cx = c.rx0 + cc - sl.x0, cy = c.ry0 + r - sl.y0;
-                    if ((unsigned)cx < (unsigned)sl.w && (unsigned)cy < (unsigned)sl.h)
-                        v[k] = p.pool[sl.off + (long long)cy * sl.w + cx];
+        for (int q = 0; q < EHB_RL; q++) { lk[q] = b ? __ffs(b) - 1 : 0; b &= b - 1; }
+    }
+    {
+        const int nrows = take * EHB_RS;
+        for (int base = warp; base < nrows; base += 4 * EHB_TWARPS) {
+            unsigned long long v0[4], v1[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int sr = base + j * EHB_TWARPS;
+                v0[j] = EHB_EMPTY; v1[j] = EHB_EMPTY;
+                if (sr < nrows) {
+                    const int s = sr / EHB_RS, r = sr - s * EHB_RS;
+                    int l = lk[0];
+#pragma unroll
+                    for (int q = 1; q < EHB_RL; q++) l = s == q ? lk[q] : l;
+                    const EhbPlane& pl = sm.planes[l];
+                    const int cy = c.ry0 + r - pl.y0, cx = c.rx0 - pl.x0 + lane;
+                    if ((unsigned)cy < (unsigned)pl.h) {
+                        const unsigned long long* row = p.pool + pl.off + (long long)cy * pl.w;
+                        if ((unsigned)cx < (unsigned)pl.w) v0[j] = row[cx];
+                        if (lane < EHB_RS - 32 && (unsigned)(cx + 32) < (unsigned)pl.w) v1[j] = row[cx + 32];
+                    }
                 }
             }
 #pragma unroll
-            for (int k = 0; k < 6; k++) {
-                const int ee = e0 + k * EHB_TTHREADS;
-                if (ee < total) {
-                    const int s = ee / EHB_NP, i = ee - s * EHB_NP;
-                    sm.ids[s * EHB_IDS_WORDS + i] = (uint32_t)v[k];   // low word = triangle id (all ones: empty)
+            for (int j = 0; j < 4; j++) {
+                const int sr = base + j * EHB_TWARPS;
+                if (sr < nrows) {                    // (warp-uniform)
+                    const int s = sr / EHB_RS, r = sr - s * EHB_RS;
+                    uint32_t* dst = &sm.ids[s][r * EHB_RS];
+                    dst[lane] = (uint32_t)v0[j];     // low word = triangle id (all ones: empty)
+                    if (lane < EHB_RS - 32) dst[32 + lane] = (uint32_t)v1[j];
+                    const unsigned b0 = __ballot_sync(0xffffffffu, v0[j] != EHB_EMPTY);
+                    const unsigned b1 = __ballot_sync(0xffffffffu, lane < EHB_RS - 32 && v1[j] != EHB_EMPTY);
+                    if (lane == 0) sm.cov[s][r] = (unsigned long long)b0 | ((unsigned long long)b1 << 32);
                 }
             }
         }
+        if (tid < take) sm.cov[tid][EHB_RS] = 0ull;
     }
     __syncthreads();
-    // row coverage masks: (slot, row) pairs over the warps; bits 0..31 from one ballot, 32..34 from a second
-    for (int sr = warp; sr < take * (EHB_RS + 1); sr += EHB_TWARPS) {
-        const int s = sr / (EHB_RS + 1), r = sr - s * (EHB_RS + 1);
-        unsigned long long m = 0ull;
-        if (r < EHB_RS) {
-            const uint32_t* row = sm.ids + s * EHB_IDS_WORDS + r * EHB_RS;
-            const unsigned b0 = __ballot_sync(0xffffffffu, row[lane] != 0xFFFFFFFFu);
-            const unsigned b1 = __ballot_sync(0xffffffffu, lane < EHB_RS - 32 && row[32 + lane] != 0xFFFFFFFFu);
-            m = (unsigned long long)b0 | ((unsigned long long)b1 << 32);
-        }
-        if (lane == 0) sm.cov[s * 36 + r] = m;
-    }
-    __syncthreads();
+    EHB_STAT_T(tB);
+    EHB_STAT_ADD(5, tB - tA);
     // ================================ B: silhouette pairs, one warp per slot, lane = window row ================================
     // columns whose pixel is inside the image, and for which the right neighbour is too
     const unsigned long long inX = ehb_bits(-c.rx0, W - 1 - c.rx0), inX1 = ehb_bits(-c.rx0, W - 2 - c.rx0);
     unsigned long long hm[2] = {0ull, 0ull}, vm[2] = {0ull, 0ull}, om[2] = {0ull, 0ull};
     int o0 = 0, o1 = 0;
     if (warp < take) {
-        const unsigned long long* cv = sm.cov + warp * 36;
+        const unsigned long long* cv = sm.cov[warp];
         int cnt[2];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -190,7 +179,7 @@ __device__ __forceinline__ void ehb_tile_round(const EhbRobot& rb, const EhbPara
                 const unsigned long long cm = cv[r], cu = cv[r + 1];
                 // pairs wanted: forward = those touching a pixel of the out region; otherwise only owned ones
                 unsigned long long wantH, wantV;
-                if (c.needAA) {
+                if (NEEDAA) {
                     wantH = (r >= hlo && r <= hlo + ow - 1) ? ehb_bits(hlo - 1, hlo + ow - 1) : 0ull;
                     wantV = (r >= hlo - 1 && r <= hlo + ow - 1) ? ehb_bits(hlo, hlo + ow - 1) : 0ull;
                 } else {
@@ -218,100 +207,129 @@ __device__ __forceinline__ void ehb_tile_round(const EhbRobot& rb, const EhbPara
         }
         const int tot1 = __shfl_sync(0xffffffffu, inc1, 3);
         o0 = inc - cnt[0]; o1 = tot0 + inc1 - cnt[1];
-        if (lane == 0) sm.slot[warp].nPairs = tot0 + tot1;
+        if (lane == 0) {
+            int l = lk[0];
+#pragma unroll
+            for (int q = 1; q < EHB_RL; q++) l = warp == q ? lk[q] : l;
+            sm.slot[warp].nPairs = tot0 + tot1; sm.slot[warp].link = l;
+        }
     }
     __syncthreads();
-    // fit the round into the pair arrays: the longest prefix of slots whose pairs fit (at least one slot)
+    // fit the round into one pair list: the longest prefix of slots whose pairs fit a slab (at least one slot: a window
+    // has at most 2380 pairs); every thread computes the same answer from the slots' counts
     nPairsRound = 0;
-    int fit = 0;
+    int fit = 0, myBase = 0;
     for (int s = 0; s < take; s++) {
         const int n = sm.slot[s].nPairs;
-        if (s > 0 && nPairsRound + n > cap) break;
+        if (s > 0 && nPairsRound + n > EHB_CAPG) break;
+        if (s == warp) myBase = nPairsRound;
         nPairsRound += n; fit = s + 1;
     }
-    if (nPairsRound > cap) {          // one window with more pairs than the arrays hold: flagged, grow and rerun
-        if (tid == 0) atomicOr(&p.ctr->flags, 1u);
-        nPairsRound = cap;
-    }
+    nPairsRound = min(nPairsRound, EHB_CAPG);
     take = fit;
-    __syncthreads();
-    if (tid == 0) {
-        int b = 0;
-        for (int s = 0; s < take; s++) { sm.slot[s].pairBase = b; b += sm.slot[s].nPairs; }
+    pr.alpha = sm.alpha; pr.ptri = sm.ptri; pr.pk = sm.pk; pr.pslot = sm.pslot;
+    if (nPairsRound > EHB_CAPS) {
+        // more pairs than shared memory holds: this CTA takes a slab of the context's pair pool (kept for its later rounds)
+        if (tid == 0 && sm.slab < 0) {
+            const unsigned k = atomicAdd(&p.ctr->slabCursor, 1u);
+            if (k < (unsigned)p.nSlabs) sm.slab = (int)k;
+            else atomicOr(&p.ctr->flags, 1u);              // pool exhausted: flagged, the host grows it and reruns the pass
+        }
+        __syncthreads();
+        EHB_STAT_ADD(12, 1);
+        if (sm.slab >= 0) {
+            unsigned char* base = p.pairPool + (size_t)sm.slab * EHB_SLAB_BYTES;
+            pr.alpha = reinterpret_cast<float*>(base);
+            pr.ptri = reinterpret_cast<uint32_t*>(base + EHB_CAPG * 4);
+            pr.pk = reinterpret_cast<unsigned short*>(base + EHB_CAPG * 8);
+            pr.pslot = base + EHB_CAPG * 10;
+        } else {
+            nPairsRound = min(nPairsRound, EHB_CAPS);      // (results of this pass are discarded)
+        }
     }
-    __syncthreads();
+    const int capNow = pr.alpha == sm.alpha ? EHB_CAPS : EHB_CAPG;
     if (warp < take) {
-        const int base = sm.slot[warp].pairBase;
+        if (lane == 0) sm.slot[warp].pairBase = myBase;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            int o = base + (h ? o1 : o0);
+            int o = myBase + (h ? o1 : o0);
             unsigned long long hxm = hm[h], vym = vm[h];
             const uint32_t rowBase = (uint32_t)(lane + 32 * h) * EHB_RS;
             while (hxm) {
                 const int b = __ffsll((long long)hxm) - 1;
                 hxm &= hxm - 1;
-                if (o < cap) {
-                    sm.pk[o] = (unsigned short)((rowBase + b) | (((om[h] >> b) & 1ull) ? (1u << 12) : 0u));
-                    sm.pslot[o] = (unsigned char)warp;
+                if (o < capNow) {
+                    pr.pk[o] = (unsigned short)((rowBase + b) | (((om[h] >> b) & 1ull) ? (1u << 12) : 0u));
+                    pr.pslot[o] = (unsigned char)warp;
                 }
                 o++;
             }
             while (vym) {
                 const int b = __ffsll((long long)vym) - 1;
                 vym &= vym - 1;
-                if (o < cap) {
-                    sm.pk[o] = (unsigned short)((rowBase + b) | (1u << 11) | (((om[h] >> b) & 1ull) ? (1u << 12) : 0u));
-                    sm.pslot[o] = (unsigned char)warp;
+                if (o < capNow) {
+                    pr.pk[o] = (unsigned short)((rowBase + b) | (1u << 11) | (((om[h] >> b) & 1ull) ? (1u << 12) : 0u));
+                    pr.pslot[o] = (unsigned char)warp;
                 }
                 o++;
             }
         }
     }
     __syncthreads();
+    EHB_STAT_T(tC);
+    EHB_STAT_ADD(6, tC - tB);
+    EHB_STAT_ADD(3, nPairsRound);
     // ================================ C: blend weights, all threads over the tile's pair list ================================
     for (int i = tid; i < nPairsRound; i += EHB_TTHREADS) {
-        const uint32_t pk = sm.pk[i];
-        const int s = sm.pslot[i];
+        const uint32_t pk = pr.pk[i];
+        const int s = pr.pslot[i];
         const int l = sm.slot[s].link;
         const int idx = pk & 2047, d = (pk >> 11) & 1;
         const int ly = idx / EHB_RS, lx = idx - ly * EHB_RS;
-        const uint32_t* idw = sm.ids + s * EHB_IDS_WORDS;
-        const uint32_t ka = idw[idx], kb = idw[idx + (d ? EHB_RS : 1)];
+        const uint32_t ka = sm.ids[s][idx], kb = sm.ids[s][idx + (d ? EHB_RS : 1)];
         const int side = ka != 0xFFFFFFFFu ? 0 : 1;
         const uint32_t t = side ? kb : ka;
         int di;
         const float al = ehb_aa_pair(rb.link[l], p.vclip + (size_t)c.item * p.Vtot + rb.voff[l], (int)t, side, c.rx0 + lx, c.ry0 + ly, d,
                                      H, W, &di);
-        sm.alpha[i] = al;
-        sm.ptri[i] = t;
-        sm.pk[i] = (unsigned short)(pk | ((uint32_t)side << 13) | ((uint32_t)di << 14));
+        pr.alpha[i] = al;
+        pr.ptri[i] = t;
+        pr.pk[i] = (unsigned short)(pk | ((uint32_t)side << 13) | ((uint32_t)di << 14));
     }
     __syncthreads();
+    EHB_STAT_ADD(7, clock64() - tC);
 }
 
-// D: the antialiased masks of the round's links (out region), then the running sum in link order.
-__device__ __forceinline__ void ehb_tile_masks(const EhbTileCtx& c, int take, bool first)
+// D: the antialiased masks of the round's links (out region).
+template <int OW>
+__device__ __forceinline__ void ehb_tile_masks(const EhbParams& p, EhbTileSm& sm, const EhbTileCtx& c, const EhbPairs& pr, int take,
+                                               int nPairsRound, bool first)
 {
-    const EhbTileSmem& sm = c.sm;
-    const int lane = c.lane, warp = c.warp, hlo = 1, ow = c.ow;
-    // colour = coverage as floats (the window's ids are dead: their storage becomes the mask), then the pair
-    // contributions.  A pixel receives at most one contribution of each kind and the reference adds them in the order
-    // pair(p,p+x), pair(p,p+y), pair(p-x,p), pair(p-y,p): four sweeps over the link's pairs, one kind each (receiver = p0
-    // when alpha > 0, p1 otherwise; the contribution is alpha * (colour[p1] - colour[p0])).
-    if (warp < take) {
-        float* ot = reinterpret_cast<float*>(sm.ids + warp * EHB_IDS_WORDS);
-        const unsigned long long* cv = sm.cov + warp * 36;
-        for (int i = lane; i < ow * EHB_MW; i += 32) {
-            const int qy = i / EHB_MW, qx = i - qy * EHB_MW;
-            ot[i] = (qx < ow && ((cv[hlo + qy] >> (hlo + qx)) & 1ull)) ? 1.f : 0.f;
+    EHB_STAT_T(tD);
+    const int lane = c.lane, warp = c.warp, hlo = 1;
+    // colour = coverage as floats (the window's ids are dead: their storage becomes the mask): the warps take rows,
+    // lane = column (+ columns 32 .. 35 by the first lanes)
+    for (int s = 0; s < take; s++) {
+        float* om = reinterpret_cast<float*>(sm.ids[s]);
+        for (int qy = warp; qy < OW; qy += EHB_TWARPS) {
+            const unsigned long long cw = sm.cov[s][hlo + qy] >> hlo;
+            om[qy * EHB_MW + lane] = ((cw >> lane) & 1ull) ? 1.f : 0.f;
+            if (lane < EHB_MW - 32) om[qy * EHB_MW + 32 + lane] = (32 + lane < OW && ((cw >> 32) >> lane) & 1ull) ? 1.f : 0.f;
         }
-        const int pb = sm.slot[warp].pairBase, pn = max(0, min(sm.slot[warp].nPairs, c.cap - pb));
+    }
+    __syncthreads();
+    // the pair contributions.  A pixel receives at most one contribution of each kind and the reference adds them in the
+    // order pair(p,p+x), pair(p,p+y), pair(p-x,p), pair(p-y,p): four sweeps over the link's pairs, one kind each
+    // (receiver = p0 when alpha > 0, p1 otherwise; the contribution is alpha * (colour[p1] - colour[p0])).
+    if (warp < take) {
+        float* ot = reinterpret_cast<float*>(sm.ids[warp]);
+        const int pb = sm.slot[warp].pairBase, pn = max(0, min(sm.slot[warp].nPairs, nPairsRound - pb));
 #pragma unroll 1
         for (int kind = 0; kind < 4; kind++) {
             __syncwarp();
             for (int i = pb + lane; i < pb + pn; i += 32) {
-                const uint32_t pk = sm.pk[i];
-                const float al = sm.alpha[i];
+                const uint32_t pk = pr.pk[i];
+                const float al = pr.alpha[i];
                 const int d = (pk >> 11) & 1;
                 const bool pos = al > 0.f;
                 if (al == 0.f || d != (kind & 1) || pos != (kind < 2)) continue;
@@ -319,18 +337,25 @@ __device__ __forceinline__ void ehb_tile_masks(const EhbTileCtx& c, int take, bo
                 const int ridx = pos ? idx : idx + (d ? EHB_RS : 1);
                 const int ry = ridx / EHB_RS, rxw = ridx - ry * EHB_RS;
                 const int qy = ry - hlo, qx = rxw - hlo;
-                if (qy < 0 || qx < 0 || qy >= ow || qx >= ow) continue;
+                if (qy < 0 || qx < 0 || qy >= OW || qx >= OW) continue;
                 const float delta = side ? 1.f : -1.f;   // colour[p1] - colour[p0]: p1 is the covered one when side = 1
                 ot[qy * EHB_MW + qx] += al * delta;
             }
         }
     }
     __syncthreads();
-    // running sum in link order (rb_solver.py:68): S = m_first, then S = S + m_l
-    for (int i = c.tid; i < ow * EHB_MW; i += EHB_TTHREADS) {
+    EHB_STAT_ADD(8, clock64() - tD);
+}
+
+// Tiles with several rounds: running sum of the link masks in link order (rb_solver.py:68): S = m_first, then S = S + m_l.
+// (A tile with one round sums its masks in E.)
+template <int OW>
+__device__ __forceinline__ void ehb_tile_accum(EhbTileSm& sm, const EhbTileCtx& c, int take, bool first)
+{
+    for (int i = c.tid; i < OW * EHB_MW; i += EHB_TTHREADS) {
         float s = first ? 0.f : sm.S[i];
         for (int k = 0; k < take; k++) {
-            const float m = reinterpret_cast<const float*>(sm.ids + k * EHB_IDS_WORDS)[i];
+            const float m = reinterpret_cast<const float*>(sm.ids[k])[i];
             s = (first && k == 0) ? m : s + m;
         }
         sm.S[i] = s;
@@ -338,11 +363,12 @@ __device__ __forceinline__ void ehb_tile_masks(const EhbTileCtx& c, int take, bo
 }
 
 // F: backward of the resident pairs (sm.S holds g = dL/dsum of the out region).
-__device__ __forceinline__ void ehb_tile_backward(const EhbRobot& rb, const EhbParams& p, const EhbTileCtx& c, int take, int nPairsRound)
+__device__ __forceinline__ void ehb_tile_backward(const EhbRobot& rb, const EhbParams& p, EhbTileSm& sm, const EhbTileCtx& c,
+                                                  const EhbPairs& pr, int take, int nPairsRound)
 {
-    const EhbTileSmem& sm = c.sm;
+    EHB_STAT_T(tF);
     const int tid = c.tid, lane = c.lane, hlo = 1;
-    if (tid < EHB_RL * 12) sm.gacc[tid] = 0.0;
+    if (tid < EHB_RL * 12) (&sm.gacc[0][0])[tid] = 0.0;
     __syncthreads();                                     // ... and g / the pair weights are complete
     for (int i0 = 0; i0 < nPairsRound; i0 += EHB_TTHREADS) {
         const int i = i0 + tid;
@@ -351,8 +377,8 @@ __device__ __forceinline__ void ehb_tile_backward(const EhbRobot& rb, const EhbP
         for (int k = 0; k < 12; k++) acc[k] = 0.0;
         int key = -1;
         if (i < nPairsRound) {
-            const uint32_t pk = sm.pk[i];
-            const float al = sm.alpha[i];
+            const uint32_t pk = pr.pk[i];
+            const float al = pr.alpha[i];
             if ((pk & (1u << 12)) && al != 0.f) {        // owned (p0 inside the tile's interior) with a non-zero weight
                 const int idx = pk & 2047, d = (pk >> 11) & 1, side = (pk >> 13) & 1, di = (pk >> 14) & 3;
                 const int ridx = al > 0.f ? idx : idx + (d ? EHB_RS : 1);
@@ -360,13 +386,13 @@ __device__ __forceinline__ void ehb_tile_backward(const EhbRobot& rb, const EhbP
                 const float g = sm.S[(ry - hlo) * EHB_MW + (rxw - hlo)];
                 const float dd = g * (side ? 1.f : -1.f);   // g * (c1 - c0)
                 if (dd != 0.f) {
-                    const int s = sm.pslot[i];
+                    const int s = pr.pslot[i];
                     const int l = sm.slot[s].link;
                     const int ly = idx / EHB_RS, lx = idx - ly * EHB_RS;
                     const EhbLink& lk = rb.link[l];
                     int vi1, vi2;
                     float g1[3], g2[3];
-                    ehb_aa_pair_grad(lk, p.vclip + (size_t)c.item * p.Vtot + rb.voff[l], (int)sm.ptri[i], side, di, al, dd, c.rx0 + lx,
+                    ehb_aa_pair_grad(lk, p.vclip + (size_t)c.item * p.Vtot + rb.voff[l], (int)pr.ptri[i], side, di, al, dd, c.rx0 + lx,
                                      c.ry0 + ly, d, p.H, p.W, &vi1, &vi2, g1, g2);
                     const float4 va = __ldg(lk.verts + vi1), vb = __ldg(lk.verts + vi2);
                     const double ha[4] = {(double)va.x, (double)va.y, (double)va.z, 1.0};
@@ -397,149 +423,230 @@ __device__ __forceinline__ void ehb_tile_backward(const EhbRobot& rb, const EhbP
 #pragma unroll
             for (int k = 0; k < 12; k++) {
                 const double v = ehb_warp_sum(mine ? acc[k] : 0.0);
-                if (lane == 0 && v != 0.0) atomicAdd(sm.gacc + k0 * 12 + k, v);
+                if (lane == 0 && v != 0.0) atomicAdd(&sm.gacc[k0][k], v);
             }
         }
     }
     __syncthreads();
     if (tid < take * 12 && p.gmvp) {
         const int s = tid / 12, k = tid - s * 12;
-        const double v = sm.gacc[tid];
+        const double v = sm.gacc[s][k];
         // rows x (0), y (1), w (3) of d loss / d mvp; the z row carries no gradient
         if (v != 0.0) atomicAdd(p.gmvp + ((size_t)c.item * p.L + sm.slot[s].link) * 16 + (k < 8 ? k : k + 4), v);
     }
+    EHB_STAT_ADD(10, clock64() - tF);
 }
 
-__global__ void __launch_bounds__(EHB_TTHREADS) ehb_k_tiles(const __grid_constant__ EhbRobot rb,
-                                                            const __grid_constant__ EhbParams p, int cap)
+// MODE: 0 = fused / antialiased forward (needs the masks), 1 = operator backward (g comes from the caller).
+// REFKIND: 0 none, 1 f32, 2 u8, 3 registered bits.  BWD: the backward follows the forward in the same pass.
+template <int MODE, int REFKIND, bool BWD>
+__global__ void __launch_bounds__(EHB_TTHREADS, 7) ehb_k_tiles(const __grid_constant__ EhbRobot rb,
+                                                               const __grid_constant__ EhbParams p)
 {
     ehb_pdl_enter();
-    extern __shared__ unsigned char ehb_dsm[];
+    __shared__ EhbTileSm sm;
+    constexpr bool NEEDAA = MODE == 0;
+    constexpr int OW = EHB_T + ((NEEDAA && BWD) ? 1 : 0);   // out region whose S is needed (33 when g is needed on it)
+    constexpr bool OEXT = NEEDAA && BWD;
     EhbTileCtx c;
-    c.sm = ehb_tile_smem(ehb_dsm, cap);
-    c.cap = cap;
     c.tid = threadIdx.x; c.lane = c.tid & 31; c.warp = c.tid >> 5;
-    const EhbTileSmem& sm = c.sm;
     const int tid = c.tid, lane = c.lane, warp = c.warp;
     const int H = p.H, W = p.W;
-    const bool fused = p.mode == EHB_MODE_FUSED;
-    c.needAA = fused || p.mode == EHB_MODE_AA_FWD;
-    const bool doBwd = (fused && p.do_bwd) || p.mode == EHB_MODE_AA_BWD;
-    const int oext = (fused && p.do_bwd) ? 1 : 0;
-    c.ow = EHB_T + oext;                                 // out region whose S is needed
-    const int ow = c.ow;
-    const int refKind = !fused ? 0 : (p.refBits ? 3 : (p.ref ? 1 : (p.ref_u8 ? 2 : 0)));
     const unsigned nHeavy = p.ctr->nTiles, nEntries = nHeavy + p.ctr->nLight;
     const uint32_t linkMask = p.L >= 32 ? 0xFFFFFFFFu : ((1u << p.L) - 1u);
-    const bool tma = p.masks != nullptr && p.useTma;
+    const bool tma = NEEDAA && p.masks != nullptr && p.useTma;
+    float* stage = reinterpret_cast<float*>(sm.ids[0]);
     bool storePending = false;                           // thread 0: a TMA store may still be reading the staging tile
+    if (tid == 0) sm.slab = -1;
 
     for (unsigned e = blockIdx.x; e < nEntries; e += gridDim.x) {
+        EHB_STAT_T(tTile);
         const uint32_t wid = ehb_list_at(p, e, nHeavy);
         c.item = (int)(wid / (uint32_t)p.ntiles); c.tile = (int)(wid - (uint32_t)c.item * (uint32_t)p.ntiles);
-        c.x0 = (c.tile % p.ntx) * EHB_T; c.y0 = (c.tile / p.ntx) * EHB_T;
+        const int tyy = c.tile / p.ntx;
+        c.x0 = (c.tile - tyy * p.ntx) * EHB_T; c.y0 = tyy * EHB_T;
         c.rx0 = c.x0 - 1; c.ry0 = c.y0 - 1;              // window = tile + 1 low / 2 high halo pixels (35 x 35), all modes
-        c.bits = p.touch[wid] & linkMask;
-        c.nl = __popc(c.bits);
-        const int item = c.item, x0 = c.x0, y0 = c.y0, nl = c.nl;
+        const int item = c.item, x0 = c.x0, y0 = c.y0;
         const size_t ibase = (size_t)item * H * W;
-        // ---- reference values of this thread's out-region pixels: issued now, consumed in E -------------------------
-        // pixel k of a thread: i = tid + k * 256 over the 33 x 33 out region (row-major), 5 per thread at most
-        float rf[5];
+        __syncthreads();                                 // the previous tile is done with shared memory
+        if (tid == 0 && storePending) { ehb_bulk_wait_read(); storePending = false; }
+        // one round trip fetches everything that depends only on the tile: its link bits, the item's depth planes, the
+        // reference bits of its out region and its reference count
+        if (tid == 0) {
+            sm.bits = p.touch[wid] & linkMask;
+            sm.refCnt = REFKIND == 3 ? __ldg(p.refCnt + (size_t)item * p.ntiles + c.tile) : 0u;
+        }
+        if (tid < p.L) sm.planes[tid] = p.plane[(size_t)item * p.L + tid];
+        if (REFKIND == 3 && tid >= 32 && tid < 32 + 2 * EHB_MROWS) {
+            const int k = tid - 32, qy = k >> 1, wx = (x0 >> 5) + (k & 1), py = y0 + qy;
+            sm.rbits[qy][k & 1] = (py < H && wx < p.ntx) ? __ldg(p.refBits + ((size_t)item * H + py) * p.ntx + wx) : 0u;
+        }
+        if (MODE == 1) {                                 // g = dL/dmask comes from the caller
+            for (int qy = warp; qy < EHB_MROWS; qy += EHB_TWARPS) {
+                const int py = y0 + qy;
 #pragma unroll
-        for (int k = 0; k < 5; k++) {
-            rf[k] = 0.f;
-            const int i = tid + k * EHB_TTHREADS;
-            if (refKind && i < EHB_MROWS * EHB_MROWS) {
-                const int qy = i / EHB_MROWS, qx = i - qy * EHB_MROWS;
-                const int px = x0 + qx, py = y0 + qy;
-                if (px < W && py < H && qy < ow && qx < ow) {
-                    if (refKind == 3) {
-                        const uint32_t wbits = __ldg(p.refBits + ((size_t)item * H + py) * p.ntx + (px >> 5));
-                        rf[k] = ((wbits >> (px & 31)) & 1u) ? 1.f : 0.f;
-                    } else {
-                        const size_t o = ibase + (size_t)(H - 1 - py) * W + px;
-                        rf[k] = refKind == 1 ? __ldg(p.ref + o) : (__ldg(p.ref_u8 + o) ? 1.f : 0.f);
-                    }
+                for (int part = 0; part < 2; part++) {
+                    const int qx = part ? EHB_T : lane, px = x0 + qx;
+                    if (part && lane != 0) break;
+                    sm.S[qy * EHB_MW + qx] = (px < W && py < H) ? __ldg(p.dy + ibase + (size_t)(H - 1 - py) * W + px) : 0.f;
                 }
             }
         }
-        __syncthreads();                                 // the previous tile is done with S
-        if (p.mode == EHB_MODE_AA_BWD) {                 // g = dL/dmask comes from the caller
-            for (int i = tid; i < EHB_MROWS * EHB_MROWS; i += EHB_TTHREADS) {
-                const int qy = i / EHB_MROWS, qx = i - qy * EHB_MROWS;
-                const int px = x0 + qx, py = y0 + qy;
-                sm.S[qy * EHB_MW + qx] = (px < W && py < H) ? __ldg(p.dy + ibase + (size_t)(H - 1 - py) * W + px) : 0.f;
+        __syncthreads();
+        c.bits = sm.bits;
+        c.nl = __popc(c.bits);
+        const int nl = c.nl;
+        EHB_STAT_ADD(0, 1); EHB_STAT_ADD(1, nl); EHB_STAT_ADD(2, nl == 0);
+        // ---- a listed tile that no triangle reaches: a zero tile (registered reference: its loss is part of refTotal) ------
+        if (nl == 0 && (REFKIND == 0 || REFKIND == 3)) {
+            if (NEEDAA && p.masks) {
+                if (tma) {
+                    for (int i = tid; i < EHB_T * EHB_T / 4; i += EHB_TTHREADS) reinterpret_cast<float4*>(stage)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    ehb_fence_proxy_async();
+                    __syncthreads();
+                    if (tid == 0) {
+                        const int row0 = H - EHB_T - y0;
+                        ehb_tma_store_3d(row0 < 0 ? &p.tmMaskTop : &p.tmMask, stage, x0, max(row0, 0), item);
+                        ehb_bulk_commit();
+                        storePending = true;
+                    }
+                } else {
+                    for (int i = tid; i < EHB_T * EHB_T; i += EHB_TTHREADS) {
+                        const int px = x0 + (i & 31), py = y0 + (i >> 5);
+                        if (px < W && py < H) p.masks[ibase + (size_t)(H - 1 - py) * W + px] = 0.f;
+                    }
+                }
             }
+            EHB_STAT_ADD(11, clock64() - tTile);
+            continue;
         }
         // ---- rounds over the tile's links (one round for the tiles of a robot arm) -------------------------------------
         int lNext = 0, rounds = 0, take = 0, nPairsRound = 0;
-        bool first = true;
+        EhbPairs pr;
+        pr.alpha = sm.alpha; pr.ptri = sm.ptri; pr.pk = sm.pk; pr.pslot = sm.pslot;
         while (lNext < nl) {
-            ehb_tile_round(rb, p, c, lNext, take, nPairsRound);
-            if (c.needAA) ehb_tile_masks(c, take, first);
-            else ehb_tile_backward(rb, p, c, take, nPairsRound);          // operator backward: g is already there
-            lNext += take; first = false; rounds++;
+            ehb_tile_round<NEEDAA, OW>(rb, p, sm, c, lNext, take, nPairsRound, pr);
+            if (NEEDAA) {
+                ehb_tile_masks<OW>(p, sm, c, pr, take, nPairsRound, rounds == 0);
+                if (rounds > 0 || lNext + take < nl) ehb_tile_accum<OW>(sm, c, take, rounds == 0);   // several rounds: running sum
+            } else {
+                ehb_tile_backward(rb, p, sm, c, pr, take, nPairsRound);          // operator backward: g is already there
+            }
+            lNext += take; rounds++;
         }
-        if (!c.needAA) continue;
+        EHB_STAT_ADD(4, rounds > 1);
+        if (!NEEDAA) { EHB_STAT_ADD(11, clock64() - tTile); continue; }
         // ================================ E: compose, loss, dL/dsum ================================
+        // warp w takes the rows qy = w, w + 4, ...; lane = column.  With one round the link masks are summed here, in link
+        // order (rb_solver.py:68); with several the running sum is in S.
         __syncthreads();
-        if (tid == 0 && storePending) { ehb_bulk_wait_read(); storePending = false; }
-        __syncthreads();
+        EHB_STAT_T(tE);
+        const int nSum = rounds == 1 ? take : 0;
         double lacc = 0.0;
-#pragma unroll
-        for (int k = 0; k < 5; k++) {
-            const int i = tid + k * EHB_TTHREADS;
-            if (i >= EHB_MROWS * EHB_MROWS) continue;
-            const int qy = i / EHB_MROWS, qx = i - qy * EHB_MROWS;
-            if (qy >= ow || qx >= ow) continue;
+        auto pixel = [&](int qy, int qx, uint32_t refBit, bool interior) {
             const int px = x0 + qx, py = y0 + qy;
-            const bool inImg = px < W && py < H;
-            const float s = nl > 0 ? sm.S[qy * EHB_MW + qx] : 0.f;
+            const bool inImg = py < H && px < W;
+            float s = 0.f;
+            if (nSum > 0) {
+                s = reinterpret_cast<const float*>(sm.ids[0])[qy * EHB_MW + qx];
+                for (int k = 1; k < nSum; k++) s = s + reinterpret_cast<const float*>(sm.ids[k])[qy * EHB_MW + qx];
+            } else if (nl > 0) s = sm.S[qy * EHB_MW + qx];
             const float Sv = (p.clamp && s > 1.f) ? 1.f : s;
             float gv = 0.f;
-            if (refKind && inImg) {
-                const float diff = Sv - rf[k];
-                if (qx < EHB_T && qy < EHB_T) lacc += (double)(diff * diff);
+            if (REFKIND && inImg) {
+                float rf;
+                if (REFKIND == 3) rf = refBit ? 1.f : 0.f;
+                else {
+                    const size_t o = ibase + (size_t)(H - 1 - py) * W + px;
+                    rf = REFKIND == 1 ? __ldg(p.ref + o) : (__ldg(p.ref_u8 + o) ? 1.f : 0.f);
+                }
+                const float diff = Sv - rf;
+                if (interior) lacc += (double)(diff * diff);
                 gv = (!p.clamp || s <= 1.f) ? (2.f * diff) * p.invB : 0.f;
             }
-            if (qx < EHB_T && qy < EHB_T && p.masks) {
-                if (tma) sm.stage[(EHB_T - 1 - qy) * EHB_T + qx] = Sv;          // image rows run downwards
-                else if (inImg) p.masks[ibase + (size_t)(H - 1 - py) * W + px] = Sv;
+            if (OEXT) sm.S[qy * EHB_MW + qx] = gv;
+            return Sv;
+        };
+        float keep[(EHB_T + EHB_TWARPS - 1) / EHB_TWARPS];   // this lane's composed values of the interior rows
+#pragma unroll
+        for (int j = 0; j < (OW + EHB_TWARPS - 1) / EHB_TWARPS; j++) {
+            const int qy = warp + j * EHB_TWARPS;
+            if (qy < OW) {
+                const float Sv = pixel(qy, lane, REFKIND == 3 ? (sm.rbits[qy][0] >> lane) & 1u : 0u, qy < EHB_T);
+                if (j < (EHB_T + EHB_TWARPS - 1) / EHB_TWARPS) keep[j] = Sv;
             }
-            if (oext) sm.S[qy * EHB_MW + qx] = gv;      // (a thread rewrites only the pixels it has just read)
         }
-        if (refKind && p.loss) {
+        if (OEXT && warp == EHB_TWARPS - 1) {            // column 32 of the out region (33 pixels): g only
+            pixel(lane, EHB_T, REFKIND == 3 ? sm.rbits[lane][1] & 1u : 0u, false);
+            if (lane == 0) pixel(EHB_T, EHB_T, REFKIND == 3 ? sm.rbits[EHB_T][1] & 1u : 0u, false);
+        }
+        if (REFKIND && p.loss) {
             lacc = ehb_warp_sum(lacc);
             if (lane == 0) sm.lsum[warp] = lacc;
         }
-        if (tma) ehb_fence_proxy_async();
+        if (p.masks) {
+            // (the staging tile aliases window 0, whose mask every warp is still summing: write it after a barrier)
+            if (tma) __syncthreads();
+#pragma unroll
+            for (int j = 0; j < (EHB_T + EHB_TWARPS - 1) / EHB_TWARPS; j++) {
+                const int qy = warp + j * EHB_TWARPS, py = y0 + qy;
+                if (qy < EHB_T && py < H) {
+                    if (tma) stage[(H - 1 - py - max(H - EHB_T - y0, 0)) * EHB_T + lane] = keep[j];          // image rows run downwards
+                    else if (x0 + lane < W) p.masks[ibase + (size_t)(H - 1 - py) * W + x0 + lane] = keep[j];
+                }
+            }
+            if (tma) ehb_fence_proxy_async();
+        }
         __syncthreads();
         if (tid == 0) {
             if (tma) {
-                // the tile's image rows: H - 32 - y0 .. H - 1 - y0 (negative start for the top row of tiles: clipped)
-                ehb_tma_store_3d(&p.tmMask, sm.stage, x0, H - EHB_T - y0, item);
+                // the tile's image rows: H - 32 - y0 .. H - 1 - y0; the top row of tiles of an image whose height is not a
+                // multiple of 32 starts at image row 0 and uses the shorter box
+                const int row0 = H - EHB_T - y0;
+                ehb_tma_store_3d(row0 < 0 ? &p.tmMaskTop : &p.tmMask, stage, x0, max(row0, 0), item);
                 ehb_bulk_commit();
                 storePending = true;
             }
-            if (refKind && p.loss) {
+            if (REFKIND && p.loss) {
                 double t = 0.0;
                 for (int w = 0; w < EHB_TWARPS; w++) t += sm.lsum[w];
-                if (refKind == 3) t -= (double)__ldg(p.refCnt + (size_t)item * p.ntiles + c.tile);   // loss[item] starts at sum(ref)
+                if (REFKIND == 3) t -= (double)sm.refCnt;   // loss[item] starts at sum(ref)
                 if (t != 0.0) atomicAdd(&p.loss[item], t);
             }
         }
-        if (!doBwd || nl == 0) continue;
+        EHB_STAT_ADD(9, clock64() - tE);
+        if (!BWD || nl == 0) { EHB_STAT_ADD(11, clock64() - tTile); continue; }
         if (rounds == 1) {
-            ehb_tile_backward(rb, p, c, take, nPairsRound);          // the pairs of the forward are still resident
+            ehb_tile_backward(rb, p, sm, c, pr, take, nPairsRound);          // the pairs of the forward are still resident
         } else {
+            // g is known now: rebuild each round's pairs for the backward.  (The staging tile aliases window 0: the store
+            // must have read it before the windows are loaded again.)
+            if (tid == 0 && storePending) { ehb_bulk_wait_read(); storePending = false; }
             lNext = 0;
-            while (lNext < nl) {                                      // g is known now: rebuild each round's pairs for the backward
-                ehb_tile_round(rb, p, c, lNext, take, nPairsRound);
-                ehb_tile_backward(rb, p, c, take, nPairsRound);
+            while (lNext < nl) {
+                ehb_tile_round<NEEDAA, OW>(rb, p, sm, c, lNext, take, nPairsRound, pr);
+                ehb_tile_backward(rb, p, sm, c, pr, take, nPairsRound);
                 lNext += take;
             }
         }
+        EHB_STAT_ADD(11, clock64() - tTile);
     }
     if (tid == 0 && storePending) ehb_bulk_wait_read();
+}
+
+// the instantiation of a pass
+typedef void (*EhbTilesKernel)(const EhbRobot, const EhbParams);
+inline EhbTilesKernel ehb_tiles_kernel(int mode, int refKind, bool bwd)
+{
+    if (mode == EHB_MODE_AA_BWD) return ehb_k_tiles<1, 0, true>;
+    if (mode != EHB_MODE_FUSED) return ehb_k_tiles<0, 0, false>;
+    switch (refKind * 2 + (bwd ? 1 : 0)) {
+    case 0: case 1: return ehb_k_tiles<0, 0, false>;
+    case 2: return ehb_k_tiles<0, 1, false>;
+    case 3: return ehb_k_tiles<0, 1, true>;
+    case 4: return ehb_k_tiles<0, 2, false>;
+    case 5: return ehb_k_tiles<0, 2, true>;
+    case 6: return ehb_k_tiles<0, 3, false>;
+    default: return ehb_k_tiles<0, 3, true>;
+    }
 }
