@@ -2,25 +2,27 @@
 //
 // The reference antialiases every link on its own, sums the per-link masks and clamps (rb_solver.py:62-68), and its
 // backward scatters one gradient per silhouette pixel pair (dr.antialias).  Here one small CTA (4 warps)
-// owns one listed 32x32 tile and keeps everything of it in shared memory, so that no intermediate (per-link mask,
-// gradient window, pair list) ever goes to L2 / HBM and the whole stage is a single launch with every tile of the pass
-// resident at once (7 CTAs per SM):
-//   A  windows   35x35 window of every link's depth plane that reaches into the tile -> triangle ids in shared memory
-//                (all threads load, every load of a batch in flight at once), row coverage masks by ballot
-//   B  pairs     silhouette pixel pairs by XOR of neighbouring coverage masks (one warp per link, lane = row) -> ONE pair
-//                list for the tile
-//   C  weights   blend weight of every pair (ehb_aa_pair), all threads stride over the tile's list
-//   D  masks     per link: coverage as floats + the four contribution kinds in the reference's order
-//   E  compose   S = min(sum of the link masks in link order, 1) -> staging tile -> ONE TMA tensor store (UTMASTG);
-//                (S - ref)^2 -> loss; g = dL/dsum of the out region stays in shared memory
+// owns one listed 32x32 tile and keeps everything of it in shared memory (20 KB), so that no intermediate (per-link
+// mask, gradient window, pair list) ever goes to L2 / HBM and the whole stage is a single launch with every tile of the
+// pass resident at once:
+//   A  coverage  35x35 window of every link's depth plane that reaches into the tile: a warp loads nine rows at a time
+//                (lane = column), the coverage bits of a row come straight from the loaded values by ballot; nothing but
+//                36 64-bit row masks per link is kept
+//   B  pairs     silhouette pixel pairs by XOR of neighbouring row masks (a warp per link, lane = row) -> ONE pair list
+//                for the tile
+//   C  weights   all threads stride over the tile's list: triangle of the covered pixel (depth plane, L1 / L2 hit), blend
+//                weight (ehb_aa_pair)
+//   D  masks     link by link through ONE mask buffer: coverage as floats + the four contribution kinds in the reference's
+//                order, added to the running sum S in link order
+//   E  compose   S = min(sum, 1) -> staging tile -> ONE TMA tensor store (UTMASTG); (S - ref)^2 -> loss; g = dL/dsum of the
+//                out region stays in shared memory
 //   F  backward  every owned pair with a non-zero weight: analytic gradient of its two edge vertices
 //                (ehb_aa_pair_grad), contracted with [x y z 1] on the fly (fp64), reduced per link by shuffles and
 //                shared-memory accumulators, 12 fp64 atomics per (tile, link) into d loss / d mvp
 // Listed tiles that no triangle reaches (a link's bounding box overlaps them, nothing more) are a zero tile: one TMA store.
-// Links are processed in rounds of at most EHB_RL (their windows' storage); a round's pairs live in shared memory
-// (EHB_CAPS) or, for the rare window with more, in a slab of the context's pair pool in global memory.  A tile that needs
-// several rounds runs A-D per round for the forward and A-C again per round for the backward (g is only known once every
-// link has been composed).  Tiles of a robot arm need one round.
+// A round handles up to EHB_RL = 8 links of a tile; its pairs live in shared memory (EHB_CAPS) or, for the rare tile with
+// more, in a slab of the context's pair pool in global memory.  A tile with more links runs A-D per round for the forward
+// and A-C again per round for the backward (g is only known once every link has been composed).
 #pragma once
 #include "ehb_kernels.cuh"
 
@@ -28,19 +30,16 @@
 #define EHB_MW 36                        // row pitch (floats) of a link mask / the S / g window
 #define EHB_MSZ (EHB_MROWS * EHB_MW)
 #ifndef EHB_RL
-#define EHB_RL 3                         // links whose windows are resident at a time
+#define EHB_RL 8                         // links of a tile per round
 #endif
 #define EHB_TTHREADS 128
 #define EHB_TWARPS (EHB_TTHREADS / 32)
-#define EHB_IDS_WORDS (EHB_NP + 3)       // ids of one window (35 x 35); the same storage later holds the link's mask
 #ifndef EHB_CAPS
 #define EHB_CAPS 512                     // pairs of a round that fit shared memory
 #endif
 #define EHB_CAPG 2432                    // pairs of a slab in global memory (>= the 2380 pairs one window can have)
 #define EHB_SLAB_BYTES (EHB_CAPG * 12)   // alpha f32 | tri u32 | pk u16 | slot u8 (+ 1 pad)
-static_assert(EHB_IDS_WORDS >= EHB_MSZ, "the mask of a link reuses its window's storage");
-static_assert(EHB_IDS_WORDS * 4 >= EHB_T * EHB_T * 4, "the staging tile of the TMA store reuses the first window's storage");
-static_assert(EHB_RL <= EHB_TWARPS, "one warp per resident link in the per-link phases");
+static_assert(EHB_MSZ * 4 >= EHB_T * EHB_T * 4, "the staging tile of the TMA store reuses the mask buffer");
 
 __device__ __forceinline__ unsigned long long ehb_bits(int lo, int hi)   // bits lo..hi (inclusive), empty if lo > hi
 {
@@ -62,9 +61,9 @@ struct EhbSlot {                         // one resident link of the tile
 };
 
 struct __align__(128) EhbTileSm {
-    uint32_t ids[EHB_RL][EHB_IDS_WORDS];         // [0] doubles as the 32 x 32 staging tile of the TMA store (128-byte aligned)
+    float mbuf[EHB_MSZ];                         // antialiased mask of one link; doubles as the 32 x 32 staging tile of the TMA store
     float S[EHB_MSZ];                            // running sum of the link masks, then g = dL/dsum
-    unsigned long long cov[EHB_RL][36];
+    unsigned long long cov[EHB_RL][36];          // row coverage masks of the round's windows (rows 0..34, [35] = 0)
     float alpha[EHB_CAPS];
     uint32_t ptri[EHB_CAPS];
     unsigned short pk[EHB_CAPS];                 // idx (11) | d << 11 | own << 12 | side << 13 | di << 14
@@ -101,6 +100,31 @@ struct EhbTileCtx {
     uint32_t bits;
 };
 
+// hm / vm / om of window row r of one slot: silhouette pairs to the right (hm) and upwards (vm) that are wanted, and the
+// columns whose pairs this tile owns (om)
+template <bool NEEDAA, int OW>
+__device__ __forceinline__ void ehb_row_pairs(const unsigned long long* cv, int r, int py, int H, unsigned long long inX,
+                                              unsigned long long inX1, unsigned long long& hm, unsigned long long& vm,
+                                              unsigned long long& om)
+{
+    const int hlo = 1;
+    hm = vm = om = 0ull;
+    if (r >= EHB_RS) return;
+    const unsigned long long cm = cv[r], cu = cv[r + 1];
+    // pairs wanted: forward = those touching a pixel of the out region; otherwise only owned ones
+    unsigned long long wantH, wantV;
+    if (NEEDAA) {
+        wantH = (r >= hlo && r <= hlo + OW - 1) ? ehb_bits(hlo - 1, hlo + OW - 1) : 0ull;
+        wantV = (r >= hlo - 1 && r <= hlo + OW - 1) ? ehb_bits(hlo, hlo + OW - 1) : 0ull;
+    } else {
+        wantH = wantV = (r >= hlo && r <= hlo + EHB_T - 1) ? ehb_bits(hlo, hlo + EHB_T - 1) : 0ull;
+    }
+    const bool rowIn = py >= 0 && py < H;
+    if (rowIn) hm = (cm ^ (cm >> 1)) & inX1 & wantH & ehb_bits(0, EHB_RS - 2);
+    if (rowIn && py < H - 1 && r < EHB_RS - 1) vm = (cm ^ cu) & inX & wantV;
+    om = (r >= hlo && r <= hlo + EHB_T - 1) ? ehb_bits(hlo, hlo + EHB_T - 1) : 0ull;
+}
+
 // A + B + C for the links [lNext, lNext + take) of the tile (in link order).  On return `take` is the number of links
 // whose pairs fit one list (>= 1), `pr` the list (shared memory or a global slab) with the `nPairsRound` pairs and weights.
 template <bool NEEDAA, int OW>
@@ -108,121 +132,75 @@ __device__ __forceinline__ void ehb_tile_round(const EhbRobot& rb, const EhbPara
                                                int& take, int& nPairsRound, EhbPairs& pr)
 {
     const int tid = c.tid, lane = c.lane, warp = c.warp;
-    const int H = p.H, W = p.W, hlo = 1, ow = OW;
+    const int H = p.H, W = p.W;
     __syncthreads();                                     // the previous round / tile is done with the arrays
     EHB_STAT_T(tA);
     take = min(EHB_RL, c.nl - lNext);
-    // ================================ A: windows, coverage ================================
-    // One window row per warp and step, lane = column (columns 32..34 by lanes 0..2), four rows of loads in flight per
-    // warp; the coverage bits of a row come straight from the loaded values by ballot.
-    int lk[EHB_RL];                                  // links of the round's slots (link order)
+    // ================================ A: coverage of the windows ================================
+    // Link by link: warp w loads the window rows w, w + 4, ... (nine of them) -- lane = column for columns 0..31, and the
+    // three extra columns of its rows with one more load (lane = 3 * row + column) -- all ten loads in flight at once; the
+    // coverage bits of a row come straight from the loaded values by ballot.
     {
         uint32_t b = c.bits;
         for (int q = 0; q < lNext; q++) b &= b - 1;
+        for (int s = 0; s < take; s++) {
+            const int l = __ffs(b) - 1;
+            b &= b - 1;
+            if (tid == 0) { sm.slot[s].link = l; sm.slot[s].nPairs = 0; sm.slot[s].pairBase = 0; }
+            const EhbPlane& pl = sm.planes[l];
+            const int cx = c.rx0 - pl.x0 + lane;
+            const int cyb = c.ry0 - pl.y0 + warp;
+            constexpr int NR = (EHB_RS + EHB_TWARPS - 1) / EHB_TWARPS;   // rows per warp (9)
+            unsigned long long v[NR], vx = EHB_EMPTY;
 #pragma unroll
-        for (int q = 0; q < EHB_RL; q++) { lk[q] = b ? __ffs(b) - 1 : 0; b &= b - 1; }
-    }
-    {
-        const int nrows = take * EHB_RS;
-        for (int base = warp; base < nrows; base += 4 * EHB_TWARPS) {
-            unsigned long long v0[4], v1[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int sr = base + j * EHB_TWARPS;
-                v0[j] = EHB_EMPTY; v1[j] = EHB_EMPTY;
-                if (sr < nrows) {
-                    const int s = sr / EHB_RS, r = sr - s * EHB_RS;
-                    int l = lk[0];
-#pragma unroll
-                    for (int q = 1; q < EHB_RL; q++) l = s == q ? lk[q] : l;
-                    const EhbPlane& pl = sm.planes[l];
-                    const int cy = c.ry0 + r - pl.y0, cx = c.rx0 - pl.x0 + lane;
-                    if ((unsigned)cy < (unsigned)pl.h) {
-                        const unsigned long long* row = p.pool + pl.off + (long long)cy * pl.w;
-                        if ((unsigned)cx < (unsigned)pl.w) v0[j] = row[cx];
-                        if (lane < EHB_RS - 32 && (unsigned)(cx + 32) < (unsigned)pl.w) v1[j] = row[cx + 32];
-                    }
-                }
+            for (int j = 0; j < NR; j++) {
+                const int r = warp + j * EHB_TWARPS, cy = cyb + j * EHB_TWARPS;
+                v[j] = EHB_EMPTY;
+                if (r < EHB_RS && (unsigned)cy < (unsigned)pl.h && (unsigned)cx < (unsigned)pl.w)
+                    v[j] = p.pool[pl.off + (long long)cy * pl.w + cx];
             }
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int sr = base + j * EHB_TWARPS;
-                if (sr < nrows) {                    // (warp-uniform)
-                    const int s = sr / EHB_RS, r = sr - s * EHB_RS;
-                    uint32_t* dst = &sm.ids[s][r * EHB_RS];
-                    dst[lane] = (uint32_t)v0[j];     // low word = triangle id (all ones: empty)
-                    if (lane < EHB_RS - 32) dst[32 + lane] = (uint32_t)v1[j];
-                    const unsigned b0 = __ballot_sync(0xffffffffu, v0[j] != EHB_EMPTY);
-                    const unsigned b1 = __ballot_sync(0xffffffffu, lane < EHB_RS - 32 && v1[j] != EHB_EMPTY);
-                    if (lane == 0) sm.cov[s][r] = (unsigned long long)b0 | ((unsigned long long)b1 << 32);
-                }
+            {
+                const int j = lane / 3, k = lane - 3 * j;            // extra columns 32..34 of this warp's row j
+                const int r = warp + j * EHB_TWARPS, cy = cyb + j * EHB_TWARPS, cxx = c.rx0 - pl.x0 + 32 + k;
+                if (j < NR && r < EHB_RS && (unsigned)cy < (unsigned)pl.h && (unsigned)cxx < (unsigned)pl.w)
+                    vx = p.pool[pl.off + (long long)cy * pl.w + cxx];
             }
+            const unsigned bx = __ballot_sync(0xffffffffu, vx != EHB_EMPTY);
+#pragma unroll
+            for (int j = 0; j < NR; j++) {
+                const int r = warp + j * EHB_TWARPS;
+                const unsigned b0 = __ballot_sync(0xffffffffu, v[j] != EHB_EMPTY);
+                if (lane == 0 && r < EHB_RS) sm.cov[s][r] = (unsigned long long)b0 | ((unsigned long long)((bx >> (3 * j)) & 7u) << 32);
+            }
+            if (tid == 0) sm.cov[s][EHB_RS] = 0ull;
         }
-        if (tid < take) sm.cov[tid][EHB_RS] = 0ull;
     }
     __syncthreads();
     EHB_STAT_T(tB);
     EHB_STAT_ADD(5, tB - tA);
-    // ================================ B: silhouette pairs, one warp per slot, lane = window row ================================
+    // ================================ B: silhouette pairs, a warp per slot, lane = window row ================================
     // columns whose pixel is inside the image, and for which the right neighbour is too
     const unsigned long long inX = ehb_bits(-c.rx0, W - 1 - c.rx0), inX1 = ehb_bits(-c.rx0, W - 2 - c.rx0);
-    unsigned long long hm[2] = {0ull, 0ull}, vm[2] = {0ull, 0ull}, om[2] = {0ull, 0ull};
-    int o0 = 0, o1 = 0;
-    if (warp < take) {
-        const unsigned long long* cv = sm.cov[warp];
-        int cnt[2];
+    for (int s = warp; s < take; s += EHB_TWARPS) {       // count
+        int cnt = 0;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            const int r = lane + 32 * h;
-            if (r < EHB_RS) {
-                const int py = c.ry0 + r;
-                const unsigned long long cm = cv[r], cu = cv[r + 1];
-                // pairs wanted: forward = those touching a pixel of the out region; otherwise only owned ones
-                unsigned long long wantH, wantV;
-                if (NEEDAA) {
-                    wantH = (r >= hlo && r <= hlo + ow - 1) ? ehb_bits(hlo - 1, hlo + ow - 1) : 0ull;
-                    wantV = (r >= hlo - 1 && r <= hlo + ow - 1) ? ehb_bits(hlo, hlo + ow - 1) : 0ull;
-                } else {
-                    wantH = wantV = (r >= hlo && r <= hlo + EHB_T - 1) ? ehb_bits(hlo, hlo + EHB_T - 1) : 0ull;
-                }
-                const bool rowIn = py >= 0 && py < H;
-                if (rowIn) hm[h] = (cm ^ (cm >> 1)) & inX1 & wantH & ehb_bits(0, EHB_RS - 2);
-                if (rowIn && py < H - 1 && r < EHB_RS - 1) vm[h] = (cm ^ cu) & inX & wantV;
-                om[h] = (r >= hlo && r <= hlo + EHB_T - 1) ? ehb_bits(hlo, hlo + EHB_T - 1) : 0ull;
-            }
-            cnt[h] = __popcll(hm[h]) + __popcll(vm[h]);
+            unsigned long long hm, vm, om;
+            ehb_row_pairs<NEEDAA, OW>(sm.cov[s], lane + 32 * h, c.ry0 + lane + 32 * h, H, inX, inX1, hm, vm, om);
+            cnt += __popcll(hm) + __popcll(vm);
         }
-        int inc = cnt[0];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
-        }
-        const int tot0 = __shfl_sync(0xffffffffu, inc, 31);
-        int inc1 = cnt[1];
-#pragma unroll
-        for (int o = 1; o < 4; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, inc1, o);
-            if (lane >= o) inc1 += v;
-        }
-        const int tot1 = __shfl_sync(0xffffffffu, inc1, 3);
-        o0 = inc - cnt[0]; o1 = tot0 + inc1 - cnt[1];
-        if (lane == 0) {
-            int l = lk[0];
-#pragma unroll
-            for (int q = 1; q < EHB_RL; q++) l = warp == q ? lk[q] : l;
-            sm.slot[warp].nPairs = tot0 + tot1; sm.slot[warp].link = l;
-        }
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) sm.slot[s].nPairs = cnt;
     }
     __syncthreads();
     // fit the round into one pair list: the longest prefix of slots whose pairs fit a slab (at least one slot: a window
     // has at most 2380 pairs); every thread computes the same answer from the slots' counts
     nPairsRound = 0;
-    int fit = 0, myBase = 0;
+    int fit = 0;
     for (int s = 0; s < take; s++) {
         const int n = sm.slot[s].nPairs;
         if (s > 0 && nPairsRound + n > EHB_CAPG) break;
-        if (s == warp) myBase = nPairsRound;
         nPairsRound += n; fit = s + 1;
     }
     nPairsRound = min(nPairsRound, EHB_CAPG);
@@ -248,28 +226,39 @@ __device__ __forceinline__ void ehb_tile_round(const EhbRobot& rb, const EhbPara
         }
     }
     const int capNow = pr.alpha == sm.alpha ? EHB_CAPS : EHB_CAPG;
-    if (warp < take) {
-        if (lane == 0) sm.slot[warp].pairBase = myBase;
+    for (int s = warp; s < take; s += EHB_TWARPS) {       // write: the rows' pairs in row order, horizontal before vertical
+        int base = 0;
+        for (int q = 0; q < s; q++) base += sm.slot[q].nPairs;
+        if (lane == 0) sm.slot[s].pairBase = base;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            int o = myBase + (h ? o1 : o0);
-            unsigned long long hxm = hm[h], vym = vm[h];
+            unsigned long long hm, vm, om;
+            ehb_row_pairs<NEEDAA, OW>(sm.cov[s], lane + 32 * h, c.ry0 + lane + 32 * h, H, inX, inX1, hm, vm, om);
+            const int n = __popcll(hm) + __popcll(vm);
+            int inc = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            int o = base + inc - n;
+            base += __shfl_sync(0xffffffffu, inc, 31);
             const uint32_t rowBase = (uint32_t)(lane + 32 * h) * EHB_RS;
-            while (hxm) {
-                const int b = __ffsll((long long)hxm) - 1;
-                hxm &= hxm - 1;
+            while (hm) {
+                const int bb = __ffsll((long long)hm) - 1;
+                hm &= hm - 1;
                 if (o < capNow) {
-                    pr.pk[o] = (unsigned short)((rowBase + b) | (((om[h] >> b) & 1ull) ? (1u << 12) : 0u));
-                    pr.pslot[o] = (unsigned char)warp;
+                    pr.pk[o] = (unsigned short)((rowBase + bb) | (((om >> bb) & 1ull) ? (1u << 12) : 0u));
+                    pr.pslot[o] = (unsigned char)s;
                 }
                 o++;
             }
-            while (vym) {
-                const int b = __ffsll((long long)vym) - 1;
-                vym &= vym - 1;
+            while (vm) {
+                const int bb = __ffsll((long long)vm) - 1;
+                vm &= vm - 1;
                 if (o < capNow) {
-                    pr.pk[o] = (unsigned short)((rowBase + b) | (1u << 11) | (((om[h] >> b) & 1ull) ? (1u << 12) : 0u));
-                    pr.pslot[o] = (unsigned char)warp;
+                    pr.pk[o] = (unsigned short)((rowBase + bb) | (1u << 11) | (((om >> bb) & 1ull) ? (1u << 12) : 0u));
+                    pr.pslot[o] = (unsigned char)s;
                 }
                 o++;
             }
@@ -286,9 +275,12 @@ __device__ __forceinline__ void ehb_tile_round(const EhbRobot& rb, const EhbPara
         const int l = sm.slot[s].link;
         const int idx = pk & 2047, d = (pk >> 11) & 1;
         const int ly = idx / EHB_RS, lx = idx - ly * EHB_RS;
-        const uint32_t ka = sm.ids[s][idx], kb = sm.ids[s][idx + (d ? EHB_RS : 1)];
-        const int side = ka != 0xFFFFFFFFu ? 0 : 1;
-        const uint32_t t = side ? kb : ka;
+        // the covered pixel of the pair shows the triangle: p0 when it is covered, else p1 (the plane was read by this SM
+        // in A: an L1 / L2 hit)
+        const int side = ((sm.cov[s][ly] >> lx) & 1ull) ? 0 : 1;
+        const int wx = lx + (side ? 1 - d : 0), wy = ly + (side ? d : 0);
+        const EhbPlane& pl = sm.planes[l];
+        const uint32_t t = (uint32_t)p.pool[pl.off + (long long)(c.ry0 + wy - pl.y0) * pl.w + (c.rx0 + wx - pl.x0)];
         int di;
         const float al = ehb_aa_pair(rb.link[l], p.vclip + (size_t)c.item * p.Vtot + rb.voff[l], (int)t, side, c.rx0 + lx, c.ry0 + ly, d,
                                      H, W, &di);
@@ -300,34 +292,40 @@ __device__ __forceinline__ void ehb_tile_round(const EhbRobot& rb, const EhbPara
     EHB_STAT_ADD(7, clock64() - tC);
 }
 
-// D: the antialiased masks of the round's links (out region).
+// D: link by link (link order, rb_solver.py:68): the link's antialiased mask of the out region in the mask buffer, then
+// the running sum S = m_first, S = S + m_l.
 template <int OW>
 __device__ __forceinline__ void ehb_tile_masks(const EhbParams& p, EhbTileSm& sm, const EhbTileCtx& c, const EhbPairs& pr, int take,
                                                int nPairsRound, bool first)
 {
     EHB_STAT_T(tD);
-    const int lane = c.lane, warp = c.warp, hlo = 1;
-    // colour = coverage as floats (the window's ids are dead: their storage becomes the mask): the warps take rows,
-    // lane = column (+ columns 32 .. 35 by the first lanes)
-    for (int s = 0; s < take; s++) {
-        float* om = reinterpret_cast<float*>(sm.ids[s]);
+    const int tid = c.tid, lane = c.lane, warp = c.warp, hlo = 1;
+    for (int s = 0; s < take; s++, first = false) {
+        const int pb = sm.slot[s].pairBase, pn = max(0, min(sm.slot[s].nPairs, nPairsRound - pb));
+        // colour = coverage as floats: the warps take rows, lane = column (+ columns 32 .. 35 by the first lanes); a link
+        // without pairs in this window goes straight into the sum
+        float* dst = pn > 0 ? sm.mbuf : sm.S;
         for (int qy = warp; qy < OW; qy += EHB_TWARPS) {
             const unsigned long long cw = sm.cov[s][hlo + qy] >> hlo;
-            om[qy * EHB_MW + lane] = ((cw >> lane) & 1ull) ? 1.f : 0.f;
-            if (lane < EHB_MW - 32) om[qy * EHB_MW + 32 + lane] = (32 + lane < OW && ((cw >> 32) >> lane) & 1ull) ? 1.f : 0.f;
+            const float a0 = ((cw >> lane) & 1ull) ? 1.f : 0.f;
+            const float a1 = (lane < EHB_MW - 32 && 32 + lane < OW && (((cw >> 32) >> lane) & 1ull)) ? 1.f : 0.f;
+            float* row = dst + qy * EHB_MW;
+            if (pn > 0 || first) {
+                row[lane] = a0;
+                if (lane < EHB_MW - 32) row[32 + lane] = a1;
+            } else {
+                row[lane] = row[lane] + a0;
+                if (lane < EHB_MW - 32) row[32 + lane] = row[32 + lane] + a1;
+            }
         }
-    }
-    __syncthreads();
-    // the pair contributions.  A pixel receives at most one contribution of each kind and the reference adds them in the
-    // order pair(p,p+x), pair(p,p+y), pair(p-x,p), pair(p-y,p): four sweeps over the link's pairs, one kind each
-    // (receiver = p0 when alpha > 0, p1 otherwise; the contribution is alpha * (colour[p1] - colour[p0])).
-    if (warp < take) {
-        float* ot = reinterpret_cast<float*>(sm.ids[warp]);
-        const int pb = sm.slot[warp].pairBase, pn = max(0, min(sm.slot[warp].nPairs, nPairsRound - pb));
+        if (pn == 0) { __syncthreads(); continue; }
+        // the pair contributions.  A pixel receives at most one contribution of each kind and the reference adds them in
+        // the order pair(p,p+x), pair(p,p+y), pair(p-x,p), pair(p-y,p): four sweeps over the link's pairs, one kind each
+        // (receiver = p0 when alpha > 0, p1 otherwise; the contribution is alpha * (colour[p1] - colour[p0])).
 #pragma unroll 1
         for (int kind = 0; kind < 4; kind++) {
-            __syncwarp();
-            for (int i = pb + lane; i < pb + pn; i += 32) {
+            __syncthreads();
+            for (int i = pb + tid; i < pb + pn; i += EHB_TTHREADS) {
                 const uint32_t pk = pr.pk[i];
                 const float al = pr.alpha[i];
                 const int d = (pk >> 11) & 1;
@@ -339,27 +337,14 @@ __device__ __forceinline__ void ehb_tile_masks(const EhbParams& p, EhbTileSm& sm
                 const int qy = ry - hlo, qx = rxw - hlo;
                 if (qy < 0 || qx < 0 || qy >= OW || qx >= OW) continue;
                 const float delta = side ? 1.f : -1.f;   // colour[p1] - colour[p0]: p1 is the covered one when side = 1
-                ot[qy * EHB_MW + qx] += al * delta;
+                sm.mbuf[qy * EHB_MW + qx] += al * delta;
             }
         }
+        __syncthreads();
+        for (int i = tid; i < OW * EHB_MW; i += EHB_TTHREADS) sm.S[i] = first ? sm.mbuf[i] : sm.S[i] + sm.mbuf[i];
+        __syncthreads();
     }
-    __syncthreads();
     EHB_STAT_ADD(8, clock64() - tD);
-}
-
-// Tiles with several rounds: running sum of the link masks in link order (rb_solver.py:68): S = m_first, then S = S + m_l.
-// (A tile with one round sums its masks in E.)
-template <int OW>
-__device__ __forceinline__ void ehb_tile_accum(EhbTileSm& sm, const EhbTileCtx& c, int take, bool first)
-{
-    for (int i = c.tid; i < OW * EHB_MW; i += EHB_TTHREADS) {
-        float s = first ? 0.f : sm.S[i];
-        for (int k = 0; k < take; k++) {
-            const float m = reinterpret_cast<const float*>(sm.ids[k])[i];
-            s = (first && k == 0) ? m : s + m;
-        }
-        sm.S[i] = s;
-    }
 }
 
 // F: backward of the resident pairs (sm.S holds g = dL/dsum of the out region).
@@ -455,7 +440,7 @@ __global__ void __launch_bounds__(EHB_TTHREADS, 7) ehb_k_tiles(const __grid_cons
     const unsigned nHeavy = p.ctr->nTiles, nEntries = nHeavy + p.ctr->nLight;
     const uint32_t linkMask = p.L >= 32 ? 0xFFFFFFFFu : ((1u << p.L) - 1u);
     const bool tma = NEEDAA && p.masks != nullptr && p.useTma;
-    float* stage = reinterpret_cast<float*>(sm.ids[0]);
+    float* stage = sm.mbuf;
     bool storePending = false;                           // thread 0: a TMA store may still be reading the staging tile
     if (tid == 0) sm.slab = -1;
 
@@ -528,7 +513,6 @@ __global__ void __launch_bounds__(EHB_TTHREADS, 7) ehb_k_tiles(const __grid_cons
             ehb_tile_round<NEEDAA, OW>(rb, p, sm, c, lNext, take, nPairsRound, pr);
             if (NEEDAA) {
                 ehb_tile_masks<OW>(p, sm, c, pr, take, nPairsRound, rounds == 0);
-                if (rounds > 0 || lNext + take < nl) ehb_tile_accum<OW>(sm, c, take, rounds == 0);   // several rounds: running sum
             } else {
                 ehb_tile_backward(rb, p, sm, c, pr, take, nPairsRound);          // operator backward: g is already there
             }
@@ -537,20 +521,14 @@ __global__ void __launch_bounds__(EHB_TTHREADS, 7) ehb_k_tiles(const __grid_cons
         EHB_STAT_ADD(4, rounds > 1);
         if (!NEEDAA) { EHB_STAT_ADD(11, clock64() - tTile); continue; }
         // ================================ E: compose, loss, dL/dsum ================================
-        // warp w takes the rows qy = w, w + 4, ...; lane = column.  With one round the link masks are summed here, in link
-        // order (rb_solver.py:68); with several the running sum is in S.
+        // warp w takes the rows qy = w, w + 4, ...; lane = column; S holds the sum of the link masks
         __syncthreads();
         EHB_STAT_T(tE);
-        const int nSum = rounds == 1 ? take : 0;
         double lacc = 0.0;
         auto pixel = [&](int qy, int qx, uint32_t refBit, bool interior) {
             const int px = x0 + qx, py = y0 + qy;
             const bool inImg = py < H && px < W;
-            float s = 0.f;
-            if (nSum > 0) {
-                s = reinterpret_cast<const float*>(sm.ids[0])[qy * EHB_MW + qx];
-                for (int k = 1; k < nSum; k++) s = s + reinterpret_cast<const float*>(sm.ids[k])[qy * EHB_MW + qx];
-            } else if (nl > 0) s = sm.S[qy * EHB_MW + qx];
+            const float s = nl > 0 ? sm.S[qy * EHB_MW + qx] : 0.f;
             const float Sv = (p.clamp && s > 1.f) ? 1.f : s;
             float gv = 0.f;
             if (REFKIND && inImg) {
@@ -585,8 +563,7 @@ __global__ void __launch_bounds__(EHB_TTHREADS, 7) ehb_k_tiles(const __grid_cons
             if (lane == 0) sm.lsum[warp] = lacc;
         }
         if (p.masks) {
-            // (the staging tile aliases window 0, whose mask every warp is still summing: write it after a barrier)
-            if (tma) __syncthreads();
+            // (the staging tile aliases the mask buffer, which is dead: S is complete)
 #pragma unroll
             for (int j = 0; j < (EHB_T + EHB_TWARPS - 1) / EHB_TWARPS; j++) {
                 const int qy = warp + j * EHB_TWARPS, py = y0 + qy;
@@ -619,9 +596,7 @@ __global__ void __launch_bounds__(EHB_TTHREADS, 7) ehb_k_tiles(const __grid_cons
         if (rounds == 1) {
             ehb_tile_backward(rb, p, sm, c, pr, take, nPairsRound);          // the pairs of the forward are still resident
         } else {
-            // g is known now: rebuild each round's pairs for the backward.  (The staging tile aliases window 0: the store
-            // must have read it before the windows are loaded again.)
-            if (tid == 0 && storePending) { ehb_bulk_wait_read(); storePending = false; }
+            // g is known now: rebuild each round's pairs for the backward
             lNext = 0;
             while (lNext < nl) {
                 ehb_tile_round<NEEDAA, OW>(rb, p, sm, c, lNext, take, nPairsRound, pr);
