@@ -508,32 +508,12 @@ __device__ __forceinline__ void ehb_rec_store_soa(uint32_t* b, int t, const EhbR
     for (int k = 0; k < 12; k++) b[(20 + k) * 32 + t] = __float_as_uint(rc.clip[k]);
 }
 
-// Primitive assembly of one triangle from the pre-transformed vertices -> record.  Same tests, in the same order,
-// as the oracle's eho_rasterize.  Returns the number of rows of its clipped bbox (0: nothing to draw).
-__device__ __forceinline__ int ehb_make_record(const EhbRobot& rb, const EhbParams& p, int item, int l, int f, EhbRec& rc)
+// Setup of one triangle given by its snapped vertices (1/16 px) -> record.  c0..c2 = the ORIGINAL clip-space vertices
+// (the depth of a sample is shaded from them, also for the sub-triangles of a clipped triangle).  Same tests, in the same
+// order, as the oracle's raster_snapped.  Returns the number of rows of the clipped bbox (0: nothing to draw).
+__device__ __forceinline__ int ehb_setup_record(const EhbParams& p, const EhbPlane& pl, int x0, int y0, int x1, int y1, int x2, int y2,
+                                                const float4& c0, const float4& c1, const float4& c2, uint32_t id, EhbRec& rc)
 {
-    const int g = rb.foff[l] + f;
-    const EhbLink& lk = rb.link[l];
-    const int4 id = __ldg(lk.faces + f);
-    const EhbPlane pl = p.plane[(size_t)item * p.Lp + (p.Lp == 1 ? 0 : l)];   // depends on the link only: issued with the face
-    if ((unsigned)id.x >= (unsigned)lk.V || (unsigned)id.y >= (unsigned)lk.V || (unsigned)id.z >= (unsigned)lk.V) return 0;
-    const size_t vb = (size_t)item * p.Vtot + rb.voff[l];
-    // all seven loads that depend on the face go out together (one L2 round trip), before the first test consumes one
-    const float4 c0 = p.vclip[vb + id.x], c1 = p.vclip[vb + id.y], c2 = p.vclip[vb + id.z];
-    const int2 s0 = p.vsnap[vb + id.x], s1 = p.vsnap[vb + id.y], s2 = p.vsnap[vb + id.z];
-    if ((c0.w < c0.x && c1.w < c1.x && c2.w < c2.x) || (c0.w < -c0.x && c1.w < -c1.x && c2.w < -c2.x) ||
-        (c0.w < c0.y && c1.w < c1.y && c2.w < c2.y) || (c0.w < -c0.y && c1.w < -c1.y && c2.w < -c2.y) ||
-        (c0.w < c0.z && c1.w < c1.z && c2.w < c2.z) || (c0.w < -c0.z && c1.w < -c1.z && c2.w < -c2.z))
-        return 0;
-    const int G = 1 << 28;
-    if (s0.x == INT_MIN || s1.x == INT_MIN || s2.x == INT_MIN ||   // a vertex outside the depth range: needs the clipper
-        s0.x > G || s0.x < -G || s0.y > G || s0.y < -G || s1.x > G || s1.x < -G || s1.y > G || s1.y < -G ||
-        s2.x > G || s2.x < -G || s2.y > G || s2.y < -G) {
-        atomicAdd(&p.ctr->nNeedClip, 1ull);
-        atomicOr(&p.ctr->flags, 2u);
-        return 0;
-    }
-    int x0 = s0.x, y0 = s0.y, x1 = s1.x, y1 = s1.y, x2 = s2.x, y2 = s2.y;
     const long long area = (long long)(x1 - x0) * (y2 - y0) - (long long)(y1 - y0) * (x2 - x0);
     if (area == 0) return 0;
     if (area < 0) { int t = x1; x1 = x2; x2 = t; t = y1; y1 = y2; y2 = t; }
@@ -552,11 +532,151 @@ __device__ __forceinline__ int ehb_make_record(const EhbRobot& rb, const EhbPara
     rc.x0 = pxlo; rc.y0 = pylo; rc.w = pxhi - pxlo + 1; rc.h = pyhi - pylo + 1;
     rc.base = pl.off - (long long)pl.y0 * pl.w - pl.x0;
     rc.pw = pl.w;
-    rc.id = p.Lp == 1 ? (uint32_t)g : (uint32_t)f;
+    rc.id = id;
     rc.clip[0] = c0.x; rc.clip[1] = c0.y; rc.clip[2] = c0.z; rc.clip[3] = c0.w;
     rc.clip[4] = c1.x; rc.clip[5] = c1.y; rc.clip[6] = c1.z; rc.clip[7] = c1.w;
     rc.clip[8] = c2.x; rc.clip[9] = c2.y; rc.clip[10] = c2.z; rc.clip[11] = c2.w;
     return rc.h;
+}
+
+// Primitive assembly of one triangle from the pre-transformed vertices -> record.  Same tests, in the same order, as the
+// oracle's eho_rasterize.  Returns the number of rows of its clipped bbox (0: nothing to draw here); needClip: the
+// triangle survives the trivial rejection but leaves the depth range or the fixed-point guard band -- it goes through the
+// clipper (ehb_emit_clipped).
+__device__ __forceinline__ int ehb_make_record(const EhbRobot& rb, const EhbParams& p, int item, int l, int f, EhbRec& rc, bool& needClip)
+{
+    needClip = false;
+    const int g = rb.foff[l] + f;
+    const EhbLink& lk = rb.link[l];
+    const int4 id = __ldg(lk.faces + f);
+    const EhbPlane pl = p.plane[(size_t)item * p.Lp + (p.Lp == 1 ? 0 : l)];   // depends on the link only: issued with the face
+    if ((unsigned)id.x >= (unsigned)lk.V || (unsigned)id.y >= (unsigned)lk.V || (unsigned)id.z >= (unsigned)lk.V) return 0;
+    const size_t vb = (size_t)item * p.Vtot + rb.voff[l];
+    // all seven loads that depend on the face go out together (one L2 round trip), before the first test consumes one
+    const float4 c0 = p.vclip[vb + id.x], c1 = p.vclip[vb + id.y], c2 = p.vclip[vb + id.z];
+    const int2 s0 = p.vsnap[vb + id.x], s1 = p.vsnap[vb + id.y], s2 = p.vsnap[vb + id.z];
+    if ((c0.w < c0.x && c1.w < c1.x && c2.w < c2.x) || (c0.w < -c0.x && c1.w < -c1.x && c2.w < -c2.x) ||
+        (c0.w < c0.y && c1.w < c1.y && c2.w < c2.y) || (c0.w < -c0.y && c1.w < -c1.y && c2.w < -c2.y) ||
+        (c0.w < c0.z && c1.w < c1.z && c2.w < c2.z) || (c0.w < -c0.z && c1.w < -c1.z && c2.w < -c2.z))
+        return 0;
+    const int G = 1 << 28;
+    if (s0.x == INT_MIN || s1.x == INT_MIN || s2.x == INT_MIN ||   // a vertex outside the depth range
+        s0.x > G || s0.x < -G || s0.y > G || s0.y < -G || s1.x > G || s1.x < -G || s1.y > G || s1.y < -G ||
+        s2.x > G || s2.x < -G || s2.y > G || s2.y < -G) {
+        needClip = true;
+        return 0;
+    }
+    return ehb_setup_record(p, pl, s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, c0, c1, c2, p.Lp == 1 ? (uint32_t)g : (uint32_t)f, rc);
+}
+
+// Sutherland-Hodgman clip of a triangle against the six planes of the view frustum in clip space (x >= -w, x <= w,
+// y >= -w, y <= w, z >= -w, z <= w), fp32, one rounding per operation; an intersection is always computed from the
+// INSIDE vertex towards the outside one, so that neighbours are cut at bit-identical points (oracle: clip_triangle).
+__device__ __forceinline__ float ehb_clip_dist(const float* v, int plane)
+{
+    const float c = plane < 2 ? v[0] : (plane < 4 ? v[1] : v[2]);
+    return (plane & 1) ? v[3] - c : v[3] + c;
+}
+__device__ __noinline__ int ehb_clip_triangle(const float4 c0, const float4 c1, const float4 c2, float (*out)[4])
+{
+    float a[9][4], b[9][4];
+    int n = 3;
+    a[0][0] = c0.x; a[0][1] = c0.y; a[0][2] = c0.z; a[0][3] = c0.w;
+    a[1][0] = c1.x; a[1][1] = c1.y; a[1][2] = c1.z; a[1][3] = c1.w;
+    a[2][0] = c2.x; a[2][1] = c2.y; a[2][2] = c2.z; a[2][3] = c2.w;
+    for (int plane = 0; plane < 6 && n >= 3; plane++) {
+        int m = 0;
+        for (int i = 0; i < n; i++) {
+            const float* pp = a[i];
+            const float* qq = a[(i + 1) % n];
+            const float dp = ehb_clip_dist(pp, plane), dq = ehb_clip_dist(qq, plane);
+            const bool ip = dp >= 0.f, iq = dq >= 0.f;
+            if (ip && m < 9) { for (int k = 0; k < 4; k++) b[m][k] = pp[k]; m++; }
+            if (ip != iq && m < 9) {
+                const float* in = ip ? pp : qq;
+                const float* ou = ip ? qq : pp;
+                const float din = ip ? dp : dq, dou = ip ? dq : dp;
+                const float t = din / (din - dou);
+                for (int k = 0; k < 4; k++) b[m][k] = in[k] + t * (ou[k] - in[k]);
+                m++;
+            }
+        }
+        n = m;
+        for (int i = 0; i < n; i++)
+            for (int k = 0; k < 4; k++) a[i][k] = b[i][k];
+    }
+    if (n < 3) return 0;
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < 4; k++) out[i][k] = a[i][k];
+    return n;
+}
+
+// One lane draws one record by testing every sample of its bbox: only when the deferred-work queues are full.
+__device__ __noinline__ void ehb_draw_serial(const EhbParams& p, const EhbRec& rc)
+{
+    const float p0[4] = {rc.clip[0], rc.clip[1], rc.clip[2], rc.clip[3]}, p1[4] = {rc.clip[4], rc.clip[5], rc.clip[6], rc.clip[7]},
+                p2[4] = {rc.clip[8], rc.clip[9], rc.clip[10], rc.clip[11]};
+    for (int dy = 0; dy < rc.h; dy++)
+        for (int dx = 0; dx < rc.w; dx++) {
+            bool in = true;
+            for (int k = 0; k < 3; k++)
+                in = in && (rc.E[k] + 16ll * rc.ex[k] * (long long)dy - 16ll * rc.ey[k] * (long long)dx) >= 0;
+            if (!in) continue;
+            const int px = rc.x0 + dx, py = rc.y0 + dy;
+            const float zw = ehb_shade_zw(p0, p1, p2, p.xs * (float)px + p.xo, p.ys * (float)py + p.yo);
+            atomicMin(p.pool + (rc.base + (long long)py * rc.pw + px), ((unsigned long long)ehb_order_key(zw) << 32) | rc.id);
+        }
+}
+
+// A triangle that needs the clipper (one lane, rare): clipped polygon -> fan of sub-triangles -> each one a deferred
+// record whose bbox is cut into bounded units for k_raster_big (a triangle that crosses the near plane can cover the
+// whole screen), with the link's touch bits of the tiles it reaches.
+__device__ __noinline__ void ehb_emit_clipped(const EhbRobot& rb, const EhbParams& p, int item, int l, int f, int qi)
+{
+    atomicAdd(&p.ctr->nNeedClip, 1ull);
+    atomicOr(&p.ctr->flags, 2u);
+    const EhbLink& lk = rb.link[l];
+    const int4 id = __ldg(lk.faces + f);
+    const EhbPlane pl = p.plane[(size_t)item * p.Lp + (p.Lp == 1 ? 0 : l)];
+    const size_t vb = (size_t)item * p.Vtot + rb.voff[l];
+    const float4 c0 = p.vclip[vb + id.x], c1 = p.vclip[vb + id.y], c2 = p.vclip[vb + id.z];
+    float poly[9][4];
+    const int n = ehb_clip_triangle(c0, c1, c2, poly);
+    int sx[9], sy[9];
+    for (int i = 0; i < n; i++) {
+        if (!(poly[i][3] > 0.f)) return;
+        const float r = 1.0f / poly[i][3];
+        sx[i] = ehb_rni_sat(poly[i][0] * r * (float)(p.W * 8));
+        sy[i] = ehb_rni_sat(poly[i][1] * r * (float)(p.H * 8));
+    }
+    EhbCounters::Q& myq = p.ctr->q[qi];
+    const uint32_t tid = p.Lp == 1 ? (uint32_t)(rb.foff[l] + f) : (uint32_t)f;
+    for (int i = 1; i + 1 < n; i++) {
+        EhbRec rc;
+        if (ehb_setup_record(p, pl, sx[0], sy[0], sx[i], sy[i], sx[i + 1], sy[i + 1], c0, c1, c2, tid, rc) == 0) continue;
+        if (p.touch) {
+            const int txlo = max(0, (rc.x0 - p.hhi) >> 5), txhi = min(p.ntx - 1, (rc.x0 + rc.w - 1 + p.hlo) >> 5);
+            const int tylo = max(0, (rc.y0 - p.hhi) >> 5), tyhi = min(p.nty - 1, (rc.y0 + rc.h - 1 + p.hlo) >> 5);
+            uint32_t* trow = p.touch + (size_t)item * p.ntiles;
+            for (int ty = tylo; ty <= tyhi; ty++)
+                for (int tx = txlo; tx <= txhi; tx++) atomicOr(trow + ty * p.ntx + tx, 1u << l);
+        }
+        const int nux = (rc.w + EHB_UNIT_W - 1) / EHB_UNIT_W, nuy = (rc.h + EHB_UNIT_H - 1) / EHB_UNIT_H, nu = nux * nuy;
+        const unsigned kq = atomicAdd(&myq.nBigRec, 1u), uq = atomicAdd(&myq.nUnits, (unsigned)nu);
+        const bool fits = (int)kq < p.bigCap && (int)(uq + nu) <= p.unitCap;
+        const unsigned u0 = (unsigned)qi * (unsigned)p.unitCap + uq;
+        if (fits) {
+            const unsigned k = (unsigned)qi * (unsigned)p.bigCap + kq;
+            p.bigRec[k] = rc;
+            for (int uy = 0; uy < nuy; uy++)
+                for (int ux = 0; ux < nux; ux++)
+                    p.units[u0 + uy * nux + ux] = EhbUnit{k, (unsigned short)(ux * EHB_UNIT_W), (unsigned short)(uy * EHB_UNIT_H)};
+        } else {
+            atomicOr(&p.ctr->flags, 4u);   // queues full: drawn here (slow but complete); its units are void
+            for (int u = 0; u < nu && (int)(uq + u) < p.unitCap; u++) p.units[u0 + u] = EhbUnit{0xFFFFFFFFu, 0, 0};
+            ehb_draw_serial(p, rc);
+        }
+    }
 }
 
 template <class RV>
@@ -675,7 +795,7 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
     const int link = ehb_find_link(rb.boff, rb.L, bl);    // (warp-uniform)
     const int f = (bl - rb.boff[link]) * 32 + lane;
     int rows = 0, wide = 0, touchRows = 0;
-    bool big = false;
+    bool big = false, needClip = false;
     int4 tb = make_int4(0, 0, 0, 0);   // clipped bbox of this lane's triangle (x0, y0, w, h)
     // Frustum cull of the whole batch: the 8 corners of its object-space AABB, one per lane.  When every corner is in
     // front of the camera and all of them lie beyond one side of the screen (two pixels of margin for snapping and
@@ -700,7 +820,7 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
     }
     if (visible && f < rb.link[link].F) {
         EhbRec rc;
-        rows = ehb_make_record(rb, p, item, link, f, rc);
+        rows = ehb_make_record(rb, p, item, link, f, rc, needClip);
         touchRows = rows;
         if (rows > 0) tb = make_int4(rc.x0, rc.y0, rc.w, rc.h);
         if (rows > 0) {
@@ -767,6 +887,8 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
             }
         }
     }
+    if (needClip) ehb_emit_clipped(rb, p, item, link, f, qi);   // (rare: one lane clips, sets up and queues its sub-triangles)
+    __syncwarp();
     if (p.touch) {
         // Tell k_tiles which (tile, link) windows the triangles reach into.  Neighbouring triangles of a warp mostly
         // fall into the same tile of the same link: lanes with equal (tile, link) elect one to issue the RED (no load,

@@ -49,7 +49,8 @@ extern "C" {
 #define EHB_FLAG_POOL_OVERFLOW 1u /* a scratch pool (depth planes, jobs, silhouette pairs) was too small: results of that
                                      launch are incomplete */
 #define EHB_FLAG_PAIR_OVERFLOW EHB_FLAG_POOL_OVERFLOW
-#define EHB_FLAG_NEEDS_CLIP 2u    /* triangles crossing the near/far plane were skipped (not supported yet) */
+#define EHB_FLAG_NEEDS_CLIP 2u    /* informational: triangles left the depth range / guard band and went through the
+                                     frustum clipper (drawn; ehb_ctx_status reports how many) */
 #define EHB_FLAG_QUEUES_FULL 4u   /* informational: the deferred-triangle queues were full, some large triangles were drawn
                                      inline (slower, results complete) */
 
@@ -87,7 +88,7 @@ EHB_API int ehb_ctx_debug_counters(ehb_ctx_t ctx, unsigned long long* out16, int
 /* Developer aid: first call allocates a device scratch buffer that debug builds may fill, later calls copy up to
  * n_words 64-bit words of it out. */
 EHB_API int ehb_ctx_debug_buffer(ehb_ctx_t ctx, unsigned long long* out, int n_words);
-/* Synchronises the device, returns and clears the sticky flags, reports triangles skipped for clipping. */
+/* Synchronises the device, returns and clears the sticky flags, reports the triangles that went through the clipper. */
 EHB_API int ehb_ctx_status(ehb_ctx_t ctx, unsigned* flags, long long* n_need_clip);
 
 /* Register a mesh once: verts_host f32[V*3], faces_host i32[F*3].  Builds the padded float4 / int4 device

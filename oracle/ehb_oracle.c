@@ -123,15 +123,109 @@ static inline float shade_zw(const float* p0, const float* p1, const float* p2, 
     return fminf(fmaxf(zw, -1.f), 1.f);
 }
 
+/* Coverage + depth of one triangle given by its SNAPPED vertices (sub-pixel units) into key[]; z/w is shaded from the
+ * three ORIGINAL clip-space vertices c0, c1, c2 (the rasterizer's shader recomputes it per pixel from the unclipped
+ * positions), id = triangle id. */
+static void raster_snapped(int64_t x0, int64_t y0, int64_t x1, int64_t y1, int64_t x2, int64_t y2, const float* c0,
+                           const float* c1, const float* c2, uint32_t id, int H, int W, int rule, uint64_t* key)
+{
+    const float xs = 2.f / (float)W, xo = 1.f / (float)W - 1.f;
+    const float ys = 2.f / (float)H, yo = 1.f / (float)H - 1.f;
+    int64_t area = (x1 - x0) * (y2 - y0) - (y1 - y0) * (x2 - x0);
+    if (area == 0) return;
+    if (area < 0) { int64_t tx = x1, ty = y1; x1 = x2; y1 = y2; x2 = tx; y2 = ty; }
+    int64_t lox = x0 < x1 ? (x0 < x2 ? x0 : x2) : (x1 < x2 ? x1 : x2);
+    int64_t hix = x0 > x1 ? (x0 > x2 ? x0 : x2) : (x1 > x2 ? x1 : x2);
+    int64_t loy = y0 < y1 ? (y0 < y2 ? y0 : y2) : (y1 < y2 ? y1 : y2);
+    int64_t hiy = y0 > y1 ? (y0 > y2 ? y0 : y2) : (y1 > y2 ? y1 : y2);
+    /* samples at 16*p + 8 - 8*W:  p >= ceil((lo + 8W - 8)/16), p <= floor((hi + 8W - 8)/16) */
+    int64_t bx = 8 * (int64_t)W - 8, by = 8 * (int64_t)H - 8;
+    int64_t pxlo = (lox + bx + 15) >> 4, pxhi = (hix + bx) >> 4;
+    int64_t pylo = (loy + by + 15) >> 4, pyhi = (hiy + by) >> 4;
+    if (pxlo < 0) pxlo = 0;
+    if (pylo < 0) pylo = 0;
+    if (pxhi > W - 1) pxhi = W - 1;
+    if (pyhi > H - 1) pyhi = H - 1;
+    if (pxlo > pxhi || pylo > pyhi) return;
+    int64_t ex[3] = {x1 - x0, x2 - x1, x0 - x2}, ey[3] = {y1 - y0, y2 - y1, y0 - y2};
+    int64_t ax[3] = {x0, x1, x2}, ay[3] = {y0, y1, y2};
+    int64_t thr[3];
+    for (int k = 0; k < 3; k++) thr[k] = edge_inclusive(ex[k], ey[k], rule) ? 0 : 1;
+    for (int64_t py = pylo; py <= pyhi; py++) {
+        int64_t sy = 16 * py - by;
+        for (int64_t px = pxlo; px <= pxhi; px++) {
+            int64_t sx = 16 * px - bx;
+            int in = 1;
+            for (int k = 0; k < 3; k++) {
+                int64_t e = ex[k] * (sy - ay[k]) - ey[k] * (sx - ax[k]);
+                if (e < thr[k]) { in = 0; break; }
+            }
+            if (!in) continue;
+            float fx = xs * (float)px + xo, fy = ys * (float)py + yo;
+            float zw = shade_zw(c0, c1, c2, fx, fy);
+            uint64_t k64 = ((uint64_t)order_key(zw) << 32) | id;
+            uint64_t* dst = key + py * W + px;
+            if (k64 < *dst) *dst = k64;
+        }
+    }
+}
+
+/* Sutherland-Hodgman clip of a triangle against the six planes of the view frustum in clip space
+ * (x >= -w, x <= w, y >= -w, y <= w, z >= -w, z <= w), fp32, one rounding per operation.  An intersection is always
+ * computed from the INSIDE vertex towards the outside one (t = d_in / (d_in - d_out), p = in + t * (out - in)), so an
+ * edge shared by two triangles is cut at bit-identical points whichever way each triangle runs through it.
+ * out[9][4]; returns the number of vertices (0 when nothing is left). */
+static float clip_dist(const float* v, int plane)
+{
+    switch (plane) {
+    case 0: return v[3] + v[0];
+    case 1: return v[3] - v[0];
+    case 2: return v[3] + v[1];
+    case 3: return v[3] - v[1];
+    case 4: return v[3] + v[2];
+    default: return v[3] - v[2];
+    }
+}
+static int clip_triangle(const float* v0, const float* v1, const float* v2, float out[9][4])
+{
+    float a[9][4], b[9][4];
+    int n = 3;
+    memcpy(a[0], v0, 16); memcpy(a[1], v1, 16); memcpy(a[2], v2, 16);
+    for (int plane = 0; plane < 6 && n >= 3; plane++) {
+        int m = 0;
+        for (int i = 0; i < n; i++) {
+            const float* p = a[i];
+            const float* q = a[(i + 1) % n];
+            float dp = clip_dist(p, plane), dq = clip_dist(q, plane);
+            int ip = dp >= 0.f, iq = dq >= 0.f;
+            if (ip && m < 9) { memcpy(b[m], p, 16); m++; }
+            if (ip != iq && m < 9) {
+                const float* in = ip ? p : q;
+                const float* ou = ip ? q : p;
+                float din = ip ? dp : dq, dou = ip ? dq : dp;
+                float t = din / (din - dou);
+                for (int k = 0; k < 4; k++) b[m][k] = in[k] + t * (ou[k] - in[k]);
+                m++;
+            }
+        }
+        n = m;
+        memcpy(a, b, sizeof a);
+    }
+    if (n < 3) return 0;
+    memcpy(out, a, sizeof a);
+    return n;
+}
+
 /* Visibility pass.  key[H*W] (GL rows, row 0 = bottom): (order_key(z/w) << 32) | tri, or ~0 when
- * empty.  Returns the number of triangles that would need near/far-plane clipping (not drawn). */
+ * empty.  A triangle that lies inside the depth range and the fixed-point guard band is snapped and drawn directly;
+ * any other one that survives the trivial frustum rejection is clipped against the view frustum first and drawn as a
+ * fan of sub-triangles with its own id and its own (unclipped) vertices for the depth -- like cudaraster's triangle
+ * setup.  Returns the number of triangles that went through the clipper. */
 EHO_API int eho_rasterize(const float* clip, int V, const int* tri, int F, int H, int W, int rule,
                           uint64_t* key)
 {
     int nclip = 0;
     const float vsx = (float)(W * 8), vsy = (float)(H * 8);
-    const float xs = 2.f / (float)W, xo = 1.f / (float)W - 1.f;
-    const float ys = 2.f / (float)H, yo = 1.f / (float)H - 1.f;
     for (long i = 0; i < (long)H * W; i++) key[i] = ~0ull;
     for (int t = 0; t < F; t++) {
         int i0 = tri[3 * t], i1 = tri[3 * t + 1], i2 = tri[3 * t + 2];
@@ -142,56 +236,36 @@ EHO_API int eho_rasterize(const float* clip, int V, const int* tri, int F, int H
             (v0[3] < v0[1] && v1[3] < v1[1] && v2[3] < v2[1]) || (v0[3] < -v0[1] && v1[3] < -v1[1] && v2[3] < -v2[1]) ||
             (v0[3] < v0[2] && v1[3] < v1[2] && v2[3] < v2[2]) || (v0[3] < -v0[2] && v1[3] < -v1[2] && v2[3] < -v2[2]))
             continue;
-        /* must be inside the depth range for the direct path */
-        if (!(v0[3] >= fabsf(v0[2]) && v1[3] >= fabsf(v1[2]) && v2[3] >= fabsf(v2[2]))) { nclip++; continue; }
-        float r0 = 1.0f / v0[3], r1 = 1.0f / v1[3], r2 = 1.0f / v2[3];
-        int64_t x0 = rni_sat(v0[0] * r0 * vsx), y0 = rni_sat(v0[1] * r0 * vsy);
-        int64_t x1 = rni_sat(v1[0] * r1 * vsx), y1 = rni_sat(v1[1] * r1 * vsy);
-        int64_t x2 = rni_sat(v2[0] * r2 * vsx), y2 = rni_sat(v2[1] * r2 * vsy);
-        /* guard band: beyond +-2^28 sub-pixel units the 64-bit edge products could overflow; such a
-         * triangle would go through the clipper in cudaraster => counted with the needs-clip ones */
-        {
+        int direct = v0[3] >= fabsf(v0[2]) && v1[3] >= fabsf(v1[2]) && v2[3] >= fabsf(v2[2]);
+        int64_t x0 = 0, y0 = 0, x1 = 0, y1 = 0, x2 = 0, y2 = 0;
+        if (direct) {
+            float r0 = 1.0f / v0[3], r1 = 1.0f / v1[3], r2 = 1.0f / v2[3];
+            x0 = rni_sat(v0[0] * r0 * vsx); y0 = rni_sat(v0[1] * r0 * vsy);
+            x1 = rni_sat(v1[0] * r1 * vsx); y1 = rni_sat(v1[1] * r1 * vsy);
+            x2 = rni_sat(v2[0] * r2 * vsx); y2 = rni_sat(v2[1] * r2 * vsy);
+            /* guard band: beyond +-2^28 sub-pixel units the 64-bit edge products could overflow: clipped instead */
             const int64_t G = (int64_t)1 << 28;
             if (x0 > G || x0 < -G || y0 > G || y0 < -G || x1 > G || x1 < -G || y1 > G || y1 < -G ||
-                x2 > G || x2 < -G || y2 > G || y2 < -G) { nclip++; continue; }
+                x2 > G || x2 < -G || y2 > G || y2 < -G) direct = 0;
         }
-        int64_t area = (x1 - x0) * (y2 - y0) - (y1 - y0) * (x2 - x0);
-        if (area == 0) continue;
-        if (area < 0) { int64_t tx = x1, ty = y1; x1 = x2; y1 = y2; x2 = tx; y2 = ty; }
-        int64_t lox = x0 < x1 ? (x0 < x2 ? x0 : x2) : (x1 < x2 ? x1 : x2);
-        int64_t hix = x0 > x1 ? (x0 > x2 ? x0 : x2) : (x1 > x2 ? x1 : x2);
-        int64_t loy = y0 < y1 ? (y0 < y2 ? y0 : y2) : (y1 < y2 ? y1 : y2);
-        int64_t hiy = y0 > y1 ? (y0 > y2 ? y0 : y2) : (y1 > y2 ? y1 : y2);
-        /* samples at 16*p + 8 - 8*W:  p >= ceil((lo + 8W - 8)/16), p <= floor((hi + 8W - 8)/16) */
-        int64_t bx = 8 * (int64_t)W - 8, by = 8 * (int64_t)H - 8;
-        int64_t pxlo = (lox + bx + 15) >> 4, pxhi = (hix + bx) >> 4;
-        int64_t pylo = (loy + by + 15) >> 4, pyhi = (hiy + by) >> 4;
-        if (pxlo < 0) pxlo = 0;
-        if (pylo < 0) pylo = 0;
-        if (pxhi > W - 1) pxhi = W - 1;
-        if (pyhi > H - 1) pyhi = H - 1;
-        if (pxlo > pxhi || pylo > pyhi) continue;
-        int64_t ex[3] = {x1 - x0, x2 - x1, x0 - x2}, ey[3] = {y1 - y0, y2 - y1, y0 - y2};
-        int64_t ax[3] = {x0, x1, x2}, ay[3] = {y0, y1, y2};
-        int64_t thr[3];
-        for (int k = 0; k < 3; k++) thr[k] = edge_inclusive(ex[k], ey[k], rule) ? 0 : 1;
-        for (int64_t py = pylo; py <= pyhi; py++) {
-            int64_t sy = 16 * py - by;
-            for (int64_t px = pxlo; px <= pxhi; px++) {
-                int64_t sx = 16 * px - bx;
-                int in = 1;
-                for (int k = 0; k < 3; k++) {
-                    int64_t e = ex[k] * (sy - ay[k]) - ey[k] * (sx - ax[k]);
-                    if (e < thr[k]) { in = 0; break; }
-                }
-                if (!in) continue;
-                float fx = xs * (float)px + xo, fy = ys * (float)py + yo;
-                float zw = shade_zw(v0, v1, v2, fx, fy);
-                uint64_t k64 = ((uint64_t)order_key(zw) << 32) | (uint32_t)t;
-                uint64_t* dst = key + py * W + px;
-                if (k64 < *dst) *dst = k64;
-            }
+        if (direct) {
+            raster_snapped(x0, y0, x1, y1, x2, y2, v0, v1, v2, (uint32_t)t, H, W, rule, key);
+            continue;
         }
+        nclip++;
+        float poly[9][4];
+        int n = clip_triangle(v0, v1, v2, poly);
+        int64_t sx[9], sy[9];
+        int ok = 1;
+        for (int i = 0; i < n; i++) {
+            if (!(poly[i][3] > 0.f)) { ok = 0; break; }
+            float r = 1.0f / poly[i][3];
+            sx[i] = rni_sat(poly[i][0] * r * vsx);
+            sy[i] = rni_sat(poly[i][1] * r * vsy);
+        }
+        if (!ok) continue;
+        for (int i = 1; i + 1 < n; i++)
+            raster_snapped(sx[0], sy[0], sx[i], sy[i], sx[i + 1], sy[i + 1], v0, v1, v2, (uint32_t)t, H, W, rule, key);
     }
     return nclip;
 }

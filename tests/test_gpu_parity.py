@@ -152,14 +152,15 @@ def test_edge_cases(gpu_ctx):
     assert not got.any()
     g_mvp, _ = gpu_ctx.render_mask_bwd(mid, to_dev(mvp_b), H, W, to_dev(np.ones((H, W), np.float32)))
     assert not g_mvp.cpu().numpy().any()
-    # (c) triangle crossing the near plane: skipped and counted on both sides
+    # (c) triangles crossing the near plane are clipped and drawn (both sides count them)
     near = np.eye(4); near[2, 3] = -1.0 + 1e-4
     mvp_n = mvp_of(K, H, W, near)
-    want, st = oracle.render_mask(q.vertices, q.faces, mvp_n, H, W, anti_aliasing=False, save=True)
     gpu_ctx.status()
-    got = gpu_ctx.render_mask_fwd(mid, to_dev(mvp_n), H, W, anti_aliasing=False).cpu().numpy().astype(bool)
-    flags, nclip = gpu_ctx.status()
-    assert np.array_equal(got, want) and nclip == st[3]
+    for aa in (False, True):
+        want, st = oracle.render_mask(q.vertices, q.faces, mvp_n, H, W, anti_aliasing=aa, save=True)
+        got = gpu_ctx.render_mask_fwd(mid, to_dev(mvp_n), H, W, anti_aliasing=aa).cpu().numpy()
+        flags, nclip = gpu_ctx.status()
+        assert np.array_equal(got.astype(want.dtype), want) and nclip == st[3] == 2 and flags & 2
     gpu_ctx.release_mesh(mid)
     # (d) empty mesh
     mid = gpu_ctx.register_mesh(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int32))
@@ -334,3 +335,46 @@ def test_windows_with_more_pairs_than_shared_memory_holds():
         assert np.allclose(loss.cpu().numpy(), want["loss_per_view"], rtol=1e-12, atol=0)
         assert rel_err(g.cpu().numpy(), want["g_mvp"]) < 1e-9
         ctx.close()
+
+
+def test_clipper_ground_plane_and_close_up_robot(gpu_ctx, xarm):
+    """Triangles that leave the depth range or the guard band go through the frustum clipper on both sides: a ground
+    plane from behind the camera to 8 m ahead (whole-screen sub-triangles through the deferred-work queue), and the arm
+    seen from so close that links cross the camera plane -- masks bit-exact, gradients as usual."""
+    H, W = 120, 160
+    K = scaled_K(H, W)
+    v = np.array([[-3, 0.4, -2], [3, 0.4, -2], [3, 0.4, 8], [-3, 0.4, 8]], np.float32)
+    f = np.array([[0, 1, 2], [0, 2, 3]], np.int32)
+    mvp = mvp_of(K, H, W, np.eye(4))
+    mid = gpu_ctx.register_mesh(v, f)
+    gpu_ctx.status()
+    for aa in (False, True):
+        want = oracle.render_mask(v, f, mvp, H, W, anti_aliasing=aa)
+        got = gpu_ctx.render_mask_fwd(mid, to_dev(mvp), H, W, anti_aliasing=aa).cpu().numpy()
+        assert want.mean() > 0.3 and np.array_equal(got.astype(want.dtype), want)
+    assert gpu_ctx.status()[1] == 4
+    gpu_ctx.release_mesh(mid)
+    # the robot, camera inside it: the camera sits 3 cm behind / 4 cm beside the origin of link 4 of the first view
+    H, W, B = 240, 320, 3
+    sc = make_scene(B, H, W, links="xarm7", seed=2)
+    R = sc["Tc_c2b"][:3, :3]
+    close = np.eye(4)
+    close[:3, :3] = R
+    close[:3, 3] = -R @ sc["link_poses"][0, 3][:3, 3].astype(np.float64) + np.array([-0.04, 0.0, 0.03])
+    packed = oracle.pack_links(sc["meshes"])
+    ref = oracle.union_binary(packed, scene_mvps(sc, H, W, close), H, W)
+    from easyhec_b200.scenes import perturb_pose
+    mvp2 = scene_mvps(sc, H, W, perturb_pose(close, np.random.RandomState(3), 0.01, 1.0))
+    want = oracle.render_views(packed, mvp2, ref.astype(np.float32), H, W)
+    assert want["n_need_clip"] >= 8 and 0.05 < (want["masks"] > 0).mean() < 0.9
+    ids = [gpu_ctx.register_mesh(m.vertices, m.faces) for m in sc["meshes"]]
+    masks, loss, g = gpu_ctx.render_views_fused(ids, to_dev(mvp2), to_dev(ref.astype(np.float32)), H, W, backward=True)
+    flags, nclip = gpu_ctx.status()
+    assert flags & 1 == 0 and nclip == want["n_need_clip"]
+    assert np.array_equal(masks.cpu().numpy(), want["masks"])
+    assert np.allclose(loss.cpu().numpy(), want["loss_per_view"], rtol=1e-12, atol=0)
+    assert rel_err(g.cpu().numpy(), want["g_mvp"]) < 1e-9
+    got_u = gpu_ctx.render_binary_batch(ids, to_dev(mvp2), H, W).cpu().numpy().astype(bool)
+    assert np.array_equal(got_u, oracle.union_binary(packed, mvp2, H, W))
+    for i in ids:
+        gpu_ctx.release_mesh(i)
