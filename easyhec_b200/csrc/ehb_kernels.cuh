@@ -887,8 +887,6 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
             }
         }
     }
-    if (needClip) ehb_emit_clipped(rb, p, item, link, f, qi);   // (rare: one lane clips, sets up and queues its sub-triangles)
-    __syncwarp();
     if (p.touch) {
         // Tell k_tiles which (tile, link) windows the triangles reach into.  Neighbouring triangles of a warp mostly
         // fall into the same tile of the same link: lanes with equal (tile, link) elect one to issue the RED (no load,
@@ -965,6 +963,11 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
                 if ((int)(u0 + i) < p.unitCap) p.units[uBase + i] = EhbUnit{0xFFFFFFFFu, 0, 0};
             draw_rows(nInline, nRowsAll);
         }
+    }
+    // (rare) triangles of this batch that left the depth range / guard band: one lane each clips, sets up and queues the
+    // sub-triangles -- at the end of the iteration, where nothing of the batch is live any more
+    if (__any_sync(0xffffffffu, needClip)) {
+        if (needClip) ehb_emit_clipped(rb, p, item, link, f, qi);
     }
     __syncwarp();   // the records of this batch are dead: the next one may overwrite them
     if (++sub == EHB_RBATCH) { sub = 0; bcur = __shfl_sync(0xffffffffu, bnext, 0); }

@@ -153,13 +153,17 @@ def test_edge_cases(gpu_ctx):
     g_mvp, _ = gpu_ctx.render_mask_bwd(mid, to_dev(mvp_b), H, W, to_dev(np.ones((H, W), np.float32)))
     assert not g_mvp.cpu().numpy().any()
     # (c) triangles crossing the near plane are clipped and drawn (both sides count them)
-    near = np.eye(4); near[2, 3] = -1.0 + 1e-4
+    a = np.deg2rad(75.0)
+    near = np.eye(4)
+    near[:3, :3] = [[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]]
+    near[:3, 3] = [0.0, 0.2, 0.5]                        # the quad now spans camera depths of about 0.5 -+ 4.8 m
     mvp_n = mvp_of(K, H, W, near)
     gpu_ctx.status()
     for aa in (False, True):
         want, st = oracle.render_mask(q.vertices, q.faces, mvp_n, H, W, anti_aliasing=aa, save=True)
         got = gpu_ctx.render_mask_fwd(mid, to_dev(mvp_n), H, W, anti_aliasing=aa).cpu().numpy()
         flags, nclip = gpu_ctx.status()
+        assert want.any() and not want.all()
         assert np.array_equal(got.astype(want.dtype), want) and nclip == st[3] == 2 and flags & 2
     gpu_ctx.release_mesh(mid)
     # (d) empty mesh
@@ -362,11 +366,11 @@ def test_clipper_ground_plane_and_close_up_robot(gpu_ctx, xarm):
     close[:3, :3] = R
     close[:3, 3] = -R @ sc["link_poses"][0, 3][:3, 3].astype(np.float64) + np.array([-0.04, 0.0, 0.03])
     packed = oracle.pack_links(sc["meshes"])
-    ref = oracle.union_binary(packed, scene_mvps(sc, H, W, close), H, W)
     from easyhec_b200.scenes import perturb_pose
-    mvp2 = scene_mvps(sc, H, W, perturb_pose(close, np.random.RandomState(3), 0.01, 1.0))
+    ref = oracle.union_binary(packed, scene_mvps(sc, H, W, perturb_pose(close, np.random.RandomState(3), 0.01, 1.0)), H, W)
+    mvp2 = scene_mvps(sc, H, W, close)
     want = oracle.render_views(packed, mvp2, ref.astype(np.float32), H, W)
-    assert want["n_need_clip"] >= 8 and 0.05 < (want["masks"] > 0).mean() < 0.9
+    assert want["n_need_clip"] >= 8 and 0.05 < (want["masks"] > 0).mean() < 0.9 and np.abs(want["g_mvp"]).max() > 0
     ids = [gpu_ctx.register_mesh(m.vertices, m.faces) for m in sc["meshes"]]
     masks, loss, g = gpu_ctx.render_views_fused(ids, to_dev(mvp2), to_dev(ref.astype(np.float32)), H, W, backward=True)
     flags, nclip = gpu_ctx.status()
