@@ -65,6 +65,10 @@ _PROTOS = {
     "ehb_variance_score": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]),
     "ehb_explore_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p]),
+    "ehb_robot_register": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.POINTER(C.c_int)]),
+    "ehb_explore_fk_mvp": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                     C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ehb_solver_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ehb_solver_step_host_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
@@ -344,6 +348,61 @@ class Context:
         score = torch.empty((Q,), dtype=torch.float64, device=self.device)
         _check(lib().ehb_explore_scores(self._h, ids, L, Q, Cn, _ptr(mvp), H, W, _ptr(score), _stream(self.device)))
         return score
+
+    # -- space exploration: forward kinematics on the device ---------------------------------------------------------------
+    def register_robot(self, kin):
+        """kin: URDFKinematics -> handle for explore_fk_mvp.  The kinematic tree goes to the device once (links in an order
+        where parents precede children; the handle keeps the map from the URDF's link order)."""
+        order, parent_of = [kin.root_link], {kin.root_link: None}
+        pending = [j for j in kin.joints]
+        while pending:
+            rest = [j for j in pending if j["parent"] not in parent_of]
+            for j in pending:
+                if j["parent"] in parent_of and j["child"] not in parent_of:
+                    parent_of[j["child"]] = j
+                    order.append(j["child"])
+            if len(rest) == len(pending):
+                break
+            pending = rest
+        idx = {n: i for i, n in enumerate(order)}
+        qi = {j["name"]: i for i, j in enumerate(kin.movable)}
+        n = len(order)
+        parent = np.full(n, -1, np.int32); jtype = np.zeros(n, np.int32); qidx = np.full(n, -1, np.int32)
+        mult = np.ones(n); offs = np.zeros(n); axis = np.zeros((n, 3)); origin = np.tile(np.eye(4), (n, 1, 1))
+        for name in order[1:]:
+            j, i = parent_of[name], idx[name]
+            parent[i] = idx[j["parent"]]
+            origin[i] = j["origin"]
+            axis[i] = j["axis"]
+            if j["type"] in ("revolute", "continuous", "prismatic"):
+                jtype[i] = 2 if j["type"] == "prismatic" else 1
+                if j["mimic"] is not None and j["mimic"][0] in qi:
+                    qidx[i], mult[i], offs[i] = qi[j["mimic"][0]], j["mimic"][1], j["mimic"][2]
+                elif j["name"] in qi:
+                    qidx[i] = qi[j["name"]]
+                else:
+                    jtype[i] = 0
+        rid = C.c_int(-1)
+        arrs = [np.ascontiguousarray(a) for a in (parent, jtype, qidx, mult, offs, axis, origin)]
+        _check(lib().ehb_robot_register(self._h, n, *[a.ctypes.data_as(C.c_void_p) for a in arrs], C.byref(rid)))
+        return {"id": rid.value, "tree_index": {name: idx[name] for name in kin.link_names if name in idx},
+                "link_names": list(kin.link_names), "dof": kin.dof}
+
+    def explore_fk_mvp(self, robot, qpos, cam_poses, K, H, W, links):
+        """qpos (Q, <= dof) float64 CUDA tensor, cam_poses (C,4,4), K (3,3), links: indices into the URDF's link order (or
+        names) -> mvp (Q, C, L, 4, 4) float32 on the device, computed by ehb_k_fk_mvp."""
+        _dev_check(qpos, torch.float64, self.device, "qpos")
+        Q, dof = qpos.shape
+        cams = np.ascontiguousarray(np.asarray(cam_poses.cpu() if isinstance(cam_poses, torch.Tensor) else cam_poses, np.float64))
+        if cams.ndim == 2:
+            cams = cams[None]
+        Kh = np.ascontiguousarray(np.asarray(K.cpu() if isinstance(K, torch.Tensor) else K, np.float32))
+        sel = np.ascontiguousarray([robot["tree_index"][robot["link_names"][l] if not isinstance(l, str) else l] for l in links], np.int32)
+        mvp = torch.empty((Q, len(cams), len(sel), 4, 4), dtype=torch.float32, device=self.device)
+        _check(lib().ehb_explore_fk_mvp(self._h, robot["id"], _ptr(qpos), dof, Q, cams.ctypes.data_as(C.c_void_p), len(cams),
+                                        Kh.ctypes.data_as(C.c_void_p), H, W, sel.ctypes.data_as(C.c_void_p), len(sel), _ptr(mvp),
+                                        _stream(self.device)))
+        return mvp
 
     def solver_step_host(self, mesh_ids, mvp_host, ref_dev, H, W, loss_host, g_mvp_host):
         """Host-buffer form: mvp_host (B,L,4,4) f32 pinned CPU tensor; loss_host (B,), g_mvp_host (B,L,4,4) f64

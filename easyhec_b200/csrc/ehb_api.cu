@@ -100,6 +100,18 @@ struct Scratch {
     }
 };
 
+// Kinematic tree of a robot (ehb_robot_register): links in an order where a parent precedes its children.
+#define EHB_KIN_MAX 64
+struct KinTree {
+    int n;
+    int parent[EHB_KIN_MAX];      // -1: root
+    int jtype[EHB_KIN_MAX];       // 0 fixed, 1 revolute / continuous, 2 prismatic
+    int qidx[EHB_KIN_MAX];        // index into qpos of the joint that moves this link (-1: none)
+    double mult[EHB_KIN_MAX], offs[EHB_KIN_MAX];   // joint value = qpos[qidx] * mult + offs (mimic joints)
+    double axis[EHB_KIN_MAX][3];
+    double origin[EHB_KIN_MAX][12];   // top three rows of the joint origin (parent frame -> joint frame)
+};
+
 struct Ctx {
     int device = 0;
     int nSM = 148;
@@ -109,6 +121,10 @@ struct Ctx {
     int nPipes = 3;
     std::vector<Mesh> meshes;
     std::vector<Ref> refs;
+    std::vector<KinTree*> robots;     // device copies of registered kinematic trees (ehb_robot_register)
+    std::vector<int> robotLinks;
+    DevBuf<double> fkScratch, fkIn;
+    DevBuf<int> fkSel;
     Scratch sc[N_SCRATCH];            // [0, MAX_PIPES): pipelines of a device-pointer call; then one per host-step slot
     cudaStream_t pipeStream[MAX_PIPES] = {};
     cudaEvent_t evFork = nullptr, evJoin[MAX_PIPES] = {};
@@ -313,6 +329,111 @@ __global__ void ehb_k_pack_ref(const T* __restrict__ ref, int B, int H, int W, i
     }
 }
 
+// ---------------------------------------------------------------------------------------------------- space exploration
+__device__ __forceinline__ void ehb_mul34(const double* A, const double* B, double* C)   // C = A @ B, 3x4 rigid transforms
+{
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 4; c++) {
+            double s = A[4 * r] * B[c] + A[4 * r + 1] * B[4 + c] + A[4 * r + 2] * B[8 + c];
+            if (c == 3) s += A[4 * r + 3];
+            C[4 * r + c] = s;
+        }
+    }
+}
+
+// One thread per candidate joint configuration: forward kinematics of the whole tree in fp64 (URDF conventions of
+// easyhec_b200/urdf_fk.py, which stands in for sapien / pinocchio: easyhec/structures/sapien_kin.py:26-30), then for every
+// camera pose c and selected link l   mvp[q, c, l] = P @ cam[c] @ T_link   (nvdiffrast_renderer.py:33-37 with
+// object_pose = Tc_c2b @ link_pose, render_api.py:179-190), rounded to fp32 once.
+__global__ void ehb_k_fk_mvp(const KinTree* __restrict__ kt, const double* __restrict__ qpos, int dof, int Q,
+                             const double* __restrict__ cams, int C, const double* __restrict__ P, const int* __restrict__ sel,
+                             int L, float* __restrict__ mvp, double* __restrict__ scratch)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    double* T = scratch + (size_t)q * kt->n * 12;   // link poses of this candidate (global scratch: up to 64 x 12 doubles)
+    for (int l = 0; l < kt->n; l++) {
+        double J[12];
+        const double* O = kt->origin[l];
+        const int qi = kt->qidx[l];
+        if (kt->jtype[l] != 0 && qi >= 0) {
+            const double v = (qi < dof ? qpos[(size_t)q * dof + qi] : 0.0) * kt->mult[l] + kt->offs[l];
+            double M[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+            const double x = kt->axis[l][0], y = kt->axis[l][1], z = kt->axis[l][2];
+            if (kt->jtype[l] == 2) { M[3] = v * x; M[7] = v * y; M[11] = v * z; }
+            else {   // Rodrigues: I + sin(v) K + (1 - cos(v)) K^2
+                const double sn = sin(v), cs = 1.0 - cos(v);
+                const double K[9] = {0, -z, y, z, 0, -x, -y, x, 0};
+                for (int r = 0; r < 3; r++)
+                    for (int c = 0; c < 3; c++) {
+                        double k2 = 0.0;
+                        for (int k = 0; k < 3; k++) k2 += K[3 * r + k] * K[3 * k + c];
+                        M[4 * r + c] = (r == c ? 1.0 : 0.0) + sn * K[3 * r + c] + cs * k2;
+                    }
+            }
+            ehb_mul34(O, M, J);
+        } else {
+            for (int i = 0; i < 12; i++) J[i] = O[i];
+        }
+        const int pa = kt->parent[l];
+        if (pa < 0) { for (int i = 0; i < 12; i++) T[l * 12 + i] = J[i]; }
+        else {
+            double R[12];
+            ehb_mul34(T + pa * 12, J, R);
+            for (int i = 0; i < 12; i++) T[l * 12 + i] = R[i];
+        }
+    }
+    for (int c = 0; c < C; c++)
+        for (int k = 0; k < L; k++) {
+            double CT[12];
+            const double* cam = cams + (size_t)c * 16;
+            ehb_mul34(cam, T + sel[k] * 12, CT);
+            float* out = mvp + (((size_t)q * C + c) * L + k) * 16;
+            for (int r = 0; r < 4; r++)
+                for (int cc = 0; cc < 4; cc++) {
+                    double s = P[4 * r] * CT[cc] + P[4 * r + 1] * CT[4 + cc] + P[4 * r + 2] * CT[8 + cc];
+                    if (cc == 3) s += P[4 * r + 3];
+                    out[4 * r + cc] = (float)s;
+                }
+        }
+}
+
+// Variance score straight from the depth planes of a packed-robot pass (one plane per (candidate, camera)): for every
+// pixel of the union of the candidate's C plane boxes, k = number of cameras whose nearest triangle there has z/w > 0;
+// num[q] += sum k (C - k).  Pixels outside every box have k = 0.  No mask is written anywhere.
+__global__ void __launch_bounds__(256) ehb_k_variance_planes(const EhbPlane* __restrict__ plane, const unsigned long long* __restrict__ pool,
+                                                             int C, unsigned long long* __restrict__ num)
+{
+    const int q = blockIdx.y;
+    const EhbPlane* pl = plane + (size_t)q * C;
+    int x0 = INT_MAX, y0 = INT_MAX, x1 = INT_MIN, y1 = INT_MIN;
+    for (int c = 0; c < C; c++)
+        if (pl[c].w > 0) {
+            x0 = min(x0, pl[c].x0); y0 = min(y0, pl[c].y0);
+            x1 = max(x1, pl[c].x0 + pl[c].w - 1); y1 = max(y1, pl[c].y0 + pl[c].h - 1);
+        }
+    unsigned long long acc = 0;
+    if (x0 <= x1) {
+        const int bw = x1 - x0 + 1;
+        const long long n = (long long)bw * (y1 - y0 + 1);
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+            const int py = y0 + (int)(i / bw), px = x0 + (int)(i % bw);
+            unsigned k = 0;
+            for (int c = 0; c < C; c++) {
+                const int cx = px - pl[c].x0, cy = py - pl[c].y0;
+                if ((unsigned)cx < (unsigned)pl[c].w && (unsigned)cy < (unsigned)pl[c].h) {
+                    const unsigned long long key = pool[pl[c].off + (long long)cy * pl[c].w + cx];
+                    k += key != EHB_EMPTY && (uint32_t)(key >> 32) > 0x80000000u;
+                }
+            }
+            acc += (unsigned long long)(k * ((unsigned)C - k));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(num + q, acc);
+}
+
 // Developer knob: integer from the environment, read once per name (launch-shape experiments without a rebuild).
 int tune_int(const char* name, int dflt)
 {
@@ -515,7 +636,9 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
     CU(launch(ehb_k_raster, dim3((unsigned)(streamBlocks + rasterBlocks)), dim3(EHB_RWARPS * 32), 0, st, true, rb, p, streamBlocks, chunks));
     CU(launch(ehb_k_raster_big, dim3(c->nSM * EHB_BMIN_BLOCKS), dim3(256), 0, st, true, p));
     if (ev) cudaEventRecord(ev[3], st);
-    if (unionMode) {
+    if (unionMode && !io.out_u8) {
+        // planes only (space exploration scores them directly)
+    } else if (unionMode) {
         const int nq = ((W + 3) / 4) * H;
         CU(launch(ehb_k_union_out, dim3((unsigned)std::min((nq + 255) / 256, 4 * c->nSM), (unsigned)items), dim3(256), 0, st, true, p));
     } else {
@@ -628,6 +751,8 @@ int ehb_ctx_destroy(ehb_ctx_t h)
     cudaDeviceSynchronize();
     for (auto& m : c->meshes) if (m.live) { cudaFree(m.verts); cudaFree(m.faces); cudaFree(m.opp); cudaFree(m.boxes); cudaFree(m.fboxes); }
     for (auto& r : c->refs) if (r.live) { cudaFree(r.bits); cudaFree(r.cnt); cudaFree(r.total); }
+    for (auto k : c->robots) if (k) cudaFree(k);
+    c->fkScratch.release(); c->fkIn.release(); c->fkSel.release();
     for (int k = 0; k < MAX_PIPES; k++) { cudaStreamDestroy(c->pipeStream[k]); cudaEventDestroy(c->evJoin[k]); }
     for (int k = 0; k < N_SCRATCH; k++) c->sc[k].release();
     for (int k = 0; k < N_SLOTS; k++) { cudaStreamDestroy(c->slotStream[k]); cudaEventDestroy(c->slotDone[k]); c->slotMvp[k].release(); c->slotOut[k].release(); c->slotRef[k].release(); }
@@ -1001,18 +1126,103 @@ int ehb_explore_scores(ehb_ctx_t h, const int* mesh_ids, int L, int Q, int C, co
     if (Q == 0) return EHB_OK;
     DeviceGuard guard(c->device);
     cudaStream_t st = (cudaStream_t)stream;
-    const long long n = (long long)H * W;
-    // candidates are processed in chunks so that the transient masks stay L2-sized and scratch stays bounded
-    const int chunk = std::max(1, std::min(Q, std::max(1, 64 / C)));
-    int r = c->maskDev.ensure((size_t)chunk * C * n, is_capturing(st));
+    const bool capturing = is_capturing(st);
+    int r = c->numDev.ensure((size_t)Q, capturing);
     if (r) return r;
-    for (int q0 = 0; q0 < Q; q0 += chunk) {
-        const int nq = std::min(chunk, Q - q0);
-        r = ehb_render_binary_batch(h, mesh_ids, L, nq * C, mvp_dev + (size_t)q0 * C * L * 16, H, W, c->maskDev.p, stream);
+    CU(cudaMemsetAsync(c->numDev.p, 0, (size_t)Q * sizeof(unsigned long long), st));
+    // Candidates are rendered in chunks (bounded scratch: one depth plane per (candidate, camera), no mask anywhere); the
+    // chunks alternate over the context's pipelines, each on its own stream, and every chunk is scored straight from its
+    // planes by ehb_k_variance_planes on that stream.
+    const int chunk = std::max(1, std::min(Q, std::max(1, 64 / C)));
+    const int np = c->profiling ? 1 : std::max(1, std::min(c->nPipes, (Q + chunk - 1) / chunk));
+    CU(cudaEventRecord(c->evFork, st));
+    for (int k = 1; k < np; k++) CU(cudaStreamWaitEvent(c->pipeStream[k], c->evFork, 0));
+    int turn = 0;
+    for (int q0 = 0; q0 < Q; q0 += chunk, turn++) {
+        const int nq = std::min(chunk, Q - q0), k = turn % np;
+        cudaStream_t sk = k == 0 ? st : c->pipeStream[k];
+        Io io;   // union mode without an output image: planes only
+        r = run_pass(c, c->sc[k], mesh_ids, L, nq * C, mvp_dev + (size_t)q0 * C * L * 16, H, W, EHB_MODE_UNION, io, sk);
         if (r) return r;
-        r = ehb_variance_score(h, c->maskDev.p, nq, C, n, score_dev + q0, stream);
-        if (r) return r;
+        ehb_k_variance_planes<<<dim3(32, (unsigned)nq), 256, 0, sk>>>(c->sc[k].plane.p, c->sc[k].pool.p, C, c->numDev.p + q0);
+        c->launches += 1;
     }
+    for (int k = 1; k < np; k++) {
+        CU(cudaEventRecord(c->evJoin[k], c->pipeStream[k]));
+        CU(cudaStreamWaitEvent(st, c->evJoin[k], 0));
+    }
+    ehb_k_variance_finish<<<(Q + 255) / 256, 256, 0, st>>>(c->numDev.p, Q, C, score_dev);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    return EHB_OK;
+}
+
+int ehb_robot_register(ehb_ctx_t h, int n_links, const int* parent, const int* jtype, const int* qidx, const double* mult,
+                       const double* offs, const double* axis, const double* origin, int* robot_id)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || !robot_id || n_links < 1 || n_links > EHB_KIN_MAX || !parent || !jtype || !qidx || !mult || !offs || !axis || !origin)
+        return fail(EHB_E_ARG, "bad robot arguments (1 <= links <= %d)", EHB_KIN_MAX);
+    KinTree kt;
+    memset(&kt, 0, sizeof kt);
+    kt.n = n_links;
+    for (int l = 0; l < n_links; l++) {
+        if (parent[l] >= l || parent[l] < -1) return fail(EHB_E_ARG, "link %d: parents must precede their children", l);
+        kt.parent[l] = parent[l]; kt.jtype[l] = jtype[l]; kt.qidx[l] = qidx[l]; kt.mult[l] = mult[l]; kt.offs[l] = offs[l];
+        for (int k = 0; k < 3; k++) kt.axis[l][k] = axis[3 * l + k];
+        for (int k = 0; k < 12; k++) kt.origin[l][k] = origin[16 * l + k];
+    }
+    DeviceGuard guard(c->device);
+    KinTree* d = nullptr;
+    CU(cudaMalloc((void**)&d, sizeof kt));
+    CU(cudaMemcpy(d, &kt, sizeof kt, cudaMemcpyHostToDevice));
+    c->robots.push_back(d);
+    c->robotLinks.push_back(n_links);
+    *robot_id = (int)c->robots.size() - 1;
+    return EHB_OK;
+}
+
+int ehb_explore_fk_mvp(ehb_ctx_t h, int robot_id, const double* qpos_dev, int dof, int Q, const double* cams_host, int C,
+                       const float* K_host, int H, int W, const int* sel_links, int L, float* mvp_dev, void* stream)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || robot_id < 0 || robot_id >= (int)c->robots.size() || !qpos_dev || !cams_host || !K_host || !sel_links || !mvp_dev ||
+        Q < 0 || C < 1 || L < 1 || dof < 0)
+        return fail(EHB_E_ARG, "bad explore_fk_mvp arguments");
+    if (Q == 0) return EHB_OK;
+    const int n = c->robotLinks[robot_id];
+    for (int k = 0; k < L; k++)
+        if (sel_links[k] < 0 || sel_links[k] >= n) return fail(EHB_E_ARG, "selected link %d outside the robot's %d links", sel_links[k], n);
+    DeviceGuard guard(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int r;
+    if ((r = c->fkScratch.ensure((size_t)Q * n * 12, false))) return r;
+    if ((r = c->fkIn.ensure((size_t)C * 16 + 16, false))) return r;
+    if ((r = c->fkSel.ensure((size_t)L, false))) return r;
+    // P = K_to_projection(K, H, W, n = 0.001, f = 10) @ diag(1, -1, -1, 1), as fp32 arithmetic like the host composes it
+    // (easyhec/utils/nvdiffrast_utils.py:5-11), then widened
+    std::vector<double> in((size_t)C * 16 + 16);
+    {
+        const float fu = K_host[0], fv = K_host[4], cu = K_host[2], cv = K_host[5];
+        const float a = (float)(-(10.0 + 0.001) / (10.0 - 0.001)), b = (float)(-2.0 * 10.0 * 0.001 / (10.0 - 0.001));
+        double* P = in.data() + (size_t)C * 16;
+        for (int i = 0; i < 16; i++) P[i] = 0.0;
+        P[0] = (double)((2.f * fu) / (float)W);
+        P[2] = (double)(-((-2.f * cu) / (float)W + 1.f));
+        P[5] = (double)(-((2.f * fv) / (float)H));
+        P[6] = (double)(-((2.f * cv) / (float)H - 1.f));
+        P[10] = (double)(-a);
+        P[11] = (double)b;
+        P[14] = 1.0;
+    }
+    memcpy(in.data(), cams_host, (size_t)C * 16 * sizeof(double));
+    CU(cudaMemcpyAsync(c->fkIn.p, in.data(), in.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->fkSel.p, sel_links, (size_t)L * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));   // (the staging vectors are pageable host memory)
+    ehb_k_fk_mvp<<<(Q + 63) / 64, 64, 0, st>>>(c->robots[robot_id], qpos_dev, dof, Q, c->fkIn.p, C, c->fkIn.p + (size_t)C * 16,
+                                                c->fkSel.p, L, mvp_dev, c->fkScratch.p);
+    c->launches += 1;
+    CU(cudaGetLastError());
     return EHB_OK;
 }
 

@@ -15,7 +15,7 @@ import torch
 
 from .projection import K_to_projection, opencv2gl
 
-__all__ = ["candidate_mvps", "score_candidates", "select_next_qpos"]
+__all__ = ["candidate_mvps", "score_candidates", "select_next_qpos", "shard_candidates"]
 
 
 def candidate_mvps(kin, links, qposes, cam_poses, K, H, W, pad_left=0, pad_right=0, dtype=torch.float32):
@@ -43,11 +43,51 @@ def candidate_mvps(kin, links, qposes, cam_poses, K, H, W, pad_left=0, pad_right
     return mvp.to(dtype).contiguous()
 
 
-def score_candidates(ctx, mesh_ids, kin, links, qposes, cam_poses, K, H, W, valid=None, pad_left=0, pad_right=0):
+def shard_candidates(n: int, rank: int, world: int):
+    """Block partition of n candidates over `world` ranks: (first, count) of one rank (candidates are independent,
+    space_explorer.py:99)."""
+    base, extra = divmod(n, world)
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
+
+
+def score_candidates(ctx, mesh_ids, kin, links, qposes, cam_poses, K, H, W, valid=None, pad_left=0, pad_right=0,
+                     device_fk=True, group=None, robot=None):
     """Variance score of every candidate (space_explorer.py:163-164: ``torch.var(masks, dim=0).sum()``, unbiased) as a
-    (Q,) float64 tensor on the context's device; candidates with ``valid[q] == False`` score 0."""
-    mvp = candidate_mvps(kin, links, qposes, cam_poses, K, H, W, pad_left, pad_right).to(ctx.device)
-    scores = ctx.explore_scores(mesh_ids, mvp, H, W)
+    (Q,) float64 tensor on the context's device; candidates with ``valid[q] == False`` score 0.
+
+    device_fk: forward kinematics and matrix composition run on the GPU (``ehb_explore_fk_mvp``); otherwise
+    ``candidate_mvps`` composes them with torch.  group / an initialised ``torch.distributed``: every rank scores its block of
+    the candidates and ONE all-gather of the scores follows -- the only exchange of this path."""
+    q = torch.as_tensor(np.asarray(qposes) if not isinstance(qposes, torch.Tensor) else qposes).double()
+    if q.ndim == 1:
+        q = q[None]
+    if pad_left or pad_right:
+        q = torch.cat([q.new_zeros(q.shape[0], pad_left), q, q.new_zeros(q.shape[0], pad_right)], 1)
+    Q = q.shape[0]
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    first, count = shard_candidates(Q, rank, world)
+    mine = q[first:first + count]
+    if count == 0:
+        local = torch.zeros(0, dtype=torch.float64, device=ctx.device)
+    elif device_fk:
+        robot = robot or ctx.register_robot(kin)
+        mvp = ctx.explore_fk_mvp(robot, mine.to(ctx.device).contiguous(), cam_poses, K, H, W, links)
+        local = ctx.explore_scores(mesh_ids, mvp, H, W)
+    else:
+        mvp = candidate_mvps(kin, links, mine, cam_poses, K, H, W).to(ctx.device)
+        local = ctx.explore_scores(mesh_ids, mvp, H, W)
+    if world > 1:
+        per = -(-Q // world)                               # equal-sized slots for the all-gather, trimmed afterwards
+        buf = torch.zeros(per, dtype=torch.float64, device=ctx.device)
+        buf[:count] = local
+        out = torch.empty(world * per, dtype=torch.float64, device=ctx.device)
+        dist.all_gather_into_tensor(out, buf, group=group)
+        scores = torch.cat([out[r * per:r * per + shard_candidates(Q, r, world)[1]] for r in range(world)])
+    else:
+        scores = local
     if valid is not None:
         scores = torch.where(torch.as_tensor(np.asarray(valid), dtype=torch.bool, device=scores.device), scores,
                              torch.zeros_like(scores))

@@ -144,10 +144,24 @@ EHB_API int ehb_render_binary_batch(ehb_ctx_t ctx, const int* mesh_ids, int L, i
 /* score[q] = sum_px unbiased_var_c(masks[q,c,px]), masks_dev u8[Q*C*n] -> score_dev f64[Q]. */
 EHB_API int ehb_variance_score(ehb_ctx_t ctx, const uint8_t* masks_dev, int Q, int C, long long n, double* score_dev,
                        void* stream);
-/* Fused space-exploration score: renders Q*C packed binary masks (mvp_dev f32[Q*C*L*16]) tile by tile and
- * reduces the per-pixel variance over the C cameras without writing the masks. */
+/* Fused space-exploration score: rasterizes the Q*C packed-robot renders (mvp_dev f32[Q*C*L*16]) into one depth plane each
+ * and reduces the per-pixel variance over the C cameras of a candidate straight from those planes -- no mask is written
+ * (easyhec/modeling/models/rb_solve/space_explorer.py:152-165). */
 EHB_API int ehb_explore_scores(ehb_ctx_t ctx, const int* mesh_ids, int L, int Q, int C, const float* mvp_dev, int H, int W,
                        double* score_dev, void* stream);
+
+/* Kinematic tree of a robot for the device-side forward kinematics (stands in for sapien / pinocchio,
+ * easyhec/structures/sapien_kin.py:26-30).  Links in an order where parents precede children; per link: parent (-1 = root),
+ * jtype (0 fixed, 1 revolute / continuous, 2 prismatic), qidx (index into qpos of its joint, -1 = none), joint value =
+ * qpos[qidx] * mult + offs (mimic joints), unit axis f64[3], joint origin f64[16] (row-major 4x4, parent -> joint frame). */
+EHB_API int ehb_robot_register(ehb_ctx_t ctx, int n_links, const int* parent, const int* jtype, const int* qidx,
+                       const double* mult, const double* offs, const double* axis, const double* origin, int* robot_id);
+/* mvp[q, c, l] = K_to_projection(K, H, W) @ diag(1,-1,-1,1) @ cams[c] @ FK(qpos[q])[sel_links[l]] for every candidate joint
+ * configuration q (qpos_dev f64[Q*dof], device), camera pose c (cams_host f64[C*16] = Tc_c2b of each camera) and selected
+ * link l -> mvp_dev f32[Q*C*L*16], the input of ehb_explore_scores (render_api.py:179-190 + nvdiffrast_renderer.py:33-37).
+ * Synchronises the stream once (small host inputs). */
+EHB_API int ehb_explore_fk_mvp(ehb_ctx_t ctx, int robot_id, const double* qpos_dev, int dof, int Q, const double* cams_host,
+                       int C, const float* K_host, int H, int W, const int* sel_links, int L, float* mvp_dev, void* stream);
 
 /* Host-buffer form of ehb_render_views_fused for callers without device pointers of their own: copies
  * mvp_host (pinned or pageable) to the device, runs the fused step on ref_dev, copies loss f64[B] and

@@ -57,7 +57,7 @@ def test_score_candidates_masks_invalid_and_selection_skips_history(tmp_path):
     ctx = _FakeCtx()
     q = np.zeros((4, 3))
     s = score_candidates(ctx, [7, 8, 9, 10], kin, [0, 1, 2, 3], q, SAMPLE_POSE[None], scaled_K(48, 64), 48, 64,
-                         valid=[True, True, False, True])
+                         valid=[True, True, False, True], device_fk=False)
     assert ctx.seen == ([7, 8, 9, 10], (4, 1, 4, 4, 4), 48, 64)
     assert s.tolist() == [1.0, 2.0, 0.0, 4.0]                 # rejected candidates score 0 (space_explorer.py:109,120,135)
     assert select_next_qpos(s) == (3, 4.0)
@@ -75,3 +75,13 @@ def test_xarm_chain_urdf_reproduces_the_fixture_kinematics(tmp_path):
     got = kin.forward(q).numpy()
     for i in range(4):
         assert np.allclose(got[i], chain_fk(fx["joint_origin"], fx["joint_axis"], q[i]), atol=1e-9)
+
+
+def test_shard_candidates_is_a_block_partition():
+    from easyhec_b200.explore import shard_candidates
+    for n in (0, 1, 7, 256, 1000):
+        for world in (1, 2, 3, 8):
+            parts = [shard_candidates(n, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and sum(c for _, c in parts) == n
+            assert all(parts[r][0] + parts[r][1] == parts[r + 1][0] for r in range(world - 1))
+            assert max(c for _, c in parts) - min(c for _, c in parts) <= 1

@@ -102,16 +102,29 @@ def test_cfg4_score_candidates_end_to_end_1920x1080(gpu_ctx, tmp_path):
     links = list(range(8))
     ids = [gpu_ctx.register_mesh(m.vertices, m.faces) for m in fx["meshes"]]
     valid = np.ones(Q, bool); valid[3] = False
-    got = score_candidates(gpu_ctx, ids, kin, links, q, cams, K, H, W, valid=valid).cpu().numpy()
+    packed = oracle.pack_links(fx["meshes"])
+    # (a) matrices composed on the host (torch): the device render + variance against the oracle on the same matrices
+    got = score_candidates(gpu_ctx, ids, kin, links, q, cams, K, H, W, valid=valid, device_fk=False).cpu().numpy()
     flags, _ = gpu_ctx.status()
     assert flags & 1 == 0
     mvp = candidate_mvps(kin, links, q, cams, K, H, W).numpy()
-    packed = oracle.pack_links(fx["meshes"])
     masks = oracle.union_binary(packed, mvp.reshape(Q * C, len(links), 4, 4), H, W)
     want = oracle.variance_scores(masks.reshape(Q, C, H, W))
     want[3] = 0.0
     assert want.max() > 0
-    assert np.allclose(got, want, rtol=1e-12, atol=0)
+    assert np.allclose(got, want, rtol=1e-14, atol=0)
+    # (b) forward kinematics + composition on the device (ehb_explore_fk_mvp): its matrices agree with the host's to fp32
+    # rounding, and the scores are exact for the matrices it produced
+    robot = gpu_ctx.register_robot(kin)
+    mvp_d = gpu_ctx.explore_fk_mvp(robot, to_dev(q), cams, K, H, W, links)
+    assert mvp_d.shape == (Q, C, len(links), 4, 4)
+    assert np.abs(mvp_d.cpu().numpy() - mvp).max() <= 2e-6 * np.abs(mvp).max()
+    got_d = score_candidates(gpu_ctx, ids, kin, links, q, cams, K, H, W, valid=valid, robot=robot).cpu().numpy()
+    masks_d = oracle.union_binary(packed, mvp_d.cpu().numpy().reshape(Q * C, len(links), 4, 4), H, W)
+    want_d = oracle.variance_scores(masks_d.reshape(Q, C, H, W))
+    want_d[3] = 0.0
+    assert np.allclose(got_d, want_d, rtol=1e-14, atol=0)
+    assert np.abs(got_d - want).max() < 0.02 * want.max()       # and both describe the same candidates
     for i in ids:
         gpu_ctx.release_mesh(i)
 

@@ -70,6 +70,30 @@ def main():
         print("sharded vs single-rank dof max |diff| = %.2e; pose error %.3f mm / %.4f deg (peer all-reduce: %s)" %
               (d, 1e3 * e[0], e[1], s._peer))
     assert d < 2e-3, d
+    # space exploration: candidates block-partitioned over the ranks + ONE all-gather == all candidates on one rank
+    from easyhec_b200.explore import score_candidates
+    from easyhec_b200.scenes import load_xarm7
+    from util import xarm_urdf
+    import pathlib
+    import tempfile
+    fx = load_xarm7()
+    kin = xarm_urdf(pathlib.Path(tempfile.mkdtemp()), fx)
+    Hx, Wx, Qn, Cn = 270, 480, 11, 3                      # 11 candidates over the ranks: uneven blocks
+    qs = np.random.RandomState(5).uniform(-1.5, 1.5, size=(Qn, 7))
+    cams = np.stack([perturb_pose(sc["Tc_c2b"], np.random.RandomState(40 + k), 0.05, 5.0) for k in range(Cn)])
+    from easyhec_b200.scenes import scaled_K
+    Kx = scaled_K(Hx, Wx)
+    ids8 = [ctx.register_mesh(m.vertices, m.faces) for m in fx["meshes"]]
+    sharded = score_candidates(ctx, ids8, kin, list(range(8)), qs, cams, Kx, Hx, Wx)
+    was = dist.is_initialized
+    dist.is_initialized = lambda: False                   # the same call as a single-rank job
+    try:
+        single = score_candidates(ctx, ids8, kin, list(range(8)), qs, cams, Kx, Hx, Wx)
+    finally:
+        dist.is_initialized = was
+    assert sharded.shape == (Qn,) and torch.equal(sharded, single) and float(single.max()) > 0
+    if rank == 0:
+        print("exploration scores sharded over %d ranks + all-gather == single rank (%d candidates)" % (world, Qn))
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
