@@ -372,7 +372,7 @@ def run_b200(args):
         if args.collective == "peer":
             try:   # one-shot all-reduce through NVLink peer mailboxes (ehb_allreduce7); NCCL stays the fallback
                 ctx.comm_connect()
-                collective = "NVLink peer-mailbox all-reduce 7xf32 per step (ehb_allreduce7)"
+                collective = "NVLink peer-mailbox all-reduce 7xf32 per step, fused into pose_backward (send) and adam (recv)"
             except Exception as e:   # noqa: BLE001
                 if rank == 0:
                     print("peer all-reduce unavailable (%s); using NCCL" % e, file=sys.stderr)
@@ -386,13 +386,11 @@ def run_b200(args):
         s = k % R
         ctx.render_views_fused(ids, mvp_dev[s], ref_h[s], H, W, backward=True, out=(masks[s], loss, gmvp))
         ctx.pose_backward(dof_dev[s], K_dev, lp_dev[s], gmvp, loss, H, W, grad_scale=1.0 / world,
-                          loss_scale=1.0 / (B * world), out=g7)
+                          loss_scale=1.0 / (B * world), out=g7, send=use_peer)
         if world > 1:   # the solver's one exchange step: all-reduce of (g_dof[6], loss) -- trainer/base.py:349 -- then Adam
-            if use_peer:
-                ctx.allreduce7(g7)
-            else:
+            if not use_peer:
                 dist.all_reduce(g7)
-            ctx.adam_step(dof_scratch, g7, adam_state, 3e-3, weight_decay=5e-4)
+            ctx.adam_step(dof_scratch, g7, adam_state, 3e-3, weight_decay=5e-4, recv=use_peer)
 
     def barrier():
         torch.cuda.synchronize()
@@ -609,8 +607,105 @@ def main():
         run_b200(args)
 
 
-def run_explore(args):   # filled in with the sharded exploration scorer (BASELINE.json configs[3])
-    raise SystemExit("--workload explore: not built yet")
+def run_explore(args):
+    """BASELINE.json configs[3]: space-exploration scoring, 256 candidate joint configurations x 4 camera poses, xArm7 base +
+    links 1-7 (41,096 triangles), 1920x1080, forward-only binary render + variance score.  Candidates are block-partitioned
+    over the ranks (no data-path collective), one all-gather of the scores ends a step.  value = renders/s of the job."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    out = JsonStdout(world > 1)
+    import pathlib
+    import tempfile
+    import torch
+    import torch.distributed as dist
+    from easyhec_b200._lib import Context
+    from easyhec_b200.explore import score_candidates, shard_candidates
+    from easyhec_b200.scenes import FRANKA_K, load_xarm7, make_scene, perturb_pose, scaled_K
+    from util import xarm_urdf
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ex = EXPLORE
+    Q, C, H, W = ex["Q"], ex["C"], ex["H"], ex["W"]
+    fx = load_xarm7()
+    kin = xarm_urdf(pathlib.Path(tempfile.mkdtemp()), fx)
+    lim = fx["joint_limits"]
+    q = np.random.RandomState(0).uniform(np.maximum(lim[:, 0], -np.pi) * 0.6, np.minimum(lim[:, 1], np.pi) * 0.6, size=(Q, len(lim)))
+    sc = make_scene(1, H, W, links="xarm7_all", seed=0, K_base=FRANKA_K)
+    cams = np.stack([perturb_pose(sc["Tc_c2b"], np.random.RandomState(1 + c), 0.05, 5.0) for c in range(C)])
+    K = scaled_K(H, W, FRANKA_K)
+    ctx = Context(dev)
+    ids = [ctx.register_mesh(m.vertices, m.faces) for m in fx["meshes"]]
+    robot = ctx.register_robot(kin)
+    links = list(range(8))
+    V = sum(len(m.vertices) for m in fx["meshes"]); F = sum(len(m.faces) for m in fx["meshes"])
+    q_dev = torch.from_numpy(q).to(dev)
+
+    def step(_k):
+        return score_candidates(ctx, ids, kin, links, q_dev, cams, K, H, W, robot=robot)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(max(args.warmup, 3)):
+        scores = step(k)
+    flags, nclip = ctx.status()
+    assert flags & 1 == 0
+    sampler = ClockSampler(physical_gpu_index(local))
+    barrier()
+    sampler.start()
+    l0 = ctx.launch_count()
+    steps = min(args.steps, 50)
+    ms, regions = timed_regions(step, steps, barrier, torch)
+    clocks = sampler.stop()
+    launches = (ctx.launch_count() - l0) // max(len(regions), 1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    renders = Q * C * steps
+    value = renders / (ms * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg = algorithmic_bytes_per_render(H, W, V, F) * Q * C        # per step of the whole job
+    if rank == 0:
+        parity = None
+        if not args.no_cpu and world == 1:
+            from oracle import oracle
+            packed = oracle.pack_links(fx["meshes"])
+            n = 8                                                   # a bounded sample of the candidates on the host cores
+            mvp = ctx.explore_fk_mvp(robot, q_dev[:n].contiguous(), cams, K, H, W, links).cpu().numpy()
+            t0 = time.perf_counter()
+            masks = oracle.union_binary(packed, mvp.reshape(n * C, len(links), 4, 4), H, W)
+            want = oracle.variance_scores(masks.reshape(n, C, H, W))
+            dt = time.perf_counter() - t0
+            parity = {"ok": bool(np.allclose(scores[:n].cpu().numpy(), want, rtol=1e-14, atol=0)), "candidates": n,
+                      "cpu_renders_per_s": n * C / dt, "cores": oracle.num_threads()}
+        line = {"metric": "space-exploration scoring renders/sec @1920x1080 xArm7 (256 qpos x 4 cameras)", "value": value,
+                "unit": "renders/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": ex["name"], "Q": Q, "C": C, "H": H, "W": W, "triangles": F, "candidates_per_rank":
+                           shard_candidates(Q, 0, world)[1], "collective": "one all-gather of the scores per step" if world > 1 else "none",
+                           "step": "device FK->MVP, packed binary render, variance from the depth planes" +
+                                   (", all-gather of %d scores" % Q if world > 1 else ""),
+                           "timed_regions": len(regions), "timed_region_ms": ms},
+                "candidates_per_s": Q * steps / (ms * 1e-3), "clocks": clocks, "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": alg / (ms / steps * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
+                             "frac": alg / (ms / steps * 1e-3) / 1e9 / (peak * world), "algorithmic_bytes_per_step": alg,
+                             "note": "whole step against the aggregate peak of the GPUs used"},
+                "parity_checked": bool(parity and parity["ok"]), "parity": parity, "best_candidate": int(scores.argmax().item())}
+        out.emit(line)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

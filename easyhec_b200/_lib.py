@@ -77,6 +77,10 @@ _PROTOS = {
                                    C.c_void_p, C.c_void_p]),
     "ehb_pose_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                     C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
+    "ehb_pose_backward_send": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
+    "ehb_adam_step_recv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
+                                     C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
     "ehb_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
     "ehb_solver_step_begin_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
@@ -435,8 +439,9 @@ class Context:
                                       _stream(self.device)))
         return out
 
-    def pose_backward(self, dof, K, link_poses, g_mvp, loss, H, W, grad_scale=1.0, loss_scale=None, out=None):
-        """-> out7 f32 (7,) = [grad_scale * dL/ddof, loss_scale * sum(loss)]"""
+    def pose_backward(self, dof, K, link_poses, g_mvp, loss, H, W, grad_scale=1.0, loss_scale=None, out=None, send=False):
+        """-> out7 f32 (7,) = [grad_scale * dL/ddof, loss_scale * sum(loss)].  send=True: the same kernel also posts out7 to
+        every peer's mailbox (first half of the fused all-reduce; pair with adam_step(recv=True))."""
         _dev_check(g_mvp, torch.float64, self.device, "g_mvp")
         _dev_check(loss, torch.float64, self.device, "loss")
         B, L = link_poses.shape[0], link_poses.shape[1]
@@ -444,17 +449,19 @@ class Context:
             loss_scale = 1.0 / B
         if out is None:
             out = torch.empty((7,), dtype=torch.float32, device=self.device)
-        _check(lib().ehb_pose_backward(self._h, _ptr(dof), _ptr(K), _ptr(link_poses), _ptr(g_mvp), _ptr(loss), B, L, H,
-                                       W, float(grad_scale), float(loss_scale), _ptr(out), _stream(self.device)))
+        fn = lib().ehb_pose_backward_send if send else lib().ehb_pose_backward
+        _check(fn(self._h, _ptr(dof), _ptr(K), _ptr(link_poses), _ptr(g_mvp), _ptr(loss), B, L, H,
+                  W, float(grad_scale), float(loss_scale), _ptr(out), _stream(self.device)))
         return out
 
-    def adam_step(self, dof, g7, state, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, hist=None):
+    def adam_step(self, dof, g7, state, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, hist=None, recv=False):
         _dev_check(dof, torch.float32, self.device, "dof")
         _dev_check(g7, torch.float32, self.device, "g7")
         _dev_check(state, torch.float32, self.device, "state")
         cap = 0 if hist is None else hist.shape[0]
-        _check(lib().ehb_adam_step(self._h, _ptr(dof), _ptr(g7), _ptr(state), lr, betas[0], betas[1], eps, weight_decay,
-                                   _ptr(hist), cap, _stream(self.device)))
+        fn = lib().ehb_adam_step_recv if recv else lib().ehb_adam_step
+        _check(fn(self._h, _ptr(dof), _ptr(g7), _ptr(state), lr, betas[0], betas[1], eps, weight_decay,
+                  _ptr(hist), cap, _stream(self.device)))
 
     def solver_step_begin_u8(self, slot, mesh_ids, mvp_host, ref_u8_host, H, W, loss_host, g_mvp_host):
         """Asynchronous host-buffer step on slot 0/1 (own stream): returns at once; pair with solver_step_end(slot)."""

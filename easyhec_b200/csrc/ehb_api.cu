@@ -1306,7 +1306,22 @@ int ehb_pose_backward(ehb_ctx_t h, const float* dof_dev, const float* K_dev, con
         return fail(EHB_E_ARG, "bad pose_backward arguments");
     DeviceGuard guard(c->device);
     CU(launch(ehb_k_pose_backward, dim3(1), dim3(256), 0, (cudaStream_t)stream, true, dof_dev, K_dev, link_poses_dev, g_mvp_dev,
-              loss_dev, B, L, H, W, grad_scale, loss_scale, out7_dev));
+              loss_dev, B, L, H, W, grad_scale, loss_scale, out7_dev, c->comm, 0));
+    c->launches += 1;
+    return EHB_OK;
+}
+
+int ehb_pose_backward_send(ehb_ctx_t h, const float* dof_dev, const float* K_dev, const float* link_poses_dev,
+                           const double* g_mvp_dev, const double* loss_dev, int B, int L, int H, int W, double grad_scale,
+                           double loss_scale, float* out7_dev, void* stream)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || !dof_dev || !K_dev || !link_poses_dev || !g_mvp_dev || !loss_dev || !out7_dev || B < 1 || L < 1)
+        return fail(EHB_E_ARG, "bad pose_backward arguments");
+    if (!c->commReady) return fail(EHB_E_ARG, "peer mailboxes are not connected (ehb_comm_connect)");
+    DeviceGuard guard(c->device);
+    CU(launch(ehb_k_pose_backward, dim3(1), dim3(256), 0, (cudaStream_t)stream, true, dof_dev, K_dev, link_poses_dev, g_mvp_dev,
+              loss_dev, B, L, H, W, grad_scale, loss_scale, out7_dev, c->comm, 1));
     c->launches += 1;
     return EHB_OK;
 }
@@ -1317,8 +1332,21 @@ int ehb_adam_step(ehb_ctx_t h, float* dof_dev, const float* g7_dev, float* state
     Ctx* c = (Ctx*)h;
     if (!c || !dof_dev || !g7_dev || !state_dev) return fail(EHB_E_ARG, "bad adam arguments");
     DeviceGuard guard(c->device);
+    CU(launch(ehb_k_adam, dim3(1), dim3(32), 0, (cudaStream_t)stream, true, dof_dev, (float*)g7_dev, state_dev, lr, beta1, beta2, eps,
+              weight_decay, hist_dev, hist_cap, c->comm, 0));
+    c->launches += 1;
+    return EHB_OK;
+}
+
+int ehb_adam_step_recv(ehb_ctx_t h, float* dof_dev, float* g7_dev, float* state_dev, float lr, float beta1, float beta2,
+                       float eps, float weight_decay, float* hist_dev, int hist_cap, void* stream)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || !dof_dev || !g7_dev || !state_dev) return fail(EHB_E_ARG, "bad adam arguments");
+    if (!c->commReady) return fail(EHB_E_ARG, "peer mailboxes are not connected (ehb_comm_connect)");
+    DeviceGuard guard(c->device);
     CU(launch(ehb_k_adam, dim3(1), dim3(32), 0, (cudaStream_t)stream, true, dof_dev, g7_dev, state_dev, lr, beta1, beta2, eps,
-              weight_decay, hist_dev, hist_cap));
+              weight_decay, hist_dev, hist_cap, c->comm, 1));
     c->launches += 1;
     return EHB_OK;
 }

@@ -116,14 +116,30 @@ __global__ void ehb_k_pose_compose(const float* __restrict__ dof, const float* _
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// One-shot all-reduce of the 7 floats (d loss/d dof, loss) over NVLink peer memory.  Every rank owns a mailbox
+// [2 parities][world][8 words] that its peers map with CUDA IPC.  One step: write (7 floats, step tag) into slot
+// [parity][my rank] of EVERY rank's mailbox (plain stores over NVLink / NVSwitch), fence, then spin until all slots of
+// the own mailbox carry this step's tag and add them in rank order (so every rank gets bit-identical sums).
+// Two parities are enough: a rank can only be one step ahead of a peer that has not yet read its previous message.
+// 28 bytes cross the switch per peer, so the cost is one NVLink round trip (~2-4 us) instead of a collective launch.
+#define EHB_COMM_MAX 16
+struct EhbComm {
+    unsigned int* peer[EHB_COMM_MAX];   // peer[r] = rank r's mailbox, as mapped in this process (peer[rank] = own)
+    unsigned int* step;                 // device counter of completed all-reduces (own)
+    int rank, world;
+};
+
 // one block of 256 threads.  out7 = { d loss / d dof [6], loss } with the caller's scales applied.  The tail is spread over
 // threads (12 for P^T S, 6 for the six dual-number evaluations of the exp map): fp64 on one thread was 6 us of pure latency.
 __global__ void __launch_bounds__(256) ehb_k_pose_backward(const float* __restrict__ dof, const float* __restrict__ K,
                                                            const float* __restrict__ lp, const double* __restrict__ gmvp,
                                                            const double* __restrict__ loss, int B, int L, int H, int W,
-                                                           double grad_scale, double loss_scale, float* __restrict__ out7)
+                                                           double grad_scale, double loss_scale, float* __restrict__ out7,
+                                                           const EhbComm cm, int send)
 {
     ehb_pose_pdl_enter();
+    __shared__ float s_out[8];
     __shared__ double S[8][17];
     __shared__ double T[17];
     __shared__ double G[12];
@@ -170,18 +186,53 @@ __global__ void __launch_bounds__(256) ehb_k_pose_backward(const float* __restri
         ehb_se3_exp<EhbDual>(d, t, 1e-4);
         double s = 0.0;
         for (int j = 0; j < 12; j++) s += G[j] * t[j].d;
-        out7[tid] = (float)(s * grad_scale);
+        out7[tid] = s_out[tid] = (float)(s * grad_scale);
     } else if (tid == 6) {
-        out7[6] = (float)(T[16] * loss_scale);
+        out7[6] = s_out[6] = (float)(T[16] * loss_scale);
+    }
+    if (send) {
+        // first half of the all-reduce, fused: this rank's 7 floats + the step tag go into every peer's mailbox (plain
+        // stores over NVLink); ehb_k_adam (recv) waits for all of them and adds them in rank order
+        __syncthreads();
+        if (tid < cm.world) {
+            const unsigned int step = *cm.step + 1u;
+            volatile unsigned int* dst = cm.peer[tid] + ((size_t)(step & 1u) * EHB_COMM_MAX + cm.rank) * 8;
+            for (int i = 0; i < 7; i++) dst[i] = __float_as_uint(s_out[i]);
+            __threadfence_system();
+            dst[7] = step;
+        }
     }
 }
 
 // state = { m[6], v[6], t }.  torch.optim.Adam (L2 weight decay folded into the gradient, bias-corrected).
-__global__ void ehb_k_adam(float* __restrict__ dof, const float* __restrict__ g7, float* __restrict__ state, float lr,
-                           float beta1, float beta2, float eps, float wd, float* __restrict__ hist, int hist_cap)
+__global__ void ehb_k_adam(float* __restrict__ dof, float* __restrict__ g7, float* __restrict__ state, float lr,
+                           float beta1, float beta2, float eps, float wd, float* __restrict__ hist, int hist_cap,
+                           const EhbComm cm, int recv)
 {
     ehb_pose_pdl_enter();
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (blockIdx.x != 0) return;
+    if (recv) {
+        // second half of the fused all-reduce: wait until every rank's message of this step is in the own mailbox, add
+        // them in rank order (bit-identical sums on every rank), leave the sum in g7
+        __shared__ float s_val[EHB_COMM_MAX][7];
+        const int t = threadIdx.x;
+        const unsigned int step = *cm.step + 1u;
+        if (t < cm.world) {
+            volatile unsigned int* src = cm.peer[cm.rank] + ((size_t)(step & 1u) * EHB_COMM_MAX + t) * 8;
+            while (src[7] != step) { }
+            __threadfence_system();
+            for (int i = 0; i < 7; i++) s_val[t][i] = __uint_as_float(src[i]);
+        }
+        __syncthreads();
+        if (t < 7) {
+            float acc = 0.f;
+            for (int r = 0; r < cm.world; r++) acc += s_val[r][t];
+            g7[t] = acc;
+        }
+        if (t == 0) *cm.step = step;
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
     const int t = (int)state[12] + 1;
     if (hist && t - 1 < hist_cap)
         for (int i = 0; i < 6; i++) hist[(size_t)(t - 1) * 6 + i] = dof[i];
@@ -198,20 +249,6 @@ __global__ void ehb_k_adam(float* __restrict__ dof, const float* __restrict__ g7
     }
     state[12] = (float)t;
 }
-
-// ---------------------------------------------------------------------------------------------------------------
-// One-shot all-reduce of the 7 floats (d loss/d dof, loss) over NVLink peer memory.  Every rank owns a mailbox
-// [2 parities][world][8 words] that its peers map with CUDA IPC.  One step: write (7 floats, step tag) into slot
-// [parity][my rank] of EVERY rank's mailbox (plain stores over NVLink / NVSwitch), fence, then spin until all slots of
-// the own mailbox carry this step's tag and add them in rank order (so every rank gets bit-identical sums).
-// Two parities are enough: a rank can only be one step ahead of a peer that has not yet read its previous message.
-// 28 bytes cross the switch per peer, so the cost is one NVLink round trip (~2-4 us) instead of a collective launch.
-#define EHB_COMM_MAX 16
-struct EhbComm {
-    unsigned int* peer[EHB_COMM_MAX];   // peer[r] = rank r's mailbox, as mapped in this process (peer[rank] = own)
-    unsigned int* step;                 // device counter of completed all-reduces (own)
-    int rank, world;
-};
 
 __global__ void ehb_k_allreduce7(const EhbComm cm, float* __restrict__ g7)
 {

@@ -86,14 +86,12 @@ class PoseSolver:
         c.render_views_fused(self.mesh_ids, self.mvp, self.ref, self.H, self.W, backward=True,
                              out=(self.masks, self.loss_b, self.g_mvp))
         # fused kernel scaled by 1/B_local; rescale so that the sum over ranks is the global mean's gradient
+        fusedx = self.world > 1 and self._peer      # the 7-float exchange rides inside pose_backward (send) and adam (recv)
         c.pose_backward(self.dof, self.K, self.link_poses, self.g_mvp, self.loss_b, self.H, self.W,
-                        grad_scale=self.B / self.B_global, loss_scale=1.0 / self.B_global, out=self.g7)
-        if self.world > 1:
-            if self._peer:
-                c.allreduce7(self.g7)
-            else:
-                torch.distributed.all_reduce(self.g7, group=self.group)
-        c.adam_step(self.dof, self.g7, self.state, self.lr, self.betas, self.eps, self.wd, hist=self.hist)
+                        grad_scale=self.B / self.B_global, loss_scale=1.0 / self.B_global, out=self.g7, send=fusedx)
+        if self.world > 1 and not self._peer:
+            torch.distributed.all_reduce(self.g7, group=self.group)
+        c.adam_step(self.dof, self.g7, self.state, self.lr, self.betas, self.eps, self.wd, hist=self.hist, recv=fusedx)
 
     def _check_flags(self):
         flags, _ = self.ctx.status()

@@ -214,6 +214,16 @@ EHB_API int ehb_comm_local_handle(ehb_ctx_t ctx, void* handle64);
 EHB_API int ehb_comm_connect(ehb_ctx_t ctx, int rank, int world, const void* handles);
 EHB_API int ehb_allreduce7(ehb_ctx_t ctx, float* g7_dev, void* stream);
 
+/* The same exchange fused into the pose chain (one launch fewer per optimizer iteration): ehb_pose_backward_send computes
+ * out7 like ehb_pose_backward and posts it to every peer's mailbox from the same kernel; ehb_adam_step_recv waits for all
+ * ranks' messages of the step, adds them in rank order into g7_dev (the reduced values) and applies Adam.  Always used as
+ * a pair, on the same stream, by every rank. */
+EHB_API int ehb_pose_backward_send(ehb_ctx_t ctx, const float* dof_dev, const float* K_dev, const float* link_poses_dev,
+                           const double* g_mvp_dev, const double* loss_dev, int B, int L, int H, int W, double grad_scale,
+                           double loss_scale, float* out7_dev, void* stream);
+EHB_API int ehb_adam_step_recv(ehb_ctx_t ctx, float* dof_dev, float* g7_dev, float* state_dev, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, float* hist_dev, int hist_cap, void* stream);
+
 /* Number of kernels this library has launched on the context since creation (for launch accounting). */
 EHB_API long long ehb_launch_count(ehb_ctx_t ctx);
 

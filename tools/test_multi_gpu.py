@@ -39,6 +39,25 @@ def main():
         dist.all_gather(gathered, a)
         assert all(torch.equal(gathered[0], t) for t in gathered), "ranks disagree"
     assert worst < 1e-5, worst
+    # the exchange fused into the pose chain: pose_backward(send) + adam(recv) leaves the NCCL sum of the ranks' out7 in g7
+    Bq, Lq = 3, 2
+    gen = torch.Generator(device="cpu").manual_seed(100 + rank)
+    dofq = (torch.randn(6, generator=gen) * 0.3).to(dev)
+    Kq = torch.tensor([[100.0, 0, 64], [0, 100.0, 48], [0, 0, 1]], device=dev)
+    lpq = torch.eye(4).repeat(Bq, Lq, 1, 1).to(dev).contiguous()
+    for step in range(20):
+        gm = torch.randn(Bq, Lq, 4, 4, generator=gen, dtype=torch.float64).to(dev)
+        lb = torch.rand(Bq, generator=gen, dtype=torch.float64).to(dev)
+        ref7 = ctx.pose_backward(dofq, Kq, lpq, gm, lb, 96, 128)
+        dist.all_reduce(ref7)
+        g7 = ctx.pose_backward(dofq, Kq, lpq, gm, lb, 96, 128, send=True)
+        ctx.adam_step(dofq.clone(), g7, torch.zeros(13, device=dev), 0.0, recv=True)
+        assert torch.allclose(g7, ref7, rtol=1e-5, atol=1e-6), (g7, ref7)
+        gathered = [torch.empty_like(g7) for _ in range(world)]
+        dist.all_gather(gathered, g7)
+        assert all(torch.equal(gathered[0], t) for t in gathered), "ranks disagree (fused exchange)"
+    if rank == 0:
+        print("fused exchange (pose_backward send + adam recv) == NCCL all-reduce, identical on every rank")
     # latency of the two collectives (device time, 200 back-to-back calls)
     for name, fn in (("peer", lambda t: ctx.allreduce7(t)), ("nccl", lambda t: dist.all_reduce(t))):
         t = torch.zeros(7, device=dev)
