@@ -44,6 +44,7 @@ _PROTOS = {
     "ehb_ctx_debug_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]),
     "ehb_ctx_debug_buffer": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]),
     "ehb_ctx_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint), C.POINTER(C.c_longlong)]),
+    "ehb_ctx_poll": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint)]),
     "ehb_mesh_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "ehb_mesh_update_verts": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "ehb_mesh_release": (C.c_int, [C.c_void_p, C.c_int]),
@@ -251,6 +252,18 @@ class Context:
         fl, nc = C.c_uint(), C.c_longlong()
         _check(lib().ehb_ctx_status(self._h, C.byref(fl), C.byref(nc)))
         return fl.value, nc.value
+
+    def poll(self) -> int:
+        """The sticky flags without synchronising (may lag behind work that is still running); cleared by status()."""
+        fl = C.c_uint()
+        _check(lib().ehb_ctx_poll(self._h, C.byref(fl)))
+        return fl.value
+
+    def check(self, what="launch"):
+        """Raise if an earlier launch overflowed a scratch pool (its results are incomplete).  Non-synchronising."""
+        if self.poll() & EHB_FLAG_PAIR_OVERFLOW:
+            raise EhbError("a scratch pool of the rasterizer overflowed during an earlier %s: results of that launch are "
+                           "incomplete (call status(), grow_scratch() and run it again)" % what)
 
     def profile(self, enable: bool):
         _check(lib().ehb_ctx_profile(self._h, int(bool(enable))))

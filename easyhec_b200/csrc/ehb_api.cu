@@ -151,6 +151,8 @@ struct Ctx {
     unsigned int* commBox = nullptr;  // own mailbox (device)
     bool commReady = false;
     unsigned long long* dbgbuf = nullptr;   // EHB_TIMING builds
+    unsigned int* hostFlags = nullptr;      // mapped pinned host words set by the kernels (ehb_ctx_poll)
+    unsigned int* hostFlagsDev = nullptr;   // the same memory as the device sees it
 };
 
 struct DeviceGuard {
@@ -601,6 +603,7 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
     p.useTma = (!unionMode && io.masks && make_mask_map(&p.tmMask, io.masks, items, H, W, EHB_T) &&
                 ((H % EHB_T) == 0 || make_mask_map(&p.tmMaskTop, io.masks, items, H, W, H % EHB_T))) ? 1 : 0;
     p.dbgbuf = c->dbgbuf;
+    p.hostFlags = c->hostFlagsDev;
 
     cudaEvent_t* ev = nullptr;
     if (c->profiling && !capturing) {
@@ -717,6 +720,13 @@ int ehb_ctx_create(int device, ehb_ctx_t* out)
     CU(cudaMalloc((void**)&c->ctr, N_SCRATCH * sizeof(EhbCounters)));
     CU(cudaMemset(c->ctr, 0, N_SCRATCH * sizeof(EhbCounters)));
     CU(cudaMallocHost((void**)&c->ctrHost, N_SCRATCH * sizeof(EhbCounters)));
+    if (cudaHostAlloc((void**)&c->hostFlags, 16 * sizeof(unsigned), cudaHostAllocMapped) == cudaSuccess &&
+        cudaHostGetDevicePointer((void**)&c->hostFlagsDev, c->hostFlags, 0) == cudaSuccess) {
+        for (int i = 0; i < 16; i++) c->hostFlags[i] = 0u;
+    } else {
+        cudaGetLastError();
+        c->hostFlags = nullptr; c->hostFlagsDev = nullptr;
+    }
     for (int k = 0; k < N_SCRATCH; k++) c->sc[k].ctr = c->ctr + k;
     for (int k = 0; k < N_SLOTS; k++) {
         CU(cudaStreamCreateWithFlags(&c->slotStream[k], cudaStreamNonBlocking));
@@ -761,6 +771,7 @@ int ehb_ctx_destroy(ehb_ctx_t h)
     for (auto e : c->evPool) cudaEventDestroy(e);
     cudaFree(c->ctr);
     cudaFreeHost(c->ctrHost);
+    if (c->hostFlags) cudaFreeHost(c->hostFlags);
     delete c;
     return EHB_OK;
 }
@@ -862,6 +873,19 @@ int ehb_ctx_status(ehb_ctx_t h, unsigned* flags, long long* n_need_clip)
     if (flags) *flags = f;
     if (n_need_clip) *n_need_clip = nc;
     CU(cudaMemcpy(c->ctr, hc, sizeof hc, cudaMemcpyHostToDevice));
+    if (c->hostFlags) for (int i = 0; i < 3; i++) c->hostFlags[i] = 0u;
+    return EHB_OK;
+}
+
+int ehb_ctx_poll(ehb_ctx_t h, unsigned* flags)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || !flags) return fail(EHB_E_ARG, "null pointer argument");
+    unsigned f = 0;
+    if (c->hostFlags)
+        for (int i = 0; i < 3; i++)
+            if (*reinterpret_cast<volatile unsigned int*>(c->hostFlags + i)) f |= 1u << i;
+    *flags = f;
     return EHB_OK;
 }
 

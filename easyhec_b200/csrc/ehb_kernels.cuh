@@ -118,7 +118,19 @@ struct EhbParams {
     const uint32_t* refCnt;  // [items, ntiles]
     const unsigned long long* refTotal;   // [items]
     unsigned long long* dbgbuf;   // unused (kept for the developer ABI)
+    unsigned int* hostFlags;      // mapped pinned host memory: word b is set when flag bit b is raised (ehb_ctx_poll reads it
+                                  // without synchronising)
 };
+
+// Raise sticky status bits: in the pass's counters (read by ehb_ctx_status) and in host-visible memory (ehb_ctx_poll).
+__device__ __forceinline__ void ehb_raise(const EhbParams& p, unsigned bits)
+{
+    atomicOr(&p.ctr->flags, bits);
+    if (p.hostFlags) {
+        for (unsigned b = 0; b < 3; b++)
+            if (bits & (1u << b)) *reinterpret_cast<volatile unsigned int*>(p.hostFlags + b) = 1u;
+    }
+}
 
 #ifndef EHB_SMALL_AREA
 #define EHB_SMALL_AREA 96               // triangles whose clipped bbox has more candidate samples are deferred
@@ -254,7 +266,7 @@ __global__ void __launch_bounds__(256) ehb_k_table(const __grid_constant__ EhbRo
             const unsigned long long area = (unsigned long long)pl.w * (unsigned long long)pl.h;
             const unsigned long long off = atomicAdd(&p.ctr->planeCursor, area);
             if (off + area <= p.poolCap) pl.off = (long long)off;
-            else { pl.w = pl.h = 0; atomicOr(&p.ctr->flags, 1u); }
+            else { pl.w = pl.h = 0; ehb_raise(p, 1u); }
             p.plane[i] = pl;
         }
     }
@@ -634,7 +646,7 @@ __device__ __noinline__ void ehb_draw_serial(const EhbParams& p, const EhbRec& r
 __device__ __noinline__ void ehb_emit_clipped(const EhbRobot& rb, const EhbParams& p, int item, int l, int f, int qi)
 {
     atomicAdd(&p.ctr->nNeedClip, 1ull);
-    atomicOr(&p.ctr->flags, 2u);
+    ehb_raise(p, 2u);
     const EhbLink& lk = rb.link[l];
     const int4 id = __ldg(lk.faces + f);
     const EhbPlane pl = p.plane[(size_t)item * p.Lp + (p.Lp == 1 ? 0 : l)];
@@ -672,7 +684,7 @@ __device__ __noinline__ void ehb_emit_clipped(const EhbRobot& rb, const EhbParam
                 for (int ux = 0; ux < nux; ux++)
                     p.units[u0 + uy * nux + ux] = EhbUnit{k, (unsigned short)(ux * EHB_UNIT_W), (unsigned short)(uy * EHB_UNIT_H)};
         } else {
-            atomicOr(&p.ctr->flags, 4u);   // queues full: drawn here (slow but complete); its units are void
+            ehb_raise(p, 4u);   // queues full: drawn here (slow but complete); its units are void
             for (int u = 0; u < nu && (int)(uq + u) < p.unitCap; u++) p.units[u0 + u] = EhbUnit{0xFFFFFFFFu, 0, 0};
             ehb_draw_serial(p, rc);
         }
@@ -872,7 +884,7 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
                         }
                     rows = 0;
                 } else {
-                    atomicOr(&p.ctr->flags, 4u);   // queues full: this one is drawn inline (slow but complete); its units are void
+                    ehb_raise(p, 4u);   // queues full: this one is drawn inline (slow but complete); its units are void
                     for (int i = 0; i < nu && (int)(uq + i) < p.unitCap; i++) p.units[u0 + i] = EhbUnit{0xFFFFFFFFu, 0, 0};
                 }
             }

@@ -211,7 +211,7 @@ __device__ __forceinline__ void ehb_tile_round(const EhbRobot& rb, const EhbPara
         if (tid == 0 && sm.slab < 0) {
             const unsigned k = atomicAdd(&p.ctr->slabCursor, 1u);
             if (k < (unsigned)p.nSlabs) sm.slab = (int)k;
-            else atomicOr(&p.ctr->flags, 1u);              // pool exhausted: flagged, the host grows it and reruns the pass
+            else ehb_raise(p, 1u);              // pool exhausted: flagged, the host grows it and reruns the pass
         }
         __syncthreads();
         EHB_STAT_ADD(12, 1);

@@ -52,7 +52,7 @@ def shard_candidates(n: int, rank: int, world: int):
 
 
 def score_candidates(ctx, mesh_ids, kin, links, qposes, cam_poses, K, H, W, valid=None, pad_left=0, pad_right=0,
-                     device_fk=True, group=None, robot=None):
+                     device_fk=True, group=None, robot=None, check=True):
     """Variance score of every candidate (space_explorer.py:163-164: ``torch.var(masks, dim=0).sum()``, unbiased) as a
     (Q,) float64 tensor on the context's device; candidates with ``valid[q] == False`` score 0.
 
@@ -72,13 +72,22 @@ def score_candidates(ctx, mesh_ids, kin, links, qposes, cam_poses, K, H, W, vali
     mine = q[first:first + count]
     if count == 0:
         local = torch.zeros(0, dtype=torch.float64, device=ctx.device)
-    elif device_fk:
-        robot = robot or ctx.register_robot(kin)
-        mvp = ctx.explore_fk_mvp(robot, mine.to(ctx.device).contiguous(), cam_poses, K, H, W, links)
-        local = ctx.explore_scores(mesh_ids, mvp, H, W)
     else:
-        mvp = candidate_mvps(kin, links, mine, cam_poses, K, H, W).to(ctx.device)
+        if device_fk:
+            robot = robot or ctx.register_robot(kin)
+            mvp = ctx.explore_fk_mvp(robot, mine.to(ctx.device).contiguous(), cam_poses, K, H, W, links)
+        else:
+            mvp = candidate_mvps(kin, links, mine, cam_poses, K, H, W).to(ctx.device)
         local = ctx.explore_scores(mesh_ids, mvp, H, W)
+        if check and hasattr(ctx, "status"):
+            # the scores are about to be read by the host anyway: look at the sticky flags once per batch; an overflowed
+            # scratch pool (incomplete renders) is grown and the batch scored again
+            for _ in range(12):
+                flags, _ = ctx.status()
+                if not flags & 1:
+                    break
+                ctx.grow_scratch()
+                local = ctx.explore_scores(mesh_ids, mvp, H, W)
     if world > 1:
         per = -(-Q // world)                               # equal-sized slots for the all-gather, trimmed afterwards
         buf = torch.zeros(per, dtype=torch.float64, device=ctx.device)

@@ -37,8 +37,26 @@ class _FusedViews(torch.autograd.Function):
     def forward(ctx, mvp, ref, solver, want_masks):
         r = solver.renderer
         need_grad = mvp.requires_grad
-        masks, loss_b, g_mvp = r.ctx.render_views_fused(solver.mesh_ids, mvp.detach().contiguous().float(), ref,
-                                                        r.H, r.W, backward=need_grad, want_masks=want_masks)
+        mvp_c = mvp.detach().contiguous().float()
+        # Scratch overflow (EHB_FLAG_POOL_OVERFLOW) makes a launch's results incomplete.  The first call for a batch shape
+        # synchronises, grows the scratch and reruns until the launch is clean; later calls (same views, slowly moving pose)
+        # only look at the host-visible flag word -- no synchronisation -- and raise if an earlier launch overflowed.
+        shape = (tuple(mvp_c.shape), r.H, r.W)
+        if solver._sized_for != shape:
+            for _ in range(12):
+                masks, loss_b, g_mvp = r.ctx.render_views_fused(solver.mesh_ids, mvp_c, ref, r.H, r.W, backward=need_grad,
+                                                                want_masks=want_masks)
+                flags, _ = r.ctx.status()
+                if not flags & 1:
+                    break
+                r.ctx.grow_scratch()
+            else:
+                raise EhbError("the rasterizer's scratch pools kept overflowing")
+            solver._sized_for = shape
+        else:
+            r.ctx.check("fused render")
+            masks, loss_b, g_mvp = r.ctx.render_views_fused(solver.mesh_ids, mvp_c, ref, r.H, r.W, backward=need_grad,
+                                                            want_masks=want_masks)
         ctx.g_mvp = g_mvp
         loss = (loss_b.sum() / mvp.shape[0]).to(torch.float32)
         if masks is None:
@@ -78,6 +96,7 @@ class RBSolver(nn.Module):
         self.register_buffer("history_ops", torch.zeros(10000, 6, device=device))
         self._put_id = 0
         self._ref, self._ref_key = None, None
+        self._sized_for = None
 
     def _reference(self, masks_ref):
         """The batch's reference masks as the fused kernels want them.  The trainer hands over the SAME masks every

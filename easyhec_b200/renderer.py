@@ -99,6 +99,7 @@ class B200Renderer:
 
     # -- the operator ------------------------------------------------------------------------------------
     def _render(self, verts, faces, mvp, anti_aliasing):
+        self.ctx.check("render_mask")        # an earlier launch overflowed its scratch: raise instead of returning garbage
         mesh_id = self._mesh_for(verts, faces)
         if anti_aliasing:
             return _RenderMaskAA.apply(mvp, verts, self, mesh_id)

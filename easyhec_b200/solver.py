@@ -93,45 +93,56 @@ class PoseSolver:
             torch.distributed.all_reduce(self.g7, group=self.group)
         c.adam_step(self.dof, self.g7, self.state, self.lr, self.betas, self.eps, self.wd, hist=self.hist, recv=fusedx)
 
-    def _check_flags(self):
+    def _overflowed(self) -> bool:
+        """Synchronises; True when a launch since the last look overflowed a scratch pool on ANY rank (the decision to
+        redo iterations must be the same everywhere, or the ranks' exchanges would fall out of step)."""
         flags, _ = self.ctx.status()
-        if flags & 1:
-            self.ctx.grow_scratch()
-            return False
-        return True
+        bad = bool(flags & 1)
+        if self.world > 1:
+            t = torch.tensor([1.0 if bad else 0.0], device=self.device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX, group=self.group)
+            bad = t.item() > 0
+        return bad
 
-    def step(self, n: int = 1):
-        """Run n Adam iterations (no host synchronisation inside)."""
-        if self.iterations == 0:   # first iteration eagerly: sizes scratch, validates capacity
-            while True:
-                snap = (self.dof.clone(), self.state.clone())
+    def _capture(self):
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            with torch.cuda.graph(g, stream=s):     # capture does not execute: dof / state are untouched
                 self._iteration()
-                if self._check_flags():
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        self._graph = g
+
+    def step(self, n: int = 1, check_every: int = 64):
+        """Run n Adam iterations.  Iterations are replayed in chunks of `check_every` with no host synchronisation inside
+        a chunk; after each chunk the sticky status flags are read once.  A scratch-pool overflow (the silhouette grew
+        beyond what was reserved) restores the chunk's starting state, grows the scratch, re-captures the graph and
+        runs the chunk again -- on every rank alike."""
+        done = 0
+        while done < n:
+            m = min(check_every, n - done) if self.iterations > 0 else 1     # the very first iteration sizes the scratch
+            snap = (self.dof.clone(), self.state.clone())
+            for _attempt in range(12):
+                if self.use_graph and self.iterations > 0 and self._graph is None:
+                    self._capture()
+                for _ in range(m):
+                    if self._graph is not None:
+                        self._graph.replay()
+                    else:
+                        self._iteration()
+                if not self._overflowed():
                     break
                 self.dof.copy_(snap[0]); self.state.copy_(snap[1])
-            self.iterations += 1
-            n -= 1
-        if n <= 0:
-            return
-        if self.use_graph and self._graph is None:
-            torch.cuda.synchronize(self.device)
-            g = torch.cuda.CUDAGraph()
-            s = torch.cuda.Stream(self.device)
-            s.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(s):
-                snap = (self.dof.clone(), self.state.clone(), None if self.hist is None else self.hist.clone())
-                with torch.cuda.graph(g, stream=s):
-                    self._iteration()
-                # capture does not execute; nothing to restore, but keep the snapshot semantics explicit
-                del snap
-            torch.cuda.current_stream(self.device).wait_stream(s)
-            self._graph = g
-        for _ in range(n):
-            if self._graph is not None:
-                self._graph.replay()
+                self.ctx.grow_scratch()
+                self._graph = None                  # scratch buffers move when they grow: the captured pointers are stale
+                F = sum(self.ctx.mesh_info(i)[1] for i in self.mesh_ids)
+                self.ctx.reserve(self.B, self.L, F, self.H, self.W)
             else:
-                self._iteration()
-        self.iterations += n
+                raise EhbError("the rasterizer's scratch pools kept overflowing")
+            self.iterations += m
+            done += m
 
     @property
     def loss(self) -> torch.Tensor:

@@ -90,6 +90,10 @@ EHB_API int ehb_ctx_debug_counters(ehb_ctx_t ctx, unsigned long long* out16, int
 EHB_API int ehb_ctx_debug_buffer(ehb_ctx_t ctx, unsigned long long* out, int n_words);
 /* Synchronises the device, returns and clears the sticky flags, reports the triangles that went through the clipper. */
 EHB_API int ehb_ctx_status(ehb_ctx_t ctx, unsigned* flags, long long* n_need_clip);
+/* The same sticky flags WITHOUT synchronising: the kernels also set them in host-visible (mapped) memory, so a caller can
+ * look between launches or graph replays at no cost.  A flag raised by work that is still running shows up on a later
+ * poll; ehb_ctx_status clears what both report. */
+EHB_API int ehb_ctx_poll(ehb_ctx_t ctx, unsigned* flags);
 
 /* Register a mesh once: verts_host f32[V*3], faces_host i32[F*3].  Builds the padded float4 / int4 device
  * buffers and the cached edge adjacency (replaces the per-call topology hash of dr.antialias). */
