@@ -995,9 +995,14 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
 __global__ void __launch_bounds__(256, EHB_BMIN_BLOCKS) ehb_k_raster_big(const __grid_constant__ EhbParams p)
 {
     ehb_pdl_enter();
-    __shared__ __align__(16) uint32_t s_blk[8][EHB_BLK_WORDS];
+    __shared__ __align__(128) uint32_t s_blk[8][EHB_BLK_WORDS];
+    __shared__ __align__(8) uint64_t s_bar[8];           // one mbarrier per warp: completion of its bulk copies
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nUnitBlocks = (int)gridDim.x;
+    if (lane == 0) ehb_mbar_init(&s_bar[warp], 1);
+    ehb_fence_mbar_init();
+    __syncwarp();
+    uint32_t phase = 0;
     // units of all sub-queues as one list: lane s holds the (inclusive) prefix of the sub-queue sizes
     int qn = min((int)p.ctr->q[lane].nUnits, p.unitCap), qinc = qn;
 #pragma unroll
@@ -1008,7 +1013,7 @@ __global__ void __launch_bounds__(256, EHB_BMIN_BLOCKS) ehb_k_raster_big(const _
     const int n = __shfl_sync(0xffffffffu, qinc, 31);
     const float xs = p.xs, xo = p.xo, ys = p.ys, yo = p.yo;
     uint32_t* sb = s_blk[warp];
-    for (int u = blockIdx.x * 8 + warp; u < n; u += nUnitBlocks * 8) {
+    auto unit_at = [&](int u) -> EhbUnit {
         int sq = 0;   // sub-queue of unit u = number of sub-queues whose inclusive prefix is <= u
 #pragma unroll
         for (int st = 16; st >= 1; st >>= 1) {
@@ -1017,21 +1022,36 @@ __global__ void __launch_bounds__(256, EHB_BMIN_BLOCKS) ehb_k_raster_big(const _
         }
         sq = min(sq, 31);
         const int before = __shfl_sync(0xffffffffu, qinc - qn, sq);
-        const EhbUnit un = p.units[(size_t)sq * p.unitCap + (u - before)];
-        if (un.rec == 0xFFFFFFFFu) continue;
-        __syncwarp();
-        if (un.rec & 0x80000000u) {
+        return p.units[(size_t)sq * p.unitCap + (u - before)];
+    };
+    // a block of a warp's shared memory <- global memory as ONE bulk asynchronous copy (UBLKCP) that completes on the
+    // warp's mbarrier: no register staging, one instruction instead of a load + store per word
+    auto fetch = [&](const void* src, uint32_t bytes) {
+        __syncwarp();                          // every lane is done reading the previous contents
+        if (lane == 0) {
+            ehb_fence_proxy_async();           // ... and those reads are ordered before the asynchronous write
+            ehb_mbar_arrive_expect_tx(&s_bar[warp], bytes);
+            ehb_bulk_g2s(sb, src, bytes, &s_bar[warp]);
+        }
+        ehb_mbar_wait(&s_bar[warp], phase);
+        phase ^= 1u;
+    };
+    const int u0 = blockIdx.x * 8 + warp, stride = nUnitBlocks * 8;
+    EhbUnit un = u0 < n ? unit_at(u0) : EhbUnit{0xFFFFFFFFu, 0, 0};
+    for (int u = u0; u < n; u += stride) {
+        // the next unit's descriptor is fetched while this one is drawn
+        const EhbUnit cur = un;
+        if (u + stride < n) un = unit_at(u + stride);
+        if (cur.rec == 0xFFFFFFFFu) continue;
+        if (cur.rec & 0x80000000u) {
             // rows [32 * dx0, 32 * (dx0 + dy0)) of a parked batch: the same row-group loop as k_raster
-            const uint32_t* blk = p.batchBlk + (size_t)(un.rec & 0x7FFFFFFFu) * EHB_BLK_WORDS;
-#pragma unroll
-            for (int k = 0; k < EHB_BLK_WORDS / 32; k++) sb[k * 32 + lane] = __ldcg(blk + k * 32 + lane);
-            __syncwarp();
+            fetch(p.batchBlk + (size_t)(cur.rec & 0x7FFFFFFFu) * EHB_BLK_WORDS, EHB_BLK_WORDS * 4);
             const int* off = reinterpret_cast<const int*>(sb + 1024);
             const int nRows = off[32];
             const bool anyWide = off[33] != 0;
             const EhbRecSoA recs{sb};
-            for (int gi = 0; gi < (int)un.dy0; gi++) {
-                const int r0 = ((int)un.dx0 + gi) * 32;
+            for (int gi = 0; gi < (int)cur.dy0; gi++) {
+                const int r0 = ((int)cur.dx0 + gi) * 32;
                 if (r0 >= nRows) break;
                 const int r = r0 + lane;
                 int t = -1, dy = 0;
@@ -1050,15 +1070,14 @@ __global__ void __launch_bounds__(256, EHB_BMIN_BLOCKS) ehb_k_raster_big(const _
             continue;
         }
         // a 64 x 32 window of one deferred triangle
-        EhbRec* rc = reinterpret_cast<EhbRec*>(sb);
-        sb[lane] = reinterpret_cast<const uint32_t*>(p.bigRec + un.rec)[lane];   // 128 B
-        __syncwarp();
+        fetch(p.bigRec + cur.rec, (uint32_t)sizeof(EhbRec));
+        const EhbRec* rc = reinterpret_cast<const EhbRec*>(sb);
         const int ext = max(max(abs(rc->ex[0]), abs(rc->ex[1])), max(max(abs(rc->ex[2]), abs(rc->ey[0])), max(abs(rc->ey[1]), abs(rc->ey[2]))));
-        const int dy = un.dy0 + lane;
+        const int dy = cur.dy0 + lane;
         const int t = dy < rc->h ? 0 : -1;
         const EhbRecAoS rv{reinterpret_cast<const uint32_t*>(rc)};
-        if (ext >= 32768) ehb_rows_group<long long, double, EhbRecAoS>(rv, t, dy, lane, p.pool, xs, xo, ys, yo, un.dx0, un.dx0 + EHB_UNIT_W - 1);
-        else ehb_rows_group<int, float, EhbRecAoS>(rv, t, dy, lane, p.pool, xs, xo, ys, yo, un.dx0, un.dx0 + EHB_UNIT_W - 1);
+        if (ext >= 32768) ehb_rows_group<long long, double, EhbRecAoS>(rv, t, dy, lane, p.pool, xs, xo, ys, yo, cur.dx0, cur.dx0 + EHB_UNIT_W - 1);
+        else ehb_rows_group<int, float, EhbRecAoS>(rv, t, dy, lane, p.pool, xs, xo, ys, yo, cur.dx0, cur.dx0 + EHB_UNIT_W - 1);
     }
 }
 
