@@ -89,6 +89,10 @@ _PROTOS = {
     "ehb_solver_step_end": (C.c_int, [C.c_void_p, C.c_int]),
     "ehb_solver_step_begin_ref": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                             C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "ehb_step_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ehb_slot_stream": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "ehb_slots_fork": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ehb_slots_join": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ehb_comm_local_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ehb_comm_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ehb_allreduce7": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -135,6 +139,12 @@ def _dev_check(t, dtype, device, name):
         raise EhbError("%s must have dtype %s, got %s" % (name, dtype, t.dtype))
     if not t.is_contiguous():
         raise EhbError("%s must be contiguous" % name)
+
+
+class StepIO(C.Structure):
+    """ehb_step_io_t (include/easyhec_b200.h)"""
+    _fields_ = [(n, C.c_void_p) for n in ("mvp_host", "mvp_dev", "masks_dev", "loss_host", "g_mvp_host", "dof_dev", "K_dev",
+                                          "link_poses_dev", "out7_dev", "out7_host")]
 
 
 class RefMasks:
@@ -497,6 +507,39 @@ class Context:
             raise EhbError("registered reference has %d views, the step %d" % (len(ref), B))
         _check(lib().ehb_solver_step_begin_ref(self._h, slot, ids, L, B, _ptr(mvp_host), ref.ref_id, ref.first, H, W,
                                                _ptr(loss_host), _ptr(g_mvp_host)))
+
+    def step_begin(self, slot, mesh_ids, ref: RefMasks, H, W, mvp, masks=None, loss_host=None, g_mvp_host=None, dof=None,
+                   K=None, link_poses=None, out7=None, out7_host=None):
+        """General asynchronous step on slot 0..3 (ehb_step_begin): mvp (B,L,4,4) f32 is a pinned host tensor (copied in) or
+        a device tensor; optional outputs masks (device), loss_host / g_mvp_host (pinned), and with dof / K / link_poses
+        (device) the pose chain's out7 on the device (out7) and / or the host (out7_host, pinned)."""
+        B, L = mvp.shape[0], mvp.shape[1]
+        ids = (C.c_int * L)(*mesh_ids)
+        if len(ref) != B or (ref.H, ref.W) != (H, W):
+            raise EhbError("registered reference does not match the step (%d views of %dx%d)" % (len(ref), ref.H, ref.W))
+        for t in (mvp if not mvp.is_cuda else None, loss_host, g_mvp_host, out7_host):
+            if t is not None and (not t.is_pinned() or not t.is_contiguous()):
+                raise EhbError("host buffers of an asynchronous step must be pinned and contiguous")
+        io = StepIO()
+        io.mvp_host, io.mvp_dev = (None, mvp.data_ptr()) if mvp.is_cuda else (mvp.data_ptr(), None)
+        for name, t in (("masks_dev", masks), ("loss_host", loss_host), ("g_mvp_host", g_mvp_host), ("dof_dev", dof), ("K_dev", K),
+                        ("link_poses_dev", link_poses), ("out7_dev", out7), ("out7_host", out7_host)):
+            setattr(io, name, None if t is None else t.data_ptr())
+        _check(lib().ehb_step_begin(self._h, slot, ids, L, B, ref.ref_id, ref.first, H, W, C.byref(io)))
+
+    def slot_stream(self, slot):
+        """The slot's CUDA stream as a torch.cuda.ExternalStream."""
+        h = C.c_void_p()
+        _check(lib().ehb_slot_stream(self._h, slot, C.byref(h)))
+        return torch.cuda.ExternalStream(h.value, device=self.device)
+
+    def slots_fork(self):
+        """Every slot stream waits for the work enqueued so far on the current stream."""
+        _check(lib().ehb_slots_fork(self._h, _stream(self.device)))
+
+    def slots_join(self):
+        """The current stream waits for everything enqueued on the slot streams."""
+        _check(lib().ehb_slots_join(self._h, _stream(self.device)))
 
     def solver_step_end(self, slot):
         _check(lib().ehb_solver_step_end(self._h, slot))

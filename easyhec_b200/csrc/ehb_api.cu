@@ -1429,6 +1429,76 @@ int ehb_solver_step_begin_ref(ehb_ctx_t h, int slot, const int* mesh_ids, int L,
     return EHB_OK;
 }
 
+int ehb_step_begin(ehb_ctx_t h, int slot, const int* mesh_ids, int L, int B, int ref_id, int first_view, int H, int W,
+                   const ehb_step_io_t* sio)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || slot < 0 || slot >= N_SLOTS || !mesh_ids || !sio || (!sio->mvp_host && !sio->mvp_dev)) return fail(EHB_E_ARG, "bad step_begin arguments");
+    if (B < 1 || L < 1) return fail(EHB_E_ARG, "empty batch");
+    const bool pose = sio->out7_dev || sio->out7_host;
+    if (pose && (!sio->dof_dev || !sio->K_dev || !sio->link_poses_dev)) return fail(EHB_E_ARG, "the pose chain needs dof_dev, K_dev and link_poses_dev");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = c->slotStream[slot];
+    int r;
+    const size_t nm = (size_t)B * L * 16, no = (size_t)B + nm + 8;
+    if ((r = c->slotOut[slot].ensure(no, false))) return r;
+    Io io;
+    if ((r = ref_io(c, ref_id, first_view, B, H, W, io))) return r;
+    const float* mvp = sio->mvp_dev;
+    if (!mvp) {
+        if ((r = c->slotMvp[slot].ensure(nm, false))) return r;
+        CU(cudaMemcpyAsync(c->slotMvp[slot].p, sio->mvp_host, nm * sizeof(float), cudaMemcpyHostToDevice, st));
+        mvp = c->slotMvp[slot].p;
+    }
+    io.masks = sio->masks_dev; io.loss = c->slotOut[slot].p; io.gmvp = c->slotOut[slot].p + B;
+    io.do_bwd = 1; io.clamp = 1; io.invB = 1.0f / (float)B;
+    r = run_pass(c, c->sc[MAX_PIPES + slot], mesh_ids, L, B, mvp, H, W, EHB_MODE_FUSED, io, st);
+    if (r) return r;
+    if (pose) {
+        float* o7 = sio->out7_dev ? sio->out7_dev : reinterpret_cast<float*>(c->slotOut[slot].p + B + nm);
+        CU(launch(ehb_k_pose_backward, dim3(1), dim3(256), 0, st, true, sio->dof_dev, sio->K_dev, sio->link_poses_dev,
+                  (const double*)(c->slotOut[slot].p + B), (const double*)c->slotOut[slot].p, B, L, H, W, 1.0, 1.0 / (double)B, o7,
+                  c->comm, 0));
+        c->launches += 1;
+        if (sio->out7_host) CU(cudaMemcpyAsync(sio->out7_host, o7, 7 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    if (sio->loss_host) CU(cudaMemcpyAsync(sio->loss_host, c->slotOut[slot].p, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (sio->g_mvp_host) CU(cudaMemcpyAsync(sio->g_mvp_host, c->slotOut[slot].p + B, nm * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->ctrHost + MAX_PIPES + slot, c->ctr + MAX_PIPES + slot, sizeof(EhbCounters), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(c->slotDone[slot], st));
+    return EHB_OK;
+}
+
+int ehb_slot_stream(ehb_ctx_t h, int slot, void** stream)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || slot < 0 || slot >= N_SLOTS || !stream) return fail(EHB_E_ARG, "bad slot");
+    *stream = (void*)c->slotStream[slot];
+    return EHB_OK;
+}
+
+int ehb_slots_fork(ehb_ctx_t h, void* stream)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c) return fail(EHB_E_ARG, "null context");
+    DeviceGuard guard(c->device);
+    CU(cudaEventRecord(c->evFork, (cudaStream_t)stream));
+    for (int k = 0; k < N_SLOTS; k++) CU(cudaStreamWaitEvent(c->slotStream[k], c->evFork, 0));
+    return EHB_OK;
+}
+
+int ehb_slots_join(ehb_ctx_t h, void* stream)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c) return fail(EHB_E_ARG, "null context");
+    DeviceGuard guard(c->device);
+    for (int k = 0; k < N_SLOTS; k++) {
+        CU(cudaEventRecord(c->slotDone[k], c->slotStream[k]));
+        CU(cudaStreamWaitEvent((cudaStream_t)stream, c->slotDone[k], 0));
+    }
+    return EHB_OK;
+}
+
 int ehb_solver_step_end(ehb_ctx_t h, int slot)
 {
     Ctx* c = (Ctx*)h;

@@ -207,6 +207,32 @@ EHB_API int ehb_solver_step_end(ehb_ctx_t ctx, int slot);
 EHB_API int ehb_solver_step_begin_ref(ehb_ctx_t ctx, int slot, const int* mesh_ids, int L, int B, const float* mvp_host,
                               int ref_id, int first_view, int H, int W, double* loss_host, double* g_mvp_host);
 
+/* General asynchronous step on a slot (0..3) against registered reference masks: independent batches -- the views of
+ * several solves, exploration rounds, ring slots of a benchmark -- run concurrently, each on its slot's stream and scratch.
+ * The matrices come from the host (copied in) or are already on the device; optional outputs: the rendered masks (device),
+ * loss / d loss/d mvp (host), and -- when dof_dev, K_dev, link_poses_dev are given -- the pose chain's out7 = { d loss/d dof
+ * [6], mean loss } of the step (rb_solver.py:52-72 backward) on the device and / or the host.  ehb_solver_step_end(slot)
+ * waits for the slot's last step and reports a scratch overflow; ehb_slots_fork / _join order all slot streams after / before
+ * a caller's stream (for timing or for handing results on without a host wait). */
+typedef struct ehb_step_io {
+    const float* mvp_host;        /* f32[B*L*16], pinned host memory ... */
+    const float* mvp_dev;         /* ... or on the device (one of the two) */
+    float* masks_dev;             /* optional f32[B*H*W] */
+    double* loss_host;            /* optional f64[B] */
+    double* g_mvp_host;           /* optional f64[B*L*16] */
+    const float* dof_dev;         /* optional pose chain: f32[6] */
+    const float* K_dev;           /* f32[9] */
+    const float* link_poses_dev;  /* f32[B*L*16] */
+    float* out7_dev;              /* optional f32[7] */
+    float* out7_host;             /* optional f32[7], pinned */
+} ehb_step_io_t;
+EHB_API int ehb_step_begin(ehb_ctx_t ctx, int slot, const int* mesh_ids, int L, int B, int ref_id, int first_view, int H, int W,
+                   const ehb_step_io_t* io);
+/* the CUDA stream (cudaStream_t) of a slot, for callers that order their own work after a slot's step */
+EHB_API int ehb_slot_stream(ehb_ctx_t ctx, int slot, void** stream);
+EHB_API int ehb_slots_fork(ehb_ctx_t ctx, void* stream);
+EHB_API int ehb_slots_join(ehb_ctx_t ctx, void* stream);
+
 /* One-shot all-reduce (sum) of the 7 floats { d loss/d dof, loss } over NVLink peer memory, for view sharding across
  * the GPUs of one box -- the exchange DDP performs for the reference's 6-float parameter (easyhec/trainer/base.py:349).
  *   ehb_comm_local_handle: allocates this rank's mailbox, returns its 64-byte CUDA IPC handle
