@@ -12,10 +12,13 @@ rnd = sys.argv[2] if len(sys.argv) > 2 else "r01"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 dst = os.path.join(ROOT, "profiles")
 os.makedirs(dst, exist_ok=True)
-KERNELS = ["table", "front", "raster", "raster_big", "windows", "compose", "pairgrad"]
+KERNELS = ["table", "front", "raster", "raster_big", "tiles"]
 
 for a, b in [("bench.json", "bench_%s.json"), ("bench_reference.json", "bench_%s_reference.json"),
-             ("configs.jsonl", "configs_%s.jsonl"), ("launches.csv", "launches_%s.csv"), ("pipes.txt", "pipelines_%s.txt")]:
+             ("bench_inview.json", "bench_%s_inview.json"), ("configs.jsonl", "configs_%s.jsonl"), ("launches.csv", "launches_%s.csv"),
+             ("pipes.txt", "pipelines_%s.txt"), ("pytest_gpu.log", "pytest_gpu_%s.log"),
+             ("memcheck_smoke.log", "sanitizer_%s_memcheck_smoke.log"), ("racecheck_smoke.log", "sanitizer_%s_racecheck_smoke.log"),
+             ("memcheck_fused.log", "sanitizer_%s_memcheck_fused.log")]:
     if os.path.exists(os.path.join(src, a)):
         shutil.copy(os.path.join(src, a), os.path.join(dst, b % rnd))
 
@@ -44,16 +47,15 @@ with open(os.path.join(dst, "ncu_%s_summary.txt" % rnd), "w") as f:
             u = units[key].lower()
             return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
         traffic[k if k != "raster_big" else "raster_big"] = int(to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"))
-# bench.py looks the dominant stage up by its stage name: the raster stage = k_raster + k_raster_big, tiles = the three image-space kernels
+# bench.py looks the dominant stage up by its stage name: the raster stage = k_raster + k_raster_big
 traffic["raster"] = traffic.get("raster", 0) + traffic.pop("raster_big", 0)
-traffic["tiles"] = sum(traffic.pop(k, 0) for k in ("windows", "compose", "pairgrad"))
 json.dump(traffic, open(os.path.join(dst, "traffic.json"), "w"), indent=1)
 with open(os.path.join(dst, "ncu_%s_source_lines.txt" % rnd), "w") as f:
-    for k in ["raster", "raster_big", "windows", "compose", "pairgrad"]:
+    for k in ["raster", "raster_big", "tiles", "front", "table"]:
         rep = os.path.join(src, k + ".ncu-rep")
         if not os.path.exists(rep):
             continue
         f.write("# ehb_k_%s: instructions and stall samples by function, then the top source lines\n" % k)
         f.write(run([sys.executable, os.path.join(ROOT, "tools", "ncu_regions.py"), rep]))
-        f.write(run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, "ehb_k_" + k + "$", "0", "25"]) + "\n")
+        f.write(run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, "ehb_k_" + k, "0", "25"]) + "\n")
 print(open(os.path.join(dst, "traffic.json")).read())
