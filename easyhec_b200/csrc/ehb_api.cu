@@ -619,8 +619,9 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
     // spare CTAs of the raster launch finish the tiles no link touches; with registered reference masks (or none) that is
     // only the zero fill of the masks -- nothing to do at all when no masks are wanted
     const bool legacyStream = mode == EHB_MODE_FUSED && (io.ref || io.ref_u8);
+    p.prezero = (!unionMode && mode != EHB_MODE_AA_BWD && !legacyStream && io.masks) ? 1 : 0;
     const int streamBlocks = (unionMode || mode == EHB_MODE_AA_BWD || (!legacyStream && !io.masks)) ? 0
-                             : c->nSM * ((legacyStream || !p.useTma) ? tune_int("EHB_STREAM_MULT", 2) : 1);
+                             : legacyStream ? c->nSM * tune_int("EHB_STREAM_MULT", 2) : c->nSM;
     const long long tickets = ((long long)chunks * items + EHB_RBATCH - 1) / EHB_RBATCH;
     long long rasterBlocks = (tickets + EHB_RWARPS - 1) / EHB_RWARPS;
 #ifdef EHB_RPERSIST
@@ -826,7 +827,7 @@ int ehb_ctx_debug_buffer(ehb_ctx_t h, unsigned long long* out, int n_words)
     Ctx* c = (Ctx*)h;
     if (!c) return fail(EHB_E_ARG, "null context");
     DeviceGuard guard(c->device);
-    const size_t words = (size_t)c->nSM * 8 * 5;
+    const size_t words = (size_t)6 * EHB_TL_N * 2;   // EHB_TIMELINE builds: six regions of (start, end | smid) entries
     if (!c->dbgbuf) { CU(cudaMalloc((void**)&c->dbgbuf, words * 8)); CU(cudaMemset(c->dbgbuf, 0, words * 8)); return EHB_OK; }
     CU(cudaDeviceSynchronize());
     if (out && n_words > 0) CU(cudaMemcpy(out, c->dbgbuf, std::min((size_t)n_words, words) * 8, cudaMemcpyDeviceToHost));

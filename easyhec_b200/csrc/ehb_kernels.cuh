@@ -63,7 +63,8 @@ struct __align__(128) EhbCounters {
         unsigned int nBigRec;    // deferred (not small) triangles: records parked in global memory ...
         unsigned int nUnits;     // ... and cut into bounded units that k_raster_big spreads over the whole chip
         unsigned int nBatchBlk;  // batches with many rows: records parked, the rows beyond the inline share become units too
-        unsigned int pad[29];
+        unsigned int take;       // k_raster_big: units of this sub-queue handed out so far
+        unsigned int pad[28];
     } q[32];
     // pair pool of the image-space stage: slabs handed to the rare tile whose pairs do not fit shared memory
     unsigned int slabCursor;
@@ -79,6 +80,7 @@ struct EhbParams {
     // top of the image get their own, shorter box that starts at image row 0
     CUtensorMap tmMask, tmMaskTop;
     int useTma;
+    int prezero;             // the raster launch's spare CTAs zero the whole mask tensor: tiles without coverage need no store
     int H, W, ntx, nty, ntiles;
     int items, L, Lp, Ftot, Vtot;   // Lp = planes per item: L (per-link visibility) or 1 (packed robot)
     int hlo, hhi;
@@ -131,6 +133,21 @@ __device__ __forceinline__ void ehb_raise(const EhbParams& p, unsigned bits)
             if (bits & (1u << b)) *reinterpret_cast<volatile unsigned int*>(p.hostFlags + b) = 1u;
     }
 }
+
+// EHB_TIMELINE builds (developer tool, tools/timeline.py): start / end of every warp or CTA of a pass on the global timer,
+// region k of the debug buffer (ehb_ctx_debug_buffer): 0 table, 1 front, 2 raster (per warp), 3 raster_big (per warp),
+// 4 tiles (per CTA), 5 raster's stream CTAs (per warp)
+#define EHB_TL_N 16384
+#ifdef EHB_TIMELINE
+__device__ __forceinline__ unsigned long long ehb_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned ehb_smid() { unsigned s; asm("mov.u32 %0, %%smid;" : "=r"(s)); return s; }
+#define EHB_TL_START(var) const unsigned long long var = ehb_gtime()
+#define EHB_TL_STOP(p, k, idx, var) do { if ((p).dbgbuf && (unsigned)(idx) < EHB_TL_N) { (p).dbgbuf[((size_t)(k) * EHB_TL_N + (idx)) * 2] = (var); \
+    (p).dbgbuf[((size_t)(k) * EHB_TL_N + (idx)) * 2 + 1] = (ehb_gtime() << 8) | ehb_smid(); } } while (0)
+#else
+#define EHB_TL_START(var)
+#define EHB_TL_STOP(p, k, idx, var)
+#endif
 
 #ifndef EHB_SMALL_AREA
 #define EHB_SMALL_AREA 96               // triangles whose clipped bbox has more candidate samples are deferred
@@ -186,6 +203,7 @@ __global__ void __launch_bounds__(256) ehb_k_table(const __grid_constant__ EhbRo
                                                    const __grid_constant__ EhbParams p)
 {
     ehb_pdl_enter();
+    EHB_TL_START(tl0);
     const int lane = threadIdx.x & 31;
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -194,7 +212,7 @@ __global__ void __launch_bounds__(256) ehb_k_table(const __grid_constant__ EhbRo
         p.ctr->slabCursor = 0u;
     }
     if (blockIdx.x == 0 && threadIdx.x < EHB_NQ) {
-        p.ctr->q[threadIdx.x].nBigRec = 0u; p.ctr->q[threadIdx.x].nUnits = 0u; p.ctr->q[threadIdx.x].nBatchBlk = 0u;
+        p.ctr->q[threadIdx.x].nBigRec = 0u; p.ctr->q[threadIdx.x].nUnits = 0u; p.ctr->q[threadIdx.x].nBatchBlk = 0u; p.ctr->q[threadIdx.x].take = 0u;
     }
     // outputs that the later kernels accumulate into
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.items; i += gridDim.x * blockDim.x) {
@@ -252,7 +270,7 @@ __global__ void __launch_bounds__(256) ehb_k_table(const __grid_constant__ EhbRo
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(&p.ctr->vertexDone, 1u) == gridDim.x - 1u;
     __syncthreads();
-    if (!s_last) return;
+    if (!s_last) { if (threadIdx.x == 0) EHB_TL_STOP(p, 0, blockIdx.x, tl0); return; }
     __threadfence();
     if (threadIdx.x == 0) { p.ctr->vertexDone = 0u; p.ctr->planeCursor = 0ull; }
     __syncthreads();
@@ -270,6 +288,7 @@ __global__ void __launch_bounds__(256) ehb_k_table(const __grid_constant__ EhbRo
             p.plane[i] = pl;
         }
     }
+    if (threadIdx.x == 0) EHB_TL_STOP(p, 0, blockIdx.x, tl0);
 }
 
 // ------------------------------------------------------------------------------------------------ empty tiles
@@ -361,6 +380,7 @@ __global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRo
                                                    const __grid_constant__ EhbParams p, int vchunks, int clearBlocks)
 {
     ehb_pdl_enter();
+    EHB_TL_START(tl0);
     const int vertexBlocks = vchunks * p.items;
     if ((int)blockIdx.x < vertexBlocks) {
         const int item = blockIdx.x / vchunks;
@@ -377,6 +397,7 @@ __global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRo
         }
         p.vclip[(size_t)item * p.Vtot + g] = make_float4(c[0], c[1], c[2], c[3]);
         p.vsnap[(size_t)item * p.Vtot + g] = sn;
+        if (threadIdx.x == 0) EHB_TL_STOP(p, 1, blockIdx.x, tl0);
         return;
     }
     const int cb = (int)blockIdx.x - vertexBlocks;
@@ -390,6 +411,7 @@ __global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRo
         if ((total & 1ull) && cb == 0 && threadIdx.x == 0) p.pool[total - 1] = EHB_EMPTY;
         if (p.touch)
             for (int i = cb * blockDim.x + threadIdx.x; i < p.items * p.ntiles; i += clearBlocks * blockDim.x) p.touch[i] = 0u;
+        if (threadIdx.x == 0) EHB_TL_STOP(p, 1, blockIdx.x, tl0);
         return;
     }
     // (c) one LANE per tile; the three list counters get one atomic per warp each (a tile per warp meant ten thousand
@@ -422,6 +444,7 @@ __global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRo
     if (heavy) p.tileList[baseH + __popc(bh & below)] = (uint32_t)wid;
     else if (light) p.tileList[(unsigned)(p.items * p.ntiles) - 1u - (baseL + __popc(bl & below))] = (uint32_t)wid;
     else if (empty) p.emptyList[baseE + __popc(be & below)] = (uint32_t)wid;
+    if (threadIdx.x == 0) EHB_TL_STOP(p, 1, blockIdx.x, tl0);
 }
 
 // ------------------------------------------------------------------------------------------------ k_raster
@@ -752,6 +775,7 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
                                                                 int chunks)
 {
     ehb_pdl_enter();
+    EHB_TL_START(tl0);
     __shared__ __align__(128) uint32_t s_rec[EHB_RWARPS][32 * 32];   // 32 records per warp, transposed
     __shared__ int s_off[EHB_RWARPS][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -759,25 +783,25 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
         // spare CTAs of this launch finish the tiles no link touches: pure HBM streaming that overlaps the
         // instruction-bound rasterization instead of sitting in front of it
         const int n = (int)p.ctr->nEmpty;
-        const bool legacy = (p.mode == EHB_MODE_FUSED && (p.ref || p.ref_u8)) || !p.useTma;
-        if (!legacy) {
-            // mask = 0 with ONE bulk tensor store per tile (UTMASTG) from a zeroed 4 KB shared-memory tile; out-of-image
-            // parts of a tile are clipped by the hardware.  (Registered reference masks: the loss of these tiles is part of
-            // refTotal, nothing is read.)
-            float* zero = reinterpret_cast<float*>(&s_rec[0][0]);
-            for (int i = threadIdx.x; i < EHB_T * EHB_T; i += blockDim.x) zero[i] = 0.f;
-            ehb_fence_proxy_async();
-            __syncthreads();
-            if (lane == 0) {
-                for (int i = blockIdx.x * EHB_RWARPS + warp; i < n; i += streamBlocks * EHB_RWARPS) {
-                    const int wid = (int)p.emptyList[i];
-                    const int item = wid / p.ntiles, tile = wid - item * p.ntiles;
-                    const int row0 = p.H - EHB_T - (tile / p.ntx) * EHB_T;   // first image row of the tile (negative: top row of tiles)
-                    ehb_tma_store_3d(row0 < 0 ? &p.tmMaskTop : &p.tmMask, zero, (tile % p.ntx) * EHB_T, max(row0, 0), item);
-                }
-                ehb_bulk_commit();
-                ehb_bulk_wait_read();
+        if (p.prezero) {
+            // No reference to read (registered reference masks: the loss of the untouched tiles is part of refTotal): the
+            // whole mask tensor := 0 with coalesced 16-B streaming stores, a few microseconds at HBM write bandwidth while
+            // the rasterizer's warps wait for their loads; the image-space stage overwrites the listed tiles afterwards.
+            // (Measured alternative: one bulk tensor store (UTMASTG) of a zero tile per untouched tile costs 0.2 us per
+            // tile and SM -- 18 - 33 us for the 7,800 tiles of ten views.)
+            float* m = p.masks;
+            const size_t nAll = (size_t)p.items * p.H * p.W;
+            const size_t head = min(nAll, (size_t)((16u - (unsigned)((uintptr_t)m & 15u)) & 15u) >> 2);
+            const size_t n4 = (nAll - head) >> 2;
+            float4* m4 = reinterpret_cast<float4*>(m + head);
+            const size_t nthr = (size_t)streamBlocks * blockDim.x;
+            for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += nthr) __stcs(m4 + i, make_float4(0.f, 0.f, 0.f, 0.f));
+            if (blockIdx.x == 0 && threadIdx.x < 8) {
+                if (threadIdx.x < head) m[threadIdx.x] = 0.f;
+                const size_t t = head + 4 * n4 + (threadIdx.x - 4);
+                if (threadIdx.x >= 4 && t < nAll) m[t] = 0.f;
             }
+            if (lane == 0) EHB_TL_STOP(p, 5, blockIdx.x * EHB_RWARPS + warp, tl0);
             return;
         }
         for (int i = blockIdx.x * EHB_RWARPS + warp; i < n; i += streamBlocks * EHB_RWARPS) {
@@ -982,12 +1006,14 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
         if (needClip) ehb_emit_clipped(rb, p, item, link, f, qi);
     }
     __syncwarp();   // the records of this batch are dead: the next one may overwrite them
+    if (lane == 0) EHB_TL_STOP(p, 2, ((int)blockIdx.x - streamBlocks) * EHB_RWARPS + warp, tl0);
     if (++sub == EHB_RBATCH) { sub = 0; bcur = __shfl_sync(0xffffffffu, bnext, 0); }
     else bcur++;
     }
 }
 
-// Deferred triangles: warps stride over the unit list; one unit = a 64 x 32 pixel window of one triangle's bbox.
+// Deferred work: the warps draw units from the 32 sub-queues; one unit = a 64 x 32 pixel window of one triangle's bbox, or
+// two groups of 32 rows of a parked batch.
 
 #ifndef EHB_BMIN_BLOCKS
 #define EHB_BMIN_BLOCKS 4
@@ -995,57 +1021,62 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
 __global__ void __launch_bounds__(256, EHB_BMIN_BLOCKS) ehb_k_raster_big(const __grid_constant__ EhbParams p)
 {
     ehb_pdl_enter();
+    EHB_TL_START(tl0);
     __shared__ __align__(128) uint32_t s_blk[8][EHB_BLK_WORDS];
     __shared__ __align__(8) uint64_t s_bar[8];           // one mbarrier per warp: completion of its bulk copies
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nUnitBlocks = (int)gridDim.x;
     if (lane == 0) ehb_mbar_init(&s_bar[warp], 1);
     ehb_fence_mbar_init();
     __syncwarp();
     uint32_t phase = 0;
-    // units of all sub-queues as one list: lane s holds the (inclusive) prefix of the sub-queue sizes
-    int qn = min((int)p.ctr->q[lane].nUnits, p.unitCap), qinc = qn;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, qinc, o);
-        if (lane >= o) qinc += v;
-    }
-    const int n = __shfl_sync(0xffffffffu, qinc, 31);
+    const int qn = min((int)p.ctr->q[lane].nUnits, p.unitCap);   // lane s: units of sub-queue s
     const float xs = p.xs, xo = p.xo, ys = p.ys, yo = p.yo;
     uint32_t* sb = s_blk[warp];
-    auto unit_at = [&](int u) -> EhbUnit {
-        int sq = 0;   // sub-queue of unit u = number of sub-queues whose inclusive prefix is <= u
-#pragma unroll
-        for (int st = 16; st >= 1; st >>= 1) {
-            const int v = __shfl_sync(0xffffffffu, qinc, sq + st - 1);
-            if (v <= u) sq += st;
-        }
-        sq = min(sq, 31);
-        const int before = __shfl_sync(0xffffffffu, qinc - qn, sq);
-        return p.units[(size_t)sq * p.unitCap + (u - before)];
-    };
     // a block of a warp's shared memory <- global memory as ONE bulk asynchronous copy (UBLKCP) that completes on the
     // warp's mbarrier: no register staging, one instruction instead of a load + store per word
-    auto fetch = [&](const void* src, uint32_t bytes) {
+    auto fetch_issue = [&](const void* src, uint32_t bytes) {
         __syncwarp();                          // every lane is done reading the previous contents
         if (lane == 0) {
             ehb_fence_proxy_async();           // ... and those reads are ordered before the asynchronous write
             ehb_mbar_arrive_expect_tx(&s_bar[warp], bytes);
             ehb_bulk_g2s(sb, src, bytes, &s_bar[warp]);
         }
+    };
+    auto fetch_wait = [&]() {
         ehb_mbar_wait(&s_bar[warp], phase);
         phase ^= 1u;
     };
-    const int u0 = blockIdx.x * 8 + warp, stride = nUnitBlocks * 8;
-    EhbUnit un = u0 < n ? unit_at(u0) : EhbUnit{0xFFFFFFFFu, 0, 0};
-    for (int u = u0; u < n; u += stride) {
-        // the next unit's descriptor is fetched while this one is drawn
+    // Units are drawn dynamically: every sub-queue has a cursor (on the sub-queue's own L2 line) and 1/32 of the warps;
+    // a warp takes the units of its sub-queue one at a time until they are used up -- the units' cost varies from nothing
+    // (a sliver's window) to 2048 samples: with a static split a tenth of the warps were still drawing in the last 8 us.
+    // The sub-queues themselves hold equal shares of the work (batches are dealt round-robin, ~500 units each), so nothing
+    // is stolen across them: a look at the other cursors costs more than the imbalance (measured).  The ticket of the
+    // next unit and its descriptor are fetched while the current unit is drawn.
+    const int sq = (blockIdx.x * 8 + warp) & (EHB_NQ - 1);
+    const int qs = __shfl_sync(0xffffffffu, qn, sq);
+    const EhbUnit UNIT_END = EhbUnit{0xFFFFFFFEu, 0, 0};
+    auto take = [&]() -> unsigned { return lane == 0 ? atomicAdd(&p.ctr->q[sq].take, 1u) : 0u; };
+    auto resolve = [&](unsigned tk) -> EhbUnit {          // ticket (lane 0) -> unit descriptor
+        const unsigned b = __shfl_sync(0xffffffffu, tk, 0);
+        return (int)b < qs ? p.units[(size_t)sq * p.unitCap + b] : UNIT_END;
+    };
+    EhbUnit un = resolve(take());
+    unsigned tk = take();
+    for (;;) {
         const EhbUnit cur = un;
-        if (u + stride < n) un = unit_at(u + stride);
-        if (cur.rec == 0xFFFFFFFFu) continue;
-        if (cur.rec & 0x80000000u) {
+        if (cur.rec == UNIT_END.rec) break;
+        // this unit's record(s) -> shared memory (bulk copy), and behind it -- after the copy's fence, which waits for
+        // everything this lane has in flight -- the next unit's descriptor load and the ticket of the one after, so that both
+        // travel while this unit is drawn (a ticket drawn past the end is harmless)
+        const bool isVoid = cur.rec == 0xFFFFFFFFu, isBatch = !isVoid && (cur.rec & 0x80000000u);
+        if (isBatch) fetch_issue(p.batchBlk + (size_t)(cur.rec & 0x7FFFFFFFu) * EHB_BLK_WORDS, EHB_BLK_WORDS * 4);
+        else if (!isVoid) fetch_issue(p.bigRec + cur.rec, (uint32_t)sizeof(EhbRec));
+        un = resolve(tk);
+        tk = take();
+        if (isVoid) continue;
+        fetch_wait();
+        if (isBatch) {
             // rows [32 * dx0, 32 * (dx0 + dy0)) of a parked batch: the same row-group loop as k_raster
-            fetch(p.batchBlk + (size_t)(cur.rec & 0x7FFFFFFFu) * EHB_BLK_WORDS, EHB_BLK_WORDS * 4);
             const int* off = reinterpret_cast<const int*>(sb + 1024);
             const int nRows = off[32];
             const bool anyWide = off[33] != 0;
@@ -1070,7 +1101,6 @@ __global__ void __launch_bounds__(256, EHB_BMIN_BLOCKS) ehb_k_raster_big(const _
             continue;
         }
         // a 64 x 32 window of one deferred triangle
-        fetch(p.bigRec + cur.rec, (uint32_t)sizeof(EhbRec));
         const EhbRec* rc = reinterpret_cast<const EhbRec*>(sb);
         const int ext = max(max(abs(rc->ex[0]), abs(rc->ex[1])), max(max(abs(rc->ex[2]), abs(rc->ey[0])), max(abs(rc->ey[1]), abs(rc->ey[2]))));
         const int dy = cur.dy0 + lane;
@@ -1079,6 +1109,7 @@ __global__ void __launch_bounds__(256, EHB_BMIN_BLOCKS) ehb_k_raster_big(const _
         if (ext >= 32768) ehb_rows_group<long long, double, EhbRecAoS>(rv, t, dy, lane, p.pool, xs, xo, ys, yo, cur.dx0, cur.dx0 + EHB_UNIT_W - 1);
         else ehb_rows_group<int, float, EhbRecAoS>(rv, t, dy, lane, p.pool, xs, xo, ys, yo, cur.dx0, cur.dx0 + EHB_UNIT_W - 1);
     }
+    if (lane == 0) EHB_TL_STOP(p, 3, blockIdx.x * 8 + warp, tl0);
 }
 
 // UNION (packed robot, no antialiasing): mask = (z/w of the nearest triangle > 0), straight from the item's plane.

@@ -429,6 +429,7 @@ __global__ void __launch_bounds__(EHB_TTHREADS, 7) ehb_k_tiles(const __grid_cons
                                                                const __grid_constant__ EhbParams p)
 {
     ehb_pdl_enter();
+    EHB_TL_START(tl0);
     __shared__ EhbTileSm sm;
     constexpr bool NEEDAA = MODE == 0;
     constexpr int OW = EHB_T + ((NEEDAA && BWD) ? 1 : 0);   // out region whose S is needed (33 when g is needed on it)
@@ -484,7 +485,7 @@ __global__ void __launch_bounds__(EHB_TTHREADS, 7) ehb_k_tiles(const __grid_cons
         EHB_STAT_ADD(0, 1); EHB_STAT_ADD(1, nl); EHB_STAT_ADD(2, nl == 0);
         // ---- a listed tile that no triangle reaches: a zero tile (registered reference: its loss is part of refTotal) ------
         if (nl == 0 && (REFKIND == 0 || REFKIND == 3)) {
-            if (NEEDAA && p.masks) {
+            if (NEEDAA && p.masks && !p.prezero) {
                 if (tma) {
                     for (int i = tid; i < EHB_T * EHB_T / 4; i += EHB_TTHREADS) reinterpret_cast<float4*>(stage)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     ehb_fence_proxy_async();
@@ -607,6 +608,7 @@ __global__ void __launch_bounds__(EHB_TTHREADS, 7) ehb_k_tiles(const __grid_cons
         EHB_STAT_ADD(11, clock64() - tTile);
     }
     if (tid == 0 && storePending) ehb_bulk_wait_read();
+    if (tid == 0) EHB_TL_STOP(p, 4, blockIdx.x, tl0);
 }
 
 // the instantiation of a pass
