@@ -296,18 +296,17 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
-def timed_regions(step, steps, barrier, torch, min_ms=MIN_TIMED_MS, max_repeats=400):
-    """Times EXACTLY `steps` steps between two CUDA events, bracketed by barrier + synchronize on both sides; the region is
-    repeated until `min_ms` of device time has been measured (a 20-step region of a 0.1 ms step is 2 ms: one region is
-    noise).  Returns (median ms per region, all region times)."""
+def timed_regions(run, steps, barrier, torch, min_ms=MIN_TIMED_MS, max_repeats=400):
+    """Times EXACTLY `steps` steps (run(steps, first_step_index)) between two CUDA events, bracketed by barrier +
+    synchronize on both sides; the region is repeated until `min_ms` of device time has been measured (a 20-step region
+    of a 0.1 ms step is 2 ms: one region is noise).  Returns (median ms per region, all region times)."""
     regions = []
     k0 = 0
     while True:
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for k in range(steps):
-            step(k0 + k)
+        run(steps, k0)
         e1.record()
         barrier()
         regions.append(e0.elapsed_time(e1))
@@ -432,29 +431,114 @@ def run_b200(args):
             graphs[k % R].replay()
         for k in range(2 * R):
             step(k)
-    # ---- timed region (device-resident inputs) ------------------------------------------------------------
+    def run_serial(n, k0):
+        for k in range(n):
+            step(k0 + k)
+
+    # ---- steps in flight: the same step submitted to the context's four slots (ehb_step_begin), each slot a stream with its
+    # own scratch -- independent batches (the views of different solves, exploration rounds, the ring slots here) overlap
+    # one step's latency-bound kernels and tails with the others' work.  Step k runs on slot k % S on every rank, so the
+    # exchanges of a slot (its own mailbox channel) pair up across the ranks.
+    S = max(1, min(4, int(os.environ.get("EHB_VALUE_SLOTS", "4"))))
+    inflight = S > 1 and (world == 1 or use_peer)
+    G = 32                                     # steps per captured graph (the slots drain at a graph's end)
+    g7s = [torch.zeros(7, dtype=torch.float32, device=dev) for _ in range(S)]
+    dof_scr = [dof_dev[0].clone() for _ in range(S)]
+    adam_st = [torch.zeros(13, dtype=torch.float32, device=dev) for _ in range(S)]
+
+    def slot_step(k):
+        s_, sl = k % R, k % S
+        ctx.step_begin(sl, ids, ref_h[s_], H, W, mvp_dev[s_], masks=masks[s_], dof=dof_dev[s_], K=K_dev, link_poses=lp_dev[s_],
+                       out7=g7s[sl], adam_dof=dof_scr[sl] if world > 1 else None, adam_state=adam_st[sl] if world > 1 else None,
+                       lr=3e-3, weight_decay=5e-4, grad_scale=1.0 / world, loss_scale=1.0 / (B * world), exchange=use_peer)
+
+    slot_graph, slot_launches = None, None
+    if inflight:
+        ctx.slots_fork()
+        for k in range(2 * S):
+            slot_step(k)
+        ctx.slots_join()
+        torch.cuda.synchronize()
+        for sl in range(S):
+            ctx.solver_step_end(sl)            # raises if a slot's scratch overflowed
+        if not os.environ.get("EHB_BENCH_NOGRAPH"):
+            try:
+                cap = torch.cuda.Stream()
+                cap.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(cap):
+                    slot_graph = torch.cuda.CUDAGraph()
+                    l_before = ctx.launch_count()
+                    with torch.cuda.graph(slot_graph, stream=cap):
+                        ctx.slots_fork()
+                        for k in range(G):
+                            slot_step(k)
+                        ctx.slots_join()
+                    slot_launches = (ctx.launch_count() - l_before) / G
+                torch.cuda.current_stream().wait_stream(cap)
+                torch.cuda.synchronize()
+            except Exception as e:   # noqa: BLE001
+                slot_graph = None
+                if rank == 0:
+                    print("CUDA graph capture of the slot steps failed (%s); eager" % str(e)[:200], file=sys.stderr)
+
+    def run_inflight(n, k0):
+        q, r_ = (n // G, n % G) if slot_graph is not None else (0, n)
+        for _ in range(q):
+            slot_graph.replay()
+        if r_:
+            ctx.slots_fork()
+            for k in range(r_):
+                slot_step(k0 + q * G + k)      # (G is a multiple of the ring and of S: the slot / ring pairing continues)
+            ctx.slots_join()
+
+    # ---- timed regions (device-resident inputs) ------------------------------------------------------------
     sampler = ClockSampler(physical_gpu_index(local))
     barrier()
     sampler.start()
     l0 = ctx.launch_count()
-    ms, regions = timed_regions(step, args.steps, barrier, torch)
-    clocks = sampler.stop()
-    launches = (ctx.launch_count() - l0) // max(len(regions), 1)
+    ms_serial, regions_serial = timed_regions(run_serial, args.steps, barrier, torch)
+    launches = (ctx.launch_count() - l0) // max(len(regions_serial), 1)
     if graphs is not None:
         launches = launches_per_step * args.steps
+    ms, regions = ms_serial, regions_serial
+    if inflight:
+        for k in range(2):
+            run_inflight(G, 0)
+        l0 = ctx.launch_count()
+        ms, regions = timed_regions(run_inflight, args.steps, barrier, torch)
+        launches = (ctx.launch_count() - l0) // max(len(regions), 1)
+        if slot_graph is not None:
+            launches = int(round(slot_launches * (args.steps - args.steps % G))) + (launches if args.steps % G else 0)
+    clocks = sampler.stop()
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, ms_serial], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms, ms_serial = float(t[0].item()), float(t[1].item())
     frames = B * args.steps * world
     value = frames / (ms * 1e-3)
+    serial = {"value": frames / (ms_serial * 1e-3), "unit": "frames/s", "ms_per_step": ms_serial / max(args.steps, 1),
+              "launch": "CUDA graph replay, one graph per ring slot" if graphs is not None else "eager",
+              "what": "one step at a time on one stream (each step's views split over %d pipelines): the latency of a step, "
+                      "what a single sequential solve sees" % int(os.environ.get("EHB_PIPES", "3"))}
 
     # ---- parity of what was just timed: GPU results of every ring slot, checked by the CPU leg below -------------
-    gpu_results = []
+    gpu_results, slot_path_ok = [], None
     if rank == 0 and world == 1 and not args.no_cpu:
         for s in range(R):
             eager_step(s)
-            gpu_results.append((masks[s].cpu().numpy(), loss.cpu().numpy().copy(), gmvp.cpu().numpy().copy()))
+            gpu_results.append((masks[s].cpu().numpy(), loss.cpu().numpy().copy(), gmvp.cpu().numpy().copy(), g7.cpu().numpy().copy()))
+        if inflight:   # the slot path on the same inputs: masks and the 7 floats must equal the single-stream path's
+            slot_path_ok = True
+            for s in range(R):
+                masks[s].fill_(-1.0)
+            ctx.slots_fork()
+            for s in range(R):
+                slot_step(s)
+            ctx.slots_join()
+            torch.cuda.synchronize()
+            for s in range(R):
+                slot_path_ok &= bool(np.array_equal(masks[s].cpu().numpy(), gpu_results[s][0]))
+                slot_path_ok &= bool(np.allclose(g7s[s % S].cpu().numpy(), gpu_results[s][3], rtol=1e-5, atol=1e-7))
 
     # ---- per-kernel pass (CUDA events around each kernel, on the launching stream) ----------------------
     ctx.profile(True)
@@ -494,20 +578,20 @@ def run_b200(args):
     # four steps in flight so that one step's copies overlap the others' kernels.  Each step's result is complete on the
     # host when its _end returns.
     mvp_host = [torch.from_numpy(s["mvp"]).pin_memory() for s in sets]
-    S = max(2, min(4, int(os.environ.get("EHB_E2E_SLOTS", "4"))))   # steps in flight
-    loss_host = [torch.empty((B,), dtype=torch.float64).pin_memory() for _ in range(S)]
-    gmvp_host = [torch.empty((B, L, 4, 4), dtype=torch.float64).pin_memory() for _ in range(S)]
+    Se = max(2, min(4, int(os.environ.get("EHB_E2E_SLOTS", "4"))))   # steps in flight
+    loss_host = [torch.empty((B,), dtype=torch.float64).pin_memory() for _ in range(Se)]
+    gmvp_host = [torch.empty((B, L, 4, 4), dtype=torch.float64).pin_memory() for _ in range(Se)]
 
     def e2e_run(n, begin):
         for k in range(n):
             begin(k)
-            if k >= S - 1:
-                ctx.solver_step_end((k - S + 1) % S)
-        for k in range(max(n - S + 1, 0), n):
-            ctx.solver_step_end(k % S)
+            if k >= Se - 1:
+                ctx.solver_step_end((k - Se + 1) % Se)
+        for k in range(max(n - Se + 1, 0), n):
+            ctx.solver_step_end(k % Se)
 
     def begin_ref(k):
-        ctx.solver_step_begin_ref(k % S, ids, mvp_host[k % R], ref_h[k % R], H, W, loss_host[k % S], gmvp_host[k % S])
+        ctx.solver_step_begin_ref(k % Se, ids, mvp_host[k % R], ref_h[k % R], H, W, loss_host[k % Se], gmvp_host[k % Se])
 
     def e2e_time(begin, n):
         e2e_run(16, begin)
@@ -526,13 +610,13 @@ def run_b200(args):
     ms_e2e = e2e_time(begin_ref, e2e_steps)
     e2e = {"value": B * e2e_steps * world / (ms_e2e * 1e-3), "unit": "frames/s",
            "h2d_bytes_per_step": int(B * L * 64), "d2h_bytes_per_step": int(8 * B + 128 * B * L + 176),
-           "steps": e2e_steps, "api": "ehb_solver_step_begin_ref / _end, %d slots (pinned host mvp in, loss + g_mvp out, " % S +
+           "steps": e2e_steps, "api": "ehb_solver_step_begin_ref / _end, %d slots (pinned host mvp in, loss + g_mvp out, " % Se +
                                       "host-visible result every step; reference masks registered once with ehb_ref_register)"}
     # the reference trainer's quirk, for comparison: the masks re-uploaded on every step (trainer/rbsolver.py:31 to_cuda(batch))
     ref_host = [r.to(torch.uint8).cpu().pin_memory() for r in ref_dev]
 
     def begin_u8(k):
-        ctx.solver_step_begin_u8(k % S, ids, mvp_host[k % R], ref_host[k % R], H, W, loss_host[k % S], gmvp_host[k % S])
+        ctx.solver_step_begin_u8(k % Se, ids, mvp_host[k % R], ref_host[k % R], H, W, loss_host[k % Se], gmvp_host[k % Se])
 
     n_up = min(e2e_steps, 400)
     ms_up = e2e_time(begin_u8, n_up)
@@ -552,14 +636,17 @@ def run_b200(args):
                    "sample": "the %d ring slots (%d views each) x 5 passes (+1 warm-up pass), OpenMP over views" % (R, B)}
             ok, worst_g, worst_l = True, 0.0, 0.0
             for s in range(R):
-                gm, gl, gg = gpu_results[s]
+                gm, gl, gg, _ = gpu_results[s]
                 w = last[s]
                 ok &= bool(np.array_equal(gm, w["masks"]))
                 worst_l = max(worst_l, rel_err(gl, w["loss_per_view"]))
                 worst_g = max(worst_g, rel_err(gg, w["g_mvp"]))
             ok &= worst_l < 1e-12 and worst_g < 1e-6
+            if slot_path_ok is not None:
+                ok &= slot_path_ok
             parity = {"ok": bool(ok), "slots": R, "masks": "bit-exact" if ok else "MISMATCH", "loss_rel_err": worst_l,
-                      "g_mvp_rel_err": worst_g, "checker": "oracle.render_views on the timed inputs (outside the timed region)"}
+                      "g_mvp_rel_err": worst_g, "checker": "oracle.render_views on the timed inputs (outside the timed region)",
+                      "slot_path_equals_single_stream_path": slot_path_ok}
             if not args.no_proxy:
                 try:
                     proxy = time_proxy(wl, sets, ids, dev)
@@ -576,10 +663,13 @@ def run_b200(args):
                            "l2": "ring of %d view-sets (%.0f MB of masks+refs) > 126 MB L2" %
                                  (R, R * B * H * W * 8 / 1e6),
                            "pipelines": int(os.environ.get("EHB_PIPES", "3")),
-                           "launch": "CUDA graph replay, one graph per ring slot" if graphs is not None else "eager",
+                           "launch": ("%d steps in flight on the context's slots (ehb_step_begin), " % S +
+                                      ("CUDA graph replay, %d steps per graph" % G if slot_graph is not None else "eager"))
+                                     if inflight else ("CUDA graph replay, one graph per ring slot" if graphs is not None else "eager"),
+                           "steps_in_flight": S if inflight else 1,
                            "scenes": "identical on every rank", "collective": collective,
                            "timed_regions": len(regions), "timed_region_ms": ms},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "clocks": clocks, "e2e": e2e, "serial": serial, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu, "parity_checked": bool(parity and parity["ok"]), "parity": parity,
                 "proxy": proxy, "nvdiffrast": nvd, "pytorch3d": probe_pytorch3d(),
                 "need_clip_triangles": int(nclip)}
@@ -661,7 +751,7 @@ def run_explore(args):
     sampler.start()
     l0 = ctx.launch_count()
     steps = min(args.steps, 50)
-    ms, regions = timed_regions(step, steps, barrier, torch)
+    ms, regions = timed_regions(lambda n, k0: [step(k0 + k) for k in range(n)], steps, barrier, torch)
     clocks = sampler.stop()
     launches = (ctx.launch_count() - l0) // max(len(regions), 1)
     if world > 1:

@@ -143,8 +143,10 @@ def _dev_check(t, dtype, device, name):
 
 class StepIO(C.Structure):
     """ehb_step_io_t (include/easyhec_b200.h)"""
-    _fields_ = [(n, C.c_void_p) for n in ("mvp_host", "mvp_dev", "masks_dev", "loss_host", "g_mvp_host", "dof_dev", "K_dev",
-                                          "link_poses_dev", "out7_dev", "out7_host")]
+    _fields_ = ([(n, C.c_void_p) for n in ("mvp_host", "mvp_dev", "masks_dev", "loss_host", "g_mvp_host", "dof_dev", "K_dev",
+                                           "link_poses_dev", "out7_dev", "out7_host", "adam_dof_dev", "adam_state_dev")] +
+                [("grad_scale", C.c_double), ("loss_scale", C.c_double), ("lr", C.c_float), ("weight_decay", C.c_float),
+                 ("exchange", C.c_int), ("pad", C.c_int)])
 
 
 class RefMasks:
@@ -509,10 +511,12 @@ class Context:
                                                _ptr(loss_host), _ptr(g_mvp_host)))
 
     def step_begin(self, slot, mesh_ids, ref: RefMasks, H, W, mvp, masks=None, loss_host=None, g_mvp_host=None, dof=None,
-                   K=None, link_poses=None, out7=None, out7_host=None):
+                   K=None, link_poses=None, out7=None, out7_host=None, adam_dof=None, adam_state=None, lr=3e-3, weight_decay=0.0,
+                   grad_scale=0.0, loss_scale=0.0, exchange=False):
         """General asynchronous step on slot 0..3 (ehb_step_begin): mvp (B,L,4,4) f32 is a pinned host tensor (copied in) or
         a device tensor; optional outputs masks (device), loss_host / g_mvp_host (pinned), and with dof / K / link_poses
-        (device) the pose chain's out7 on the device (out7) and / or the host (out7_host, pinned)."""
+        (device) the pose chain's out7 on the device (out7) and / or the host (out7_host, pinned); with adam_dof / adam_state
+        the Adam update behind it, with exchange=True after the all-reduce of out7 over the connected ranks."""
         B, L = mvp.shape[0], mvp.shape[1]
         ids = (C.c_int * L)(*mesh_ids)
         if len(ref) != B or (ref.H, ref.W) != (H, W):
@@ -523,8 +527,10 @@ class Context:
         io = StepIO()
         io.mvp_host, io.mvp_dev = (None, mvp.data_ptr()) if mvp.is_cuda else (mvp.data_ptr(), None)
         for name, t in (("masks_dev", masks), ("loss_host", loss_host), ("g_mvp_host", g_mvp_host), ("dof_dev", dof), ("K_dev", K),
-                        ("link_poses_dev", link_poses), ("out7_dev", out7), ("out7_host", out7_host)):
+                        ("link_poses_dev", link_poses), ("out7_dev", out7), ("out7_host", out7_host), ("adam_dof_dev", adam_dof),
+                        ("adam_state_dev", adam_state)):
             setattr(io, name, None if t is None else t.data_ptr())
+        io.grad_scale, io.loss_scale, io.lr, io.weight_decay, io.exchange = grad_scale, loss_scale, lr, weight_decay, int(bool(exchange))
         _check(lib().ehb_step_begin(self._h, slot, ids, L, B, ref.ref_id, ref.first, H, W, C.byref(io)))
 
     def slot_stream(self, slot):

@@ -79,6 +79,7 @@ constexpr double POOL_BUDGET = 8e9;  // bytes of plane pool per pipeline reserve
 constexpr int MAX_PIPES = 4;
 constexpr int N_SLOTS = 4;      // in-flight host-buffer steps (ehb_solver_step_begin_u8 / _end)
 constexpr int N_SCRATCH = MAX_PIPES + N_SLOTS;
+constexpr size_t COMM_CH_WORDS = 2 * EHB_COMM_MAX * 8 + 8;   // one channel of a peer mailbox: [2 parities][ranks][8 words] + step counter
 
 // Scratch of one pipeline.  A call's items are split over up to MAX_PIPES independent pipelines that run on internal
 // streams: every kernel of the pass is latency / tail bound, so the pipelines fill each other's idle SMs.
@@ -147,7 +148,8 @@ struct Ctx {
     size_t evUsed = 0;
     double poolFactor = 2.0;          // beyond the budget: plane pool = items * H * W * poolFactor entries, grown on overflow
     double poolBudget = POOL_BUDGET;
-    EhbComm comm = {};                // NVLink peer mailboxes (ehb_comm_*)
+    EhbComm comm = {};                // NVLink peer mailboxes (ehb_comm_*): channel 0, the caller's stream ...
+    EhbComm commSlot[N_SLOTS] = {};   // ... and one channel per slot, so that the exchanges of steps in flight never mix
     unsigned int* commBox = nullptr;  // own mailbox (device)
     bool commReady = false;
     unsigned long long* dbgbuf = nullptr;   // EHB_TIMING builds
@@ -1436,8 +1438,13 @@ int ehb_step_begin(ehb_ctx_t h, int slot, const int* mesh_ids, int L, int B, int
     Ctx* c = (Ctx*)h;
     if (!c || slot < 0 || slot >= N_SLOTS || !mesh_ids || !sio || (!sio->mvp_host && !sio->mvp_dev)) return fail(EHB_E_ARG, "bad step_begin arguments");
     if (B < 1 || L < 1) return fail(EHB_E_ARG, "empty batch");
-    const bool pose = sio->out7_dev || sio->out7_host;
+    const bool adam = sio->adam_dof_dev != nullptr;
+    const bool pose = sio->out7_dev || sio->out7_host || adam;
     if (pose && (!sio->dof_dev || !sio->K_dev || !sio->link_poses_dev)) return fail(EHB_E_ARG, "the pose chain needs dof_dev, K_dev and link_poses_dev");
+    if (adam && !sio->adam_state_dev) return fail(EHB_E_ARG, "the Adam update needs adam_state_dev");
+    const int exch = sio->exchange ? 1 : 0;
+    if (exch && !c->commReady) return fail(EHB_E_ARG, "peer mailboxes are not connected (ehb_comm_connect)");
+    if (exch && !adam) return fail(EHB_E_ARG, "an exchanged step ends with the Adam update (it receives the sum)");
     DeviceGuard guard(c->device);
     cudaStream_t st = c->slotStream[slot];
     int r;
@@ -1457,10 +1464,16 @@ int ehb_step_begin(ehb_ctx_t h, int slot, const int* mesh_ids, int L, int B, int
     if (r) return r;
     if (pose) {
         float* o7 = sio->out7_dev ? sio->out7_dev : reinterpret_cast<float*>(c->slotOut[slot].p + B + nm);
+        const double gs = sio->grad_scale != 0.0 ? sio->grad_scale : 1.0, ls = sio->loss_scale != 0.0 ? sio->loss_scale : 1.0 / (double)B;
         CU(launch(ehb_k_pose_backward, dim3(1), dim3(256), 0, st, true, sio->dof_dev, sio->K_dev, sio->link_poses_dev,
-                  (const double*)(c->slotOut[slot].p + B), (const double*)c->slotOut[slot].p, B, L, H, W, 1.0, 1.0 / (double)B, o7,
-                  c->comm, 0));
+                  (const double*)(c->slotOut[slot].p + B), (const double*)c->slotOut[slot].p, B, L, H, W, gs, ls, o7,
+                  c->commSlot[slot], exch));
         c->launches += 1;
+        if (adam) {
+            CU(launch(ehb_k_adam, dim3(1), dim3(32), 0, st, true, sio->adam_dof_dev, o7, sio->adam_state_dev, sio->lr, 0.9f, 0.999f, 1e-8f,
+                      sio->weight_decay, (float*)nullptr, 0, c->commSlot[slot], exch));
+            c->launches += 1;
+        }
         if (sio->out7_host) CU(cudaMemcpyAsync(sio->out7_host, o7, 7 * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     if (sio->loss_host) CU(cudaMemcpyAsync(sio->loss_host, c->slotOut[slot].p, B * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1521,7 +1534,7 @@ int ehb_comm_local_handle(ehb_ctx_t h, void* handle64)
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     DeviceGuard guard(c->device);
     if (!c->commBox) {
-        const size_t words = 2 * EHB_COMM_MAX * 8 + 8;
+        const size_t words = (size_t)(1 + N_SLOTS) * COMM_CH_WORDS;
         CU(cudaMalloc((void**)&c->commBox, words * sizeof(unsigned)));
         CU(cudaMemset(c->commBox, 0, words * sizeof(unsigned)));
         CU(cudaDeviceSynchronize());
@@ -1548,6 +1561,11 @@ int ehb_comm_connect(ehb_ctx_t h, int rank, int world, const void* handles)
     }
     c->comm.step = c->commBox + 2 * EHB_COMM_MAX * 8;
     c->comm.rank = rank; c->comm.world = world;
+    for (int k = 0; k < N_SLOTS; k++) {   // channel 1 + k: the same layout, COMM_CH_WORDS further on in every mailbox
+        c->commSlot[k] = c->comm;
+        for (int r = 0; r < world; r++) c->commSlot[k].peer[r] = c->comm.peer[r] + (size_t)(1 + k) * COMM_CH_WORDS;
+        c->commSlot[k].step = c->comm.step + (size_t)(1 + k) * COMM_CH_WORDS;
+    }
     c->commReady = true;
     return EHB_OK;
 }

@@ -211,7 +211,8 @@ EHB_API int ehb_solver_step_begin_ref(ehb_ctx_t ctx, int slot, const int* mesh_i
  * several solves, exploration rounds, ring slots of a benchmark -- run concurrently, each on its slot's stream and scratch.
  * The matrices come from the host (copied in) or are already on the device; optional outputs: the rendered masks (device),
  * loss / d loss/d mvp (host), and -- when dof_dev, K_dev, link_poses_dev are given -- the pose chain's out7 = { d loss/d dof
- * [6], mean loss } of the step (rb_solver.py:52-72 backward) on the device and / or the host.  ehb_solver_step_end(slot)
+ * [6], mean loss } of the step (rb_solver.py:52-72 backward) on the device and / or the host, optionally followed by the
+ * all-reduce of out7 over the ranks and the Adam update of a parameter vector.  ehb_solver_step_end(slot)
  * waits for the slot's last step and reports a scratch overflow; ehb_slots_fork / _join order all slot streams after / before
  * a caller's stream (for timing or for handing results on without a host wait). */
 typedef struct ehb_step_io {
@@ -225,6 +226,14 @@ typedef struct ehb_step_io {
     const float* link_poses_dev;  /* f32[B*L*16] */
     float* out7_dev;              /* optional f32[7] */
     float* out7_host;             /* optional f32[7], pinned */
+    float* adam_dof_dev;          /* optional Adam update behind the pose chain (trainer/rbsolver.py:29-43): the parameter f32[6] ... */
+    float* adam_state_dev;        /* ... and its state f32[13] = { m[6], v[6], t } */
+    double grad_scale, loss_scale;/* scales of out7 (0: 1 and 1 / B); a data-parallel caller passes 1 / world and 1 / (B * world) */
+    float lr, weight_decay;       /* Adam (betas 0.9 / 0.999, eps 1e-8) */
+    int exchange;                 /* != 0: out7 is summed over the ranks (ehb_comm_connect) between the pose chain and Adam, on the
+                                     slot's own mailbox channel -- steps in flight on different slots never mix their messages, as
+                                     long as every rank submits step k to the same slot */
+    int pad;
 } ehb_step_io_t;
 EHB_API int ehb_step_begin(ehb_ctx_t ctx, int slot, const int* mesh_ids, int L, int B, int ref_id, int first_view, int H, int W,
                    const ehb_step_io_t* io);

@@ -130,3 +130,60 @@ def test_pose_solver_converges_and_graph_equals_eager():
     assert e1[0] < 0.35 * e0[0] and e1[0] < 0.006, (e0, e1)
     assert a.history_ops().shape == (200, 6)
     assert float(a.loss) >= 0
+
+
+@pytest.mark.gpu
+def test_steps_in_flight_on_slots_match_the_single_stream_path(gpu_ctx):
+    """ehb_step_begin: two rounds of four steps over the four slots (device matrices, masks out, pose chain + Adam behind the pass) give
+    the oracle's masks and the same 7 floats / Adam update as the single-stream calls; host matrices + host outputs too."""
+    from easyhec_b200.se3 import matrix_to_dof
+    B, H, W = 3, 240, 320
+    sc = make_scene(B, H, W, links="xarm7", seed=9)
+    packed = oracle.pack_links(sc["meshes"])
+    ref = oracle.union_binary(packed, scene_mvps(sc, H, W), H, W)
+    ids = [gpu_ctx.register_mesh(m.vertices, m.faces) for m in sc["meshes"]]
+    h = gpu_ctx.register_ref(ref)
+    K = to_dev(sc["K"]); lp = to_dev(sc["link_poses"])
+    sets = []
+    for k in range(4):
+        Tc = perturb_pose(sc["Tc_c2b"], np.random.RandomState(50 + k), 0.02, 2.0)
+        mvp = scene_mvps(sc, H, W, Tc)
+        want = oracle.render_views(packed, mvp, ref.astype(np.float32), H, W)
+        dof = matrix_to_dof(torch.tensor(Tc, dtype=torch.float32)).cuda().contiguous()
+        _, l1, g1 = gpu_ctx.render_views_fused(ids, to_dev(mvp), h, H, W, backward=True, want_masks=False)
+        g7 = gpu_ctx.pose_backward(dof, K, lp, g1, l1, H, W, grad_scale=1.0, loss_scale=1.0 / B)
+        d2 = torch.zeros(6, device="cuda"); st2 = torch.zeros(13, device="cuda")
+        gpu_ctx.adam_step(d2, g7, st2, 3e-3, weight_decay=5e-4)
+        sets.append(dict(mvp=mvp, want=want, dof=dof, g7=g7.clone(), adam=d2))
+    masks = [torch.full((B, H, W), -1.0, device="cuda") for _ in range(4)]
+    o7 = [torch.zeros(7, device="cuda") for _ in range(4)]
+    ad = [torch.zeros(6, device="cuda") for _ in range(4)]
+    st = [torch.zeros(13, device="cuda") for _ in range(4)]
+    mvp_dev = [to_dev(s["mvp"]) for s in sets]
+    for rnd in range(2):                                     # the second round reuses every slot and overwrites the outputs
+        for j in range(4):
+            ad[j].zero_(); st[j].zero_(); masks[j].fill_(-1.0)
+        gpu_ctx.slots_fork()                                 # the slot streams wait for the zeroing above
+        for j in range(4):
+            gpu_ctx.step_begin(j, ids, h, H, W, mvp_dev[j], masks=masks[j], dof=sets[j]["dof"], K=K, link_poses=lp, out7=o7[j],
+                               adam_dof=ad[j], adam_state=st[j], lr=3e-3, weight_decay=5e-4)
+        gpu_ctx.slots_join()
+        torch.cuda.synchronize()
+        for j in range(4):
+            gpu_ctx.solver_step_end(j)
+            assert np.array_equal(masks[j].cpu().numpy(), sets[j]["want"]["masks"])
+            assert torch.allclose(o7[j], sets[j]["g7"], rtol=1e-5, atol=1e-7)
+            assert torch.allclose(ad[j], sets[j]["adam"], rtol=1e-5, atol=1e-8)
+    # host matrices in, host results out (what the end-to-end leg of the bench uses), on two slots at once
+    loss_h = [torch.empty(B, dtype=torch.float64).pin_memory() for _ in range(2)]
+    g_h = [torch.empty((B, len(ids), 4, 4), dtype=torch.float64).pin_memory() for _ in range(2)]
+    o7_h = [torch.empty(7, dtype=torch.float32).pin_memory() for _ in range(2)]
+    mvp_h = [torch.from_numpy(sets[j]["mvp"]).pin_memory() for j in range(2)]
+    for j in range(2):
+        gpu_ctx.step_begin(j, ids, h, H, W, mvp_h[j], loss_host=loss_h[j], g_mvp_host=g_h[j], dof=sets[j]["dof"], K=K, link_poses=lp,
+                           out7_host=o7_h[j])
+    for j in range(2):
+        gpu_ctx.solver_step_end(j)
+        assert np.allclose(loss_h[j].numpy(), sets[j]["want"]["loss_per_view"], rtol=1e-12, atol=0)
+        assert rel_err(g_h[j].numpy(), sets[j]["want"]["g_mvp"]) < 1e-9
+        assert torch.allclose(o7_h[j], sets[j]["g7"].cpu(), rtol=1e-5, atol=1e-7)

@@ -58,6 +58,38 @@ def main():
         assert all(torch.equal(gathered[0], t) for t in gathered), "ranks disagree (fused exchange)"
     if rank == 0:
         print("fused exchange (pose_backward send + adam recv) == NCCL all-reduce, identical on every rank")
+    # steps in flight on the context's slots: every slot exchanges on its own mailbox channel; 12 steps over 4 slots leave the
+    # NCCL sum of the ranks' out7 in every slot's buffer, and the Adam parameters agree on every rank
+    Hs, Ws, Bs = 120, 160, 2
+    scs = make_scene(Bs, Hs, Ws, links="xarm7", seed=31 + rank)
+    ids_s = [ctx.register_mesh(m.vertices, m.faces) for m in scs["meshes"]]
+    ref_s = ctx.register_ref(ctx.render_binary_batch(ids_s, torch.from_numpy(scene_mvps(scs, Hs, Ws)).to(dev), Hs, Ws))
+    from easyhec_b200.se3 import matrix_to_dof
+    Tcs = perturb_pose(scs["Tc_c2b"], np.random.RandomState(32 + rank), 0.02, 2.0)
+    mvp_s = torch.from_numpy(scene_mvps(scs, Hs, Ws, Tcs)).to(dev)
+    dof_s = matrix_to_dof(torch.tensor(Tcs, dtype=torch.float32)).to(dev).contiguous()
+    K_s = torch.from_numpy(scs["K"]).to(dev).contiguous()
+    lp_s = torch.from_numpy(scs["link_poses"]).to(dev).contiguous()
+    _, l_ref, g_ref = ctx.render_views_fused(ids_s, mvp_s, ref_s, Hs, Ws, backward=True, want_masks=False)
+    want7 = ctx.pose_backward(dof_s, K_s, lp_s, g_ref, l_ref, Hs, Ws, grad_scale=1.0 / world, loss_scale=1.0 / (Bs * world))
+    dist.all_reduce(want7)
+    o7 = [torch.zeros(7, device=dev) for _ in range(4)]
+    ad = [torch.zeros(6, device=dev) for _ in range(4)]
+    st = [torch.zeros(13, device=dev) for _ in range(4)]
+    ctx.slots_fork()
+    for k in range(12):
+        ctx.step_begin(k % 4, ids_s, ref_s, Hs, Ws, mvp_s, dof=dof_s, K=K_s, link_poses=lp_s, out7=o7[k % 4], adam_dof=ad[k % 4],
+                       adam_state=st[k % 4], lr=1e-3, grad_scale=1.0 / world, loss_scale=1.0 / (Bs * world), exchange=True)
+    ctx.slots_join()
+    torch.cuda.synchronize()
+    for k in range(4):
+        ctx.solver_step_end(k)
+        assert torch.allclose(o7[k], want7, rtol=1e-5, atol=1e-6), (k, o7[k], want7)
+        gathered = [torch.empty_like(ad[k]) for _ in range(world)]
+        dist.all_gather(gathered, ad[k])
+        assert all(torch.equal(gathered[0], t) for t in gathered) and float(ad[k].abs().max()) > 0, "ranks disagree (slot exchange)"
+    if rank == 0:
+        print("12 steps in flight over 4 slots: every slot's exchange == NCCL all-reduce, Adam parameters identical on every rank")
     # latency of the two collectives (device time, 200 back-to-back calls)
     for name, fn in (("peer", lambda t: ctx.allreduce7(t)), ("nccl", lambda t: dist.all_reduce(t))):
         t = torch.zeros(7, device=dev)
