@@ -43,6 +43,7 @@ _PROTOS = {
     "ehb_ctx_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "ehb_ctx_debug_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]),
     "ehb_ctx_debug_buffer": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]),
+    "ehb_ctx_debug_marks": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint)]),
     "ehb_ctx_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint), C.POINTER(C.c_longlong)]),
     "ehb_ctx_poll": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint)]),
     "ehb_mesh_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
@@ -296,6 +297,11 @@ class Context:
         out = (C.c_ulonglong * max(n_words, 1))()
         _check(lib().ehb_ctx_debug_buffer(self._h, out, n_words))
         return list(out)[:n_words]
+
+    def debug_marks(self):
+        out = (C.c_uint * 16)()
+        _check(lib().ehb_ctx_debug_marks(self._h, out))
+        return list(out)
 
     def launch_count(self) -> int:
         return int(lib().ehb_launch_count(self._h))

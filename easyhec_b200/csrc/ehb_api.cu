@@ -92,12 +92,13 @@ struct Scratch {
     DevBuf<EhbRec> bigRec;
     DevBuf<EhbUnit> units;
     DevBuf<uint32_t> batchBlk;        // parked heavy batches of k_raster
+    DevBuf<uint32_t> batchList;       // visible batches of the pass (k_front -> k_raster)
     DevBuf<unsigned char> pairPool;   // slabs for tiles whose silhouette pairs do not fit shared memory (k_tiles)
     EhbCounters* ctr = nullptr;
     void release()
     {
         vclip.release(); vsnap.release(); plane.release(); pool.release(); tileList.release(); emptyList.release();
-        touch.release(); bigRec.release(); units.release(); batchBlk.release(); pairPool.release();
+        touch.release(); bigRec.release(); units.release(); batchBlk.release(); pairPool.release(); batchList.release();
     }
 };
 
@@ -556,6 +557,7 @@ int ensure_scratch(Ctx* c, Scratch& sc, int items, int L, int Lp, int H, int W, 
     if ((r = sc.bigRec.ensure(bigCap * EHB_NQ, capturing))) return r;
     if ((r = sc.units.ensure((tinyQ ? 4 : std::max<size_t>(UNIT_CAP / EHB_NQ, 4 * bigCap)) * EHB_NQ, capturing))) return r;
     if ((r = sc.batchBlk.ensure((size_t)BATCH_CAP * EHB_BLK_WORDS, capturing))) return r;
+    if ((r = sc.batchList.ensure((size_t)items * (size_t)(std::max(Ftot, 1) / 32 + EHB_MAX_LINKS + 1), capturing))) return r;
     // Plane pool: the worst case (every link's bbox is the whole screen) is items * Lp * H * W entries.  That is what is
     // reserved while it stays under POOL_BUDGET (180 GB of HBM: 10 views x 7 links x 1280x720 is 0.5 GB) -- then the
     // pool can never overflow; beyond it the pool holds poolFactor screens per item and grows on the overflow flag.
@@ -597,7 +599,7 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
     p.mvp = mvp_dev;
     p.vclip = sc.vclip.p; p.vsnap = sc.vsnap.p;
     p.plane = sc.plane.p; p.pool = sc.pool.p; p.poolCap = sc.pool.n;
-    p.tileList = sc.tileList.p; p.emptyList = sc.emptyList.p; p.touch = unionMode ? nullptr : sc.touch.p; p.bigRec = sc.bigRec.p; p.units = sc.units.p; p.bigCap = (int)(sc.bigRec.n / EHB_NQ); p.unitCap = (int)(sc.units.n / EHB_NQ); p.batchBlk = tune_int("EHB_NO_OFFLOAD", 0) ? nullptr : sc.batchBlk.p; p.batchCap = c->poolBudget == 0.0 ? 1 : BATCH_CAP / EHB_NQ; p.ctr = sc.ctr;
+    p.tileList = sc.tileList.p; p.emptyList = sc.emptyList.p; p.touch = unionMode ? nullptr : sc.touch.p; p.bigRec = sc.bigRec.p; p.units = sc.units.p; p.bigCap = (int)(sc.bigRec.n / EHB_NQ); p.unitCap = (int)(sc.units.n / EHB_NQ); p.batchBlk = tune_int("EHB_NO_OFFLOAD", 0) ? nullptr : sc.batchBlk.p; p.batchCap = c->poolBudget == 0.0 ? 1 : BATCH_CAP / EHB_NQ; p.ctr = sc.ctr; p.batchList = sc.batchList.p; p.heavyArea = (float)tune_int("EHB_HEAVY_AREA", 1024);
     p.ref = io.ref; p.ref_u8 = io.ref_u8; p.masks = io.masks; p.loss = io.loss; p.gmvp = io.gmvp; p.gpos = io.gpos;
     p.dy = io.dy; p.out_u8 = io.out_u8;
     p.refBits = io.refBits; p.refCnt = io.refCnt; p.refTotal = io.refTotal;
@@ -624,20 +626,22 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
     p.prezero = (!unionMode && mode != EHB_MODE_AA_BWD && !legacyStream && io.masks) ? 1 : 0;
     const int streamBlocks = (unionMode || mode == EHB_MODE_AA_BWD || (!legacyStream && !io.masks)) ? 0
                              : legacyStream ? c->nSM * tune_int("EHB_STREAM_MULT", 2) : c->nSM;
-    const long long tickets = ((long long)chunks * items + EHB_RBATCH - 1) / EHB_RBATCH;
-    long long rasterBlocks = (tickets + EHB_RWARPS - 1) / EHB_RWARPS;
-#ifdef EHB_RPERSIST
-    rasterBlocks = std::min<long long>(rasterBlocks, (long long)c->nSM * tune_int("EHB_RASTER_OCC", c->occRaster));
-#endif
-    p.rasterStart = (int)(rasterBlocks * EHB_RWARPS * EHB_RBATCH);
+    const long long rasterBlocks = ((long long)chunks * items + EHB_RWARPS - 1) / EHB_RWARPS;
     if (ev) cudaEventRecord(ev[0], st);
-    CU(launch(ehb_k_table, dim3((unsigned)((items * p.Lp + 7) / 8)), dim3(256), 0, st, false, rb, p));
     if (ev) cudaEventRecord(ev[1], st);
+    const int tableBlocks = (items * p.Lp + 7) / 8;
     const int vchunks = std::max(1, (p.Vtot + 255) / 256);
+    const int batchBlocks = (int)(((long long)chunks * items + 31) / 32);
     const int clearBlocks = c->nSM;
     const long long tileThreads = unionMode ? 0 : (long long)items * p.ntiles;   // one lane per tile
-    CU(launch(ehb_k_front, dim3((unsigned)(vchunks * items + clearBlocks + (tileThreads + 255) / 256)), dim3(256), 0, st, true, rb, p,
-              vchunks, clearBlocks));
+    const unsigned restBlocks = (unsigned)(vchunks * items + batchBlocks + clearBlocks + (tileThreads + 255) / 256);
+    if (tune_int("EHB_FRONT_SPLIT", 0)) {   // developer switch: the table CTAs as a launch of their own
+        CU(launch(ehb_k_front, dim3((unsigned)tableBlocks), dim3(256), 0, st, false, rb, p, tableBlocks, vchunks, batchBlocks, clearBlocks, chunks, 0));
+        CU(launch(ehb_k_front, dim3(restBlocks), dim3(256), 0, st, false, rb, p, tableBlocks, vchunks, batchBlocks, clearBlocks, chunks, tableBlocks));
+    } else {
+        CU(launch(ehb_k_front, dim3((unsigned)tableBlocks + restBlocks), dim3(256), 0, st, false, rb, p, tableBlocks, vchunks, batchBlocks,
+                  clearBlocks, chunks, 0));
+    }
     if (ev) cudaEventRecord(ev[2], st);
     CU(launch(ehb_k_raster, dim3((unsigned)(streamBlocks + rasterBlocks)), dim3(EHB_RWARPS * 32), 0, st, true, rb, p, streamBlocks, chunks));
     CU(launch(ehb_k_raster_big, dim3(c->nSM * EHB_BMIN_BLOCKS), dim3(256), 0, st, true, p));
@@ -654,7 +658,7 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
         CU(launch(ehb_tiles_kernel(mode, refKind, io.do_bwd != 0), dim3(grid), dim3(EHB_TTHREADS), 0, st, true, rb, p));
     }
     if (ev) cudaEventRecord(ev[4], st);
-    c->launches += 5;   // table, front, raster, raster_big, tiles | union_out
+    c->launches += 4;   // front, raster, raster_big, tiles | union_out
     CU(cudaGetLastError());
     return EHB_OK;
 }
@@ -833,6 +837,14 @@ int ehb_ctx_debug_buffer(ehb_ctx_t h, unsigned long long* out, int n_words)
     if (!c->dbgbuf) { CU(cudaMalloc((void**)&c->dbgbuf, words * 8)); CU(cudaMemset(c->dbgbuf, 0, words * 8)); return EHB_OK; }
     CU(cudaDeviceSynchronize());
     if (out && n_words > 0) CU(cudaMemcpy(out, c->dbgbuf, std::min((size_t)n_words, words) * 8, cudaMemcpyDeviceToHost));
+    return EHB_OK;
+}
+
+int ehb_ctx_debug_marks(ehb_ctx_t h, unsigned* out16)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || !out16 || !c->hostFlags) return fail(EHB_E_ARG, "no marks");
+    for (int i = 0; i < 16; i++) out16[i] = ((volatile unsigned*)c->hostFlags)[i];
     return EHB_OK;
 }
 

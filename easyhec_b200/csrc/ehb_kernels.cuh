@@ -51,9 +51,12 @@ struct __align__(128) EhbCounters {
     unsigned int nEmpty;     // tiles no link touches: streamed (mask = 0, loss += ref^2) by spare CTAs of the raster launch
     unsigned int vertexDone; // CTAs of k_table that have finished: the last one allocates the planes
     unsigned int flags;      // 1: plane pool too small (results invalid, grow and rerun), 2: triangles need clipping
-    unsigned int pad0[22];
-    // line 1: the ticket counter of k_raster's persistent warps, alone on its line (thousands of atomics per pass)
-    unsigned int rasterCursor;
+    unsigned int nBatchHeavy; // visible 32-triangle batches with a large screen footprint: listed from the front of batchList ...
+    unsigned int nBatchLight; // ... the other visible ones from the back (k_front writes, k_raster reads, k_raster_big resets)
+    unsigned int pad0[20];
+    // line 1: set by the last table CTA of k_front when the planes of the pass are allocated and the list counters are
+    // reset; the CTAs of the same launch that need the planes wait for it (k_raster resets it)
+    unsigned int tableReady;
     unsigned int pad1[31];
     unsigned int pad2[32];
     // lines 4..35: the queues of deferred work, split into EHB_NQ sub-queues with their counters on separate lines --
@@ -84,7 +87,8 @@ struct EhbParams {
     int H, W, ntx, nty, ntiles;
     int items, L, Lp, Ftot, Vtot;   // Lp = planes per item: L (per-link visibility) or 1 (packed robot)
     int hlo, hhi;
-    int rasterStart;         // first ticket the persistent warps of k_raster draw (EHB_RPERSIST builds)
+    uint32_t* batchList;     // [items * chunks]  the batches that survive the frustum test of their AABB (k_front)
+    float heavyArea;         // screen footprint (px^2) of a batch's AABB from which it is listed in front
     int mode, rule, do_bwd, clamp;
     float invB;
     float xs, xo, ys, yo;    // NDC of a pixel centre: x = xs * px + xo, y = ys * py + yo (2/W, 1/W - 1, 2/H, 1/H - 1 in fp32)
@@ -149,6 +153,11 @@ __device__ __forceinline__ unsigned ehb_smid() { unsigned s; asm("mov.u32 %0, %%
 #define EHB_TL_STOP(p, k, idx, var)
 #endif
 
+#ifdef EHB_MARKS
+#define EHB_MARK(p, i) do { if ((p).hostFlags) *reinterpret_cast<volatile unsigned int*>((p).hostFlags + (i)) = 1u; } while (0)
+#else
+#define EHB_MARK(p, i)
+#endif
 #ifndef EHB_SMALL_AREA
 #define EHB_SMALL_AREA 96               // triangles whose clipped bbox has more candidate samples are deferred
 #endif
@@ -193,102 +202,6 @@ __device__ __forceinline__ double ehb_warp_sum(double v)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
-}
-
-// ------------------------------------------------------------------------------------------------ k_table
-// One warp per depth plane: conservative screen bounding box of the link from the projected corners of its (up to
-// 32) object-space chunk AABBs -- 256 point transforms instead of a reduction over all vertices, and no dependency on
-// the vertex pass.  The last CTA to finish (atomic ticket) bump-allocates the planes in the pool.
-__global__ void __launch_bounds__(256) ehb_k_table(const __grid_constant__ EhbRobot rb,
-                                                   const __grid_constant__ EhbParams p)
-{
-    ehb_pdl_enter();
-    EHB_TL_START(tl0);
-    const int lane = threadIdx.x & 31;
-    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        p.ctr->nTiles = 0u; p.ctr->nLight = 0u; p.ctr->nEmpty = 0u; p.ctr->workCursor = 0u;
-        p.ctr->rasterCursor = (unsigned)p.rasterStart;
-        p.ctr->slabCursor = 0u;
-    }
-    if (blockIdx.x == 0 && threadIdx.x < EHB_NQ) {
-        p.ctr->q[threadIdx.x].nBigRec = 0u; p.ctr->q[threadIdx.x].nUnits = 0u; p.ctr->q[threadIdx.x].nBatchBlk = 0u; p.ctr->q[threadIdx.x].take = 0u;
-    }
-    // outputs that the later kernels accumulate into
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.items; i += gridDim.x * blockDim.x) {
-        if (p.loss) p.loss[i] = p.refTotal ? (double)p.refTotal[i] : 0.0;
-    }
-    if (p.gmvp)
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.items * p.L * 16; i += gridDim.x * blockDim.x) p.gmvp[i] = 0.0;
-    if (wid < p.items * p.Lp) {
-        const int item = wid / p.Lp, pli = wid - item * p.Lp;
-        float umin = 3.0e38f, umax = -3.0e38f, vmin = 3.0e38f, vmax = -3.0e38f;
-        bool bad = false, any = false;
-        const int l0 = p.Lp == 1 ? 0 : pli, l1 = p.Lp == 1 ? p.L : pli + 1;
-        for (int l = l0; l < l1; l++) {
-            const EhbLink& lk = rb.link[l];
-            if (lane < lk.nboxes) {
-                float m[16];
-                ehb_load_mvp(p.mvp + ((size_t)item * p.L + l) * 16, m);
-                const float4 lo = __ldg(lk.boxes + 2 * lane), hi = __ldg(lk.boxes + 2 * lane + 1);
-                any = true;
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const float4 v = make_float4((k & 1) ? hi.x : lo.x, (k & 2) ? hi.y : lo.y, (k & 4) ? hi.z : lo.z, 1.f);
-                    float c[4];
-                    ehb_xform(v, m, c);
-                    if (!(c[3] > 1e-6f)) { bad = true; continue; }   // corner at or behind the camera plane: no finite bound
-                    const float u = (c[0] / c[3] + 1.f) * (0.5f * (float)p.W), w = (c[1] / c[3] + 1.f) * (0.5f * (float)p.H);
-                    umin = fminf(umin, u); umax = fmaxf(umax, u); vmin = fminf(vmin, w); vmax = fmaxf(vmax, w);
-                }
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            umin = fminf(umin, __shfl_xor_sync(0xffffffffu, umin, o)); umax = fmaxf(umax, __shfl_xor_sync(0xffffffffu, umax, o));
-            vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o)); vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-        }
-        bad = __any_sync(0xffffffffu, bad);
-        any = __any_sync(0xffffffffu, any);
-        if (lane == 0) {
-            EhbPlane pl;
-            pl.x0 = pl.y0 = pl.w = pl.h = 0; pl.off = 0; pl.pad = 0;
-            if (any) {
-                int x0 = 0, y0 = 0, x1 = p.W - 1, y1 = p.H - 1;
-                if (!bad) {   // pixel p is sampled at p + 0.5; two pixels of margin cover snapping and rounding
-                    x0 = max(0, (int)fmaxf(fminf(floorf(umin) - 2.f, 1e6f), -1e6f)); x1 = min(p.W - 1, (int)fmaxf(fminf(ceilf(umax) + 2.f, 1e6f), -1e6f));
-                    y0 = max(0, (int)fmaxf(fminf(floorf(vmin) - 2.f, 1e6f), -1e6f)); y1 = min(p.H - 1, (int)fmaxf(fminf(ceilf(vmax) + 2.f, 1e6f), -1e6f));
-                }
-                if (x0 <= x1 && y0 <= y1) { pl.x0 = x0; pl.y0 = y0; pl.w = x1 - x0 + 1; pl.h = y1 - y0 + 1; }
-            }
-            p.plane[wid] = pl;
-        }
-    }
-    // the last CTA to finish sees every bounding box: it bump-allocates the planes of this pass
-    __shared__ unsigned s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(&p.ctr->vertexDone, 1u) == gridDim.x - 1u;
-    __syncthreads();
-    if (!s_last) { if (threadIdx.x == 0) EHB_TL_STOP(p, 0, blockIdx.x, tl0); return; }
-    __threadfence();
-    if (threadIdx.x == 0) { p.ctr->vertexDone = 0u; p.ctr->planeCursor = 0ull; }
-    __syncthreads();
-    for (int i = threadIdx.x; i < p.items * p.Lp; i += blockDim.x) {
-        EhbPlane pl;
-        {
-            const int4 a = __ldcg(reinterpret_cast<const int4*>(&p.plane[i]));   // written by other CTAs of this launch: read at L2
-            pl.x0 = a.x; pl.y0 = a.y; pl.w = a.z; pl.h = a.w; pl.off = 0; pl.pad = 0;
-        }
-        if (pl.w > 0) {
-            const unsigned long long area = (unsigned long long)pl.w * (unsigned long long)pl.h;
-            const unsigned long long off = atomicAdd(&p.ctr->planeCursor, area);
-            if (off + area <= p.poolCap) pl.off = (long long)off;
-            else { pl.w = pl.h = 0; ehb_raise(p, 1u); }
-            p.plane[i] = pl;
-        }
-    }
-    if (threadIdx.x == 0) EHB_TL_STOP(p, 0, blockIdx.x, tl0);
 }
 
 // ------------------------------------------------------------------------------------------------ empty tiles
@@ -374,17 +287,163 @@ __device__ __forceinline__ void ehb_stream_empty_tile(const EhbParams& p, int it
 }
 
 // ------------------------------------------------------------------------------------------------ k_front
-// Three independent jobs in one launch (block ranges): (a) transform + snap every vertex once, (b) planes := EMPTY and
-// link bitmaps := 0, (c) tile classification, one warp per tile.
-__global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRobot rb,
-                                                   const __grid_constant__ EhbParams p, int vchunks, int clearBlocks)
+// ONE launch in front of the rasterizer, five kinds of CTAs (block ranges, in this order):
+//   (T) table     one warp per depth plane: conservative screen bounding box of the link from the projected corners of its
+//                 (up to 32) object-space chunk AABBs -- 256 point transforms instead of a reduction over all vertices.  The
+//                 last table CTA to finish (atomic ticket) allocates the planes of the pass in the pool by a block-wide
+//                 prefix sum (deterministic), resets the list counters and raises ctr->tableReady.
+//   (V) vertices  one thread per (item, vertex): transform and snap ONCE (a vertex is shared by ~6 triangles), keep the
+//                 clip-space and snapped positions (a few MB, L2-resident)
+//   (B) batches   frustum test of every 32-triangle batch's object-space AABB (8 corners, one per lane): the batches that
+//                 survive are listed -- large screen footprints from the front, the rest from the back -- so that k_raster
+//                 runs only warps that have something to draw, the long ones first
+//   (C) clear     planes := EMPTY (allocated part only), link bitmaps := 0          } wait for tableReady (the table CTAs
+//   (L) tiles     one lane per tile: tiles that some link's bbox touches -> tile     }  have the lowest block indices: they
+//                 list (several links first), the others -> empty-tile list         }  are resident before any waiter)
+// V and B do not depend on the table and sit between T and the waiters: by the time C and L are dispatched the table is
+// usually ready.  (As two launches -- table, then the rest -- the pass paid one more launch gap and the table's 4 us with
+// 9 CTAs on the chip.)
+__device__ __forceinline__ void ehb_wait_table(const EhbParams& p)
+{
+    if (threadIdx.x == 0) {
+        unsigned v;
+        EHB_MARK(p, 11);
+        for (;;) {
+            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(&p.ctr->tableReady) : "memory");
+            if (v) break;
+            __nanosleep(64);
+        }
+        EHB_MARK(p, 7);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRobot rb, const __grid_constant__ EhbParams p,
+                                                   int tableBlocks, int vchunks, int batchBlocks, int clearBlocks, int chunks,
+                                                   int blockBase)
 {
     ehb_pdl_enter();
     EHB_TL_START(tl0);
+    const int lane = threadIdx.x & 31;
+    int blk = (int)blockIdx.x + blockBase;   // (blockBase != 0: the launch without the table CTAs, developer switch EHB_FRONT_SPLIT)
+    // ---------------------------------------------------------------- (T) table
+    if (blk < tableBlocks) {
+        EHB_MARK(p, 4);
+        const int wid = (blk * (int)blockDim.x + (int)threadIdx.x) >> 5;
+        // outputs that the later kernels accumulate into
+        for (int i = blk * blockDim.x + threadIdx.x; i < p.items; i += tableBlocks * blockDim.x)
+            if (p.loss) p.loss[i] = p.refTotal ? (double)p.refTotal[i] : 0.0;
+        if (p.gmvp)
+            for (int i = blk * blockDim.x + threadIdx.x; i < p.items * p.L * 16; i += tableBlocks * blockDim.x) p.gmvp[i] = 0.0;
+        if (wid < p.items * p.Lp) {
+            const int item = wid / p.Lp, pli = wid - item * p.Lp;
+            float umin = 3.0e38f, umax = -3.0e38f, vmin = 3.0e38f, vmax = -3.0e38f;
+            bool bad = false, any = false;
+            const int l0 = p.Lp == 1 ? 0 : pli, l1 = p.Lp == 1 ? p.L : pli + 1;
+            for (int l = l0; l < l1; l++) {
+                const EhbLink& lk = rb.link[l];
+                if (lane < lk.nboxes) {
+                    float m[16];
+                    ehb_load_mvp(p.mvp + ((size_t)item * p.L + l) * 16, m);
+                    const float4 lo = __ldg(lk.boxes + 2 * lane), hi = __ldg(lk.boxes + 2 * lane + 1);
+                    any = true;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const float4 v = make_float4((k & 1) ? hi.x : lo.x, (k & 2) ? hi.y : lo.y, (k & 4) ? hi.z : lo.z, 1.f);
+                        float c[4];
+                        ehb_xform(v, m, c);
+                        if (!(c[3] > 1e-6f)) { bad = true; continue; }   // corner at or behind the camera plane: no finite bound
+                        const float u = (c[0] / c[3] + 1.f) * (0.5f * (float)p.W), w = (c[1] / c[3] + 1.f) * (0.5f * (float)p.H);
+                        umin = fminf(umin, u); umax = fmaxf(umax, u); vmin = fminf(vmin, w); vmax = fmaxf(vmax, w);
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                umin = fminf(umin, __shfl_xor_sync(0xffffffffu, umin, o)); umax = fmaxf(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+                vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o)); vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+            }
+            bad = __any_sync(0xffffffffu, bad);
+            any = __any_sync(0xffffffffu, any);
+            if (lane == 0) {
+                EhbPlane pl;
+                pl.x0 = pl.y0 = pl.w = pl.h = 0; pl.off = 0; pl.pad = 0;
+                if (any) {
+                    int x0 = 0, y0 = 0, x1 = p.W - 1, y1 = p.H - 1;
+                    if (!bad) {   // pixel p is sampled at p + 0.5; two pixels of margin cover snapping and rounding
+                        x0 = max(0, (int)fmaxf(fminf(floorf(umin) - 2.f, 1e6f), -1e6f)); x1 = min(p.W - 1, (int)fmaxf(fminf(ceilf(umax) + 2.f, 1e6f), -1e6f));
+                        y0 = max(0, (int)fmaxf(fminf(floorf(vmin) - 2.f, 1e6f), -1e6f)); y1 = min(p.H - 1, (int)fmaxf(fminf(ceilf(vmax) + 2.f, 1e6f), -1e6f));
+                    }
+                    if (x0 <= x1 && y0 <= y1) { pl.x0 = x0; pl.y0 = y0; pl.w = x1 - x0 + 1; pl.h = y1 - y0 + 1; }
+                }
+                p.plane[wid] = pl;
+            }
+        }
+        // the last table CTA to finish sees every bounding box: it allocates the planes of this pass
+        __shared__ unsigned s_last;
+        __shared__ unsigned long long s_wsum[8], s_base;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(&p.ctr->vertexDone, 1u) == (unsigned)tableBlocks - 1u;
+        __syncthreads();
+        if (!s_last) { if (threadIdx.x == 0) EHB_TL_STOP(p, 0, blockIdx.x, tl0); return; }
+        __threadfence();
+        EHB_MARK(p, 5);
+        if (threadIdx.x == 0) {
+            s_base = 0ull;
+            p.ctr->vertexDone = 0u;
+            p.ctr->nTiles = 0u; p.ctr->nLight = 0u; p.ctr->nEmpty = 0u; p.ctr->workCursor = 0u; p.ctr->slabCursor = 0u;
+        }
+        if (threadIdx.x < EHB_NQ) {
+            p.ctr->q[threadIdx.x].nBigRec = 0u; p.ctr->q[threadIdx.x].nUnits = 0u; p.ctr->q[threadIdx.x].nBatchBlk = 0u;
+            p.ctr->q[threadIdx.x].take = 0u;
+        }
+        __syncthreads();
+        const int warp = threadIdx.x >> 5;
+        for (int i0 = 0; i0 < p.items * p.Lp; i0 += blockDim.x) {      // block-wide exclusive prefix sum of the plane areas
+            const int i = i0 + threadIdx.x;
+            EhbPlane pl;
+            pl.x0 = pl.y0 = pl.w = pl.h = 0; pl.off = 0; pl.pad = 0;
+            if (i < p.items * p.Lp) {
+                const int4 a = __ldcg(reinterpret_cast<const int4*>(&p.plane[i]));   // written by other CTAs of this launch: read at L2
+                pl.x0 = a.x; pl.y0 = a.y; pl.w = a.z; pl.h = a.w;
+            }
+            const unsigned long long area = (unsigned long long)pl.w * (unsigned long long)pl.h;
+            unsigned long long inc = area;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            if (lane == 31) s_wsum[warp] = inc;
+            __syncthreads();
+            unsigned long long before = s_base;
+            for (int w = 0; w < warp; w++) before += s_wsum[w];
+            const unsigned long long off = before + inc - area;
+            if (pl.w > 0) {
+                if (off + area <= p.poolCap) pl.off = (long long)off;
+                else { pl.w = pl.h = 0; ehb_raise(p, 1u); }
+                p.plane[i] = pl;
+            }
+            __syncthreads();
+            if (threadIdx.x == blockDim.x - 1) s_base = before + inc;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            p.ctr->planeCursor = min(s_base, p.poolCap);
+            __threadfence();
+            asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(&p.ctr->tableReady), "r"(1u) : "memory");
+            EHB_MARK(p, 6);
+            EHB_TL_STOP(p, 0, blockIdx.x, tl0);
+        }
+        return;
+    }
+    blk -= tableBlocks;
+    // ---------------------------------------------------------------- (V) vertices
     const int vertexBlocks = vchunks * p.items;
-    if ((int)blockIdx.x < vertexBlocks) {
-        const int item = blockIdx.x / vchunks;
-        const int g = (blockIdx.x - item * vchunks) * blockDim.x + threadIdx.x;
+    if (blk < vertexBlocks) {
+        const int item = blk / vchunks;
+        const int g = (blk - item * vchunks) * blockDim.x + threadIdx.x;
         if (g >= p.Vtot) return;
         const int lk = ehb_find_link(rb.voff, rb.L, g);
         float m[16], c[4];
@@ -400,24 +459,93 @@ __global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRo
         if (threadIdx.x == 0) EHB_TL_STOP(p, 1, blockIdx.x, tl0);
         return;
     }
-    const int cb = (int)blockIdx.x - vertexBlocks;
-    if (cb < clearBlocks) {
-        const unsigned long long total = min(p.ctr->planeCursor, p.poolCap);
-        const unsigned long long n2 = total >> 1;
-        ulonglong2* p2 = reinterpret_cast<ulonglong2*>(p.pool);
-        for (unsigned long long i = (unsigned long long)cb * blockDim.x + threadIdx.x; i < n2;
-             i += (unsigned long long)clearBlocks * blockDim.x)
-            p2[i] = make_ulonglong2(EHB_EMPTY, EHB_EMPTY);
-        if ((total & 1ull) && cb == 0 && threadIdx.x == 0) p.pool[total - 1] = EHB_EMPTY;
-        if (p.touch)
-            for (int i = cb * blockDim.x + threadIdx.x; i < p.items * p.ntiles; i += clearBlocks * blockDim.x) p.touch[i] = 0u;
+    blk -= vertexBlocks;
+    // ---------------------------------------------------------------- (B) visible batches
+    if (blk < batchBlocks) {
+        // 8 lanes per batch (one per corner of its AABB), 32 batches per CTA.  When every corner is in front of the camera
+        // and all of them lie beyond one side of the screen (two pixels of margin for snapping and rounding), every vertex
+        // of the batch does too (projection keeps convex hulls when w > 0), so each of its triangles would fail the
+        // per-triangle tests: the batch is not listed.
+        const int total = chunks * p.items;
+        const int b = blk * 32 + (int)(threadIdx.x >> 3);
+        const int k = threadIdx.x & 7;
+        const unsigned gm = 0xFFu << (lane & 24);             // the lanes of this batch
+        bool front = false, oxr = false, oxl = false, oyt = false, oyb = false, emptyBox = true;
+        float u = 0.f, v = 0.f;
+        if (b < total) {
+            const int item = b / chunks, bl = b - item * chunks;
+            const int link = ehb_find_link(rb.boff, rb.L, bl);
+            const float4* fb = rb.link[link].fboxes + 2 * (bl - rb.boff[link]);
+            const float4 lo = __ldg(fb), hi = __ldg(fb + 1);
+            float m[16], c[4];
+            ehb_load_mvp(p.mvp + ((size_t)item * p.L + link) * 16, m);
+            ehb_xform(make_float4((k & 1) ? hi.x : lo.x, (k & 2) ? hi.y : lo.y, (k & 4) ? hi.z : lo.z, 1.f), m, c);
+            front = c[3] > 1e-6f;
+            const float mx = 4.f / (float)p.W, my = 4.f / (float)p.H;
+            oxr = c[0] - (1.f + mx) * c[3] > 0.f; oxl = -c[0] - (1.f + mx) * c[3] > 0.f;   // beyond the right / left side
+            oyt = c[1] - (1.f + my) * c[3] > 0.f; oyb = -c[1] - (1.f + my) * c[3] > 0.f;
+            emptyBox = lo.x > hi.x;
+            if (front) { u = c[0] / c[3] * (0.5f * (float)p.W); v = c[1] / c[3] * (0.5f * (float)p.H); }
+        }
+        const unsigned bf = __ballot_sync(0xffffffffu, front);
+        const bool allFront = (bf & gm) == gm;
+        // (every ballot is taken by the whole warp before the results are combined: the 8-lane groups differ)
+        const unsigned bxr = __ballot_sync(0xffffffffu, oxr), bxl = __ballot_sync(0xffffffffu, oxl);
+        const unsigned byt = __ballot_sync(0xffffffffu, oyt), byb = __ballot_sync(0xffffffffu, oyb);
+        const bool out = (bxr & gm) == gm || (bxl & gm) == gm || (byt & gm) == gm || (byb & gm) == gm;
+        // screen footprint of the AABB (finite when every corner is in front): a batch with large triangles keeps its warp
+        // busy several times longer than the median -- those go first
+        float umin = u, umax = u, vmin = v, vmax = v;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            umin = fminf(umin, __shfl_xor_sync(0xffffffffu, umin, o)); umax = fmaxf(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+            vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o)); vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        }
+        const bool visible = b < total && !(allFront && out) && !emptyBox;
+        const bool leader = k == 0;
+        const bool heavy = visible && (!allFront || (umax - umin) * (vmax - vmin) >= p.heavyArea);
+        const unsigned bh = __ballot_sync(0xffffffffu, leader && heavy), bl_ = __ballot_sync(0xffffffffu, leader && visible && !heavy);
+        __shared__ unsigned s_cnt[8][2], s_baseHL[2];
+        const int warp = threadIdx.x >> 5;
+        if (lane == 0) { s_cnt[warp][0] = __popc(bh); s_cnt[warp][1] = __popc(bl_); }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            unsigned t = 0;
+            for (int w = 0; w < 8; w++) t += s_cnt[w][threadIdx.x];
+            s_baseHL[threadIdx.x] = t ? atomicAdd(threadIdx.x == 0 ? &p.ctr->nBatchHeavy : &p.ctr->nBatchLight, t) : 0u;
+        }
+        __syncthreads();
+        if (leader && visible) {
+            unsigned o = s_baseHL[heavy ? 0 : 1];
+            for (int w = 0; w < warp; w++) o += s_cnt[w][heavy ? 0 : 1];
+            o += __popc((heavy ? bh : bl_) & ((1u << lane) - 1u));
+            p.batchList[heavy ? o : (unsigned)total - 1u - o] = (uint32_t)b;
+        }
         if (threadIdx.x == 0) EHB_TL_STOP(p, 1, blockIdx.x, tl0);
         return;
     }
-    // (c) one LANE per tile; the three list counters get one atomic per warp each (a tile per warp meant ten thousand
+    blk -= batchBlocks;
+    // ---------------------------------------------------------------- (C) clear
+    if (blk < clearBlocks) {
+        ehb_wait_table(p);
+        const unsigned long long total = min(*(volatile unsigned long long*)&p.ctr->planeCursor, p.poolCap);
+        const unsigned long long n2 = total >> 1;
+        ulonglong2* p2 = reinterpret_cast<ulonglong2*>(p.pool);
+        for (unsigned long long i = (unsigned long long)blk * blockDim.x + threadIdx.x; i < n2;
+             i += (unsigned long long)clearBlocks * blockDim.x)
+            p2[i] = make_ulonglong2(EHB_EMPTY, EHB_EMPTY);
+        if ((total & 1ull) && blk == 0 && threadIdx.x == 0) p.pool[total - 1] = EHB_EMPTY;
+        if (p.touch)
+            for (int i = blk * blockDim.x + threadIdx.x; i < p.items * p.ntiles; i += clearBlocks * blockDim.x) p.touch[i] = 0u;
+        if (threadIdx.x == 0) EHB_TL_STOP(p, 1, blockIdx.x, tl0);
+        return;
+    }
+    blk -= clearBlocks;
+    // ---------------------------------------------------------------- (L) tile lists
+    // one LANE per tile; the three list counters get one atomic per warp each (a tile per warp meant ten thousand
     // same-address atomics per pass, which serialise on their L2 line)
-    const int wid = (cb - clearBlocks) * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
+    ehb_wait_table(p);
+    const int wid = blk * blockDim.x + threadIdx.x;
     const bool valid = wid < p.items * p.ntiles;
     int nhit = 0;
     if (valid) {
@@ -426,7 +554,7 @@ __global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRo
         const int rx0 = tx * EHB_T - p.hlo, ry0 = ty * EHB_T - p.hlo;
         const int rx1 = tx * EHB_T + EHB_T - 1 + p.hhi, ry1 = ty * EHB_T + EHB_T - 1 + p.hhi;
         for (int l = 0; l < p.Lp; l++) {
-            const int4 pl = *reinterpret_cast<const int4*>(&p.plane[(size_t)item * p.Lp + l]);   // x0, y0, w, h
+            const int4 pl = __ldcg(reinterpret_cast<const int4*>(&p.plane[(size_t)item * p.Lp + l]));   // x0, y0, w, h
             nhit += pl.z > 0 && pl.x <= rx1 && pl.x + pl.z - 1 >= rx0 && pl.y <= ry1 && pl.y + pl.w - 1 >= ry0;
         }
     }
@@ -450,9 +578,6 @@ __global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRo
 // ------------------------------------------------------------------------------------------------ k_raster
 #ifndef EHB_RWARPS
 #define EHB_RWARPS 8         // warps per raster CTA; every warp works alone on batches of 32 triangles
-#endif
-#ifndef EHB_RBATCH
-#define EHB_RBATCH 1         // 32-triangle batches per ticket
 #endif
 #ifndef EHB_RINLINE
 #define EHB_RINLINE 2        // groups of 32 rows a warp of k_raster draws itself; the rest of a heavy batch is handed on
@@ -811,49 +936,31 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
         }
         return;
     }
-    // Every warp starts with the batch (32 triangles) of its own index.  EHB_RPERSIST builds launch one wave of CTAs and
-    // let the warps draw further tickets (EHB_RBATCH batches each) from a counter that k_table set to the number of
-    // warps; the default launches one warp per batch (measured faster: the tickets serialise on one L2 line).
+    // One warp per listed batch (32 consecutive faces of one link of one item): k_front listed the batches that survive the
+    // frustum test of their AABB, the ones with a large screen footprint first.  The grid covers every batch of the pass;
+    // the warps beyond the list leave at once.
+    if (blockIdx.x == (unsigned)streamBlocks && threadIdx.x == 0) p.ctr->tableReady = 0u;   // k_front is complete: re-arm its flag
+    EHB_MARK(p, 8);
     const int total = chunks * p.items;   // chunks = 32-triangle batches per item
-    unsigned bcur = (unsigned)(((int)blockIdx.x - streamBlocks) * EHB_RWARPS + warp) * (unsigned)EHB_RBATCH, bnext = 0xFFFFFFFFu;
+    const unsigned e = (unsigned)(((int)blockIdx.x - streamBlocks) * EHB_RWARPS + warp);
+    const unsigned listed = e < (unsigned)total ? p.batchList[e] : 0u;               // (speculative: issued with the counters)
+    const unsigned nHeavy = p.ctr->nBatchHeavy, nLight = p.ctr->nBatchLight;
+    if (e >= nHeavy + nLight) return;
+    const unsigned bcur = e < nHeavy ? listed : p.batchList[(unsigned)total - 1u - (e - nHeavy)];
     const float xs = p.xs, xo = p.xo, ys = p.ys, yo = p.yo;
     const EhbRecSoA recs{s_rec[warp]};
     int* off = s_off[warp];
-    for (int sub = 0; bcur < (unsigned)total;) {
-    // a ticket is EHB_RBATCH consecutive batches; the next ticket is drawn when the last batch of this one starts
-#ifdef EHB_RPERSIST
-    if (lane == 0 && sub == EHB_RBATCH - 1) bnext = atomicAdd(&p.ctr->rasterCursor, (unsigned)EHB_RBATCH);
-#endif
+    {
     const int qi = (int)(bcur & (EHB_NQ - 1));            // this batch's sub-queue
     EhbCounters::Q& myq = p.ctr->q[qi];
     const int item = (int)bcur / chunks;
-    const int bl = (int)bcur - item * chunks;             // batch of the item: 32 consecutive faces of ONE link
+    const int bl = (int)bcur - item * chunks;             // batch of the item
     const int link = ehb_find_link(rb.boff, rb.L, bl);    // (warp-uniform)
     const int f = (bl - rb.boff[link]) * 32 + lane;
     int rows = 0, wide = 0, touchRows = 0;
     bool big = false, needClip = false;
     int4 tb = make_int4(0, 0, 0, 0);   // clipped bbox of this lane's triangle (x0, y0, w, h)
-    // Frustum cull of the whole batch: the 8 corners of its object-space AABB, one per lane.  When every corner is in
-    // front of the camera and all of them lie beyond one side of the screen (two pixels of margin for snapping and
-    // rounding), every vertex of the batch does too (projection keeps convex hulls when w > 0), so each of its triangles
-    // would fail the per-triangle tests: nothing to load, nothing to set up.
-    bool visible = true;
-    {
-        const float4* fb = rb.link[link].fboxes + 2 * (bl - rb.boff[link]);
-        const float4 lo = __ldg(fb), hi = __ldg(fb + 1);
-        float m[16], c[4];
-        ehb_load_mvp(p.mvp + ((size_t)item * p.L + link) * 16, m);
-        const int k = lane & 7;
-        ehb_xform(make_float4((k & 1) ? hi.x : lo.x, (k & 2) ? hi.y : lo.y, (k & 4) ? hi.z : lo.z, 1.f), m, c);
-        const bool front = c[3] > 1e-6f;
-        const float mx = 4.f / (float)p.W, my = 4.f / (float)p.H;
-        const float xr = c[0] - (1.f + mx) * c[3], xl = -c[0] - (1.f + mx) * c[3];   // > 0: beyond the right / left side
-        const float yt = c[1] - (1.f + my) * c[3], yb = -c[1] - (1.f + my) * c[3];
-        const bool allFront = __all_sync(0xffffffffu, front);
-        const bool out = __all_sync(0xffffffffu, xr > 0.f) || __all_sync(0xffffffffu, xl > 0.f) ||
-                         __all_sync(0xffffffffu, yt > 0.f) || __all_sync(0xffffffffu, yb > 0.f);
-        visible = !(allFront && out) && !(lo.x > hi.x);
-    }
+    const bool visible = true;
     if (visible && f < rb.link[link].F) {
         EhbRec rc;
         rows = ehb_make_record(rb, p, item, link, f, rc, needClip);
@@ -1005,10 +1112,7 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
     if (__any_sync(0xffffffffu, needClip)) {
         if (needClip) ehb_emit_clipped(rb, p, item, link, f, qi);
     }
-    __syncwarp();   // the records of this batch are dead: the next one may overwrite them
     if (lane == 0) EHB_TL_STOP(p, 2, ((int)blockIdx.x - streamBlocks) * EHB_RWARPS + warp, tl0);
-    if (++sub == EHB_RBATCH) { sub = 0; bcur = __shfl_sync(0xffffffffu, bnext, 0); }
-    else bcur++;
     }
 }
 
@@ -1025,6 +1129,8 @@ __global__ void __launch_bounds__(256, EHB_BMIN_BLOCKS) ehb_k_raster_big(const _
     __shared__ __align__(128) uint32_t s_blk[8][EHB_BLK_WORDS];
     __shared__ __align__(8) uint64_t s_bar[8];           // one mbarrier per warp: completion of its bulk copies
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { p.ctr->nBatchHeavy = 0u; p.ctr->nBatchLight = 0u; }   // k_raster is complete
+    EHB_MARK(p, 9);
     if (lane == 0) ehb_mbar_init(&s_bar[warp], 1);
     ehb_fence_mbar_init();
     __syncwarp();
@@ -1110,6 +1216,7 @@ __global__ void __launch_bounds__(256, EHB_BMIN_BLOCKS) ehb_k_raster_big(const _
         else ehb_rows_group<int, float, EhbRecAoS>(rv, t, dy, lane, p.pool, xs, xo, ys, yo, cur.dx0, cur.dx0 + EHB_UNIT_W - 1);
     }
     if (lane == 0) EHB_TL_STOP(p, 3, blockIdx.x * 8 + warp, tl0);
+    EHB_MARK(p, 12);
 }
 
 // UNION (packed robot, no antialiasing): mask = (z/w of the nearest triangle > 0), straight from the item's plane.

@@ -430,6 +430,7 @@ __global__ void __launch_bounds__(EHB_TTHREADS, 7) ehb_k_tiles(const __grid_cons
 {
     ehb_pdl_enter();
     EHB_TL_START(tl0);
+    EHB_MARK(p, 10);
     __shared__ EhbTileSm sm;
     constexpr bool NEEDAA = MODE == 0;
     constexpr int OW = EHB_T + ((NEEDAA && BWD) ? 1 : 0);   // out region whose S is needed (33 when g is needed on it)

@@ -88,6 +88,8 @@ EHB_API int ehb_ctx_debug_counters(ehb_ctx_t ctx, unsigned long long* out16, int
 /* Developer aid: first call allocates a device scratch buffer that debug builds may fill, later calls copy up to
  * n_words 64-bit words of it out. */
 EHB_API int ehb_ctx_debug_buffer(ehb_ctx_t ctx, unsigned long long* out, int n_words);
+/* developer builds (-DEHB_MARKS): progress marks the kernels leave in host-visible memory, readable while a kernel runs */
+EHB_API int ehb_ctx_debug_marks(ehb_ctx_t ctx, unsigned* out16);
 /* Synchronises the device, returns and clears the sticky flags, reports the triangles that went through the clipper. */
 EHB_API int ehb_ctx_status(ehb_ctx_t ctx, unsigned* flags, long long* n_need_clip);
 /* The same sticky flags WITHOUT synchronising: the kernels also set them in host-visible (mapped) memory, so a caller can
