@@ -93,12 +93,14 @@ struct Scratch {
     DevBuf<EhbUnit> units;
     DevBuf<uint32_t> batchBlk;        // parked heavy batches of k_raster
     DevBuf<uint32_t> batchList;       // visible batches of the pass (k_front -> k_raster)
+    DevBuf<unsigned long long> bitPool;   // coverage bit per pixel of every plane (what the image-space stage reads)
+    DevBuf<EhbBitsRec> bigBits;       // bit-plane address of every parked record
     DevBuf<unsigned char> pairPool;   // slabs for tiles whose silhouette pairs do not fit shared memory (k_tiles)
     EhbCounters* ctr = nullptr;
     void release()
     {
         vclip.release(); vsnap.release(); plane.release(); pool.release(); tileList.release(); emptyList.release();
-        touch.release(); bigRec.release(); units.release(); batchBlk.release(); pairPool.release(); batchList.release();
+        touch.release(); bigRec.release(); units.release(); batchBlk.release(); pairPool.release(); batchList.release(); bitPool.release(); bigBits.release();
     }
 };
 
@@ -564,6 +566,10 @@ int ensure_scratch(Ctx* c, Scratch& sc, int items, int L, int Lp, int H, int W, 
     const double worst = (double)items * Lp * H * W;
     const double f = worst * 8.0 <= c->poolBudget ? (double)Lp : std::min(std::max(c->poolFactor, c->poolBudget / (8.0 * items * H * W)), (double)Lp);
     if ((r = sc.pool.ensure((size_t)((double)items * H * W * f) + 1024, capturing))) return r;
+    if (Lp == L) {   // coverage bits: a row of a plane is ceil(w / 64) <= w / 64 + 1 words
+        if ((r = sc.bitPool.ensure(sc.pool.n / 64 + (size_t)items * Lp * H + 1024, capturing))) return r;
+        if ((r = sc.bigBits.ensure(sc.bigRec.n, capturing))) return r;
+    }
     return EHB_OK;
 }
 
@@ -599,7 +605,7 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
     p.mvp = mvp_dev;
     p.vclip = sc.vclip.p; p.vsnap = sc.vsnap.p;
     p.plane = sc.plane.p; p.pool = sc.pool.p; p.poolCap = sc.pool.n;
-    p.tileList = sc.tileList.p; p.emptyList = sc.emptyList.p; p.touch = unionMode ? nullptr : sc.touch.p; p.bigRec = sc.bigRec.p; p.units = sc.units.p; p.bigCap = (int)(sc.bigRec.n / EHB_NQ); p.unitCap = (int)(sc.units.n / EHB_NQ); p.batchBlk = tune_int("EHB_NO_OFFLOAD", 0) ? nullptr : sc.batchBlk.p; p.batchCap = c->poolBudget == 0.0 ? 1 : BATCH_CAP / EHB_NQ; p.ctr = sc.ctr; p.batchList = sc.batchList.p; p.heavyArea = (float)tune_int("EHB_HEAVY_AREA", 1024);
+    p.tileList = sc.tileList.p; p.emptyList = sc.emptyList.p; p.touch = unionMode ? nullptr : sc.touch.p; p.bigRec = sc.bigRec.p; p.units = sc.units.p; p.bigCap = (int)(sc.bigRec.n / EHB_NQ); p.unitCap = (int)(sc.units.n / EHB_NQ); p.batchBlk = tune_int("EHB_NO_OFFLOAD", 0) ? nullptr : sc.batchBlk.p; p.batchCap = c->poolBudget == 0.0 ? 1 : BATCH_CAP / EHB_NQ; p.ctr = sc.ctr; p.bits = unionMode ? nullptr : sc.bitPool.p; p.bitCap = unionMode ? 0 : sc.bitPool.n; p.bigBits = unionMode ? nullptr : sc.bigBits.p; p.batchList = sc.batchList.p; p.heavyArea = (float)tune_int("EHB_HEAVY_AREA", 1024);
     p.ref = io.ref; p.ref_u8 = io.ref_u8; p.masks = io.masks; p.loss = io.loss; p.gmvp = io.gmvp; p.gpos = io.gpos;
     p.dy = io.dy; p.out_u8 = io.out_u8;
     p.refBits = io.refBits; p.refCnt = io.refCnt; p.refTotal = io.refTotal;

@@ -36,7 +36,7 @@ enum { EHB_MODE_FUSED = 0, EHB_MODE_AA_FWD = 1, EHB_MODE_AA_BWD = 2, EHB_MODE_UN
 struct EhbPlane {            // depth plane of one (item, link): pixels [x0, x0+w) x [y0, y0+h), GL rows
     int x0, y0, w, h;
     long long off;           // first element in the plane pool
-    long long pad;
+    long long boff;          // first 64-bit word of the plane's coverage bits in the bit pool (h rows of ceil(w / 64) words)
 };
 
 struct EhbUnit { uint32_t rec; unsigned short dx0, dy0; };   // a 64 x 32 pixel window of a deferred triangle's bbox
@@ -53,7 +53,8 @@ struct __align__(128) EhbCounters {
     unsigned int flags;      // 1: plane pool too small (results invalid, grow and rerun), 2: triangles need clipping
     unsigned int nBatchHeavy; // visible 32-triangle batches with a large screen footprint: listed from the front of batchList ...
     unsigned int nBatchLight; // ... the other visible ones from the back (k_front writes, k_raster reads, k_raster_big resets)
-    unsigned int pad0[20];
+    unsigned long long bitCursor;   // words of the bit pool in use
+    unsigned int pad0[18];
     // line 1: set by the last table CTA of k_front when the planes of the pass are allocated and the list counters are
     // reset; the CTAs of the same launch that need the planes wait for it (k_raster resets it)
     unsigned int tableReady;
@@ -98,6 +99,9 @@ struct EhbParams {
     EhbPlane* plane;         // [items, Lp]
     unsigned long long* pool;
     unsigned long long poolCap;
+    unsigned long long* bits;    // coverage bit per pixel of every plane (per-link visibility only): what the image-space stage
+    unsigned long long bitCap;   //   reads instead of the 64 times larger depth planes; NULL in the packed-robot mode
+    struct EhbBitsRec* bigBits;  // [bigCap * EHB_NQ]  bit-plane address of every parked record
     uint32_t* tileList;      // [items * ntiles]
     uint32_t* emptyList;     // [items * ntiles]
     uint32_t* touch;         // [items * ntiles]  bit l: a triangle of link l reaches into this tile's window
@@ -127,6 +131,35 @@ struct EhbParams {
     unsigned int* hostFlags;      // mapped pinned host memory: word b is set when flag bit b is raised (ehb_ctx_poll reads it
                                   // without synchronising)
 };
+
+// Coverage bits of a plane: bit (px - x0) of row (py - y0); a row is ceil(w / 64) words.  `base` folds the plane's origin in:
+// bit index in the pool = base + py * pitch + px.
+struct EhbBits { unsigned long long* w; long long base; int pitch; };
+struct __align__(16) EhbBitsRec { long long base; int pitch; int pad; };
+__device__ __forceinline__ EhbBits ehb_bits_of(unsigned long long* words, const EhbPlane& pl)
+{
+    EhbBits b;
+    b.w = words;
+    b.pitch = ((pl.w + 63) >> 6) << 6;
+    b.base = pl.boff * 64 - (long long)pl.y0 * b.pitch - pl.x0;
+    return b;
+}
+// set the bits of `len` >= 1 pixels of one row, starting at (px, py): one RED.OR per 64-bit word the run touches (one for
+// nearly every run: the runs of small triangles are a few pixels long)
+__device__ __forceinline__ void ehb_bits_set(const EhbBits& b, int px, int py, int len)
+{
+    const long long pos = b.base + (long long)(py * b.pitch + px);   // (py * pitch + px < 2^27)
+    unsigned long long* wp = b.w + (pos >> 6);
+    const int bo = (int)((unsigned)pos & 63u);
+    const int n0 = min(len, 64 - bo);
+    atomicOr(wp, (n0 == 64 ? ~0ull : ((1ull << n0) - 1ull)) << bo);
+    int rem = len - n0;
+    while (rem > 0) {                                                // (rare: the run crosses a word boundary)
+        wp++;
+        atomicOr(wp, rem >= 64 ? ~0ull : ((1ull << rem) - 1ull));
+        rem -= 64;
+    }
+}
 
 // Raise sticky status bits: in the pass's counters (read by ehb_ctx_status) and in host-visible memory (ehb_ctx_poll).
 __device__ __forceinline__ void ehb_raise(const EhbParams& p, unsigned bits)
@@ -367,7 +400,7 @@ __global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRo
             any = __any_sync(0xffffffffu, any);
             if (lane == 0) {
                 EhbPlane pl;
-                pl.x0 = pl.y0 = pl.w = pl.h = 0; pl.off = 0; pl.pad = 0;
+                pl.x0 = pl.y0 = pl.w = pl.h = 0; pl.off = 0; pl.boff = 0;
                 if (any) {
                     int x0 = 0, y0 = 0, x1 = p.W - 1, y1 = p.H - 1;
                     if (!bad) {   // pixel p is sampled at p + 0.5; two pixels of margin cover snapping and rounding
@@ -381,7 +414,7 @@ __global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRo
         }
         // the last table CTA to finish sees every bounding box: it allocates the planes of this pass
         __shared__ unsigned s_last;
-        __shared__ unsigned long long s_wsum[8], s_base;
+        __shared__ unsigned long long s_wsum[8], s_base, s_wsumb[8], s_baseb;
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) s_last = atomicAdd(&p.ctr->vertexDone, 1u) == (unsigned)tableBlocks - 1u;
@@ -390,7 +423,7 @@ __global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRo
         __threadfence();
         EHB_MARK(p, 5);
         if (threadIdx.x == 0) {
-            s_base = 0ull;
+            s_base = 0ull; s_baseb = 0ull;
             p.ctr->vertexDone = 0u;
             p.ctr->nTiles = 0u; p.ctr->nLight = 0u; p.ctr->nEmpty = 0u; p.ctr->workCursor = 0u; p.ctr->slabCursor = 0u;
         }
@@ -400,37 +433,39 @@ __global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRo
         }
         __syncthreads();
         const int warp = threadIdx.x >> 5;
-        for (int i0 = 0; i0 < p.items * p.Lp; i0 += blockDim.x) {      // block-wide exclusive prefix sum of the plane areas
+        for (int i0 = 0; i0 < p.items * p.Lp; i0 += blockDim.x) {      // block-wide exclusive prefix sums: plane areas, bit words
             const int i = i0 + threadIdx.x;
             EhbPlane pl;
-            pl.x0 = pl.y0 = pl.w = pl.h = 0; pl.off = 0; pl.pad = 0;
+            pl.x0 = pl.y0 = pl.w = pl.h = 0; pl.off = 0; pl.boff = 0;
             if (i < p.items * p.Lp) {
                 const int4 a = __ldcg(reinterpret_cast<const int4*>(&p.plane[i]));   // written by other CTAs of this launch: read at L2
                 pl.x0 = a.x; pl.y0 = a.y; pl.w = a.z; pl.h = a.w;
             }
             const unsigned long long area = (unsigned long long)pl.w * (unsigned long long)pl.h;
-            unsigned long long inc = area;
+            const unsigned long long words = p.bits ? (unsigned long long)((pl.w + 63) >> 6) * (unsigned long long)pl.h : 0ull;
+            unsigned long long inc = area, incb = words;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += v;
+                const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o), vb = __shfl_up_sync(0xffffffffu, incb, o);
+                if (lane >= o) { inc += v; incb += vb; }
             }
-            if (lane == 31) s_wsum[warp] = inc;
+            if (lane == 31) { s_wsum[warp] = inc; s_wsumb[warp] = incb; }
             __syncthreads();
-            unsigned long long before = s_base;
-            for (int w = 0; w < warp; w++) before += s_wsum[w];
-            const unsigned long long off = before + inc - area;
+            unsigned long long before = s_base, beforeb = s_baseb;
+            for (int w = 0; w < warp; w++) { before += s_wsum[w]; beforeb += s_wsumb[w]; }
+            const unsigned long long off = before + inc - area, offb = beforeb + incb - words;
             if (pl.w > 0) {
-                if (off + area <= p.poolCap) pl.off = (long long)off;
+                if (off + area <= p.poolCap && offb + words <= p.bitCap) { pl.off = (long long)off; pl.boff = (long long)offb; }
                 else { pl.w = pl.h = 0; ehb_raise(p, 1u); }
                 p.plane[i] = pl;
             }
             __syncthreads();
-            if (threadIdx.x == blockDim.x - 1) s_base = before + inc;
+            if (threadIdx.x == blockDim.x - 1) { s_base = before + inc; s_baseb = beforeb + incb; }
             __syncthreads();
         }
         if (threadIdx.x == 0) {
             p.ctr->planeCursor = min(s_base, p.poolCap);
+            p.ctr->bitCursor = min(s_baseb, p.bitCap);
             __threadfence();
             asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(&p.ctr->tableReady), "r"(1u) : "memory");
             EHB_MARK(p, 6);
@@ -535,6 +570,14 @@ __global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRo
              i += (unsigned long long)clearBlocks * blockDim.x)
             p2[i] = make_ulonglong2(EHB_EMPTY, EHB_EMPTY);
         if ((total & 1ull) && blk == 0 && threadIdx.x == 0) p.pool[total - 1] = EHB_EMPTY;
+        if (p.bits) {
+            const unsigned long long nb = min(*(volatile unsigned long long*)&p.ctr->bitCursor, p.bitCap), nb2 = nb >> 1;
+            ulonglong2* b2 = reinterpret_cast<ulonglong2*>(p.bits);
+            for (unsigned long long i = (unsigned long long)blk * blockDim.x + threadIdx.x; i < nb2;
+                 i += (unsigned long long)clearBlocks * blockDim.x)
+                b2[i] = make_ulonglong2(0ull, 0ull);
+            if ((nb & 1ull) && blk == 0 && threadIdx.x == 0) p.bits[nb - 1] = 0ull;
+        }
         if (p.touch)
             for (int i = blk * blockDim.x + threadIdx.x; i < p.items * p.ntiles; i += clearBlocks * blockDim.x) p.touch[i] = 0u;
         if (threadIdx.x == 0) EHB_TL_STOP(p, 1, blockIdx.x, tl0);
@@ -772,7 +815,7 @@ __device__ __noinline__ int ehb_clip_triangle(const float4 c0, const float4 c1, 
 }
 
 // One lane draws one record by testing every sample of its bbox: only when the deferred-work queues are full.
-__device__ __noinline__ void ehb_draw_serial(const EhbParams& p, const EhbRec& rc)
+__device__ __noinline__ void ehb_draw_serial(const EhbParams& p, const EhbRec& rc, const EhbBits bits)
 {
     const float p0[4] = {rc.clip[0], rc.clip[1], rc.clip[2], rc.clip[3]}, p1[4] = {rc.clip[4], rc.clip[5], rc.clip[6], rc.clip[7]},
                 p2[4] = {rc.clip[8], rc.clip[9], rc.clip[10], rc.clip[11]};
@@ -785,6 +828,7 @@ __device__ __noinline__ void ehb_draw_serial(const EhbParams& p, const EhbRec& r
             const int px = rc.x0 + dx, py = rc.y0 + dy;
             const float zw = ehb_shade_zw(p0, p1, p2, p.xs * (float)px + p.xo, p.ys * (float)py + p.yo);
             atomicMin(p.pool + (rc.base + (long long)py * rc.pw + px), ((unsigned long long)ehb_order_key(zw) << 32) | rc.id);
+            if (bits.w) ehb_bits_set(bits, px, py, 1);
         }
 }
 
@@ -798,6 +842,7 @@ __device__ __noinline__ void ehb_emit_clipped(const EhbRobot& rb, const EhbParam
     const EhbLink& lk = rb.link[l];
     const int4 id = __ldg(lk.faces + f);
     const EhbPlane pl = p.plane[(size_t)item * p.Lp + (p.Lp == 1 ? 0 : l)];
+    const EhbBits bits = ehb_bits_of(p.bits, pl);
     const size_t vb = (size_t)item * p.Vtot + rb.voff[l];
     const float4 c0 = p.vclip[vb + id.x], c1 = p.vclip[vb + id.y], c2 = p.vclip[vb + id.z];
     float poly[9][4];
@@ -828,13 +873,14 @@ __device__ __noinline__ void ehb_emit_clipped(const EhbRobot& rb, const EhbParam
         if (fits) {
             const unsigned k = (unsigned)qi * (unsigned)p.bigCap + kq;
             p.bigRec[k] = rc;
+            if (p.bigBits) p.bigBits[k] = EhbBitsRec{bits.base, bits.pitch, 0};
             for (int uy = 0; uy < nuy; uy++)
                 for (int ux = 0; ux < nux; ux++)
                     p.units[u0 + uy * nux + ux] = EhbUnit{k, (unsigned short)(ux * EHB_UNIT_W), (unsigned short)(uy * EHB_UNIT_H)};
         } else {
             ehb_raise(p, 4u);   // queues full: drawn here (slow but complete); its units are void
             for (int u = 0; u < nu && (int)(uq + u) < p.unitCap; u++) p.units[u0 + u] = EhbUnit{0xFFFFFFFFu, 0, 0};
-            ehb_draw_serial(p, rc);
+            ehb_draw_serial(p, rc, bits);
         }
     }
 }
@@ -856,7 +902,8 @@ __device__ __forceinline__ void ehb_shade_global(const RV rv, int t, int px, int
 // `t` = this lane's record index in recs (-1: no row), `dy` = its row inside that record's bbox.
 template <typename I, typename F, class RV>
 __device__ __forceinline__ void ehb_rows_group(const RV rv, int t, int dy, int lane, unsigned long long* pool,
-                                               float xs, float xo, float ys, float yo, int cx0 = 0, int cx1 = 1 << 20)
+                                               float xs, float xo, float ys, float yo, const EhbBits bits, int cx0 = 0,
+                                               int cx1 = 1 << 20)
 {
     int len = 0;
     uint32_t pos = 0;   // t << 26 | py << 13 | px of the first covered sample of this lane's row
@@ -868,6 +915,8 @@ __device__ __forceinline__ void ehb_rows_group(const RV rv, int t, int dy, int l
         a = max(a, cx0); b = min(b, cx1);   // window of a deferred triangle's unit
         len = max(0, b - a + 1);
         pos = ((uint32_t)t << 26) | ((uint32_t)(rv.i(t, 13) + dy) << 13) | (uint32_t)(rv.i(t, 12) + a);
+        // the covered run of this row -> the plane's coverage bits (one or two RED.OR); the depth samples follow below
+        if (bits.w && len > 0) ehb_bits_set(bits, rv.i(t, 12) + a, rv.i(t, 13) + dy, len);
     }
     int inc = len;
 #pragma unroll
@@ -961,6 +1010,8 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
     bool big = false, needClip = false;
     int4 tb = make_int4(0, 0, 0, 0);   // clipped bbox of this lane's triangle (x0, y0, w, h)
     const bool visible = true;
+    // the coverage bits of the batch's plane (one link of one item: the same for every lane)
+    const EhbBits bits = ehb_bits_of(p.bits, p.plane[(size_t)item * p.Lp + (p.Lp == 1 ? 0 : link)]);
     if (visible && f < rb.link[link].F) {
         EhbRec rc;
         rows = ehb_make_record(rb, p, item, link, f, rc, needClip);
@@ -1027,6 +1078,7 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
                 todo &= todo - 1;
                 const unsigned kt = __shfl_sync(0xffffffffu, k, t);
                 reinterpret_cast<uint32_t*>(p.bigRec + kt)[lane] = s_rec[warp][lane * 32 + t];
+                if (lane == 0 && p.bigBits) p.bigBits[kt] = EhbBitsRec{bits.base, bits.pitch, 0};
             }
         }
     }
@@ -1083,8 +1135,8 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
                 }
                 t = lo; dy = r - off[t];
             }
-            if (anyWide) ehb_rows_group<long long, double, EhbRecSoA>(recs, t, dy, lane, p.pool, xs, xo, ys, yo);
-            else ehb_rows_group<int, float, EhbRecSoA>(recs, t, dy, lane, p.pool, xs, xo, ys, yo);
+            if (anyWide) ehb_rows_group<long long, double, EhbRecSoA>(recs, t, dy, lane, p.pool, xs, xo, ys, yo, bits);
+            else ehb_rows_group<int, float, EhbRecSoA>(recs, t, dy, lane, p.pool, xs, xo, ys, yo, bits);
         }
     };
     draw_rows(0, nInline);
@@ -1098,7 +1150,11 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
 #pragma unroll 8
             for (int k = 0; k < 32; k++) blk[k * 32 + lane] = s_rec[warp][k * 32 + lane];
             blk[1024 + lane] = (uint32_t)off[lane];
-            if (lane == 0) { blk[1024 + 32] = (uint32_t)nRowsAll; blk[1024 + 33] = anyWide ? 1u : 0u; }
+            if (lane == 0) {
+                blk[1024 + 32] = (uint32_t)nRowsAll; blk[1024 + 33] = anyWide ? 1u : 0u;
+                blk[1024 + 34] = (uint32_t)(unsigned long long)bits.base; blk[1024 + 35] = (uint32_t)((unsigned long long)bits.base >> 32);
+                blk[1024 + 36] = (uint32_t)bits.pitch;
+            }
             for (int i = lane; i < nitems; i += 32)
                 p.units[uBase + i] = EhbUnit{0x80000000u | slot, (unsigned short)(EHB_RINLINE + i * EHB_RGROUPS), (unsigned short)EHB_RGROUPS};
         } else {   // no room: the units are void and the rest of the batch is drawn here
@@ -1177,6 +1233,12 @@ __global__ void __launch_bounds__(256, EHB_BMIN_BLOCKS) ehb_k_raster_big(const _
         const bool isVoid = cur.rec == 0xFFFFFFFFu, isBatch = !isVoid && (cur.rec & 0x80000000u);
         if (isBatch) fetch_issue(p.batchBlk + (size_t)(cur.rec & 0x7FFFFFFFu) * EHB_BLK_WORDS, EHB_BLK_WORDS * 4);
         else if (!isVoid) fetch_issue(p.bigRec + cur.rec, (uint32_t)sizeof(EhbRec));
+        EhbBits ubits;
+        ubits.w = nullptr; ubits.base = 0; ubits.pitch = 0;
+        if (!isVoid && !isBatch && p.bigBits) {
+            const EhbBitsRec br = p.bigBits[cur.rec];
+            ubits.w = p.bits; ubits.base = br.base; ubits.pitch = br.pitch;
+        }
         un = resolve(tk);
         tk = take();
         if (isVoid) continue;
@@ -1186,6 +1248,8 @@ __global__ void __launch_bounds__(256, EHB_BMIN_BLOCKS) ehb_k_raster_big(const _
             const int* off = reinterpret_cast<const int*>(sb + 1024);
             const int nRows = off[32];
             const bool anyWide = off[33] != 0;
+            EhbBits bits;
+            bits.w = p.bits; bits.base = (long long)(((unsigned long long)sb[1024 + 35] << 32) | sb[1024 + 34]); bits.pitch = off[36];
             const EhbRecSoA recs{sb};
             for (int gi = 0; gi < (int)cur.dy0; gi++) {
                 const int r0 = ((int)cur.dx0 + gi) * 32;
@@ -1201,8 +1265,8 @@ __global__ void __launch_bounds__(256, EHB_BMIN_BLOCKS) ehb_k_raster_big(const _
                     }
                     t = lo; dy = r - off[t];
                 }
-                if (anyWide) ehb_rows_group<long long, double, EhbRecSoA>(recs, t, dy, lane, p.pool, xs, xo, ys, yo);
-                else ehb_rows_group<int, float, EhbRecSoA>(recs, t, dy, lane, p.pool, xs, xo, ys, yo);
+                if (anyWide) ehb_rows_group<long long, double, EhbRecSoA>(recs, t, dy, lane, p.pool, xs, xo, ys, yo, bits);
+                else ehb_rows_group<int, float, EhbRecSoA>(recs, t, dy, lane, p.pool, xs, xo, ys, yo, bits);
             }
             continue;
         }
@@ -1212,8 +1276,8 @@ __global__ void __launch_bounds__(256, EHB_BMIN_BLOCKS) ehb_k_raster_big(const _
         const int dy = cur.dy0 + lane;
         const int t = dy < rc->h ? 0 : -1;
         const EhbRecAoS rv{reinterpret_cast<const uint32_t*>(rc)};
-        if (ext >= 32768) ehb_rows_group<long long, double, EhbRecAoS>(rv, t, dy, lane, p.pool, xs, xo, ys, yo, cur.dx0, cur.dx0 + EHB_UNIT_W - 1);
-        else ehb_rows_group<int, float, EhbRecAoS>(rv, t, dy, lane, p.pool, xs, xo, ys, yo, cur.dx0, cur.dx0 + EHB_UNIT_W - 1);
+        if (ext >= 32768) ehb_rows_group<long long, double, EhbRecAoS>(rv, t, dy, lane, p.pool, xs, xo, ys, yo, ubits, cur.dx0, cur.dx0 + EHB_UNIT_W - 1);
+        else ehb_rows_group<int, float, EhbRecAoS>(rv, t, dy, lane, p.pool, xs, xo, ys, yo, ubits, cur.dx0, cur.dx0 + EHB_UNIT_W - 1);
     }
     if (lane == 0) EHB_TL_STOP(p, 3, blockIdx.x * 8 + warp, tl0);
     EHB_MARK(p, 12);

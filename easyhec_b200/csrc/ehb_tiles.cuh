@@ -75,6 +75,9 @@ struct __align__(128) EhbTileSm {
     uint32_t rbits[EHB_MROWS][2];                // registered reference: bits of the out region's rows
     uint32_t bits, refCnt;
     int slab;                                    // index of the CTA's slab in the pair pool (-1: none yet)
+#ifdef EHB_STATS
+    long long stat[8];                           // this tile's cycles per phase (A B C D E F whole) and its pairs
+#endif
 };
 
 // the pair arrays of a round: shared memory, or a slab in global memory
@@ -87,7 +90,8 @@ struct EhbPairs {
 // [7] C weights, [8] D masks, [9] E compose, [10] F backward, [11] whole tile, [12] rounds in a global slab
 #ifdef EHB_STATS
 #define EHB_STAT_T(var) const long long var = clock64()
-#define EHB_STAT_ADD(i, v) do { if (threadIdx.x == 0) atomicAdd(&p.ctr->dbg[i], (unsigned long long)(v)); } while (0)
+#define EHB_STAT_ADD(i, v) do { if (threadIdx.x == 0) { atomicAdd(&p.ctr->dbg[i], (unsigned long long)(v)); \
+    if ((i) >= 5 && (i) <= 11) sm.stat[(i) - 5] += (long long)(v); if ((i) == 3) sm.stat[7] += (long long)(v); } } while (0)
 #else
 #define EHB_STAT_T(var)
 #define EHB_STAT_ADD(i, v)
@@ -137,9 +141,10 @@ __device__ __forceinline__ void ehb_tile_round(const EhbRobot& rb, const EhbPara
     EHB_STAT_T(tA);
     take = min(EHB_RL, c.nl - lNext);
     // ================================ A: coverage of the windows ================================
-    // Link by link: warp w loads the window rows w, w + 4, ... (nine of them) -- lane = column for columns 0..31, and the
-    // three extra columns of its rows with one more load (lane = 3 * row + column) -- all ten loads in flight at once; the
-    // coverage bits of a row come straight from the loaded values by ballot.
+    // The rasterizer kept one coverage bit per pixel of every plane (ehb_bits_set): a window row is 35 bits out of two
+    // 64-bit words.  A warp per link, lane = window row (rows 32..34 by the first three lanes): every load of the round is
+    // in flight at once, and a link costs 0.6 KB of L2 traffic instead of the 9.8 KB of its depth-plane window (with every
+    // tile of the pass starting together, those windows queued at L2 for 5,000 cycles per link).
     {
         uint32_t b = c.bits;
         for (int q = 0; q < lNext; q++) b &= b - 1;
@@ -147,32 +152,26 @@ __device__ __forceinline__ void ehb_tile_round(const EhbRobot& rb, const EhbPara
             const int l = __ffs(b) - 1;
             b &= b - 1;
             if (tid == 0) { sm.slot[s].link = l; sm.slot[s].nPairs = 0; sm.slot[s].pairBase = 0; }
+            if ((s & (EHB_TWARPS - 1)) != warp) continue;
             const EhbPlane& pl = sm.planes[l];
-            const int cx = c.rx0 - pl.x0 + lane;
-            const int cyb = c.ry0 - pl.y0 + warp;
-            constexpr int NR = (EHB_RS + EHB_TWARPS - 1) / EHB_TWARPS;   // rows per warp (9)
-            unsigned long long v[NR], vx = EHB_EMPTY;
+            const int bw = (pl.w + 63) >> 6;
+            const int bx0 = c.rx0 - pl.x0;                    // plane column of window column 0 (may be negative)
+            const int s0 = max(bx0, 0), wi = s0 >> 6, bo = s0 & 63;
 #pragma unroll
-            for (int j = 0; j < NR; j++) {
-                const int r = warp + j * EHB_TWARPS, cy = cyb + j * EHB_TWARPS;
-                v[j] = EHB_EMPTY;
-                if (r < EHB_RS && (unsigned)cy < (unsigned)pl.h && (unsigned)cx < (unsigned)pl.w)
-                    v[j] = p.pool[pl.off + (long long)cy * pl.w + cx];
+            for (int part = 0; part < 2; part++) {
+                const int r = part ? 32 + lane : lane;
+                if (r > EHB_RS) break;
+                unsigned long long v = 0ull;
+                const int by = c.ry0 + r - pl.y0;
+                if (r < EHB_RS && (unsigned)by < (unsigned)pl.h && wi < bw && bx0 < pl.w && bx0 > -EHB_RS) {
+                    const unsigned long long* row = p.bits + pl.boff + (long long)by * bw;
+                    const unsigned long long lo = __ldcg(row + wi), hi = (wi + 1 < bw && bo) ? __ldcg(row + wi + 1) : 0ull;
+                    v = bo ? ((lo >> bo) | (hi << (64 - bo))) : lo;
+                    if (bx0 < 0) v <<= -bx0;                  // window columns left of the plane are empty
+                    v &= (1ull << EHB_RS) - 1ull;
+                }
+                if (r <= EHB_RS) sm.cov[s][r] = v;            // (row 35 = 0: the pair search looks one row up)
             }
-            {
-                const int j = lane / 3, k = lane - 3 * j;            // extra columns 32..34 of this warp's row j
-                const int r = warp + j * EHB_TWARPS, cy = cyb + j * EHB_TWARPS, cxx = c.rx0 - pl.x0 + 32 + k;
-                if (j < NR && r < EHB_RS && (unsigned)cy < (unsigned)pl.h && (unsigned)cxx < (unsigned)pl.w)
-                    vx = p.pool[pl.off + (long long)cy * pl.w + cxx];
-            }
-            const unsigned bx = __ballot_sync(0xffffffffu, vx != EHB_EMPTY);
-#pragma unroll
-            for (int j = 0; j < NR; j++) {
-                const int r = warp + j * EHB_TWARPS;
-                const unsigned b0 = __ballot_sync(0xffffffffu, v[j] != EHB_EMPTY);
-                if (lane == 0 && r < EHB_RS) sm.cov[s][r] = (unsigned long long)b0 | ((unsigned long long)((bx >> (3 * j)) & 7u) << 32);
-            }
-            if (tid == 0) sm.cov[s][EHB_RS] = 0ull;
         }
     }
     __syncthreads();
@@ -448,6 +447,9 @@ __global__ void __launch_bounds__(EHB_TTHREADS, 7) ehb_k_tiles(const __grid_cons
 
     for (unsigned e = blockIdx.x; e < nEntries; e += gridDim.x) {
         EHB_STAT_T(tTile);
+#ifdef EHB_STATS
+        if (tid == 0) for (int k = 0; k < 8; k++) sm.stat[k] = 0;
+#endif
         const uint32_t wid = ehb_list_at(p, e, nHeavy);
         c.item = (int)(wid / (uint32_t)p.ntiles); c.tile = (int)(wid - (uint32_t)c.item * (uint32_t)p.ntiles);
         const int tyy = c.tile / p.ntx;
@@ -607,6 +609,12 @@ __global__ void __launch_bounds__(EHB_TTHREADS, 7) ehb_k_tiles(const __grid_cons
             }
         }
         EHB_STAT_ADD(11, clock64() - tTile);
+#ifdef EHB_STATS
+        if (tid == 0 && p.dbgbuf && e < 4096u) {
+            for (int k = 0; k < 7; k++) p.dbgbuf[(size_t)e * 8 + k] = (unsigned long long)sm.stat[k];
+            p.dbgbuf[(size_t)e * 8 + 7] = (unsigned long long)nl | ((unsigned long long)sm.stat[7] << 8);
+        }
+#endif
     }
     if (tid == 0 && storePending) ehb_bulk_wait_read();
     if (tid == 0) EHB_TL_STOP(p, 4, blockIdx.x, tl0);

@@ -23,6 +23,7 @@ mvp = torch.from_numpy(s["mvp"]).cuda()
 for _ in range(3):
     ctx.render_views_fused(ids, mvp, ref, H, W, backward=True)
 ctx.debug_counters(reset=True)
+ctx.debug_buffer(0)
 n = 10
 for _ in range(n):
     ctx.render_views_fused(ids, mvp, ref, H, W, backward=True)
@@ -32,3 +33,17 @@ names = ["tiles", "links", "tiles_nl0", "pairs", "multi_round", "A_windows", "B_
 t = max(c[0], 1)
 print({k: v / n for k, v in zip(names[:5], c[:5])})
 print({k: round(v / t) for k, v in zip(names[5:], c[5:12])}, "(cycles per tile, thread 0)")
+
+import numpy as np
+buf = np.array(ctx.debug_buffer(4096 * 8), dtype=np.uint64).reshape(4096, 8).astype(np.int64)
+ok = buf[:, 6] > 0
+rows = buf[ok]
+order = np.argsort(-rows[:, 6])
+print("slowest tiles of the last pass (cycles, thread 0): A B C D E F whole | links pairs")
+for r in rows[order[:12]]:
+    print("  %6d %6d %6d %6d %6d %6d %7d | %d %d" % (r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7] & 255, r[7] >> 8))
+nl = rows[:, 7] & 255
+for k in range(0, 8):
+    m = nl == k
+    if m.any():
+        print("  tiles with %d links: %4d, mean whole %.0f cycles, max %d" % (k, m.sum(), rows[m, 6].mean(), rows[m, 6].max()))

@@ -2,7 +2,7 @@
 of the five kernels on the global timer: per-kernel span, distribution of the entries' durations, how many SMs are
 still busy towards the end (the tail), gaps between the kernels.
    make -C easyhec_b200/csrc EXTRA=-DEHB_TIMELINE OUT=../libehb_tl.so
-   EHB_LIB=easyhec_b200/libehb_tl.so python tools/timeline.py [headline|inview] [items]"""
+   EHB_LIB=easyhec_b200/libehb_tl.so python tools/timeline.py [headline|inview] [items] [H W]"""
 import importlib.util
 import os
 import sys
@@ -18,6 +18,8 @@ from easyhec_b200._lib import Context  # noqa: E402
 
 wl = dict(b.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "headline"])
 items = int(sys.argv[2]) if len(sys.argv) > 2 else wl["B"]
+if len(sys.argv) > 4:
+    wl["H"], wl["W"] = int(sys.argv[3]), int(sys.argv[4])
 H, W = wl["H"], wl["W"]
 s = b.build_sets(wl, 0, 1)[0]
 ctx = Context("cuda:0")
