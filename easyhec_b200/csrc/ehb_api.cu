@@ -565,9 +565,22 @@ int ensure_scratch(Ctx* c, Scratch& sc, int items, int L, int Lp, int H, int W, 
     // pool can never overflow; beyond it the pool holds poolFactor screens per item and grows on the overflow flag.
     const double worst = (double)items * Lp * H * W;
     const double f = worst * 8.0 <= c->poolBudget ? (double)Lp : std::min(std::max(c->poolFactor, c->poolBudget / (8.0 * items * H * W)), (double)Lp);
+    // k_front clears only what the previous pass used: a new allocation starts clean (EMPTY is all ones) with zero extents
+    const unsigned long long* pool0 = sc.pool.p;
     if ((r = sc.pool.ensure((size_t)((double)items * H * W * f) + 1024, capturing))) return r;
+    if (sc.pool.p != pool0) {
+        CU(cudaMemset(sc.pool.p, 0xFF, sc.pool.n * sizeof(unsigned long long)));
+        CU(cudaMemset(&sc.ctr->prevCursor, 0, sizeof(unsigned long long)));
+        CU(cudaDeviceSynchronize());
+    }
     if (Lp == L) {   // coverage bits: a row of a plane is ceil(w / 64) <= w / 64 + 1 words
+        const unsigned long long* bits0 = sc.bitPool.p;
         if ((r = sc.bitPool.ensure(sc.pool.n / 64 + (size_t)items * Lp * H + 1024, capturing))) return r;
+        if (sc.bitPool.p != bits0) {
+            CU(cudaMemset(sc.bitPool.p, 0, sc.bitPool.n * sizeof(unsigned long long)));
+            CU(cudaMemset(&sc.ctr->prevBitCursor, 0, sizeof(unsigned long long)));
+            CU(cudaDeviceSynchronize());
+        }
         if ((r = sc.bigBits.ensure(sc.bigRec.n, capturing))) return r;
     }
     return EHB_OK;
@@ -629,9 +642,8 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
     // spare CTAs of the raster launch finish the tiles no link touches; with registered reference masks (or none) that is
     // only the zero fill of the masks -- nothing to do at all when no masks are wanted
     const bool legacyStream = mode == EHB_MODE_FUSED && (io.ref || io.ref_u8);
-    p.prezero = (!unionMode && mode != EHB_MODE_AA_BWD && !legacyStream && io.masks) ? 1 : 0;
-    const int streamBlocks = (unionMode || mode == EHB_MODE_AA_BWD || (!legacyStream && !io.masks)) ? 0
-                             : legacyStream ? c->nSM * tune_int("EHB_STREAM_MULT", 2) : c->nSM;
+    p.fillEmpty = (!unionMode && mode != EHB_MODE_AA_BWD && !legacyStream && io.masks) ? 1 : 0;
+    const int streamBlocks = legacyStream ? c->nSM * tune_int("EHB_STREAM_MULT", 2) : 0;
     const long long rasterBlocks = ((long long)chunks * items + EHB_RWARPS - 1) / EHB_RWARPS;
     if (ev) cudaEventRecord(ev[0], st);
     if (ev) cudaEventRecord(ev[1], st);

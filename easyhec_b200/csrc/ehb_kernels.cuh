@@ -54,7 +54,8 @@ struct __align__(128) EhbCounters {
     unsigned int nBatchHeavy; // visible 32-triangle batches with a large screen footprint: listed from the front of batchList ...
     unsigned int nBatchLight; // ... the other visible ones from the back (k_front writes, k_raster reads, k_raster_big resets)
     unsigned long long bitCursor;   // words of the bit pool in use
-    unsigned int pad0[18];
+    unsigned long long prevCursor, prevBitCursor;   // what the previous pass on this scratch used: the part k_front clears
+    unsigned int pad0[14];
     // line 1: set by the last table CTA of k_front when the planes of the pass are allocated and the list counters are
     // reset; the CTAs of the same launch that need the planes wait for it (k_raster resets it)
     unsigned int tableReady;
@@ -84,7 +85,7 @@ struct EhbParams {
     // top of the image get their own, shorter box that starts at image row 0
     CUtensorMap tmMask, tmMaskTop;
     int useTma;
-    int prezero;             // the raster launch's spare CTAs zero the whole mask tensor: tiles without coverage need no store
+    int fillEmpty;           // k_tiles zero-fills the tiles no link touches (no reference to read there)
     int H, W, ntx, nty, ntiles;
     int items, L, Lp, Ftot, Vtot;   // Lp = planes per item: L (per-link visibility) or 1 (packed robot)
     int hlo, hhi;
@@ -330,11 +331,11 @@ __device__ __forceinline__ void ehb_stream_empty_tile(const EhbParams& p, int it
 //   (B) batches   frustum test of every 32-triangle batch's object-space AABB (8 corners, one per lane): the batches that
 //                 survive are listed -- large screen footprints from the front, the rest from the back -- so that k_raster
 //                 runs only warps that have something to draw, the long ones first
-//   (C) clear     planes := EMPTY (allocated part only), link bitmaps := 0          } wait for tableReady (the table CTAs
-//   (L) tiles     one lane per tile: tiles that some link's bbox touches -> tile     }  have the lowest block indices: they
-//                 list (several links first), the others -> empty-tile list         }  are resident before any waiter)
-// V and B do not depend on the table and sit between T and the waiters: by the time C and L are dispatched the table is
-// usually ready.  (As two launches -- table, then the rest -- the pass paid one more launch gap and the table's 4 us with
+//   (C) clear     what the previous pass used of the plane and bit pools := EMPTY / 0, link bitmaps := 0
+//   (L) tiles     one lane per tile: tiles that some link's bbox touches -> tile list (several links first), the others ->
+//                 empty-tile list.  These CTAs wait for tableReady (the table CTAs have the lowest block indices: they are
+//                 resident before any waiter).
+// Only L depends on the table; V, B and C run beside it.  (As two launches -- table, then the rest -- the pass paid one more launch gap and the table's 4 us with
 // 9 CTAs on the chip.)
 __device__ __forceinline__ void ehb_wait_table(const EhbParams& p)
 {
@@ -561,22 +562,22 @@ __global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRo
     }
     blk -= batchBlocks;
     // ---------------------------------------------------------------- (C) clear
+    // What the PREVIOUS pass on this scratch dirtied: planes [0, prevCursor) := EMPTY, bits [0, prevBitCursor) := 0 (k_raster
+    // notes a pass's extents; beyond them the pools are still clean, a new allocation is cleared by the host).  Nothing here
+    // depends on this pass's table, so the clear runs beside it.
     if (blk < clearBlocks) {
-        ehb_wait_table(p);
-        const unsigned long long total = min(*(volatile unsigned long long*)&p.ctr->planeCursor, p.poolCap);
-        const unsigned long long n2 = total >> 1;
+        const unsigned long long total = min(p.ctr->prevCursor, p.poolCap);
+        const unsigned long long n2 = (total + 1ull) >> 1;
         ulonglong2* p2 = reinterpret_cast<ulonglong2*>(p.pool);
         for (unsigned long long i = (unsigned long long)blk * blockDim.x + threadIdx.x; i < n2;
              i += (unsigned long long)clearBlocks * blockDim.x)
             p2[i] = make_ulonglong2(EHB_EMPTY, EHB_EMPTY);
-        if ((total & 1ull) && blk == 0 && threadIdx.x == 0) p.pool[total - 1] = EHB_EMPTY;
         if (p.bits) {
-            const unsigned long long nb = min(*(volatile unsigned long long*)&p.ctr->bitCursor, p.bitCap), nb2 = nb >> 1;
+            const unsigned long long nb2 = (min(p.ctr->prevBitCursor, p.bitCap) + 1ull) >> 1;
             ulonglong2* b2 = reinterpret_cast<ulonglong2*>(p.bits);
             for (unsigned long long i = (unsigned long long)blk * blockDim.x + threadIdx.x; i < nb2;
                  i += (unsigned long long)clearBlocks * blockDim.x)
                 b2[i] = make_ulonglong2(0ull, 0ull);
-            if ((nb & 1ull) && blk == 0 && threadIdx.x == 0) p.bits[nb - 1] = 0ull;
         }
         if (p.touch)
             for (int i = blk * blockDim.x + threadIdx.x; i < p.items * p.ntiles; i += clearBlocks * blockDim.x) p.touch[i] = 0u;
@@ -957,27 +958,6 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
         // spare CTAs of this launch finish the tiles no link touches: pure HBM streaming that overlaps the
         // instruction-bound rasterization instead of sitting in front of it
         const int n = (int)p.ctr->nEmpty;
-        if (p.prezero) {
-            // No reference to read (registered reference masks: the loss of the untouched tiles is part of refTotal): the
-            // whole mask tensor := 0 with coalesced 16-B streaming stores, a few microseconds at HBM write bandwidth while
-            // the rasterizer's warps wait for their loads; the image-space stage overwrites the listed tiles afterwards.
-            // (Measured alternative: one bulk tensor store (UTMASTG) of a zero tile per untouched tile costs 0.2 us per
-            // tile and SM -- 18 - 33 us for the 7,800 tiles of ten views.)
-            float* m = p.masks;
-            const size_t nAll = (size_t)p.items * p.H * p.W;
-            const size_t head = min(nAll, (size_t)((16u - (unsigned)((uintptr_t)m & 15u)) & 15u) >> 2);
-            const size_t n4 = (nAll - head) >> 2;
-            float4* m4 = reinterpret_cast<float4*>(m + head);
-            const size_t nthr = (size_t)streamBlocks * blockDim.x;
-            for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += nthr) __stcs(m4 + i, make_float4(0.f, 0.f, 0.f, 0.f));
-            if (blockIdx.x == 0 && threadIdx.x < 8) {
-                if (threadIdx.x < head) m[threadIdx.x] = 0.f;
-                const size_t t = head + 4 * n4 + (threadIdx.x - 4);
-                if (threadIdx.x >= 4 && t < nAll) m[t] = 0.f;
-            }
-            if (lane == 0) EHB_TL_STOP(p, 5, blockIdx.x * EHB_RWARPS + warp, tl0);
-            return;
-        }
         for (int i = blockIdx.x * EHB_RWARPS + warp; i < n; i += streamBlocks * EHB_RWARPS) {
             const int wid = (int)p.emptyList[i];
             const int item = wid / p.ntiles, tile = wid - item * p.ntiles;
@@ -988,7 +968,11 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
     // One warp per listed batch (32 consecutive faces of one link of one item): k_front listed the batches that survive the
     // frustum test of their AABB, the ones with a large screen footprint first.  The grid covers every batch of the pass;
     // the warps beyond the list leave at once.
-    if (blockIdx.x == (unsigned)streamBlocks && threadIdx.x == 0) p.ctr->tableReady = 0u;   // k_front is complete: re-arm its flag
+    if (blockIdx.x == (unsigned)streamBlocks && threadIdx.x == 0) {
+        p.ctr->tableReady = 0u;                          // k_front is complete: re-arm its flag,
+        p.ctr->prevCursor = p.ctr->planeCursor;          // note what this pass dirties (the next k_front clears it)
+        if (p.bits) p.ctr->prevBitCursor = p.ctr->bitCursor;
+    }
     EHB_MARK(p, 8);
     const int total = chunks * p.items;   // chunks = 32-triangle batches per item
     const unsigned e = (unsigned)(((int)blockIdx.x - streamBlocks) * EHB_RWARPS + warp);

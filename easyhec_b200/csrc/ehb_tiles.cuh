@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(EHB_TTHREADS, 7) ehb_k_tiles(const __grid_cons
         EHB_STAT_ADD(0, 1); EHB_STAT_ADD(1, nl); EHB_STAT_ADD(2, nl == 0);
         // ---- a listed tile that no triangle reaches: a zero tile (registered reference: its loss is part of refTotal) ------
         if (nl == 0 && (REFKIND == 0 || REFKIND == 3)) {
-            if (NEEDAA && p.masks && !p.prezero) {
+            if (NEEDAA && p.masks) {
                 if (tma) {
                     for (int i = tid; i < EHB_T * EHB_T / 4; i += EHB_TTHREADS) reinterpret_cast<float4*>(stage)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     ehb_fence_proxy_async();
@@ -617,6 +617,20 @@ __global__ void __launch_bounds__(EHB_TTHREADS, 7) ehb_k_tiles(const __grid_cons
 #endif
     }
     if (tid == 0 && storePending) ehb_bulk_wait_read();
+    // The tiles no link touches (registered reference masks: their loss is part of refTotal, nothing is read): mask := 0, a
+    // warp per tile with 16-B streaming stores, by every CTA of this launch once its own tiles are done -- the CTAs beyond
+    // the tile list start with it.  31 MB of HBM writes for ten views that overlap the latency-bound tile work.  (Measured
+    // alternatives: a bulk tensor store (UTMASTG) of a zero tile per untouched tile costs 0.2 us per tile and SM, 18 - 33 us
+    // per pass; as spare CTAs of the raster launch the fill held a quarter of its CTA slots for 6 - 10 us; as CTAs of
+    // k_front it was the longest part of that launch, 13 us.)
+    if (NEEDAA && p.fillEmpty) {
+        const int nEmpty = (int)p.ctr->nEmpty;
+        for (int i = (int)blockIdx.x * EHB_TWARPS + warp; i < nEmpty; i += (int)gridDim.x * EHB_TWARPS) {
+            const int wid = (int)p.emptyList[i];
+            const int it = wid / p.ntiles, tile = wid - it * p.ntiles;
+            ehb_stream_empty_tile(p, it, tile % p.ntx, tile / p.ntx, lane);
+        }
+    }
     if (tid == 0) EHB_TL_STOP(p, 4, blockIdx.x, tl0);
 }
 
