@@ -41,6 +41,7 @@ _PROTOS = {
     "ehb_ctx_grow_scratch": (C.c_int, [C.c_void_p]),
     "ehb_ctx_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "ehb_ctx_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "ehb_ctx_kernel_times_peek": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "ehb_ctx_debug_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]),
     "ehb_ctx_debug_buffer": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]),
     "ehb_ctx_debug_marks": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint)]),
@@ -281,12 +282,13 @@ class Context:
     def profile(self, enable: bool):
         _check(lib().ehb_ctx_profile(self._h, int(bool(enable))))
 
-    def kernel_times(self):
-        """-> ({table, front (vertex | clear | classify), raster (+raster_big, + empty-tile stream), tiles: summed ms}, passes); synchronises."""
+    def kernel_times(self, peek=False):
+        """-> ({front (table | vertices | batch lists | clear | tile lists), raster (+ raster_big), tiles: summed ms}, passes);
+        synchronises.  peek=True keeps the recorded passes (passes captured in a CUDA graph: read after every replay)."""
         ms = (C.c_double * 4)()
         n = C.c_longlong()
-        _check(lib().ehb_ctx_kernel_times(self._h, ms, C.byref(n)))
-        return dict(zip(("table", "front", "raster", "tiles"), list(ms))), n.value
+        _check((lib().ehb_ctx_kernel_times_peek if peek else lib().ehb_ctx_kernel_times)(self._h, ms, C.byref(n)))
+        return {"front": ms[0] + ms[1], "raster": ms[2], "tiles": ms[3]}, n.value
 
     def debug_counters(self, reset=True):
         out = (C.c_ulonglong * 16)()

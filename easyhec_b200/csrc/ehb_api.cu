@@ -628,9 +628,13 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
     p.dbgbuf = c->dbgbuf;
     p.hostFlags = c->hostFlagsDev;
 
+    // Stage timing (ehb_ctx_profile): CUDA events around the stages on the launching stream.  Under stream capture they
+    // become event-record nodes of the graph (cudaEventRecordExternal), so that a replayed pass is timed with the graph's
+    // launch gaps instead of the eager launch overhead of four kernels and five event records.
     cudaEvent_t* ev = nullptr;
-    if (c->profiling && !capturing) {
+    if (c->profiling) {
         if (c->evUsed + 5 > c->evPool.size()) {
+            if (capturing) return fail(EHB_E_CAPACITY, "event pool exhausted during stream capture");
             const size_t old = c->evPool.size();
             c->evPool.resize(old + 5 * 256);
             for (size_t i = old; i < c->evPool.size(); i++) CU(cudaEventCreate(&c->evPool[i]));
@@ -638,6 +642,11 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
         ev = &c->evPool[c->evUsed];
         c->evUsed += 5;
     }
+    auto mark = [&](int i) {
+        if (!ev) return;
+        if (capturing) cudaEventRecordWithFlags(ev[i], st, cudaEventRecordExternal);
+        else cudaEventRecord(ev[i], st);
+    };
     const int chunks = std::max(1, rb.boff[L]);   // 32-triangle batches per item (a batch never straddles two links)
     // spare CTAs of the raster launch finish the tiles no link touches; with registered reference masks (or none) that is
     // only the zero fill of the masks -- nothing to do at all when no masks are wanted
@@ -645,8 +654,7 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
     p.fillEmpty = (!unionMode && mode != EHB_MODE_AA_BWD && !legacyStream && io.masks) ? 1 : 0;
     const int streamBlocks = legacyStream ? c->nSM * tune_int("EHB_STREAM_MULT", 2) : 0;
     const long long rasterBlocks = ((long long)chunks * items + EHB_RWARPS - 1) / EHB_RWARPS;
-    if (ev) cudaEventRecord(ev[0], st);
-    if (ev) cudaEventRecord(ev[1], st);
+    mark(0); mark(1);
     const int tableBlocks = (items * p.Lp + 7) / 8;
     const int vchunks = std::max(1, (p.Vtot + 255) / 256);
     const int batchBlocks = (int)(((long long)chunks * items + 31) / 32);
@@ -660,10 +668,10 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
         CU(launch(ehb_k_front, dim3((unsigned)tableBlocks + restBlocks), dim3(256), 0, st, false, rb, p, tableBlocks, vchunks, batchBlocks,
                   clearBlocks, chunks, 0));
     }
-    if (ev) cudaEventRecord(ev[2], st);
+    mark(2);
     CU(launch(ehb_k_raster, dim3((unsigned)(streamBlocks + rasterBlocks)), dim3(EHB_RWARPS * 32), 0, st, true, rb, p, streamBlocks, chunks));
     CU(launch(ehb_k_raster_big, dim3(c->nSM * EHB_BMIN_BLOCKS), dim3(256), 0, st, true, p));
-    if (ev) cudaEventRecord(ev[3], st);
+    mark(3);
     if (unionMode && !io.out_u8) {
         // planes only (space exploration scores them directly)
     } else if (unionMode) {
@@ -675,7 +683,7 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
         const int refKind = mode != EHB_MODE_FUSED ? 0 : (io.refBits ? 3 : (io.ref ? 1 : (io.ref_u8 ? 2 : 0)));
         CU(launch(ehb_tiles_kernel(mode, refKind, io.do_bwd != 0), dim3(grid), dim3(EHB_TTHREADS), 0, st, true, rb, p));
     }
-    if (ev) cudaEventRecord(ev[4], st);
+    mark(4);
     c->launches += 4;   // front, raster, raster_big, tiles | union_out
     CU(cudaGetLastError());
     return EHB_OK;
@@ -742,6 +750,7 @@ int ehb_ctx_create(int device, ehb_ctx_t* out)
     Ctx* c = new Ctx();
     c->device = device;
     c->nSM = prop.multiProcessorCount;
+    c->nPipes = std::max(1, std::min(MAX_PIPES, tune_int("EHB_PIPES", c->nPipes)));   // (developer switch; ehb_ctx_set_pipelines)
     CU(cudaMalloc((void**)&c->ctr, N_SCRATCH * sizeof(EhbCounters)));
     CU(cudaMemset(c->ctr, 0, N_SCRATCH * sizeof(EhbCounters)));
     CU(cudaMallocHost((void**)&c->ctrHost, N_SCRATCH * sizeof(EhbCounters)));
@@ -871,12 +880,22 @@ int ehb_ctx_profile(ehb_ctx_t h, int enable)
     Ctx* c = (Ctx*)h;
     if (!c) return fail(EHB_E_ARG, "null context");
     c->profiling = enable != 0;
+    if (c->profiling && c->evPool.empty()) {   // (created here: a captured pass cannot create them)
+        DeviceGuard guard(c->device);
+        c->evPool.resize(5 * 256);
+        for (size_t i = 0; i < c->evPool.size(); i++) CU(cudaEventCreate(&c->evPool[i]));
+    }
     return EHB_OK;
 }
 
-int ehb_ctx_kernel_times(ehb_ctx_t h, double* ms4, long long* n_passes)
+static int kernel_times(Ctx* c, double* ms4, long long* n_passes, bool reset);
+
+int ehb_ctx_kernel_times(ehb_ctx_t h, double* ms4, long long* n_passes) { return kernel_times((Ctx*)h, ms4, n_passes, true); }
+/* the same without forgetting the recorded passes: for passes captured in a CUDA graph, whose events every replay records again */
+int ehb_ctx_kernel_times_peek(ehb_ctx_t h, double* ms4, long long* n_passes) { return kernel_times((Ctx*)h, ms4, n_passes, false); }
+
+static int kernel_times(Ctx* c, double* ms4, long long* n_passes, bool reset)
 {
-    Ctx* c = (Ctx*)h;
     if (!c || !ms4 || !n_passes) return fail(EHB_E_ARG, "null pointer argument");
     DeviceGuard guard(c->device);
     CU(cudaDeviceSynchronize());
@@ -888,7 +907,7 @@ int ehb_ctx_kernel_times(ehb_ctx_t h, double* ms4, long long* n_passes)
             ms4[k] += ms;
         }
     *n_passes = (long long)(c->evUsed / 5);
-    c->evUsed = 0;
+    if (reset) c->evUsed = 0;
     return EHB_OK;
 }
 

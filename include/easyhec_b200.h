@@ -82,6 +82,9 @@ EHB_API int ehb_ctx_grow_scratch(ehb_ctx_t ctx);
  * the last query, and their number. */
 EHB_API int ehb_ctx_profile(ehb_ctx_t ctx, int enable);
 EHB_API int ehb_ctx_kernel_times(ehb_ctx_t ctx, double* ms4, long long* n_passes);
+/* the same without forgetting the recorded passes (for passes captured in a CUDA graph: every replay records their events
+ * again, so the times of the last replay can be read after each one) */
+EHB_API int ehb_ctx_kernel_times_peek(ehb_ctx_t ctx, double* ms4, long long* n_passes);
 /* Per-kernel timing covers the stages {table, front, raster (+ raster_big), tiles (= windows + compose + pairgrad)}. */
 /* Developer aid: 16 raw 64-bit scratch counters of the first pipeline (zero unless a debug build fills them). */
 EHB_API int ehb_ctx_debug_counters(ehb_ctx_t ctx, unsigned long long* out16, int reset);
