@@ -439,9 +439,9 @@ def run_b200(args):
     # own scratch -- independent batches (the views of different solves, exploration rounds, the ring slots here) overlap
     # one step's latency-bound kernels and tails with the others' work.  Step k runs on slot k % S on every rank, so the
     # exchanges of a slot (its own mailbox channel) pair up across the ranks.
-    S = max(1, min(4, int(os.environ.get("EHB_VALUE_SLOTS", "4"))))
+    S = max(1, min(8, int(os.environ.get("EHB_VALUE_SLOTS", "4"))))
     inflight = S > 1 and (world == 1 or use_peer)
-    G = 32                                     # steps per captured graph (the slots drain at a graph's end)
+    G = int(os.environ.get("EHB_VALUE_GRAPH", "64"))   # steps per captured graph (the slots drain at a graph's end)
     g7s = [torch.zeros(7, dtype=torch.float32, device=dev) for _ in range(S)]
     dof_scr = [dof_dev[0].clone() for _ in range(S)]
     adam_st = [torch.zeros(13, dtype=torch.float32, device=dev) for _ in range(S)]
@@ -615,7 +615,7 @@ def run_b200(args):
     # four steps in flight so that one step's copies overlap the others' kernels.  Each step's result is complete on the
     # host when its _end returns.
     mvp_host = [torch.from_numpy(s["mvp"]).pin_memory() for s in sets]
-    Se = max(2, min(4, int(os.environ.get("EHB_E2E_SLOTS", "4"))))   # steps in flight
+    Se = max(2, min(8, int(os.environ.get("EHB_E2E_SLOTS", "4"))))   # steps in flight
     loss_host = [torch.empty((B,), dtype=torch.float64).pin_memory() for _ in range(Se)]
     gmvp_host = [torch.empty((B, L, 4, 4), dtype=torch.float64).pin_memory() for _ in range(Se)]
 

@@ -77,7 +77,10 @@ struct DevBuf {
 
 constexpr double POOL_BUDGET = 8e9;  // bytes of plane pool per pipeline reserved without asking
 constexpr int MAX_PIPES = 4;
-constexpr int N_SLOTS = 4;      // in-flight host-buffer steps (ehb_solver_step_begin_u8 / _end)
+#ifndef EHB_NSLOTS
+#define EHB_NSLOTS 4
+#endif
+constexpr int N_SLOTS = EHB_NSLOTS;   // steps in flight (ehb_step_begin / ehb_solver_step_begin_* / _end)
 constexpr int N_SCRATCH = MAX_PIPES + N_SLOTS;
 constexpr size_t COMM_CH_WORDS = 2 * EHB_COMM_MAX * 8 + 8;   // one channel of a peer mailbox: [2 parities][ranks][8 words] + step counter
 
