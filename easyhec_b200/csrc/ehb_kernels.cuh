@@ -901,11 +901,16 @@ __device__ __forceinline__ void ehb_shade_global(const RV rv, int t, int px, int
 }
 
 // One group of up to 32 rows (one per lane): spans, then the warp shades the covered samples 32 at a time.
-// `t` = this lane's record index in recs (-1: no row), `dy` = its row inside that record's bbox.
-template <typename I, typename F, class RV>
+// `t` = this lane's record index in recs (-1: no row), `dy` = its row inside that record's bbox.  `cmp` = 32 words-pairs of
+// the warp's shared memory.  The covered runs of the rows form one flat list of samples; sample j belongs to the last
+// non-empty row that starts at or before j.  The non-empty rows are compacted into `cmp` (first sample, start offset) once
+// per group; per 32 samples ONE warp-wide OR (REDUX) of "my row starts at sample s of this chunk" bits and a popcount give
+// every lane its row -- instead of a five-step binary search over the row prefix by shuffles (a third of the loop's
+// instructions).  SINGLE: every row belongs to record 0 (a deferred triangle's window): its fields stay in registers.
+template <typename I, typename F, class RV, bool SINGLE>
 __device__ __forceinline__ void ehb_rows_group(const RV rv, int t, int dy, int lane, unsigned long long* pool,
-                                               float xs, float xo, float ys, float yo, const EhbBits bits, int cx0 = 0,
-                                               int cx1 = 1 << 20)
+                                               float xs, float xo, float ys, float yo, const EhbBits bits, uint2* cmp,
+                                               int cx0 = 0, int cx1 = 1 << 20)
 {
     int len = 0;
     uint32_t pos = 0;   // t << 26 | py << 13 | px of the first covered sample of this lane's row
@@ -920,6 +925,8 @@ __device__ __forceinline__ void ehb_rows_group(const RV rv, int t, int dy, int l
         // the covered run of this row -> the plane's coverage bits (one or two RED.OR); the depth samples follow below
         if (bits.w && len > 0) ehb_bits_set(bits, rv.i(t, 12) + a, rv.i(t, 13) + dy, len);
     }
+    const unsigned ne = __ballot_sync(0xffffffffu, len > 0);
+    if (ne == 0u) return;                                  // nothing covered in these rows
     int inc = len;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -928,20 +935,35 @@ __device__ __forceinline__ void ehb_rows_group(const RV rv, int t, int dy, int l
     }
     const int total = __shfl_sync(0xffffffffu, inc, 31);
     const int exc = inc - len;
-    for (int j0 = 0; j0 < total; j0 += 32) {
-        const int j = j0 + lane;
-        int o = 0;   // owner lane = number of lanes whose inclusive prefix is <= j
+    __syncwarp();                                          // (the previous group's readers are done with cmp)
+    if (len > 0) cmp[__popc(ne & ((1u << lane) - 1u))] = make_uint2(pos, (uint32_t)exc);
+    __syncwarp();
+    // SINGLE: the one record's fields, loaded once
+    float s0[4], s1[4], s2[4];
+    long long sbase = 0; int spw = 0; uint32_t sid = 0;
+    if (SINGLE) {
 #pragma unroll
-        for (int st = 16; st >= 1; st >>= 1) {
-            const int v = __shfl_sync(0xffffffffu, inc, o + st - 1);
-            if (v <= j) o += st;
-        }
-        o = min(o, 31);
-        const uint32_t opos = __shfl_sync(0xffffffffu, pos, o);
-        const int oexc = __shfl_sync(0xffffffffu, exc, o);
+        for (int k = 0; k < 4; k++) { s0[k] = rv.f(0, 20 + k); s1[k] = rv.f(0, 24 + k); s2[k] = rv.f(0, 28 + k); }
+        sbase = rv.ll(0, 16); spw = rv.i(0, 18); sid = rv.u(0, 19);
+    }
+    int kbase = 0;                                         // non-empty rows that start before the chunk
+    const unsigned upto = 0xFFFFFFFFu >> (31 - lane);      // bits 0 .. lane
+    for (int j0 = 0; j0 < total; j0 += 32) {
+        const unsigned rel = (unsigned)(exc - j0);
+        const unsigned heads = __reduce_or_sync(0xffffffffu, (len > 0 && rel < 32u) ? (1u << rel) : 0u);
+        const int k = kbase + __popc(heads & upto) - 1;
+        kbase += __popc(heads);
+        const int j = j0 + lane;
         if (j < total) {
-            const uint32_t q = opos + (uint32_t)(j - oexc);
-            ehb_shade_global(rv, (int)(q >> 26), (int)(q & 8191u), (int)((q >> 13) & 8191u), pool, xs, xo, ys, yo);
+            const uint2 c = cmp[k];
+            const uint32_t q = c.x + (uint32_t)(j - (int)c.y);
+            const int px = (int)(q & 8191u), py = (int)((q >> 13) & 8191u);
+            if (SINGLE) {
+                const float zw = ehb_shade_zw(s0, s1, s2, xs * (float)px + xo, ys * (float)py + yo);
+                atomicMin(pool + (sbase + (long long)py * spw + px), ((unsigned long long)ehb_order_key(zw) << 32) | sid);
+            } else {
+                ehb_shade_global(rv, (int)(q >> 26), px, py, pool, xs, xo, ys, yo);
+            }
         }
     }
 }
@@ -954,6 +976,7 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
     EHB_TL_START(tl0);
     __shared__ __align__(128) uint32_t s_rec[EHB_RWARPS][32 * 32];   // 32 records per warp, transposed
     __shared__ int s_off[EHB_RWARPS][33];
+    __shared__ uint2 s_cmp[EHB_RWARPS][32];                           // compacted non-empty rows of a group (ehb_rows_group)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if ((int)blockIdx.x < streamBlocks) {
         // spare CTAs of this launch finish the tiles no link touches: pure HBM streaming that overlaps the
@@ -984,6 +1007,7 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
     const float xs = p.xs, xo = p.xo, ys = p.ys, yo = p.yo;
     const EhbRecSoA recs{s_rec[warp]};
     int* off = s_off[warp];
+    uint2* cmp = s_cmp[warp];
     {
     const int qi = (int)(bcur & (EHB_NQ - 1));            // this batch's sub-queue
     EhbCounters::Q& myq = p.ctr->q[qi];
@@ -1120,8 +1144,8 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
                 }
                 t = lo; dy = r - off[t];
             }
-            if (anyWide) ehb_rows_group<long long, double, EhbRecSoA>(recs, t, dy, lane, p.pool, xs, xo, ys, yo, bits);
-            else ehb_rows_group<int, float, EhbRecSoA>(recs, t, dy, lane, p.pool, xs, xo, ys, yo, bits);
+            if (anyWide) ehb_rows_group<long long, double, EhbRecSoA, false>(recs, t, dy, lane, p.pool, xs, xo, ys, yo, bits, cmp);
+            else ehb_rows_group<int, float, EhbRecSoA, false>(recs, t, dy, lane, p.pool, xs, xo, ys, yo, bits, cmp);
         }
     };
     draw_rows(0, nInline);
@@ -1169,6 +1193,7 @@ __global__ void __launch_bounds__(256, EHB_BMIN_BLOCKS) ehb_k_raster_big(const _
     EHB_TL_START(tl0);
     __shared__ __align__(128) uint32_t s_blk[8][EHB_BLK_WORDS];
     __shared__ __align__(8) uint64_t s_bar[8];           // one mbarrier per warp: completion of its bulk copies
+    __shared__ uint2 s_cmp[8][32];                       // compacted non-empty rows of a group (ehb_rows_group)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (blockIdx.x == 0 && threadIdx.x == 0) { p.ctr->nBatchHeavy = 0u; p.ctr->nBatchLight = 0u; }   // k_raster is complete
     EHB_MARK(p, 9);
@@ -1179,6 +1204,7 @@ __global__ void __launch_bounds__(256, EHB_BMIN_BLOCKS) ehb_k_raster_big(const _
     const int qn = min((int)p.ctr->q[lane].nUnits, p.unitCap);   // lane s: units of sub-queue s
     const float xs = p.xs, xo = p.xo, ys = p.ys, yo = p.yo;
     uint32_t* sb = s_blk[warp];
+    uint2* cmp = s_cmp[warp];
     // a block of a warp's shared memory <- global memory as ONE bulk asynchronous copy (UBLKCP) that completes on the
     // warp's mbarrier: no register staging, one instruction instead of a load + store per word
     auto fetch_issue = [&](const void* src, uint32_t bytes) {
@@ -1250,8 +1276,8 @@ __global__ void __launch_bounds__(256, EHB_BMIN_BLOCKS) ehb_k_raster_big(const _
                     }
                     t = lo; dy = r - off[t];
                 }
-                if (anyWide) ehb_rows_group<long long, double, EhbRecSoA>(recs, t, dy, lane, p.pool, xs, xo, ys, yo, bits);
-                else ehb_rows_group<int, float, EhbRecSoA>(recs, t, dy, lane, p.pool, xs, xo, ys, yo, bits);
+                if (anyWide) ehb_rows_group<long long, double, EhbRecSoA, false>(recs, t, dy, lane, p.pool, xs, xo, ys, yo, bits, cmp);
+                else ehb_rows_group<int, float, EhbRecSoA, false>(recs, t, dy, lane, p.pool, xs, xo, ys, yo, bits, cmp);
             }
             continue;
         }
@@ -1261,8 +1287,8 @@ __global__ void __launch_bounds__(256, EHB_BMIN_BLOCKS) ehb_k_raster_big(const _
         const int dy = cur.dy0 + lane;
         const int t = dy < rc->h ? 0 : -1;
         const EhbRecAoS rv{reinterpret_cast<const uint32_t*>(rc)};
-        if (ext >= 32768) ehb_rows_group<long long, double, EhbRecAoS>(rv, t, dy, lane, p.pool, xs, xo, ys, yo, ubits, cur.dx0, cur.dx0 + EHB_UNIT_W - 1);
-        else ehb_rows_group<int, float, EhbRecAoS>(rv, t, dy, lane, p.pool, xs, xo, ys, yo, ubits, cur.dx0, cur.dx0 + EHB_UNIT_W - 1);
+        if (ext >= 32768) ehb_rows_group<long long, double, EhbRecAoS, true>(rv, t, dy, lane, p.pool, xs, xo, ys, yo, ubits, cmp, cur.dx0, cur.dx0 + EHB_UNIT_W - 1);
+        else ehb_rows_group<int, float, EhbRecAoS, true>(rv, t, dy, lane, p.pool, xs, xo, ys, yo, ubits, cmp, cur.dx0, cur.dx0 + EHB_UNIT_W - 1);
     }
     if (lane == 0) EHB_TL_STOP(p, 3, blockIdx.x * 8 + warp, tl0);
     EHB_MARK(p, 12);
