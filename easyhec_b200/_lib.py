@@ -84,6 +84,9 @@ _PROTOS = {
                                          C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
     "ehb_adam_step_recv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
                                      C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
+    "ehb_adam_step_compose": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float,
+                                        C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_void_p, C.c_void_p]),
     "ehb_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
     "ehb_solver_step_begin_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
@@ -487,11 +490,21 @@ class Context:
                   W, float(grad_scale), float(loss_scale), _ptr(out), _stream(self.device)))
         return out
 
-    def adam_step(self, dof, g7, state, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, hist=None, recv=False):
+    def adam_step(self, dof, g7, state, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, hist=None, recv=False, compose=None):
+        """torch.optim.Adam step of the 6 parameters on the device.  compose=(K, link_poses, H, W, mvp_out): the same launch
+        also writes the matrices of the next iteration from the updated parameters (ehb_adam_step_compose)."""
         _dev_check(dof, torch.float32, self.device, "dof")
         _dev_check(g7, torch.float32, self.device, "g7")
         _dev_check(state, torch.float32, self.device, "state")
         cap = 0 if hist is None else hist.shape[0]
+        if compose is not None:
+            K, lp, H, W, mvp = compose
+            _dev_check(K, torch.float32, self.device, "K"); _dev_check(lp, torch.float32, self.device, "link_poses")
+            _dev_check(mvp, torch.float32, self.device, "mvp")
+            _check(lib().ehb_adam_step_compose(self._h, _ptr(dof), _ptr(g7), _ptr(state), lr, betas[0], betas[1], eps, weight_decay,
+                                               _ptr(hist), cap, int(bool(recv)), _ptr(K), _ptr(lp), lp.shape[0], lp.shape[1], H, W,
+                                               _ptr(mvp), _stream(self.device)))
+            return
         fn = lib().ehb_adam_step_recv if recv else lib().ehb_adam_step
         _check(fn(self._h, _ptr(dof), _ptr(g7), _ptr(state), lr, betas[0], betas[1], eps, weight_decay,
                   _ptr(hist), cap, _stream(self.device)))

@@ -1412,7 +1412,22 @@ int ehb_adam_step(ehb_ctx_t h, float* dof_dev, const float* g7_dev, float* state
     if (!c || !dof_dev || !g7_dev || !state_dev) return fail(EHB_E_ARG, "bad adam arguments");
     DeviceGuard guard(c->device);
     CU(launch(ehb_k_adam, dim3(1), dim3(32), 0, (cudaStream_t)stream, true, dof_dev, (float*)g7_dev, state_dev, lr, beta1, beta2, eps,
-              weight_decay, hist_dev, hist_cap, c->comm, 0));
+              weight_decay, hist_dev, hist_cap, c->comm, 0, (const float*)nullptr, (const float*)nullptr, 0, 0, 0, (float*)nullptr));
+    c->launches += 1;
+    return EHB_OK;
+}
+
+int ehb_adam_step_compose(ehb_ctx_t h, float* dof_dev, float* g7_dev, float* state_dev, float lr, float beta1, float beta2,
+                          float eps, float weight_decay, float* hist_dev, int hist_cap, int recv, const float* K_dev,
+                          const float* link_poses_dev, int B, int L, int H, int W, float* mvp_dev, void* stream)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || !dof_dev || !g7_dev || !state_dev || !K_dev || !link_poses_dev || !mvp_dev || B < 1 || L < 1)
+        return fail(EHB_E_ARG, "bad adam_step_compose arguments");
+    if (recv && !c->commReady) return fail(EHB_E_ARG, "peer mailboxes are not connected (ehb_comm_connect)");
+    DeviceGuard guard(c->device);
+    CU(launch(ehb_k_adam, dim3(1), dim3(256), 0, (cudaStream_t)stream, true, dof_dev, g7_dev, state_dev, lr, beta1, beta2, eps,
+              weight_decay, hist_dev, hist_cap, c->comm, recv ? 1 : 0, K_dev, link_poses_dev, B * L, H, W, mvp_dev));
     c->launches += 1;
     return EHB_OK;
 }
@@ -1425,7 +1440,7 @@ int ehb_adam_step_recv(ehb_ctx_t h, float* dof_dev, float* g7_dev, float* state_
     if (!c->commReady) return fail(EHB_E_ARG, "peer mailboxes are not connected (ehb_comm_connect)");
     DeviceGuard guard(c->device);
     CU(launch(ehb_k_adam, dim3(1), dim3(32), 0, (cudaStream_t)stream, true, dof_dev, g7_dev, state_dev, lr, beta1, beta2, eps,
-              weight_decay, hist_dev, hist_cap, c->comm, 1));
+              weight_decay, hist_dev, hist_cap, c->comm, 1, (const float*)nullptr, (const float*)nullptr, 0, 0, 0, (float*)nullptr));
     c->launches += 1;
     return EHB_OK;
 }
@@ -1523,7 +1538,7 @@ int ehb_step_begin(ehb_ctx_t h, int slot, const int* mesh_ids, int L, int B, int
         c->launches += 1;
         if (adam) {
             CU(launch(ehb_k_adam, dim3(1), dim3(32), 0, st, true, sio->adam_dof_dev, o7, sio->adam_state_dev, sio->lr, 0.9f, 0.999f, 1e-8f,
-                      sio->weight_decay, (float*)nullptr, 0, c->commSlot[slot], exch));
+                      sio->weight_decay, (float*)nullptr, 0, c->commSlot[slot], exch, (const float*)nullptr, (const float*)nullptr, 0, 0, 0, (float*)nullptr));
             c->launches += 1;
         }
         if (sio->out7_host) CU(cudaMemcpyAsync(sio->out7_host, o7, 7 * sizeof(float), cudaMemcpyDeviceToHost, st));

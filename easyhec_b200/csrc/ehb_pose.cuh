@@ -77,12 +77,12 @@ __device__ __forceinline__ void ehb_projection(const float* K, int H, int W, flo
     P[14] = 1.f;
 }
 
-__global__ void ehb_k_pose_compose(const float* __restrict__ dof, const float* __restrict__ K,
-                                   const float* __restrict__ lp, int n, int H, int W, float* __restrict__ mvp)
+// mvp[i] = P @ (Tc @ lp[i]) for the matrices i = first, first + stride, ... (all threads of a block; M, Tc: 16 floats each in
+// shared memory, thread 0 fills them from dof / K first)
+__device__ __forceinline__ void ehb_compose_block(const float* __restrict__ dof, const float* __restrict__ K,
+                                                  const float* __restrict__ lp, int n, int H, int W, float* __restrict__ mvp,
+                                                  float* M, float* Tc, int first, int stride)
 {
-    ehb_pose_pdl_enter();
-    __shared__ float M[16];   // P @ [Tc; 0 0 0 1] is NOT pre-multiplied: the reference composes P @ (Tc @ lp)
-    __shared__ float Tc[16];
     if (threadIdx.x == 0) {
         float d[6], t[12];
         for (int i = 0; i < 6; i++) d[i] = dof[i];
@@ -94,7 +94,7 @@ __global__ void ehb_k_pose_compose(const float* __restrict__ dof, const float* _
         ehb_projection(k, H, W, M);
     }
     __syncthreads();
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = first; i < n; i += stride) {
         float A[16], B[16];
         for (int j = 0; j < 16; j++) A[j] = lp[(size_t)i * 16 + j];
         for (int r = 0; r < 4; r++)
@@ -114,6 +114,15 @@ __global__ void ehb_k_pose_compose(const float* __restrict__ dof, const float* _
                 mvp[(size_t)i * 16 + 4 * r + c] = s;
             }
     }
+}
+
+__global__ void ehb_k_pose_compose(const float* __restrict__ dof, const float* __restrict__ K,
+                                   const float* __restrict__ lp, int n, int H, int W, float* __restrict__ mvp)
+{
+    ehb_pose_pdl_enter();
+    __shared__ float M[16];   // P @ [Tc; 0 0 0 1] is NOT pre-multiplied: the reference composes P @ (Tc @ lp)
+    __shared__ float Tc[16];
+    ehb_compose_block(dof, K, lp, n, H, W, mvp, M, Tc, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -205,12 +214,16 @@ __global__ void __launch_bounds__(256) ehb_k_pose_backward(const float* __restri
 }
 
 // state = { m[6], v[6], t }.  torch.optim.Adam (L2 weight decay folded into the gradient, bias-corrected).
+// With mvp_out != NULL the same launch composes the matrices of the NEXT iteration from the updated parameters
+// (ehb_k_pose_compose's arithmetic): one launch less on the critical path of a pose-optimisation iteration.
 __global__ void ehb_k_adam(float* __restrict__ dof, float* __restrict__ g7, float* __restrict__ state, float lr,
                            float beta1, float beta2, float eps, float wd, float* __restrict__ hist, int hist_cap,
-                           const EhbComm cm, int recv)
+                           const EhbComm cm, int recv, const float* __restrict__ K, const float* __restrict__ lp, int n,
+                           int H, int W, float* __restrict__ mvp_out)
 {
     ehb_pose_pdl_enter();
     if (blockIdx.x != 0) return;
+    __shared__ float s_M[16], s_Tc[16];
     if (recv) {
         // second half of the fused all-reduce: wait until every rank's message of this step is in the own mailbox, add
         // them in rank order (bit-identical sums on every rank), leave the sum in g7
@@ -232,7 +245,7 @@ __global__ void ehb_k_adam(float* __restrict__ dof, float* __restrict__ g7, floa
         if (t == 0) *cm.step = step;
         __syncthreads();
     }
-    if (threadIdx.x != 0) return;
+    if (threadIdx.x == 0) {
     const int t = (int)state[12] + 1;
     if (hist && t - 1 < hist_cap)
         for (int i = 0; i < 6; i++) hist[(size_t)(t - 1) * 6 + i] = dof[i];
@@ -248,6 +261,11 @@ __global__ void ehb_k_adam(float* __restrict__ dof, float* __restrict__ g7, floa
         dof[i] = dof[i] - step_size * (m / denom);
     }
     state[12] = (float)t;
+    }
+    if (mvp_out) {
+        __syncthreads();                                   // (thread 0's parameter update is visible to itself; the others wait)
+        ehb_compose_block(dof, K, lp, n, H, W, mvp_out, s_M, s_Tc, threadIdx.x, blockDim.x);
+    }
 }
 
 __global__ void ehb_k_allreduce7(const EhbComm cm, float* __restrict__ g7)

@@ -4,7 +4,7 @@ The reference runs one Adam step per "epoch": zero_grad -> RBSolver.forward (B x
 backward -> Adam (easyhec/trainer/rbsolver.py:29-43, easyhec/solver/build.py:12-29: lr 3e-3, weight decay 5e-4
 as L2 on ``dof``).  Here one iteration is a fixed sequence of kernels
 
-    pose_compose -> [table, front, raster, raster_big, tiles] -> pose_backward -> (all-reduce 7 floats) -> adam
+    [front, raster, raster_big, tiles] -> pose_backward -> (all-reduce 7 floats) -> adam + pose_compose of the next iteration
 
 captured once into a CUDA graph and replayed; nothing returns to the host inside the loop.  When views are sharded
 over ranks (``torch.distributed``), each rank renders its own views and the only exchange is the 7-float
@@ -77,12 +77,15 @@ class PoseSolver:
             torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN, group=group)
             self._peer = ok.item() >= 1.0
         self._graph = None
+        self._mvp_valid = False      # self.mvp == compose(self.dof)
         self.iterations = 0
 
     # one iteration, enqueued on the current stream
     def _iteration(self):
         c = self.ctx
-        c.pose_compose(self.dof, self.K, self.link_poses, self.H, self.W, out=self.mvp)
+        if not self._mvp_valid:      # (outside the captured graph: the first iteration, or after a roll-back)
+            c.pose_compose(self.dof, self.K, self.link_poses, self.H, self.W, out=self.mvp)
+            self._mvp_valid = True
         c.render_views_fused(self.mesh_ids, self.mvp, self.ref, self.H, self.W, backward=True,
                              out=(self.masks, self.loss_b, self.g_mvp))
         # fused kernel scaled by 1/B_local; rescale so that the sum over ranks is the global mean's gradient
@@ -91,13 +94,19 @@ class PoseSolver:
                         grad_scale=self.B / self.B_global, loss_scale=1.0 / self.B_global, out=self.g7, send=fusedx)
         if self.world > 1 and not self._peer:
             torch.distributed.all_reduce(self.g7, group=self.group)
-        c.adam_step(self.dof, self.g7, self.state, self.lr, self.betas, self.eps, self.wd, hist=self.hist, recv=fusedx)
+        # Adam, and in the same launch the matrices of the next iteration from the updated parameters
+        c.adam_step(self.dof, self.g7, self.state, self.lr, self.betas, self.eps, self.wd, hist=self.hist, recv=fusedx,
+                    compose=(self.K, self.link_poses, self.H, self.W, self.mvp))
 
     def _overflowed(self) -> bool:
         """Synchronises; True when a launch since the last look overflowed a scratch pool on ANY rank (the decision to
         redo iterations must be the same everywhere, or the ranks' exchanges would fall out of step)."""
-        flags, _ = self.ctx.status()
-        bad = bool(flags & 1)
+        # one stream synchronisation per chunk, then the flags from host-visible memory (ehb_ctx_poll); the full status
+        # read-out -- a device synchronisation and two copies of every counter block -- only when a flag is up
+        torch.cuda.current_stream(self.device).synchronize()
+        bad = bool(self.ctx.poll() & 1)
+        if bad or self.ctx.poll():
+            self.ctx.status()
         if self.world > 1:
             t = torch.tensor([1.0 if bad else 0.0], device=self.device)
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX, group=self.group)
@@ -105,6 +114,9 @@ class PoseSolver:
         return bad
 
     def _capture(self):
+        if not self._mvp_valid:      # the captured iteration starts from valid matrices; it never composes them first
+            self.ctx.pose_compose(self.dof, self.K, self.link_poses, self.H, self.W, out=self.mvp)
+            self._mvp_valid = True
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         s = torch.cuda.Stream(self.device)
@@ -115,7 +127,7 @@ class PoseSolver:
         torch.cuda.current_stream(self.device).wait_stream(s)
         self._graph = g
 
-    def step(self, n: int = 1, check_every: int = 64):
+    def step(self, n: int = 1, check_every: int = 128):
         """Run n Adam iterations.  Iterations are replayed in chunks of `check_every` with no host synchronisation inside
         a chunk; after each chunk the sticky status flags are read once.  A scratch-pool overflow (the silhouette grew
         beyond what was reserved) restores the chunk's starting state, grows the scratch, re-captures the graph and
@@ -135,6 +147,7 @@ class PoseSolver:
                 if not self._overflowed():
                     break
                 self.dof.copy_(snap[0]); self.state.copy_(snap[1])
+                self._mvp_valid = False
                 self.ctx.grow_scratch()
                 self._graph = None                  # scratch buffers move when they grow: the captured pointers are stale
                 F = sum(self.ctx.mesh_info(i)[1] for i in self.mesh_ids)

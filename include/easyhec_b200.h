@@ -267,6 +267,12 @@ EHB_API int ehb_pose_backward_send(ehb_ctx_t ctx, const float* dof_dev, const fl
                            double loss_scale, float* out7_dev, void* stream);
 EHB_API int ehb_adam_step_recv(ehb_ctx_t ctx, float* dof_dev, float* g7_dev, float* state_dev, float lr, float beta1,
                        float beta2, float eps, float weight_decay, float* hist_dev, int hist_cap, void* stream);
+/* Adam update and, in the same launch, the matrices of the next iteration from the updated parameters (ehb_pose_compose's
+ * arithmetic): mvp_dev f32[B*L*16].  recv != 0: the gradient is first summed over the ranks (as ehb_adam_step_recv). */
+EHB_API int ehb_adam_step_compose(ehb_ctx_t ctx, float* dof_dev, float* g7_dev, float* state_dev, float lr, float beta1,
+                                  float beta2, float eps, float weight_decay, float* hist_dev, int hist_cap, int recv,
+                                  const float* K_dev, const float* link_poses_dev, int B, int L, int H, int W, float* mvp_dev,
+                                  void* stream);
 
 /* Number of kernels this library has launched on the context since creation (for launch accounting). */
 EHB_API long long ehb_launch_count(ehb_ctx_t ctx);

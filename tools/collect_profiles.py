@@ -12,7 +12,7 @@ rnd = sys.argv[2] if len(sys.argv) > 2 else "r01"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 dst = os.path.join(ROOT, "profiles")
 os.makedirs(dst, exist_ok=True)
-KERNELS = ["table", "front", "raster", "raster_big", "tiles"]
+KERNELS = ["front", "raster", "raster_big", "tiles"]
 
 for a, b in [("bench.json", "bench_%s.json"), ("bench_reference.json", "bench_%s_reference.json"),
              ("bench_inview.json", "bench_%s_inview.json"), ("configs.jsonl", "configs_%s.jsonl"), ("launches.csv", "launches_%s.csv"),
@@ -51,7 +51,7 @@ with open(os.path.join(dst, "ncu_%s_summary.txt" % rnd), "w") as f:
 traffic["raster"] = traffic.get("raster", 0) + traffic.pop("raster_big", 0)
 json.dump(traffic, open(os.path.join(dst, "traffic.json"), "w"), indent=1)
 with open(os.path.join(dst, "ncu_%s_source_lines.txt" % rnd), "w") as f:
-    for k in ["raster", "raster_big", "tiles", "front", "table"]:
+    for k in ["raster", "raster_big", "tiles", "front"]:
         rep = os.path.join(src, k + ".ncu-rep")
         if not os.path.exists(rep):
             continue

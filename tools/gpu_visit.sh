@@ -24,8 +24,8 @@ for A in "$@"; do
   ncu)
     timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv \
         python bench.py --steps 4 --warmup 3 --no-cpu > $O/ncu_launches.log 2>&1
-    for K in ${NCU_KERNELS:-raster raster_big}; do
-      EHB_PIPES=1 EHB_BENCH_NOGRAPH=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ehb_k_$K\$ -s 14 -c 1 -f -o $O/$K \
+    for K in ${NCU_KERNELS:-front raster raster_big tiles}; do
+      EHB_PIPES=1 EHB_BENCH_NOGRAPH=1 EHB_VALUE_SLOTS=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ehb_k_$K\$ -s 10 -c 1 -f -o $O/$K \
         python bench.py --steps 4 --warmup 3 --no-cpu > $O/ncu_$K.log 2>&1
       ls -la $O/$K.ncu-rep
     done
