@@ -6,6 +6,12 @@
 // fp32 rounding per operation in a fixed order (this translation unit is compiled with -fmad=false;
 // intended fused operations use __fmaf_rn explicitly) so that coverage, depth winners and the
 // antialias weights are reproducible bit for bit against the CPU checker in oracle/.
+//
+// Provenance of the antialias arithmetic: ehb_aa_pair / ehb_aa_pair_grad keep the operation ORDER and the constants of
+// nvdiffrast's published antialias analysis / gradient kernels as summarised in SURVEY.md Appendix A.4 (nvdiffrast is
+// not vendored under /root/reference and was not available here; NVIDIA non-commercial source licence).  The order is
+// parity-mandated -- another order changes the last bits of the blend weights -- and is the only thing taken over: the
+// rasterizer, the data layout and the work decomposition are this repository's own (no bin / coarse / fine pipeline).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

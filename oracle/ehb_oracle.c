@@ -26,6 +26,13 @@
  *   eho_union_binary / eho_variance_scores
  *                            easyhec/utils/render_api.py:70-96 + space_explorer.py:152-165
  *
+ * PROVENANCE of the antialias arithmetic: the pair analysis (pair_alpha) and its gradient (pair_grad) keep the
+ * operation ORDER and the constants of nvdiffrast's published antialias analysis / gradient kernels as summarised
+ * in SURVEY.md Appendix A.4 (nvdiffrast itself is NOT under /root/reference and was not available here; its
+ * licence is NVIDIA's non-commercial source licence).  The order is parity-mandated -- a different order changes
+ * the last bits of the blend weights -- and is the only thing taken over; the rasterizer, the data layout and
+ * the work decomposition around it are this repository's own.
+ *
  * All fp32 arithmetic is written one rounding per operation (compile with -ffp-contract=off);
  * the CUDA kernels use the same operation order with __fmul_rn/__fadd_rn so that coverage,
  * depth winners and antialias weights are reproducible bit for bit.
