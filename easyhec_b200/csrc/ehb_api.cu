@@ -464,6 +464,7 @@ struct Io {
     float* masks = nullptr; double* loss = nullptr; double* gmvp = nullptr; float* gpos = nullptr;
     const float* dy = nullptr; uint8_t* out_u8 = nullptr; float* score = nullptr; int C = 0;
     int do_bwd = 0, clamp = 0; float invB = 1.f;
+    int inflight = 0;                 // the pass is one of several in flight (slots): fewest instructions rather than shortest tails
     const uint32_t* refBits = nullptr; const uint32_t* refCnt = nullptr; const unsigned long long* refTotal = nullptr;
 };
 
@@ -622,6 +623,9 @@ int run_pass(Ctx* c, Scratch& sc, const int* mesh_ids, int L, int items, const f
     p.vclip = sc.vclip.p; p.vsnap = sc.vsnap.p;
     p.plane = sc.plane.p; p.pool = sc.pool.p; p.poolCap = sc.pool.n;
     p.tileList = sc.tileList.p; p.emptyList = sc.emptyList.p; p.touch = unionMode ? nullptr : sc.touch.p; p.bigRec = sc.bigRec.p; p.units = sc.units.p; p.bigCap = (int)(sc.bigRec.n / EHB_NQ); p.unitCap = (int)(sc.units.n / EHB_NQ); p.batchBlk = tune_int("EHB_NO_OFFLOAD", 0) ? nullptr : sc.batchBlk.p; p.batchCap = c->poolBudget == 0.0 ? 1 : BATCH_CAP / EHB_NQ; p.ctr = sc.ctr; p.bits = unionMode ? nullptr : sc.bitPool.p; p.bitCap = unionMode ? 0 : sc.bitPool.n; p.bigBits = unionMode ? nullptr : sc.bigBits.p; p.batchList = sc.batchList.p; p.heavyArea = (float)tune_int("EHB_HEAVY_AREA", 1024);
+    const int ovArea = tune_int("EHB_SMALL_AREA", -1), ovInline = tune_int("EHB_RINLINE", -1);   // (developer overrides)
+    p.smallArea = ovArea >= 0 ? ovArea : (io.inflight ? EHB_SMALL_AREA_INFLIGHT : EHB_SMALL_AREA_SERIAL);
+    p.inlineGroups = ovInline >= 1 ? ovInline : (io.inflight ? EHB_INLINE_INFLIGHT : EHB_INLINE_SERIAL);
     p.ref = io.ref; p.ref_u8 = io.ref_u8; p.masks = io.masks; p.loss = io.loss; p.gmvp = io.gmvp; p.gpos = io.gpos;
     p.dy = io.dy; p.out_u8 = io.out_u8;
     p.refBits = io.refBits; p.refCnt = io.refCnt; p.refTotal = io.refTotal;
@@ -1462,7 +1466,7 @@ int ehb_solver_step_begin_u8(ehb_ctx_t h, int slot, const int* mesh_ids, int L, 
     CU(cudaMemcpyAsync(c->slotRef[slot].p, ref_u8_host, npx, cudaMemcpyHostToDevice, st));
     Io io;
     io.ref_u8 = c->slotRef[slot].p; io.loss = c->slotOut[slot].p; io.gmvp = c->slotOut[slot].p + B;
-    io.do_bwd = 1; io.clamp = 1; io.invB = 1.0f / (float)B;
+    io.do_bwd = 1; io.clamp = 1; io.invB = 1.0f / (float)B; io.inflight = 1;
     r = run_pass(c, c->sc[MAX_PIPES + slot], mesh_ids, L, B, c->slotMvp[slot].p, H, W, EHB_MODE_FUSED, io, st);
     if (r) return r;
     CU(cudaMemcpyAsync(loss_host, c->slotOut[slot].p, B * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1489,7 +1493,7 @@ int ehb_solver_step_begin_ref(ehb_ctx_t h, int slot, const int* mesh_ids, int L,
     if ((r = ref_io(c, ref_id, first_view, B, H, W, io))) return r;
     CU(cudaMemcpyAsync(c->slotMvp[slot].p, mvp_host, nm * sizeof(float), cudaMemcpyHostToDevice, st));
     io.loss = c->slotOut[slot].p; io.gmvp = c->slotOut[slot].p + B;
-    io.do_bwd = 1; io.clamp = 1; io.invB = 1.0f / (float)B;
+    io.do_bwd = 1; io.clamp = 1; io.invB = 1.0f / (float)B; io.inflight = 1;
     r = run_pass(c, c->sc[MAX_PIPES + slot], mesh_ids, L, B, c->slotMvp[slot].p, H, W, EHB_MODE_FUSED, io, st);
     if (r) return r;
     CU(cudaMemcpyAsync(loss_host, c->slotOut[slot].p, B * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1526,7 +1530,7 @@ int ehb_step_begin(ehb_ctx_t h, int slot, const int* mesh_ids, int L, int B, int
         mvp = c->slotMvp[slot].p;
     }
     io.masks = sio->masks_dev; io.loss = c->slotOut[slot].p; io.gmvp = c->slotOut[slot].p + B;
-    io.do_bwd = 1; io.clamp = 1; io.invB = 1.0f / (float)B;
+    io.do_bwd = 1; io.clamp = 1; io.invB = 1.0f / (float)B; io.inflight = 1;
     r = run_pass(c, c->sc[MAX_PIPES + slot], mesh_ids, L, B, mvp, H, W, EHB_MODE_FUSED, io, st);
     if (r) return r;
     if (pose) {

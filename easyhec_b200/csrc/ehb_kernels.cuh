@@ -89,6 +89,7 @@ struct EhbParams {
     int H, W, ntx, nty, ntiles;
     int items, L, Lp, Ftot, Vtot;   // Lp = planes per item: L (per-link visibility) or 1 (packed robot)
     int hlo, hhi;
+    int smallArea, inlineGroups;   // per-pass knobs of the rasterizer (see EHB_SMALL_AREA_SERIAL / _INFLIGHT)
     uint32_t* batchList;     // [items * chunks]  the batches that survive the frustum test of their AABB (k_front)
     float heavyArea;         // screen footprint (px^2) of a batch's AABB from which it is listed in front
     int mode, rule, do_bwd, clamp;
@@ -192,10 +193,15 @@ __device__ __forceinline__ unsigned ehb_smid() { unsigned s; asm("mov.u32 %0, %%
 #else
 #define EHB_MARK(p, i)
 #endif
-#ifndef EHB_SMALL_AREA
-#define EHB_SMALL_AREA 256              // triangles whose clipped bbox has more candidate samples are deferred (96 -> 256
-                                        // with 4 inline groups: +8 % frames/s in flight -- less parking and re-fetching)
-#endif
+// Two knobs of the rasterizer are per pass (EhbParams): smallArea -- triangles whose clipped bbox has more candidate
+// samples are deferred to k_raster_big -- and inlineGroups -- groups of 32 rows a warp of k_raster draws itself before it
+// hands the rest of a heavy batch on.  A pass that runs alone wants its tails short (96 samples, 2 groups: the work
+// spreads over the chip early); passes in flight on the slots overlap each other's tails and want the fewest instructions
+// (256 samples, 4 groups: less parking and re-fetching, +8 % frames/s).  Measured on the B200, see DESIGN.md.
+#define EHB_SMALL_AREA_SERIAL 96
+#define EHB_INLINE_SERIAL 2
+#define EHB_SMALL_AREA_INFLIGHT 256
+#define EHB_INLINE_INFLIGHT 4
 #define EHB_NQ 32
 #define EHB_UNIT_W 64
 #define EHB_UNIT_H 32
@@ -624,9 +630,6 @@ __global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRo
 #ifndef EHB_RWARPS
 #define EHB_RWARPS 8         // warps per raster CTA; every warp works alone on batches of 32 triangles
 #endif
-#ifndef EHB_RINLINE
-#define EHB_RINLINE 4        // groups of 32 rows a warp of k_raster draws itself; the rest of a heavy batch is handed on
-#endif
 #ifndef EHB_RGROUPS
 #define EHB_RGROUPS 2        // groups of 32 rows per handed-on unit
 #endif
@@ -1029,7 +1032,7 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
         if (rows > 0) {
             const int ext = max(max(abs(rc.ex[0]), abs(rc.ex[1])), max(max(abs(rc.ex[2]), abs(rc.ey[0])), max(abs(rc.ey[1]), abs(rc.ey[2]))));
             wide = ext >= 32768;   // 32-bit edge arithmetic is exact below 2^15 sub-pixel units per edge
-            big = rc.w * rc.h > EHB_SMALL_AREA;   // not small: park the record, cut the bbox into bounded units
+            big = rc.w * rc.h > p.smallArea;   // not small: park the record, cut the bbox into bounded units
             ehb_rec_store_soa(s_rec[warp], lane, rc);
         }
     }
@@ -1122,15 +1125,15 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
     const bool anyWide = __any_sync(0xffffffffu, wide && rows > 0);
     __syncwarp();
     const int nRowsAll = off[32];
-    // A heavy batch would make this warp the tail of the launch: it keeps EHB_RINLINE groups of 32 rows and hands the
+    // A heavy batch would make this warp the tail of the launch: it keeps p.inlineGroups groups of 32 rows and hands the
     // rest to k_raster_big, which spreads such units over the whole chip (records + row prefix parked in global).  The
     // queue tickets are drawn before the inline groups and used after them, so nothing waits for the atomics.
-    const bool heavy = nRowsAll > 32 * EHB_RINLINE && p.batchBlk != nullptr;
+    const bool heavy = nRowsAll > 32 * p.inlineGroups && p.batchBlk != nullptr;
     const int ngroups = (nRowsAll + 31) >> 5;
-    const int nitems = heavy ? (ngroups - EHB_RINLINE + EHB_RGROUPS - 1) / EHB_RGROUPS : 0;
+    const int nitems = heavy ? (ngroups - p.inlineGroups + EHB_RGROUPS - 1) / EHB_RGROUPS : 0;
     unsigned slot = 0, u0 = 0;
     if (heavy && lane == 0) { slot = atomicAdd(&myq.nBatchBlk, 1u); u0 = atomicAdd(&myq.nUnits, (unsigned)nitems); }
-    const int nInline = heavy ? 32 * EHB_RINLINE : nRowsAll;
+    const int nInline = heavy ? 32 * p.inlineGroups : nRowsAll;
     auto draw_rows = [&](int rBegin, int rEnd) {
         for (int r0 = rBegin; r0 < rEnd; r0 += 32) {
             const int r = r0 + lane;
@@ -1165,7 +1168,7 @@ __global__ void __launch_bounds__(EHB_RWARPS * 32, EHB_RMIN_BLOCKS) ehb_k_raster
                 blk[1024 + 36] = (uint32_t)bits.pitch;
             }
             for (int i = lane; i < nitems; i += 32)
-                p.units[uBase + i] = EhbUnit{0x80000000u | slot, (unsigned short)(EHB_RINLINE + i * EHB_RGROUPS), (unsigned short)EHB_RGROUPS};
+                p.units[uBase + i] = EhbUnit{0x80000000u | slot, (unsigned short)(p.inlineGroups + i * EHB_RGROUPS), (unsigned short)EHB_RGROUPS};
         } else {   // no room: the units are void and the rest of the batch is drawn here
             for (int i = lane; i < nitems; i += 32)
                 if ((int)(u0 + i) < p.unitCap) p.units[uBase + i] = EhbUnit{0xFFFFFFFFu, 0, 0};

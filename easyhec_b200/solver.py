@@ -78,6 +78,8 @@ class PoseSolver:
             self._peer = ok.item() >= 1.0
         self._graph = None
         self._mvp_valid = False      # self.mvp == compose(self.dof)
+        import os
+        self._fuse_compose = not os.environ.get("EHB_SOLVER_NOFUSE")
         self.iterations = 0
 
     # one iteration, enqueued on the current stream
@@ -95,8 +97,12 @@ class PoseSolver:
         if self.world > 1 and not self._peer:
             torch.distributed.all_reduce(self.g7, group=self.group)
         # Adam, and in the same launch the matrices of the next iteration from the updated parameters
-        c.adam_step(self.dof, self.g7, self.state, self.lr, self.betas, self.eps, self.wd, hist=self.hist, recv=fusedx,
-                    compose=(self.K, self.link_poses, self.H, self.W, self.mvp))
+        if self._fuse_compose:
+            c.adam_step(self.dof, self.g7, self.state, self.lr, self.betas, self.eps, self.wd, hist=self.hist, recv=fusedx,
+                        compose=(self.K, self.link_poses, self.H, self.W, self.mvp))
+        else:
+            c.adam_step(self.dof, self.g7, self.state, self.lr, self.betas, self.eps, self.wd, hist=self.hist, recv=fusedx)
+            c.pose_compose(self.dof, self.K, self.link_poses, self.H, self.W, out=self.mvp)
 
     def _overflowed(self) -> bool:
         """Synchronises; True when a launch since the last look overflowed a scratch pool on ANY rank (the decision to
