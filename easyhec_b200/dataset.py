@@ -99,9 +99,35 @@ def write_offline_dataset(data_dir: str, masks, qpos, K, Tc_c2b=None, colors=Non
         np.savetxt(osp.join(data_dir, "Tc_c2b.txt"), np.asarray(Tc_c2b, dtype=np.float64))
 
 
+def adam_state_dict(adam_state=None, lr: float = 3e-3, weight_decay: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8):
+    """``torch.optim.Adam(...).state_dict()`` of the single 6-vector parameter, from the device solver's state
+    ``{m[6], v[6], t}`` (ehb_adam_step) -- what the reference's ``BaseTrainer.load`` hands to
+    ``optimizer.load_state_dict`` (trainer/base.py:398).  No state yet: an optimizer that has not stepped."""
+    group = {"lr": float(lr), "betas": tuple(betas), "eps": float(eps), "weight_decay": float(weight_decay), "amsgrad": False,
+             "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None, "params": [0]}
+    state = {}
+    if adam_state is not None:
+        a = torch.as_tensor(adam_state, dtype=torch.float32).detach().cpu().reshape(13)
+        if a[12] > 0:
+            state[0] = {"step": torch.tensor(float(a[12])), "exp_avg": a[0:6].clone(), "exp_avg_sq": a[6:12].clone()}
+    return {"state": state, "param_groups": [group]}
+
+
+def adam_state_from_dict(sd):
+    """The inverse: an Adam ``state_dict`` -> the device solver's 13 floats."""
+    a = torch.zeros(13)
+    st = sd.get("state", {}).get(0)
+    if st:
+        a[0:6] = st["exp_avg"].float().reshape(6); a[6:12] = st["exp_avg_sq"].float().reshape(6); a[12] = float(st["step"])
+    return a
+
+
 def save_checkpoint(path: str, dof, history_ops=None, global_steps: int = 0, epoch: int = 0, best_val_loss: float = 1e10,
-                    optimizer_state=None):
-    """Reference-layout checkpoint: ``ckpt['model']['dof']`` (6,), ``ckpt['model']['history_ops']`` (10000, 6)."""
+                    optimizer_state=None, adam_state=None, lr: float = 3e-3, weight_decay: float = 5e-4, scheduler_state=None):
+    """Reference-layout checkpoint (trainer/base.py:380-386): ``ckpt['model']['dof']`` (6,), ``ckpt['model']['history_ops']``
+    (10000, 6), ``optimizer`` (Adam state_dict layout, from ``adam_state`` = the device solver's 13 floats unless a ready
+    ``optimizer_state`` is given), ``scheduler`` (the constant-lr schedule's counters), ``epoch``, ``best_val_loss``,
+    ``global_steps`` -- every key ``BaseTrainer.load`` reads (base.py:388-402)."""
     dof = torch.as_tensor(dof, dtype=torch.float32).detach().cpu().reshape(6)
     hist = torch.zeros(HISTORY_CAPACITY, 6)
     if history_ops is not None:
@@ -109,8 +135,8 @@ def save_checkpoint(path: str, dof, history_ops=None, global_steps: int = 0, epo
         hist[:len(h)] = h
     d = {"model": {"dof": dof, "history_ops": hist}, "epoch": int(epoch), "best_val_loss": float(best_val_loss),
          "global_steps": int(global_steps)}
-    if optimizer_state is not None:
-        d["optimizer"] = optimizer_state
+    d["optimizer"] = optimizer_state if optimizer_state is not None else adam_state_dict(adam_state, lr, weight_decay)
+    d["scheduler"] = scheduler_state if scheduler_state is not None else {"last_epoch": int(global_steps), "_step_count": int(global_steps) + 1}
     os.makedirs(osp.dirname(osp.abspath(path)), exist_ok=True)
     torch.save(d, path)
     return path
@@ -126,4 +152,5 @@ def load_checkpoint(path: str):
     keep = (hist != 0).any(dim=1)
     n = int(keep.nonzero().max().item()) + 1 if keep.any() else 0
     return {"dof": dof, "Tc_c2b": dof_to_matrix(dof), "history_ops": hist[:n], "global_steps": int(ckpt.get("global_steps", 0)),
-            "epoch": int(ckpt.get("epoch", 0))}
+            "epoch": int(ckpt.get("epoch", 0)),
+            "adam_state": adam_state_from_dict(ckpt["optimizer"]) if isinstance(ckpt.get("optimizer"), dict) else torch.zeros(13)}

@@ -98,6 +98,10 @@ class RBSolver(nn.Module):
         self._ref, self._ref_key = None, None
         self._sized_for = None
 
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self._put_id = None          # history_ops came from a checkpoint: find the cursor on the next forward
+
     def _reference(self, masks_ref):
         """The batch's reference masks as the fused kernels want them.  The trainer hands over the SAME masks every
         iteration (one batch holds all views, rb_solver.py:49): they are registered with the context once (bit-packed) and
@@ -115,7 +119,10 @@ class RBSolver(nn.Module):
 
     def forward(self, dps):
         assert dps["global_step"] == 0
-        if self._put_id < self.history_ops.shape[0]:   # host-side cursor: no device sync (cf. rb_solver.py:50)
+        if self._put_id is None:     # after load_state_dict: resume at the first all-zero row like the reference (rb_solver.py:50)
+            used = (self.history_ops != 0).any(dim=1).nonzero()
+            self._put_id = int(used.max().item()) + 1 if used.numel() else 0      # (one synchronisation, once)
+        if self._put_id < self.history_ops.shape[0]:   # host-side cursor: no device sync per iteration
             self.history_ops[self._put_id] = self.dof.detach()
             self._put_id += 1
         Tc_c2b = se3_exp_map(self.dof[None]).permute(0, 2, 1)[0]

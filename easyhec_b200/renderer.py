@@ -52,6 +52,7 @@ class B200Renderer:
         self.opencv2blender = opencv2gl(self.device)
         self._meshes = OrderedDict()   # (faces ptr, F, version) -> [mesh_id, faces ref, verts key, verts ref]
         self._max_cached = 64
+        self._pf_key, self._pf = None, None   # projection @ flip of the last intrinsics tensor
 
     # -- mesh cache: the reference passes (verts, faces) tensors on every call ---------------------------
     @staticmethod
@@ -114,14 +115,24 @@ class B200Renderer:
         @param object_pose: 4,4 torch.tensor, float, cuda
         @return: mask: 0 to 1, HxW torch.cuda.FloatTensor (bool when anti_aliasing=False)
         """
-        proj = K_to_projection(K, self.H, self.W).to(self.device)
-        pose = self.opencv2blender @ object_pose
-        return self._render(verts, faces, proj @ pose, anti_aliasing)
+        return self._render(verts, faces, self._proj_flip(K) @ object_pose, anti_aliasing)
 
     def batch_render_mask(self, verts, faces, K, anti_aliasing=True):
         """Vertices already in the camera frame (packed multi-link mesh, render_api.py:81-92)."""
-        proj = K_to_projection(K, self.H, self.W).to(self.device)
-        return self._render(verts, faces, proj @ self.opencv2blender, anti_aliasing)
+        return self._render(verts, faces, self._proj_flip(K), anti_aliasing)
+
+    def _proj_flip(self, K):
+        """``K_to_projection(K, H, W) @ diag(1,-1,-1,1)``, kept per intrinsics tensor (storage + version): the reference
+        rebuilds the projection from sixteen 0-d tensors on every call (nvdiffrast_renderer.py:33-36), ~20 micro-kernels per
+        (view, link).  Multiplying by the flip first is bit-identical to the reference's ``proj @ (flip @ pose)``: the flip
+        only changes signs."""
+        if isinstance(K, torch.Tensor) and K.requires_grad:
+            return K_to_projection(K, self.H, self.W).to(self.device) @ self.opencv2blender
+        key = (K.data_ptr(), K._version, str(K.device)) if isinstance(K, torch.Tensor) else None
+        if key is None or key != self._pf_key:
+            self._pf = K_to_projection(K, self.H, self.W).to(self.device) @ self.opencv2blender
+            self._pf_key = key
+        return self._pf
 
 
 NVDiffrastRenderer = B200Renderer

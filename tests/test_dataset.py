@@ -82,3 +82,24 @@ def test_checkpoint_layout_and_roundtrip(tmp_path):
     back = load_checkpoint(p)
     assert torch.equal(back["history_ops"], hist) and back["global_steps"] == 17
     assert np.allclose(back["Tc_c2b"].numpy(), T, atol=1e-5)
+
+
+def test_checkpoint_has_every_key_the_reference_trainer_loads(tmp_path):
+    """BaseTrainer.load (trainer/base.py:388-402) reads model, optimizer, scheduler, epoch, best_val_loss, global_steps;
+    the optimizer entry must load into a torch.optim.Adam over the single 6-vector parameter."""
+    from easyhec_b200.dataset import adam_state_dict
+    dof = torch.arange(6, dtype=torch.float32) * 0.1
+    st = torch.cat([torch.full((6,), 0.25), torch.full((6,), 0.5), torch.tensor([7.0])])
+    p = save_checkpoint(str(tmp_path / "m.pth"), dof, None, global_steps=7, epoch=7, adam_state=st, lr=3e-3, weight_decay=5e-4)
+    raw = torch.load(p, map_location="cpu", weights_only=False)
+    assert {"model", "optimizer", "scheduler", "epoch", "best_val_loss", "global_steps"} <= set(raw)
+    param = torch.nn.Parameter(dof.clone())
+    opt = torch.optim.Adam([param], lr=1.0)
+    opt.load_state_dict(raw["optimizer"])
+    assert opt.param_groups[0]["lr"] == 3e-3 and opt.param_groups[0]["weight_decay"] == 5e-4
+    s0 = opt.state[param]
+    assert float(s0["step"]) == 7 and torch.allclose(s0["exp_avg"], st[0:6]) and torch.allclose(s0["exp_avg_sq"], st[6:12])
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=10**9)          # (a generic scheduler: __dict__.update of the entry)
+    sched.load_state_dict(raw["scheduler"])
+    assert torch.allclose(load_checkpoint(p)["adam_state"], st)
+    assert adam_state_dict(None)["state"] == {}          # an optimizer that has not stepped

@@ -110,7 +110,15 @@ def test_dropin_renderer_matches_oracle_and_autograd():
     # batch_render_mask: vertices already in the camera frame
     vc = (verts @ pose.detach()[:3, :3].T + pose.detach()[:3, 3]).contiguous()
     b2 = r.batch_render_mask(vc, faces, K, anti_aliasing=False)
-    assert (b2 != b).float().mean().item() < 2e-3
+    want2 = oracle.render_mask(vc.cpu().numpy(), m.faces, mvp_of(sc["K"], H, W, np.eye(4)), H, W, anti_aliasing=False)
+    assert np.array_equal(b2.cpu().numpy(), want2) and want2.sum() > 0     # the oracle on the same camera-frame vertices
+    # the projection is kept per intrinsics tensor: a second call gives the same mask, an in-place change of K a new one
+    assert torch.equal(r.render_mask(verts, faces, K, pose.detach()), mask.detach())
+    K2 = K.clone(); r.render_mask(verts, faces, K2, pose.detach()); K2[0, 2] += 7.0
+    shifted = r.render_mask(verts, faces, K2, pose.detach())
+    Ks = sc["K"].copy(); Ks[0, 2] += 7.0
+    want3 = oracle.render_mask(m.vertices, m.faces, mvp_of(Ks, H, W, pose.detach().cpu().numpy()), H, W, anti_aliasing=True)
+    assert np.abs(shifted.cpu().numpy() - want3).max() < 1e-6 and not torch.equal(shifted, mask.detach())
     with pytest.raises(RuntimeError):
         r.render_mask(verts, faces.long(), K, pose)        # int64 faces are rejected like nvdiffrast does
 
