@@ -116,9 +116,14 @@ def test_dropin_renderer_matches_oracle_and_autograd():
     assert torch.equal(r.render_mask(verts, faces, K, pose.detach()), mask.detach())
     K2 = K.clone(); r.render_mask(verts, faces, K2, pose.detach()); K2[0, 2] += 7.0
     shifted = r.render_mask(verts, faces, K2, pose.detach())
-    Ks = sc["K"].copy(); Ks[0, 2] += 7.0
-    want3 = oracle.render_mask(m.vertices, m.faces, mvp_of(Ks, H, W, pose.detach().cpu().numpy()), H, W, anti_aliasing=True)
-    assert np.abs(shifted.cpu().numpy() - want3).max() < 1e-6 and not torch.equal(shifted, mask.detach())
+    assert not torch.equal(shifted, mask.detach())
+    # the oracle on the matrix the operator composed (a 4x4 product on the device may round differently from the host's in the last
+    # ulp, which an antialiased edge magnifies); that matrix against the host composition separately
+    mvp3 = (r._proj_flip(K2) @ pose.detach()).cpu().numpy()
+    assert np.allclose(mvp3, mvp_of(K2.cpu().numpy(), H, W, pose.detach().cpu().numpy()), rtol=1e-5, atol=1e-6)
+    want3 = oracle.render_mask(m.vertices, m.faces, mvp3, H, W, anti_aliasing=True)
+    d3 = np.abs(shifted.cpu().numpy() - want3).max()
+    assert d3 < 1e-6, d3
     with pytest.raises(RuntimeError):
         r.render_mask(verts, faces.long(), K, pose)        # int64 faces are rejected like nvdiffrast does
 

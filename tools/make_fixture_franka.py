@@ -39,8 +39,8 @@ INIT = np.array([[9.3969262e-01, 3.4202009e-01, 6.4914198e-09, -6.4085639e-01],
                  [0.0, 0.0, 0.0, 1.0]])
 # The YAML pose overlaps the annotated masks with IoU 0.25 and the oracle-driven solve drifts away from it; a random
 # search over poses (mean per-view IoU as the score, union_binary of the oracle as the renderer, this session) ends at
-# the pose below (mean IoU 0.70; single views fitted alone reach 0.79-0.93, i.e. the capture itself -- qpos timing,
-# masks that include the fingers -- limits the fit).  The fixture's solve starts 2 cm / 2 deg away from it, like a
+# the pose below (mean IoU 0.70; single views fitted alone reach 0.79-0.93).  tools/franka_sync_probe.py shows why: the
+# capture's images lag its joint positions by about one sample in four of the ten views (IoU 0.87 once that is modelled).  The fixture's solve starts 2 cm / 2 deg away from it, like a
 # hand-tuned initialisation (tools/manual_tune_franka_init.py in the reference).
 TUNED = np.array([[0.96903512, -0.24688871, -0.00410332, -0.47387618],
                   [-0.12451614, -0.47423916, -0.87154636, 0.52374082],
