@@ -386,10 +386,11 @@ def run_b200(args):
         ctx.render_views_fused(ids, mvp_dev[s], ref_h[s], H, W, backward=True, out=(masks[s], loss, gmvp))
         ctx.pose_backward(dof_dev[s], K_dev, lp_dev[s], gmvp, loss, H, W, grad_scale=1.0 / world,
                           loss_scale=1.0 / (B * world), out=g7, send=use_peer)
-        if world > 1:   # the solver's one exchange step: all-reduce of (g_dof[6], loss) -- trainer/base.py:349 -- then Adam
-            if not use_peer:
-                dist.all_reduce(g7)
-            ctx.adam_step(dof_scratch, g7, adam_state, 3e-3, weight_decay=5e-4, recv=use_peer)
+        # the solver's one exchange step: all-reduce of (g_dof[6], loss) -- trainer/base.py:349 -- then Adam.  One rank runs
+        # the same chain without the exchange, so that the N-GPU lines differ from the 1-GPU line by the exchange alone.
+        if world > 1 and not use_peer:
+            dist.all_reduce(g7)
+        ctx.adam_step(dof_scratch, g7, adam_state, 3e-3, weight_decay=5e-4, recv=use_peer)
 
     def barrier():
         torch.cuda.synchronize()
@@ -449,7 +450,7 @@ def run_b200(args):
     def slot_step(k):
         s_, sl = k % R, k % S
         ctx.step_begin(sl, ids, ref_h[s_], H, W, mvp_dev[s_], masks=masks[s_], dof=dof_dev[s_], K=K_dev, link_poses=lp_dev[s_],
-                       out7=g7s[sl], adam_dof=dof_scr[sl] if world > 1 else None, adam_state=adam_st[sl] if world > 1 else None,
+                       out7=g7s[sl], adam_dof=dof_scr[sl], adam_state=adam_st[sl],
                        lr=3e-3, weight_decay=5e-4, grad_scale=1.0 / world, loss_scale=1.0 / (B * world), exchange=use_peer)
 
     slot_graph, slot_launches = None, None
@@ -695,8 +696,8 @@ def run_b200(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl["name"], "views_per_step_per_gpu": B, "H": H, "W": W, "links": L,
                            "triangles": F, "vertices": V, "onscreen_frac": onscreen, "coverage": coverage,
-                           "step": "fused render + loss + backward to d loss/d mvp, pose chain to d loss/d dof" +
-                                   (", all-reduce of 7 floats, Adam" if world > 1 else ""),
+                           "step": "fused render + loss + backward to d loss/d mvp, pose chain to d loss/d dof, " +
+                                   ("all-reduce of 7 floats, " if world > 1 else "") + "Adam",
                            "l2": "ring of %d view-sets (%.0f MB of masks+refs) > 126 MB L2" %
                                  (R, R * B * H * W * 8 / 1e6),
                            "pipelines": int(os.environ.get("EHB_PIPES", "3")),
