@@ -336,6 +336,8 @@ def run_b200(args):
     ctx = Context(dev)
     if os.environ.get("EHB_PIPES"):
         ctx.set_pipelines(int(os.environ["EHB_PIPES"]))
+    # default: the library splits a call over 3 pipelines only when it has more than 16 items
+    pipes_used = int(os.environ["EHB_PIPES"]) if os.environ.get("EHB_PIPES") else (1 if wl["B"] <= 16 else 3)
     # every rank renders the SAME scenes (weak scaling: B views per rank): the ranks' work is balanced by construction, so
     # what the N-GPU line shows is the cost of the exchange, not of unequal scenes
     sets = build_sets(wl, rank, R, same_on_every_rank=True)
@@ -384,13 +386,17 @@ def run_b200(args):
     def step(k):
         s = k % R
         ctx.render_views_fused(ids, mvp_dev[s], ref_h[s], H, W, backward=True, out=(masks[s], loss, gmvp))
-        ctx.pose_backward(dof_dev[s], K_dev, lp_dev[s], gmvp, loss, H, W, grad_scale=1.0 / world,
-                          loss_scale=1.0 / (B * world), out=g7, send=use_peer)
         # the solver's one exchange step: all-reduce of (g_dof[6], loss) -- trainer/base.py:349 -- then Adam.  One rank runs
         # the same chain without the exchange, so that the N-GPU lines differ from the 1-GPU line by the exchange alone.
-        if world > 1 and not use_peer:
+        if world == 1 or use_peer:   # pose chain (+ send), (recv +) Adam in one launch
+            ctx.pose_backward_adam(dof_dev[s], K_dev, lp_dev[s], gmvp, loss, H, W, adam_state, 3e-3, weight_decay=5e-4,
+                                   grad_scale=1.0 / world, loss_scale=1.0 / (B * world), out=g7, exchange=use_peer,
+                                   adam_dof=dof_scratch)
+        else:
+            ctx.pose_backward(dof_dev[s], K_dev, lp_dev[s], gmvp, loss, H, W, grad_scale=1.0 / world,
+                              loss_scale=1.0 / (B * world), out=g7)
             dist.all_reduce(g7)
-        ctx.adam_step(dof_scratch, g7, adam_state, 3e-3, weight_decay=5e-4, recv=use_peer)
+            ctx.adam_step(dof_scratch, g7, adam_state, 3e-3, weight_decay=5e-4)
 
     def barrier():
         torch.cuda.synchronize()
@@ -520,7 +526,7 @@ def run_b200(args):
     serial = {"value": frames / (ms_serial * 1e-3), "unit": "frames/s", "ms_per_step": ms_serial / max(args.steps, 1),
               "launch": "CUDA graph replay, one graph per ring slot" if graphs is not None else "eager",
               "what": "one step at a time on one stream (each step's views split over %d pipelines): the latency of a step, "
-                      "what a single sequential solve sees" % int(os.environ.get("EHB_PIPES", "3"))}
+                      "what a single sequential solve sees" % pipes_used}
 
     # ---- parity of what was just timed: GPU results of every ring slot, checked by the CPU leg below -------------
     gpu_results, slot_path_ok = [], None
@@ -700,7 +706,7 @@ def run_b200(args):
                                    ("all-reduce of 7 floats, " if world > 1 else "") + "Adam",
                            "l2": "ring of %d view-sets (%.0f MB of masks+refs) > 126 MB L2" %
                                  (R, R * B * H * W * 8 / 1e6),
-                           "pipelines": int(os.environ.get("EHB_PIPES", "3")),
+                           "pipelines": pipes_used,
                            "launch": ("%d steps in flight on the context's slots (ehb_step_begin), " % S +
                                       ("CUDA graph replay, %d steps per graph" % G if slot_graph is not None else "eager"))
                                      if inflight else ("CUDA graph replay, one graph per ring slot" if graphs is not None else "eager"),

@@ -89,6 +89,10 @@ _PROTOS = {
                                         C.c_int, C.c_void_p, C.c_void_p]),
     "ehb_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
+    "ehb_pose_backward_adam": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_void_p,
+                                         C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int,
+                                         C.c_void_p, C.c_void_p]),
     "ehb_solver_step_begin_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                            C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ehb_solver_step_end": (C.c_int, [C.c_void_p, C.c_int]),
@@ -508,6 +512,30 @@ class Context:
         fn = lib().ehb_adam_step_recv if recv else lib().ehb_adam_step
         _check(fn(self._h, _ptr(dof), _ptr(g7), _ptr(state), lr, betas[0], betas[1], eps, weight_decay,
                   _ptr(hist), cap, _stream(self.device)))
+
+    def pose_backward_adam(self, dof, K, link_poses, g_mvp, loss, H, W, state, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                           grad_scale=1.0, loss_scale=None, out=None, exchange=False, adam_dof=None, hist=None, mvp_next=None):
+        """pose_backward + (exchange) + adam_step (+ the next iteration's matrices) in one launch: the tail of a solver
+        iteration.  adam_dof: the parameters Adam updates (default: dof itself)."""
+        for t, n, dt in ((dof, "dof", torch.float32), (K, "K", torch.float32), (link_poses, "link_poses", torch.float32),
+                         (g_mvp, "g_mvp", torch.float64), (loss, "loss", torch.float64), (state, "state", torch.float32)):
+            _dev_check(t, dt, self.device, n)
+        B, L = link_poses.shape[0], link_poses.shape[1]
+        if loss_scale is None:
+            loss_scale = 1.0 / B
+        if out is None:
+            out = torch.empty((7,), dtype=torch.float32, device=self.device)
+        if adam_dof is None:
+            adam_dof = dof
+        _dev_check(adam_dof, torch.float32, self.device, "adam_dof")
+        if mvp_next is not None:
+            _dev_check(mvp_next, torch.float32, self.device, "mvp_next")
+        cap = 0 if hist is None else hist.shape[0]
+        _check(lib().ehb_pose_backward_adam(self._h, _ptr(dof), _ptr(K), _ptr(link_poses), _ptr(g_mvp), _ptr(loss), B, L, H, W,
+                                            float(grad_scale), float(loss_scale), _ptr(out), int(bool(exchange)), _ptr(adam_dof),
+                                            _ptr(state), lr, betas[0], betas[1], eps, weight_decay, _ptr(hist), cap,
+                                            _ptr(mvp_next), _stream(self.device)))
+        return out
 
     def solver_step_begin_u8(self, slot, mesh_ids, mvp_host, ref_u8_host, H, W, loss_host, g_mvp_host):
         """Asynchronous host-buffer step on slot 0/1 (own stream): returns at once; pair with solver_step_end(slot)."""

@@ -126,6 +126,7 @@ struct Ctx {
     int occRaster = 4;                // resident k_raster CTAs per SM (persistent warps)
     int rule = 0;
     int nPipes = 3;
+    bool pipesAuto = true;            // a call of <= 16 items runs as one pipeline unless the count was set explicitly (measured: r02)
     std::vector<Mesh> meshes;
     std::vector<Ref> refs;
     std::vector<KinTree*> robots;     // device copies of registered kinematic trees (ehb_robot_register)
@@ -701,7 +702,8 @@ int run_split(Ctx* c, const int* mesh_ids, int L, int items, const float* mvp_de
               cudaStream_t st)
 {
     if (!c) return fail(EHB_E_ARG, "null context");
-    const int n = (c->profiling || items < 2) ? 1 : std::min(c->nPipes, items);
+    // few items: the forks / joins and the split tails cost more than the overlap gives (10 views: 94 us against 101 us)
+    const int n = (c->profiling || items < 2 || (c->pipesAuto && items <= 16)) ? 1 : std::min(c->nPipes, items);
     if (n <= 1) return run_pass(c, c->sc[0], mesh_ids, L, items, mvp_dev, H, W, mode, io, st);
     DeviceGuard guard(c->device);
     const size_t px = (size_t)H * W;
@@ -757,6 +759,7 @@ int ehb_ctx_create(int device, ehb_ctx_t* out)
     Ctx* c = new Ctx();
     c->device = device;
     c->nSM = prop.multiProcessorCount;
+    if (getenv("EHB_PIPES")) c->pipesAuto = false;
     c->nPipes = std::max(1, std::min(MAX_PIPES, tune_int("EHB_PIPES", c->nPipes)));   // (developer switch; ehb_ctx_set_pipelines)
     CU(cudaMalloc((void**)&c->ctr, N_SCRATCH * sizeof(EhbCounters)));
     CU(cudaMemset(c->ctr, 0, N_SCRATCH * sizeof(EhbCounters)));
@@ -962,6 +965,7 @@ int ehb_ctx_set_pipelines(ehb_ctx_t h, int n)
     Ctx* c = (Ctx*)h;
     if (!c || n < 1 || n > MAX_PIPES) return fail(EHB_E_ARG, "pipelines must be in [1, %d]", MAX_PIPES);
     c->nPipes = n;
+    c->pipesAuto = false;
     return EHB_OK;
 }
 
@@ -1436,6 +1440,25 @@ int ehb_adam_step_compose(ehb_ctx_t h, float* dof_dev, float* g7_dev, float* sta
     return EHB_OK;
 }
 
+int ehb_pose_backward_adam(ehb_ctx_t h, const float* dof_dev, const float* K_dev, const float* link_poses_dev,
+                           const double* g_mvp_dev, const double* loss_dev, int B, int L, int H, int W, double grad_scale,
+                           double loss_scale, float* out7_dev, int exchange, float* adam_dof_dev, float* state_dev, float lr,
+                           float beta1, float beta2, float eps, float weight_decay, float* hist_dev, int hist_cap,
+                           float* mvp_next_dev, void* stream)
+{
+    Ctx* c = (Ctx*)h;
+    if (!c || !dof_dev || !K_dev || !link_poses_dev || !g_mvp_dev || !loss_dev || !out7_dev || !adam_dof_dev || !state_dev ||
+        B < 1 || L < 1)
+        return fail(EHB_E_ARG, "bad pose_backward_adam arguments");
+    if (exchange && !c->commReady) return fail(EHB_E_ARG, "peer mailboxes are not connected (ehb_comm_connect)");
+    DeviceGuard guard(c->device);
+    CU(launch(ehb_k_pose_adam, dim3(1), dim3(256), 0, (cudaStream_t)stream, true, dof_dev, K_dev, link_poses_dev, g_mvp_dev,
+              loss_dev, B, L, H, W, grad_scale, loss_scale, out7_dev, c->comm, exchange ? 1 : 0, adam_dof_dev, state_dev, lr,
+              beta1, beta2, eps, weight_decay, hist_dev, hist_cap, mvp_next_dev));
+    c->launches += 1;
+    return EHB_OK;
+}
+
 int ehb_adam_step_recv(ehb_ctx_t h, float* dof_dev, float* g7_dev, float* state_dev, float lr, float beta1, float beta2,
                        float eps, float weight_decay, float* hist_dev, int hist_cap, void* stream)
 {
@@ -1536,15 +1559,17 @@ int ehb_step_begin(ehb_ctx_t h, int slot, const int* mesh_ids, int L, int B, int
     if (pose) {
         float* o7 = sio->out7_dev ? sio->out7_dev : reinterpret_cast<float*>(c->slotOut[slot].p + B + nm);
         const double gs = sio->grad_scale != 0.0 ? sio->grad_scale : 1.0, ls = sio->loss_scale != 0.0 ? sio->loss_scale : 1.0 / (double)B;
-        CU(launch(ehb_k_pose_backward, dim3(1), dim3(256), 0, st, true, sio->dof_dev, sio->K_dev, sio->link_poses_dev,
-                  (const double*)(c->slotOut[slot].p + B), (const double*)c->slotOut[slot].p, B, L, H, W, gs, ls, o7,
-                  c->commSlot[slot], exch));
-        c->launches += 1;
-        if (adam) {
-            CU(launch(ehb_k_adam, dim3(1), dim3(32), 0, st, true, sio->adam_dof_dev, o7, sio->adam_state_dev, sio->lr, 0.9f, 0.999f, 1e-8f,
-                      sio->weight_decay, (float*)nullptr, 0, c->commSlot[slot], exch, (const float*)nullptr, (const float*)nullptr, 0, 0, 0, (float*)nullptr));
-            c->launches += 1;
+        if (adam) {   // pose chain, exchange and Adam in one launch
+            CU(launch(ehb_k_pose_adam, dim3(1), dim3(256), 0, st, true, sio->dof_dev, sio->K_dev, sio->link_poses_dev,
+                      (const double*)(c->slotOut[slot].p + B), (const double*)c->slotOut[slot].p, B, L, H, W, gs, ls, o7,
+                      c->commSlot[slot], exch, sio->adam_dof_dev, sio->adam_state_dev, sio->lr, 0.9f, 0.999f, 1e-8f,
+                      sio->weight_decay, (float*)nullptr, 0, (float*)nullptr));
+        } else {
+            CU(launch(ehb_k_pose_backward, dim3(1), dim3(256), 0, st, true, sio->dof_dev, sio->K_dev, sio->link_poses_dev,
+                      (const double*)(c->slotOut[slot].p + B), (const double*)c->slotOut[slot].p, B, L, H, W, gs, ls, o7,
+                      c->commSlot[slot], exch));
         }
+        c->launches += 1;
         if (sio->out7_host) CU(cudaMemcpyAsync(sio->out7_host, o7, 7 * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     if (sio->loss_host) CU(cudaMemcpyAsync(sio->loss_host, c->slotOut[slot].p, B * sizeof(double), cudaMemcpyDeviceToHost, st));

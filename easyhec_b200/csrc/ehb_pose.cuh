@@ -141,17 +141,18 @@ struct EhbComm {
 
 // one block of 256 threads.  out7 = { d loss / d dof [6], loss } with the caller's scales applied.  The tail is spread over
 // threads (12 for P^T S, 6 for the six dual-number evaluations of the exp map): fp64 on one thread was 6 us of pure latency.
-__global__ void __launch_bounds__(256) ehb_k_pose_backward(const float* __restrict__ dof, const float* __restrict__ K,
-                                                           const float* __restrict__ lp, const double* __restrict__ gmvp,
-                                                           const double* __restrict__ loss, int B, int L, int H, int W,
-                                                           double grad_scale, double loss_scale, float* __restrict__ out7,
-                                                           const EhbComm cm, int send)
+struct EhbPoseShared {
+    float out[8];
+    double S[8][17];
+    double T[17];
+    double G[12];
+};
+__device__ __forceinline__ void ehb_pose_backward_block(EhbPoseShared& sh, const float* __restrict__ dof, const float* __restrict__ K,
+                                                        const float* __restrict__ lp, const double* __restrict__ gmvp,
+                                                        const double* __restrict__ loss, int B, int L, int H, int W,
+                                                        double grad_scale, double loss_scale, float* __restrict__ out7,
+                                                        const EhbComm& cm, int send)
 {
-    ehb_pose_pdl_enter();
-    __shared__ float s_out[8];
-    __shared__ double S[8][17];
-    __shared__ double T[17];
-    __shared__ double G[12];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // S = sum_{b,l} g_mvp[b,l] @ lp[b,l]^T ;  S[16] = sum_b loss_b
     double acc[17];
@@ -170,13 +171,13 @@ __global__ void __launch_bounds__(256) ehb_k_pose_backward(const float* __restri
     for (int i = 0; i < 17; i++) {
         double v = acc[i];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) S[warp][i] = v;
+        if (lane == 0) sh.S[warp][i] = v;
     }
     __syncthreads();
     if (tid < 17) {
         double t = 0.0;
-        for (int w = 0; w < 8; w++) t += S[w][tid];
-        T[tid] = t;
+        for (int w = 0; w < 8; w++) t += sh.S[w][tid];
+        sh.T[tid] = t;
     }
     __syncthreads();
     if (tid < 12) {   // top three rows of P^T @ S
@@ -185,8 +186,8 @@ __global__ void __launch_bounds__(256) ehb_k_pose_backward(const float* __restri
         ehb_projection(k, H, W, P);
         const int r = tid >> 2, c = tid & 3;
         double s = 0.0;
-        for (int q = 0; q < 4; q++) s += (double)P[4 * q + r] * T[4 * q + c];
-        G[tid] = s;
+        for (int q = 0; q < 4; q++) s += (double)P[4 * q + r] * sh.T[4 * q + c];
+        sh.G[tid] = s;
     }
     __syncthreads();
     if (tid < 6) {
@@ -194,28 +195,92 @@ __global__ void __launch_bounds__(256) ehb_k_pose_backward(const float* __restri
         for (int j = 0; j < 6; j++) d[j] = {(double)dof[j], j == tid ? 1.0 : 0.0};
         ehb_se3_exp<EhbDual>(d, t, 1e-4);
         double s = 0.0;
-        for (int j = 0; j < 12; j++) s += G[j] * t[j].d;
-        out7[tid] = s_out[tid] = (float)(s * grad_scale);
+        for (int j = 0; j < 12; j++) s += sh.G[j] * t[j].d;
+        out7[tid] = sh.out[tid] = (float)(s * grad_scale);
     } else if (tid == 6) {
-        out7[6] = s_out[6] = (float)(T[16] * loss_scale);
+        out7[6] = sh.out[6] = (float)(sh.T[16] * loss_scale);
     }
     if (send) {
         // first half of the all-reduce, fused: this rank's 7 floats + the step tag go into every peer's mailbox (plain
-        // stores over NVLink); ehb_k_adam (recv) waits for all of them and adds them in rank order
+        // stores over NVLink); the Adam half (recv) waits for all of them and adds them in rank order
         __syncthreads();
         if (tid < cm.world) {
             const unsigned int step = *cm.step + 1u;
             volatile unsigned int* dst = cm.peer[tid] + ((size_t)(step & 1u) * EHB_COMM_MAX + cm.rank) * 8;
-            for (int i = 0; i < 7; i++) dst[i] = __float_as_uint(s_out[i]);
+            for (int i = 0; i < 7; i++) dst[i] = __float_as_uint(sh.out[i]);
             __threadfence_system();
             dst[7] = step;
         }
     }
 }
 
+__global__ void __launch_bounds__(256) ehb_k_pose_backward(const float* __restrict__ dof, const float* __restrict__ K,
+                                                           const float* __restrict__ lp, const double* __restrict__ gmvp,
+                                                           const double* __restrict__ loss, int B, int L, int H, int W,
+                                                           double grad_scale, double loss_scale, float* __restrict__ out7,
+                                                           const EhbComm cm, int send)
+{
+    ehb_pose_pdl_enter();
+    __shared__ EhbPoseShared sh;
+    ehb_pose_backward_block(sh, dof, K, lp, gmvp, loss, B, L, H, W, grad_scale, loss_scale, out7, cm, send);
+}
+
 // state = { m[6], v[6], t }.  torch.optim.Adam (L2 weight decay folded into the gradient, bias-corrected).
 // With mvp_out != NULL the same launch composes the matrices of the NEXT iteration from the updated parameters
 // (ehb_k_pose_compose's arithmetic): one launch less on the critical path of a pose-optimisation iteration.
+struct EhbAdamShared {
+    float M[16], Tc[16];
+    float val[EHB_COMM_MAX][7];
+};
+__device__ __forceinline__ void ehb_adam_block(EhbAdamShared& sh, float* __restrict__ dof, float* __restrict__ g7,
+                                               float* __restrict__ state, float lr, float beta1, float beta2, float eps, float wd,
+                                               float* __restrict__ hist, int hist_cap, const EhbComm& cm, int recv,
+                                               const float* __restrict__ K, const float* __restrict__ lp, int n, int H, int W,
+                                               float* __restrict__ mvp_out)
+{
+    if (recv) {
+        // second half of the fused all-reduce: wait until every rank's message of this step is in the own mailbox, add
+        // them in rank order (bit-identical sums on every rank), leave the sum in g7
+        const int t = threadIdx.x;
+        const unsigned int step = *cm.step + 1u;
+        if (t < cm.world) {
+            volatile unsigned int* src = cm.peer[cm.rank] + ((size_t)(step & 1u) * EHB_COMM_MAX + t) * 8;
+            while (src[7] != step) { }
+            __threadfence_system();
+            for (int i = 0; i < 7; i++) sh.val[t][i] = __uint_as_float(src[i]);
+        }
+        __syncthreads();
+        if (t < 7) {
+            float acc = 0.f;
+            for (int r = 0; r < cm.world; r++) acc += sh.val[r][t];
+            g7[t] = acc;
+        }
+        if (t == 0) *cm.step = step;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int t = (int)state[12] + 1;
+        if (hist && t - 1 < hist_cap)
+            for (int i = 0; i < 6; i++) hist[(size_t)(t - 1) * 6 + i] = dof[i];
+        const double bc1 = 1.0 - pow((double)beta1, (double)t), bc2 = 1.0 - pow((double)beta2, (double)t);
+        for (int i = 0; i < 6; i++) {
+            float g = g7[i];
+            if (wd != 0.f) g = g + wd * dof[i];
+            const float m = beta1 * state[i] + (1.f - beta1) * g;
+            const float v = beta2 * state[6 + i] + (1.f - beta2) * g * g;
+            state[i] = m; state[6 + i] = v;
+            const float step_size = (float)((double)lr / bc1);
+            const float denom = (float)((double)sqrtf(v) / sqrt(bc2)) + eps;
+            dof[i] = dof[i] - step_size * (m / denom);
+        }
+        state[12] = (float)t;
+    }
+    if (mvp_out) {
+        __syncthreads();                                   // (thread 0's parameter update is visible to itself; the others wait)
+        ehb_compose_block(dof, K, lp, n, H, W, mvp_out, sh.M, sh.Tc, threadIdx.x, blockDim.x);
+    }
+}
+
 __global__ void ehb_k_adam(float* __restrict__ dof, float* __restrict__ g7, float* __restrict__ state, float lr,
                            float beta1, float beta2, float eps, float wd, float* __restrict__ hist, int hist_cap,
                            const EhbComm cm, int recv, const float* __restrict__ K, const float* __restrict__ lp, int n,
@@ -223,49 +288,28 @@ __global__ void ehb_k_adam(float* __restrict__ dof, float* __restrict__ g7, floa
 {
     ehb_pose_pdl_enter();
     if (blockIdx.x != 0) return;
-    __shared__ float s_M[16], s_Tc[16];
-    if (recv) {
-        // second half of the fused all-reduce: wait until every rank's message of this step is in the own mailbox, add
-        // them in rank order (bit-identical sums on every rank), leave the sum in g7
-        __shared__ float s_val[EHB_COMM_MAX][7];
-        const int t = threadIdx.x;
-        const unsigned int step = *cm.step + 1u;
-        if (t < cm.world) {
-            volatile unsigned int* src = cm.peer[cm.rank] + ((size_t)(step & 1u) * EHB_COMM_MAX + t) * 8;
-            while (src[7] != step) { }
-            __threadfence_system();
-            for (int i = 0; i < 7; i++) s_val[t][i] = __uint_as_float(src[i]);
-        }
-        __syncthreads();
-        if (t < 7) {
-            float acc = 0.f;
-            for (int r = 0; r < cm.world; r++) acc += s_val[r][t];
-            g7[t] = acc;
-        }
-        if (t == 0) *cm.step = step;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-    const int t = (int)state[12] + 1;
-    if (hist && t - 1 < hist_cap)
-        for (int i = 0; i < 6; i++) hist[(size_t)(t - 1) * 6 + i] = dof[i];
-    const double bc1 = 1.0 - pow((double)beta1, (double)t), bc2 = 1.0 - pow((double)beta2, (double)t);
-    for (int i = 0; i < 6; i++) {
-        float g = g7[i];
-        if (wd != 0.f) g = g + wd * dof[i];
-        const float m = beta1 * state[i] + (1.f - beta1) * g;
-        const float v = beta2 * state[6 + i] + (1.f - beta2) * g * g;
-        state[i] = m; state[6 + i] = v;
-        const float step_size = (float)((double)lr / bc1);
-        const float denom = (float)((double)sqrtf(v) / sqrt(bc2)) + eps;
-        dof[i] = dof[i] - step_size * (m / denom);
-    }
-    state[12] = (float)t;
-    }
-    if (mvp_out) {
-        __syncthreads();                                   // (thread 0's parameter update is visible to itself; the others wait)
-        ehb_compose_block(dof, K, lp, n, H, W, mvp_out, s_M, s_Tc, threadIdx.x, blockDim.x);
-    }
+    __shared__ EhbAdamShared sh;
+    ehb_adam_block(sh, dof, g7, state, lr, beta1, beta2, eps, wd, hist, hist_cap, cm, recv, K, lp, n, H, W, mvp_out);
+}
+
+// The tail of a solver iteration in ONE launch: pose chain (d loss/d mvp -> the 7 floats, + the mailbox send), then -- in the
+// same block, behind a barrier -- the exchange's receive, Adam on `adam_dof` and optionally the next iteration's matrices.
+// A launch less on the critical path of every iteration (3 us of a 75 us iteration at 640x480).
+__global__ void __launch_bounds__(256) ehb_k_pose_adam(const float* dof /* may alias adam_dof */, const float* __restrict__ K,
+                                                       const float* __restrict__ lp, const double* __restrict__ gmvp,
+                                                       const double* __restrict__ loss, int B, int L, int H, int W,
+                                                       double grad_scale, double loss_scale, float* __restrict__ out7,
+                                                       const EhbComm cm, int exch, float* adam_dof,
+                                                       float* __restrict__ state, float lr, float beta1, float beta2, float eps,
+                                                       float wd, float* __restrict__ hist, int hist_cap,
+                                                       float* __restrict__ mvp_out)
+{
+    ehb_pose_pdl_enter();
+    __shared__ EhbPoseShared shp;
+    __shared__ EhbAdamShared sha;
+    ehb_pose_backward_block(shp, dof, K, lp, gmvp, loss, B, L, H, W, grad_scale, loss_scale, out7, cm, exch);
+    __syncthreads();                                       // out7 as written by this block; dof read before Adam changes it
+    ehb_adam_block(sha, adam_dof, out7, state, lr, beta1, beta2, eps, wd, hist, hist_cap, cm, exch, K, lp, B * L, H, W, mvp_out);
 }
 
 __global__ void ehb_k_allreduce7(const EhbComm cm, float* __restrict__ g7)

@@ -93,8 +93,15 @@ class PoseSolver:
                              out=(self.masks, self.loss_b, self.g_mvp))
         # fused kernel scaled by 1/B_local; rescale so that the sum over ranks is the global mean's gradient
         fusedx = self.world > 1 and self._peer      # the 7-float exchange rides inside pose_backward (send) and adam (recv)
+        gs, ls = self.B / self.B_global, 1.0 / self.B_global
+        if self._fuse_compose and (self.world == 1 or self._peer):
+            # the tail of the iteration in one launch: pose chain (+ send), (recv +) Adam, the next iteration's matrices
+            c.pose_backward_adam(self.dof, self.K, self.link_poses, self.g_mvp, self.loss_b, self.H, self.W, self.state, self.lr,
+                                 self.betas, self.eps, self.wd, grad_scale=gs, loss_scale=ls, out=self.g7, exchange=fusedx,
+                                 hist=self.hist, mvp_next=self.mvp)
+            return
         c.pose_backward(self.dof, self.K, self.link_poses, self.g_mvp, self.loss_b, self.H, self.W,
-                        grad_scale=self.B / self.B_global, loss_scale=1.0 / self.B_global, out=self.g7, send=fusedx)
+                        grad_scale=gs, loss_scale=ls, out=self.g7, send=fusedx)
         if self.world > 1 and not self._peer:
             torch.distributed.all_reduce(self.g7, group=self.group)
         # Adam, and in the same launch the matrices of the next iteration from the updated parameters

@@ -274,6 +274,16 @@ EHB_API int ehb_adam_step_compose(ehb_ctx_t ctx, float* dof_dev, float* g7_dev, 
                                   const float* K_dev, const float* link_poses_dev, int B, int L, int H, int W, float* mvp_dev,
                                   void* stream);
 
+/* The tail of a solver iteration in ONE launch (trainer/rbsolver.py:29-43: loss.backward() through se3_exp_map, the DDP
+ * all-reduce, optimizer.step()): ehb_pose_backward's out7, with exchange != 0 its all-reduce over the connected ranks, Adam on
+ * adam_dof_dev (may be dof_dev itself) and, with mvp_next_dev != NULL, the matrices of the next iteration from the updated
+ * parameters.  Same results as ehb_pose_backward[_send] followed by ehb_adam_step[_recv | _compose]. */
+EHB_API int ehb_pose_backward_adam(ehb_ctx_t ctx, const float* dof_dev, const float* K_dev, const float* link_poses_dev,
+                                   const double* g_mvp_dev, const double* loss_dev, int B, int L, int H, int W,
+                                   double grad_scale, double loss_scale, float* out7_dev, int exchange, float* adam_dof_dev,
+                                   float* state_dev, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                   float* hist_dev, int hist_cap, float* mvp_next_dev, void* stream);
+
 /* Number of kernels this library has launched on the context since creation (for launch accounting). */
 EHB_API long long ehb_launch_count(ehb_ctx_t ctx);
 

@@ -55,6 +55,39 @@ def test_adam_step_matches_torch(gpu_ctx):
     assert state[12].item() == 5
 
 
+def test_pose_backward_adam_in_one_launch_equals_the_two_launches(gpu_ctx):
+    """ehb_pose_backward_adam = ehb_pose_backward + ehb_adam_step_compose, bit for bit (same block arithmetic)."""
+    g = torch.Generator(device="cpu").manual_seed(3)
+    B, L, H, W = 5, 7, 120, 160
+    K = torch.tensor([[150.0, 0, 80.0], [0, 151.0, 60.0], [0, 0, 1]], device="cuda")
+    lp = torch.eye(4).repeat(B, L, 1, 1) + 0.1 * torch.randn(B, L, 4, 4, generator=g)
+    lp[..., 3, :] = torch.tensor([0.0, 0, 0, 1]); lp = lp.cuda().contiguous()
+    res = {}
+    for fused in (False, True):
+        dof = torch.tensor([0.1, -0.2, 0.7, 0.3, -1.0, 0.5], device="cuda")
+        state = torch.zeros(13, device="cuda"); hist = torch.zeros(8, 6, device="cuda")
+        mvp = torch.zeros(B, L, 4, 4, device="cuda")
+        gg = torch.Generator(device="cpu").manual_seed(4)
+        outs = []
+        for it in range(3):
+            g_mvp = torch.randn(B, L, 4, 4, generator=gg, dtype=torch.float64).cuda()
+            loss = torch.rand(B, generator=gg, dtype=torch.float64).cuda()
+            if fused:
+                o7 = gpu_ctx.pose_backward_adam(dof, K, lp, g_mvp, loss, H, W, state, 3e-3, weight_decay=5e-4, hist=hist, mvp_next=mvp)
+            else:
+                o7 = gpu_ctx.pose_backward(dof, K, lp, g_mvp, loss, H, W)
+                gpu_ctx.adam_step(dof, o7, state, 3e-3, weight_decay=5e-4, hist=hist, compose=(K, lp, H, W, mvp))
+            outs.append(o7.clone())
+        res[fused] = (torch.stack(outs), dof.clone(), state.clone(), hist.clone(), mvp.clone())
+    for a, b in zip(res[False], res[True]):
+        assert torch.equal(a, b)
+    assert res[True][2][12].item() == 3 and res[True][4].abs().sum() > 0
+    # Adam on a copy of the parameters (the bench's scratch): the pose parameters stay
+    dof = torch.tensor([0.1, -0.2, 0.7, 0.3, -1.0, 0.5], device="cuda"); scratch = dof.clone(); keep = dof.clone()
+    gpu_ctx.pose_backward_adam(dof, K, lp, g_mvp, loss, H, W, torch.zeros(13, device="cuda"), 3e-3, adam_dof=scratch)
+    assert torch.equal(dof, keep) and not torch.equal(scratch, keep)
+
+
 def test_rbsolver_fused_vs_loop_vs_oracle():
     from easyhec_b200.rb_solver import RBSolver, compose_link_mvp
     from easyhec_b200.se3 import dof_to_matrix
