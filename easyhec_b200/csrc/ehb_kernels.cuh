@@ -39,7 +39,7 @@ struct EhbPlane {            // depth plane of one (item, link): pixels [x0, x0+
     long long boff;          // first 64-bit word of the plane's coverage bits in the bit pool (h rows of ceil(w / 64) words)
 };
 
-struct EhbUnit { uint32_t rec; unsigned short dx0, dy0; };   // a 64 x 32 pixel window of a deferred triangle's bbox
+struct __align__(8) EhbUnit { uint32_t rec; unsigned short dx0, dy0; };   // a 64 x 32 pixel window of a deferred triangle's bbox
 
 struct __align__(128) EhbCounters {
     // line 0: pass bookkeeping (one writer at a time, or a few hundred atomics per pass)
