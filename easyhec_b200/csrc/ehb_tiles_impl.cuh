@@ -348,18 +348,41 @@ __device__ __forceinline__ void ehb_tile_backward(const EhbRobot& rb, const EhbP
                 }
             }
         }
-        // everything of a warp that belongs to one link: reduced by shuffles, then one shared-memory atomic per component
+        // everything of a warp that belongs to one link: the 12 components are reduced TOGETHER (a reduce-scatter: every
+        // step halves the values a lane holds and doubles the lanes they are summed over -- 16 exchanges instead of the 60 of
+        // twelve butterflies), component c ends up on lane 2c, and those twelve lanes issue their shared-memory atomics at
+        // once (twelve one after the other from lane 0, each a compare-and-swap loop, were half of this phase)
         unsigned todo = __ballot_sync(0xffffffffu, key >= 0);
         while (todo) {
             const int leader = __ffs(todo) - 1;
             const int k0 = __shfl_sync(0xffffffffu, key, leader);
             const bool mine = key == k0;
             todo &= ~__ballot_sync(0xffffffffu, mine);
+            double v8[8], v4[4], v2[2], v1;
+            const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
 #pragma unroll
-            for (int k = 0; k < 12; k++) {
-                const double v = ehb_warp_sum(mine ? acc[k] : 0.0);
-                if (lane == 0 && v != 0.0) atomicAdd(&sm.gacc[k0][k], v);
+            for (int j = 0; j < 8; j++) {              // component index = 8 * b4 + j
+                const double lo = mine ? acc[j] : 0.0, hi = (mine && j + 8 < 12) ? acc[(j + 8) % 12] : 0.0;
+                const double keep = b4 ? hi : lo, give = b4 ? lo : hi;
+                v8[j] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
             }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {              // ... + 4 * b3 + j
+                const double keep = b3 ? v8[j + 4] : v8[j], give = b3 ? v8[j] : v8[j + 4];
+                v4[j] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; j++) {              // ... + 2 * b2 + j
+                const double keep = b2 ? v4[j + 2] : v4[j], give = b2 ? v4[j] : v4[j + 2];
+                v2[j] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+            }
+            {                                           // ... + b1
+                const double keep = b1 ? v2[1] : v2[0], give = b1 ? v2[0] : v2[1];
+                v1 = keep + __shfl_xor_sync(0xffffffffu, give, 2);
+            }
+            v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+            const int comp = lane >> 1;                // = 8 b4 + 4 b3 + 2 b2 + b1
+            if ((lane & 1) == 0 && comp < 12 && v1 != 0.0) atomicAdd(&sm.gacc[k0][comp], v1);
         }
     }
     __syncthreads();

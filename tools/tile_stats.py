@@ -1,5 +1,5 @@
 """Developer tool: per-phase cycle counters of ehb_k_tiles (EHB_STATS build) on the bench scene.
-   EHB_LIB=easyhec_b200/libehb_stats.so python tools/tile_stats.py [headline|inview]"""
+   EHB_LIB=easyhec_b200/libehb_stats.so python tools/tile_stats.py [headline|inview] [H W]"""
 import importlib.util
 import os
 import sys
@@ -12,7 +12,9 @@ spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench
 b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
 from easyhec_b200._lib import Context  # noqa: E402
 
-wl = b.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "headline"]
+wl = dict(b.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "headline"])
+if len(sys.argv) > 3:
+    wl["H"], wl["W"] = int(sys.argv[2]), int(sys.argv[3])
 H, W, B = wl["H"], wl["W"], wl["B"]
 s = b.build_sets(wl, 0, 1)[0]
 ctx = Context("cuda:0")
