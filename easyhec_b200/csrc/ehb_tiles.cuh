@@ -57,16 +57,20 @@ static_assert(EHB_MSZ * 4 >= EHB_T * EHB_T * 4, "the staging tile of the TMA sto
 
 #define EHB_TTHREADS 128
 #define EHB_TMIN_BLOCKS 7
+#define EHB_TMB 1                        // mask buffers: links whose masks are built together (ehb_tile_masks)
 #define EHB_TNS t128
 #include "ehb_tiles_impl.cuh"
 #undef EHB_TTHREADS
 #undef EHB_TMIN_BLOCKS
+#undef EHB_TMB
 #undef EHB_TNS
 
 #define EHB_TTHREADS 256
 #define EHB_TMIN_BLOCKS 3
+#define EHB_TMB 6
 #define EHB_TNS t256
 #include "ehb_tiles_impl.cuh"
 #undef EHB_TTHREADS
 #undef EHB_TMIN_BLOCKS
+#undef EHB_TMB
 #undef EHB_TNS

@@ -24,7 +24,7 @@ struct EhbSlot {                         // one resident link of the tile
 };
 
 struct __align__(128) EhbTileSm {
-    float mbuf[EHB_MSZ];                         // antialiased mask of one link; doubles as the 32 x 32 staging tile of the TMA store
+    float mbuf[EHB_TMB][EHB_MSZ];                // antialiased masks of EHB_TMB links at a time; [0] doubles as the 32 x 32 staging tile of the TMA store
     float S[EHB_MSZ];                            // running sum of the link masks, then g = dL/dsum
     unsigned long long cov[EHB_RL][36];          // row coverage masks of the round's windows (rows 0..34, [35] = 0)
     float alpha[EHB_CAPS];
@@ -242,56 +242,55 @@ __device__ __forceinline__ void ehb_tile_round(const EhbRobot& rb, const EhbPara
     EHB_STAT_ADD(7, clock64() - tC);
 }
 
-// D: link by link (link order, rb_solver.py:68): the link's antialiased mask of the out region in the mask buffer, then
-// the running sum S = m_first, S = S + m_l.
+// D: the antialiased masks of the round's links, EHB_TMB links at a time in as many mask buffers, then the running sum in
+// link order (rb_solver.py:68): S = m_first, S = S + m_l.  A pixel receives at most one contribution of each kind and the
+// reference adds them in the order pair(p,p+x), pair(p,p+y), pair(p-x,p), pair(p-y,p): four sweeps, one kind each, over the
+// pairs of ALL links of the group (receiver = p0 when alpha > 0, p1 otherwise; contribution alpha * (colour[p1] - colour[p0]))
+// -- the seven block barriers of the phase are paid once per group instead of once per link (2,600 cycles per link).
 template <int OW>
 __device__ __forceinline__ void ehb_tile_masks(const EhbParams& p, EhbTileSm& sm, const EhbTileCtx& c, const EhbPairs& pr, int take,
                                                int nPairsRound, bool first)
 {
     EHB_STAT_T(tD);
     const int tid = c.tid, lane = c.lane, warp = c.warp, hlo = 1;
-    for (int s = 0; s < take; s++, first = false) {
-        const int pb = sm.slot[s].pairBase, pn = max(0, min(sm.slot[s].nPairs, nPairsRound - pb));
-        // colour = coverage as floats: the warps take rows, lane = column (+ columns 32 .. 35 by the first lanes); a link
-        // without pairs in this window goes straight into the sum
-        float* dst = pn > 0 ? sm.mbuf : sm.S;
-        for (int qy = warp; qy < OW; qy += EHB_TWARPS) {
-            const unsigned long long cw = sm.cov[s][hlo + qy] >> hlo;
-            const float a0 = ((cw >> lane) & 1ull) ? 1.f : 0.f;
-            const float a1 = (lane < EHB_MW - 32 && 32 + lane < OW && (((cw >> 32) >> lane) & 1ull)) ? 1.f : 0.f;
-            float* row = dst + qy * EHB_MW;
-            if (pn > 0 || first) {
-                row[lane] = a0;
-                if (lane < EHB_MW - 32) row[32 + lane] = a1;
-            } else {
-                row[lane] = row[lane] + a0;
-                if (lane < EHB_MW - 32) row[32 + lane] = row[32 + lane] + a1;
-            }
+    for (int s0 = 0; s0 < take; s0 += EHB_TMB, first = false) {
+        const int ns = min(EHB_TMB, take - s0);
+        // colour = coverage as floats: the warps take (link, row)s, lane = column (+ columns 32 .. 35 by the first lanes)
+        for (int k = warp; k < ns * OW; k += EHB_TWARPS) {
+            const int sl = k / OW, qy = k - sl * OW;
+            const unsigned long long cw = sm.cov[s0 + sl][hlo + qy] >> hlo;
+            float* row = sm.mbuf[sl] + qy * EHB_MW;
+            row[lane] = ((cw >> lane) & 1ull) ? 1.f : 0.f;
+            if (lane < EHB_MW - 32) row[32 + lane] = (32 + lane < OW && (((cw >> 32) >> lane) & 1ull)) ? 1.f : 0.f;
         }
-        if (pn == 0) { __syncthreads(); continue; }
-        // the pair contributions.  A pixel receives at most one contribution of each kind and the reference adds them in
-        // the order pair(p,p+x), pair(p,p+y), pair(p-x,p), pair(p-y,p): four sweeps over the link's pairs, one kind each
-        // (receiver = p0 when alpha > 0, p1 otherwise; the contribution is alpha * (colour[p1] - colour[p0])).
+        const int lo = sm.slot[s0].pairBase;
+        const int hi = min(sm.slot[s0 + ns - 1].pairBase + sm.slot[s0 + ns - 1].nPairs, nPairsRound);
+        if (hi > lo) {
 #pragma unroll 1
-        for (int kind = 0; kind < 4; kind++) {
-            __syncthreads();
-            for (int i = pb + tid; i < pb + pn; i += EHB_TTHREADS) {
-                const uint32_t pk = pr.pk[i];
-                const float al = pr.alpha[i];
-                const int d = (pk >> 11) & 1;
-                const bool pos = al > 0.f;
-                if (al == 0.f || d != (kind & 1) || pos != (kind < 2)) continue;
-                const int idx = pk & 2047, side = (pk >> 13) & 1;
-                const int ridx = pos ? idx : idx + (d ? EHB_RS : 1);
-                const int ry = ridx / EHB_RS, rxw = ridx - ry * EHB_RS;
-                const int qy = ry - hlo, qx = rxw - hlo;
-                if (qy < 0 || qx < 0 || qy >= OW || qx >= OW) continue;
-                const float delta = side ? 1.f : -1.f;   // colour[p1] - colour[p0]: p1 is the covered one when side = 1
-                sm.mbuf[qy * EHB_MW + qx] += al * delta;
+            for (int kind = 0; kind < 4; kind++) {
+                __syncthreads();
+                for (int i = lo + tid; i < hi; i += EHB_TTHREADS) {
+                    const uint32_t pk = pr.pk[i];
+                    const float al = pr.alpha[i];
+                    const int d = (pk >> 11) & 1;
+                    const bool pos = al > 0.f;
+                    if (al == 0.f || d != (kind & 1) || pos != (kind < 2)) continue;
+                    const int idx = pk & 2047, side = (pk >> 13) & 1;
+                    const int ridx = pos ? idx : idx + (d ? EHB_RS : 1);
+                    const int ry = ridx / EHB_RS, rxw = ridx - ry * EHB_RS;
+                    const int qy = ry - hlo, qx = rxw - hlo;
+                    if (qy < 0 || qx < 0 || qy >= OW || qx >= OW) continue;
+                    const float delta = side ? 1.f : -1.f;   // colour[p1] - colour[p0]: p1 is the covered one when side = 1
+                    sm.mbuf[(int)pr.pslot[i] - s0][qy * EHB_MW + qx] += al * delta;
+                }
             }
         }
         __syncthreads();
-        for (int i = tid; i < OW * EHB_MW; i += EHB_TTHREADS) sm.S[i] = first ? sm.mbuf[i] : sm.S[i] + sm.mbuf[i];
+        for (int i = tid; i < OW * EHB_MW; i += EHB_TTHREADS) {
+            float acc = first ? sm.mbuf[0][i] : sm.S[i] + sm.mbuf[0][i];
+            for (int sl = 1; sl < ns; sl++) acc = acc + sm.mbuf[sl][i];
+            sm.S[i] = acc;
+        }
         __syncthreads();
     }
     EHB_STAT_ADD(8, clock64() - tD);
@@ -415,7 +414,7 @@ __global__ void __launch_bounds__(EHB_TTHREADS, EHB_TMIN_BLOCKS) ehb_k_tiles(con
     const unsigned nHeavy = p.ctr->nTiles, nEntries = nHeavy + p.ctr->nLight;
     const uint32_t linkMask = p.L >= 32 ? 0xFFFFFFFFu : ((1u << p.L) - 1u);
     const bool tma = NEEDAA && p.masks != nullptr && p.useTma;
-    float* stage = sm.mbuf;
+    float* stage = sm.mbuf[0];
     bool storePending = false;                           // thread 0: a TMA store may still be reading the staging tile
     if (tid == 0) sm.slab = -1;
 
