@@ -57,7 +57,10 @@ static_assert(EHB_MSZ * 4 >= EHB_T * EHB_T * 4, "the staging tile of the TMA sto
 
 #define EHB_TTHREADS 128
 #define EHB_TMIN_BLOCKS 7
-#define EHB_TMB 1                        // mask buffers: links whose masks are built together (ehb_tile_masks)
+#ifndef EHB_TMB128
+#define EHB_TMB128 1
+#endif
+#define EHB_TMB EHB_TMB128                // mask buffers: links whose masks are built together (ehb_tile_masks)
 #define EHB_TNS t128
 #include "ehb_tiles_impl.cuh"
 #undef EHB_TTHREADS
