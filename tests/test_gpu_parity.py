@@ -83,7 +83,8 @@ def test_fused_views_match_oracle(gpu_ctx, B, H, W, links):
 
 
 def test_fused_more_links_than_resident_planes(gpu_ctx):
-    """9 overlapping links > the 6 planes a CTA keeps resident: the multi-round path must give the same answer."""
+    """9 overlapping links in one tile: more than the 8 links of a k_tiles round and more than the 6 mask buffers of a group
+    (256-thread variant) -- two rounds, groups of 6 + 2 and 1: the same answer as the oracle's link-by-link sum."""
     H, W, B = 96, 128, 2
     links = synthetic_links([300] * 9, radius=0.05, length=0.2, seed=2)
     rng = np.random.RandomState(0)
