@@ -1,12 +1,13 @@
-"""Pose optimisation loop on the device: RBSolver's Adam iteration as one CUDA graph.
+"""Pose optimisation loop on the device: RBSolver's Adam iteration as a CUDA graph.
 
 The reference runs one Adam step per "epoch": zero_grad -> RBSolver.forward (B x L render_mask calls) ->
 backward -> Adam (easyhec/trainer/rbsolver.py:29-43, easyhec/solver/build.py:12-29: lr 3e-3, weight decay 5e-4
 as L2 on ``dof``).  Here one iteration is a fixed sequence of kernels
 
-    [front, raster, raster_big, tiles] -> pose_backward -> (all-reduce 7 floats) -> adam + pose_compose of the next iteration
+    [front, raster, raster_big, tiles] -> pose_adam: pose chain, (all-reduce of 7 floats), Adam, pose_compose of the next iteration
 
-captured once into a CUDA graph and replayed; nothing returns to the host inside the loop.  When views are sharded
+(five launches; with NCCL instead of the peer mailboxes the last one splits around the collective) captured into CUDA graphs
+of 1 and 8 iterations and replayed; nothing returns to the host inside the loop.  When views are sharded
 over ranks (``torch.distributed``), each rank renders its own views and the only exchange is the 7-float
 all-reduce of (d loss/d dof, loss) -- the collective DDP performs for the reference (trainer/base.py:349).
 """

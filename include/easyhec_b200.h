@@ -67,8 +67,9 @@ EHB_API int ehb_ctx_destroy(ehb_ctx_t ctx);
 EHB_API int ehb_ctx_reserve(ehb_ctx_t ctx, int n_items, int n_links, int max_faces, int H, int W);
 /* Tie rule for a pixel centre lying exactly on a snapped edge: 0 (default) or 1 (mirror); see DESIGN.md. */
 EHB_API int ehb_ctx_set_fill_rule(ehb_ctx_t ctx, int rule);
-/* A call's items (views / renders) are split over n (1..4, default 2) independent pipelines that run concurrently on
- * internal streams forked from, and joined back into, the caller's stream (CUDA-graph capturable). */
+/* A call's items (views / renders) are split over n (1..4) independent pipelines that run concurrently on internal streams
+ * forked from, and joined back into, the caller's stream (CUDA-graph capturable).  Default: 3 for calls of more than 16
+ * items, 1 otherwise (measured); setting n makes every call of >= 2 items use min(n, items) pipelines. */
 EHB_API int ehb_ctx_set_pipelines(ehb_ctx_t ctx, int n);
 /* Bytes of depth-plane pool a pipeline may reserve up front (default 8e9).  While the worst case of a call
  * (items x links x H x W x 8 B) fits, the pool cannot overflow; beyond it the pool starts at 2 screens per item and
