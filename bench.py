@@ -296,7 +296,7 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
-def timed_regions(run, steps, barrier, torch, min_ms=MIN_TIMED_MS, max_repeats=400):
+def timed_regions(run, steps, barrier, torch, min_ms=MIN_TIMED_MS, max_repeats=400, agree=None):
     """Times EXACTLY `steps` steps (run(steps, first_step_index)) between two CUDA events, bracketed by barrier +
     synchronize on both sides; the region is repeated until `min_ms` of device time has been measured (a 20-step region
     of a 0.1 ms step is 2 ms: one region is noise).  Returns (median ms per region, all region times)."""
@@ -311,7 +311,10 @@ def timed_regions(run, steps, barrier, torch, min_ms=MIN_TIMED_MS, max_repeats=4
         barrier()
         regions.append(e0.elapsed_time(e1))
         k0 += steps
-        if sum(regions) >= min_ms or len(regions) >= max_repeats:
+        done = sum(regions) >= min_ms or len(regions) >= max_repeats
+        if agree is not None:      # several ranks: every rank must run the same number of regions (each one ends in a barrier)
+            done = agree(done)
+        if done:
             break
     return float(np.median(regions)), regions
 
@@ -403,6 +406,13 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def agree(done):               # a region loop ends when EVERY rank has measured enough
+        if world == 1:
+            return done
+        t = torch.tensor([1.0 if done else 0.0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item() >= 1.0)
 
     for k in range(max(args.warmup, 3)):
         step(k)
@@ -503,7 +513,7 @@ def run_b200(args):
     barrier()
     sampler.start()
     l0 = ctx.launch_count()
-    ms_serial, regions_serial = timed_regions(run_serial, args.steps, barrier, torch)
+    ms_serial, regions_serial = timed_regions(run_serial, args.steps, barrier, torch, agree=agree)
     launches = (ctx.launch_count() - l0) // max(len(regions_serial), 1)
     if graphs is not None:
         launches = launches_per_step * args.steps
@@ -512,7 +522,7 @@ def run_b200(args):
         for k in range(2):
             run_inflight(G, 0)
         l0 = ctx.launch_count()
-        ms, regions = timed_regions(run_inflight, args.steps, barrier, torch)
+        ms, regions = timed_regions(run_inflight, args.steps, barrier, torch, agree=agree)
         launches = (ctx.launch_count() - l0) // max(len(regions), 1)
         if slot_graph is not None:
             launches = int(round(slot_launches * (args.steps - args.steps % G))) + (launches if args.steps % G else 0)
@@ -795,7 +805,14 @@ def run_explore(args):
     sampler.start()
     l0 = ctx.launch_count()
     steps = min(args.steps, 50)
-    ms, regions = timed_regions(lambda n, k0: [step(k0 + k) for k in range(n)], steps, barrier, torch)
+    def agree(done):               # every rank runs the same number of timed regions
+        if world == 1:
+            return done
+        t = torch.tensor([1.0 if done else 0.0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item() >= 1.0)
+
+    ms, regions = timed_regions(lambda n, k0: [step(k0 + k) for k in range(n)], steps, barrier, torch, agree=agree)
     clocks = sampler.stop()
     launches = (ctx.launch_count() - l0) // max(len(regions), 1)
     if world > 1:
