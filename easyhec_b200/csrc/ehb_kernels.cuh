@@ -56,8 +56,8 @@ struct __align__(128) EhbCounters {
     unsigned long long bitCursor;   // words of the bit pool in use
     unsigned long long prevCursor, prevBitCursor;   // what the previous pass on this scratch used: the part k_front clears
     unsigned int pad0[14];
-    // line 1: set by the last table CTA of k_front when the planes of the pass are allocated and the list counters are
-    // reset; the CTAs of the same launch that need the planes wait for it (k_raster resets it)
+    // line 1: set by the last table CTA of k_front when every plane's bounding box is written and the list counters are
+    // reset; the tile-list CTAs of the same launch wait for it (k_raster resets it)
     unsigned int tableReady;
     unsigned int pad1[31];
     unsigned int pad2[32];
@@ -332,7 +332,7 @@ __device__ __forceinline__ void ehb_stream_empty_tile(const EhbParams& p, int it
 //   (T) table     one warp per depth plane: conservative screen bounding box of the link from the projected corners of its
 //                 (up to 32) object-space chunk AABBs -- 256 point transforms instead of a reduction over all vertices.  The
 //                 last table CTA to finish (atomic ticket) allocates the planes of the pass in the pool by a block-wide
-//                 prefix sum (deterministic), resets the list counters and raises ctr->tableReady.
+//                 prefix sum (deterministic); before that it resets the list counters and raises ctr->tableReady.
 //   (V) vertices  one thread per (item, vertex): transform and snap ONCE (a vertex is shared by ~6 triangles), keep the
 //                 clip-space and snapped positions (a few MB, L2-resident)
 //   (B) batches   frustum test of every 32-triangle batch's object-space AABB (8 corners, one per lane): the batches that
@@ -439,7 +439,11 @@ __global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRo
             p.ctr->q[threadIdx.x].nBigRec = 0u; p.ctr->q[threadIdx.x].nUnits = 0u; p.ctr->q[threadIdx.x].nBatchBlk = 0u;
             p.ctr->q[threadIdx.x].take = 0u;
         }
+        __threadfence();
         __syncthreads();
+        // the tile-list CTAs need the bounding boxes and the reset counters, not the allocation that follows (only the kernels
+        // after this launch read it): they are released now, a prefix sum and two L2 round trips earlier
+        if (threadIdx.x == 0) asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(&p.ctr->tableReady), "r"(1u) : "memory");
         const int warp = threadIdx.x >> 5;
         for (int i0 = 0; i0 < p.items * p.Lp; i0 += blockDim.x) {      // block-wide exclusive prefix sums: plane areas, bit words
             const int i = i0 + threadIdx.x;
@@ -474,8 +478,6 @@ __global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRo
         if (threadIdx.x == 0) {
             p.ctr->planeCursor = min(s_base, p.poolCap);
             p.ctr->bitCursor = min(s_baseb, p.bitCap);
-            __threadfence();
-            asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(&p.ctr->tableReady), "r"(1u) : "memory");
             EHB_MARK(p, 6);
             EHB_TL_STOP(p, 0, blockIdx.x, tl0);
         }
