@@ -370,6 +370,15 @@ __global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRo
     // ---------------------------------------------------------------- (T) table
     if (blk < tableBlocks) {
         EHB_MARK(p, 4);
+        // the first table CTA resets the counters the tile-list CTAs and the rasterizer add to (nobody touches them before the
+        // table is ready, the previous pass is complete): off the critical path of the last CTA's hand-off
+        if (blk == 0) {
+            if (threadIdx.x == 0) { p.ctr->nTiles = 0u; p.ctr->nLight = 0u; p.ctr->nEmpty = 0u; p.ctr->workCursor = 0u; p.ctr->slabCursor = 0u; }
+            if (threadIdx.x < EHB_NQ) {
+                p.ctr->q[threadIdx.x].nBigRec = 0u; p.ctr->q[threadIdx.x].nUnits = 0u; p.ctr->q[threadIdx.x].nBatchBlk = 0u;
+                p.ctr->q[threadIdx.x].take = 0u;
+            }
+        }
         const int wid = (blk * (int)blockDim.x + (int)threadIdx.x) >> 5;
         // outputs that the later kernels accumulate into
         for (int i = blk * blockDim.x + threadIdx.x; i < p.items; i += tableBlocks * blockDim.x)
@@ -430,20 +439,14 @@ __global__ void __launch_bounds__(256) ehb_k_front(const __grid_constant__ EhbRo
         if (!s_last) { if (threadIdx.x == 0) EHB_TL_STOP(p, 0, blockIdx.x, tl0); return; }
         __threadfence();
         EHB_MARK(p, 5);
+        // the tile-list CTAs need the bounding boxes and the reset counters (every table CTA fenced its writes before its
+        // ticket), not the allocation that follows (only the kernels after this launch read it): they are released now
         if (threadIdx.x == 0) {
+            asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(&p.ctr->tableReady), "r"(1u) : "memory");
             s_base = 0ull; s_baseb = 0ull;
             p.ctr->vertexDone = 0u;
-            p.ctr->nTiles = 0u; p.ctr->nLight = 0u; p.ctr->nEmpty = 0u; p.ctr->workCursor = 0u; p.ctr->slabCursor = 0u;
         }
-        if (threadIdx.x < EHB_NQ) {
-            p.ctr->q[threadIdx.x].nBigRec = 0u; p.ctr->q[threadIdx.x].nUnits = 0u; p.ctr->q[threadIdx.x].nBatchBlk = 0u;
-            p.ctr->q[threadIdx.x].take = 0u;
-        }
-        __threadfence();
         __syncthreads();
-        // the tile-list CTAs need the bounding boxes and the reset counters, not the allocation that follows (only the kernels
-        // after this launch read it): they are released now, a prefix sum and two L2 round trips earlier
-        if (threadIdx.x == 0) asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(&p.ctr->tableReady), "r"(1u) : "memory");
         const int warp = threadIdx.x >> 5;
         for (int i0 = 0; i0 < p.items * p.Lp; i0 += blockDim.x) {      // block-wide exclusive prefix sums: plane areas, bit words
             const int i = i0 + threadIdx.x;
