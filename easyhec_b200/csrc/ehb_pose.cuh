@@ -146,6 +146,7 @@ struct EhbPoseShared {
     double S[8][17];
     double T[17];
     double G[12];
+    double dT[6][12];        // d exp_map(dof)[j] / d dof[i]: depends on dof only, computed beside the reduction
 };
 __device__ __forceinline__ void ehb_pose_backward_block(EhbPoseShared& sh, const float* __restrict__ dof, const float* __restrict__ K,
                                                         const float* __restrict__ lp, const double* __restrict__ gmvp,
@@ -154,6 +155,14 @@ __device__ __forceinline__ void ehb_pose_backward_block(EhbPoseShared& sh, const
                                                         const EhbComm& cm, int send)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // the six dual-number evaluations of the exp map need dof only: the last warp does them while the others wait for the
+    // gradient's loads (they were 1 - 2 us at the end of the chain)
+    if (warp == 7 && lane < 6) {
+        EhbDual d[6], t[12];
+        for (int j = 0; j < 6; j++) d[j] = {(double)dof[j], j == lane ? 1.0 : 0.0};
+        ehb_se3_exp<EhbDual>(d, t, 1e-4);
+        for (int j = 0; j < 12; j++) sh.dT[lane][j] = t[j].d;
+    }
     // S = sum_{b,l} g_mvp[b,l] @ lp[b,l]^T ;  S[16] = sum_b loss_b
     double acc[17];
     for (int i = 0; i < 17; i++) acc[i] = 0.0;
@@ -191,11 +200,8 @@ __device__ __forceinline__ void ehb_pose_backward_block(EhbPoseShared& sh, const
     }
     __syncthreads();
     if (tid < 6) {
-        EhbDual d[6], t[12];
-        for (int j = 0; j < 6; j++) d[j] = {(double)dof[j], j == tid ? 1.0 : 0.0};
-        ehb_se3_exp<EhbDual>(d, t, 1e-4);
         double s = 0.0;
-        for (int j = 0; j < 12; j++) s += sh.G[j] * t[j].d;
+        for (int j = 0; j < 12; j++) s += sh.G[j] * sh.dT[tid][j];
         out7[tid] = sh.out[tid] = (float)(s * grad_scale);
     } else if (tid == 6) {
         out7[6] = sh.out[6] = (float)(sh.T[16] * loss_scale);
@@ -236,7 +242,7 @@ __device__ __forceinline__ void ehb_adam_block(EhbAdamShared& sh, float* __restr
                                                float* __restrict__ state, float lr, float beta1, float beta2, float eps, float wd,
                                                float* __restrict__ hist, int hist_cap, const EhbComm& cm, int recv,
                                                const float* __restrict__ K, const float* __restrict__ lp, int n, int H, int W,
-                                               float* __restrict__ mvp_out)
+                                               float* __restrict__ mvp_out, const double* bc = nullptr)
 {
     if (recv) {
         // second half of the fused all-reduce: wait until every rank's message of this step is in the own mailbox, add
@@ -262,7 +268,8 @@ __device__ __forceinline__ void ehb_adam_block(EhbAdamShared& sh, float* __restr
         const int t = (int)state[12] + 1;
         if (hist && t - 1 < hist_cap)
             for (int i = 0; i < 6; i++) hist[(size_t)(t - 1) * 6 + i] = dof[i];
-        const double bc1 = 1.0 - pow((double)beta1, (double)t), bc2 = 1.0 - pow((double)beta2, (double)t);
+        // (bc: the bias corrections of step t, computed by idle threads at the start of the launch)
+        const double bc1 = bc ? bc[0] : 1.0 - pow((double)beta1, (double)t), bc2 = bc ? bc[1] : 1.0 - pow((double)beta2, (double)t);
         for (int i = 0; i < 6; i++) {
             float g = g7[i];
             if (wd != 0.f) g = g + wd * dof[i];
@@ -307,9 +314,14 @@ __global__ void __launch_bounds__(256) ehb_k_pose_adam(const float* dof /* may a
     ehb_pose_pdl_enter();
     __shared__ EhbPoseShared shp;
     __shared__ EhbAdamShared sha;
+    __shared__ double s_bc[2];
+    if (threadIdx.x == 230 || threadIdx.x == 231) {        // Adam's bias corrections need the step count only
+        const int k = threadIdx.x - 230;
+        s_bc[k] = 1.0 - pow((double)(k ? beta2 : beta1), (double)((int)state[12] + 1));
+    }
     ehb_pose_backward_block(shp, dof, K, lp, gmvp, loss, B, L, H, W, grad_scale, loss_scale, out7, cm, exch);
     __syncthreads();                                       // out7 as written by this block; dof read before Adam changes it
-    ehb_adam_block(sha, adam_dof, out7, state, lr, beta1, beta2, eps, wd, hist, hist_cap, cm, exch, K, lp, B * L, H, W, mvp_out);
+    ehb_adam_block(sha, adam_dof, out7, state, lr, beta1, beta2, eps, wd, hist, hist_cap, cm, exch, K, lp, B * L, H, W, mvp_out, s_bc);
 }
 
 __global__ void ehb_k_allreduce7(const EhbComm cm, float* __restrict__ g7)
