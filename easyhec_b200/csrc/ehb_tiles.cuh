@@ -56,7 +56,7 @@ static_assert(EHB_MSZ * 4 >= EHB_T * EHB_T * 4, "the staging tile of the TMA sto
 #endif
 
 #define EHB_TTHREADS 128
-#define EHB_TMIN_BLOCKS 7
+#define EHB_TMIN_BLOCKS 8                // 64 registers: the ~1,100 tiles with links of a 10-view pass are resident at once (+2 % in flight)
 #ifndef EHB_TMB128
 #define EHB_TMB128 1
 #endif
