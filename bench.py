@@ -458,7 +458,7 @@ def run_b200(args):
     # exchanges of a slot (its own mailbox channel) pair up across the ranks.
     S = max(1, min(8, int(os.environ.get("EHB_VALUE_SLOTS", "4"))))
     inflight = S > 1 and (world == 1 or use_peer)
-    G = int(os.environ.get("EHB_VALUE_GRAPH", "64"))   # steps per captured graph (the slots drain at a graph's end)
+    G = int(os.environ.get("EHB_VALUE_GRAPH", "128"))   # steps per captured graph (the slots drain at a graph's end)
     g7s = [torch.zeros(7, dtype=torch.float32, device=dev) for _ in range(S)]
     dof_scr = [dof_dev[0].clone() for _ in range(S)]
     adam_st = [torch.zeros(13, dtype=torch.float32, device=dev) for _ in range(S)]
