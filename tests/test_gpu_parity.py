@@ -82,6 +82,34 @@ def test_fused_views_match_oracle(gpu_ctx, B, H, W, links):
     assert rel_err(g_u8.cpu().numpy(), want["g_mvp"]) < 1e-9
 
 
+def test_explicit_pipelines_give_the_same_result_as_one():
+    """A call of <= 16 items runs as one pipeline by default; ehb_ctx_set_pipelines(n) splits it over n internal streams with
+    their own scratch -- same masks and losses bit for bit, same gradients (the views' atomics never meet)."""
+    from easyhec_b200._lib import Context
+    from easyhec_b200.scenes import perturb_pose
+    B, H, W = 5, 120, 160
+    sc = make_scene(B, H, W, links="xarm7", seed=7)
+    packed = oracle.pack_links(sc["meshes"])
+    ref = oracle.union_binary(packed, scene_mvps(sc, H, W), H, W).astype(np.float32)
+    mvp = scene_mvps(sc, H, W, perturb_pose(sc["Tc_c2b"], np.random.RandomState(2), 0.02, 2.0))
+    want = oracle.render_views(packed, mvp, ref, H, W)
+    out = {}
+    for n in (None, 2, 3, 4):
+        ctx = Context("cuda:0")
+        if n is not None:
+            ctx.set_pipelines(n)
+        ids = [ctx.register_mesh(m.vertices, m.faces) for m in sc["meshes"]]
+        masks, loss, g = ctx.render_views_fused(ids, to_dev(mvp), to_dev(ref), H, W, backward=True)
+        flags, _ = ctx.status()
+        assert flags & 1 == 0
+        out[n] = (masks.cpu().numpy(), loss.cpu().numpy(), g.cpu().numpy())
+        ctx.close()
+    assert np.array_equal(out[None][0], want["masks"])
+    for n in (2, 3, 4):
+        assert np.array_equal(out[n][0], out[None][0]) and np.array_equal(out[n][1], out[None][1])
+        assert rel_err(out[n][2], out[None][2]) < 1e-12
+
+
 def test_fused_more_links_than_resident_planes(gpu_ctx):
     """9 overlapping links in one tile: more than the 8 links of a k_tiles round and more than the 6 mask buffers of a group
     (256-thread variant) -- two rounds, groups of 6 + 2 and 1: the same answer as the oracle's link-by-link sum."""
