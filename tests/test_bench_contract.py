@@ -44,3 +44,44 @@ def test_reference_arm_exits_quietly_on_non_zero_ranks():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "0"], capture_output=True, text=True, env=env, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_timed_regions_repeat_until_every_rank_has_measured_enough():
+    """The K-step region is repeated until MIN_TIMED_MS of device time is measured; with several ranks the decision to stop
+    is collective (agree), or a rank that needs one region more would wait in a barrier the others never enter."""
+    b = _bench()
+
+    class Ev:
+        clock = [0.0]
+
+        def __init__(self, enable_timing=True):
+            self.t = None
+
+        def record(self):
+            self.t = Ev.clock[0]
+
+        def elapsed_time(self, other):
+            return other.t - self.t
+
+    class FakeTorch:
+        class cuda:
+            Event = Ev
+
+    calls = []
+
+    def run(n, k0):
+        calls.append((n, k0))
+        Ev.clock[0] += 2.0 * n          # 2 ms per step
+
+    ms, regions = b.timed_regions(run, 10, lambda: None, FakeTorch, min_ms=50.0)
+    assert regions == [20.0, 20.0, 20.0] and ms == 20.0 and calls == [(10, 0), (10, 10), (10, 20)]
+    # a peer that is not done yet keeps this rank going; the loop ends when both agree
+    votes = []
+
+    def agree(done):
+        votes.append(done)
+        return done and len(votes) >= 5
+
+    calls.clear()
+    ms, regions = b.timed_regions(run, 10, lambda: None, FakeTorch, min_ms=50.0, agree=agree)
+    assert len(regions) == 5 and votes == [False, False, True, True, True]
