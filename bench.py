@@ -14,6 +14,7 @@ See DESIGN.md "Measurement" for the byte accounting.
 """
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -296,6 +297,16 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
+def graph_steps(k, cap, unit):
+    """Steps per captured graph: the largest multiple of `unit` that is <= cap and divides k; without such a divisor the
+    largest multiple of `unit` <= min(cap, k) (at least `unit`)."""
+    best = 0
+    for g in range(unit, min(cap, k) + 1, unit):
+        if k % g == 0:
+            best = g
+    return best or max(unit, min(cap, k) - min(cap, k) % unit)
+
+
 def timed_regions(run, steps, barrier, torch, min_ms=MIN_TIMED_MS, max_repeats=400, agree=None):
     """Times EXACTLY `steps` steps (run(steps, first_step_index)) between two CUDA events, bracketed by barrier +
     synchronize on both sides; the region is repeated until `min_ms` of device time has been measured (a 20-step region
@@ -458,7 +469,9 @@ def run_b200(args):
     # exchanges of a slot (its own mailbox channel) pair up across the ranks.
     S = max(1, min(8, int(os.environ.get("EHB_VALUE_SLOTS", "4"))))
     inflight = S > 1 and (world == 1 or use_peer)
-    G = int(os.environ.get("EHB_VALUE_GRAPH", "128"))   # steps per captured graph (the slots drain at a graph's end)
+    # steps per captured graph (the slots drain at a graph's end): as many as 128, a multiple of the ring and the slots, and
+    # when possible a divisor of K, so that a timed region is graph replays only (a remainder runs as eager launches)
+    G = int(os.environ["EHB_VALUE_GRAPH"]) if os.environ.get("EHB_VALUE_GRAPH") else graph_steps(args.steps, 128, R * S // math.gcd(R, S))
     g7s = [torch.zeros(7, dtype=torch.float32, device=dev) for _ in range(S)]
     dof_scr = [dof_dev[0].clone() for _ in range(S)]
     adam_st = [torch.zeros(13, dtype=torch.float32, device=dev) for _ in range(S)]

@@ -85,3 +85,13 @@ def test_timed_regions_repeat_until_every_rank_has_measured_enough():
     calls.clear()
     ms, regions = b.timed_regions(run, 10, lambda: None, FakeTorch, min_ms=50.0, agree=agree)
     assert len(regions) == 5 and votes == [False, False, True, True, True]
+
+
+def test_graph_steps_divide_the_timed_region_when_they_can():
+    b = _bench()
+    assert b.graph_steps(2000, 128, 4) == 100      # 20 replays, no eager remainder
+    assert b.graph_steps(1024, 128, 4) == 128
+    assert b.graph_steps(20, 128, 4) == 20
+    assert b.graph_steps(50, 128, 4) == 48         # no multiple of 4 divides 50: 48 + 2 eager steps
+    assert b.graph_steps(3, 128, 4) == 4           # (fewer steps than a graph: all of them run eagerly)
+    assert b.graph_steps(200, 128, 4) == 100
