@@ -332,7 +332,8 @@ __device__ __forceinline__ void ehb_stream_empty_tile(const EhbParams& p, int it
 //   (T) table     one warp per depth plane: conservative screen bounding box of the link from the projected corners of its
 //                 (up to 32) object-space chunk AABBs -- 256 point transforms instead of a reduction over all vertices.  The
 //                 last table CTA to finish (atomic ticket) allocates the planes of the pass in the pool by a block-wide
-//                 prefix sum (deterministic); before that it resets the list counters and raises ctr->tableReady.
+//                 prefix sum (deterministic); before that -- as soon as every box is written -- it raises ctr->tableReady
+//                 (the first table CTA has reset the list counters by then).
 //   (V) vertices  one thread per (item, vertex): transform and snap ONCE (a vertex is shared by ~6 triangles), keep the
 //                 clip-space and snapped positions (a few MB, L2-resident)
 //   (B) batches   frustum test of every 32-triangle batch's object-space AABB (8 corners, one per lane): the batches that
